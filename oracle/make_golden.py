@@ -1,0 +1,338 @@
+"""TEST INFRASTRUCTURE ONLY — generates `tests/golden/*.npz` by running the UNMODIFIED reference
+(`/root/reference/src/torchfem`, imported through `oracle/ref_import.py`) in the build container.
+
+    python oracle/make_golden.py            # rewrites tests/golden/
+
+The fixtures are committed; the GPU box (which has no /root/reference) reads only them.
+Everything is float64 / CPU, seeds are fixed, so re-running reproduces the files bit for bit
+(torch 2.11.0, numpy 2.3, scipy 1.18.1).
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_import  # noqa: E402
+
+tf = ref_import.load()
+import torch  # noqa: E402
+from torchfem import Planar, PlanarHeat, Solid, SolidHeat  # noqa: E402
+from torchfem import elements as E  # noqa: E402
+from torchfem import materials as M  # noqa: E402
+from torchfem import mesh  # noqa: E402
+from torchfem.sparse import sparse_solve  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def npy(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+# ---------------------------------------------------------------------------------- element tables
+def element_tables():
+    out = {}
+    g = torch.Generator().manual_seed(1234)
+    for name in ["Tria1", "Tria2", "Quad1", "Quad2", "Tetra1", "Tetra2", "Hexa1", "Hexa2"]:
+        c = getattr(E, name)
+        ip = c.ipoints
+        out[f"{name}.iso_coords"] = npy(c.iso_coords)
+        out[f"{name}.ipoints"] = npy(ip)
+        out[f"{name}.iweights"] = npy(c.iweights)
+        out[f"{name}.B_ip"] = npy(c.B(ip))
+        out[f"{name}.N_ip"] = npy(c.N(ip))
+        out[f"{name}.edges"] = npy(c.edges)
+        out[f"{name}.facets"] = npy(c.facets)
+        xi = torch.rand(5, c.iso_dim, generator=g) * 0.5
+        out[f"{name}.xi"] = npy(xi)
+        out[f"{name}.N_xi"] = npy(c.N(xi))
+        out[f"{name}.B_xi"] = npy(c.B(xi))
+        out[f"{name}.meta"] = np.array([c.nodes, c.iso_dim], dtype=np.int64)
+        out[f"{name}.iso_volume"] = np.array(c.iso_volume)
+    np.savez_compressed(os.path.join(OUT, "element_tables.npz"), **out)
+
+
+# ---------------------------------------------------------------------------------- small meshes
+def distort(nodes, amp, seed):
+    g = torch.Generator().manual_seed(seed)
+    return nodes + amp * (torch.rand(nodes.shape, generator=g) - 0.5)
+
+
+def random_C(n_elem, d, seed):
+    """Random tangent with the minor/major structure of nothing in particular — the kernel must be
+    exact for ANY ddsdde, so no symmetry is assumed."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n_elem, d, d, d, d, generator=g) + 0.1
+
+
+def small_cases():
+    cases = {}
+    n3, e3 = mesh.cube_hexa(4, 3, 3, 1.5, 1.0, 1.0)
+    n3 = distort(n3, 0.08, 1)
+    nt, et = mesh.cube_tetra(3, 3, 3)
+    nt = distort(nt, 0.05, 2)
+    n2, e2 = mesh.rect_quad(5, 4, 2.0, 1.0)
+    n2 = distort(n2, 0.06, 3)
+    ntr, etr = mesh.rect_tri(4, 4)
+    ntr = distort(ntr, 0.05, 4)
+
+    def mech(tag, nodes, elements, planar):
+        n_elem = len(elements)
+        d = nodes.shape[1]
+        if planar:
+            mat = M.IsotropicElasticityPlaneStress(E=1000.0, nu=0.3).vectorize(n_elem)
+        else:
+            mat = M.IsotropicElasticity3D(E=1000.0, nu=0.3).vectorize(n_elem)
+        mat.C = random_C(n_elem, d, 7) * 100.0
+        if planar:
+            g = torch.Generator().manual_seed(9)
+            th = torch.rand(n_elem, generator=g) + 0.5
+            model = Planar(nodes, elements, mat, thickness=th)
+        else:
+            th = None
+            model = Solid(nodes, elements, mat)
+        k = model.k0()
+        con_mask = torch.zeros(model.n_nod, d, dtype=torch.bool)
+        con_mask[nodes[:, 0] < 0.05, :] = True
+        con_mask[-1, 0] = True
+        con = torch.nonzero(con_mask.ravel()).ravel()
+        K = model.assemble_matrix(k, con)
+        cases[tag] = dict(
+            nodes=npy(nodes), elements=npy(elements), C=npy(mat.C), k=npy(k),
+            idx=npy(model.idx), glob_idx=npy(model.glob_idx), k_map=npy(model.k_map),
+            diag_map=npy(model.diag_map), con=npy(con), K_val=npy(K._values()),
+            etype=np.array(model.etype.__name__),
+        )
+        if th is not None:
+            cases[tag]["thickness"] = npy(th)
+
+    def heat(tag, nodes, elements, planar):
+        n_elem = len(elements)
+        d = nodes.shape[1]
+        g = torch.Generator().manual_seed(11)
+        A = torch.rand(n_elem, d, d, generator=g)
+        kappa = A @ A.transpose(-1, -2) + torch.eye(d)
+        if planar:
+            mat = M.IsotropicConductivity2D(kappa=1.0).vectorize(n_elem)
+            mat.KAPPA = kappa
+            th = torch.rand(n_elem, generator=g) + 0.5
+            model = PlanarHeat(nodes, elements, mat, thickness=th)
+        else:
+            mat = M.IsotropicConductivity3D(kappa=1.0).vectorize(n_elem)
+            mat.KAPPA = kappa
+            th = None
+            model = SolidHeat(nodes, elements, mat)
+        k = model.k0()
+        con_mask = torch.zeros(model.n_nod, 1, dtype=torch.bool)
+        con_mask[nodes[:, 0] < 0.05, :] = True
+        con = torch.nonzero(con_mask.ravel()).ravel()
+        K = model.assemble_matrix(k, con)
+        cases[tag] = dict(
+            nodes=npy(nodes), elements=npy(elements), kappa=npy(kappa), k=npy(k),
+            idx=npy(model.idx), glob_idx=npy(model.glob_idx), k_map=npy(model.k_map),
+            diag_map=npy(model.diag_map), con=npy(con), K_val=npy(K._values()),
+            etype=np.array(model.etype.__name__),
+        )
+        if th is not None:
+            cases[tag]["thickness"] = npy(th)
+
+    mech("hexa1", n3, e3, False)
+    mech("hexa2", *E.linear_to_quadratic(n3, e3), False)
+    mech("tetra1", nt, et, False)
+    mech("tetra2", *E.linear_to_quadratic(nt, et), False)
+    mech("quad1", n2, e2, True)
+    mech("quad2", *E.linear_to_quadratic(n2, e2), True)
+    mech("tria1", ntr, etr, True)
+    mech("tria2", *E.linear_to_quadratic(ntr, etr), True)
+    heat("heat_hexa1", n3, e3, False)
+    heat("heat_tetra2", *E.linear_to_quadratic(nt, et), False)
+    heat("heat_quad1", n2, e2, True)
+    heat("heat_quad2", *E.linear_to_quadratic(n2, e2), True)
+
+    # orphan node (not referenced by any element) + element order shuffled: pins the lone-diagonal
+    # rule of base.py:89-91 and that the pattern does not depend on element order
+    n_or = torch.cat([n3, torch.tensor([[5.0, 5.0, 5.0]])])
+    mech("hexa1_orphan", n_or, e3.flip(0), False)
+
+    # per-Gauss-point tangent (hyperelastic, nlgeom): capture ddsdde of Material.step
+    nh, eh = mesh.cube_hexa(3, 3, 3)
+    nh = distort(nh, 0.05, 5)
+
+    def psi(F, params):
+        Cg = F.transpose(-1, -2) @ F
+        logJ = 0.5 * torch.logdet(Cg)
+        return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ**2
+
+    params = torch.tensor([384.6153846153846, 576.9230769230769])
+    box = Solid(nh, eh, M.Hyperelastic3D(psi, params))
+    captured = []
+    orig_step = box.material.step
+
+    def spy(*a, **k):
+        r = orig_step(*a, **k)
+        captured.append(r[2].detach().clone())
+        return r
+
+    box.material.step = spy
+    g = torch.Generator().manual_seed(6)
+    du = 0.05 * (torch.rand(box.n_nod, 3, generator=g) - 0.5)
+    grad = torch.zeros(box.n_int, box.n_elem, 3, 3)
+    grad[:] = torch.eye(3)
+    flux = torch.zeros(box.n_int, box.n_elem, 3, 3)
+    state = torch.zeros(box.n_int, box.n_elem, 0)
+    box.K = torch.empty(0)
+    k, f, *_ = box.integrate_material(
+        torch.zeros(box.n_nod, 3), grad, flux, state, du, torch.zeros(box.n_elem, 3, 3), 0, True)
+    cases["hyper_hexa1"] = dict(
+        nodes=npy(nh), elements=npy(eh), C=npy(torch.stack(captured)), k=npy(k), f=npy(f),
+        du=npy(du), etype=np.array("Hexa1"))
+
+    for tag, d in cases.items():
+        np.savez_compressed(os.path.join(OUT, f"case_{tag}.npz"), **d)
+
+
+# ---------------------------------------------------------------------------------- config A
+def config_a():
+    """BASELINE config[0]: benchmarks/cubes.py with N=11 (SURVEY §8c golden vectors)."""
+    nodes, elements = mesh.cube_hexa(11, 11, 11)
+    cube = Solid(nodes, elements, M.IsotropicElasticity3D(E=1000.0, nu=0.3))
+    cube.forces = torch.zeros_like(nodes, requires_grad=True)
+    cube.constraints[nodes[:, 0] == 0.0, :] = True
+    cube.constraints[nodes[:, 0] == 1.0, 0] = True
+    cube.displacements[nodes[:, 0] == 1.0, 0] = 0.1
+    k = cube.k0()
+    con = torch.nonzero(cube.constraints.ravel()).ravel()
+    K = cube.assemble_matrix(k, con)
+    val = K._values()
+    u, f, sigma, eps, _ = cube.solve(differentiable_parameters=cube.forces, method="spsolve")
+    u.sum().backward()
+    gF = cube.forces.grad.clone()
+    # Jacobi-CG / MINRES through the reference's own sparse_solve CPU code path (Jacobi stand-in)
+    u_cg, *_ = cube.solve(method="cg", stol=1e-10)
+    u_mr, *_ = cube.solve(method="minres", stol=1e-10)
+    # linear system of the first Newton step, for solver-level parity
+    du0 = torch.zeros(cube.n_dofs)
+    du0[con] = cube.displacements.ravel()[con]
+    g = torch.Generator().manual_seed(0)
+    probe = torch.randn(val.shape[0], generator=g)
+    kprobe = torch.randn(k.numel(), generator=g)
+    out = dict(
+        sha_idx=np.array(sha(npy(cube.idx))), sha_glob_idx=np.array(sha(npy(cube.glob_idx))),
+        sha_k_map=np.array(sha(npy(cube.k_map))), sha_diag_map=np.array(sha(npy(cube.diag_map))),
+        nnz=np.array(val.shape[0]), k_fro=npy(torch.linalg.norm(k)), k_000=npy(k[0, 0, :]),
+        k_probe=npy((k.ravel() * kprobe).sum()), k_absmax=npy(k.abs().max()),
+        k_e0=npy(k[0]), k_e777=npy(k[777]),
+        val_norm=npy(torch.linalg.norm(val)), val_sum=npy(val.sum()),
+        val_probe=npy((val * probe).sum()), val_absmax=npy(val.abs().max()),
+        val_n_zero=np.array(int((val == 0).sum())), val_n_one=np.array(int((val == 1).sum())),
+        val_head=npy(val[:4096]), con=npy(con),
+        u=npy(u), f=npy(f), sigma=npy(sigma), eps=npy(eps), grad_forces=npy(gF),
+        u_cg=npy(u_cg), u_minres=npy(u_mr),
+    )
+    np.savez_compressed(os.path.join(OUT, "config_a.npz"), **out)
+    print("config A: nnz", val.shape[0], "sha glob_idx", out["sha_glob_idx"], "k_map", out["sha_k_map"])
+
+
+# ---------------------------------------------------------------------------------- gradients
+def topopt_small():
+    """benchmarks/topopt.py at N=3 (6x3x3 elements): compliance and its density gradient."""
+    N = 3
+    nx, ny, nz = 2 * N, N, N
+    nodes, elements = mesh.cube_hexa(nx + 1, ny + 1, nz + 1, 2.0, 1.0, 1.0)
+    rng = np.random.default_rng(0)
+    values = np.clip(0.5 + 0.3 * rng.standard_normal(len(elements)), 0.05, 0.95)
+    rho = torch.tensor(values, requires_grad=True)
+    material = M.IsotropicElasticity3D(E=70000.0, nu=0.3).vectorize(len(elements))
+    scale = 1e-3 + (1.0 - 1e-3) * rho**3.0
+    material.C = scale[:, None, None, None, None] * material.C
+    model = Solid(nodes, elements, material)
+    model.constraints[nodes[:, 0] == 0.0, :] = True
+    right = nodes[:, 0] == 2.0
+    wy = torch.full((model.n_nod,), 1.0 / ny)
+    wy[(nodes[:, 1] == 0.0) | (nodes[:, 1] == 1.0)] /= 2.0
+    wz = torch.full((model.n_nod,), 1.0 / nz)
+    wz[(nodes[:, 2] == 0.0) | (nodes[:, 2] == 1.0)] /= 2.0
+    model.forces[right, 2] = -1.0 * wy[right] * wz[right]
+    u, *_ = model.solve(differentiable_parameters=rho, method="spsolve")
+    c = torch.inner(model.forces.ravel(), u.ravel())
+    c.backward()
+    np.savez_compressed(os.path.join(OUT, "topopt_n3.npz"), rho=values, u=npy(u),
+                        compliance=npy(c), grad_rho=npy(rho.grad), forces=npy(model.forces))
+
+
+def hyper_small():
+    """benchmarks/hyperelasticity.py at N=3 with 3 increments: reaction force and d/d(mu,lambda)."""
+    import math
+
+    En, NU = 1000.0, 0.3
+    LBD = En * NU / ((1.0 + NU) * (1.0 - 2.0 * NU))
+    MU = En / (2.0 * (1.0 + NU))
+
+    def psi(F, params):
+        Cg = F.transpose(-1, -2) @ F
+        logJ = 0.5 * torch.logdet(Cg)
+        return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ**2
+
+    N = 3
+    lx = 4.0 / (N - 1)
+    nodes, elements = mesh.cube_hexa(5, N, N, lx, 1.0, 1.0)
+    params = torch.tensor([MU, LBD], requires_grad=True)
+    box = Solid(nodes, elements, M.Hyperelastic3D(psi, params))
+    left = nodes[:, 0] == 0.0
+    right = nodes[:, 0] == lx
+    box.constraints[left, 0] = True
+    box.constraints[right, 0] = True
+    box.constraints[nodes[:, 1] == 0.5, 1] = True
+    box.constraints[nodes[:, 2] == 0.5, 2] = True
+    STRETCH = 2.0
+    box.displacements[right, 0] = (STRETCH - 1.0) * lx
+    lam = torch.logspace(0, math.log10(STRETCH), 4)
+    increments = (lam - 1.0) / (STRETCH - 1.0)
+    u, f, *_ = box.solve(increments=increments, nlgeom=True, differentiable_parameters=params,
+                         method="spsolve")
+    reaction = f[right, 0].sum()
+    reaction.backward()
+    np.savez_compressed(os.path.join(OUT, "hyper_n3.npz"), u=npy(u), f=npy(f),
+                        reaction=npy(reaction), grad_params=npy(params.grad),
+                        increments=npy(increments))
+
+
+def sparse_small():
+    """tests/test_sparse.py-style systems: SPD and non-symmetric 6x6 COO with dense solutions."""
+    g = torch.Generator().manual_seed(42)
+    Ad = torch.rand(6, 6, generator=g)
+    spd = Ad @ Ad.T + 6 * torch.eye(6)
+    nonsym = torch.rand(6, 6, generator=g) + 6 * torch.eye(6)
+    b = torch.rand(6, generator=g)
+    out = {}
+    for tag, Am in [("spd", spd), ("nonsym", nonsym)]:
+        A = Am.to_sparse_coo().detach().requires_grad_(True)
+        bb = b.clone().requires_grad_(True)
+        x = tf.sparse.differentiable_sparse_solve(A, bb, method="spsolve")
+        x.sum().backward()
+        out[f"{tag}.A"] = npy(Am)
+        out[f"{tag}.x"] = npy(x)
+        out[f"{tag}.gb"] = npy(bb.grad)
+        out[f"{tag}.gA_idx"] = npy(A.grad.coalesce().indices())
+        out[f"{tag}.gA_val"] = npy(A.grad.coalesce().values())
+    out["b"] = npy(b)
+    np.savez_compressed(os.path.join(OUT, "sparse_small.npz"), **out)
+
+
+if __name__ == "__main__":
+    element_tables()
+    small_cases()
+    config_a()
+    topopt_small()
+    hyper_small()
+    sparse_small()
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)))
