@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — DOFs solved/sec (integrate + assemble + Jacobi-PCG to 1e-8) on the linear-elastic Hexa1 cube.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--edge E]
+
+One "step" = one pass of the hot path over the synthetic cube-extension problem of the reference's
+benchmarks/cubes.py (cube_hexa(E+1,E+1,E+1), E=1000, nu=0.3, x=0 clamped, u_x=0.1 at x=1):
+element matrices (K1) -> deterministic assembly with Dirichlet masking (K2/K3) -> right-hand side ->
+Jacobi setup (K4) -> PCG to ||r|| <= 1e-8 ||b|| (K5/K6). The sparsity pattern (K0) is setup and is reported
+separately, as the reference does (benchmarks/run.py:56-58: "setup" vs "fwd").
+
+N=1 runs BASELINE.json configs[1]: 150^3 elements, 10,328,853 DOFs, nnz 825,604,659 (matrix 10.1 GB >> L2).
+`--impl reference` times the CPU oracle port of the same path (oracle/fem_oracle.py) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DOFs solved/sec (assembly+PCG)"
+UNIT = "DOF/s"
+RTOL = 1e-8
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU baseline: the oracle port of the reference path (numpy einsum + scipy-style Jacobi-CG), all
+    host threads numpy/BLAS will use, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import fem_oracle as O
+
+    E = args.cpu_edge
+    N = E + 1
+    nodes, elements = O.cube_hexa(N, N, N)
+    bref, w = O.hexa1_tables()
+    C = O.isotropic_C3d(1000.0, 0.3, len(elements))
+    con_mask, disp = O.cube_extension_bcs(nodes)
+    n_dofs = nodes.size
+    times = []
+    its = 0
+    for s in range(args.warmup + args.steps):
+        out = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=RTOL)
+        t = out["t_integrate"] + out["t_assemble"] + out["t_rhs"] + out["t_solve"]
+        its = out["iterations"]
+        if s >= args.warmup:
+            times.append(t)
+    ms = 1e3 * float(np.mean(times))
+    value = n_dofs / (ms / 1e3)
+    cores = os.cpu_count()
+    sample = (f"cube_hexa({N},{N},{N}) = {E}^3 Hexa1 elements, {n_dofs} DOFs, {its} Jacobi-CG iterations to "
+              f"1e-8; oracle port (numpy einsum integrate, bincount assemble, scipy-CSR SpMV CG); "
+              f"os.cpu_count()={cores}, CG SpMV is single-threaded as in scipy")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"linear-elastic Hexa1 cube {E}^3 elements (bounded CPU sample of configs[1])",
+                   "n_dofs": int(n_dofs), "rtol": RTOL, "cg_iterations": int(its)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def build_problem(T, torch, E, device):
+    """Synthetic inputs exactly as the reference generators make them (mesh.py:8-46, cubes.py:9-24),
+    built with torch on the host, then moved to the device."""
+    N = E + 1
+    X = torch.linspace(0, 1.0, N, dtype=torch.float64)
+    x, y, z = torch.meshgrid(X, X, X, indexing="ij")
+    nodes = torch.stack([x.ravel(), y.ravel(), z.ravel()], dim=1).contiguous()
+    ind = torch.arange(N * N * N, dtype=torch.int64).reshape(N, N, N)
+    n0 = ind[:-1, :-1, :-1].ravel()
+    n1 = ind[1:, :-1, :-1].ravel()
+    n2 = ind[:-1, 1:, :-1].ravel()
+    n3 = ind[1:, 1:, :-1].ravel()
+    n4 = ind[:-1, :-1, 1:].ravel()
+    n5 = ind[1:, :-1, 1:].ravel()
+    n6 = ind[:-1, 1:, 1:].ravel()
+    n7 = ind[1:, 1:, 1:].ravel()
+    elements = torch.stack([n0, n1, n3, n2, n4, n5, n7, n6], dim=1).contiguous()
+    con = torch.zeros(N * N * N, 3, dtype=torch.bool)
+    disp = torch.zeros(N * N * N, 3, dtype=torch.float64)
+    con[nodes[:, 0] == 0.0, :] = True
+    con[nodes[:, 0] == 1.0, 0] = True
+    disp[nodes[:, 0] == 1.0, 0] = 0.1
+    return nodes, elements, con, disp
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    torch.set_default_dtype(torch.float64)
+    import torchfem_b200 as T
+    from torchfem_b200 import csr
+    from oracle import fem_oracle as O  # tables only (bref/w are 200 numbers) + cpu_baseline leg
+
+    if world > 1:
+        from torchfem_b200 import distributed as D
+        return D.bench_multi_gpu(args, METRIC, UNIT, RTOL)
+
+    E = args.edge
+    t0 = time.perf_counter()
+    nodes_h, elements_h, con_h, disp_h = build_problem(T, torch, E, device)
+    n_elem = elements_h.shape[0]
+    n_dofs = nodes_h.numel()
+    bref_np, w_np = O.hexa1_tables()
+    bref, w = torch.as_tensor(bref_np), torch.as_tensor(w_np)
+    C1 = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1))
+    C_h = C1.expand(n_elem, 3, 3, 3, 3).contiguous()  # vectorised material, as Material.vectorize does
+    host = [nodes_h, elements_h, C_h, con_h.ravel().to(torch.uint8), disp_h.ravel().contiguous()]
+    host = [t.pin_memory() for t in host]
+    nodes_h, elements_h, C_h, iscon_h, disp_h = host
+    t_gen = time.perf_counter() - t0
+
+    # ---- setup (pattern), timed separately
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    elements = elements_h.to(device, non_blocking=True)
+    ev0.record()
+    pattern = csr.Pattern(elements, nodes_h.shape[0], 3)
+    ev1.record()
+    torch.cuda.synchronize()
+    t_setup_ms = ev0.elapsed_time(ev1)
+    nnz = pattern.nnz
+
+    nodes = nodes_h.to(device)
+    C = C_h.to(device)
+    is_con = iscon_h.to(device)
+    disp = disp_h.to(device)
+    vals = torch.empty(nnz, dtype=torch.float64, device=device)
+    vals_free = torch.empty(nnz, dtype=torch.float64, device=device)
+    state = {}
+
+    def hot_path(nodes, elements, C, is_con, disp):
+        """integrate -> assemble (constrained for the solve, unconstrained for the Dirichlet rhs) -> PCG."""
+        k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
+        csr.assemble(pattern, k, is_con, out=vals)
+        csr.assemble(pattern, k, None, out=vals_free)
+        del k
+        A_free = csr.CSRMatrix(pattern.indptr, pattern.indices, vals_free, n_dofs,
+                               chunk_rows=pattern.chunk_rows, diag_pos=pattern.diag_pos, symmetric=True)
+        A = csr.CSRMatrix(pattern.indptr, pattern.indices, vals, n_dofs, chunk_rows=pattern.chunk_rows,
+                          diag_pos=pattern.diag_pos, symmetric=True)
+        # residual of the first Newton step: F_int(du_bc) with du_bc = prescribed increment (base.py:708-741)
+        rhs = A_free.matvec(disp * is_con)
+        rhs.masked_fill_(is_con.bool(), 0.0)
+        x, M, info = csr.krylov_solve(A, rhs, method="cg", rtol=RTOL)
+        u = torch.where(is_con.bool(), disp, -x)
+        state.update(info=info, A=A, rhs=rhs, x=x)
+        return u
+
+    def step_resident():
+        return hot_path(nodes, elements, C, is_con, disp)
+
+    def step_e2e():
+        d = [t.to(device, non_blocking=True) for t in (nodes_h, elements_h, C_h, iscon_h, disp_h)]
+        u = hot_path(*d)
+        return u.cpu()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps, out
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, u = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    info = dict(state["info"])
+    value = n_dofs / (ms / 1e3)
+
+    ms_e2e, u_h = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+    h2d = sum(t.numel() * t.element_size() for t in (nodes_h, elements_h, C_h, iscon_h, disp_h))
+    d2h = u_h.numel() * u_h.element_size()
+
+    # ---- true relative residual of the last solve (checks the work was done)
+    A, rhs, x = state["A"], state["rhs"], state["x"]
+    true_res = float(torch.linalg.norm(rhs - A.matvec(x)) / torch.linalg.norm(rhs))
+
+    # ---- per-phase times + dominant kernel (SpMV) measured live with CUDA events
+    def ev_time(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    xs = torch.randn(n_dofs, dtype=torch.float64, device=device,
+                     generator=torch.Generator(device=device).manual_seed(0))
+    ys = torch.empty_like(xs)
+    spmv_ms = ev_time(lambda: A.matvec(xs, out=ys), 20)
+    spmv_bytes = 12 * nnz + 20 * n_dofs
+    peak, peak_src = measured_peaks()
+    achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    k_ms = ev_time(lambda: csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False), 3)
+    kk = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
+    asm_ms = ev_time(lambda: csr.assemble(pattern, kk, is_con, out=vals), 3)
+    del kk
+    t_s = time.perf_counter()
+    x2, _, info2 = csr.krylov_solve(A, rhs, method="cg", rtol=RTOL)
+    torch.cuda.synchronize()
+    solve_ms = 1e3 * (time.perf_counter() - t_s)
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N=1 only
+    cpu = None
+    if not args.no_cpu_baseline:
+        Ec = args.cpu_edge
+        Nc = Ec + 1
+        nd_c, el_c = O.cube_hexa(Nc, Nc, Nc)
+        Cc = O.isotropic_C3d(1000.0, 0.3, len(el_c))
+        cm, dp = O.cube_extension_bcs(nd_c)
+        out = O.linear_solve_reference_flow(nd_c, el_c, bref_np, w_np, Cc, cm, dp, rtol=RTOL)
+        t_cpu = out["t_integrate"] + out["t_assemble"] + out["t_rhs"] + out["t_solve"]
+        cpu = {"value": nd_c.size / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": (f"{Ec}^3 Hexa1 elements, {nd_c.size} DOFs, {out['iterations']} CG its to 1e-8: "
+                          f"setup {out['t_setup']:.2f}s (excluded) integrate {out['t_integrate']:.2f}s "
+                          f"assemble {out['t_assemble']:.2f}s solve {out['t_solve']:.2f}s; numpy/scipy oracle "
+                          f"port of the reference CPU path, scipy-CSR SpMV single-threaded")}
+
+    launches = info["launches"] + 2 + 2 + 1 + 1  # integrate, 2x assemble, rhs spmv, jacobi
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"linear-elastic Hexa1 cube {E}^3 elements, Jacobi-PCG to 1e-8 (BASELINE configs[1])"
+                   if E == 150 else f"linear-elastic Hexa1 cube {E}^3 elements, Jacobi-PCG to 1e-8",
+                   "n_dofs": int(n_dofs), "n_elem": int(n_elem), "nnz": int(nnz), "rtol": RTOL,
+                   "cg_iterations": info["iterations"], "true_rel_residual": true_res,
+                   "l2_policy": "inputs larger than L2 (CSR matrix 10.1 GB, k_e 15.6 GB vs 126 MB L2)",
+                   "setup_ms_pattern": t_setup_ms, "phases_ms": {"integrate_k": k_ms, "assemble": asm_ms,
+                                                                 "pcg_solve": solve_ms,
+                                                                 "per_cg_iteration": solve_ms / max(1, info2["iterations"])}},
+        "e2e": {"value": n_dofs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_spmv<16> (CSR SpMV, fp64 vals + int32 cols)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "frac_of_spec_8000": achieved / 8000.0,
+                     "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms, "traffic": None},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--edge", type=int, default=150, help="elements per cube edge (150 = BASELINE configs[1])")
+    ap.add_argument("--cpu-edge", type=int, default=40, help="elements per edge of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+/*
+ * tfem_b200.h — C ABI of libtfem_b200.so: the B200 (sm_100a) kernels behind torch-fem's implicit-solve
+ * hot path (element stiffness integration -> sparse assembly -> Jacobi-preconditioned Krylov solve).
+ *
+ * Conventions (modelled on the reference's only native boundary, the AmgX ctypes binding,
+ * /root/reference/src/torchfem/amgx.py:148-208):
+ *   - every entry point returns `int rc` (0 = TFEM_OK); `tfem_get_error_string(rc, buf, len)` describes it
+ *     (amgx.py:195-201 `_check` / `AMGX_get_error_string`);
+ *   - plain pointers and sizes only; "dev" pointers are device memory owned by the caller (torch tensors,
+ *     `tensor.data_ptr()`), borrowed for the duration of the call; "host" pointers are host memory;
+ *   - every call is stream-ordered on the `stream` argument (a `cudaStream_t` passed as void*; the Python
+ *     side passes `torch.cuda.current_stream().cuda_stream`); no hidden synchronisation unless stated;
+ *   - no global state besides a once-initialised attribute cache; float64 values, int32/int64 indices.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to /root/reference).
+ */
+#ifndef TFEM_B200_H
+#define TFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFEM_OK 0
+#define TFEM_ERR_INVALID 1      /* bad argument (null pointer, unsupported element, misaligned buffer) */
+#define TFEM_ERR_CUDA 2         /* a CUDA runtime call or kernel launch failed; see error string */
+#define TFEM_ERR_CAPACITY 3     /* a documented static limit was exceeded (node valence, index width) */
+#define TFEM_ERR_NOT_CONVERGED 4/* Krylov solver hit maxiter (reference: RuntimeError "CG failed ...") */
+#define TFEM_ERR_BREAKDOWN 5    /* Krylov breakdown (non-finite or non-positive curvature) */
+#define TFEM_ERR_NCCL 6
+
+#define TFEM_KIND_MECH 0        /* vector field, tangent [.., d,d,d,d]  (base.py:1086-1090) */
+#define TFEM_KIND_HEAT 1        /* scalar field, tangent [.., d,d]      (base.py:1272-1278) */
+
+#define TFEM_METHOD_CG 0        /* sparse.py:414-421 (cupy_cg + Jacobi) */
+#define TFEM_METHOD_MINRES 1    /* sparse.py:406-413 (cupy_minres + Jacobi) */
+
+/* Library version (major*10000 + minor*100 + patch). */
+int tfem_version(void);
+
+/* Human-readable text for `rc`; for TFEM_ERR_CUDA/NCCL includes the last runtime error of this thread.
+ * Mirrors AMGX_get_error_string (amgx.py:195-201). */
+int tfem_get_error_string(int rc, char* buf, int len);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K0 — sparsity pattern.  Replaces the packed-key sort/unique/searchsorted of FEM.__init__
+ * (src/torchfem/base.py:78-118) with a node-graph build: node->element incidence, per-node sorted
+ * unique neighbour list, expanded to dpn x dpn blocks. The result is bit-identical to the reference's
+ * `glob_idx` (as CSR), `k_map` and `diag_map`, including the lone diagonal entry of nodes that no
+ * element references (base.py:89-91).
+ *
+ * Phase 1 sizes the pattern, phase 2 fills caller-allocated arrays.
+ * ------------------------------------------------------------------------------------------------- */
+
+/* elements_dev: int64 [n_elem*nn] (the reference's connectivity dtype).
+ * inc_ptr_dev : int32 [n_nod+1]   out: CSR offsets of the node->element-slot incidence
+ * inc_list_dev: int32 [n_elem*nn] out: for every node the slots (e*nn + a) that reference it, ascending
+ * blk_cnt_dev : int32 [n_nod]     out: number of distinct neighbour nodes (0 for an unreferenced node)
+ * totals_dev  : int64 [4]         out: {nnzb (node blocks), nnz (scalar entries for dpn), max blk_cnt,
+ *                                       max incident slots}
+ * Fails with TFEM_ERR_CAPACITY if a node has more than 2048/nn incident elements or n_elem*nn*nn >= 2^31. */
+int tfem_pattern_phase1(int64_t n_nod, int64_t n_elem, int nn, int dpn, const int64_t* elements_dev,
+                        int32_t* inc_ptr_dev, int32_t* inc_list_dev, int32_t* blk_cnt_dev,
+                        int64_t* totals_dev, void* stream);
+
+/* node_ptr_dev: int64 [n_nod+1] out: block-CSR offsets (exclusive scan of blk_cnt)
+ * adj_dev     : int32 [nnzb]    out: neighbour node ids, ascending per node
+ * indptr_dev  : int64 [n_dofs+1] out: scalar CSR row offsets (== bincount/cumsum of glob_idx[0], sparse.py:389-390)
+ * indices_dev : int32 [nnz]     out: scalar CSR column indices (== glob_idx[1])
+ * diag_map_dev: int32 [n_dofs]  out: position of (i,i) (base.py:106-108)
+ * src_ptr_dev : int64 [nnzb+1]  out: offsets into src of the element contributions of every node block
+ * src_dev     : int32 [n_elem*nn*nn] out: contributions e*nn*nn + a*nn + b, ascending per block — the
+ *               element-slot -> CSR permutation of the deterministic assembly (replaces k_map in K2) */
+int tfem_pattern_phase2(int64_t n_nod, int64_t n_elem, int nn, int dpn, const int64_t* elements_dev,
+                        const int32_t* inc_ptr_dev, const int32_t* inc_list_dev,
+                        const int32_t* blk_cnt_dev, int64_t* node_ptr_dev, int32_t* adj_dev,
+                        int64_t* indptr_dev, int32_t* indices_dev, int32_t* diag_map_dev,
+                        int64_t* src_ptr_dev, int32_t* src_dev, void* stream);
+
+/* Reference-compatible `k_map` (int32 [n_elem*(nn*dpn)^2], base.py:94-104): CSR position of every element
+ * slot in k.ravel() order. Only needed for API compatibility; the assembly kernel uses `src`. */
+int tfem_pattern_k_map(int64_t n_nod, int64_t n_elem, int nn, int dpn, const int64_t* elements_dev,
+                       const int64_t* node_ptr_dev, const int32_t* adj_dev, const int64_t* indptr_dev,
+                       int32_t* k_map_dev, void* stream);
+
+/* Reference-compatible `glob_idx` rows (int64 [nnz]) from indptr (base.py:110-118). */
+int tfem_pattern_coo_rows(int64_t n_dofs, const int64_t* indptr_dev, int64_t* rows_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K1 — element matrices.  Replaces eval_shape_functions (base.py:293-314) + the Gauss-point loop's
+ * stiffness branch (base.py:1086-1090 mechanics, :1272-1278 heat) + compute_k (solid.py:52-54,
+ * planar.py:86-88).
+ *   k_e[(p,i),(r,k)] = sum_q w_q detJ_q s_e sum_{J,L} B_q[J,p] C[i,J,k,L] B_q[L,r]     (MECH)
+ *   k_e[p,r]         = sum_q w_q detJ_q s_e sum_{i,j} kappa[i,j] B_q[i,p] B_q[j,r]     (HEAT)
+ * bref_host  : double [n_int*dim*nn]  reference-space gradients etype.B(ipoints) (host memory)
+ * w_host     : double [n_int]         etype.iweights (host memory)
+ * nodes_dev  : double [n_nod*dim];  elements_dev: int64 [n_elem*nn]
+ * tangent_dev: double [(n_int if tangent_per_gp else 1), n_elem, dim^4 | dim^2]
+ * scale_dev  : double [n_elem] (planar thickness) or NULL
+ * k_dev      : double [n_elem*(nn*dpn)^2] out, row-major, local DOF order node-major / dof-minor
+ * neg_jac_dev: int32 [1] in/out: set to 1 if any detJ <= 0 (caller raises the reference's
+ *              ValueError("Negative Jacobian. Check element numbering."), base.py:311-312)
+ * Supported (dim,nn,n_int): (3,8,8) Hexa1, (3,20,8) Hexa2, (3,4,1) Tetra1, (3,10,4) Tetra2,
+ *                           (2,4,4) Quad1, (2,8,4) Quad2, (2,3,1) Tria1, (2,6,3) Tria2. */
+int tfem_integrate_k(int kind, int dim, int nn, int n_int, const double* bref_host,
+                     const double* w_host, const double* nodes_dev, const int64_t* elements_dev,
+                     int64_t n_elem, const double* tangent_dev, int tangent_per_gp,
+                     const double* scale_dev, double* k_dev, int32_t* neg_jac_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K2/K3 — deterministic assembly.  Replaces FEM.assemble_matrix (base.py:398-426): index_add_ scatter
+ * (atomics on CUDA) becomes a gather over the precomputed `src` permutation with a fixed summation
+ * order (element order), fused with the Dirichlet masking (rows/cols of constrained DOFs zeroed, unit
+ * diagonal, base.py:414-419).
+ * is_con_dev: uint8 [n_dofs] (1 = constrained) or NULL for no constraints (assembly.py:19,509 EMPTY)
+ * vals_dev  : double [nnz] out, in the CSR order of tfem_pattern_phase2 (== reference COO order) */
+int tfem_assemble(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr_dev, const int32_t* adj_dev,
+                  const int64_t* indptr_dev, const int64_t* src_ptr_dev, const int32_t* src_dev,
+                  const double* k_dev, const uint8_t* is_con_dev, double* vals_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K5 — CSR SpMV y = A x (fp64 values, int32 columns, int64 row offsets).  Replaces cusparseSpMV inside
+ * cupy_cg / cupy_minres (sparse.py:411,419). Algorithmic bytes: 12*nnz + 20*n_rows.
+ *
+ * The plan splits the nonzero stream into chunks of TFEM_SPMV_CHUNK entries; chunk c owns the rows whose
+ * first entry lies in [c*CHUNK, (c+1)*CHUNK).
+ * chunk_rows_dev: int32 [n_chunks+1] out, n_chunks = tfem_spmv_num_chunks(nnz). */
+#define TFEM_SPMV_CHUNK 512
+int64_t tfem_spmv_num_chunks(int64_t nnz);
+int tfem_spmv_plan(int64_t n_rows, int64_t nnz, const int64_t* indptr_dev, int32_t* chunk_rows_dev,
+                   void* stream);
+int tfem_spmv(int64_t n_rows, int64_t nnz, const int64_t* indptr_dev, const int32_t* indices_dev,
+              const double* vals_dev, const int32_t* chunk_rows_dev, const double* x_dev,
+              double* y_dev, void* stream);
+
+/* y = A^T x for a general (non-symmetric) CSR matrix — the adjoint of `Solve` with non-symmetric A
+ * (sparse.py:203; tests/test_sparse.py:94-158). Deterministic: builds on a transposed copy made by the
+ * caller with tfem_csr_transpose. */
+int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr_dev,
+                       const int32_t* indices_dev, const double* vals_dev, int64_t* t_indptr_dev,
+                       int32_t* t_indices_dev, double* t_vals_dev, void* stream);
+
+/* K4 — Jacobi preconditioner: dinv[i] = 1 / vals[diag_pos[i]]  (sparse.py:408-409 `diags(1/A.diagonal())`).
+ * diag_pos_dev: int64 [n] position of the diagonal entry of every row, or -1 (then dinv = inf like 1/0). */
+int tfem_csr_diag_positions(int64_t n_rows, const int64_t* indptr_dev, const int32_t* indices_dev,
+                            int64_t* diag_pos_dev, void* stream);
+int tfem_jacobi_setup(int64_t n_rows, const double* vals_dev, const int64_t* diag_pos_dev,
+                      double* dinv_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K5+K6 — Jacobi-preconditioned Krylov solve on one GPU.  Replaces cupy_cg / cupy_minres + the
+ * per-iteration host synchronisation of the reference GPU path (sparse.py:406-421).
+ * CG follows scipy/cupy `cg`: stop when ||r||_2 < max(atol, rtol*||b||_2), tested before every
+ * iteration; maxiter <= 0 means 10*n. MINRES follows Paige-Saunders as in scipy `minres` (test1/test2),
+ * maxiter <= 0 means 5*n.
+ * Per iteration: SpMV fused with the p.q dot; one fused axpy/axpy/precondition/dot kernel; one direction
+ * update. All reductions are fixed-order (deterministic); convergence is tested on the device and the
+ * host polls a flag every `check_every` iterations (<=0: default 32).
+ * x0_dev may be NULL (zero initial guess). work_dev: double [tfem_krylov_work_doubles(n)] scratch.
+ * info_host: double [8] out (host): {iterations, final ||r||_2, ||b||_2, converged(1/0), spmv count,
+ *            kernel launches, reserved, reserved}.
+ * Returns TFEM_ERR_NOT_CONVERGED at maxiter (x still holds the last iterate). */
+int64_t tfem_krylov_work_doubles(int64_t n_rows);
+int tfem_krylov_solve(int method, int64_t n_rows, int64_t nnz, const int64_t* indptr_dev,
+                      const int32_t* indices_dev, const double* vals_dev,
+                      const int32_t* chunk_rows_dev, const double* dinv_dev, const double* b_dev,
+                      const double* x0_dev, double rtol, double atol, int64_t maxiter,
+                      int check_every, double* x_dev, double* work_dev, double* info_host,
+                      void* stream);
+
+/* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
+ * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */
+int tfem_adjoint_matrix_grad(int64_t n_rows, const int64_t* indptr_dev, const int32_t* indices_dev,
+                             const double* lambda_dev, const double* x_dev, double* g_dev,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFEM_B200_H */

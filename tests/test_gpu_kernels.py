@@ -1,0 +1,282 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI (torchfem_b200.csr -> libtfem_b200.so),
+against the CPU oracle and the fixtures generated from the unmodified reference.
+
+Bars (BASELINE.json): integer CSR structure bit-exact; element matrices and assembled K <= 1e-12
+relative (max|d| / max|ref| per tensor); displacements <= 1e-8 relative at equal tolerance.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import HEAT_CASES, MECH_CASES, load_case
+from oracle import fem_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_K = 1e-12
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torchfem_b200 as T
+
+    assert torch.cuda.is_available()
+    return T
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a), device="cuda")
+    return t.to(dtype) if dtype is not None else t
+
+
+def build_pattern(T, c, dpn):
+    return T.csr.Pattern(dev(c["elements"]), c["nodes"].shape[0], dpn)
+
+
+@pytest.mark.parametrize("tag", MECH_CASES + HEAT_CASES)
+def test_pattern_bit_exact(T, tag):
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    p = build_pattern(T, c, dpn)
+    assert p.nnz == c["glob_idx"].shape[1]
+    g = p.glob_idx.cpu().numpy()
+    assert g.dtype == np.int64 and np.array_equal(g, c["glob_idx"])
+    km = p.k_map.cpu().numpy()
+    assert km.dtype == np.int32 and np.array_equal(km, c["k_map"])
+    dm = p.diag_map.cpu().numpy()
+    assert dm.dtype == np.int32 and np.array_equal(dm, c["diag_map"])
+    indptr, indices = O.csr_from_glob_idx(c["glob_idx"], dpn * c["nodes"].shape[0])
+    assert np.array_equal(p.indptr.cpu().numpy(), indptr)
+    assert np.array_equal(p.indices.cpu().numpy(), indices)
+
+
+@pytest.mark.parametrize("tag", MECH_CASES)
+def test_integrate_k_mech(T, tag, tables):
+    c = load_case(f"case_{tag}.npz")
+    et = str(c["etype"])
+    th = dev(c["thickness"]) if "thickness" in c else None
+    k = T.csr.integrate_k(T._lib.KIND_MECH, torch.as_tensor(tables[f"{et}.B_ip"]),
+                          torch.as_tensor(tables[f"{et}.iweights"]), dev(c["nodes"]),
+                          dev(c["elements"]), dev(c["C"]), th)
+    assert rel(k.cpu().numpy(), c["k"]) <= TOL_K
+
+
+@pytest.mark.parametrize("tag", HEAT_CASES)
+def test_integrate_k_heat(T, tag, tables):
+    c = load_case(f"case_{tag}.npz")
+    et = str(c["etype"])
+    th = dev(c["thickness"]) if "thickness" in c else None
+    k = T.csr.integrate_k(T._lib.KIND_HEAT, torch.as_tensor(tables[f"{et}.B_ip"]),
+                          torch.as_tensor(tables[f"{et}.iweights"]), dev(c["nodes"]),
+                          dev(c["elements"]), dev(c["kappa"]), th)
+    assert rel(k.cpu().numpy(), c["k"]) <= TOL_K
+
+
+def test_integrate_k_per_gauss_point_tangent(T, tables):
+    c = load_case("case_hyper_hexa1.npz")
+    k = T.csr.integrate_k(T._lib.KIND_MECH, torch.as_tensor(tables["Hexa1.B_ip"]),
+                          torch.as_tensor(tables["Hexa1.iweights"]), dev(c["nodes"]),
+                          dev(c["elements"]), dev(c["C"]))
+    assert rel(k.cpu().numpy(), c["k"]) <= TOL_K
+
+
+def test_negative_jacobian_raises(T, tables):
+    c = load_case("case_hexa1.npz")
+    el = c["elements"].copy()
+    el[3] = el[3][[1, 0, 3, 2, 5, 4, 7, 6]]
+    with pytest.raises(ValueError, match="Negative Jacobian. Check element numbering."):
+        T.csr.integrate_k(T._lib.KIND_MECH, torch.as_tensor(tables["Hexa1.B_ip"]),
+                          torch.as_tensor(tables["Hexa1.iweights"]), dev(c["nodes"]), dev(el),
+                          dev(c["C"]))
+
+
+@pytest.mark.parametrize("tag", MECH_CASES + HEAT_CASES)
+def test_assemble(T, tag):
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    n_dofs = dpn * c["nodes"].shape[0]
+    p = build_pattern(T, c, dpn)
+    is_con = np.zeros(n_dofs, dtype=np.uint8)
+    is_con[c["con"]] = 1
+    vals = T.csr.assemble(p, dev(c["k"]), dev(is_con))
+    v = vals.cpu().numpy()
+    assert rel(v, c["K_val"]) <= TOL_K
+    assert np.array_equal(v == 1.0, c["K_val"] == 1.0)
+    masked = (is_con[c["glob_idx"][0]] | is_con[c["glob_idx"][1]]).astype(bool)
+    assert np.all((v[masked] == 0.0) | (v[masked] == 1.0))
+    # bitwise run-to-run determinism (no FP atomics)
+    v2 = T.csr.assemble(p, dev(c["k"]), dev(is_con)).cpu().numpy()
+    assert np.array_equal(v, v2)
+    # unconstrained assembly (reference passes con=EMPTY, assembly.py:19,509)
+    v3 = T.csr.assemble(p, dev(c["k"]), None).cpu().numpy()
+    ref3 = O.assemble_values(c["k"], c["k_map"], c["glob_idx"], c["diag_map"],
+                             np.zeros(0, dtype=np.int64), n_dofs)
+    assert rel(v3, ref3) <= TOL_K
+
+
+def _cube_system(T, N, tables):
+    nodes, elements = O.cube_hexa(N, N, N)
+    bref, w = O.hexa1_tables()
+    C = O.isotropic_C3d(1000.0, 0.3, len(elements))
+    con_mask, disp = O.cube_extension_bcs(nodes)
+    p = T.csr.Pattern(dev(elements), nodes.shape[0], 3)
+    k = T.csr.integrate_k(T._lib.KIND_MECH, torch.as_tensor(bref), torch.as_tensor(w), dev(nodes),
+                          dev(elements), dev(C))
+    vals = T.csr.assemble(p, k, dev(con_mask.ravel().astype(np.uint8)))
+    A = T.csr.CSRMatrix(p.indptr, p.indices, vals, p.n_dofs, chunk_rows=p.chunk_rows,
+                        diag_pos=p.diag_pos, symmetric=True)
+    return nodes, elements, bref, w, C, con_mask, disp, p, k, A
+
+
+def test_config_a_structure_and_values(T, tables):
+    """BASELINE config[0] (benchmarks/cubes.py, N=11) against the reference's golden vectors."""
+    g = load_case("config_a.npz")
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 11, tables)
+    assert p.nnz == int(g["nnz"]) == 268119
+    assert sha(p.glob_idx.cpu().numpy()) == str(g["sha_glob_idx"])
+    assert sha(p.k_map.cpu().numpy()) == str(g["sha_k_map"])
+    assert sha(p.diag_map.cpu().numpy()) == str(g["sha_diag_map"])
+    kk = k.cpu().numpy()
+    assert rel(kk[0], g["k_e0"]) <= TOL_K and rel(kk[777], g["k_e777"]) <= TOL_K
+    assert abs(np.linalg.norm(kk) - g["k_fro"]) <= TOL_K * g["k_fro"]
+    v = A.values_.cpu().numpy()
+    assert np.abs(v[:4096] - g["val_head"]).max() <= TOL_K * g["val_absmax"]
+    assert abs(np.linalg.norm(v) - g["val_norm"]) <= TOL_K * g["val_norm"]
+    assert int((v == 1.0).sum()) == int(g["val_n_one"])
+
+
+@pytest.mark.parametrize("N", [4, 11, 24])
+def test_spmv_matches_oracle(T, tables, N):
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, N, tables)
+    A_ref = O.to_csr(A.values_.cpu().numpy(), p.glob_idx.cpu().numpy(), p.n_dofs)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(p.n_dofs, generator=g, dtype=torch.float64)
+    y = A.matvec(x.cuda()).cpu().numpy()
+    y_ref = A_ref @ x.numpy()
+    assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * 81
+    y2 = A.matvec(x.cuda()).cpu().numpy()
+    assert np.array_equal(y, y2)
+
+
+@pytest.mark.parametrize("tag", ["hexa2", "tetra2", "quad1", "heat_quad2", "hexa1_orphan"])
+def test_spmv_other_row_lengths(T, tag):
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    n = dpn * c["nodes"].shape[0]
+    p = build_pattern(T, c, dpn)
+    A = T.csr.CSRMatrix(p.indptr, p.indices, dev(c["K_val"]), n, chunk_rows=p.chunk_rows)
+    A_ref = O.to_csr(c["K_val"], c["glob_idx"], n)
+    x = np.random.default_rng(1).standard_normal(n)
+    y = A.matvec(dev(x)).cpu().numpy()
+    y_ref = A_ref @ x
+    assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+
+
+@pytest.mark.parametrize("method", ["cg", "minres"])
+def test_config_a_solve(T, tables, method):
+    """Displacements of config A vs the reference (spsolve golden and the reference's own Jacobi-CG /
+    MINRES run at the same stol=1e-10): <= 1e-8 relative."""
+    g = load_case("config_a.npz")
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 11, tables)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10,
+                                        method=method)
+    b = dev(ref["res"])
+    x, M, info = T.csr.krylov_solve(A, b, method=method, rtol=1e-10)
+    con = np.nonzero(con_mask.ravel())[0]
+    u = -x.cpu().numpy()
+    u[con] = disp.ravel()[con]
+    u = u.reshape(-1, 3)
+    nrm = np.linalg.norm(g["u"])
+    assert np.linalg.norm(u - g["u"]) / nrm <= 1e-8
+    assert np.linalg.norm(u - g["u_cg" if method == "cg" else "u_minres"]) / nrm <= 1e-8
+    assert np.linalg.norm(u - ref["u"]) / nrm <= 1e-8
+    # same algorithm -> same iteration count as the oracle (scipy restatement), give or take round-off
+    assert abs(info["iterations"] - ref["iterations"]) <= 2, (info, ref["iterations"])
+    assert info["converged"]
+
+
+def test_cg_warm_start_and_zero_rhs(T, tables):
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 6, tables)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
+    b = dev(ref["res"])
+    x, M, info = T.csr.krylov_solve(A, b, method="cg", rtol=1e-10)
+    x2, _, info2 = T.csr.krylov_solve(A, b, method="cg", rtol=1e-10, x0=x, M=M)
+    assert info2["iterations"] <= 1
+    assert torch.allclose(x, x2, atol=1e-8)
+    x3, _, info3 = T.csr.krylov_solve(A, torch.zeros_like(b), method="cg", rtol=1e-10)
+    assert info3["iterations"] == 0 and float(x3.abs().max()) == 0.0
+
+
+def test_cg_maxiter_raises_runtime_error(T, tables):
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 6, tables)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
+    with pytest.raises(RuntimeError, match="CG failed with exit code"):
+        T.csr.krylov_solve(A, dev(ref["res"]), method="cg", rtol=1e-14, maxiter=3)
+
+
+def test_transpose_and_general_matvec(T):
+    rng = np.random.default_rng(3)
+    n = 200
+    import scipy.sparse as sp
+
+    Am = sp.random(n, n, density=0.05, random_state=3, format="csr") + sp.eye(n, format="csr") * 4
+    Am = Am.tocsr()
+    Am.sort_indices()
+    A = T.csr.CSRMatrix(dev(Am.indptr.astype(np.int64)), dev(Am.indices.astype(np.int32)),
+                        dev(Am.data), n)
+    x = rng.standard_normal(n)
+    assert np.allclose(A.matvec(dev(x)).cpu().numpy(), Am @ x, atol=1e-12)
+    assert np.allclose(A.T.matvec(dev(x)).cpu().numpy(), Am.T @ x, atol=1e-12)
+    At = Am.T.tocsr()
+    At.sort_indices()
+    assert np.array_equal(A.T.indices.cpu().numpy(), At.indices)
+    assert np.array_equal(A.T.values_.cpu().numpy(), At.data)
+
+
+def test_full_size_properties(T, tables):
+    """Size-independent checks at a size the CPU oracle does not touch (N=64, 786k DOFs):
+    rigid-body translations are in the null space of the unconstrained K (row sums of each DOF
+    direction vanish), K is symmetric in action (x.Ay == y.Ax), CG converges and the residual it
+    reports is the true residual."""
+    N = 64
+    nodes, elements = O.cube_hexa(N, N, N)
+    bref, w = O.hexa1_tables()
+    p = T.csr.Pattern(dev(elements), nodes.shape[0], 3)
+    assert p.nnz == 9 * (3 * N - 2) ** 3
+    Cd = dev(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous()
+    k = T.csr.integrate_k(T._lib.KIND_MECH, torch.as_tensor(bref), torch.as_tensor(w), dev(nodes),
+                          dev(elements), Cd)
+    vals = T.csr.assemble(p, k, None)
+    A = T.csr.CSRMatrix(p.indptr, p.indices, vals, p.n_dofs, chunk_rows=p.chunk_rows, symmetric=True)
+    scale = float(vals.abs().max())
+    for d in range(3):
+        t = torch.zeros(p.n_nod, 3, dtype=torch.float64, device="cuda")
+        t[:, d] = 1.0
+        assert float(A.matvec(t.ravel()).abs().max()) <= 1e-12 * scale * 81
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(p.n_dofs, generator=g, dtype=torch.float64, device="cuda")
+    y = torch.randn(p.n_dofs, generator=g, dtype=torch.float64, device="cuda")
+    a, b = float(x @ A.matvec(y)), float(y @ A.matvec(x))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b), scale)
+    con_mask, disp = O.cube_extension_bcs(nodes)
+    is_con = dev(con_mask.ravel().astype(np.uint8))
+    vals_c = T.csr.assemble(p, k, is_con)
+    Ac = T.csr.CSRMatrix(p.indptr, p.indices, vals_c, p.n_dofs, chunk_rows=p.chunk_rows,
+                         diag_pos=p.diag_pos, symmetric=True)
+    du = dev(disp.ravel()) * is_con
+    rhs = A.matvec(du)
+    rhs[is_con.bool()] = 0.0
+    xs, M, info = T.csr.krylov_solve(Ac, rhs, method="cg", rtol=1e-8)
+    true_res = float(torch.linalg.norm(rhs - Ac.matvec(xs)) / torch.linalg.norm(rhs))
+    assert info["converged"] and true_res <= 2e-8
+    assert 250 <= info["iterations"] <= 400  # ~5(N-1)+2

@@ -1,0 +1,10 @@
+"""torch-fem_b200 — B200-native implicit-solve hot path of torch-fem (integration -> assembly -> Krylov).
+
+Drop-in surface (same names as the reference's `torchfem/__init__.py:1-6` for the models on the path):
+`Solid`, `SolidHeat`, `Planar`, `PlanarHeat`, plus `sparse`, `materials`, `mesh`, `elements`.
+All numerics run in hand-written sm_100a kernels behind the C ABI of `libtfem_b200.so`
+(include/tfem_b200.h); there is no CPU fallback.
+"""
+from . import _lib, csr  # noqa: F401  (loads libtfem_b200.so; ImportError if it is missing)
+
+__all__ = ["csr"]

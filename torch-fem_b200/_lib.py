@@ -1,0 +1,114 @@
+"""ctypes binding of libtfem_b200.so (C ABI declared in include/tfem_b200.h).
+
+Mirrors how the reference binds its only native library, AmgX (/root/reference/src/torchfem/amgx.py):
+library path from an environment variable with a default next to the package (amgx.py:148-163),
+`ImportError` when it cannot be loaded, every entry point returns `int rc` which `_check` turns into a
+`RuntimeError` carrying `tfem_get_error_string` (amgx.py:195-201), raw device pointers from
+`tensor.data_ptr()` and the caller's current CUDA stream.
+
+There is NO fallback: if the shared library is missing or a CUDA device is absent, the ops raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_ENV = "TFEM_B200_LIB"
+DEFAULT_LIB = os.path.join(_HERE, "libtfem_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NCCL = range(7)
+KIND_MECH, KIND_HEAT = 0, 1
+METHOD_CG, METHOD_MINRES = 0, 1
+SPMV_CHUNK = 512
+
+_SIGNATURES = {
+    "tfem_version": (c_int, []),
+    "tfem_get_error_string": (c_int, [c_int, c_char_p, c_int]),
+    "tfem_pattern_phase1": (c_int, [c_int64, c_int64, c_int, c_int] + [c_void_p] * 6),
+    "tfem_pattern_phase2": (c_int, [c_int64, c_int64, c_int, c_int] + [c_void_p] * 12),
+    "tfem_pattern_k_map": (c_int, [c_int64, c_int64, c_int, c_int] + [c_void_p] * 6),
+    "tfem_pattern_coo_rows": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
+    "tfem_integrate_k": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfem_assemble": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 9),
+    "tfem_spmv_num_chunks": (c_int64, [c_int64]),
+    "tfem_spmv_plan": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "tfem_spmv": (c_int, [c_int64, c_int64] + [c_void_p] * 7),
+    "tfem_csr_transpose": (c_int, [c_int64, c_int64, c_int64] + [c_void_p] * 7),
+    "tfem_csr_diag_positions": (c_int, [c_int64] + [c_void_p] * 4),
+    "tfem_jacobi_setup": (c_int, [c_int64] + [c_void_p] * 4),
+    "tfem_krylov_work_doubles": (c_int64, [c_int64]),
+    "tfem_krylov_solve": (c_int, [c_int, c_int64, c_int64] + [c_void_p] * 7 + [c_double, c_double, c_int64,
+                                  c_int] + [c_void_p] * 4),
+    "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
+}
+
+EXPORTED = tuple(_SIGNATURES)
+
+
+def _load() -> ctypes.CDLL:
+    path = os.environ.get(LIB_ENV, DEFAULT_LIB)
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as exc:  # same contract as amgx.py:153-157
+        raise ImportError(
+            f"libtfem_b200.so could not be loaded from {path!r} ({exc}). Build it with "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` or `make -C torch-fem_b200/csrc`, "
+            f"or point {LIB_ENV} at the shared library."
+        ) from exc
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+LIB_PATH = os.environ.get(LIB_ENV, DEFAULT_LIB)
+
+
+class TfemError(RuntimeError):
+    """A C-ABI call failed. Subclass of RuntimeError on purpose: `FEM.solve` cuts the load step back on
+    exactly that exception type when the Krylov solver fails (reference base.py:831)."""
+
+    def __init__(self, rc: int, msg: str):
+        super().__init__(f"tfem_b200 error {rc}: {msg}")
+        self.rc = rc
+
+
+def error_string(rc: int) -> str:
+    buf = ctypes.create_string_buffer(1024)
+    lib.tfem_get_error_string(rc, buf, len(buf))
+    return buf.value.decode(errors="replace")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise TfemError(rc, error_string(rc))
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    """No CPU fallback: every tensor handed to a kernel must live on a CUDA device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "torch-fem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback. "
+            "The CPU oracle under oracle/ is test infrastructure and is never used by the product."
+        )
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(f"expected a CUDA tensor, got device {t.device}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    assert t.is_contiguous(), "kernel arguments must be contiguous"
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

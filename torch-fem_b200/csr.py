@@ -1,0 +1,377 @@
+"""Device-resident sparsity pattern and CSR matrix — the host objects that own the buffers the
+C-ABI kernels work on (torch tensors; the library only borrows pointers).
+
+`Pattern` replaces the products of the reference's `FEM.__init__` (src/torchfem/base.py:73-119):
+`glob_idx` / `k_map` / `diag_map`. `CSRMatrix` replaces the `torch.sparse_coo_tensor` returned by
+`FEM.assemble_matrix` (base.py:421-426) and the CuPy CSR built from it on every solve
+(src/torchfem/sparse.py:385-393); it answers the handful of sparse-tensor methods the reference's
+callers use (`.T`, `._indices()`, `._values()`, `.shape`, `.to_dense()`, `@`).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+
+def _i32(n, device):
+    return torch.empty(int(n), dtype=torch.int32, device=device)
+
+
+def _i64(n, device):
+    return torch.empty(int(n), dtype=torch.int64, device=device)
+
+
+class Pattern:
+    """CSR sparsity pattern of a mesh with `dpn` DOFs per node, built once on the device (kernel K0).
+
+    Attributes (device tensors): `indptr` int64 [n_dofs+1], `indices` int32 [nnz], `diag_map` int32
+    [n_dofs], `node_ptr` int64 [n_nod+1] / `adj` int32 [nnzb] (node graph), `src_ptr` int64 [nnzb+1] /
+    `src` int32 [n_elem*nn*nn] (element-slot -> CSR permutation of the deterministic assembly),
+    `chunk_rows` int32 (SpMV plan).
+    """
+
+    def __init__(self, elements: Tensor, n_nod: int, dpn: int):
+        L.require_cuda(elements)
+        if elements.dtype != torch.int64:
+            elements = elements.to(torch.int64)
+        elements = elements.contiguous()
+        dev = elements.device
+        self.device = dev
+        self.n_nod = int(n_nod)
+        self.dpn = int(dpn)
+        self.n_elem, self.nn = (int(s) for s in elements.shape)
+        self.n_dofs = self.n_nod * self.dpn
+        self.elements = elements
+        st = L.stream()
+
+        inc_ptr = _i32(self.n_nod + 1, dev)
+        inc_list = _i32(max(1, self.n_elem * self.nn), dev)
+        blk_cnt = _i32(self.n_nod, dev)
+        totals = _i64(4, dev)
+        L.check(L.lib.tfem_pattern_phase1(self.n_nod, self.n_elem, self.nn, self.dpn, L.ptr(elements),
+                                          L.ptr(inc_ptr), L.ptr(inc_list), L.ptr(blk_cnt),
+                                          L.ptr(totals), st))
+        nnzb, nnz, max_blk, max_inc = (int(v) for v in totals.tolist())
+        self.nnzb, self.nnz = nnzb, nnz
+        self.max_blocks_per_node, self.max_elements_per_node = max_blk, max_inc
+
+        self.node_ptr = _i64(self.n_nod + 1, dev)
+        self.adj = _i32(max(1, nnzb), dev)
+        self.indptr = _i64(self.n_dofs + 1, dev)
+        self.indices = _i32(nnz, dev)
+        self.diag_map = _i32(self.n_dofs, dev)
+        self.src_ptr = _i64(nnzb + 1, dev)
+        self.src = _i32(max(1, self.n_elem * self.nn * self.nn), dev)
+        L.check(L.lib.tfem_pattern_phase2(self.n_nod, self.n_elem, self.nn, self.dpn, L.ptr(elements),
+                                          L.ptr(inc_ptr), L.ptr(inc_list), L.ptr(blk_cnt),
+                                          L.ptr(self.node_ptr), L.ptr(self.adj), L.ptr(self.indptr),
+                                          L.ptr(self.indices), L.ptr(self.diag_map),
+                                          L.ptr(self.src_ptr), L.ptr(self.src), st))
+        self.chunk_rows = spmv_plan(self.indptr, self.n_dofs, nnz)
+        self._k_map = None
+        self._glob_idx = None
+        self._diag_pos = None
+
+    # -- reference-compatible views, materialised only on request (they are large) --------------
+    @property
+    def k_map(self) -> Tensor:
+        """int32 [n_elem*(nn*dpn)^2] — the reference's `k_map` (base.py:94-104), bit-identical."""
+        if self._k_map is None:
+            nd = self.nn * self.dpn
+            if self.nnz >= 2**31:
+                raise RuntimeError("k_map is int32 in the reference; nnz >= 2^31 needs a partitioned mesh")
+            out = _i32(self.n_elem * nd * nd, self.device)
+            L.check(L.lib.tfem_pattern_k_map(self.n_nod, self.n_elem, self.nn, self.dpn,
+                                             L.ptr(self.elements), L.ptr(self.node_ptr),
+                                             L.ptr(self.adj), L.ptr(self.indptr), L.ptr(out), L.stream()))
+            self._k_map = out
+        return self._k_map
+
+    @property
+    def glob_idx(self) -> Tensor:
+        """int64 [2, nnz] — the reference's `glob_idx` (base.py:110-118), bit-identical."""
+        if self._glob_idx is None:
+            out = torch.empty(2, self.nnz, dtype=torch.int64, device=self.device)
+            L.check(L.lib.tfem_pattern_coo_rows(self.n_dofs, L.ptr(self.indptr), out[0].data_ptr(),
+                                                L.stream()))
+            out[1] = self.indices
+            self._glob_idx = out
+        return self._glob_idx
+
+    @property
+    def diag_pos(self) -> Tensor:
+        if self._diag_pos is None:
+            self._diag_pos = self.diag_map.to(torch.int64)
+        return self._diag_pos
+
+
+def spmv_plan(indptr: Tensor, n_rows: int, nnz: int) -> Tensor:
+    n_chunks = int(L.lib.tfem_spmv_num_chunks(nnz))
+    chunk_rows = _i32(n_chunks + 1, indptr.device)
+    L.check(L.lib.tfem_spmv_plan(n_rows, nnz, L.ptr(indptr), L.ptr(chunk_rows), L.stream()))
+    return chunk_rows
+
+
+class CSRMatrix:
+    """Square CSR matrix on the device: int64 `indptr`, int32 `indices`, float64 `values`.
+
+    `symmetric=True` (FEM tangents) makes `.T` free. For general matrices `.T` builds the transposed
+    copy with `tfem_csr_transpose` (needed by the adjoint of `differentiable_sparse_solve` with a
+    non-symmetric A, reference sparse.py:203).
+    """
+
+    def __init__(self, indptr: Tensor, indices: Tensor, values: Tensor, n: int, *, chunk_rows=None,
+                 diag_pos=None, symmetric=False, coo_indices=None):
+        L.require_cuda(indptr, indices, values)
+        if values.dtype != torch.float64:
+            raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
+        self.indptr, self.indices, self.values_ = indptr, indices, values
+        self.n = int(n)
+        self.nnz = int(values.shape[0])
+        self.symmetric = symmetric
+        self.chunk_rows = chunk_rows if chunk_rows is not None else spmv_plan(indptr, self.n, self.nnz)
+        self._diag_pos = diag_pos
+        self._coo = coo_indices
+        self._T = None
+
+    # ---- torch-sparse look-alike surface used by the reference's callers
+    @property
+    def shape(self):
+        return torch.Size((self.n, self.n))
+
+    def size(self):
+        return self.shape
+
+    @property
+    def ndim(self):
+        return 2
+
+    @property
+    def device(self):
+        return self.values_.device
+
+    @property
+    def dtype(self):
+        return self.values_.dtype
+
+    @property
+    def is_cuda(self):
+        return True
+
+    def numel(self):
+        return self.n * self.n
+
+    def is_coalesced(self):
+        return True
+
+    def coalesce(self):
+        return self
+
+    def _values(self):
+        return self.values_
+
+    values = _values
+
+    def _indices(self):
+        if self._coo is None:
+            out = torch.empty(2, self.nnz, dtype=torch.int64, device=self.device)
+            L.check(L.lib.tfem_pattern_coo_rows(self.n, L.ptr(self.indptr), out[0].data_ptr(), L.stream()))
+            out[1] = self.indices
+            self._coo = out
+        return self._coo
+
+    indices_coo = _indices
+
+    def to_sparse_coo(self) -> Tensor:
+        with torch.sparse.check_sparse_tensor_invariants(False):
+            return torch.sparse_coo_tensor(self._indices(), self.values_, size=(self.n, self.n),
+                                           is_coalesced=True)
+
+    def to_dense(self) -> Tensor:
+        return self.to_sparse_coo().to_dense()
+
+    def detach(self):
+        return self
+
+    @property
+    def diag_pos(self) -> Tensor:
+        if self._diag_pos is None:
+            pos = _i64(self.n, self.device)
+            L.check(L.lib.tfem_csr_diag_positions(self.n, L.ptr(self.indptr), L.ptr(self.indices),
+                                                  L.ptr(pos), L.stream()))
+            self._diag_pos = pos
+        return self._diag_pos
+
+    def diagonal(self) -> Tensor:
+        pos = self.diag_pos
+        d = torch.zeros(self.n, dtype=torch.float64, device=self.device)
+        ok = pos >= 0
+        d[ok] = self.values_[pos[ok]]
+        return d
+
+    @property
+    def T(self) -> "CSRMatrix":
+        if self.symmetric:
+            return self
+        if self._T is None:
+            dev = self.device
+            t_indptr = _i64(self.n + 1, dev)
+            t_indices = _i32(max(1, self.nnz), dev)[: self.nnz]
+            t_vals = torch.empty(self.nnz, dtype=torch.float64, device=dev)
+            L.check(L.lib.tfem_csr_transpose(self.n, self.n, self.nnz, L.ptr(self.indptr),
+                                             L.ptr(self.indices), L.ptr(self.values_),
+                                             L.ptr(t_indptr), L.ptr(t_indices), L.ptr(t_vals), L.stream()))
+            self._T = CSRMatrix(t_indptr, t_indices, t_vals, self.n)
+            self._T._T = self
+        return self._T
+
+    def matvec(self, x: Tensor, out: Tensor | None = None) -> Tensor:
+        """y = A x with the K5 SpMV kernel."""
+        L.require_cuda(x)
+        x = x.contiguous()
+        if x.dtype != torch.float64 or x.shape != (self.n,):
+            raise ValueError("matvec expects a float64 vector of length n")
+        y = out if out is not None else torch.empty_like(x)
+        L.check(L.lib.tfem_spmv(self.n, self.nnz, L.ptr(self.indptr), L.ptr(self.indices),
+                                L.ptr(self.values_), L.ptr(self.chunk_rows), L.ptr(x), L.ptr(y),
+                                L.stream()))
+        return y
+
+    def __matmul__(self, x: Tensor) -> Tensor:
+        return self.matvec(x)
+
+    # ---- construction from what the reference passes around
+    @staticmethod
+    def from_coo(A: Tensor) -> "CSRMatrix":
+        """From a torch sparse COO tensor (possibly uncoalesced, e.g. `M + 0.5*dt*K`, or a
+        transposed view `K.T`): duplicates are summed like scipy's `coo_matrix.tocsr` does on the
+        reference's CPU path (sparse.py:462-464) and `A.coalesce()` on its GPU path (:379-384)."""
+        L.require_cuda(A)
+        if A.layout != torch.sparse_coo:
+            A = A.to_sparse_coo()
+        A = A.detach().coalesce()
+        n = int(A.shape[0])
+        row, col = A.indices()
+        vals = A.values().to(torch.float64).contiguous()
+        counts = torch.bincount(row, minlength=n)
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=A.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        return CSRMatrix(indptr, col.to(torch.int32).contiguous(), vals, n,
+                         coo_indices=A.indices())
+
+
+def integrate_k(kind: int, bref: Tensor, w: Tensor, nodes: Tensor, elements: Tensor, tangent: Tensor,
+                scale: Tensor | None = None, check: bool = True) -> Tensor:
+    """Element matrices with kernel K1 (see include/tfem_b200.h `tfem_integrate_k`).
+
+    bref: [n_int, dim, nn] = etype.B(etype.ipoints) (host or device, any float dtype);
+    w: [n_int] = etype.iweights; tangent: [n_elem, d,d,d,d] | [n_int, n_elem, d,d,d,d] (mechanics) or
+    [n_elem, d, d] | [n_int, n_elem, d, d] (heat). Raises the reference's
+    ValueError("Negative Jacobian. Check element numbering.") (base.py:311-312) when `check`.
+    """
+    L.require_cuda(nodes, elements, tangent)
+    if nodes.dtype != torch.float64 or tangent.dtype != torch.float64:
+        raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
+    n_int, dim, nn = (int(s) for s in bref.shape)
+    n_elem = int(elements.shape[0])
+    dpn = dim if kind == L.KIND_MECH else 1
+    base_nd = 5 if kind == L.KIND_MECH else 3
+    per_gp = tangent.dim() == base_nd + 1
+    if tangent.dim() not in (base_nd, base_nd + 1):
+        raise ValueError("tangent has the wrong number of dimensions")
+    bref_h = np.ascontiguousarray(bref.detach().cpu().numpy(), dtype=np.float64)
+    w_h = np.ascontiguousarray(w.detach().cpu().numpy(), dtype=np.float64)
+    nodes = nodes.contiguous()
+    elements = elements.to(torch.int64).contiguous()
+    tangent = tangent.contiguous()
+    if scale is not None:
+        scale = scale.to(torch.float64).contiguous()
+    nd = nn * dpn
+    k = torch.empty(n_elem, nd, nd, dtype=torch.float64, device=nodes.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=nodes.device)
+    L.check(L.lib.tfem_integrate_k(kind, dim, nn, n_int, bref_h.ctypes.data, w_h.ctypes.data,
+                                   L.ptr(nodes), L.ptr(elements), n_elem, L.ptr(tangent),
+                                   1 if per_gp else 0, L.ptr(scale), L.ptr(k), L.ptr(flag), L.stream()))
+    if check and int(flag.item()) != 0:
+        raise ValueError("Negative Jacobian. Check element numbering.")
+    return k
+
+
+def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | None = None) -> Tensor:
+    """CSR values from element matrices with kernel K2/K3 (deterministic; Dirichlet rows/cols fused)."""
+    L.require_cuda(k)
+    nd = pattern.nn * pattern.dpn
+    if k.dtype != torch.float64:
+        raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
+    if tuple(k.shape) != (pattern.n_elem, nd, nd):
+        raise ValueError(f"k must have shape {(pattern.n_elem, nd, nd)}")
+    k = k.contiguous()
+    if is_con is not None:
+        is_con = is_con.to(torch.uint8).contiguous() if is_con.dtype != torch.uint8 else is_con.contiguous()
+    vals = out if out is not None else torch.empty(pattern.nnz, dtype=torch.float64, device=k.device)
+    L.check(L.lib.tfem_assemble(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
+                                L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
+                                L.ptr(pattern.src), L.ptr(k), L.ptr(is_con), L.ptr(vals), L.stream()))
+    return vals
+
+
+class JacobiPreconditioner:
+    """M = diag(A)^-1 (reference GPU path: `cupy_diags(1.0 / A_cp.diagonal())`, sparse.py:408-409).
+    Returned by `sparse_solve` as `M` and accepted back, like the reference's preconditioner object."""
+
+    def __init__(self, A: CSRMatrix):
+        self.dinv = torch.empty(A.n, dtype=torch.float64, device=A.device)
+        L.check(L.lib.tfem_jacobi_setup(A.n, L.ptr(A.values_), L.ptr(A.diag_pos), L.ptr(self.dinv),
+                                        L.stream()))
+        self.shape = (A.n, A.n)
+
+
+_WORK_CACHE: dict = {}
+
+
+def krylov_solve(A: CSRMatrix, b: Tensor, method: str = "cg", rtol: float = 1e-10, atol: float = 0.0,
+                 x0: Tensor | None = None, M: JacobiPreconditioner | None = None, maxiter: int = 0,
+                 check_every: int = 0):
+    """Jacobi-preconditioned CG / MINRES on the device (kernels K5+K6). Returns (x, M, info dict).
+    Raises RuntimeError("CG failed with exit code …") / ("minres failed …") like sparse.py:413,421."""
+    L.require_cuda(b)
+    if b.dtype != torch.float64:
+        raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
+    b = b.contiguous()
+    if M is None:
+        M = JacobiPreconditioner(A)
+    x = torch.empty_like(b)
+    nwork = int(L.lib.tfem_krylov_work_doubles(A.n))
+    key = (b.device, nwork)
+    work = _WORK_CACHE.get(key)
+    if work is None:
+        _WORK_CACHE.clear()
+        work = torch.empty(nwork, dtype=torch.float64, device=b.device)
+        _WORK_CACHE[key] = work
+    info = np.zeros(8, dtype=np.float64)
+    meth = {"cg": L.METHOD_CG, "minres": L.METHOD_MINRES}[method]
+    if x0 is not None:
+        x0 = x0.to(device=b.device, dtype=torch.float64).contiguous()
+    rc = L.lib.tfem_krylov_solve(meth, A.n, A.nnz, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.values_),
+                                 L.ptr(A.chunk_rows), L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol),
+                                 float(atol), int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
+                                 info.ctypes.data, L.stream())
+    stats = {"iterations": int(info[0]), "resnorm": float(info[1]), "bnorm": float(info[2]),
+             "converged": bool(info[3]), "spmv": int(info[4]), "launches": int(info[5])}
+    if rc in (L.ERR_NOT_CONVERGED, L.ERR_BREAKDOWN):
+        name = "CG" if method == "cg" else "minres"
+        raise RuntimeError(f"{name} failed with exit code {stats['iterations'] if rc == L.ERR_NOT_CONVERGED else -1}")
+    L.check(rc)
+    return x, M, stats
+
+
+def adjoint_matrix_grad(A: CSRMatrix, lam: Tensor, x: Tensor) -> Tensor:
+    """g[p] = -lam[row(p)] * x[col(p)] on A's pattern (kernel K7; reference sparse.py:212-216)."""
+    g = torch.empty(A.nnz, dtype=torch.float64, device=A.device)
+    L.check(L.lib.tfem_adjoint_matrix_grad(A.n, L.ptr(A.indptr), L.ptr(A.indices),
+                                           L.ptr(lam.contiguous()), L.ptr(x.contiguous()), L.ptr(g),
+                                           L.stream()))
+    return g

@@ -1,0 +1,264 @@
+// K1 — element matrices k_e = sum_q w_q detJ_q s_e B_q^T C B_q in FP64.
+//
+// Replaces, in one launch, what the reference does with ~10 torch ops per Gauss point
+// (src/torchfem/base.py:293-314 eval_shape_functions: einsum + batched LU det/inv; base.py:1086-1090 /
+// :1272-1278: 3-operand einsum + compute_k + accumulate) and its [n_int,n_elem,d,nn] temporaries.
+//
+// Mapping: one thread per (element, row node p, column node r); it owns the dpn x dpn block of k_e.
+// Per element the node coordinates, the physical gradients B_q = J_q^-1 b_q of all Gauss points, w_q detJ_q
+// and the material tangent are staged in shared memory (the reference-space table b_q and the weights come
+// in as a __grid_constant__ kernel parameter, so the call is re-entrant across streams). The finished
+// element matrix is staged in shared memory and written with fully coalesced stores: HBM traffic is
+// the 8*(nn*dpn)^2 B/element output plus ~1 kB/element of inputs.
+#include "common.cuh"
+
+namespace tfem {
+namespace {
+
+template <int DIM, int NN, int NINT>
+struct Tables {
+  double bref[NINT * DIM * NN];  // [q][i][N] = d N_N / d xi_i at Gauss point q
+  double w[NINT];
+};
+
+template <int DIM>
+__device__ __forceinline__ double inv_det(const double (&J)[DIM][DIM], double (&inv)[DIM][DIM]);
+
+template <>
+__device__ __forceinline__ double inv_det<2>(const double (&J)[2][2], double (&inv)[2][2]) {
+  const double det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  const double id = 1.0 / det;
+  inv[0][0] = J[1][1] * id;
+  inv[0][1] = -J[0][1] * id;
+  inv[1][0] = -J[1][0] * id;
+  inv[1][1] = J[0][0] * id;
+  return det;
+}
+
+template <>
+__device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&inv)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+  const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+  const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+  const double id = 1.0 / det;
+  inv[0][0] = c00 * id;
+  inv[1][0] = c01 * id;
+  inv[2][0] = c02 * id;
+  inv[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+  inv[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+  inv[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+  inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+  inv[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+  inv[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  return det;
+}
+
+template <int KIND, int DIM, int NN, int NINT, int EPC, bool PERGP>
+__global__ void __launch_bounds__(((EPC * NN * NN + 31) / 32) * 32)
+    k_integrate(const __grid_constant__ Tables<DIM, NN, NINT> tab, const double* __restrict__ nodes,
+                const int64_t* __restrict__ elements, int64_t n_elem,
+                const double* __restrict__ tangent, const double* __restrict__ scale,
+                double* __restrict__ k_out, int32_t* __restrict__ neg_jac) {
+  constexpr int DPN = (KIND == TFEM_KIND_MECH) ? DIM : 1;
+  constexpr int ND = NN * DPN;
+  constexpr int TS = (KIND == TFEM_KIND_MECH) ? DIM * DIM * DIM * DIM : DIM * DIM;
+  constexpr int NQC = PERGP ? NINT : 1;
+  constexpr int TPE = NN * NN;  // threads per element
+  // per-element shared layout (doubles)
+  constexpr int OFF_X = 0;
+  constexpr int OFF_B = OFF_X + NN * DIM;
+  constexpr int OFF_WD = OFF_B + NINT * DIM * NN;
+  constexpr int OFF_C = OFF_WD + NINT;
+  constexpr int OFF_K = OFF_C + NQC * TS;
+  constexpr int PER_ELEM = OFF_K + ND * ND;
+
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int el = tid / TPE;
+  const int pr = tid - el * TPE;
+  const int64_t e0 = (int64_t)blockIdx.x * EPC;
+  const int64_t e = e0 + el;
+  const bool active = (el < EPC) && (e < n_elem);
+  double* S = smem + (size_t)(el < EPC ? el : 0) * PER_ELEM;
+
+  if (active) {
+    for (int t = pr; t < NN * DIM; t += TPE) {
+      const int a = t / DIM, c = t - a * DIM;
+      S[OFF_X + t] = nodes[elements[e * NN + a] * DIM + c];
+    }
+    for (int t = pr; t < NQC * TS; t += TPE) {
+      const int q = t / TS, c = t - q * TS;
+      S[OFF_C + t] = tangent[((int64_t)q * n_elem + e) * TS + c];
+    }
+  }
+  __syncthreads();
+
+  if (active && pr < NINT) {
+    const int q = pr;
+    double J[DIM][DIM], inv[DIM][DIM];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < NN; ++n) s += tab.bref[(q * DIM + i) * NN + n] * S[OFF_X + n * DIM + j];
+        J[i][j] = s;
+      }
+    const double det = inv_det<DIM>(J, inv);
+    if (!(det > 0.0)) atomicOr(neg_jac, 1);
+    S[OFF_WD + q] = tab.w[q] * det * (scale ? scale[e] : 1.0);
+#pragma unroll
+    for (int i = 0; i < DIM; ++i)
+#pragma unroll
+      for (int n = 0; n < NN; ++n) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < DIM; ++j) s += inv[i][j] * tab.bref[(q * DIM + j) * NN + n];
+        S[OFF_B + (q * DIM + i) * NN + n] = s;
+      }
+  }
+  __syncthreads();
+
+  if (active) {
+    const int p = pr / NN, r = pr - p * NN;
+    double acc[DPN][DPN];
+#pragma unroll
+    for (int i = 0; i < DPN; ++i)
+#pragma unroll
+      for (int k = 0; k < DPN; ++k) acc[i][k] = 0.0;
+
+#pragma unroll 1
+    for (int q = 0; q < NINT; ++q) {
+      const double* Cq = S + OFF_C + (PERGP ? q * TS : 0);
+      double bp[DIM], br[DIM];
+#pragma unroll
+      for (int j = 0; j < DIM; ++j) {
+        bp[j] = S[OFF_B + (q * DIM + j) * NN + p];
+        br[j] = S[OFF_B + (q * DIM + j) * NN + r];
+      }
+      const double wd = S[OFF_WD + q];
+      if (KIND == TFEM_KIND_MECH) {
+        double s[DPN][DPN];
+#pragma unroll
+        for (int i = 0; i < DPN; ++i)
+#pragma unroll
+          for (int k = 0; k < DPN; ++k) s[i][k] = 0.0;
+#pragma unroll
+        for (int Jx = 0; Jx < DIM; ++Jx)
+#pragma unroll
+          for (int L = 0; L < DIM; ++L) {
+            const double bb = bp[Jx] * br[L];
+#pragma unroll
+            for (int i = 0; i < DPN; ++i)
+#pragma unroll
+              for (int k = 0; k < DPN; ++k)
+                s[i][k] = fma(bb, Cq[((i * DIM + Jx) * DIM + k) * DIM + L], s[i][k]);
+          }
+#pragma unroll
+        for (int i = 0; i < DPN; ++i)
+#pragma unroll
+          for (int k = 0; k < DPN; ++k) acc[i][k] = fma(wd, s[i][k], acc[i][k]);
+      } else {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i)
+#pragma unroll
+          for (int j = 0; j < DIM; ++j) s = fma(Cq[i * DIM + j] * bp[i], br[j], s);
+        acc[0][0] = fma(wd, s, acc[0][0]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DPN; ++i)
+#pragma unroll
+      for (int k = 0; k < DPN; ++k) S[OFF_K + (p * DPN + i) * ND + r * DPN + k] = acc[i][k];
+  }
+  __syncthreads();
+
+  // coalesced write of the CTA's element matrices (contiguous in k_out)
+  const int n_here = (int)((n_elem - e0) < EPC ? (n_elem - e0) : EPC);
+  double* dst = k_out + e0 * (int64_t)(ND * ND);
+  for (int t = tid; t < n_here * ND * ND; t += blockDim.x) {
+    const int le = t / (ND * ND);
+    dst[t] = smem[(size_t)le * PER_ELEM + OFF_K + (t - le * ND * ND)];
+  }
+}
+
+template <int KIND, int DIM, int NN, int NINT>
+int launch(const double* bref, const double* w, const double* nodes, const int64_t* elements,
+           int64_t n_elem, const double* tangent, int per_gp, const double* scale, double* k_out,
+           int32_t* neg_jac, cudaStream_t st) {
+  constexpr int TPE = NN * NN;
+  constexpr int EPC = (256 / TPE) > 0 ? (256 / TPE) : 1;
+  constexpr int THREADS = ((EPC * TPE + 31) / 32) * 32;
+  constexpr int DPN = (KIND == TFEM_KIND_MECH) ? DIM : 1;
+  constexpr int ND = NN * DPN;
+  constexpr int TS = (KIND == TFEM_KIND_MECH) ? DIM * DIM * DIM * DIM : DIM * DIM;
+  Tables<DIM, NN, NINT> tab;
+  for (int i = 0; i < NINT * DIM * NN; ++i) tab.bref[i] = bref[i];
+  for (int i = 0; i < NINT; ++i) tab.w[i] = w[i];
+  const unsigned grid = (unsigned)((n_elem + EPC - 1) / EPC);
+  if (per_gp) {
+    const size_t per_elem = NN * DIM + NINT * DIM * NN + NINT + NINT * TS + ND * ND;
+    const size_t bytes = per_elem * EPC * sizeof(double);
+    auto kern = k_integrate<KIND, DIM, NN, NINT, EPC, true>;
+    if (bytes > 48 * 1024)
+      TFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    kern<<<grid, THREADS, bytes, st>>>(tab, nodes, elements, n_elem, tangent, scale, k_out, neg_jac);
+  } else {
+    const size_t per_elem = NN * DIM + NINT * DIM * NN + NINT + TS + ND * ND;
+    const size_t bytes = per_elem * EPC * sizeof(double);
+    auto kern = k_integrate<KIND, DIM, NN, NINT, EPC, false>;
+    if (bytes > 48 * 1024)
+      TFEM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    kern<<<grid, THREADS, bytes, st>>>(tab, nodes, elements, n_elem, tangent, scale, k_out, neg_jac);
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <int KIND>
+int dispatch(int dim, int nn, int n_int, const double* bref, const double* w, const double* nodes,
+             const int64_t* elements, int64_t n_elem, const double* tangent, int per_gp,
+             const double* scale, double* k_out, int32_t* neg_jac, cudaStream_t st) {
+#define TFEM_CASE(D, N, Q)                                                                           \
+  if (dim == D && nn == N && n_int == Q)                                                             \
+    return launch<KIND, D, N, Q>(bref, w, nodes, elements, n_elem, tangent, per_gp, scale, k_out,    \
+                                 neg_jac, st);
+  TFEM_CASE(3, 8, 8)   // Hexa1  (elements.py:936-1075)
+  TFEM_CASE(3, 20, 8)  // Hexa2  (elements.py:1078-1406, 2x2x2 reduced integration)
+  TFEM_CASE(3, 4, 1)   // Tetra1 (elements.py:727-790)
+  TFEM_CASE(3, 10, 4)  // Tetra2 (elements.py:793-933)
+  TFEM_CASE(2, 4, 4)   // Quad1  (elements.py:491-567)
+  TFEM_CASE(2, 8, 4)   // Quad2  (elements.py:599-695)
+  TFEM_CASE(2, 3, 1)   // Tria1  (elements.py:309-360)
+  TFEM_CASE(2, 6, 3)   // Tria2  (elements.py:385-466)
+#undef TFEM_CASE
+  set_last_error("invalid argument", "unsupported (dim, nodes per element, integration points)");
+  return TFEM_ERR_INVALID;
+}
+
+}  // namespace
+}  // namespace tfem
+
+using namespace tfem;
+
+extern "C" int tfem_integrate_k(int kind, int dim, int nn, int n_int, const double* bref_host,
+                                const double* w_host, const double* nodes, const int64_t* elements,
+                                int64_t n_elem, const double* tangent, int tangent_per_gp,
+                                const double* scale, double* k_out, int32_t* neg_jac, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(bref_host && w_host && nodes && elements && tangent && k_out && neg_jac,
+               "integrate_k: null pointer");
+  TFEM_REQUIRE(n_elem >= 0, "integrate_k: negative n_elem");
+  if (n_elem == 0) return TFEM_OK;
+  if (kind == TFEM_KIND_MECH)
+    return dispatch<TFEM_KIND_MECH>(dim, nn, n_int, bref_host, w_host, nodes, elements, n_elem, tangent,
+                                    tangent_per_gp, scale, k_out, neg_jac, st);
+  if (kind == TFEM_KIND_HEAT)
+    return dispatch<TFEM_KIND_HEAT>(dim, nn, n_int, bref_host, w_host, nodes, elements, n_elem, tangent,
+                                    tangent_per_gp, scale, k_out, neg_jac, st);
+  set_last_error("invalid argument", "kind must be TFEM_KIND_MECH or TFEM_KIND_HEAT");
+  return TFEM_ERR_INVALID;
+}

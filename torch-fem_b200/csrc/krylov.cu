@@ -1,0 +1,693 @@
+// K4/K5/K6/K7 — CSR SpMV, Jacobi preconditioner and the fused Jacobi-PCG / MINRES drivers.
+//
+// Replaces the CuPy path of the reference (src/torchfem/sparse.py:350-421): COO->CSR conversion,
+// `cupy_diags(1/A.diagonal())`, and cupy_cg / cupy_minres, which launch cuSPARSE SpMV + ~6 separate
+// vector kernels per iteration and synchronise with the host every iteration to test convergence.
+//
+// Here one CG iteration is three launches (SpMV fused with p.q; x/r update fused with the Jacobi apply
+// and both dot products; direction update), all scalars live on the device, reductions are
+// fixed-order ("last block" pattern, no FP atomics) and the host only polls a flag every
+// `check_every` iterations. Kernels of already-converged iterations exit at their first instruction.
+#include <math.h>
+#include <string.h>
+
+#include "spmv.cuh"
+
+namespace tfem {
+
+__global__ void k_spmv_plan(int64_t n_rows, int64_t n_chunks, const int64_t* __restrict__ indptr,
+                            int32_t* __restrict__ chunk_rows) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c > n_chunks) return;
+  if (c == n_chunks) {
+    chunk_rows[c] = (int32_t)n_rows;
+    return;
+  }
+  const int64_t target = c * (int64_t)TFEM_SPMV_CHUNK;  // first row with indptr[row] >= target
+  int64_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (indptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  chunk_rows[c] = (int32_t)lo;
+}
+
+namespace {
+
+constexpr int kVecThreads = 256;
+
+// device-resident scalars of a Krylov solve
+enum Sc {
+  SC_RHO = 0, SC_RHO_PREV, SC_PQ, SC_RR, SC_TOL, SC_BNRM, SC_DONE, SC_ITERS, SC_ALPHA, SC_BETA,
+  // MINRES recurrences (scipy/sparse/linalg/_isolve/minres.py)
+  SC_M_BETA1, SC_M_OLDB, SC_M_BETA, SC_M_DBAR, SC_M_EPSLN, SC_M_PHIBAR, SC_M_CS, SC_M_SN, SC_M_TNORM2,
+  SC_M_GMAX, SC_M_GMIN, SC_M_ALFA, SC_M_YNORM2, SC_M_PHI, SC_M_DENOM, SC_M_OLDEPS, SC_M_DELTA,
+  SC_M_RNORM, SC_M_ISTOP, SC_COUNT = 32
+};
+
+struct Csr {
+  int64_t n, nnz, n_chunks;
+  const int64_t* indptr;
+  const int32_t* cols;
+  const double* vals;
+  const int32_t* chunk_rows;
+};
+
+// ------------------------------------------------------------------------------------------ SpMV
+template <int G, bool DOT>
+__global__ void __launch_bounds__(kSpmvWarps * 32)
+    k_spmv(Csr A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
+           double* partials, unsigned int* ticket, double* out_scalar) {
+  __shared__ __align__(16) double s_prod[kSpmvWarps][kSpmvCap];
+  __shared__ double s_red[kSpmvWarps];
+  if (DOT && sc[SC_DONE] != 0.0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double dot = 0.0;
+  for (int64_t c = (int64_t)blockIdx.x * kSpmvWarps + warp; c < A.n_chunks;
+       c += (int64_t)gridDim.x * kSpmvWarps)
+    dot += spmv_chunk<G>(c, A.indptr, A.cols, A.vals, A.chunk_rows, x, y, DOT ? x : nullptr,
+                         s_prod[warp], lane);
+  if (DOT) {
+    const double b = block_sum<kSpmvWarps * 32>(dot, s_red);
+    double mine[1] = {b}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
+  }
+}
+
+template <bool DOT>
+int launch_spmv(const Csr& A, const double* x, double* y, const double* sc, double* partials,
+                unsigned int* ticket, double* out_scalar, int grid, cudaStream_t st) {
+  const double avg = A.n > 0 ? (double)A.nnz / (double)A.n : 0.0;
+  if (avg >= 48.0)
+    k_spmv<16, DOT><<<grid, kSpmvWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  else if (avg >= 12.0)
+    k_spmv<8, DOT><<<grid, kSpmvWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  else
+    k_spmv<4, DOT><<<grid, kSpmvWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+inline int spmv_grid(int64_t n_chunks) {
+  const int64_t want = (n_chunks + kSpmvWarps - 1) / kSpmvWarps;
+  const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 6;  // 6 CTAs x 32 KB smem per SM
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+inline int vec_grid(int64_t n) {
+  const int64_t want = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
+  const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------ CG
+// r = b - q (q = A x0) or r = b ; p = z = dinv*r ; rr = r.r ; rho = r.z ; bb = b.b
+__global__ void __launch_bounds__(kVecThreads)
+    k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q_or_null,
+              const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
+              double* sc, double rtol, double atol, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  double rr = 0.0, rho = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    const double bi = b[i];
+    const double ri = q_or_null ? bi - q_or_null[i] : bi;
+    const double zi = dinv[i] * ri;
+    r[i] = ri;
+    p[i] = zi;
+    rr += ri * ri;
+    rho += ri * zi;
+    bb += bi * bi;
+  }
+  double mine[3], tot[3];
+  mine[0] = block_sum<kVecThreads>(rr, s_red);
+  mine[1] = block_sum<kVecThreads>(rho, s_red);
+  mine[2] = block_sum<kVecThreads>(bb, s_red);
+  if (publish_and_reduce<3>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    const double bnrm = sqrt(tot[2]);
+    const double tol = fmax(atol, rtol * bnrm);
+    sc[SC_RR] = tot[0];
+    sc[SC_RHO] = tot[1];
+    sc[SC_RHO_PREV] = tot[1];
+    sc[SC_BNRM] = bnrm;
+    sc[SC_TOL] = tol;
+    sc[SC_ITERS] = 0.0;
+    sc[SC_DONE] = (bnrm == 0.0 || sqrt(tot[0]) < tol) ? 1.0 : 0.0;
+  }
+}
+
+// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; rr = r.r ; rho' = r.(dinv r) ; convergence test
+__global__ void __launch_bounds__(kVecThreads)
+    k_cg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q,
+                const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+                double* sc, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  if (sc[SC_DONE] != 0.0) return;
+  const double pq = sc[SC_PQ];
+  const double alpha = sc[SC_RHO] / pq;
+  double rr = 0.0, rho = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    const double pi = p[i], qi = q[i];
+    x[i] = fma(alpha, pi, x[i]);
+    const double ri = fma(-alpha, qi, r[i]);
+    r[i] = ri;
+    rr = fma(ri, ri, rr);
+    rho = fma(ri * dinv[i], ri, rho);
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<kVecThreads>(rr, s_red);
+  mine[1] = block_sum<kVecThreads>(rho, s_red);
+  if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    const double rho_prev = sc[SC_RHO];
+    sc[SC_RHO_PREV] = rho_prev;
+    sc[SC_RHO] = tot[1];
+    sc[SC_RR] = tot[0];
+    sc[SC_ALPHA] = alpha;
+    sc[SC_BETA] = tot[1] / rho_prev;
+    sc[SC_ITERS] += 1.0;
+    if (!isfinite(tot[0])) sc[SC_DONE] = 2.0;  // breakdown (scipy would iterate on NaNs to maxiter)
+    else if (sqrt(tot[0]) < sc[SC_TOL]) sc[SC_DONE] = 1.0;
+  }
+}
+
+// p = dinv*r + beta p
+__global__ void __launch_bounds__(kVecThreads)
+    k_cg_direction(int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
+                   double* __restrict__ p, const double* sc) {
+  if (sc[SC_DONE] != 0.0) return;
+  const double beta = sc[SC_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads)
+    p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+__global__ void k_copy_or_zero(int64_t n, const double* __restrict__ src, double* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src ? src[i] : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------ MINRES
+// Paige-Saunders MINRES with a diagonal preconditioner, restating scipy `minres` (the algorithm
+// behind cupy_minres, sparse.py:411). Vector roles: r1, r2, y, v, w, w1(w_old), w2(w_cur).
+//
+// init: r1 = b - A x0 (or b); y = dinv*r1; beta1^2 = r1.y ; r2 = r1
+__global__ void __launch_bounds__(kVecThreads)
+    k_mr_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q_or_null,
+              const double* __restrict__ dinv, double* __restrict__ r1, double* __restrict__ r2,
+              double* __restrict__ y, double* __restrict__ w, double* __restrict__ w2, double* sc,
+              double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  double ry = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    const double bi = b[i];
+    const double ri = q_or_null ? bi - q_or_null[i] : bi;
+    const double yi = dinv[i] * ri;
+    r1[i] = ri;
+    r2[i] = ri;
+    y[i] = yi;
+    w[i] = 0.0;
+    w2[i] = 0.0;
+    ry += ri * yi;
+    bb += bi * bi;
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<kVecThreads>(ry, s_red);
+  mine[1] = block_sum<kVecThreads>(bb, s_red);
+  if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    const double beta1 = sqrt(fmax(tot[0], 0.0));
+    sc[SC_BNRM] = sqrt(tot[1]);
+    sc[SC_M_BETA1] = beta1;
+    sc[SC_M_OLDB] = 0.0;
+    sc[SC_M_BETA] = beta1;
+    sc[SC_M_DBAR] = 0.0;
+    sc[SC_M_EPSLN] = 0.0;
+    sc[SC_M_PHIBAR] = beta1;
+    sc[SC_M_CS] = -1.0;
+    sc[SC_M_SN] = 0.0;
+    sc[SC_M_TNORM2] = 0.0;
+    sc[SC_M_GMAX] = 0.0;
+    sc[SC_M_GMIN] = 1.7976931348623157e308;
+    sc[SC_M_YNORM2] = 0.0;
+    sc[SC_M_RNORM] = beta1;
+    sc[SC_M_ISTOP] = 0.0;
+    sc[SC_ITERS] = 0.0;
+    // beta1 == 0 -> x0 is the solution; ||b|| == 0 -> x = b (scipy returns early in both cases)
+    double done = 0.0;
+    if (tot[0] < 0.0) done = 2.0;
+    else if (beta1 == 0.0 || tot[1] == 0.0) done = 1.0;
+    sc[SC_DONE] = done;
+  }
+}
+
+// v = y / beta  (v is what the SpMV consumes)
+__global__ void __launch_bounds__(kVecThreads)
+    k_mr_v(int64_t n, const double* __restrict__ y, double* __restrict__ v, const double* sc) {
+  if (sc[SC_DONE] != 0.0) return;
+  const double s = 1.0 / sc[SC_M_BETA];
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads)
+    v[i] = s * y[i];
+}
+
+// after y = A v and alfa_raw = v.(A v) (from the SpMV kernel, stored in SC_PQ):
+//   y -= (beta/oldb) r1 (itn>=2) ; alfa = v.y ; y -= (alfa/beta) r2 ; r1 = r2 ; r2 = y ; y = dinv*r2 ;
+//   beta_new^2 = r2.y
+// v.r1 = 0 in exact arithmetic but scipy computes alfa AFTER the r1 correction, so alfa is reduced here
+// in a first pass (k_mr_alfa) and applied in the second (k_mr_lanczos).
+__global__ void __launch_bounds__(kVecThreads)
+    k_mr_alfa(int64_t n, const double* __restrict__ v, double* __restrict__ y,
+              const double* __restrict__ r1, double* sc, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  if (sc[SC_DONE] != 0.0) return;
+  const bool second = sc[SC_ITERS] >= 1.0;
+  const double f = second ? sc[SC_M_BETA] / sc[SC_M_OLDB] : 0.0;
+  double a = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    double yi = y[i];
+    if (second) {
+      yi = yi - f * r1[i];
+      y[i] = yi;
+    }
+    a += v[i] * yi;
+  }
+  double mine[1], tot[1];
+  mine[0] = block_sum<kVecThreads>(a, s_red);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) sc[SC_M_ALFA] = tot[0];
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    k_mr_lanczos(int64_t n, const double* __restrict__ dinv, double* __restrict__ y,
+                 double* __restrict__ r1, double* __restrict__ r2, double* sc, double rtol,
+                 double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  if (sc[SC_DONE] != 0.0) return;
+  const double f = sc[SC_M_ALFA] / sc[SC_M_BETA];
+  double ry = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    const double r2i = r2[i];
+    const double yi = y[i] - f * r2i;
+    r1[i] = r2i;
+    r2[i] = yi;
+    const double zi = dinv[i] * yi;
+    y[i] = zi;
+    ry += yi * zi;
+  }
+  double mine[1], tot[1];
+  mine[0] = block_sum<kVecThreads>(ry, s_red);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    // scalar recurrences of one MINRES iteration (scipy minres.py main loop)
+    const double eps = 2.220446049250313e-16;
+    const double itn = sc[SC_ITERS] + 1.0;
+    const double alfa = sc[SC_M_ALFA];
+    const double oldb = sc[SC_M_BETA];
+    if (tot[0] < 0.0 || !isfinite(tot[0])) {
+      sc[SC_DONE] = 2.0;
+      return;
+    }
+    const double beta = sqrt(tot[0]);
+    const double beta1 = sc[SC_M_BETA1];
+    double tnorm2 = sc[SC_M_TNORM2] + alfa * alfa + oldb * oldb + beta * beta;
+    double istop = 0.0;
+    if (itn == 1.0 && beta / beta1 <= 10.0 * eps) istop = -1.0;
+    const double cs0 = sc[SC_M_CS], sn0 = sc[SC_M_SN], dbar0 = sc[SC_M_DBAR];
+    const double oldeps = sc[SC_M_EPSLN];
+    const double delta = cs0 * dbar0 + sn0 * alfa;
+    const double gbar = sn0 * dbar0 - cs0 * alfa;
+    const double epsln = sn0 * beta;
+    const double dbar = -cs0 * beta;
+    const double root = hypot(gbar, dbar);
+    double gamma = hypot(gbar, beta);
+    gamma = fmax(gamma, eps);
+    const double cs = gbar / gamma, sn = beta / gamma;
+    const double phibar0 = sc[SC_M_PHIBAR];
+    const double phi = cs * phibar0;
+    const double phibar = sn * phibar0;
+    sc[SC_M_OLDB] = oldb;
+    sc[SC_M_BETA] = beta;
+    sc[SC_M_TNORM2] = tnorm2;
+    sc[SC_M_DBAR] = dbar;
+    sc[SC_M_EPSLN] = epsln;
+    sc[SC_M_CS] = cs;
+    sc[SC_M_SN] = sn;
+    sc[SC_M_PHIBAR] = phibar;
+    sc[SC_M_PHI] = phi;
+    sc[SC_M_DENOM] = 1.0 / gamma;
+    sc[SC_M_OLDEPS] = oldeps;
+    sc[SC_M_DELTA] = delta;
+    const double gmax = fmax(sc[SC_M_GMAX], gamma), gmin = fmin(sc[SC_M_GMIN], gamma);
+    sc[SC_M_GMAX] = gmax;
+    sc[SC_M_GMIN] = gmin;
+    sc[SC_M_RNORM] = phibar;
+    sc[SC_ITERS] = itn;
+    sc[SC_M_ISTOP] = istop;
+    // the ||x||-dependent stopping tests are finished in k_mr_xupdate (needs the new x)
+    sc[SC_RHO] = root;  // reused slot: root for test2
+  }
+}
+
+// w = (v - oldeps*w1 - delta*w2)/gamma ; x += phi*w ; ynorm^2 = x.x ; then the stopping tests
+__global__ void __launch_bounds__(kVecThreads)
+    k_mr_xupdate(int64_t n, const double* __restrict__ v, double* __restrict__ w1,
+                 double* __restrict__ w2, double* __restrict__ x, double* sc, double rtol,
+                 double maxiter, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  if (sc[SC_DONE] != 0.0) return;
+  const double oldeps = sc[SC_M_OLDEPS], delta = sc[SC_M_DELTA], denom = sc[SC_M_DENOM];
+  const double phi = sc[SC_M_PHI];
+  double xx = 0.0;
+  // storage rotation: w1 <- w2(old), w2 <- w(new): w1[i] holds w_{k-2}, w2[i] holds w_{k-1}
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * kVecThreads) {
+    const double wk2 = w1[i], wk1 = w2[i];
+    const double wn = (v[i] - oldeps * wk2 - delta * wk1) * denom;
+    w1[i] = wk1;
+    w2[i] = wn;
+    const double xi = fma(phi, wn, x[i]);
+    x[i] = xi;
+    xx = fma(xi, xi, xx);
+  }
+  double mine[1], tot[1];
+  mine[0] = block_sum<kVecThreads>(xx, s_red);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    const double eps = 2.220446049250313e-16;
+    const double Anorm = sqrt(sc[SC_M_TNORM2]);
+    const double ynorm = sqrt(tot[0]);
+    const double epsx = Anorm * ynorm * eps;
+    const double rnorm = sc[SC_M_RNORM];
+    const double root = sc[SC_RHO];
+    const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
+    const double test2 = (Anorm == 0.0) ? INFINITY : root / Anorm;
+    const double Acond = sc[SC_M_GMAX] / sc[SC_M_GMIN];
+    double istop = sc[SC_M_ISTOP];
+    if (istop == 0.0) {
+      const double t1 = 1.0 + test1, t2 = 1.0 + test2;
+      if (t2 <= 1.0) istop = 2.0;
+      if (t1 <= 1.0) istop = 1.0;
+      if (sc[SC_ITERS] >= maxiter) istop = 6.0;
+      if (Acond >= 0.1 / eps) istop = 4.0;
+      if (epsx >= sc[SC_M_BETA1]) istop = 3.0;
+      if (test2 <= rtol) istop = 2.0;
+      if (test1 <= rtol) istop = 1.0;
+    }
+    sc[SC_M_ISTOP] = istop;
+    sc[SC_RR] = rnorm * rnorm;
+    if (istop != 0.0) sc[SC_DONE] = (istop == 6.0) ? 3.0 : 1.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ misc
+__global__ void k_diag_positions(int64_t n, const int64_t* __restrict__ indptr,
+                                 const int32_t* __restrict__ cols, int64_t* __restrict__ pos) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int64_t lo = indptr[r], hi = indptr[r + 1];
+  int64_t found = -1;
+  while (lo < hi) {  // columns are sorted within a row
+    int64_t mid = (lo + hi) >> 1;
+    int32_t c = cols[mid];
+    if (c == (int32_t)r) {
+      found = mid;
+      break;
+    }
+    if (c < (int32_t)r) lo = mid + 1; else hi = mid;
+  }
+  pos[r] = found;
+}
+
+__global__ void k_jacobi(int64_t n, const double* __restrict__ vals, const int64_t* __restrict__ pos,
+                         double* __restrict__ dinv) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int64_t p = pos[r];
+  dinv[r] = 1.0 / (p >= 0 ? vals[p] : 0.0);
+}
+
+__global__ void k_adjoint_grad(int64_t n, const int64_t* __restrict__ indptr,
+                               const int32_t* __restrict__ cols, const double* __restrict__ lam,
+                               const double* __restrict__ x, double* __restrict__ g) {
+  // one warp per row
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const double ml = -lam[r];
+  for (int64_t k = indptr[r] + lane; k < indptr[r + 1]; k += 32) g[k] = ml * x[cols[k]];
+}
+
+// transpose helpers (integer counting sort; order inside a column fixed by a per-column sort)
+__global__ void k_tr_count(int64_t nnz, const int32_t* __restrict__ cols, int64_t* __restrict__ cnt) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < nnz) atomicAdd((unsigned long long*)&cnt[cols[k] + 1], 1ull);
+}
+__global__ void k_tr_scan_serial(int64_t n_cols, int64_t* cnt) {  // tiny matrices only; see host code
+  for (int64_t i = 0; i < n_cols; ++i) cnt[i + 1] += cnt[i];
+}
+__global__ void k_tr_fill(int64_t n_rows, const int64_t* __restrict__ indptr,
+                          const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                          const int64_t* __restrict__ t_indptr, int64_t* __restrict__ cursor,
+                          int32_t* __restrict__ t_cols, double* __restrict__ t_vals) {
+  int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k) {
+    const int32_t c = cols[k];
+    const int64_t dst = t_indptr[c] + (int64_t)atomicAdd((unsigned long long*)&cursor[c], 1ull);
+    t_cols[dst] = (int32_t)r;
+    t_vals[dst] = vals[k];
+  }
+}
+__global__ void k_tr_sort(int64_t n_cols, const int64_t* __restrict__ t_indptr,
+                          int32_t* __restrict__ t_cols, double* __restrict__ t_vals) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  const int64_t b = t_indptr[c], e = t_indptr[c + 1];
+  for (int64_t i = b + 1; i < e; ++i) {
+    const int32_t kc = t_cols[i];
+    const double kv = t_vals[i];
+    int64_t j = i - 1;
+    while (j >= b && t_cols[j] > kc) {
+      t_cols[j + 1] = t_cols[j];
+      t_vals[j + 1] = t_vals[j];
+      --j;
+    }
+    t_cols[j + 1] = kc;
+    t_vals[j + 1] = kv;
+  }
+}
+
+inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct Work {
+  double *r, *p, *q;                      // CG
+  double *r1, *r2, *y, *v, *w1, *w2;      // MINRES (aliases r/p/q for the first three)
+  double* sc;
+  double* partials;
+  unsigned int* ticket;
+};
+
+constexpr int64_t kMaxPartials = 148 * 8 * 4;  // >= any grid used here, x up to 3 values per kernel
+
+inline int64_t pad32(int64_t n) { return (n + 31) & ~(int64_t)31; }
+
+Work carve(double* work, int64_t n) {
+  const int64_t np = pad32(n);
+  Work w;
+  w.r = work;
+  w.p = work + np;
+  w.q = work + 2 * np;
+  w.r1 = w.r;
+  w.r2 = w.p;
+  w.y = w.q;
+  w.v = work + 3 * np;
+  w.w1 = work + 4 * np;
+  w.w2 = work + 5 * np;
+  w.sc = work + 6 * np;
+  w.partials = w.sc + SC_COUNT;
+  w.ticket = reinterpret_cast<unsigned int*>(w.partials + kMaxPartials);
+  return w;
+}
+
+}  // namespace
+}  // namespace tfem
+
+using namespace tfem;
+
+extern "C" int64_t tfem_spmv_num_chunks(int64_t nnz) {
+  return nnz <= 0 ? 1 : (nnz + TFEM_SPMV_CHUNK - 1) / TFEM_SPMV_CHUNK;
+}
+
+extern "C" int tfem_spmv_plan(int64_t n_rows, int64_t nnz, const int64_t* indptr, int32_t* chunk_rows,
+                              void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && chunk_rows && n_rows > 0, "spmv_plan: bad arguments");
+  TFEM_REQUIRE(n_rows < (int64_t)INT32_MAX, "spmv_plan: n_rows must be < 2^31");
+  const int64_t nc = tfem_spmv_num_chunks(nnz);
+  k_spmv_plan<<<grid_for(nc + 1, 256), 256, 0, st>>>(n_rows, nc, indptr, chunk_rows);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_spmv(int64_t n_rows, int64_t nnz, const int64_t* indptr, const int32_t* cols,
+                         const double* vals, const int32_t* chunk_rows, const double* x, double* y,
+                         void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && cols && vals && chunk_rows && x && y, "spmv: null pointer");
+  TFEM_REQUIRE(aligned16(cols) && aligned16(vals), "spmv: indices/values must be 16-byte aligned");
+  Csr A{n_rows, nnz, tfem_spmv_num_chunks(nnz), indptr, cols, vals, chunk_rows};
+  return launch_spmv<false>(A, x, y, nullptr, nullptr, nullptr, nullptr, spmv_grid(A.n_chunks), st);
+}
+
+extern "C" int tfem_csr_diag_positions(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
+                                       int64_t* pos, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && cols && pos && n_rows > 0, "diag_positions: bad arguments");
+  k_diag_positions<<<grid_for(n_rows, 256), 256, 0, st>>>(n_rows, indptr, cols, pos);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_jacobi_setup(int64_t n_rows, const double* vals, const int64_t* pos, double* dinv,
+                                 void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(vals && pos && dinv && n_rows > 0, "jacobi_setup: bad arguments");
+  k_jacobi<<<grid_for(n_rows, 256), 256, 0, st>>>(n_rows, vals, pos, dinv);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_adjoint_matrix_grad(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
+                                        const double* lam, const double* x, double* g, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && cols && lam && x && g && n_rows > 0, "adjoint_matrix_grad: bad arguments");
+  k_adjoint_grad<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, cols, lam, x, g);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* indptr,
+                                  const int32_t* cols, const double* vals, int64_t* t_indptr,
+                                  int32_t* t_cols, double* t_vals, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && cols && vals && t_indptr && t_cols && t_vals, "transpose: null pointer");
+  TFEM_CUDA(cudaMemsetAsync(t_indptr, 0, (n_cols + 1) * sizeof(int64_t), st));
+  if (nnz == 0) return TFEM_OK;
+  k_tr_count<<<grid_for(nnz, 256), 256, 0, st>>>(nnz, cols, t_indptr);
+  TFEM_LAUNCH_CHECK();
+  // general (non-symmetric) matrices reach this path only through differentiable_sparse_solve on
+  // user matrices; FEM tangents are symmetric and never transposed. A serial scan is adequate there.
+  k_tr_scan_serial<<<1, 1, 0, st>>>(n_cols, t_indptr);
+  TFEM_LAUNCH_CHECK();
+  int64_t* cursor = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&cursor, n_cols * sizeof(int64_t), st));
+  TFEM_CUDA(cudaMemsetAsync(cursor, 0, n_cols * sizeof(int64_t), st));
+  k_tr_fill<<<grid_for(n_rows, 128), 128, 0, st>>>(n_rows, indptr, cols, vals, t_indptr, cursor, t_cols, t_vals);
+  TFEM_LAUNCH_CHECK();
+  k_tr_sort<<<grid_for(n_cols, 128), 128, 0, st>>>(n_cols, t_indptr, t_cols, t_vals);
+  TFEM_LAUNCH_CHECK();
+  TFEM_CUDA(cudaFreeAsync(cursor, st));
+  return TFEM_OK;
+}
+
+extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
+  return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
+}
+
+extern "C" int tfem_krylov_solve(int method, int64_t n, int64_t nnz, const int64_t* indptr,
+                                 const int32_t* cols, const double* vals, const int32_t* chunk_rows,
+                                 const double* dinv, const double* b, const double* x0, double rtol,
+                                 double atol, int64_t maxiter, int check_every, double* x,
+                                 double* work, double* info, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && cols && vals && chunk_rows && dinv && b && x && work && info,
+               "krylov_solve: null pointer");
+  TFEM_REQUIRE(method == TFEM_METHOD_CG || method == TFEM_METHOD_MINRES, "krylov_solve: unknown method");
+  TFEM_REQUIRE(aligned16(cols) && aligned16(vals), "krylov_solve: indices/values must be 16-byte aligned");
+  TFEM_REQUIRE(n > 0, "krylov_solve: empty system");
+  if (maxiter <= 0) maxiter = (method == TFEM_METHOD_CG ? 10 : 5) * n;
+  if (check_every <= 0) check_every = 32;
+
+  Csr A{n, nnz, tfem_spmv_num_chunks(nnz), indptr, cols, vals, chunk_rows};
+  Work w = carve(work, n);
+  const int sg = spmv_grid(A.n_chunks), vg = vec_grid(n);
+  TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
+  double launches = 0, spmvs = 0;
+
+  // x = x0 (or 0); initial residual
+  k_copy_or_zero<<<vg, kVecThreads, 0, st>>>(n, x0, x);
+  TFEM_LAUNCH_CHECK();
+  const double* q0 = nullptr;
+  if (x0) {
+    int rc = launch_spmv<false>(A, x, w.q, nullptr, nullptr, nullptr, nullptr, sg, st);
+    if (rc != TFEM_OK) return rc;
+    q0 = w.q;
+    spmvs += 1;
+    launches += 1;
+  }
+  double sc_host[SC_COUNT];
+  int64_t issued = 0;
+  if (method == TFEM_METHOD_CG) {
+    k_cg_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r, w.p, w.sc, rtol, atol, w.partials, w.ticket);
+    TFEM_LAUNCH_CHECK();
+    launches += 2;
+    while (true) {
+      TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+      TFEM_CUDA(cudaStreamSynchronize(st));
+      if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
+      int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
+      for (int64_t it = 0; it < batch; ++it) {
+        int rc = launch_spmv<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, sg, st);
+        if (rc != TFEM_OK) return rc;
+        k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket);
+        k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
+      }
+      TFEM_LAUNCH_CHECK();
+      issued += batch;
+      launches += 3.0 * batch;
+      spmvs += batch;
+    }
+  } else {
+    // MINRES vectors: r1=w.r, r2=w.p, y=w.q, v, w1, w2
+    k_mr_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r1, w.r2, w.y, w.w1, w.w2, w.sc, w.partials, w.ticket);
+    TFEM_LAUNCH_CHECK();
+    launches += 2;
+    // the first SpMV consumes q0's storage (y), which k_mr_init has already folded into r1
+    while (true) {
+      TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+      TFEM_CUDA(cudaStreamSynchronize(st));
+      if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
+      int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
+      for (int64_t it = 0; it < batch; ++it) {
+        k_mr_v<<<vg, kVecThreads, 0, st>>>(n, w.y, w.v, w.sc);
+        int rc = launch_spmv<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, sg, st);
+        if (rc != TFEM_OK) return rc;
+        k_mr_alfa<<<vg, kVecThreads, 0, st>>>(n, w.v, w.y, w.r1, w.sc, w.partials, w.ticket);
+        k_mr_lanczos<<<vg, kVecThreads, 0, st>>>(n, dinv, w.y, w.r1, w.r2, w.sc, rtol, w.partials, w.ticket);
+        k_mr_xupdate<<<vg, kVecThreads, 0, st>>>(n, w.v, w.w1, w.w2, x, w.sc, rtol, (double)maxiter, w.partials, w.ticket);
+      }
+      TFEM_LAUNCH_CHECK();
+      issued += batch;
+      launches += 5.0 * batch;
+      spmvs += batch;
+    }
+  }
+  info[0] = sc_host[SC_ITERS];
+  info[1] = sqrt(sc_host[SC_RR]);
+  info[2] = sc_host[SC_BNRM];
+  info[3] = sc_host[SC_DONE] == 1.0 ? 1.0 : 0.0;
+  info[4] = spmvs;
+  info[5] = launches;
+  info[6] = sc_host[SC_DONE];
+  info[7] = method == TFEM_METHOD_MINRES ? sc_host[SC_M_ISTOP] : 0.0;
+  if (sc_host[SC_DONE] == 2.0) {
+    set_last_error("breakdown", "non-finite residual or non-positive curvature (matrix not SPD?)");
+    return TFEM_ERR_BREAKDOWN;
+  }
+  if (sc_host[SC_DONE] != 1.0) {
+    set_last_error("not converged", "iteration limit reached");
+    return TFEM_ERR_NOT_CONVERGED;
+  }
+  return TFEM_OK;
+}
