@@ -135,6 +135,22 @@ int tfem_spmv(int64_t n_rows, int64_t nnz, const int64_t* indptr_dev, const int3
               const double* vals_dev, const int32_t* chunk_rows_dev, const double* x_dev,
               double* y_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * SELL-32 — solver-internal matrix layout (sliced ELLPACK, slice height 32, no row permutation), built
+ * from the CSR arrays above. It replaces the CuPy CSR object the reference hands to cuSPARSE
+ * (sparse.py:391-393). Slice t holds rows [32t, 32t+32), width W_t = longest row rounded up to even;
+ * entry k of row 32t+l is at slice_ptr[t] + (k/2)*64 + 2*l + (k%2): each lane streams its own row with
+ * 128-bit loads and the warp reads 512 contiguous bytes per instruction. Padding = (own row, 0.0).
+ * slice_ptr_dev: int64 [ceil(n/32)+1] out; slice_ptr[last] = padded entry count (read it back to size
+ * sell_cols_dev int32 / sell_vals_dev double). tfem_sell_fill converts cols and/or vals (NULL = skip),
+ * so a values-only refresh (new Newton iteration, same pattern) re-converts 8 B/nnz only. */
+int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr_dev, int64_t* slice_ptr_dev, void* stream);
+int tfem_sell_fill(int64_t n_rows, const int64_t* indptr_dev, const int32_t* indices_dev,
+                   const double* vals_dev, const int64_t* slice_ptr_dev, int32_t* sell_cols_dev,
+                   double* sell_vals_dev, void* stream);
+int tfem_sell_spmv(int64_t n_rows, const int64_t* slice_ptr_dev, const int32_t* sell_cols_dev,
+                   const double* sell_vals_dev, const double* x_dev, double* y_dev, void* stream);
+
 /* y = A^T x for a general (non-symmetric) CSR matrix — the adjoint of `Solve` with non-symmetric A
  * (sparse.py:203; tests/test_sparse.py:94-158). Deterministic: builds on a transposed copy made by the
  * caller with tfem_csr_transpose. */
@@ -158,17 +174,17 @@ int tfem_jacobi_setup(int64_t n_rows, const double* vals_dev, const int64_t* dia
  * Per iteration: SpMV fused with the p.q dot; one fused axpy/axpy/precondition/dot kernel; one direction
  * update. All reductions are fixed-order (deterministic); convergence is tested on the device and the
  * host polls a flag every `check_every` iterations (<=0: default 32).
+ * The matrix is passed in the solver-internal SELL-32 layout (tfem_sell_* below).
  * x0_dev may be NULL (zero initial guess). work_dev: double [tfem_krylov_work_doubles(n)] scratch.
  * info_host: double [8] out (host): {iterations, final ||r||_2, ||b||_2, converged(1/0), spmv count,
  *            kernel launches, reserved, reserved}.
  * Returns TFEM_ERR_NOT_CONVERGED at maxiter (x still holds the last iterate). */
 int64_t tfem_krylov_work_doubles(int64_t n_rows);
-int tfem_krylov_solve(int method, int64_t n_rows, int64_t nnz, const int64_t* indptr_dev,
-                      const int32_t* indices_dev, const double* vals_dev,
-                      const int32_t* chunk_rows_dev, const double* dinv_dev, const double* b_dev,
-                      const double* x0_dev, double rtol, double atol, int64_t maxiter,
-                      int check_every, double* x_dev, double* work_dev, double* info_host,
-                      void* stream);
+int tfem_krylov_solve(int method, int64_t n_rows, const int64_t* slice_ptr_dev,
+                      const int32_t* sell_cols_dev, const double* sell_vals_dev,
+                      const double* dinv_dev, const double* b_dev, const double* x0_dev, double rtol,
+                      double atol, int64_t maxiter, int check_every, double* x_dev, double* work_dev,
+                      double* info_host, void* stream);
 
 /* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
  * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */

@@ -166,6 +166,9 @@ def test_spmv_matches_oracle(T, tables, N):
     assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * 81
     y2 = A.matvec(x.cuda()).cpu().numpy()
     assert np.array_equal(y, y2)
+    ys = A.matvec(x.cuda(), fmt="sell").cpu().numpy()
+    assert np.abs(ys - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * 81
+    assert np.array_equal(ys, A.matvec(x.cuda(), fmt="sell").cpu().numpy())
 
 
 @pytest.mark.parametrize("tag", ["hexa2", "tetra2", "quad1", "heat_quad2", "hexa1_orphan"])
@@ -180,6 +183,8 @@ def test_spmv_other_row_lengths(T, tag):
     y = A.matvec(dev(x)).cpu().numpy()
     y_ref = A_ref @ x
     assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    ys = A.matvec(dev(x), fmt="sell").cpu().numpy()
+    assert np.abs(ys - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
 
 
 @pytest.mark.parametrize("method", ["cg", "minres"])
@@ -236,6 +241,7 @@ def test_transpose_and_general_matvec(T):
                         dev(Am.data), n)
     x = rng.standard_normal(n)
     assert np.allclose(A.matvec(dev(x)).cpu().numpy(), Am @ x, atol=1e-12)
+    assert np.allclose(A.matvec(dev(x), fmt="sell").cpu().numpy(), Am @ x, atol=1e-12)
     assert np.allclose(A.T.matvec(dev(x)).cpu().numpy(), Am.T @ x, atol=1e-12)
     At = Am.T.tocsr()
     At.sort_indices()

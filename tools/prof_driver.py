@@ -1,0 +1,54 @@
+"""Short driver for ncu captures: one pass of pattern -> integrate -> assemble -> a few SpMV / CG iterations.
+    python tools/prof_driver.py --edge 150 --iters 5
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--edge", type=int, default=150)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--method", default="cg")
+    a = ap.parse_args()
+    torch.set_default_dtype(torch.float64)
+    import torchfem_b200 as T
+    from torchfem_b200 import csr
+    from oracle import fem_oracle as O
+
+    dev = torch.device("cuda", 0)
+    nodes, elements, con, disp = bench.build_problem(T, torch, a.edge, dev)
+    n_dofs = nodes.numel()
+    bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
+    C = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous().to(dev)
+    nodes, elements = nodes.to(dev), elements.to(dev)
+    is_con = con.ravel().to(torch.uint8).to(dev)
+    disp = disp.ravel().to(dev)
+    p = csr.Pattern(elements, nodes.shape[0], 3)
+    k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C)
+    vals = csr.assemble(p, k, is_con)
+    vals_free = csr.assemble(p, k, None)
+    del k
+    A = csr.CSRMatrix(p.indptr, p.indices, vals, n_dofs, chunk_rows=p.chunk_rows, diag_pos=p.diag_pos, symmetric=True)
+    Af = csr.CSRMatrix(p.indptr, p.indices, vals_free, n_dofs, chunk_rows=p.chunk_rows, symmetric=True)
+    rhs = Af.matvec(disp * is_con)
+    rhs.masked_fill_(is_con.bool(), 0.0)
+    y = torch.empty_like(rhs)
+    for _ in range(3):
+        A.matvec(rhs, out=y)
+    try:
+        csr.krylov_solve(A, rhs, method=a.method, rtol=1e-8, maxiter=a.iters, check_every=a.iters)
+    except RuntimeError as e:
+        print("expected:", e)
+    torch.cuda.synchronize()
+    print("done", p.nnz)
+
+
+if __name__ == "__main__":
+    main()

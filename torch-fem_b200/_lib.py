@@ -42,8 +42,11 @@ _SIGNATURES = {
     "tfem_csr_diag_positions": (c_int, [c_int64] + [c_void_p] * 4),
     "tfem_jacobi_setup": (c_int, [c_int64] + [c_void_p] * 4),
     "tfem_krylov_work_doubles": (c_int64, [c_int64]),
-    "tfem_krylov_solve": (c_int, [c_int, c_int64, c_int64] + [c_void_p] * 7 + [c_double, c_double, c_int64,
-                                  c_int] + [c_void_p] * 4),
+    "tfem_krylov_solve": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double, c_double, c_int64, c_int]
+                          + [c_void_p] * 4),
+    "tfem_sell_slice_ptr": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
+    "tfem_sell_fill": (c_int, [c_int64] + [c_void_p] * 7),
+    "tfem_sell_spmv": (c_int, [c_int64] + [c_void_p] * 6),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
 }
 

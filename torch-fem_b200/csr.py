@@ -107,6 +107,30 @@ class Pattern:
             self._diag_pos = self.diag_map.to(torch.int64)
         return self._diag_pos
 
+    @property
+    def sell_structure(self):
+        """(slice_ptr, sell_cols, padded_nnz) of the solver-internal SELL-32 layout, built once."""
+        if getattr(self, "_sell", None) is None:
+            self._sell = sell_structure(self.indptr, self.indices, self.n_dofs)
+        return self._sell
+
+    def matrix(self, values: Tensor, symmetric: bool = True) -> "CSRMatrix":
+        """Wrap CSR values living on this pattern."""
+        return CSRMatrix(self.indptr, self.indices, values, self.n_dofs, chunk_rows=self.chunk_rows,
+                         diag_pos=self.diag_pos, symmetric=symmetric, sell_struct=self.sell_structure,
+                         coo_indices=self._glob_idx)
+
+
+def sell_structure(indptr: Tensor, indices: Tensor, n: int):
+    n_slices = (n + 31) // 32
+    slice_ptr = _i64(n_slices + 1, indptr.device)
+    L.check(L.lib.tfem_sell_slice_ptr(n, L.ptr(indptr), L.ptr(slice_ptr), L.stream()))
+    padded = int(slice_ptr[-1].item())
+    sell_cols = _i32(max(padded, 4), indptr.device)
+    L.check(L.lib.tfem_sell_fill(n, L.ptr(indptr), L.ptr(indices), None, L.ptr(slice_ptr),
+                                 L.ptr(sell_cols), None, L.stream()))
+    return slice_ptr, sell_cols, padded
+
 
 def spmv_plan(indptr: Tensor, n_rows: int, nnz: int) -> Tensor:
     n_chunks = int(L.lib.tfem_spmv_num_chunks(nnz))
@@ -124,7 +148,7 @@ class CSRMatrix:
     """
 
     def __init__(self, indptr: Tensor, indices: Tensor, values: Tensor, n: int, *, chunk_rows=None,
-                 diag_pos=None, symmetric=False, coo_indices=None):
+                 diag_pos=None, symmetric=False, coo_indices=None, sell_struct=None):
         L.require_cuda(indptr, indices, values)
         if values.dtype != torch.float64:
             raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
@@ -136,6 +160,8 @@ class CSRMatrix:
         self._diag_pos = diag_pos
         self._coo = coo_indices
         self._T = None
+        self._sell_struct = sell_struct
+        self._sell_vals = None
 
     # ---- torch-sparse look-alike surface used by the reference's callers
     @property
@@ -228,16 +254,35 @@ class CSRMatrix:
             self._T._T = self
         return self._T
 
-    def matvec(self, x: Tensor, out: Tensor | None = None) -> Tensor:
-        """y = A x with the K5 SpMV kernel."""
+    def sell(self):
+        """(slice_ptr, sell_cols, sell_vals): the SELL-32 copy the Krylov kernels stream. The structure
+        is shared with the pattern; the values are converted once per matrix (8 B/nnz read + write)."""
+        if self._sell_struct is None:
+            self._sell_struct = sell_structure(self.indptr, self.indices, self.n)
+        slice_ptr, sell_cols, padded = self._sell_struct
+        if self._sell_vals is None:
+            sv = torch.empty(max(padded, 2), dtype=torch.float64, device=self.device)
+            L.check(L.lib.tfem_sell_fill(self.n, L.ptr(self.indptr), None, L.ptr(self.values_),
+                                         L.ptr(slice_ptr), None, L.ptr(sv), L.stream()))
+            self._sell_vals = sv
+        return slice_ptr, sell_cols, self._sell_vals
+
+    def matvec(self, x: Tensor, out: Tensor | None = None, fmt: str = "auto") -> Tensor:
+        """y = A x with the K5 SpMV kernels: the SELL-32 kernel when that copy exists (or fmt="sell"),
+        else the CSR-chunk kernel (no conversion; right for a one-off product)."""
         L.require_cuda(x)
         x = x.contiguous()
         if x.dtype != torch.float64 or x.shape != (self.n,):
             raise ValueError("matvec expects a float64 vector of length n")
         y = out if out is not None else torch.empty_like(x)
-        L.check(L.lib.tfem_spmv(self.n, self.nnz, L.ptr(self.indptr), L.ptr(self.indices),
-                                L.ptr(self.values_), L.ptr(self.chunk_rows), L.ptr(x), L.ptr(y),
-                                L.stream()))
+        if fmt == "sell" or (fmt == "auto" and self._sell_vals is not None):
+            slice_ptr, sell_cols, sell_vals = self.sell()
+            L.check(L.lib.tfem_sell_spmv(self.n, L.ptr(slice_ptr), L.ptr(sell_cols), L.ptr(sell_vals),
+                                         L.ptr(x), L.ptr(y), L.stream()))
+        else:
+            L.check(L.lib.tfem_spmv(self.n, self.nnz, L.ptr(self.indptr), L.ptr(self.indices),
+                                    L.ptr(self.values_), L.ptr(self.chunk_rows), L.ptr(x), L.ptr(y),
+                                    L.stream()))
         return y
 
     def __matmul__(self, x: Tensor) -> Tensor:
@@ -355,9 +400,10 @@ def krylov_solve(A: CSRMatrix, b: Tensor, method: str = "cg", rtol: float = 1e-1
     meth = {"cg": L.METHOD_CG, "minres": L.METHOD_MINRES}[method]
     if x0 is not None:
         x0 = x0.to(device=b.device, dtype=torch.float64).contiguous()
-    rc = L.lib.tfem_krylov_solve(meth, A.n, A.nnz, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(A.values_),
-                                 L.ptr(A.chunk_rows), L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol),
-                                 float(atol), int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
+    slice_ptr, sell_cols, sell_vals = A.sell()
+    rc = L.lib.tfem_krylov_solve(meth, A.n, L.ptr(slice_ptr), L.ptr(sell_cols), L.ptr(sell_vals),
+                                 L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
+                                 int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
                                  info.ctypes.data, L.stream())
     stats = {"iterations": int(info[0]), "resnorm": float(info[1]), "bnorm": float(info[2]),
              "converged": bool(info[3]), "spmv": int(info[4]), "launches": int(info[5])}

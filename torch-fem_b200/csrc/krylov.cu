@@ -11,6 +11,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "spmv.cuh"
 
 namespace tfem {
@@ -98,6 +100,130 @@ inline int vec_grid(int64_t n) {
   const int64_t want = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
   const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 8;
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+
+// ------------------------------------------------------------------------------------------ SELL-32
+// Solver-internal matrix layout (sliced ELLPACK, slice height 32 = one warp, no row sorting):
+// slice t holds rows [32t, 32t+32); its width W_t is the longest row rounded up to an even number;
+// entry k of row (32t + lane) lives at  slice_ptr[t] + (k/2)*64 + lane*2 + (k%2),  i.e. every lane
+// reads ITS row with 128-bit loads while the warp as a whole reads 512 contiguous bytes per
+// instruction (4 L1 wavefronts per 64 nonzeros — the CSR-chunk kernel above needs ~1 wavefront per
+// nonzero, which caps it at ~35 % of HBM bandwidth; see profiles/). FEM rows of neighbouring nodes
+// have equal length, so padding is < 1 % on the Hexa1 cube. Padding entries are (col = own row, 0.0).
+struct Sell {
+  int64_t n, n_slices;
+  const int64_t* slice_ptr;  // [n_slices+1], element offsets (multiples of 64)
+  const int32_t* cols;
+  const double* vals;
+};
+
+__global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
+                              int64_t* __restrict__ slice_elems) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_slices) return;
+  const int64_t r = t * 32 + lane;
+  int len = (r < n) ? (int)(indptr[r + 1] - indptr[r]) : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+  if (lane == 0) slice_elems[t] = (int64_t)((len + 1) & ~1) * 32;
+}
+
+// one warp per slice; output-coalesced transposition CSR -> SELL (cols and/or vals)
+__global__ void k_sell_fill(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
+                            const int32_t* __restrict__ cols, const double* __restrict__ vals,
+                            const int64_t* __restrict__ slice_ptr, int32_t* __restrict__ s_cols,
+                            double* __restrict__ s_vals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_slices) return;
+  const int64_t base = slice_ptr[t];
+  const int total = (int)(slice_ptr[t + 1] - base);  // 32 * W
+  const int64_t my_row = t * 32 + lane;
+  const int64_t my_beg = (my_row < n) ? indptr[my_row] : 0;
+  const int my_len = (my_row < n) ? (int)(indptr[my_row + 1] - my_beg) : 0;
+  for (int o = lane; o < total; o += 32) {
+    const int s2 = o >> 6, rem = o & 63;
+    const int rl = rem >> 1, k = s2 * 2 + (rem & 1);
+    const int64_t beg = __shfl_sync(0xffffffffu, my_beg, rl);
+    const int len = __shfl_sync(0xffffffffu, my_len, rl);
+    const bool real = k < len;
+    if (s_cols) {
+      int64_t own = t * 32 + rl;
+      if (own >= n) own = n - 1;
+      s_cols[base + o] = real ? cols[beg + k] : (int32_t)own;
+    }
+    if (s_vals) s_vals[base + o] = real ? vals[beg + k] : 0.0;
+  }
+}
+
+constexpr int kSellWarps = 8;
+
+template <bool DOT>
+__global__ void __launch_bounds__(kSellWarps * 32)
+    k_sell_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
+                double* partials, unsigned int* ticket, double* out_scalar) {
+  __shared__ double s_red[kSellWarps];
+  if (DOT && sc[SC_DONE] != 0.0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int2* c2 = reinterpret_cast<const int2*>(A.cols);
+  const double2* v2 = reinterpret_cast<const double2*>(A.vals);
+  double dot = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices;
+       t += (int64_t)gridDim.x * kSellWarps) {
+    const int64_t b2 = (A.slice_ptr[t] >> 1) + lane;
+    const int w2 = (int)((A.slice_ptr[t + 1] - A.slice_ptr[t]) >> 6);  // 128-bit steps
+    double acc = 0.0;
+    int s = 0;
+    for (; s + 4 <= w2; s += 4) {
+      int2 c[4];
+      double2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t at = b2 + (int64_t)(s + u) * 32;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(c[u].x), "=r"(c[u].y) : "l"(c2 + at));
+        v[u] = ldg_stream_double2(v2 + at);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc = fma(v[u].x, __ldg(x + c[u].x), acc);
+        acc = fma(v[u].y, __ldg(x + c[u].y), acc);
+      }
+    }
+    for (; s < w2; ++s) {
+      const int64_t at = b2 + (int64_t)s * 32;
+      int2 c;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(c.x), "=r"(c.y) : "l"(c2 + at));
+      const double2 v = ldg_stream_double2(v2 + at);
+      acc = fma(v.x, __ldg(x + c.x), acc);
+      acc = fma(v.y, __ldg(x + c.y), acc);
+    }
+    const int64_t row = t * 32 + lane;
+    if (row < A.n) {
+      y[row] = acc;
+      if (DOT) dot = fma(acc, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    const double b = block_sum<kSellWarps * 32>(dot, s_red);
+    double mine[1] = {b}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
+  }
+}
+
+inline int sell_grid(int64_t n_slices) {
+  const int64_t want = (n_slices + kSellWarps - 1) / kSellWarps;
+  const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 8;
+  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <bool DOT>
+int launch_sell(const Sell& A, const double* x, double* y, const double* sc, double* partials,
+                unsigned int* ticket, double* out_scalar, cudaStream_t st) {
+  k_sell_spmv<DOT><<<sell_grid(A.n_slices), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ CG
@@ -591,27 +717,65 @@ extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
   return TFEM_OK;
 }
 
+extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_t* slice_ptr,
+                                   void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0, "sell_slice_ptr: bad arguments");
+  const int64_t ns = (n_rows + 31) / 32;
+  TFEM_CUDA(cudaMemsetAsync(slice_ptr, 0, sizeof(int64_t), st));
+  k_sell_widths<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, ns, indptr, slice_ptr + 1);
+  TFEM_LAUNCH_CHECK();
+  size_t bytes = 0;
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, slice_ptr + 1, slice_ptr + 1, (int)ns, st));
+  void* tmp = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, slice_ptr + 1, slice_ptr + 1, (int)ns, st));
+  TFEM_CUDA(cudaFreeAsync(tmp, st));
+  return TFEM_OK;
+}
+
+extern "C" int tfem_sell_fill(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
+                              const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
+                              double* sell_vals, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0, "sell_fill: bad arguments");
+  TFEM_REQUIRE((!sell_cols || cols) && (!sell_vals || vals), "sell_fill: output without input");
+  const int64_t ns = (n_rows + 31) / 32;
+  k_sell_fill<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, ns, indptr, cols, vals, slice_ptr, sell_cols, sell_vals);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_sell_spmv(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
+                              const double* sell_vals, const double* x, double* y, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals && x && y && n_rows > 0, "sell_spmv: bad arguments");
+  TFEM_REQUIRE(aligned16(sell_cols) && aligned16(sell_vals), "sell_spmv: SELL arrays must be 16-byte aligned");
+  Sell A{n_rows, (n_rows + 31) / 32, slice_ptr, sell_cols, sell_vals};
+  return launch_sell<false>(A, x, y, nullptr, nullptr, nullptr, nullptr, st);
+}
+
 extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
   return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
 }
 
-extern "C" int tfem_krylov_solve(int method, int64_t n, int64_t nnz, const int64_t* indptr,
-                                 const int32_t* cols, const double* vals, const int32_t* chunk_rows,
-                                 const double* dinv, const double* b, const double* x0, double rtol,
-                                 double atol, int64_t maxiter, int check_every, double* x,
-                                 double* work, double* info, void* stream_) {
+extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr,
+                                 const int32_t* sell_cols, const double* sell_vals, const double* dinv,
+                                 const double* b, const double* x0, double rtol, double atol,
+                                 int64_t maxiter, int check_every, double* x, double* work,
+                                 double* info, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  TFEM_REQUIRE(indptr && cols && vals && chunk_rows && dinv && b && x && work && info,
+  TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals && dinv && b && x && work && info,
                "krylov_solve: null pointer");
   TFEM_REQUIRE(method == TFEM_METHOD_CG || method == TFEM_METHOD_MINRES, "krylov_solve: unknown method");
-  TFEM_REQUIRE(aligned16(cols) && aligned16(vals), "krylov_solve: indices/values must be 16-byte aligned");
+  TFEM_REQUIRE(aligned16(sell_cols) && aligned16(sell_vals), "krylov_solve: SELL arrays must be 16-byte aligned");
   TFEM_REQUIRE(n > 0, "krylov_solve: empty system");
   if (maxiter <= 0) maxiter = (method == TFEM_METHOD_CG ? 10 : 5) * n;
   if (check_every <= 0) check_every = 32;
 
-  Csr A{n, nnz, tfem_spmv_num_chunks(nnz), indptr, cols, vals, chunk_rows};
+  Sell A{n, (n + 31) / 32, slice_ptr, sell_cols, sell_vals};
   Work w = carve(work, n);
-  const int sg = spmv_grid(A.n_chunks), vg = vec_grid(n);
+  const int vg = vec_grid(n);
   TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
   double launches = 0, spmvs = 0;
 
@@ -620,7 +784,7 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, int64_t nnz, const int64
   TFEM_LAUNCH_CHECK();
   const double* q0 = nullptr;
   if (x0) {
-    int rc = launch_spmv<false>(A, x, w.q, nullptr, nullptr, nullptr, nullptr, sg, st);
+    int rc = launch_sell<false>(A, x, w.q, nullptr, nullptr, nullptr, nullptr, st);
     if (rc != TFEM_OK) return rc;
     q0 = w.q;
     spmvs += 1;
@@ -638,7 +802,7 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, int64_t nnz, const int64
       if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
       int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
       for (int64_t it = 0; it < batch; ++it) {
-        int rc = launch_spmv<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, sg, st);
+        int rc = launch_sell<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
         if (rc != TFEM_OK) return rc;
         k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket);
         k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
@@ -661,7 +825,7 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, int64_t nnz, const int64
       int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
       for (int64_t it = 0; it < batch; ++it) {
         k_mr_v<<<vg, kVecThreads, 0, st>>>(n, w.y, w.v, w.sc);
-        int rc = launch_spmv<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, sg, st);
+        int rc = launch_sell<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
         if (rc != TFEM_OK) return rc;
         k_mr_alfa<<<vg, kVecThreads, 0, st>>>(n, w.v, w.y, w.r1, w.sc, w.partials, w.ticket);
         k_mr_lanczos<<<vg, kVecThreads, 0, st>>>(n, dinv, w.y, w.r1, w.r2, w.sc, rtol, w.partials, w.ticket);
