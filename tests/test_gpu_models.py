@@ -1,0 +1,334 @@
+"""Model-level GPU parity: `Solid` / `Planar` / `SolidHeat` / `PlanarHeat` and `torchfem_b200.sparse`
+used exactly like the reference's classes (these tests mirror reference tests/test_models.py:54-71,
+tests/test_sparse.py:49-206, tests/test_base.py:77-128,209-220, tests/test_gradients.py) and are checked
+against fixtures generated from the unmodified reference (tests/golden/, oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def cuda_default():
+    """Run like the reference's GPU benchmarks do: default device cuda, float64
+    (reference benchmarks/utils.py:59-60)."""
+    torch.set_default_dtype(torch.float64)
+    torch.set_default_device("cuda")
+    yield
+    torch.set_default_device("cpu")
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torchfem_b200 as T
+
+    return T
+
+
+ETYPES = ["Tria1", "Tria2", "Quad1", "Quad2", "Tetra1", "Tetra2", "Hexa1", "Hexa2"]
+
+
+def _build(T, etype):
+    from torchfem_b200.elements import linear_to_quadratic
+    from torchfem_b200.materials import IsotropicElasticity3D, IsotropicElasticityPlaneStress
+    from torchfem_b200.mesh import cube_hexa, cube_tetra, rect_quad, rect_tri
+
+    planar = IsotropicElasticityPlaneStress(1000.0, 0.3)
+    solid = IsotropicElasticity3D(1000.0, 0.3)
+    cases = {
+        "Tria1": (rect_tri(4, 4), T.Planar, planar, False), "Tria2": (rect_tri(4, 4), T.Planar, planar, True),
+        "Quad1": (rect_quad(4, 4), T.Planar, planar, False), "Quad2": (rect_quad(4, 4), T.Planar, planar, True),
+        "Tetra1": (cube_tetra(3, 3, 3), T.Solid, solid, False), "Tetra2": (cube_tetra(3, 3, 3), T.Solid, solid, True),
+        "Hexa1": (cube_hexa(3, 3, 3), T.Solid, solid, False), "Hexa2": (cube_hexa(3, 3, 3), T.Solid, solid, True),
+    }
+    mesh, model, material, quadratic = cases[etype]
+    nodes, elements = linear_to_quadratic(*mesh) if quadratic else mesh
+    return model(nodes, elements, material)
+
+
+def _on_boundary(nodes):
+    mask = torch.zeros(len(nodes), dtype=torch.bool)
+    for dim in range(nodes.shape[1]):
+        c = nodes[:, dim]
+        mask |= torch.isclose(c, c.min()) | torch.isclose(c, c.max())
+    return mask
+
+
+class TestPatch:
+    @pytest.mark.parametrize("etype", ETYPES)
+    @pytest.mark.parametrize("method", [None, "cg"])
+    def test_reproduces_a_linear_displacement_field(self, T, etype, method):
+        """First-order patch test for all 8 element types (reference tests/test_models.py:54-71),
+        through the default direct method and through the Jacobi-CG kernels at stol 1e-14."""
+        model = _build(T, etype)
+        assert model.etype.__name__ == etype
+        g2 = torch.tensor([[1.0e-3, 2.0e-4], [3.0e-4, -1.0e-3]])
+        g3 = torch.tensor([[1.0e-3, 2.0e-4, -1.0e-4], [3.0e-4, -1.0e-3, 5.0e-5], [1.0e-4, 2.0e-4, 7.0e-4]])
+        gradient = g2 if model.n_dim == 2 else g3
+        u_exact = model.nodes @ gradient.T
+        model.constraints = _on_boundary(model.nodes)[:, None].repeat(1, model.n_dof_per_node)
+        model.displacements = u_exact
+        u, _, sigma, _, _ = model.solve(method=method, stol=1e-14)
+        assert torch.allclose(u, u_exact, atol=1e-12)
+        assert torch.allclose(sigma, sigma[0].expand_as(sigma), atol=1e-12)
+
+    def test_rejects_unsupported_connectivity(self, T):
+        from torchfem_b200.materials import IsotropicElasticity3D
+
+        with pytest.raises(ValueError, match="Element type not supported."):
+            T.Solid(torch.rand(5, 3), torch.tensor([[0, 1, 2, 3, 4]]), IsotropicElasticity3D(1.0, 0.3))
+
+
+class TestConfigA:
+    """BASELINE configs[0]: benchmarks/cubes.py at N=11 through the model API vs the reference's vectors."""
+
+    def _cube(self, T):
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(11, 11, 11)
+        cube = T.Solid(nodes, elements, IsotropicElasticity3D(E=1000.0, nu=0.3))
+        cube.forces = torch.zeros_like(nodes, requires_grad=True)
+        cube.constraints[nodes[:, 0] == 0.0, :] = True
+        cube.constraints[nodes[:, 0] == 1.0, 0] = True
+        cube.displacements[nodes[:, 0] == 1.0, 0] = 0.1
+        return cube
+
+    @pytest.mark.parametrize("method", ["spsolve", "cg", "minres"])
+    def test_forward_and_adjoint(self, T, method):
+        g = load_case("config_a.npz")
+        cube = self._cube(T)
+        assert cube.idx.dtype == torch.int32 and cube.k_map.dtype == torch.int32
+        u, f, sigma, eps, state = cube.solve(differentiable_parameters=cube.forces, method=method, stol=1e-10)
+        nrm = np.linalg.norm(g["u"])
+        assert np.linalg.norm(u.detach().cpu().numpy() - g["u"]) / nrm <= 1e-8
+        assert np.abs(f.detach().cpu().numpy() - g["f"]).max() <= 1e-6 * np.abs(g["f"]).max()
+        assert np.abs(sigma.detach().cpu().numpy() - g["sigma"]).max() <= 1e-6 * np.abs(g["sigma"]).max()
+        assert np.abs(eps.detach().cpu().numpy() - g["eps"]).max() <= 1e-7
+        assert state.shape == (cube.n_elem, 0)
+        u.sum().backward()
+        gf = cube.forces.grad.cpu().numpy()
+        assert np.linalg.norm(gf - g["grad_forces"]) / np.linalg.norm(g["grad_forces"]) <= 1e-7
+
+    def test_k0_and_assembled_matrix(self, T):
+        g = load_case("config_a.npz")
+        cube = self._cube(T)
+        k = cube.k0()
+        assert np.abs(k[0].cpu().numpy() - g["k_e0"]).max() <= 1e-12 * g["k_absmax"]
+        con = torch.nonzero(cube.constraints.ravel()).ravel()
+        K = cube.assemble_matrix(k, con)
+        v = K._values().cpu().numpy()
+        assert abs(np.linalg.norm(v) - g["val_norm"]) <= 1e-12 * g["val_norm"]
+        assert K.shape == (3993, 3993) and K._indices().shape == (2, 268119)
+        dense = K.to_dense()
+        assert torch.allclose(dense, dense.T, atol=1e-10)
+
+
+class TestGradients:
+    def test_topology_compliance_gradient(self, T):
+        """benchmarks/topopt.py at N=3: compliance and d(compliance)/d(rho) vs the reference."""
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        g = load_case("topopt_n3.npz")
+        nodes, elements = cube_hexa(7, 4, 4, 2.0, 1.0, 1.0)
+        rho = torch.tensor(g["rho"], requires_grad=True)
+        material = IsotropicElasticity3D(E=70000.0, nu=0.3).vectorize(len(elements))
+        scale = 1e-3 + (1.0 - 1e-3) * rho ** 3.0
+        material.C = scale[:, None, None, None, None] * material.C
+        model = T.Solid(nodes, elements, material)
+        model.constraints[nodes[:, 0] == 0.0, :] = True
+        model.forces = torch.tensor(g["forces"])
+        for method, tol in [("spsolve", 1e-9), ("cg", 1e-7)]:
+            rho.grad = None
+            u, *_ = model.solve(differentiable_parameters=rho, method=method, stol=1e-12)
+            c = torch.inner(model.forces.ravel(), u.ravel())
+            c.backward()
+            assert abs(float(c) - float(g["compliance"])) <= tol * abs(float(g["compliance"]))
+            gr = rho.grad.cpu().numpy()
+            assert np.linalg.norm(gr - g["grad_rho"]) / np.linalg.norm(g["grad_rho"]) <= tol * 10
+
+    def test_hyperelastic_increments_and_parameter_gradient(self, T):
+        """benchmarks/hyperelasticity.py at N=3, 3 increments, nlgeom: reaction force and
+        d(reaction)/d(mu, lambda) through the chained adjoint vs the reference."""
+        import math
+
+        from torchfem_b200.materials import Hyperelastic3D
+        from torchfem_b200.mesh import cube_hexa
+
+        g = load_case("hyper_n3.npz")
+        En, NU = 1000.0, 0.3
+        LBD = En * NU / ((1.0 + NU) * (1.0 - 2.0 * NU))
+        MU = En / (2.0 * (1.0 + NU))
+
+        def psi(F, params):
+            Cg = F.transpose(-1, -2) @ F
+            logJ = 0.5 * torch.logdet(Cg)
+            return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+
+        lx = 2.0
+        nodes, elements = cube_hexa(5, 3, 3, lx, 1.0, 1.0)
+        params = torch.tensor([MU, LBD], requires_grad=True)
+        box = T.Solid(nodes, elements, Hyperelastic3D(psi, params))
+        left, right = nodes[:, 0] == 0.0, nodes[:, 0] == lx
+        box.constraints[left, 0] = True
+        box.constraints[right, 0] = True
+        box.constraints[nodes[:, 1] == 0.5, 1] = True
+        box.constraints[nodes[:, 2] == 0.5, 2] = True
+        box.displacements[right, 0] = lx
+        increments = torch.tensor(g["increments"])
+        u, f, *_ = box.solve(increments=increments, nlgeom=True, differentiable_parameters=params,
+                             method="spsolve")
+        reaction = f[right, 0].sum()
+        reaction.backward()
+        assert np.abs(u.detach().cpu().numpy() - g["u"]).max() <= 1e-8 * np.abs(g["u"]).max()
+        assert abs(float(reaction) - float(g["reaction"])) <= 1e-8 * abs(float(g["reaction"]))
+        assert np.allclose(params.grad.cpu().numpy(), g["grad_params"], rtol=1e-6)
+
+    def test_outputs_detached_without_parameters(self, T):
+        model = _build(T, "Quad1")
+        model.constraints[model.nodes[:, 0] == 0.0, :] = True
+        model.forces[model.nodes[:, 0] == 1.0, 0] = 1.0
+        u, f, s, e, a = model.solve()
+        assert not any(t.requires_grad for t in (u, f, s, e, a))
+
+
+class TestSparse:
+    """reference tests/test_sparse.py:49-206 against torchfem_b200.sparse."""
+
+    def _spd(self, n, seed):
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+        A = torch.rand(n, n, generator=gen, device="cpu")
+        return (A @ A.T + n * torch.eye(n, device="cpu")).cuda()
+
+    def _sp(self, dense):
+        return dense.to_sparse_coo().coalesce()
+
+    @pytest.mark.parametrize("method", [None, "spsolve", "cg", "minres"])
+    def test_matches_dense_solution(self, T, method):
+        A = self._spd(6, 0)
+        b = torch.randn(6)
+        x, M = T.sparse.sparse_solve(self._sp(A), b, method=method)
+        assert torch.allclose(x, torch.linalg.solve(A, b), atol=1e-8)
+        assert (M is None) == (method in (None, "spsolve"))
+
+    def test_errors(self, T):
+        A = torch.sparse_coo_tensor(torch.tensor([[0, 1], [0, 1]]), torch.ones(2), (2, 3)).coalesce()
+        with pytest.raises(ValueError, match="square 2D matrix"):
+            T.sparse.sparse_solve(A, torch.ones(2))
+        with pytest.raises(ValueError, match="is not supported"):
+            T.sparse.sparse_solve(self._sp(self._spd(6, 0)), torch.randn(6), method="not-a-solver")
+
+    def test_initial_guess_does_not_change_the_solution(self, T):
+        A = self._spd(6, 0)
+        b = torch.randn(6)
+        ref = torch.linalg.solve(A, b)
+        x, _ = T.sparse.sparse_solve(self._sp(A), b, method="cg", x0=ref + 0.1 * torch.randn(6))
+        assert torch.allclose(x, ref, atol=1e-8)
+
+    @pytest.mark.parametrize("tag", ["spd", "nonsym"])
+    @pytest.mark.parametrize("method", ["spsolve", "cg"])
+    def test_adjoint_matches_reference(self, T, tag, method):
+        """Forward, dL/db and dL/dA (on A's pattern) for an SPD and a NON-symmetric matrix — pins the
+        transpose in the adjoint (reference tests/test_sparse.py:94-158); CG only for the SPD one."""
+        if tag == "nonsym" and method == "cg":
+            pytest.skip("CG needs an SPD matrix")
+        g = load_case("sparse_small.npz")
+        Ad = torch.tensor(g[f"{tag}.A"])
+        A = Ad.to_sparse_coo().detach().requires_grad_(True)
+        b = torch.tensor(g["b"]).requires_grad_(True)
+        x = T.sparse.differentiable_sparse_solve(A, b, method=method, stol=1e-13)
+        x.sum().backward()
+        assert np.allclose(x.detach().cpu().numpy(), g[f"{tag}.x"], atol=1e-10)
+        assert np.allclose(b.grad.cpu().numpy(), g[f"{tag}.gb"], atol=1e-10)
+        gA = A.grad.coalesce()
+        assert np.array_equal(gA.indices().cpu().numpy(), g[f"{tag}.gA_idx"])
+        assert np.allclose(gA.values().cpu().numpy(), g[f"{tag}.gA_val"], atol=1e-10)
+
+    def test_cached_solve_warm_start(self, T):
+        A = self._sp(self._spd(6, 1))
+        b = torch.randn(6)
+        cache = T.sparse.CachedSolve()
+        x1 = T.sparse.differentiable_sparse_solve(A, b, method="cg", cached_solve=cache, update_cache=True)
+        assert cache.previous_x is not None and not cache.previous_x.requires_grad
+        x2 = T.sparse.differentiable_sparse_solve(A, b, method="cg", cached_solve=cache)
+        assert torch.allclose(x1, x2, atol=1e-8)
+
+    def test_resolve_method_policy(self, T):
+        assert T.sparse.resolve_method(9999, "cuda", None) == "spsolve"
+        assert T.sparse.resolve_method(10000, "cuda", None) == "minres"
+        assert T.sparse.resolve_method(5, "cuda", "cg") == "cg"
+        assert T.sparse.describe_method(10000, "cuda", None) == "minres | iterative | jacobi | tfem_b200 | cuda"
+
+
+class TestBase:
+    def test_inverted_element_raises(self, T):
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(2, 2, 2)
+        elements = elements[:, [1, 0, 3, 2, 5, 4, 7, 6]]
+        model = T.Solid(nodes, elements, IsotropicElasticity3D(1000.0, 0.3))
+        with pytest.raises(ValueError, match="Negative Jacobian"):
+            model.k0()
+
+    def test_heat_k0_symmetric_zero_row_sums_and_scaling(self, T):
+        from torchfem_b200.materials import IsotropicConductivity2D, IsotropicConductivity3D
+        from torchfem_b200.mesh import cube_hexa, rect_quad
+
+        m = T.PlanarHeat(*rect_quad(3, 3), IsotropicConductivity2D(kappa=400.0))
+        k = m.k0()
+        assert k.shape == (m.n_elem, 4, 4)
+        assert torch.allclose(k, k.transpose(-1, -2))
+        assert torch.allclose(k.sum(-1), torch.zeros(m.n_elem, 4), atol=1e-10)
+        k2 = T.PlanarHeat(*rect_quad(3, 3), IsotropicConductivity2D(800.0)).k0()
+        assert torch.allclose(k2, 2.0 * k)
+        s = T.SolidHeat(*cube_hexa(3, 3, 3), IsotropicConductivity3D(400.0))
+        ks = s.k0()
+        assert ks.shape == (s.n_elem, 8, 8) and torch.allclose(ks.sum(-1), torch.zeros(s.n_elem, 8), atol=1e-10)
+
+    def test_heat_solve_linear_temperature(self, T):
+        """1-D conduction through a slab: prescribed T on two faces gives a linear profile."""
+        from torchfem_b200.materials import IsotropicConductivity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(5, 3, 3)
+        m = T.SolidHeat(nodes, elements, IsotropicConductivity3D(10.0))
+        m.constraints[nodes[:, 0] == 0.0, 0] = True
+        m.constraints[nodes[:, 0] == 1.0, 0] = True
+        m.temperatures[nodes[:, 0] == 1.0, 0] = 100.0
+        Tn, q, flux, grad, _ = m.solve()
+        assert torch.allclose(Tn[:, 0], 100.0 * nodes[:, 0], atol=1e-9)
+        assert flux.shape == (m.n_elem, 3) and torch.allclose(flux[:, 0], torch.full((m.n_elem,), 1000.0), atol=1e-7)
+
+    def test_output_shapes(self, T):
+        """reference tests/test_base.py:209-220: integration-point axis and increment axis."""
+        model = _build(T, "Hexa1")
+        model.constraints[model.nodes[:, 0] == 0.0, :] = True
+        model.forces[model.nodes[:, 0] == 1.0, 0] = 1.0
+        u, f, s, e, a = model.solve(aggregate_integration_points=False)
+        assert s.shape == (8, model.n_elem, 3, 3) and u.shape == (model.n_nod, 3)
+        inc = torch.tensor([0.0, 0.5, 1.0])
+        u, f, s, e, a = model.solve(increments=inc, return_intermediate=True)
+        assert u.shape == (3, model.n_nod, 3) and s.shape == (3, model.n_elem, 3, 3)
+        assert torch.allclose(u[1] * 2, u[2], atol=1e-10)
+
+    def test_planar_thickness_gradient_incremental_equals_single(self, T):
+        """reference tests/test_gradients.py:27-49: adjoint through increments == single step."""
+        from torchfem_b200.materials import IsotropicElasticityPlaneStress
+        from torchfem_b200.mesh import rect_quad
+
+        nodes, elements = rect_quad(4, 3)
+        grads = []
+        for inc in (torch.tensor([0.0, 1.0]), torch.tensor([0.0, 0.3, 0.7, 1.0])):
+            th = torch.full((len(elements),), 0.5, requires_grad=True)
+            m = T.Planar(nodes, elements, IsotropicElasticityPlaneStress(1000.0, 0.3), thickness=th)
+            m.constraints[nodes[:, 0] == 0.0, :] = True
+            m.forces[nodes[:, 0] == 1.0, 1] = -1.0
+            u, *_ = m.solve(increments=inc, differentiable_parameters=th)
+            (u ** 2).sum().backward()
+            grads.append(th.grad.clone())
+        assert torch.allclose(grads[0], grads[1], atol=1e-9, rtol=1e-7)

@@ -1,0 +1,583 @@
+"""FEM driver of the hot path: DOF map and sparsity pattern, Gauss-point integration, global assembly and
+the incremental Newton solve — the drop-in for the reference's `torchfem.base` (src/torchfem/base.py).
+
+Same model API (`FEM`, `Mechanics`, `Heat`; attributes `forces / displacements / constraints /
+ext_strain / heat_flux / temperatures`, `idx`, `k_map`, `diag_map`, `glob_idx`, `K`; methods `k0`,
+`integrate_material`, `assemble_matrix`, `assemble_rhs`, `eval_shape_functions`, `compute_B`, `solve` with
+every keyword of reference base.py:597-616). What runs underneath is different:
+
+* `__init__` builds the pattern with kernel K0 (node graph, `csr.Pattern`) instead of sorting packed keys
+  (base.py:78-118); `k_map` / `glob_idx` are materialised lazily, only if somebody reads them.
+* `integrate_material` computes the element tangent matrices with kernel K1 (`csr.integrate_k`) from the
+  material's `ddsdde`; the residual side (`H_inc`, `Material.step`, `compute_f`) stays in torch because the
+  adjoint differentiates through it (reference sparse.py:689-705). Shape gradients are cached per model.
+* `assemble_matrix` runs the deterministic gather kernel K2/K3 and returns a device `CSRMatrix`
+  (not a COO tensor); `sparse.sparse_solve` consumes it without any format conversion.
+
+Everything lives on the CUDA device; CPU inputs are moved there once in the constructor.
+"""
+from __future__ import annotations
+
+import math
+from abc import ABC, abstractmethod
+from collections.abc import Iterable
+from functools import cached_property
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+from . import csr as _csr
+from .elements import Element
+from .materials import Material
+from .sparse import CachedSolve, describe_method, differentiable_sparse_solve, newton_solve  # noqa: F401
+
+
+def _cuda_device(t: Tensor) -> torch.device:
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("torch-fem_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _det_inv(J: Tensor) -> tuple[Tensor, Tensor]:
+    """Closed-form determinant and inverse of batched 2x2 / 3x3 matrices (differentiable)."""
+    d = J.shape[-1]
+    if d == 1:
+        det = J[..., 0, 0]
+        return det, 1.0 / J
+    if d == 2:
+        a, b, c, e = J[..., 0, 0], J[..., 0, 1], J[..., 1, 0], J[..., 1, 1]
+        det = a * e - b * c
+        inv = torch.stack([torch.stack([e, -b], -1), torch.stack([-c, a], -1)], -2) / det[..., None, None]
+        return det, inv
+    c00 = J[..., 1, 1] * J[..., 2, 2] - J[..., 1, 2] * J[..., 2, 1]
+    c01 = J[..., 1, 2] * J[..., 2, 0] - J[..., 1, 0] * J[..., 2, 2]
+    c02 = J[..., 1, 0] * J[..., 2, 1] - J[..., 1, 1] * J[..., 2, 0]
+    det = J[..., 0, 0] * c00 + J[..., 0, 1] * c01 + J[..., 0, 2] * c02
+    r0 = torch.stack([c00, J[..., 0, 2] * J[..., 2, 1] - J[..., 0, 1] * J[..., 2, 2],
+                      J[..., 0, 1] * J[..., 1, 2] - J[..., 0, 2] * J[..., 1, 1]], -1)
+    r1 = torch.stack([c01, J[..., 0, 0] * J[..., 2, 2] - J[..., 0, 2] * J[..., 2, 0],
+                      J[..., 0, 2] * J[..., 1, 0] - J[..., 0, 0] * J[..., 1, 2]], -1)
+    r2 = torch.stack([c02, J[..., 0, 1] * J[..., 2, 0] - J[..., 0, 0] * J[..., 2, 1],
+                      J[..., 0, 0] * J[..., 1, 1] - J[..., 0, 1] * J[..., 1, 0]], -1)
+    inv = torch.stack([r0, r1, r2], -2) / det[..., None, None]
+    return det, inv
+
+
+class FEM(ABC):
+    """Abstract finite-element model (reference base.py:23-132)."""
+
+    KIND = L.KIND_MECH
+
+    def __init__(self, nodes: Tensor, elements: Tensor, material: Material | None):
+        dev = _cuda_device(nodes)
+        self.device = dev
+        self.nodes = nodes.to(dev)
+        self.elements = elements.to(dev)
+        self.n_nod, self.n_dim = self.nodes.shape
+        self.n_dofs = self.n_dof_per_node * self.n_nod
+        self.n_elem = len(self.elements)
+        self.n_int = len(self.etype.iweights)
+        dt = self.nodes.dtype
+        dpn = self.n_dof_per_node
+
+        self._neumann = torch.zeros(self.n_nod, dpn, dtype=dt, device=dev)
+        self._dirichlet = torch.zeros(self.n_nod, dpn, dtype=dt, device=dev)
+        self._constraints = torch.zeros(self.n_nod, dpn, dtype=torch.bool, device=dev)
+        self._external_gradient = torch.zeros(self.n_elem, *self.n_flux, dtype=dt, device=dev)
+
+        # local -> global DOF map (base.py:73-76,119), int32 like the reference
+        dofs = dpn * self.elements.unsqueeze(-1) + torch.arange(dpn, device=dev)
+        self.idx = dofs.reshape(self.n_elem, -1).to(torch.int32)
+
+        # sparsity pattern + assembly permutation (kernel K0; replaces base.py:78-118)
+        self.pattern = _csr.Pattern(self.elements, self.n_nod, dpn)
+
+        self.material: Material | None
+        if material is None:
+            self.material = None
+        else:
+            m = material if material.is_vectorized else material.vectorize(self.n_elem)
+            self.material = m.to(dev)
+        self.cached_solve = CachedSolve()
+        self.K = torch.empty(0, device=dev)
+        self._shape_cache = None
+
+    # ---- reference-compatible integer structure (bit-identical, materialised on demand)
+    @property
+    def k_map(self) -> Tensor:
+        return self.pattern.k_map
+
+    @property
+    def diag_map(self) -> Tensor:
+        return self.pattern.diag_map
+
+    @property
+    def glob_idx(self) -> Tensor:
+        return self.pattern.glob_idx
+
+    @property
+    def n_state(self) -> int:
+        assert self.material is not None
+        return self.material.n_state
+
+    @property
+    def volume_scale(self) -> Tensor:
+        return torch.ones(self.n_elem, dtype=self.nodes.dtype, device=self.device)
+
+    @property
+    def _k_scale(self) -> Tensor | None:
+        """Per-element factor of compute_k beyond detJ (thickness), handed to kernel K1."""
+        return None
+
+    @property
+    @abstractmethod
+    def n_flux(self) -> list[int]:
+        ...
+
+    @property
+    @abstractmethod
+    def n_dof_per_node(self) -> int:
+        ...
+
+    @property
+    @abstractmethod
+    def etype(self) -> type[Element]:
+        ...
+
+    @property
+    @abstractmethod
+    def initial_grad(self) -> Tensor:
+        ...
+
+    @abstractmethod
+    def compute_k(self, detJ: Tensor, BCB: Tensor) -> Tensor:
+        ...
+
+    @abstractmethod
+    def compute_f(self, detJ: Tensor, B: Tensor, S: Tensor) -> Tensor:
+        ...
+
+    def compute_m(self, detJ: Tensor, rho: Tensor) -> Tensor:
+        raise NotImplementedError
+
+    def plot(self, *args, **kwargs):
+        raise NotImplementedError("plotting is out of scope of torch-fem_b200 (SURVEY §2, row 19)")
+
+    # ---- boundary conditions
+    @property
+    def constraints(self) -> Tensor:
+        return self._constraints
+
+    @constraints.setter
+    def constraints(self, value: Tensor):
+        if value.shape != (self.n_nod, self.n_dof_per_node):
+            raise ValueError("Constraints must have the same shape as nodes.")
+        if value.dtype != torch.bool:
+            raise TypeError("Constraints must be a boolean tensor.")
+        self._constraints = value.to(self.device)
+
+    def _set_field(self, name: str, label: str, value: Tensor, shape_msg: str):
+        if value.shape != (self.n_nod, self.n_dof_per_node):
+            raise ValueError(shape_msg)
+        if not torch.is_floating_point(value):
+            raise TypeError(f"{label} must be a floating-point tensor.")
+        setattr(self, name, value.to(self.device))
+
+    # ---- shape functions
+    def eval_shape_functions(self, xi: Tensor) -> tuple[Tensor, Tensor, Tensor]:
+        """N, B = J^-1 dN/dxi and detJ at arbitrary reference points (reference base.py:293-314).
+        Differentiable w.r.t. `self.nodes`; raises the reference's ValueError on detJ <= 0."""
+        X = self.nodes[self.elements]
+        xi = xi.to(device=self.device, dtype=self.nodes.dtype)
+        b = self.etype.B(xi)
+        J = torch.einsum("...iN,ANj->...Aij", b, X)
+        detJ, Jinv = _det_inv(J)
+        if torch.any(detJ <= 0.0):
+            raise ValueError("Negative Jacobian. Check element numbering.")
+        B = torch.einsum("...Eij,...jN->...EiN", Jinv, b)
+        return self.etype.N(xi), B, detJ
+
+    def _ip_shape(self) -> tuple[Tensor, Tensor, Tensor]:
+        """Shape data at the integration points, cached while `nodes` is the same non-differentiable
+        tensor (the reference recomputes it on every `integrate_material` call, base.py:1048)."""
+        key = (self.nodes.data_ptr(), self.nodes._version, self.elements.data_ptr())
+        if self.nodes.requires_grad:
+            return self.eval_shape_functions(self.etype.ipoints)
+        if self._shape_cache is None or self._shape_cache[0] != key:
+            self._shape_cache = (key, self.eval_shape_functions(self.etype.ipoints))
+        return self._shape_cache[1]
+
+    def _tables(self) -> tuple[Tensor, Tensor]:
+        ip = self.etype.ipoints.to(torch.float64)
+        return self.etype.B(ip).cpu(), self.etype.iweights.to(torch.float64).cpu()
+
+    def _integrate_k(self, tangent: Tensor) -> Tensor:
+        """Element matrices from the material tangent with kernel K1. `tangent` is one tensor per
+        element or a stack over Gauss points."""
+        bref, w = self._tables()
+        return _csr.integrate_k(self.KIND, bref, w, self.nodes.detach(), self.elements,
+                                tangent.detach().to(torch.float64), self._k_scale)
+
+    def compute_B(self) -> Tensor:
+        """Rigid-body modes (near null space for AMG back ends; unused by Jacobi but part of the
+        `sparse_solve` signature, reference base.py:316-344)."""
+        d, n = self.n_dof_per_node, self.n_nod
+        kw = dict(dtype=self.nodes.dtype, device=self.device)
+        if d == 3:
+            B = torch.zeros(3 * n, 6, **kw)
+            x, y, z = self.nodes.detach().unbind(1)
+            for i in range(3):
+                B[i::3, i] = 1
+            B[1::3, 3], B[2::3, 3] = -z, y
+            B[0::3, 4], B[2::3, 4] = z, -x
+            B[0::3, 5], B[1::3, 5] = -y, x
+        elif d == 2:
+            B = torch.zeros(2 * n, 3, **kw)
+            x, y = self.nodes.detach().unbind(1)
+            B[0::2, 0] = 1
+            B[1::2, 1] = 1
+            B[1::2, 2], B[0::2, 2] = -x, y
+        else:
+            B = torch.ones(d * n, 1, **kw)
+        return B
+
+    def integrate_shape_functions(self) -> Tensor:
+        N, _, detJ = self._ip_shape()
+        w = self.etype.iweights.to(device=self.device, dtype=self.nodes.dtype)
+        return torch.einsum("i,in,ie->en", w, N, detJ)
+
+    def integrate_field(self, field: Tensor | None = None) -> Tensor:
+        """Integral of a nodal scalar field (or of 1) over each element (reference base.py:353-374)."""
+        wN = self.integrate_shape_functions()
+        if field is None:
+            return wN.sum(dim=1)
+        return (wN * field.to(self.device)[self.elements]).sum(dim=1)
+
+    def integrate_mass(self) -> Tensor:
+        """Consistent element mass matrices (reference base.py:376-396)."""
+        assert self.material is not None
+        nn, dpn = self.etype.nodes, self.n_dof_per_node
+        N, _, detJ = self._ip_shape()
+        eye = torch.eye(dpn, dtype=self.nodes.dtype, device=self.device)
+        m = torch.zeros(self.n_elem, nn * dpn, nn * dpn, dtype=self.nodes.dtype, device=self.device)
+        for q, w in enumerate(self.etype.iweights):
+            dens = self.compute_m(detJ[q], self.material.rho)
+            blk = torch.einsum("N,M,E,ij->ENiMj", N[q], N[q], dens * torch.ones_like(detJ[q]), eye)
+            m += float(w) * blk.reshape(self.n_elem, nn * dpn, nn * dpn)
+        return m
+
+    # ---- element matrices / assembly
+    def k0(self) -> Tensor:
+        """Element matrix of the reference state, [n_elem, nd, nd] (reference base.py:228-245)."""
+        kw = dict(dtype=self.nodes.dtype, device=self.device)
+        u = torch.zeros(self.n_nod, self.n_dof_per_node, **kw)
+        grad = torch.zeros(self.n_int, self.n_elem, *self.n_flux, **kw)
+        grad[:] = self.initial_grad.to(**kw)
+        flux = torch.zeros(self.n_int, self.n_elem, *self.n_flux, **kw)
+        state = torch.zeros(self.n_int, self.n_elem, self.n_state, **kw)
+        de0 = torch.zeros(self.n_elem, *self.n_flux, **kw)
+        self.K = torch.empty(0, device=self.device)
+        k, *_ = self.integrate_material(u, grad, flux, state, u.clone(), de0, 0, False)
+        assert k is not None
+        return k
+
+    @abstractmethod
+    def integrate_material(self, u_prev, grad_prev, flux_prev, state_prev, du, de0, iter, nlgeom,
+                           compute_stiffness: bool = True):
+        ...
+
+    def assemble_matrix(self, k: Tensor, con: Tensor) -> _csr.CSRMatrix:
+        """Global tangent with Dirichlet rows/columns zeroed and unit diagonal (reference
+        base.py:398-426), assembled by the deterministic kernel K2/K3. Returns a device CSR matrix
+        whose `_values()` / `_indices()` are the reference's COO values / `glob_idx`."""
+        is_con = torch.zeros(self.n_dofs, dtype=torch.bool, device=self.device)
+        is_con[con.to(self.device)] = True
+        self.is_constrained = is_con
+        vals = _csr.assemble(self.pattern, k.detach().to(torch.float64),
+                             is_con.to(torch.uint8) if con.numel() else None)
+        return self.pattern.matrix(vals, symmetric=True)
+
+    def assemble_rhs(self, f: Tensor) -> Tensor:
+        """Global vector from element vectors; differentiable (reference base.py:428-445)."""
+        F = torch.zeros(self.n_dofs, dtype=f.dtype, device=f.device)
+        return F.index_add_(0, self.idx.ravel(), f.ravel())
+
+    # ---- incremental Newton solve
+    def solve(self, increments: Tensor | None = None, max_iter: int = 10, rtol: float = 1e-8,
+              atol: float = 1e-6, stol: float = 1e-10, cutback_factor: float = 0.5,
+              growth_factor: float = 1.1, max_cutbacks: int = 10, verbose: bool = False,
+              method: str | None = None, device: str | None = None, return_intermediate: bool = False,
+              aggregate_integration_points: bool = True, use_cached_solve: bool = False,
+              nlgeom: bool = False, alpha: float = 0.0,
+              differentiable_parameters: Tensor | Iterable[Tensor] | None = None):
+        """Quasi-static solve by load increments with automatic cutback (reference base.py:597-923).
+        Returns (u, f, flux, grad, state) at the last increment, or stacked over increments when
+        `return_intermediate`."""
+        kw = dict(dtype=self.nodes.dtype, device=self.device)
+        increments = torch.tensor([0.0, 1.0]) if increments is None else increments
+        inc = [float(v) for v in increments]
+        N = len(inc)
+        dpn = self.n_dof_per_node
+
+        m = self.integrate_mass() if alpha > 0.0 else None
+        self.stabilization_energy = torch.zeros(N, **kw)
+
+        if differentiable_parameters is None:
+            params: tuple = ()
+        elif isinstance(differentiable_parameters, Tensor):
+            params = (differentiable_parameters,)
+        else:
+            params = tuple(differentiable_parameters)
+        track = any(p.requires_grad for p in params)
+
+        B = self.compute_B()
+        con = torch.nonzero(self.constraints.ravel(), as_tuple=False).ravel()
+
+        u = torch.zeros(N, self.n_nod, dpn, **kw)
+        f = torch.zeros(N, self.n_nod, dpn, **kw)
+        flux = torch.zeros(N, self.n_int, self.n_elem, *self.n_flux, **kw)
+        grad = torch.zeros(N, self.n_int, self.n_elem, *self.n_flux, **kw)
+        grad[:] = self.initial_grad.to(**kw)
+        state = torch.zeros(N, self.n_int, self.n_elem, self.n_state, **kw)
+
+        if verbose:
+            print(f"torch-fem_b200 | solve | {type(self).__name__} | {self.n_elem:,} elem | {self.n_dofs:,} dof"
+                  f" | {describe_method(self.n_dofs, 'cuda', method)}")
+
+        self.K = torch.empty(0, device=self.device)
+        du = torch.zeros(self.n_dofs, **kw)
+
+        def make_eval_residual(F_ext, DU, de0, k_visc):
+            # loads are bound per substep so that the adjoint replay sees the right ones (base.py:704-743)
+            def eval_residual(du, i, u_prev, grad_prev, flux_prev, state_prev):
+                du_bc = du.clone()
+                du_bc[con] = DU[con]
+                k, f_i, _, _, _ = self.integrate_material(u_prev, grad_prev, flux_prev, state_prev, du_bc,
+                                                          de0, i, nlgeom)
+                if k_visc is not None:
+                    du_e = du_bc.view(-1, dpn)[self.elements].flatten(1)
+                    f_i = f_i + torch.einsum("...ij,...j->...i", k_visc, du_e)
+                    if k is not None:
+                        k = k + k_visc
+                if k is not None:
+                    self.K = self.assemble_matrix(k, con)
+                res = self.assemble_rhs(f_i) - F_ext
+                res[con] = 0.0
+                return res, self.K
+
+            return eval_residual
+
+        u_cur, f_cur = u[0].clone(), f[0].clone()
+        grad_cur, flux_cur, state_cur = grad[0].clone(), flux[0].clone(), state[0].clone()
+        energy = torch.zeros((), **kw)
+        lam = inc[0]
+        step_frac = 1.0
+        k_step = 0.0
+
+        for n in range(1, N):
+            target = inc[n]
+            span = target - lam
+            direction = math.copysign(1.0, span)
+            step_size = step_frac * abs(span)
+            min_step = abs(span) * cutback_factor ** max_cutbacks
+            while abs(target - lam) > 1e-12 * max(1.0, abs(target)):
+                step = direction * min(step_size, abs(target - lam))
+                F_ext = (lam + step) * self._neumann.ravel()
+                DU = step * self._dirichlet.ravel()
+                de0 = step * self._external_gradient
+
+                k_visc = None
+                if m is not None:
+                    k_visc = alpha / abs(step) * m
+                    if abs(step) != k_step:
+                        self.K = torch.empty(0, device=self.device)
+                    k_step = abs(step)
+
+                if track:
+                    prev = (u_cur.clone(), grad_cur.clone(), flux_cur.clone(), state_cur.clone())
+                else:
+                    prev = (u_cur.detach(), grad_cur.detach(), flux_cur.detach(), state_cur.detach())
+                cached = self.cached_solve if use_cached_solve else CachedSolve()
+                try:
+                    du = newton_solve(make_eval_residual(F_ext, DU, de0, k_visc), du.detach(), B, max_iter,
+                                      rtol, atol, stol, None, method, device, cached, use_cached_solve,
+                                      *prev, *params)
+                except RuntimeError as err:
+                    step_size = cutback_factor * abs(step)
+                    if step_size < min_step:
+                        raise RuntimeError(f"Newton-Raphson did not converge in increment {n} "
+                                           f"after {max_cutbacks} cutbacks.") from err
+                    if verbose:
+                        print(f"  increment {n}: cutback to step {step_size:.3e}")
+                    continue
+
+                # converged state (no tangent needed)
+                du_eval = du.clone()
+                du_eval[con] = DU[con]
+                _, f_i, grad_cur, flux_cur, state_cur = self.integrate_material(
+                    u_cur, grad_cur, flux_cur, state_cur, du_eval, de0, max_iter, nlgeom,
+                    compute_stiffness=False)
+                F_int = self.assemble_rhs(f_i)
+                if k_visc is not None:
+                    du_e = du_eval.view(-1, dpn)[self.elements]
+                    F_v = self.assemble_rhs(torch.einsum("...ij,...j->...i", k_visc, du_e.flatten(1)))
+                    F_int = F_int + F_v
+                    energy = energy + torch.dot(du_eval, F_v).detach()
+                f_cur = F_int.reshape(-1, dpn)
+                u_cur = u_cur + du_eval.reshape(-1, dpn)
+                du = du_eval
+                lam += step
+                step_size = min(growth_factor * step_size, abs(span))
+            step_frac = min(step_size / abs(span), 1.0) if span != 0.0 else 1.0
+            u[n], f[n], grad[n], flux[n], state[n] = u_cur, f_cur, grad_cur, flux_cur, state_cur
+            self.stabilization_energy[n] = energy
+            if verbose:
+                print(f"  increment {n}/{N - 1} done (load factor {target:g})")
+
+        out = [u, f, flux, grad, state]
+        if aggregate_integration_points:
+            out[2], out[3], out[4] = out[2].mean(dim=1), out[3].mean(dim=1), out[4].mean(dim=1)
+        out[2] = out[2].squeeze((-2, -1))
+        out[3] = out[3].squeeze((-2, -1))
+        if not track:
+            out = [t.detach() for t in out]
+        if return_intermediate:
+            return tuple(out)
+        return tuple(t[-1] for t in out)
+
+
+class Mechanics(FEM, ABC):
+    """Vector-valued (displacement) problems (reference base.py:926-1129)."""
+
+    KIND = L.KIND_MECH
+
+    @property
+    def n_dof_per_node(self) -> int:
+        return self.nodes.shape[1]
+
+    @property
+    def initial_grad(self) -> Tensor:
+        return torch.eye(self.n_flux[0])
+
+    @property
+    def forces(self) -> Tensor:
+        return self._neumann
+
+    @forces.setter
+    def forces(self, value: Tensor):
+        self._set_field("_neumann", "Forces", value, "Forces must have the same shape as nodes.")
+
+    @property
+    def displacements(self) -> Tensor:
+        return self._dirichlet
+
+    @displacements.setter
+    def displacements(self, value: Tensor):
+        self._set_field("_dirichlet", "Displacements", value, "Displacements must have the same shape as nodes.")
+
+    @property
+    def ext_strain(self) -> Tensor:
+        return self._external_gradient
+
+    @ext_strain.setter
+    def ext_strain(self, value: Tensor):
+        if value.shape != (self.n_elem, self.n_dof_per_node, self.n_dim):
+            raise ValueError("External strain must have the same shape as strains.")
+        if not torch.is_floating_point(value):
+            raise TypeError("External strain must be a floating-point tensor.")
+        self._external_gradient = value.to(self.device)
+
+    def integrate_material(self, u_prev, grad_prev, flux_prev, state_prev, du, de0, iter, nlgeom,
+                           compute_stiffness: bool = True):
+        """Gauss-point loop (reference base.py:982-1092): residual quantities in torch (differentiable),
+        element tangent matrices on kernel K1. The tangent is needed only when none is cached or the
+        material / geometry is nonlinear (same rule as base.py:1031-1033)."""
+        assert self.material is not None
+        d = self.n_flux[0]
+        nd = self.etype.nodes * self.n_dof_per_node
+        du_e = du.view(-1, self.n_dof_per_node)[self.elements].reshape(self.n_elem, -1, d).transpose(-1, -2)
+        need_k = compute_stiffness and (self.K.numel() == 0 or self.n_state != 0 or nlgeom)
+        _, B, detJ = self._ip_shape()
+        f = torch.zeros(self.n_elem, nd, dtype=du.dtype, device=du.device)
+        grads, fluxes, states, tangents = [], [], [], []
+        cl = self.char_lengths
+        for q, w in enumerate(self.etype.iweights):
+            H_inc = du_e @ B[q].transpose(-1, -2)
+            F_new = grad_prev[q] + H_inc
+            P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+            grads.append(F_new)
+            fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
+            states.append(alpha)
+            f = f + float(w) * self.compute_f(detJ[q], B[q], P).reshape(-1, nd)
+            if need_k:
+                tangents.append(ddsdde)
+        k = None
+        if need_k:
+            same = all(t is tangents[0] for t in tangents)  # elastic: one tensor for every Gauss point
+            k = self._integrate_k(tangents[0] if same else torch.stack(tangents))
+        return k, f, torch.stack(grads), torch.stack(fluxes), torch.stack(states)
+
+
+class Heat(FEM, ABC):
+    """Scalar (temperature) problems (reference base.py:1132-1286)."""
+
+    KIND = L.KIND_HEAT
+
+    @property
+    def n_dof_per_node(self) -> int:
+        return 1
+
+    @property
+    def n_flux(self) -> list[int]:
+        return [1, self.n_dim]
+
+    @property
+    def initial_grad(self) -> Tensor:
+        return torch.zeros(1)
+
+    @property
+    def heat_flux(self) -> Tensor:
+        return self._neumann
+
+    @heat_flux.setter
+    def heat_flux(self, value: Tensor):
+        if value.shape != (self.n_nod, 1):
+            raise ValueError("Heat flux must have the same shape as nodes.")
+        self._set_field("_neumann", "Heat flux", value, "Heat flux must have the same shape as nodes.")
+
+    @property
+    def temperatures(self) -> Tensor:
+        return self._dirichlet
+
+    @temperatures.setter
+    def temperatures(self, value: Tensor):
+        self._set_field("_dirichlet", "Temperatures", value, "Temperatures must have the same shape as nodes.")
+
+    def integrate_material(self, u_prev, grad_prev, flux_prev, state_prev, du, de0, iter, nlgeom,
+                           compute_stiffness: bool = True):
+        """Thermal Gauss-point loop (reference base.py:1177-1286); conductivity matrices on kernel K1."""
+        assert self.material is not None
+        nn = self.etype.nodes
+        du_e = du.view(-1, 1)[self.elements].reshape(self.n_elem, -1, 1)
+        need_k = compute_stiffness and (self.K.numel() == 0 or self.n_state != 0)
+        _, B, detJ = self._ip_shape()
+        f = torch.zeros(self.n_elem, nn, dtype=du.dtype, device=du.device)
+        grads, fluxes, states, tangents = [], [], [], []
+        cl = self.char_lengths
+        for q, w in enumerate(self.etype.iweights):
+            g_inc = torch.einsum("...ij,...jk->...ki", B[q], du_e)
+            grads.append(grad_prev[q] + g_inc)
+            flux_q, state_q, kappa = self.material.step(g_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+            fluxes.append(flux_q)
+            states.append(state_q)
+            f = f + float(w) * self.compute_f(detJ[q], B[q], flux_q).reshape(-1, nn)
+            if need_k:
+                tangents.append(kappa)
+        k = None
+        if need_k:
+            same = all(t is tangents[0] for t in tangents)
+            k = self._integrate_k(tangents[0] if same else torch.stack(tangents))
+        return k, f, torch.stack(grads), torch.stack(fluxes), torch.stack(states)

@@ -1,0 +1,178 @@
+"""Material-tangent interface of the hot path.
+
+The contract is the reference's (src/torchfem/materials/base.py:31-91):
+`Material.step(H_inc, F, stress, state, de0, cl, iter) -> (stress_new, state_new, ddsdde)` evaluated per
+Gauss point on tensors batched over elements, `vectorize(n_elem)`, `rotate(R)`, attributes `n_state`,
+`is_vectorized`, `rho`. The tangent `ddsdde` ([n_elem,d,d,d,d] mechanics, [n_elem,d,d] heat) is what the
+CUDA integration kernel K1 consumes; the stress update itself stays in torch because the adjoint
+differentiates the residual through it (reference sparse.py:689-705).
+
+Materials on the path: isotropic elasticity (3-D, plane stress, plane strain; reference
+materials/elasticity.py:11-241), hyperelasticity from a strain-energy callable (materials/hyperelasticity.py:
+66-127, 309-355) and isotropic conductivity (materials/conductivity.py:11-240). Any other object with the
+same `step` contract (e.g. a plasticity model) plugs into the models unchanged.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Callable
+
+import torch
+from torch import Tensor
+from torch.func import jacrev, vmap
+
+
+class Material:
+    """Base class: bookkeeping of batched parameters (reference materials/base.py:10-103)."""
+
+    n_state: int = 0
+    is_vectorized: bool = False
+
+    def __init__(self):
+        self.n_state = 0
+        self.is_vectorized = False
+        self.rho = torch.tensor(1.0)
+
+    def vectorize(self, n_elem: int) -> "Material":
+        """Copy whose tensor attributes carry one entry per element (shared if already batched)."""
+        if self.is_vectorized:
+            return self
+        out = copy.copy(self)
+        for name, val in list(vars(out).items()):
+            if isinstance(val, Tensor):
+                setattr(out, name, val.repeat(n_elem, *([1] * val.dim())))
+        out.is_vectorized = True
+        return out
+
+    def to(self, device) -> "Material":
+        """Copy with every tensor attribute on `device` (the models keep their material on the GPU)."""
+        out = copy.copy(self)
+        for name, val in list(vars(out).items()):
+            if isinstance(val, Tensor):
+                setattr(out, name, val.to(device))
+        return out
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        raise NotImplementedError
+
+    def rotate(self, R: Tensor) -> "Material":
+        return self
+
+
+def _isotropic_tensor(lbd: Tensor, G: Tensor, d: int) -> Tensor:
+    """C_ijkl = lbd d_ij d_kl + G (d_ik d_jl + d_il d_jk), batched over the leading dims of lbd."""
+    eye = torch.eye(d, dtype=lbd.dtype, device=lbd.device)
+    vol = torch.einsum("ij,kl->ijkl", eye, eye)
+    sym = torch.einsum("ik,jl->ijkl", eye, eye) + torch.einsum("il,jk->ijkl", eye, eye)
+    return lbd[..., None, None, None, None] * vol + G[..., None, None, None, None] * sym
+
+
+class IsotropicElasticity3D(Material):
+    """Small-strain isotropic elasticity; `C` is [..., 3,3,3,3] (reference elasticity.py:11-127)."""
+
+    def __init__(self, E, nu, rho=1.0):
+        self.E = torch.as_tensor(E)
+        self.nu = torch.as_tensor(nu)
+        self.rho = torch.as_tensor(rho)
+        self.n_state = 0
+        self.is_vectorized = self.E.dim() > 0
+        self.lbd = self.E * self.nu / ((1.0 + self.nu) * (1.0 - 2.0 * self.nu))
+        self.G = self.E / (2.0 * (1.0 + self.nu))
+        self.C = _isotropic_tensor(self.lbd, self.G, 3)
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        """sigma_{n+1} = sigma_n + C : (sym(dH) - de0); tangent = C (elasticity.py:119-127)."""
+        de = 0.5 * (H_inc + H_inc.transpose(-1, -2)) - de0
+        return stress + torch.einsum("...ijkl,...kl->...ij", self.C, de), state, self.C
+
+
+class IsotropicElasticityPlaneStress(IsotropicElasticity3D):
+    """sigma_33 = 0: C_0000 = C_1111 = E/(1-nu^2), C_0011 = nu E/(1-nu^2), shear E/(2(1+nu))
+    (reference elasticity.py:130-185)."""
+
+    def __init__(self, E, nu, rho=1.0):
+        super().__init__(E, nu, rho)
+        f = self.E / (1.0 - self.nu ** 2)
+        self.C = _isotropic_tensor(f * self.nu, 0.5 * f * (1.0 - self.nu), 2)
+
+
+class IsotropicElasticityPlaneStrain(IsotropicElasticity3D):
+    """eps_33 = 0: the in-plane block of the 3-D tensor (reference elasticity.py:188-241)."""
+
+    def __init__(self, E, nu, rho=1.0):
+        super().__init__(E, nu, rho)
+        self.C = _isotropic_tensor(self.lbd, self.G, 2)
+
+
+class Hyperelastic3D(Material):
+    """Hyperelasticity from a strain-energy density psi(F, params): P = dpsi/dF and the tangent
+    d2psi/dF2 by forward-over-reverse autodiff, batched with vmap (reference hyperelasticity.py:66-127)."""
+
+    def __init__(self, psi: Callable, params, rho=1.0):
+        self.psi = psi
+        self.params = torch.as_tensor(params)
+        self.n_state = 0
+        self.rho = torch.as_tensor(rho)
+        self.is_vectorized = self.params.dim() > 1
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        with torch.enable_grad():
+            F_new = (F + H_inc).requires_grad_(True)
+            P = vmap(jacrev(self.psi))(F_new, self.params)
+            tangent = vmap(jacrev(jacrev(self.psi)))(F_new, self.params)
+        return P, state, tangent
+
+
+class HyperelasticPlaneStrain(Hyperelastic3D):
+    """Plane strain: psi is evaluated on the 3x3 embedding diag(F2d, 1), so stress and tangent are the
+    in-plane derivatives (reference hyperelasticity.py:309-355)."""
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        def psi2(F2, p):
+            F3 = torch.zeros(3, 3, dtype=F2.dtype, device=F2.device)
+            F3 = F3 + torch.nn.functional.pad(F2, (0, 1, 0, 1))
+            F3 = F3 + torch.diag(torch.tensor([0.0, 0.0, 1.0], dtype=F2.dtype, device=F2.device))
+            return self.psi(F3, p)
+
+        with torch.enable_grad():
+            F_new = (F + H_inc).requires_grad_(True)
+            P = vmap(jacrev(psi2))(F_new, self.params)
+            tangent = vmap(jacrev(jacrev(psi2)))(F_new, self.params)
+        return P, state, tangent
+
+
+class _IsotropicConductivity(Material):
+    """Fourier conduction q = kappa grad T; `KAPPA` is [..., d, d] (reference conductivity.py:11-240)."""
+
+    _dim = 3
+
+    def __init__(self, kappa, rho=1.0):
+        self.kappa = torch.as_tensor(kappa)
+        self.rho = torch.as_tensor(rho)
+        self.n_state = 0
+        self.is_vectorized = self.kappa.dim() > 0
+        self.KAPPA = self.kappa[..., None, None] * torch.eye(self._dim)
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        """flux_{n+1} = flux_n + KAPPA (dgrad - de0) on [..., 1, d] rows; tangent = KAPPA."""
+        flux = stress + torch.einsum("...ij,...kj->...ki", self.KAPPA, H_inc - de0)
+        return flux, state, self.KAPPA
+
+
+class IsotropicConductivity3D(_IsotropicConductivity):
+    _dim = 3
+
+
+class IsotropicConductivity2D(_IsotropicConductivity):
+    _dim = 2
+
+
+class IsotropicConductivity1D(_IsotropicConductivity):
+    _dim = 1
+
+
+__all__ = [
+    "Material", "IsotropicElasticity3D", "IsotropicElasticityPlaneStress", "IsotropicElasticityPlaneStrain",
+    "Hyperelastic3D", "HyperelasticPlaneStrain", "IsotropicConductivity3D", "IsotropicConductivity2D",
+    "IsotropicConductivity1D",
+]

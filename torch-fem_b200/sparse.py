@@ -1,0 +1,249 @@
+"""Linear and Newton solves with adjoint autograd — the drop-in for the reference's `torchfem.sparse`
+(src/torchfem/sparse.py) on the B200 path.
+
+Public names, signatures, error types and messages follow the reference:
+`sparse_solve` (sparse.py:271-347), `differentiable_sparse_solve` / `Solve` (:131-268),
+`newton_solve` / `NewtonRaphsonAdjoint` (:517-795), `CachedSolve` (:103-128), `resolve_method`,
+`describe_method`, `available_backends` (:43-100).
+
+What is different underneath: the matrix is a device CSR (`csr.CSRMatrix`, or any torch sparse tensor,
+which is converted), iterative methods run the fused Jacobi-PCG / MINRES kernels of libtfem_b200.so
+(`csr.krylov_solve`) instead of CuPy, and nothing ever leaves the GPU. `method="spsolve"` (the policy
+default below 10,000 DOFs, sparse.py:78-81) is a dense LU of the small system on the GPU
+(`torch.linalg.solve`); a sparse direct factorisation is out of scope. There is no CPU path.
+"""
+from __future__ import annotations
+
+from collections.abc import Callable
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import csr as _csr
+from .csr import CSRMatrix, JacobiPreconditioner
+
+available_backends = ["tfem_b200"]
+
+METHODS = ["spsolve", "minres", "cg", "pardiso", "amgx"]
+DIRECT_LIMIT = 10000  # reference policy: below this many DOFs solve directly (sparse.py:78)
+
+ERR_AMGX_MISSING = "AmgX is not available in torch-fem_b200 (AMG preconditioning is out of scope of this path)."
+ERR_NO_CPU = ("torch-fem_b200 has no CPU path: pass CUDA tensors (e.g. torch.set_default_device('cuda')). "
+              "The CPU oracle under oracle/ is test infrastructure only.")
+
+
+def resolve_method(n_dofs: int, device: str, method: str | None) -> str:
+    """Backend `sparse_solve` uses for a system of this size (policy of reference sparse.py:74-84;
+    AmgX / pardiso are never auto-selected here because they do not exist on this path)."""
+    if method is not None:
+        return method
+    return "spsolve" if n_dofs < DIRECT_LIMIT else "minres"
+
+
+def describe_method(n_dofs: int, device: str, method: str | None) -> str:
+    """`<method> | <kind> | <library> | <device>` like reference sparse.py:87-100."""
+    resolved = resolve_method(n_dofs, device, method)
+    kind = "iterative | jacobi" if resolved in ("minres", "cg") else "direct"
+    library = "torch.linalg (dense LU)" if resolved == "spsolve" else "tfem_b200"
+    return f"{resolved} | {kind} | {library} | {device}"
+
+
+class CachedSolve:
+    """Previous forward / adjoint solutions used as warm starts (reference sparse.py:103-128)."""
+
+    def __init__(self, previous_x: Tensor | None = None, previous_grad: Tensor | None = None) -> None:
+        self.previous_x = previous_x
+        self.previous_grad = previous_grad
+
+    def update_grad(self, grad: Tensor | None) -> None:
+        self.previous_grad = None if grad is None else grad.detach().clone()
+
+    def update_x(self, x: Tensor | None) -> None:
+        self.previous_x = None if x is None else x.detach().clone()
+
+
+def _as_csr(A) -> CSRMatrix:
+    if isinstance(A, CSRMatrix):
+        return A
+    if not A.is_cuda:
+        raise RuntimeError(ERR_NO_CPU)
+    return CSRMatrix.from_coo(A)
+
+
+def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, device: str | None = None,
+                 method: str | None = None, M=None, x0: Tensor | None = None):
+    """Solve A x = b. Returns `(x, M)`: x is a new tensor with b's dtype on b's device; M is the Jacobi
+    preconditioner built or reused by an iterative solve (None for a direct one), to be passed back in
+    on later calls exactly like the reference's `M` (sparse.py:570,607,671).
+
+    Raises ValueError for a non-square A or an unknown method and RuntimeError when the Krylov solver
+    fails — the type `FEM.solve` catches to cut a load step back (reference base.py:831).
+    """
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise ValueError("A should be a square 2D matrix.")
+    if method is not None and method not in METHODS:
+        raise ValueError(f"Method {method} is not supported. "
+                         "Choose from 'spsolve', 'minres', 'cg', 'pardiso', or 'amgx'.")
+    if device is not None and torch.device(device).type != "cuda":
+        raise RuntimeError(ERR_NO_CPU)
+    n = int(A.shape[0])
+    out_device = b.device
+    Ac = _as_csr(A)
+    rhs = b.detach().to(device=Ac.device, dtype=torch.float64).contiguous()
+    method = resolve_method(n, "cuda", method)
+
+    if method == "pardiso":
+        raise RuntimeError("Pardiso backend is not available on GPU.")
+    if method == "amgx":
+        raise RuntimeError(ERR_AMGX_MISSING)
+    if method == "spsolve":
+        if n > 4 * DIRECT_LIMIT:
+            raise RuntimeError(f"spsolve is a dense LU here and is limited to {4 * DIRECT_LIMIT} DOFs; "
+                               "use method='cg' or 'minres'.")
+        x = torch.linalg.solve(Ac.to_dense(), rhs)
+        M_out = None
+    else:
+        if M is not None and not isinstance(M, JacobiPreconditioner):
+            raise TypeError("M must be a JacobiPreconditioner returned by a previous sparse_solve")
+        if x0 is not None:
+            x0 = x0.detach()
+        x, M_out, _ = _csr.krylov_solve(Ac, rhs, method=method, rtol=stol, x0=x0, M=M)
+    return x.to(device=out_device, dtype=b.dtype), M_out
+
+
+class Solve(Function):
+    """Linear solve with the adjoint rule  dL/db = A^-T g,  dL/dA_ij = -(A^-T g)_i x_j  evaluated on A's
+    sparsity pattern only (reference sparse.py:131-243)."""
+
+    @staticmethod
+    def forward(A, b, B=None, stol=1e-10, device=None, method=None, M=None, cached_solve=None,
+                update_cache=False):
+        x0 = cached_solve.previous_x if cached_solve is not None else None
+        x, M = sparse_solve(A, b, B, stol, device, method, M, x0)
+        if update_cache and cached_solve is not None:
+            cached_solve.update_x(x)
+        return x, M
+
+    @staticmethod
+    def setup_context(ctx, inputs, output) -> None:
+        A, b, B, stol, device, method, M, cached_solve, update_cache = inputs
+        x, M_used = output
+        if isinstance(A, Tensor):
+            ctx.save_for_backward(A, x)
+            ctx.A_obj = None
+        else:
+            ctx.save_for_backward(x)
+            ctx.A_obj = A
+        ctx.cfg = (B, stol, device, method, M_used, cached_solve, update_cache)
+
+    @staticmethod
+    def backward(ctx, grad_x, _grad_M=None):
+        B, stol, device, method, M, cached_solve, update_cache = ctx.cfg
+        if ctx.A_obj is None:
+            A, x = ctx.saved_tensors
+        else:
+            (x,) = ctx.saved_tensors
+            A = ctx.A_obj
+        x0 = cached_solve.previous_grad if cached_solve is not None else None
+        Ac = _as_csr(A)
+        # a Jacobi preconditioner is the same for A and A^T (same diagonal)
+        gradb, _ = sparse_solve(Ac.T, grad_x, B, stol, device, method, M, x0=x0)
+        gradA = None
+        if isinstance(A, Tensor) and ctx.needs_input_grad[0]:
+            if A.is_coalesced():  # CSR order == COO order -> kernel K7
+                val = _csr.adjoint_matrix_grad(Ac, gradb.contiguous(), x.detach().contiguous())
+                idx = A._indices()
+            else:
+                idx = A._indices()
+                val = -gradb[idx[0]] * x[idx[1]]
+            with torch.sparse.check_sparse_tensor_invariants(False):
+                gradA = torch.sparse_coo_tensor(idx, val.to(A.dtype), A.shape, is_coalesced=A.is_coalesced())
+        if update_cache and cached_solve is not None:
+            cached_solve.update_grad(gradb)
+        return gradA, gradb, None, None, None, None, None, None, None
+
+
+def differentiable_sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10,
+                                device: str | None = None, method: str | None = None, M=None,
+                                cached_solve: CachedSolve | None = None, update_cache: bool = False) -> Tensor:
+    """`sparse_solve` with gradients w.r.t. A (a torch sparse tensor) and b (reference sparse.py:246-268)."""
+    x, _ = Solve.apply(A, b, B, stol, device, method, M, cached_solve, update_cache)
+    if x is None:
+        raise RuntimeError("Solve.apply returned None, expected a Tensor.")
+    return x
+
+
+class NewtonRaphsonAdjoint(Function):
+    """Newton iterations on `eval_residual(du, iter, u_prev, grad_prev, flux_prev, state_prev) ->
+    (residual, K)` with an implicit-function-theorem backward (reference sparse.py:517-724):
+    solve K^T lambda = dL/ddu once, re-evaluate the residual at the converged state with autograd on,
+    and pull -lambda back through it to the previous state and the declared parameters."""
+
+    @staticmethod
+    def forward(ctx, eval_residual: Callable, du: Tensor, B, max_iter: int, rtol: float, atol: float,
+                stol: float, report, method=None, device=None, cached_solve=None, update_cache=False,
+                u_prev=None, grad_prev=None, flux_prev=None, state_prev=None, *parameters: Tensor):
+        M = None
+        converged_iter = max_iter - 1
+        res_norm = res_norm0 = None
+        K = None
+        for i in range(max_iter):
+            residual, K = eval_residual(du, i, u_prev, grad_prev, flux_prev, state_prev)
+            res_norm = torch.linalg.norm(residual)
+            if i == 0:
+                res_norm0 = res_norm
+            if report is not None:
+                report.iteration(i, res_norm)
+            if res_norm < rtol * res_norm0 or res_norm < atol:
+                converged_iter = i
+                break
+            if not torch.isfinite(res_norm):
+                break
+            x0 = None
+            if i == 0 and cached_solve is not None and cached_solve.previous_x is not None:
+                x0 = cached_solve.previous_x
+            du_i, M = sparse_solve(K, residual, B, stol, device, method, M, x0=x0)
+            if i == 0 and update_cache and cached_solve is not None:
+                cached_solve.update_x(du_i)
+            du = du - du_i
+        if res_norm is None or not (res_norm < rtol * res_norm0 or res_norm < atol):
+            raise RuntimeError("Newton-Raphson iteration did not converge.")
+        ctx.save_for_backward(du, u_prev, grad_prev, flux_prev, state_prev, *parameters)
+        ctx.K = K  # CSRMatrix (not a tensor): kept on the context
+        ctx.cfg = (B, M, stol, device, method, eval_residual, cached_solve, update_cache, converged_iter)
+        return du
+
+    @staticmethod
+    def backward(ctx, grad_du):
+        du, u_prev, grad_prev, flux_prev, state_prev, *parameters = ctx.saved_tensors
+        B, M, stol, device, method, eval_residual, cached_solve, update_cache, converged_iter = ctx.cfg
+        K = ctx.K
+        x0 = None
+        if cached_solve is not None and cached_solve.previous_grad is not None:
+            x0 = cached_solve.previous_grad
+        lam, _ = sparse_solve(K.T, grad_du, B, stol, device, method, M, x0=x0)
+        if update_cache and cached_solve is not None:
+            cached_solve.update_grad(lam)
+        du_local = du.detach().requires_grad_(True)
+        prev_local = tuple(p.detach().requires_grad_(True) for p in (u_prev, grad_prev, flux_prev, state_prev))
+        with torch.enable_grad():
+            residual, _ = eval_residual(du_local, converged_iter, *prev_local)
+        inputs = (du_local, *prev_local, *parameters)
+        grads = torch.autograd.grad(residual, inputs, grad_outputs=-lam, allow_unused=True, retain_graph=True)
+        return (None,) * 12 + tuple(grads[1:5]) + tuple(grads[5:])
+
+
+def newton_solve(eval_residual: Callable, du: Tensor, B, max_iter: int, rtol: float, atol: float,
+                 stol: float, report, method: str | None = None, device: str | None = None,
+                 cached_solve: CachedSolve | None = None, update_cache: bool = False,
+                 u_prev: Tensor | None = None, grad_prev: Tensor | None = None,
+                 flux_prev: Tensor | None = None, state_prev: Tensor | None = None,
+                 *parameters: Tensor) -> Tensor:
+    """Adjoint-safe Newton solve; same argument list as reference sparse.py:727-795."""
+    out = NewtonRaphsonAdjoint.apply(eval_residual, du, B, max_iter, rtol, atol, stol, report, method,
+                                     device, cached_solve, update_cache, u_prev, grad_prev, flux_prev,
+                                     state_prev, *parameters)
+    if out is None:
+        raise RuntimeError("Solve.apply returned None, expected a Tensor.")
+    return out
