@@ -294,6 +294,35 @@ def run_ours(args):
     torch.cuda.synchronize()
     solve_ms = 1e3 * (time.perf_counter() - t_s)
 
+    # ---- the same through the public model API (`Solid.solve`, the call a torch-fem user makes):
+    # the model (mesh + pattern) is setup; per step the material tangent and the boundary conditions
+    # arrive from pinned host memory and the displacement field goes back to the host.
+    api = None
+    if not args.no_api:
+        from torchfem_b200.materials import IsotropicElasticity3D
+
+        state.clear()
+        del A, rhs, x, x2, xs, ys
+        torch.cuda.empty_cache()
+        model = T.Solid(nodes, elements, IsotropicElasticity3D(E=1000.0, nu=0.3))
+        model.pattern = pattern  # reuse the setup product instead of building it twice
+        con_bool_h = con_h.pin_memory()
+        disp2_h = disp_h.reshape(-1, 3)
+
+        def step_api():
+            model.material.C = C_h.to(device, non_blocking=True)
+            model.constraints = con_bool_h.to(device, non_blocking=True)
+            model.displacements = disp2_h.to(device, non_blocking=True)
+            u, *_ = model.solve(method="cg", stol=RTOL, rtol=1e-6)
+            return u.cpu()
+
+        ms_api, u_api = timed(step_api, max(1, min(args.steps, 2)), 1)
+        err = float((u_api.ravel() - u_h.ravel()).norm() / u_h.norm())
+        api = {"value": n_dofs / (ms_api / 1e3), "unit": UNIT, "ms_per_step": ms_api,
+               "h2d_bytes_per_step": int(C_h.numel() * 8 + con_bool_h.numel() + disp2_h.numel() * 8),
+               "d2h_bytes_per_step": int(d2h), "call": "Solid.solve(method='cg', stol=1e-8)",
+               "rel_diff_vs_kernel_path": err}
+
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N=1 only
     cpu = None
     if not args.no_cpu_baseline:
@@ -324,7 +353,9 @@ def run_ours(args):
                                                                  "pcg_solve": solve_ms,
                                                                  "per_cg_iteration": solve_ms / max(1, info2["iterations"])}},
         "e2e": {"value": n_dofs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
+                "call": "C-ABI ops on host buffers (H2D inputs -> integrate -> assemble -> PCG -> D2H u)",
+                "public_api": api},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_sell_spmv (SELL-32 SpMV, fp64 vals + int32 cols, 12 B/nnz)",
                      "csr_chunk_kernel_ms": spmv_csr_ms,
@@ -346,6 +377,7 @@ def main():
     ap.add_argument("--edge", type=int, default=150, help="elements per cube edge (150 = BASELINE configs[1])")
     ap.add_argument("--cpu-edge", type=int, default=40, help="elements per edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api", action="store_true", help="skip the Solid.solve end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -348,14 +348,14 @@ def linear_to_quadratic(nodes: Tensor, elements: Tensor) -> tuple[Tensor, Tensor
     dev = elements.device
     el = elements.detach().cpu()
     nd = nodes.detach().cpu()
-    edges = linear_etype(nodes, elements).edges
+    edges = linear_etype(nodes, elements).edges.cpu()
     ev = torch.sort(el[:, edges].reshape(-1, 2), dim=1).values.numpy()
     ev = np.ascontiguousarray(ev)
     raw = ev.view(np.dtype((np.void, ev.dtype.itemsize * 2)))
     _, first, inverse = np.unique(raw, return_index=True, return_inverse=True)
-    uniq = torch.as_tensor(ev[first])
+    uniq = torch.from_numpy(np.ascontiguousarray(ev[first]))  # from_numpy: always a host tensor
     mids = (nd[uniq[:, 0]] + nd[uniq[:, 1]]) / 2.0
     new_nodes = torch.cat([nd, mids], dim=0)
-    mid_ids = torch.as_tensor(inverse.reshape(el.shape[0], -1)) + nd.shape[0]
+    mid_ids = torch.from_numpy(np.ascontiguousarray(inverse.reshape(el.shape[0], -1))) + nd.shape[0]
     new_elements = torch.cat([el, mid_ids], dim=1)
     return new_nodes.to(nodes.device), new_elements.to(dev)
