@@ -186,6 +186,30 @@ int tfem_krylov_solve(int method, int64_t n_rows, const int64_t* slice_ptr_dev,
                       double atol, int64_t maxiter, int check_every, double* x_dev, double* work_dev,
                       double* info_host, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU Jacobi-PCG, one call per stage. The reference has no multi-GPU path; the partitioning
+ * (contiguous node blocks, ghost elements integrated redundantly) is described in DESIGN.md §multi-GPU.
+ * The host (torch-fem_b200/distributed.py) interleaves the NCCL collectives:
+ *   stage 0  init: x = 0, r = b, p = dinv r              red <- local (r.r, r.z, b.b)     -> all-reduce(3)
+ *   stage 1  scalars after init (tolerance, convergence of the zero iterate)
+ *   -- per iteration: halo exchange of p, then
+ *   stage 2  q = A p over all local rows                  red <- local p.q (owned rows)    -> all-reduce(1)
+ *   stage 3  scalars (p.q)
+ *   stage 4  x += alpha p ; r -= alpha q                  red <- local (r.r, r.z)          -> all-reduce(2)
+ *   stage 5  scalars (alpha, beta, iteration count, convergence flag)
+ *   stage 6  p = dinv r + beta p
+ * Vectors have n_local entries: owned rows [row_lo, row_lo + n_owned) plus halo rows; b, dinv, x are
+ * indexed like the local rows. work_dev as in tfem_krylov_solve (sized for n_local); red_dev: double[4]. */
+int tfem_cg_stage(int stage, int64_t n_local, int64_t row_lo, int64_t n_owned,
+                  const int64_t* slice_ptr_dev, const int32_t* sell_cols_dev,
+                  const double* sell_vals_dev, const double* dinv_dev, const double* b_dev,
+                  double* x_dev, double* work_dev, double* red_dev, double rtol, double atol,
+                  void* stream);
+/* Offset (in doubles) of a vector inside work_dev: which = 0 r, 1 p, 2 q, 3 device scalars. */
+int64_t tfem_krylov_work_offset(int64_t n_rows, int which);
+/* info_host[4] <- {iterations, ||r||_2, ||b||_2, done flag (0 running, 1 converged, 2 breakdown)}; synchronises. */
+int tfem_krylov_state(int64_t n_rows, const double* work_dev, double* info_host, void* stream);
+
 /* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
  * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */
 int tfem_adjoint_matrix_grad(int64_t n_rows, const int64_t* indptr_dev, const int32_t* indices_dev,

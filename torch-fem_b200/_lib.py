@@ -48,6 +48,9 @@ _SIGNATURES = {
     "tfem_sell_fill": (c_int, [c_int64] + [c_void_p] * 7),
     "tfem_sell_spmv": (c_int, [c_int64] + [c_void_p] * 6),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
+    "tfem_cg_stage": (c_int, [c_int, c_int64, c_int64, c_int64] + [c_void_p] * 8 + [c_double, c_double, c_void_p]),
+    "tfem_krylov_work_offset": (c_int64, [c_int64, c_int]),
+    "tfem_krylov_state": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED = tuple(_SIGNATURES)

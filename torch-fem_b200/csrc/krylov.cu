@@ -116,6 +116,7 @@ struct Sell {
   const int64_t* slice_ptr;  // [n_slices+1], element offsets (multiples of 64)
   const int32_t* cols;
   const double* vals;
+  int64_t dot_lo = 0, dot_hi = INT64_MAX;  // rows that enter the fused x.y dot (owned rows of a rank)
 };
 
 __global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kSellWarps * 32)
     const int64_t row = t * 32 + lane;
     if (row < A.n) {
       y[row] = acc;
-      if (DOT) dot = fma(acc, __ldg(x + row), dot);
+      if (DOT && row >= A.dot_lo && row < A.dot_hi) dot = fma(acc, __ldg(x + row), dot);
     }
   }
   if (DOT) {
@@ -227,11 +228,47 @@ int launch_sell(const Sell& A, const double* x, double* y, const double* sc, dou
 }
 
 // ------------------------------------------------------------------------------------------ CG
+// Scalar recurrences. On one GPU the last CTA of the producing kernel runs them in place; across ranks
+// the producing kernel only writes its local sums to `red`, the host all-reduces `red` (NCCL) and
+// k_cg_scalars runs the same code on the reduced values, identically on every rank.
+__device__ __forceinline__ void cg_scalars_init(double* sc, const double* tot, double rtol, double atol) {
+  const double bnrm = sqrt(tot[2]);
+  const double tol = fmax(atol, rtol * bnrm);
+  sc[SC_RR] = tot[0];
+  sc[SC_RHO] = tot[1];
+  sc[SC_RHO_PREV] = tot[1];
+  sc[SC_BNRM] = bnrm;
+  sc[SC_TOL] = tol;
+  sc[SC_ITERS] = 0.0;
+  sc[SC_DONE] = (bnrm == 0.0 || sqrt(tot[0]) < tol) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ void cg_scalars_update(double* sc, const double* tot) {
+  const double rho_prev = sc[SC_RHO];
+  sc[SC_ALPHA] = rho_prev / sc[SC_PQ];
+  sc[SC_RHO_PREV] = rho_prev;
+  sc[SC_RHO] = tot[1];
+  sc[SC_RR] = tot[0];
+  sc[SC_BETA] = tot[1] / rho_prev;
+  sc[SC_ITERS] += 1.0;
+  if (!isfinite(tot[0])) sc[SC_DONE] = 2.0;  // breakdown (scipy would iterate on NaNs to maxiter)
+  else if (sqrt(tot[0]) < sc[SC_TOL]) sc[SC_DONE] = 1.0;
+}
+
+// which: 0 after init (red = rr, rho, bb), 1 after SpMV (red = p.q), 2 after update (red = rr, rho)
+__global__ void k_cg_scalars(int which, double* sc, const double* red, double rtol, double atol) {
+  if (which == 0) cg_scalars_init(sc, red, rtol, atol);
+  else if (sc[SC_DONE] != 0.0) return;
+  else if (which == 1) sc[SC_PQ] = red[0];
+  else cg_scalars_update(sc, red);
+}
+
 // r = b - q (q = A x0) or r = b ; p = z = dinv*r ; rr = r.r ; rho = r.z ; bb = b.b
 __global__ void __launch_bounds__(kVecThreads)
     k_cg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q_or_null,
               const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
-              double* sc, double rtol, double atol, double* partials, unsigned int* ticket) {
+              double* sc, double rtol, double atol, double* partials, unsigned int* ticket,
+              double* red) {
   __shared__ double s_red[kVecThreads / 32];
   double rr = 0.0, rho = 0.0, bb = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
@@ -250,15 +287,8 @@ __global__ void __launch_bounds__(kVecThreads)
   mine[1] = block_sum<kVecThreads>(rho, s_red);
   mine[2] = block_sum<kVecThreads>(bb, s_red);
   if (publish_and_reduce<3>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    const double bnrm = sqrt(tot[2]);
-    const double tol = fmax(atol, rtol * bnrm);
-    sc[SC_RR] = tot[0];
-    sc[SC_RHO] = tot[1];
-    sc[SC_RHO_PREV] = tot[1];
-    sc[SC_BNRM] = bnrm;
-    sc[SC_TOL] = tol;
-    sc[SC_ITERS] = 0.0;
-    sc[SC_DONE] = (bnrm == 0.0 || sqrt(tot[0]) < tol) ? 1.0 : 0.0;
+    if (red) { red[0] = tot[0]; red[1] = tot[1]; red[2] = tot[2]; }
+    else cg_scalars_init(sc, tot, rtol, atol);
   }
 }
 
@@ -266,7 +296,7 @@ __global__ void __launch_bounds__(kVecThreads)
 __global__ void __launch_bounds__(kVecThreads)
     k_cg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q,
                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-                double* sc, double* partials, unsigned int* ticket) {
+                double* sc, double* partials, unsigned int* ticket, double* red) {
   __shared__ double s_red[kVecThreads / 32];
   if (sc[SC_DONE] != 0.0) return;
   const double pq = sc[SC_PQ];
@@ -285,15 +315,8 @@ __global__ void __launch_bounds__(kVecThreads)
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   mine[1] = block_sum<kVecThreads>(rho, s_red);
   if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    const double rho_prev = sc[SC_RHO];
-    sc[SC_RHO_PREV] = rho_prev;
-    sc[SC_RHO] = tot[1];
-    sc[SC_RR] = tot[0];
-    sc[SC_ALPHA] = alpha;
-    sc[SC_BETA] = tot[1] / rho_prev;
-    sc[SC_ITERS] += 1.0;
-    if (!isfinite(tot[0])) sc[SC_DONE] = 2.0;  // breakdown (scipy would iterate on NaNs to maxiter)
-    else if (sqrt(tot[0]) < sc[SC_TOL]) sc[SC_DONE] = 1.0;
+    if (red) { red[0] = tot[0]; red[1] = tot[1]; }
+    else cg_scalars_update(sc, tot);
   }
 }
 
@@ -793,7 +816,7 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr
   double sc_host[SC_COUNT];
   int64_t issued = 0;
   if (method == TFEM_METHOD_CG) {
-    k_cg_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r, w.p, w.sc, rtol, atol, w.partials, w.ticket);
+    k_cg_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r, w.p, w.sc, rtol, atol, w.partials, w.ticket, nullptr);
     TFEM_LAUNCH_CHECK();
     launches += 2;
     while (true) {
@@ -804,7 +827,7 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr
       for (int64_t it = 0; it < batch; ++it) {
         int rc = launch_sell<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
         if (rc != TFEM_OK) return rc;
-        k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket);
+        k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket, nullptr);
         k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
       }
       TFEM_LAUNCH_CHECK();
@@ -853,5 +876,78 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr
     set_last_error("not converged", "iteration limit reached");
     return TFEM_ERR_NOT_CONVERGED;
   }
+  return TFEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU CG, one call per stage (the host interleaves NCCL collectives between stages; see
+// torch-fem_b200/distributed.py). Vectors have n_local entries (owned rows [row_lo, row_lo+n_owned) plus
+// halo rows); vector kernels touch the owned range only, the SpMV runs over all local rows and its fused
+// dot covers the owned rows. `red_dev` (double[4]) carries local sums out and reduced sums back in.
+extern "C" int tfem_cg_stage(int stage, int64_t n_local, int64_t row_lo, int64_t n_owned,
+                             const int64_t* slice_ptr, const int32_t* sell_cols,
+                             const double* sell_vals, const double* dinv, const double* b, double* x,
+                             double* work, double* red, double rtol, double atol, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(work && red && n_local > 0 && n_owned > 0 && row_lo >= 0 && row_lo + n_owned <= n_local,
+               "cg_stage: bad arguments");
+  Work w = carve(work, n_local);
+  const int vg = vec_grid(n_owned);
+  const int64_t o = row_lo;
+  switch (stage) {
+    case 0:  // reset state, x = 0, r = b, p = dinv r ; red <- (rr, rho, bb)
+      TFEM_REQUIRE(dinv && b && x, "cg_stage: null pointer");
+      TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
+      TFEM_CUDA(cudaMemsetAsync(w.p, 0, n_local * sizeof(double), st));
+      k_copy_or_zero<<<vg, kVecThreads, 0, st>>>(n_owned, nullptr, x + o);
+      k_cg_init<<<vg, kVecThreads, 0, st>>>(n_owned, b + o, nullptr, dinv + o, w.r + o, w.p + o, w.sc, rtol,
+                                           atol, w.partials, w.ticket, red);
+      break;
+    case 1:
+    case 3:
+    case 5:  // scalar recurrences on the all-reduced sums
+      k_cg_scalars<<<1, 1, 0, st>>>(stage / 2, w.sc, red, rtol, atol);
+      break;
+    case 2: {  // q = A p (all local rows), red <- p.q over owned rows
+      TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals, "cg_stage: null pointer");
+      Sell A{n_local, (n_local + 31) / 32, slice_ptr, sell_cols, sell_vals, row_lo, row_lo + n_owned};
+      int rc = launch_sell<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, red, st);
+      if (rc != TFEM_OK) return rc;
+      break;
+    }
+    case 4:  // x += alpha p ; r -= alpha q ; red <- (rr, rho)
+      TFEM_REQUIRE(dinv && x, "cg_stage: null pointer");
+      k_cg_update<<<vg, kVecThreads, 0, st>>>(n_owned, w.p + o, w.q + o, dinv + o, x + o, w.r + o, w.sc,
+                                             w.partials, w.ticket, red);
+      break;
+    case 6:  // p = dinv r + beta p
+      TFEM_REQUIRE(dinv, "cg_stage: null pointer");
+      k_cg_direction<<<vg, kVecThreads, 0, st>>>(n_owned, w.r + o, dinv + o, w.p + o, w.sc);
+      break;
+    default:
+      set_last_error("invalid argument", "cg_stage: unknown stage");
+      return TFEM_ERR_INVALID;
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+// Offsets (in doubles) inside the Krylov work buffer: which = 0 r, 1 p, 2 q, 3 scalars.
+extern "C" int64_t tfem_krylov_work_offset(int64_t n_rows, int which) {
+  const int64_t np = pad32(n_rows);
+  return which <= 2 ? which * np : 6 * np;
+}
+
+// Copies {iterations, ||r||, ||b||, done flag} of the solve living in `work` to the host (synchronises).
+extern "C" int tfem_krylov_state(int64_t n_rows, const double* work, double* info_host, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(work && info_host, "krylov_state: null pointer");
+  double sc_host[SC_COUNT];
+  TFEM_CUDA(cudaMemcpyAsync(sc_host, work + 6 * pad32(n_rows), sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  info_host[0] = sc_host[SC_ITERS];
+  info_host[1] = sqrt(sc_host[SC_RR]);
+  info_host[2] = sc_host[SC_BNRM];
+  info_host[3] = sc_host[SC_DONE];
   return TFEM_OK;
 }
