@@ -50,7 +50,7 @@ def _worker(rank, world, port, N, out):
 
     # slab generator == general partition
     E = N - 1
-    nodes_s, mesh_s, ranges_s, dims = D.cube_slab(E, world, rank)
+    nodes_s, mesh_s, ranges_s, dims = D.cube_slab(2 * E, E, E, 1.0 / E, world, rank)
     assert ranges_s == ranges and dims == (2 * E + 1, N, N)
     assert torch.equal(mesh_s.global_nodes, mesh.global_nodes) and torch.equal(mesh_s.elements, mesh.elements)
     assert mesh_s.lo == mesh.lo and mesh_s.n_owned == mesh.n_owned

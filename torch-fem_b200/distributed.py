@@ -232,31 +232,37 @@ def _global_sum_int(v: int, dev, group=None) -> int:
 
 
 # ------------------------------------------------------------------------------------------ slab problem
-def cube_slab(E: int, world: int, rank: int):
-    """Rank-local part of the weak-scaling cube: the global mesh is cube_hexa(world*E+1, E+1, E+1,
-    Lx=world) (cubic elements of edge 1/E; `world` config-B cubes stacked along x), rank r owns a block of
-    x-planes. Built directly (never materialising the global mesh) and equal, entry for entry, to
+def cube_slab(Ex: int, Ey: int, Ez: int, h: float, world: int, rank: int):
+    """Rank-local part of a structured Hexa1 box of Ex x Ey x Ez cubic elements of edge h, partitioned into
+    slabs of x-planes (x is the slowest index of the `cube_hexa` numbering, so slabs are contiguous node
+    blocks). Built directly, never materialising the global mesh, and equal entry for entry to
     `local_mesh(cube_hexa(...).elements, n0, n1)` — tests/test_distributed_cpu.py checks that."""
     from .mesh import cube_hexa
 
-    Nx, Ny = world * E + 1, E + 1
-    plane = Ny * Ny
+    Nx, Ny, Nz = Ex + 1, Ey + 1, Ez + 1
+    plane = Ny * Nz
     ranges = node_ranges(Nx * plane, world, granule=plane)
     n0, n1 = ranges[rank]
     a, b = n0 // plane, n1 // plane            # owned planes [a, b)
     pa, pb = max(a - 1, 0), min(b + 1, Nx)     # local planes incl. halo
-    h = 1.0 / E
     with torch.device("cpu"):
-        nodes, elements = cube_hexa(pb - pa, Ny, Ny, (pb - pa - 1) * h, 1.0, 1.0)
+        nodes, elements = cube_hexa(pb - pa, Ny, Nz, (pb - pa - 1) * h, Ey * h, Ez * h)
         nodes[:, 0] += pa * h
     mesh = LocalMesh(torch.arange(pa * plane, pb * plane), elements, None, (a - pa) * plane, n1 - n0, n0, n1)
-    return nodes, mesh, ranges, (Nx, Ny, Ny)
+    return nodes, mesh, ranges, (Nx, Ny, Nz)
+
+
+def weak_scaling_edge(E: int, world: int) -> int:
+    """Edge (in elements) of the global cube that gives every rank a config-sized share: E * world^(1/3)."""
+    return int(round(E * world ** (1.0 / 3.0)))
 
 
 def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
-    """bench.py body for N > 1 (launched by torchrun, one rank per GPU): weak scaling — every rank holds a
-    config-B-sized slab (E^3 elements); value = global DOFs / max-over-ranks device time of
-    integrate + assemble + rhs + distributed PCG."""
+    """bench.py body for N > 1 (launched by torchrun, one rank per GPU): weak scaling of the cube benchmark —
+    the global mesh is the cube with N times the elements of the single-GPU config (edge E*N^(1/3): 189^3,
+    238^3, 300^3 elements for N = 2, 4, 8 at E = 150), cut into N slabs of x-planes, so every rank holds
+    ~E^3 elements. value = global DOFs / max-over-ranks device time of integrate + assemble + rhs +
+    distributed PCG."""
     from . import _lib as L
     from . import csr
     from .elements import Hexa1
@@ -265,9 +271,10 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.device("cuda", torch.cuda.current_device())
     E = args.edge
-    t0 = time.perf_counter()
-    nodes_h, mesh, ranges, (Nx, Ny, Nz) = cube_slab(E, world, rank)
-    Lx = float(world)
+    Eg = weak_scaling_edge(E, world)
+    h = 1.0 / E
+    nodes_h, mesh, ranges, (Nx, Ny, Nz) = cube_slab(Eg, Eg, Eg, h, world, rank)
+    Lx = Eg * h
     n_dofs_global = Nx * Ny * Nz * 3
     con_h = torch.zeros(mesh.n_local, 3, dtype=torch.bool)
     disp_h = torch.zeros(mesh.n_local, 3, dtype=torch.float64)
@@ -361,17 +368,17 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
             "metric": metric, "value": n_dofs_global / (ms / 1e3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"linear-elastic Hexa1 bar of {world} stacked {E}^3-element cubes "
-                                   f"({world * E}x{E}x{E} elements), row-block partition, Jacobi-PCG to 1e-8",
+            "config": {"workload": f"linear-elastic Hexa1 cube {Eg}^3 elements (= {world} x {E}^3, weak scaling of "
+                                   f"BASELINE configs[1]), {world} slabs of x-planes, Jacobi-PCG to 1e-8",
                        "n_dofs": int(n_dofs_global), "nnz": int(nnz_owned.item()), "rtol": rtol,
                        "cg_iterations": info["iterations"], "true_rel_residual": true_res,
                        "per_rank_local_dofs": int(A.n), "halo_bytes_per_exchange": plan.bytes_per_exchange(),
                        "collectives_per_iteration": "1 halo exchange (P2P send/recv) + 2 all-reduces (1 and 2 doubles)",
                        "l2_policy": "inputs larger than L2 (per-rank CSR matrix ~10 GB vs 126 MB L2)",
                        "setup_ms_pattern": setup_ms,
-                       "note": "iteration count grows with the bar length (Jacobi-PCG), so DOF/s per GPU "
+                       "note": "Jacobi-PCG iterations grow with the cube edge (~N^(1/3)), so DOF/s per GPU "
                                "falls with N even at perfect per-iteration scaling; per_iteration_ms is the "
-                               "scaling-relevant figure",
+                               "kernel/communication scaling figure",
                        "per_iteration_ms": ms / max(1, info["iterations"])},
             "e2e": None, "gpu_launches": int(info["launches"] + 6),
             "roofline": {"bound": "hbm", "kernel": "k_sell_spmv (per rank)", "achieved": achieved, "peak": peak,
