@@ -148,8 +148,31 @@ int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr_dev, int64_t* slic
 int tfem_sell_fill(int64_t n_rows, const int64_t* indptr_dev, const int32_t* indices_dev,
                    const double* vals_dev, const int64_t* slice_ptr_dev, int32_t* sell_cols_dev,
                    double* sell_vals_dev, void* stream);
-int tfem_sell_spmv(int64_t n_rows, const int64_t* slice_ptr_dev, const int32_t* sell_cols_dev,
-                   const double* sell_vals_dev, const double* x_dev, double* y_dev, void* stream);
+
+/* Node-block column indices (optional, dpn = 2 or 3): FEM rows come in groups of dpn that share their column
+ * blocks (column of entry k = dpn*adj[k/dpn] + k%dpn), so one int32 per (node, block) replaces one per entry
+ * and the index stream drops from 4 to 4/dpn^2 bytes per nonzero (8.5 instead of 12 B/nnz for dpn = 3).
+ * bcols[bslice_ptr[t] + kb*NPS + m] = block column kb of the m-th node touched by slice t (NPS = 12 for dpn 3,
+ * 16 for dpn 2). Not valid for patterns with unreferenced nodes (rows of length 1): use scalar columns then.
+ * bslice_ptr_dev: int64 [ceil(n/32)+1] out (last entry = length of bcols). */
+int tfem_bsell_slice_ptr(int64_t n_rows, int dpn, const int64_t* slice_ptr_dev, int64_t* bslice_ptr_dev,
+                         void* stream);
+int tfem_bsell_fill(int64_t n_rows, int dpn, int64_t n_nod, const int64_t* node_ptr_dev,
+                    const int32_t* adj_dev, const int64_t* bslice_ptr_dev, int32_t* bcols_dev, void* stream);
+
+/* A SELL-32 matrix as the solver kernels take it (all device pointers). Either `cols` (scalar columns) or
+ * `bcols` + `bslice_ptr` + `dpn` (node-block columns) must be given; if both are, block columns are used. */
+typedef struct tfem_sell {
+  int64_t n_rows;
+  const int64_t* slice_ptr;   /* [ceil(n/32)+1] */
+  const int32_t* cols;        /* [padded nnz] or NULL */
+  const double* vals;         /* [padded nnz] */
+  const int64_t* bslice_ptr;  /* [ceil(n/32)+1] or NULL */
+  const int32_t* bcols;       /* or NULL */
+  int32_t dpn;                /* DOFs per node of the block structure (2 or 3), 0 if none */
+} tfem_sell_t;
+
+int tfem_sell_spmv(const tfem_sell_t* A, const double* x_dev, double* y_dev, void* stream);
 
 /* y = A^T x for a general (non-symmetric) CSR matrix — the adjoint of `Solve` with non-symmetric A
  * (sparse.py:203; tests/test_sparse.py:94-158). Deterministic: builds on a transposed copy made by the
@@ -180,11 +203,9 @@ int tfem_jacobi_setup(int64_t n_rows, const double* vals_dev, const int64_t* dia
  *            kernel launches, reserved, reserved}.
  * Returns TFEM_ERR_NOT_CONVERGED at maxiter (x still holds the last iterate). */
 int64_t tfem_krylov_work_doubles(int64_t n_rows);
-int tfem_krylov_solve(int method, int64_t n_rows, const int64_t* slice_ptr_dev,
-                      const int32_t* sell_cols_dev, const double* sell_vals_dev,
-                      const double* dinv_dev, const double* b_dev, const double* x0_dev, double rtol,
-                      double atol, int64_t maxiter, int check_every, double* x_dev, double* work_dev,
-                      double* info_host, void* stream);
+int tfem_krylov_solve(int method, const tfem_sell_t* A, const double* dinv_dev, const double* b_dev,
+                      const double* x0_dev, double rtol, double atol, int64_t maxiter, int check_every,
+                      double* x_dev, double* work_dev, double* info_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Multi-GPU Jacobi-PCG, one call per stage. The reference has no multi-GPU path; the partitioning
@@ -198,13 +219,11 @@ int tfem_krylov_solve(int method, int64_t n_rows, const int64_t* slice_ptr_dev,
  *   stage 4  x += alpha p ; r -= alpha q                  red <- local (r.r, r.z)          -> all-reduce(2)
  *   stage 5  scalars (alpha, beta, iteration count, convergence flag)
  *   stage 6  p = dinv r + beta p
- * Vectors have n_local entries: owned rows [row_lo, row_lo + n_owned) plus halo rows; b, dinv, x are
+ * Vectors have n_local = A_local->n_rows entries: owned rows [row_lo, row_lo + n_owned) plus halo rows; b, dinv, x are
  * indexed like the local rows. work_dev as in tfem_krylov_solve (sized for n_local); red_dev: double[4]. */
-int tfem_cg_stage(int stage, int64_t n_local, int64_t row_lo, int64_t n_owned,
-                  const int64_t* slice_ptr_dev, const int32_t* sell_cols_dev,
-                  const double* sell_vals_dev, const double* dinv_dev, const double* b_dev,
-                  double* x_dev, double* work_dev, double* red_dev, double rtol, double atol,
-                  void* stream);
+int tfem_cg_stage(int stage, const tfem_sell_t* A_local, int64_t row_lo, int64_t n_owned,
+                  const double* dinv_dev, const double* b_dev, double* x_dev, double* work_dev,
+                  double* red_dev, double rtol, double atol, void* stream);
 /* Offset (in doubles) of a vector inside work_dev: which = 0 r, 1 p, 2 q, 3 device scalars. */
 int64_t tfem_krylov_work_offset(int64_t n_rows, int which);
 /* info_host[4] <- {iterations, ||r||_2, ||b||_2, done flag (0 running, 1 converged, 2 breakdown)}; synchronises. */

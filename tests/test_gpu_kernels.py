@@ -166,9 +166,14 @@ def test_spmv_matches_oracle(T, tables, N):
     assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * 81
     y2 = A.matvec(x.cuda()).cpu().numpy()
     assert np.array_equal(y, y2)
-    ys = A.matvec(x.cuda(), fmt="sell").cpu().numpy()
+    ys = A.matvec(x.cuda(), fmt="sell-scalar").cpu().numpy()
     assert np.abs(ys - y_ref).max() <= 1e-13 * np.abs(y_ref).max() * 81
-    assert np.array_equal(ys, A.matvec(x.cuda(), fmt="sell").cpu().numpy())
+    assert np.array_equal(ys, A.matvec(x.cuda(), fmt="sell-scalar").cpu().numpy())
+    # node-block column indices (pattern-built matrix): same products, same order -> bitwise equal
+    Ab = p.matrix(A.values_)
+    assert Ab.sell().block
+    yb = Ab.matvec(x.cuda(), fmt="sell").cpu().numpy()
+    assert np.array_equal(yb, ys)
 
 
 @pytest.mark.parametrize("tag", ["hexa2", "tetra2", "quad1", "heat_quad2", "hexa1_orphan"])
@@ -185,6 +190,10 @@ def test_spmv_other_row_lengths(T, tag):
     assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
     ys = A.matvec(dev(x), fmt="sell").cpu().numpy()
     assert np.abs(ys - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    Ab = p.matrix(dev(c["K_val"]), symmetric=False)
+    assert Ab.sell().block == (dpn in (2, 3) and tag != "hexa1_orphan")
+    yb = Ab.matvec(dev(x), fmt="sell").cpu().numpy()
+    assert np.array_equal(yb, ys)
 
 
 @pytest.mark.parametrize("method", ["cg", "minres"])

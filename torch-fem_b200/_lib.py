@@ -25,6 +25,14 @@ KIND_MECH, KIND_HEAT = 0, 1
 METHOD_CG, METHOD_MINRES = 0, 1
 SPMV_CHUNK = 512
 
+class SellStruct(ctypes.Structure):
+    """`tfem_sell_t` of include/tfem_b200.h."""
+    _fields_ = [("n_rows", c_int64), ("slice_ptr", c_void_p), ("cols", c_void_p), ("vals", c_void_p),
+                ("bslice_ptr", c_void_p), ("bcols", c_void_p), ("dpn", ctypes.c_int32)]
+
+
+_SELL_P = ctypes.POINTER(SellStruct)
+
 _SIGNATURES = {
     "tfem_version": (c_int, []),
     "tfem_get_error_string": (c_int, [c_int, c_char_p, c_int]),
@@ -42,13 +50,15 @@ _SIGNATURES = {
     "tfem_csr_diag_positions": (c_int, [c_int64] + [c_void_p] * 4),
     "tfem_jacobi_setup": (c_int, [c_int64] + [c_void_p] * 4),
     "tfem_krylov_work_doubles": (c_int64, [c_int64]),
-    "tfem_krylov_solve": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double, c_double, c_int64, c_int]
+    "tfem_krylov_solve": (c_int, [c_int, _SELL_P] + [c_void_p] * 3 + [c_double, c_double, c_int64, c_int]
                           + [c_void_p] * 4),
+    "tfem_bsell_slice_ptr": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "tfem_bsell_fill": (c_int, [c_int64, c_int, c_int64] + [c_void_p] * 5),
     "tfem_sell_slice_ptr": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_sell_fill": (c_int, [c_int64] + [c_void_p] * 7),
-    "tfem_sell_spmv": (c_int, [c_int64] + [c_void_p] * 6),
+    "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
-    "tfem_cg_stage": (c_int, [c_int, c_int64, c_int64, c_int64] + [c_void_p] * 8 + [c_double, c_double, c_void_p]),
+    "tfem_cg_stage": (c_int, [c_int, _SELL_P, c_int64, c_int64] + [c_void_p] * 5 + [c_double, c_double, c_void_p]),
     "tfem_krylov_work_offset": (c_int64, [c_int64, c_int]),
     "tfem_krylov_state": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
 }

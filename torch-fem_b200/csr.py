@@ -111,7 +111,11 @@ class Pattern:
     def sell_structure(self):
         """(slice_ptr, sell_cols, padded_nnz) of the solver-internal SELL-32 layout, built once."""
         if getattr(self, "_sell", None) is None:
-            self._sell = sell_structure(self.indptr, self.indices, self.n_dofs)
+            has_orphans = self.nnz != self.dpn * self.dpn * self.nnzb
+            block = None
+            if self.dpn in (2, 3) and not has_orphans:
+                block = (self.dpn, self.n_nod, self.node_ptr, self.adj)
+            self._sell = sell_structure(self.indptr, self.indices, self.n_dofs, block)
         return self._sell
 
     def matrix(self, values: Tensor, symmetric: bool = True) -> "CSRMatrix":
@@ -121,15 +125,79 @@ class Pattern:
                          coo_indices=self._glob_idx)
 
 
-def sell_structure(indptr: Tensor, indices: Tensor, n: int):
-    n_slices = (n + 31) // 32
-    slice_ptr = _i64(n_slices + 1, indptr.device)
-    L.check(L.lib.tfem_sell_slice_ptr(n, L.ptr(indptr), L.ptr(slice_ptr), L.stream()))
-    padded = int(slice_ptr[-1].item())
-    sell_cols = _i32(max(padded, 4), indptr.device)
-    L.check(L.lib.tfem_sell_fill(n, L.ptr(indptr), L.ptr(indices), None, L.ptr(slice_ptr),
-                                 L.ptr(sell_cols), None, L.stream()))
-    return slice_ptr, sell_cols, padded
+class SellStructure:
+    """Pattern-level part of the solver-internal SELL-32 layout: slice offsets, and either scalar column
+    indices (4 B/nnz) or node-block column indices (4/dpn^2 B/nnz, only for patterns built from a mesh
+    with dpn in {2,3} and no unreferenced nodes). Built lazily, shared by every matrix on the pattern."""
+
+    def __init__(self, indptr: Tensor, indices: Tensor, n: int, block=None):
+        self.indptr, self.indices, self.n = indptr, indices, int(n)
+        n_slices = (self.n + 31) // 32
+        self.slice_ptr = _i64(n_slices + 1, indptr.device)
+        L.check(L.lib.tfem_sell_slice_ptr(self.n, L.ptr(indptr), L.ptr(self.slice_ptr), L.stream()))
+        self.padded = int(self.slice_ptr[-1].item())
+        self._cols = None
+        self.block = block  # (dpn, n_nod, node_ptr, adj) or None
+        self._bslice_ptr = self._bcols = None
+
+    @property
+    def cols(self) -> Tensor:
+        if self._cols is None:
+            self._cols = _i32(max(self.padded, 4), self.indptr.device)
+            L.check(L.lib.tfem_sell_fill(self.n, L.ptr(self.indptr), L.ptr(self.indices), None,
+                                         L.ptr(self.slice_ptr), L.ptr(self._cols), None, L.stream()))
+        return self._cols
+
+    @property
+    def bcols(self):
+        if self.block is None:
+            return None
+        if self._bcols is None:
+            dpn, n_nod, node_ptr, adj = self.block
+            n_slices = (self.n + 31) // 32
+            self._bslice_ptr = _i64(n_slices + 1, self.indptr.device)
+            L.check(L.lib.tfem_bsell_slice_ptr(self.n, dpn, L.ptr(self.slice_ptr), L.ptr(self._bslice_ptr),
+                                               L.stream()))
+            total = int(self._bslice_ptr[-1].item())
+            self._bcols = _i32(max(total, 4), self.indptr.device)
+            L.check(L.lib.tfem_bsell_fill(self.n, dpn, n_nod, L.ptr(node_ptr), L.ptr(adj),
+                                          L.ptr(self._bslice_ptr), L.ptr(self._bcols), L.stream()))
+        return self._bslice_ptr, self._bcols, self.block[0]
+
+
+class SellMatrix:
+    """A `tfem_sell_t` plus the tensors that keep its pointers alive."""
+
+    def __init__(self, st: SellStructure, vals: Tensor, use_block: bool = True):
+        blk = st.bcols if use_block else None
+        self.keep = [st.slice_ptr, vals]
+        self.struct = L.SellStruct()
+        self.struct.n_rows = st.n
+        self.struct.slice_ptr = L.ptr(st.slice_ptr)
+        self.struct.vals = L.ptr(vals)
+        if blk is not None:
+            bslice_ptr, bcols, dpn = blk
+            self.keep += [bslice_ptr, bcols]
+            self.struct.bslice_ptr, self.struct.bcols, self.struct.dpn = L.ptr(bslice_ptr), L.ptr(bcols), dpn
+            self.struct.cols = None
+        else:
+            cols = st.cols
+            self.keep.append(cols)
+            self.struct.cols = L.ptr(cols)
+            self.struct.bslice_ptr = self.struct.bcols = None
+            self.struct.dpn = 0
+        self.n = st.n
+        self.block = blk is not None
+
+    @property
+    def ref(self):
+        import ctypes
+
+        return ctypes.byref(self.struct)
+
+
+def sell_structure(indptr: Tensor, indices: Tensor, n: int, block=None) -> SellStructure:
+    return SellStructure(indptr, indices, n, block)
 
 
 def spmv_plan(indptr: Tensor, n_rows: int, nnz: int) -> Tensor:
@@ -162,6 +230,7 @@ class CSRMatrix:
         self._T = None
         self._sell_struct = sell_struct
         self._sell_vals = None
+        self._sell_mats = {}
 
     # ---- torch-sparse look-alike surface used by the reference's callers
     @property
@@ -254,31 +323,34 @@ class CSRMatrix:
             self._T._T = self
         return self._T
 
-    def sell(self):
-        """(slice_ptr, sell_cols, sell_vals): the SELL-32 copy the Krylov kernels stream. The structure
-        is shared with the pattern; the values are converted once per matrix (8 B/nnz read + write)."""
+    def sell(self, block: bool = True) -> SellMatrix:
+        """The SELL-32 copy the Krylov kernels stream. The structure is shared with the pattern; the values
+        are converted once per matrix (8 B/nnz read + write). `block=False` forces scalar column indices."""
         if self._sell_struct is None:
             self._sell_struct = sell_structure(self.indptr, self.indices, self.n)
-        slice_ptr, sell_cols, padded = self._sell_struct
+        st = self._sell_struct
         if self._sell_vals is None:
-            sv = torch.empty(max(padded, 2), dtype=torch.float64, device=self.device)
+            sv = torch.empty(max(st.padded, 2), dtype=torch.float64, device=self.device)
             L.check(L.lib.tfem_sell_fill(self.n, L.ptr(self.indptr), None, L.ptr(self.values_),
-                                         L.ptr(slice_ptr), None, L.ptr(sv), L.stream()))
+                                         L.ptr(st.slice_ptr), None, L.ptr(sv), L.stream()))
             self._sell_vals = sv
-        return slice_ptr, sell_cols, self._sell_vals
+        key = bool(block and st.block is not None)
+        if self._sell_mats.get(key) is None:
+            self._sell_mats[key] = SellMatrix(st, self._sell_vals, use_block=key)
+        return self._sell_mats[key]
 
     def matvec(self, x: Tensor, out: Tensor | None = None, fmt: str = "auto") -> Tensor:
-        """y = A x with the K5 SpMV kernels: the SELL-32 kernel when that copy exists (or fmt="sell"),
-        else the CSR-chunk kernel (no conversion; right for a one-off product)."""
+        """y = A x with the K5 SpMV kernels. fmt: "sell" (block columns when the pattern has them),
+        "sell-scalar" (scalar columns, 12 B/nnz), "csr" (CSR-chunk kernel, no conversion; right for a
+        one-off product), "auto" = "sell" if that copy already exists else "csr"."""
         L.require_cuda(x)
         x = x.contiguous()
         if x.dtype != torch.float64 or x.shape != (self.n,):
             raise ValueError("matvec expects a float64 vector of length n")
         y = out if out is not None else torch.empty_like(x)
-        if fmt == "sell" or (fmt == "auto" and self._sell_vals is not None):
-            slice_ptr, sell_cols, sell_vals = self.sell()
-            L.check(L.lib.tfem_sell_spmv(self.n, L.ptr(slice_ptr), L.ptr(sell_cols), L.ptr(sell_vals),
-                                         L.ptr(x), L.ptr(y), L.stream()))
+        if fmt in ("sell", "sell-scalar") or (fmt == "auto" and self._sell_vals is not None):
+            S = self.sell(block=(fmt != "sell-scalar"))
+            L.check(L.lib.tfem_sell_spmv(S.ref, L.ptr(x), L.ptr(y), L.stream()))
         else:
             L.check(L.lib.tfem_spmv(self.n, self.nnz, L.ptr(self.indptr), L.ptr(self.indices),
                                     L.ptr(self.values_), L.ptr(self.chunk_rows), L.ptr(x), L.ptr(y),
@@ -400,9 +472,8 @@ def krylov_solve(A: CSRMatrix, b: Tensor, method: str = "cg", rtol: float = 1e-1
     meth = {"cg": L.METHOD_CG, "minres": L.METHOD_MINRES}[method]
     if x0 is not None:
         x0 = x0.to(device=b.device, dtype=torch.float64).contiguous()
-    slice_ptr, sell_cols, sell_vals = A.sell()
-    rc = L.lib.tfem_krylov_solve(meth, A.n, L.ptr(slice_ptr), L.ptr(sell_cols), L.ptr(sell_vals),
-                                 L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
+    S = A.sell()
+    rc = L.lib.tfem_krylov_solve(meth, S.ref, L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
                                  int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
                                  info.ctypes.data, L.stream())
     stats = {"iterations": int(info[0]), "resnorm": float(info[1]), "bnorm": float(info[2]),

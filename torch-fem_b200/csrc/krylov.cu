@@ -117,7 +117,32 @@ struct Sell {
   const int32_t* cols;
   const double* vals;
   int64_t dot_lo = 0, dot_hi = INT64_MAX;  // rows that enter the fused x.y dot (owned rows of a rank)
+  // optional node-block column indices (see k_bsell_spmv): one int per (node, block) instead of one per entry
+  const int64_t* bslice_ptr = nullptr;
+  const int32_t* bcols = nullptr;
+  int dpn = 0;
 };
+
+inline Sell make_sell(const tfem_sell_t* a) {
+  Sell A;
+  A.n = a->n_rows;
+  A.n_slices = (a->n_rows + 31) / 32;
+  A.slice_ptr = a->slice_ptr;
+  A.cols = a->cols;
+  A.vals = a->vals;
+  A.bslice_ptr = a->bslice_ptr;
+  A.bcols = a->bcols;
+  A.dpn = a->bcols ? a->dpn : 0;
+  return A;
+}
+
+inline int check_sell(const tfem_sell_t* a) {
+  TFEM_REQUIRE(a && a->slice_ptr && a->vals && a->n_rows > 0, "SELL matrix: null pointer or empty");
+  TFEM_REQUIRE(a->cols || (a->bcols && a->bslice_ptr), "SELL matrix: neither scalar nor block columns given");
+  TFEM_REQUIRE(aligned16(a->vals) && (!a->cols || aligned16(a->cols)), "SELL arrays must be 16-byte aligned");
+  TFEM_REQUIRE(!a->bcols || a->dpn == 2 || a->dpn == 3, "block columns need 2 or 3 DOFs per node");
+  return TFEM_OK;
+}
 
 __global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
                               int64_t* __restrict__ slice_elems) {
@@ -219,10 +244,151 @@ inline int sell_grid(int64_t n_slices) {
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
+
+// ---- node-block column indices -------------------------------------------------------------------
+// FEM rows come in groups of dpn (the DOFs of one node) that share their column BLOCKS: entry k of a row
+// has column dpn*adj[k/dpn] + k%dpn. Storing one int32 per (node, block) instead of one per entry cuts the
+// index stream from 4 B to 4/dpn^2 B per nonzero (8.5 instead of 12 B/nnz for dpn = 3). Layout, in slice
+// order so the load is one wavefront: bcols[bslice_ptr[t] + kb*NPS + m] = block column kb of the m-th node
+// touched by slice t (first node nf = 32t/dpn, NPS = 12 nodes for dpn 3, 16 for dpn 2). Padding repeats the
+// node's last block (values there are 0.0). Matrices with unreferenced nodes (rows of length 1) keep the
+// scalar-column kernel.
+template <int DPN> struct Nps { static constexpr int v = (DPN == 3) ? 12 : 16; };
+
+__global__ void k_bsell_widths(int64_t n_slices, int dpn, int nps, const int64_t* __restrict__ slice_ptr,
+                               int64_t* __restrict__ out) {
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= n_slices) return;
+  const int64_t W = (slice_ptr[t + 1] - slice_ptr[t]) >> 5;
+  out[t] = ((W + dpn - 1) / dpn) * nps;
+}
+
+__global__ void k_bsell_fill(int64_t n_slices, int64_t n_nod, int dpn, int nps,
+                             const int64_t* __restrict__ node_ptr, const int32_t* __restrict__ adj,
+                             const int64_t* __restrict__ bslice_ptr, int32_t* __restrict__ bcols) {
+  const int lane = threadIdx.x & 31;
+  const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_slices) return;
+  const int64_t base = bslice_ptr[t];
+  const int total = (int)(bslice_ptr[t + 1] - base);
+  const int64_t nf = (t * 32) / dpn;
+  for (int o = lane; o < total; o += 32) {
+    const int kb = o / nps, m = o - kb * nps;
+    int64_t node = nf + m;
+    if (node >= n_nod) node = n_nod - 1;
+    const int64_t nb = node_ptr[node];
+    const int cnt = (int)(node_ptr[node + 1] - nb);
+    bcols[base + o] = cnt > 0 ? adj[nb + (kb < cnt ? kb : cnt - 1)] : (int32_t)node;
+  }
+}
+
+template <int DPN, bool DOT>
+__global__ void __launch_bounds__(kSellWarps * 32)
+    k_bsell_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
+                 double* partials, unsigned int* ticket, double* out_scalar) {
+  constexpr int NPS = Nps<DPN>::v;
+  __shared__ double s_red[kSellWarps];
+  if (DOT && sc[SC_DONE] != 0.0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double2* v2 = reinterpret_cast<const double2*>(A.vals);
+  double dot = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices;
+       t += (int64_t)gridDim.x * kSellWarps) {
+    const int64_t b2 = (A.slice_ptr[t] >> 1) + lane;
+    const int w2 = (int)((A.slice_ptr[t + 1] - A.slice_ptr[t]) >> 6);  // 128-bit steps
+    const int64_t row = t * 32 + lane;
+    const int m = (int)(row / DPN - (t * 32) / DPN);                    // my node within the slice
+    const int32_t* bc = A.bcols + A.bslice_ptr[t] + m;
+    double acc = 0.0;
+    if (DPN == 2) {
+      int s = 0;
+      for (; s + 4 <= w2; s += 4) {
+        double2 v[4];
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          v[u] = ldg_stream_double2(v2 + b2 + (int64_t)(s + u) * 32);
+          c[u] = 2 * __ldg(bc + (s + u) * NPS);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          acc = fma(v[u].x, __ldg(x + c[u]), acc);
+          acc = fma(v[u].y, __ldg(x + c[u] + 1), acc);
+        }
+      }
+      for (; s < w2; ++s) {
+        const double2 v = ldg_stream_double2(v2 + b2 + (int64_t)s * 32);
+        const int c = 2 * __ldg(bc + s * NPS);
+        acc = fma(v.x, __ldg(x + c), acc);
+        acc = fma(v.y, __ldg(x + c + 1), acc);
+      }
+    } else {
+      // 6 entries = 3 x 128-bit value loads = 2 column blocks per step
+      int s = 0, kb = 0;
+      for (; s + 6 <= w2; s += 6, kb += 4) {
+        double2 v[6];
+        int c[4];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) v[u] = ldg_stream_double2(v2 + b2 + (int64_t)(s + u) * 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = 3 * __ldg(bc + (kb + u) * NPS);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const double* x0 = x + c[2 * h];
+          const double* x1 = x + c[2 * h + 1];
+          acc = fma(v[3 * h].x, __ldg(x0), acc);
+          acc = fma(v[3 * h].y, __ldg(x0 + 1), acc);
+          acc = fma(v[3 * h + 1].x, __ldg(x0 + 2), acc);
+          acc = fma(v[3 * h + 1].y, __ldg(x1), acc);
+          acc = fma(v[3 * h + 2].x, __ldg(x1 + 1), acc);
+          acc = fma(v[3 * h + 2].y, __ldg(x1 + 2), acc);
+        }
+      }
+      for (; s + 3 <= w2; s += 3, kb += 2) {
+        const double2 va = ldg_stream_double2(v2 + b2 + (int64_t)s * 32);
+        const double2 vb = ldg_stream_double2(v2 + b2 + (int64_t)(s + 1) * 32);
+        const double2 vc = ldg_stream_double2(v2 + b2 + (int64_t)(s + 2) * 32);
+        const double* x0 = x + 3 * __ldg(bc + kb * NPS);
+        const double* x1 = x + 3 * __ldg(bc + (kb + 1) * NPS);
+        acc = fma(va.x, __ldg(x0), acc);
+        acc = fma(va.y, __ldg(x0 + 1), acc);
+        acc = fma(vb.x, __ldg(x0 + 2), acc);
+        acc = fma(vb.y, __ldg(x1), acc);
+        acc = fma(vc.x, __ldg(x1 + 1), acc);
+        acc = fma(vc.y, __ldg(x1 + 2), acc);
+      }
+      // tail: fewer than 6 entries left; entry k uses block k/3, component k%3
+      const int nblk = (2 * w2 + 2) / 3;  // blocks stored for this slice (ceil(W/3))
+      for (; s < w2; ++s) {
+        const double2 v = ldg_stream_double2(v2 + b2 + (int64_t)s * 32);
+        const int k0 = 2 * s, k1 = 2 * s + 1;
+        const int ka = k0 / 3 < nblk ? k0 / 3 : nblk - 1, kc = k1 / 3 < nblk ? k1 / 3 : nblk - 1;
+        acc = fma(v.x, __ldg(x + 3 * __ldg(bc + ka * NPS) + k0 % 3), acc);
+        acc = fma(v.y, __ldg(x + 3 * __ldg(bc + kc * NPS) + k1 % 3), acc);
+      }
+    }
+    if (row < A.n) {
+      y[row] = acc;
+      if (DOT && row >= A.dot_lo && row < A.dot_hi) dot = fma(acc, __ldg(x + row), dot);
+    }
+  }
+  if (DOT) {
+    const double b = block_sum<kSellWarps * 32>(dot, s_red);
+    double mine[1] = {b}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
+  }
+}
+
 template <bool DOT>
 int launch_sell(const Sell& A, const double* x, double* y, const double* sc, double* partials,
                 unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  k_sell_spmv<DOT><<<sell_grid(A.n_slices), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  const int g = sell_grid(A.n_slices);
+  if (A.dpn == 3)
+    k_bsell_spmv<3, DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  else if (A.dpn == 2)
+    k_bsell_spmv<2, DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  else
+    k_sell_spmv<DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -769,12 +935,43 @@ extern "C" int tfem_sell_fill(int64_t n_rows, const int64_t* indptr, const int32
   return TFEM_OK;
 }
 
-extern "C" int tfem_sell_spmv(int64_t n_rows, const int64_t* slice_ptr, const int32_t* sell_cols,
-                              const double* sell_vals, const double* x, double* y, void* stream_) {
+extern "C" int tfem_bsell_slice_ptr(int64_t n_rows, int dpn, const int64_t* slice_ptr,
+                                    int64_t* bslice_ptr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals && x && y && n_rows > 0, "sell_spmv: bad arguments");
-  TFEM_REQUIRE(aligned16(sell_cols) && aligned16(sell_vals), "sell_spmv: SELL arrays must be 16-byte aligned");
-  Sell A{n_rows, (n_rows + 31) / 32, slice_ptr, sell_cols, sell_vals};
+  TFEM_REQUIRE(slice_ptr && bslice_ptr && n_rows > 0 && (dpn == 2 || dpn == 3), "bsell_slice_ptr: bad arguments");
+  const int64_t ns = (n_rows + 31) / 32;
+  const int nps = dpn == 3 ? 12 : 16;
+  TFEM_CUDA(cudaMemsetAsync(bslice_ptr, 0, sizeof(int64_t), st));
+  k_bsell_widths<<<grid_for(ns, 256), 256, 0, st>>>(ns, dpn, nps, slice_ptr, bslice_ptr + 1);
+  TFEM_LAUNCH_CHECK();
+  size_t bytes = 0;
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, bslice_ptr + 1, bslice_ptr + 1, (int)ns, st));
+  void* tmp = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, bslice_ptr + 1, bslice_ptr + 1, (int)ns, st));
+  TFEM_CUDA(cudaFreeAsync(tmp, st));
+  return TFEM_OK;
+}
+
+extern "C" int tfem_bsell_fill(int64_t n_rows, int dpn, int64_t n_nod, const int64_t* node_ptr,
+                               const int32_t* adj, const int64_t* bslice_ptr, int32_t* bcols,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(node_ptr && adj && bslice_ptr && bcols && n_rows == n_nod * dpn && (dpn == 2 || dpn == 3),
+               "bsell_fill: bad arguments");
+  const int64_t ns = (n_rows + 31) / 32;
+  k_bsell_fill<<<grid_for(ns * 32, 256), 256, 0, st>>>(ns, n_nod, dpn, dpn == 3 ? 12 : 16, node_ptr, adj,
+                                                       bslice_ptr, bcols);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_sell_spmv(const tfem_sell_t* a, const double* x, double* y, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = check_sell(a);
+  if (rc != TFEM_OK) return rc;
+  TFEM_REQUIRE(x && y, "sell_spmv: null pointer");
+  Sell A = make_sell(a);
   return launch_sell<false>(A, x, y, nullptr, nullptr, nullptr, nullptr, st);
 }
 
@@ -782,21 +979,19 @@ extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
   return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
 }
 
-extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr,
-                                 const int32_t* sell_cols, const double* sell_vals, const double* dinv,
-                                 const double* b, const double* x0, double rtol, double atol,
-                                 int64_t maxiter, int check_every, double* x, double* work,
-                                 double* info, void* stream_) {
+extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double* dinv, const double* b,
+                                 const double* x0, double rtol, double atol, int64_t maxiter,
+                                 int check_every, double* x, double* work, double* info, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals && dinv && b && x && work && info,
-               "krylov_solve: null pointer");
+  int rc0 = check_sell(a);
+  if (rc0 != TFEM_OK) return rc0;
+  TFEM_REQUIRE(dinv && b && x && work && info, "krylov_solve: null pointer");
   TFEM_REQUIRE(method == TFEM_METHOD_CG || method == TFEM_METHOD_MINRES, "krylov_solve: unknown method");
-  TFEM_REQUIRE(aligned16(sell_cols) && aligned16(sell_vals), "krylov_solve: SELL arrays must be 16-byte aligned");
-  TFEM_REQUIRE(n > 0, "krylov_solve: empty system");
+  const int64_t n = a->n_rows;
   if (maxiter <= 0) maxiter = (method == TFEM_METHOD_CG ? 10 : 5) * n;
   if (check_every <= 0) check_every = 32;
 
-  Sell A{n, (n + 31) / 32, slice_ptr, sell_cols, sell_vals};
+  Sell A = make_sell(a);
   Work w = carve(work, n);
   const int vg = vec_grid(n);
   TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
@@ -884,12 +1079,13 @@ extern "C" int tfem_krylov_solve(int method, int64_t n, const int64_t* slice_ptr
 // torch-fem_b200/distributed.py). Vectors have n_local entries (owned rows [row_lo, row_lo+n_owned) plus
 // halo rows); vector kernels touch the owned range only, the SpMV runs over all local rows and its fused
 // dot covers the owned rows. `red_dev` (double[4]) carries local sums out and reduced sums back in.
-extern "C" int tfem_cg_stage(int stage, int64_t n_local, int64_t row_lo, int64_t n_owned,
-                             const int64_t* slice_ptr, const int32_t* sell_cols,
-                             const double* sell_vals, const double* dinv, const double* b, double* x,
-                             double* work, double* red, double rtol, double atol, void* stream_) {
+extern "C" int tfem_cg_stage(int stage, const tfem_sell_t* a, int64_t row_lo, int64_t n_owned,
+                             const double* dinv, const double* b, double* x, double* work, double* red,
+                             double rtol, double atol, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  TFEM_REQUIRE(work && red && n_local > 0 && n_owned > 0 && row_lo >= 0 && row_lo + n_owned <= n_local,
+  TFEM_REQUIRE(a && a->n_rows > 0, "cg_stage: null matrix");
+  const int64_t n_local = a->n_rows;
+  TFEM_REQUIRE(work && red && n_owned > 0 && row_lo >= 0 && row_lo + n_owned <= n_local,
                "cg_stage: bad arguments");
   Work w = carve(work, n_local);
   const int vg = vec_grid(n_owned);
@@ -909,8 +1105,11 @@ extern "C" int tfem_cg_stage(int stage, int64_t n_local, int64_t row_lo, int64_t
       k_cg_scalars<<<1, 1, 0, st>>>(stage / 2, w.sc, red, rtol, atol);
       break;
     case 2: {  // q = A p (all local rows), red <- p.q over owned rows
-      TFEM_REQUIRE(slice_ptr && sell_cols && sell_vals, "cg_stage: null pointer");
-      Sell A{n_local, (n_local + 31) / 32, slice_ptr, sell_cols, sell_vals, row_lo, row_lo + n_owned};
+      int rcs = check_sell(a);
+      if (rcs != TFEM_OK) return rcs;
+      Sell A = make_sell(a);
+      A.dot_lo = row_lo;
+      A.dot_hi = row_lo + n_owned;
       int rc = launch_sell<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, red, st);
       if (rc != TFEM_OK) return rc;
       break;

@@ -175,7 +175,7 @@ def distributed_cg(A, dinv: Tensor, b: Tensor, row_lo: int, n_owned: int, halo: 
     from . import _lib as L
 
     n_local = A.n
-    slice_ptr, sell_cols, sell_vals = A.sell()
+    S = A.sell()
     dev = b.device
     x = torch.zeros(n_local, dtype=torch.float64, device=dev)
     work = torch.empty(int(L.lib.tfem_krylov_work_doubles(n_local)), dtype=torch.float64, device=dev)
@@ -187,8 +187,7 @@ def distributed_cg(A, dinv: Tensor, b: Tensor, row_lo: int, n_owned: int, halo: 
         maxiter = 10 * int(_global_sum_int(n_owned, dev, group))
 
     def stage(k):
-        L.check(L.lib.tfem_cg_stage(k, n_local, row_lo, n_owned, L.ptr(slice_ptr), L.ptr(sell_cols),
-                                    L.ptr(sell_vals), L.ptr(dinv), L.ptr(b), L.ptr(x), L.ptr(work),
+        L.check(L.lib.tfem_cg_stage(k, S.ref, row_lo, n_owned, L.ptr(dinv), L.ptr(b), L.ptr(x), L.ptr(work),
                                     L.ptr(red), float(rtol), float(atol), L.stream()))
 
     def allreduce(k):
