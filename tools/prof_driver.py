@@ -35,13 +35,22 @@ def main():
     vals = csr.assemble(p, k, is_con)
     vals_free = csr.assemble(p, k, None)
     del k
-    A = csr.CSRMatrix(p.indptr, p.indices, vals, n_dofs, chunk_rows=p.chunk_rows, diag_pos=p.diag_pos, symmetric=True)
-    Af = csr.CSRMatrix(p.indptr, p.indices, vals_free, n_dofs, chunk_rows=p.chunk_rows, symmetric=True)
+    A = p.matrix(vals)
+    Af = p.matrix(vals_free)
     rhs = Af.matvec(disp * is_con)
     rhs.masked_fill_(is_con.bool(), 0.0)
     y = torch.empty_like(rhs)
-    for _ in range(3):
-        A.matvec(rhs, out=y)
+    for fmt in ("csr", "sell-scalar", "sell"):
+        for _ in range(3):
+            A.matvec(rhs, out=y, fmt=fmt)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            A.matvec(rhs, out=y, fmt=fmt)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"spmv {fmt}: {e0.elapsed_time(e1) / 10:.4f} ms")
     try:
         csr.krylov_solve(A, rhs, method=a.method, rtol=1e-8, maxiter=a.iters, check_every=a.iters)
     except RuntimeError as e:

@@ -238,10 +238,15 @@ __global__ void __launch_bounds__(kSellWarps * 32)
   }
 }
 
-inline int sell_grid(int64_t n_slices) {
-  const int64_t want = (n_slices + kSellWarps - 1) / kSellWarps;
-  const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 8;
-  return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+// Persistent grids are sized from the kernel's REAL occupancy (registers may allow fewer resident CTAs
+// than the 2048-thread limit; an oversized grid would run a second, nearly empty wave).
+template <typename K>
+inline int resident_ctas(K kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int sms = num_sms() < kSMs ? num_sms() : kSMs;
+  return sms * (per_sm > 8 ? 8 : per_sm);
 }
 
 
@@ -382,13 +387,20 @@ __global__ void __launch_bounds__(kSellWarps * 32)
 template <bool DOT>
 int launch_sell(const Sell& A, const double* x, double* y, const double* sc, double* partials,
                 unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  const int g = sell_grid(A.n_slices);
-  if (A.dpn == 3)
-    k_bsell_spmv<3, DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
-  else if (A.dpn == 2)
-    k_bsell_spmv<2, DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
-  else
-    k_sell_spmv<DOT><<<g, kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  static int g3 = 0, g2 = 0, g1 = 0;  // per DOT instantiation
+  if (A.dpn == 3) {
+    if (!g3) g3 = resident_ctas(k_bsell_spmv<3, DOT>, kSellWarps * 32);
+    const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+    k_bsell_spmv<3, DOT><<<(int)(want < g3 ? want : g3), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  } else if (A.dpn == 2) {
+    if (!g2) g2 = resident_ctas(k_bsell_spmv<2, DOT>, kSellWarps * 32);
+    const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+    k_bsell_spmv<2, DOT><<<(int)(want < g2 ? want : g2), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  } else {
+    if (!g1) g1 = resident_ctas(k_sell_spmv<DOT>, kSellWarps * 32);
+    const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+    k_sell_spmv<DOT><<<(int)(want < g1 ? want : g1), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
+  }
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
