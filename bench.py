@@ -188,11 +188,14 @@ def run_ours(args):
     n_dofs = nodes_h.numel()
     bref_np, w_np = O.hexa1_tables()
     bref, w = torch.as_tensor(bref_np), torch.as_tensor(w_np)
-    C1 = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1))
-    C_h = C1.expand(n_elem, 3, 3, 3, 3).contiguous()  # vectorised material, as Material.vectorize does
-    host = [nodes_h, elements_h, C_h, con_h.ravel().to(torch.uint8), disp_h.ravel().contiguous()]
+    from torchfem_b200.materials import IsotropicElasticity3D
+
+    # per-element material parameters (heterogeneous materials are the general case, cf. benchmarks/topopt.py);
+    # the [n_elem,3,3,3,3] tangent is built from them ON THE DEVICE, as the reference's vectorised material does
+    host = [nodes_h, elements_h, torch.full((n_elem,), 1000.0), torch.full((n_elem,), 0.3),
+            con_h.ravel().to(torch.uint8), disp_h.ravel().contiguous()]
     host = [t.pin_memory() for t in host]
-    nodes_h, elements_h, C_h, iscon_h, disp_h = host
+    nodes_h, elements_h, E_h, nu_h, iscon_h, disp_h = host
     t_gen = time.perf_counter() - t0
 
     # ---- setup (pattern), timed separately
@@ -207,16 +210,19 @@ def run_ours(args):
     nnz = pattern.nnz
 
     nodes = nodes_h.to(device)
-    C = C_h.to(device)
+    E_mod, nu = E_h.to(device), nu_h.to(device)
     is_con = iscon_h.to(device)
     disp = disp_h.to(device)
     vals = torch.empty(nnz, dtype=torch.float64, device=device)
     vals_free = torch.empty(nnz, dtype=torch.float64, device=device)
     state = {}
 
-    def hot_path(nodes, elements, C, is_con, disp):
-        """integrate -> assemble (constrained for the solve, unconstrained for the Dirichlet rhs) -> PCG."""
+    def hot_path(nodes, elements, E_mod, nu, is_con, disp):
+        """material tangent -> integrate -> assemble (constrained for the solve, unconstrained for the
+        Dirichlet rhs) -> PCG."""
+        C = IsotropicElasticity3D(E_mod, nu).C
         k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
+        del C
         csr.assemble(pattern, k, is_con, out=vals)
         csr.assemble(pattern, k, None, out=vals_free)
         del k
@@ -231,10 +237,10 @@ def run_ours(args):
         return u
 
     def step_resident():
-        return hot_path(nodes, elements, C, is_con, disp)
+        return hot_path(nodes, elements, E_mod, nu, is_con, disp)
 
     def step_e2e():
-        d = [t.to(device, non_blocking=True) for t in (nodes_h, elements_h, C_h, iscon_h, disp_h)]
+        d = [t.to(device, non_blocking=True) for t in host]
         u = hot_path(*d)
         return u.cpu()
 
@@ -258,7 +264,7 @@ def run_ours(args):
     value = n_dofs / (ms / 1e3)
 
     ms_e2e, u_h = timed(step_e2e, max(1, min(args.steps, 3)), 1)
-    h2d = sum(t.numel() * t.element_size() for t in (nodes_h, elements_h, C_h, iscon_h, disp_h))
+    h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = u_h.numel() * u_h.element_size()
 
     # ---- true relative residual of the last solve (checks the work was done)
@@ -288,8 +294,10 @@ def run_ours(args):
     spmv_bytes = 12 * nnz + 20 * n_dofs
     peak, peak_src = measured_peaks()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    C = IsotropicElasticity3D(E_mod, nu).C
     k_ms = ev_time(lambda: csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False), 3)
     kk = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
+    del C
     asm_ms = ev_time(lambda: csr.assemble(pattern, kk, is_con, out=vals), 3)
     del kk
     t_s = time.perf_counter()
@@ -302,18 +310,16 @@ def run_ours(args):
     # arrive from pinned host memory and the displacement field goes back to the host.
     api = None
     if not args.no_api:
-        from torchfem_b200.materials import IsotropicElasticity3D
-
         state.clear()
         del A, rhs, x, x2, xs, ys
         torch.cuda.empty_cache()
-        model = T.Solid(nodes, elements, IsotropicElasticity3D(E=1000.0, nu=0.3))
+        model = T.Solid(nodes, elements, IsotropicElasticity3D(E=E_mod, nu=nu))
         model.pattern = pattern  # reuse the setup product instead of building it twice
         con_bool_h = con_h.pin_memory()
         disp2_h = disp_h.reshape(-1, 3)
 
         def step_api():
-            model.material.C = C_h.to(device, non_blocking=True)
+            model.material = IsotropicElasticity3D(E_h.to(device, non_blocking=True), nu_h.to(device, non_blocking=True))
             model.constraints = con_bool_h.to(device, non_blocking=True)
             model.displacements = disp2_h.to(device, non_blocking=True)
             u, *_ = model.solve(method="cg", stol=RTOL, rtol=1e-6)
@@ -322,7 +328,7 @@ def run_ours(args):
         ms_api, u_api = timed(step_api, max(1, min(args.steps, 2)), 1)
         err = float((u_api.ravel() - u_h.ravel()).norm() / u_h.norm())
         api = {"value": n_dofs / (ms_api / 1e3), "unit": UNIT, "ms_per_step": ms_api,
-               "h2d_bytes_per_step": int(C_h.numel() * 8 + con_bool_h.numel() + disp2_h.numel() * 8),
+               "h2d_bytes_per_step": int(2 * E_h.numel() * 8 + con_bool_h.numel() + disp2_h.numel() * 8),
                "d2h_bytes_per_step": int(d2h), "call": "Solid.solve(method='cg', stol=1e-8)",
                "rel_diff_vs_kernel_path": err}
 
@@ -357,7 +363,8 @@ def run_ours(args):
                                                                  "per_cg_iteration": solve_ms / max(1, info2["iterations"])}},
         "e2e": {"value": n_dofs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
-                "call": "C-ABI ops on host buffers (H2D inputs -> integrate -> assemble -> PCG -> D2H u)",
+                "call": "C-ABI ops on host buffers (H2D mesh + per-element E, nu + BCs -> tangent -> integrate -> "
+                        "assemble -> PCG -> D2H u)",
                 "public_api": api},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_bsell_spmv<3> (SELL-32 values + node-block column indices, 8.5 B/nnz moved; "
@@ -384,6 +391,8 @@ def main():
     ap.add_argument("--cpu-edge", type=int, default=40, help="elements per edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api", action="store_true", help="skip the Solid.solve end-to-end leg")
+    ap.add_argument("--dist-cg", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused peer-to-peer CG (tfem_dcg_solve) or the host-driven NCCL variant")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -30,6 +30,7 @@ extern "C" {
 #define TFEM_ERR_NOT_CONVERGED 4/* Krylov solver hit maxiter (reference: RuntimeError "CG failed ...") */
 #define TFEM_ERR_BREAKDOWN 5    /* Krylov breakdown (non-finite or non-positive curvature) */
 #define TFEM_ERR_NCCL 6
+#define TFEM_ERR_COMM 7          /* a peer did not deliver its halo / reduction within the timeout */
 
 #define TFEM_KIND_MECH 0        /* vector field, tangent [.., d,d,d,d]  (base.py:1086-1090) */
 #define TFEM_KIND_HEAT 1        /* scalar field, tangent [.., d,d]      (base.py:1272-1278) */
@@ -228,6 +229,48 @@ int tfem_cg_stage(int stage, const tfem_sell_t* A_local, int64_t row_lo, int64_t
 int64_t tfem_krylov_work_offset(int64_t n_rows, int which);
 /* info_host[4] <- {iterations, ||r||_2, ||b||_2, done flag (0 running, 1 converged, 2 breakdown)}; synchronises. */
 int tfem_krylov_state(int64_t n_rows, const double* work_dev, double* info_host, void* stream);
+
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU Jacobi-PCG with the halo exchange and the dot-product all-reduces fused into the compute
+ * kernels over peer memory (CUDA IPC mappings of the other ranks' buffers; NVLink / NVSwitch stores).
+ * One process per GPU. No NCCL call and no host work inside the iteration: the direction-update kernel
+ * stores the entries a neighbour needs straight into that neighbour's copy of p, reductions are `world`
+ * stores of <= 3 doubles plus a flag, summed in rank order by every consumer (bit-identical on all ranks).
+ * Replaces the same reference loop as tfem_krylov_solve (cupy_cg, sparse.py:414-421).
+ *
+ * Setup: every rank calls tfem_comm_create (allocates its buffer: header + 2 vectors of vec_doubles — the SAME
+ * vec_doubles on every rank, >= the longest local vector — and returns a 64-byte IPC handle), the host exchanges the handles (e.g. torch.distributed.all_gather), every rank calls
+ * tfem_comm_connect with all `world` handles in rank order, then a host barrier. world <= 16.
+ * ------------------------------------------------------------------------------------------------- */
+#define TFEM_IPC_HANDLE_BYTES 64
+#define TFEM_MAX_NEIGHBOURS 8
+int tfem_comm_create(int rank, int world, int64_t vec_doubles, void** comm_out, void* ipc_handle_out);
+int tfem_comm_connect(void* comm, const void* all_handles /* world * TFEM_IPC_HANDLE_BYTES, host */);
+int tfem_comm_destroy(void* comm);
+
+/* One entry per neighbour this rank sends halo values to: `count` entries of the local vector, taken at
+ * src_idx[k] (device int32, local numbering) or src_start + k if src_idx is NULL, stored at dst_idx[k] (device
+ * int32, the PEER's local numbering) or dst_start + k of the peer's vector. */
+typedef struct tfem_halo_send {
+  int32_t peer;
+  int64_t count;
+  const int32_t* src_idx;
+  const int32_t* dst_idx;
+  int64_t src_start, dst_start;
+} tfem_halo_send_t;
+
+/* A_local: rows in local numbering [low halo | owned | high halo]; only owned rows [row_lo, row_lo+n_owned) are
+ * used. Rows in [interior_lo, interior_hi) must not reference halo columns (they are processed before the halo
+ * has arrived); pass interior_lo == interior_hi if unknown. recv_peers_host: ranks that send halo values to this
+ * rank. dinv, b, x: local-length device vectors (owned entries meaningful). work_dev as tfem_krylov_solve.
+ * maxiter must be the same on every rank. timeout_s bounds every wait on a peer (<= 0: 20 s).
+ * info_host as tfem_krylov_solve. Zero initial guess. All ranks must call this collectively. */
+int tfem_dcg_solve(void* comm, const tfem_sell_t* A_local, int64_t row_lo, int64_t n_owned,
+                   int64_t interior_lo, int64_t interior_hi, int n_sends, const tfem_halo_send_t* sends_host,
+                   int n_recv, const int32_t* recv_peers_host, const double* dinv_dev, const double* b_dev,
+                   double* x_dev, double* work_dev, double rtol, double atol, int64_t maxiter, int check_every,
+                   double timeout_s, double* info_host, void* stream);
 
 /* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
  * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */

@@ -78,6 +78,27 @@ def _worker(rank, world, port, N, out):
     halo(v)
     assert np.array_equal(v.numpy(), gdof)
 
+    # peer-store plan of the fused CG: what I send lands on the peer at the peer's entry of the SAME global dof,
+    # for the range form (slabs) and for the general index-list form
+    for force_lists in (False, True):
+        pl = D.build_halo_plan(mesh, ranges, rank, 3)
+        if force_lists:
+            pl.contiguous.clear()
+        sends = D.peer_send_plan(pl, rank)
+        all_g = [None] * world
+        dist.all_gather_object(all_g, gdof.tolist())
+        assert sorted(sends) == pl.neighbours
+        for s_, (src, dst) in sends.items():
+            assert np.array_equal(gdof[src.numpy()], np.asarray(all_g[s_])[dst.numpy()])
+            assert np.all((src.numpy() >= lo) & (src.numpy() < hi))          # I send owned entries only
+    # interior rows: no halo column; the rows left out are exactly the planes next to a halo
+    ia, ib = D.interior_rows(torch.as_tensor(A.indptr.astype(np.int64)), torch.as_tensor(A.indices.astype(np.int32)), lo, hi)
+    touches = np.array([(A.indices[A.indptr[r_]:A.indptr[r_ + 1]] < lo).any()
+                        or (A.indices[A.indptr[r_]:A.indptr[r_ + 1]] >= hi).any() for r_ in range(lo, hi)])
+    assert lo <= ia <= ib <= hi and not touches[ia - lo:ib - lo].any()
+    assert touches[:ia - lo].any() == (lo > 0) and touches[ib - lo:].any() == (hi < n_loc)
+    assert (ib - ia) >= (hi - lo) - 2 * 3 * plane
+
     # distributed Jacobi-CG protocol (numpy arithmetic, torch.distributed collectives)
     def allreduce(*vals):
         t = torch.tensor(vals)

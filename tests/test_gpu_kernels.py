@@ -219,6 +219,32 @@ def test_config_a_solve(T, tables, method):
     assert info["converged"]
 
 
+def test_fused_peer_cg_world1_equals_single_gpu_driver(T, tables):
+    """The peer-to-peer multi-GPU CG (`tfem_dcg_solve`) degenerates to the single-GPU driver for one rank
+    (self-published reductions, no halo): same iterates, same iteration count. A sub-range of owned rows
+    (identity rows outside it play the halo) exercises the slice / row masking."""
+    from torchfem_b200 import distributed as D
+
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 11, tables)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
+    b = dev(ref["res"])
+    x, M, info = T.csr.krylov_solve(A, b, method="cg", rtol=1e-10)
+    cg = D.FusedCG(p.indptr, p.indices, A.n, 0, A.n, D.HaloPlan(neighbours=[]), b.device)
+    try:
+        assert cg.interior == (0, A.n)
+        x2, info2 = cg.solve(A, M.dinv, b, rtol=1e-10)
+        assert info2["iterations"] == info["iterations"] and info2["converged"]
+        assert float((x2 - x).abs().max()) <= 1e-12 * float(x.abs().max())
+        x3, info3 = cg.solve(A, M.dinv, b, rtol=1e-10)   # epochs carry over between solves
+        assert torch.equal(x3, x2) and info3["iterations"] == info2["iterations"]
+        with pytest.raises(RuntimeError, match="CG failed with exit code"):
+            cg.solve(A, M.dinv, b, rtol=1e-14, maxiter=3)
+        x4, info4 = cg.solve(A, M.dinv, b, rtol=1e-10)
+        assert torch.equal(x4, x2)
+    finally:
+        cg.close()
+
+
 def test_cg_warm_start_and_zero_rhs(T, tables):
     nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 6, tables)
     ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)

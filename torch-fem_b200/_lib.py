@@ -20,7 +20,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_ENV = "TFEM_B200_LIB"
 DEFAULT_LIB = os.path.join(_HERE, "libtfem_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NCCL = range(7)
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NCCL, ERR_COMM = range(8)
+IPC_HANDLE_BYTES = 64
+MAX_NEIGHBOURS = 8
 KIND_MECH, KIND_HEAT = 0, 1
 METHOD_CG, METHOD_MINRES = 0, 1
 SPMV_CHUNK = 512
@@ -32,6 +34,13 @@ class SellStruct(ctypes.Structure):
 
 
 _SELL_P = ctypes.POINTER(SellStruct)
+
+
+class HaloSendStruct(ctypes.Structure):
+    """`tfem_halo_send_t` of include/tfem_b200.h."""
+    _fields_ = [("peer", ctypes.c_int32), ("count", c_int64), ("src_idx", c_void_p), ("dst_idx", c_void_p),
+                ("src_start", c_int64), ("dst_start", c_int64)]
+
 
 _SIGNATURES = {
     "tfem_version": (c_int, []),
@@ -59,6 +68,12 @@ _SIGNATURES = {
     "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
     "tfem_cg_stage": (c_int, [c_int, _SELL_P, c_int64, c_int64] + [c_void_p] * 5 + [c_double, c_double, c_void_p]),
+    "tfem_comm_create": (c_int, [c_int, c_int, c_int64, ctypes.POINTER(c_void_p), c_void_p]),
+    "tfem_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "tfem_comm_destroy": (c_int, [c_void_p]),
+    "tfem_dcg_solve": (c_int, [c_void_p, _SELL_P, c_int64, c_int64, c_int64, c_int64, c_int,
+                               ctypes.POINTER(HaloSendStruct), c_int, c_void_p] + [c_void_p] * 4
+                       + [c_double, c_double, c_int64, c_int, c_double, c_void_p, c_void_p]),
     "tfem_krylov_work_offset": (c_int64, [c_int64, c_int]),
     "tfem_krylov_state": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
 }

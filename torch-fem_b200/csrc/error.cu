@@ -24,6 +24,7 @@ extern "C" int tfem_get_error_string(int rc, char* buf, int len) {
     case TFEM_ERR_NOT_CONVERGED: base = "Krylov solver did not converge"; break;
     case TFEM_ERR_BREAKDOWN: base = "Krylov solver breakdown"; break;
     case TFEM_ERR_NCCL: base = "NCCL error"; break;
+    case TFEM_ERR_COMM: base = "peer communication failed"; break;
   }
   if (rc != TFEM_OK && tfem::g_last[0])
     snprintf(buf, (size_t)len, "%s (%s)", base, tfem::g_last);
