@@ -1,5 +1,8 @@
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
-mkdir -p gpurun_out
-timeout 200 $RUN --master-port 29511 tools/multi_gpu_check.py --edge 24 2>&1 | grep -E "^nccl|^fused|^\{|Error" | head -20
-echo ---- no interior
-TFEM_DCG_NO_INTERIOR=1 timeout 200 $RUN --master-port 29512 tools/multi_gpu_check.py --edge 24 2>&1 | grep -E "^nccl|^fused|^\{|Error" | head -20
+timeout 200 $RUN --master-port 29511 tools/multi_gpu_check.py --edge 24 2>&1 | grep -E "^\{|Error" | head
+timeout 200 $RUN --master-port 29512 tools/multi_gpu_check.py --edge 20 --general 2>&1 | grep -E "^\{|Error" | head
+timeout 600 $RUN --master-port 29513 bench.py --gpus 2 --steps 2 --warmup 3 2>/dev/null | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print(d['value'], d['ms_per_step'], d['config']['cg_iterations'], d['config']['per_iteration_ms'], d['e2e']['value'])"

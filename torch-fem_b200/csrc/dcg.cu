@@ -156,9 +156,9 @@ __device__ __forceinline__ void reduce_publish(const Peers& P, int set, unsigned
 // system-wide once the caller has executed __threadfence_system()
 __device__ __forceinline__ bool last_cta(unsigned int* ticket) {
   __shared__ bool s_last;
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence();
     const unsigned t = atomicAdd(ticket, 1u);
     s_last = (t == gridDim.x - 1);
     if (s_last) *ticket = 0u;
@@ -176,6 +176,7 @@ __device__ __forceinline__ void release_halo_flags(const Peers& P, const Halo& H
 // value(i) for every entry a neighbour needs -> the neighbour's p buffer `which`
 template <typename F>
 __device__ __forceinline__ void halo_send(const Peers& P, const Halo& H, int which, F value) {
+  bool stored = false;
   for (int s = 0; s < H.n_send; ++s) {
     double* dst = p_buf(P, H.send_peer[s], which);
     const int32_t* si = H.send_src[s];
@@ -185,8 +186,10 @@ __device__ __forceinline__ void halo_send(const Peers& P, const Halo& H, int whi
       const int64_t i = si ? (int64_t)si[k] : H.src0[s] + k;
       const int64_t d = di ? (int64_t)di[k] : H.dst0[s] + k;
       dst[d] = value(i);
+      stored = true;
     }
   }
+  if (stored) __threadfence_system();  // my peer stores are visible system-wide before I take a ticket
 }
 
 // x = 0 ; r = b ; p0 = D^-1 b (owned rows [o, o+n)) ; halo of p0 to the neighbours ; (r.r, r.z, b.b) -> set B
@@ -208,7 +211,6 @@ __global__ void __launch_bounds__(kVecThreads)
     rho = fma(bi, zi, rho);
   }
   halo_send(P, H, 0, [&](int64_t i) { return dinv[i] * b[i]; });
-  __threadfence_system();
   double mine[2], tot[2];
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   mine[1] = block_sum<kVecThreads>(rho, s_red);
@@ -237,21 +239,25 @@ __global__ void k_dcg_scalars_init(double* sc, Peers P, unsigned long long ep_re
   }
 }
 
-// q = A p over the owned slices [ts_lo, ts_hi): interior slices [ti_lo, ti_hi) first, the slices that read
-// halo entries after the neighbours' halo flags have reached ep_halo. p.q over owned rows -> set A.
+// q = A p over the owned slices [ts_lo, ts_hi). One strided index space: the interior slices [ti_lo, ti_hi)
+// first, then the slices that read halo entries. A warp that reaches the second part waits (once) until every
+// neighbour's halo flag has reached ep_halo; by then the flags are normally long set, so the exchange is
+// hidden behind the interior rows. p.q over owned rows -> set A.
 template <int DPN>
 __global__ void __launch_bounds__(kSellWarps * 32)
     k_dcg_spmv(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
                double* __restrict__ q, double* sc, double* partials, unsigned int* ticket, Peers P, Halo H,
                unsigned long long ep_halo, unsigned long long ep_red) {
   __shared__ double s_red[kSellWarps];
-  __shared__ int s_ok;
   if (sc[SC_DONE] != 0.0) return;
   const double* __restrict__ p = p_buf(P, P.rank, which);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * kSellWarps;
+  const int64_t n_int = ti_hi - ti_lo, n_low = ti_lo - ts_lo, n_all = ts_hi - ts_lo;
   double dot = 0.0;
-  for (int64_t t = ti_lo + (int64_t)blockIdx.x * kSellWarps + warp; t < ti_hi; t += stride) {
+  int64_t j = (int64_t)blockIdx.x * kSellWarps + warp;
+  for (; j < n_int; j += stride) {
+    const int64_t t = ti_lo + j;
     const double acc = slice_row<DPN>(A, t, p, lane);
     const int64_t row = t * 32 + lane;
     if (row >= A.dot_lo && row < A.dot_hi) {
@@ -259,26 +265,26 @@ __global__ void __launch_bounds__(kSellWarps * 32)
       dot = fma(acc, __ldg(p + row), dot);
     }
   }
-  if (threadIdx.x == 0) {
-    const unsigned long long t0 = global_ns();
-    const unsigned long long* fl = halo_flag(P, P.rank);
-    bool ok = true;
-    for (int s = 0; s < H.n_recv && ok; ++s) ok = spin_until(fl + H.recv_peer[s], ep_halo, t0, P.timeout_ns);
-    if (!ok) sc[SC_DONE] = 4.0;
-    s_ok = ok ? 1 : 0;
-  }
-  __syncthreads();
-  if (!s_ok) return;
-  const int64_t n_low = ti_lo - ts_lo, n_bnd = n_low + (ts_hi - ti_hi);
-  for (int64_t j = (int64_t)blockIdx.x * kSellWarps + warp; j < n_bnd; j += stride) {
-    const int64_t t = j < n_low ? ts_lo + j : ti_hi + (j - n_low);
-    // halo entries were written by a peer while this kernel may already have been running: read them from
-    // L2 (ld.global.cg), never through an L1 sector an interior row could have pulled in earlier
-    const double acc = slice_row<DPN, true>(A, t, p, lane);
-    const int64_t row = t * 32 + lane;
-    if (row >= A.dot_lo && row < A.dot_hi) {
-      q[row] = acc;
-      dot = fma(acc, __ldg(p + row), dot);
+  if (j < n_all) {
+    int ok = 1;
+    if (lane == 0) {
+      const unsigned long long t0 = global_ns();
+      const unsigned long long* fl = halo_flag(P, P.rank);
+      for (int s = 0; s < H.n_recv && ok; ++s) ok = spin_until(fl + H.recv_peer[s], ep_halo, t0, P.timeout_ns) ? 1 : 0;
+      if (!ok) sc[SC_DONE] = 4.0;
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    for (; ok && j < n_all; j += stride) {
+      const int64_t jb = j - n_int;
+      const int64_t t = jb < n_low ? ts_lo + jb : ti_hi + (jb - n_low);
+      // halo entries were written by a peer while this kernel may already have been running: read them from
+      // L2 (ld.global.cg), never through an L1 sector an interior row could have pulled in earlier
+      const double acc = slice_row<DPN, true>(A, t, p, lane);
+      const int64_t row = t * 32 + lane;
+      if (row >= A.dot_lo && row < A.dot_hi) {
+        q[row] = acc;
+        dot = fma(acc, __ldg(p + row), dot);
+      }
     }
   }
   const double bsum = block_sum<kSellWarps * 32>(dot, s_red);
