@@ -121,6 +121,16 @@ int tfem_assemble(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr_dev, c
                   const int64_t* indptr_dev, const int64_t* src_ptr_dev, const int32_t* src_dev,
                   const double* k_dev, const uint8_t* is_con_dev, double* vals_dev, void* stream);
 
+/* The same, fused with the Dirichlet lifting the first Newton step needs (base.py:708-741: the residual of the
+ * prescribed increment du_bc is K_unconstrained du_bc on the free rows): lift_dev[row] = sum over constrained
+ * columns c of K[row, c] * ubc_dev[c] for free rows, 0 for constrained rows — taken from the entries the
+ * masking is about to zero, so no unconstrained copy of K is ever assembled. Fixed summation order.
+ * ubc_dev: double [n_dofs] (entries at constrained DOFs are read); lift_dev: double [n_dofs] out or NULL. */
+int tfem_assemble_bc(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr_dev, const int32_t* adj_dev,
+                     const int64_t* indptr_dev, const int64_t* src_ptr_dev, const int32_t* src_dev,
+                     const double* k_dev, const uint8_t* is_con_dev, const double* ubc_dev, double* vals_dev,
+                     double* lift_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * K5 — CSR SpMV y = A x (fp64 values, int32 columns, int64 row offsets).  Replaces cusparseSpMV inside
  * cupy_cg / cupy_minres (sparse.py:411,419). Algorithmic bytes: 12*nnz + 20*n_rows.

@@ -122,6 +122,18 @@ def test_assemble(T, tag):
     ref3 = O.assemble_values(c["k"], c["k_map"], c["glob_idx"], c["diag_map"],
                              np.zeros(0, dtype=np.int64), n_dofs)
     assert rel(v3, ref3) <= TOL_K
+    # Dirichlet lifting fused into the assembly == K_unconstrained @ u_bc on the free rows (base.py:708-741)
+    rng = np.random.default_rng(3)
+    ubc = rng.standard_normal(n_dofs)
+    lift = torch.full((n_dofs,), np.nan, dtype=torch.float64, device="cuda")
+    v4 = T.csr.assemble(p, dev(c["k"]), dev(is_con), ubc=dev(ubc), lift=lift).cpu().numpy()
+    assert np.array_equal(v4, v)
+    A3 = O.to_csr(ref3, c["glob_idx"], n_dofs)
+    want = A3 @ (ubc * is_con)
+    want[is_con.astype(bool)] = 0.0
+    got = lift.cpu().numpy()
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+    assert np.all(got[is_con.astype(bool)] == 0.0)
 
 
 def _cube_system(T, N, tables):

@@ -1,7 +1,8 @@
-RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
+N=${1:-2}
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 200 $RUN --master-port 29511 tools/multi_gpu_check.py --edge 24 2>&1 | grep -E "^\{|Error" | head
 timeout 200 $RUN --master-port 29512 tools/multi_gpu_check.py --edge 20 --general 2>&1 | grep -E "^\{|Error" | head
-timeout 600 $RUN --master-port 29513 bench.py --gpus 2 --steps 2 --warmup 3 2>/dev/null | python -c "
+timeout 600 $RUN --master-port 29513 bench.py --gpus $N --steps 2 --warmup 3 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):

@@ -11,7 +11,7 @@ echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python tools/prof_driver.py --edge 150 --iters 20 > gpurun_out/${TAG}_prof.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bsell_spmv -s 12 -c 1 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sell_spmv -s 30 -c 1 \
    -o gpurun_out/${TAG}_bsell_spmv -f python tools/prof_driver.py --edge 150 --iters 3 > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log
 cat gpurun_out/${TAG}_bench.json

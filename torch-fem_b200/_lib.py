@@ -52,6 +52,7 @@ _SIGNATURES = {
     "tfem_integrate_k": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfem_assemble": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 9),
+    "tfem_assemble_bc": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 11),
     "tfem_spmv_num_chunks": (c_int64, [c_int64]),
     "tfem_spmv_plan": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_spmv": (c_int, [c_int64, c_int64] + [c_void_p] * 7),

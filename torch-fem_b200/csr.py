@@ -417,8 +417,11 @@ def integrate_k(kind: int, bref: Tensor, w: Tensor, nodes: Tensor, elements: Ten
     return k
 
 
-def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | None = None) -> Tensor:
-    """CSR values from element matrices with kernel K2/K3 (deterministic; Dirichlet rows/cols fused)."""
+def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | None = None,
+             ubc: Tensor | None = None, lift: Tensor | None = None) -> Tensor:
+    """CSR values from element matrices with kernel K2/K3 (deterministic; Dirichlet rows/cols fused).
+    With `ubc` (prescribed values, [n_dofs]) and `lift` ([n_dofs] out) the kernel also returns the Dirichlet
+    lifting K[free, con] @ ubc[con] (the right-hand side of the first Newton step, base.py:708-741)."""
     L.require_cuda(k)
     nd = pattern.nn * pattern.dpn
     if k.dtype != torch.float64:
@@ -429,9 +432,15 @@ def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | N
     if is_con is not None:
         is_con = is_con.to(torch.uint8).contiguous() if is_con.dtype != torch.uint8 else is_con.contiguous()
     vals = out if out is not None else torch.empty(pattern.nnz, dtype=torch.float64, device=k.device)
-    L.check(L.lib.tfem_assemble(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
-                                L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
-                                L.ptr(pattern.src), L.ptr(k), L.ptr(is_con), L.ptr(vals), L.stream()))
+    if lift is not None:
+        if is_con is None or ubc is None:
+            raise ValueError("the Dirichlet lifting needs is_con and ubc")
+        L.require_cuda(ubc, lift)
+        ubc = ubc.to(torch.float64).contiguous()
+    L.check(L.lib.tfem_assemble_bc(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
+                                   L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
+                                   L.ptr(pattern.src), L.ptr(k), L.ptr(is_con),
+                                   L.ptr(ubc) if lift is not None else None, L.ptr(vals), L.ptr(lift), L.stream()))
     return vals
 
 

@@ -17,13 +17,16 @@ namespace {
 
 constexpr int kWarps = 8;
 
-template <int DPN>
+// NN = nodes per element as a compile-time constant (0: run-time value) so the slot decoding needs no
+// integer division. Up to 4 contributions are in flight per entry (independent loads), added in slot order.
+template <int DPN, int NN>
 __global__ void __launch_bounds__(kWarps * 32)
-    k_assemble(int64_t n_nod, int nn, const int64_t* __restrict__ node_ptr,
+    k_assemble(int64_t n_nod, int nn_rt, const int64_t* __restrict__ node_ptr,
                const int32_t* __restrict__ adj, const int64_t* __restrict__ indptr,
                const int64_t* __restrict__ src_ptr, const int32_t* __restrict__ src,
                const double* __restrict__ k, const uint8_t* __restrict__ is_con,
-               double* __restrict__ vals) {
+               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift) {
+  const int nn = NN > 0 ? NN : nn_rt;
   const int lane = threadIdx.x & 31;
   const int64_t node = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
   if (node >= n_nod) return;
@@ -31,7 +34,10 @@ __global__ void __launch_bounds__(kWarps * 32)
   const int cnt = (int)(node_ptr[node + 1] - nb);
   const int64_t row0 = node * DPN;
   if (cnt == 0) {  // unreferenced node: lone diagonal, value 0 unless constrained (base.py:419)
-    if (lane < DPN) vals[indptr[row0 + lane]] = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
+    if (lane < DPN) {
+      vals[indptr[row0 + lane]] = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
+      if (lift) lift[row0 + lane] = 0.0;
+    }
     return;
   }
   const int nd = nn * DPN;
@@ -42,23 +48,60 @@ __global__ void __launch_bounds__(kWarps * 32)
     const int64_t row = row0 + i;
     const int64_t rp = indptr[row];
     const bool row_con = is_con && is_con[row];
+    double lsum = 0.0;
     for (int t = lane; t < rowlen; t += 32) {
       const int p = t / DPN, j = t - p * DPN;
       const int64_t sb = src_ptr[nb + p], se = src_ptr[nb + p + 1];
       double acc = 0.0;
-      for (int64_t s = sb; s < se; ++s) {
-        const int c = src[s];  // e*nn*nn + a*nn + b
-        const int b = c % nn;
-        const int ea = c / nn;  // e*nn + a
-        const int a = ea % nn;
-        const int64_t e = ea / nn;
-        acc += k[e * nd2 + (int64_t)(a * DPN + i) * nd + b * DPN + j];
+      for (int64_t s = sb; s < se; s += 4) {
+        int c[4];
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c[u] = (s + u < se) ? src[s + u] : -1;  // e*nn*nn + a*nn + b
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c[u] < 0 ? 0 : c[u];
+          const int ea = cc / nn, bq = cc - ea * nn;
+          const int e = ea / nn, aq = ea - e * nn;
+          v[u] = c[u] < 0 ? 0.0 : k[e * nd2 + (int64_t)(aq * DPN + i) * nd + bq * DPN + j];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc += v[u];  // + 0.0 for the missing ones: exact
       }
       const int64_t col = (int64_t)adj[nb + p] * DPN + j;
-      if (row_con || (is_con && is_con[col])) acc = (col == row) ? 1.0 : 0.0;
+      const bool col_con = is_con && is_con[col];
+      // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
+      if (lift && col_con && !row_con) lsum = fma(acc, ubc[col], lsum);
+      if (row_con || col_con) acc = (col == row) ? 1.0 : 0.0;
       vals[rp + t] = acc;
     }
+    if (lift) {
+      lsum = warp_sum(lsum);
+      if (lane == 0) lift[row] = lsum;
+    }
   }
+}
+
+template <int DPN>
+int launch_assemble(int64_t n_nod, int nn, const int64_t* node_ptr, const int32_t* adj, const int64_t* indptr,
+                    const int64_t* src_ptr, const int32_t* src, const double* k, const uint8_t* is_con,
+                    const double* ubc, double* vals, double* lift, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n_nod + kWarps - 1) / kWarps);
+#define TFEM_ASM(NNC)                                                                                        \
+  k_assemble<DPN, NNC><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, \
+                                                     ubc, vals, lift)
+  switch (nn) {
+    case 3: TFEM_ASM(3); break;
+    case 4: TFEM_ASM(4); break;
+    case 6: TFEM_ASM(6); break;
+    case 8: TFEM_ASM(8); break;
+    case 10: TFEM_ASM(10); break;
+    case 20: TFEM_ASM(20); break;
+    default: TFEM_ASM(0); break;
+  }
+#undef TFEM_ASM
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
 }
 
 }  // namespace
@@ -66,27 +109,26 @@ __global__ void __launch_bounds__(kWarps * 32)
 
 using namespace tfem;
 
-extern "C" int tfem_assemble(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
-                             const int64_t* indptr, const int64_t* src_ptr, const int32_t* src,
-                             const double* k, const uint8_t* is_con, double* vals, void* stream_) {
+extern "C" int tfem_assemble_bc(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
+                                const int64_t* indptr, const int64_t* src_ptr, const int32_t* src,
+                                const double* k, const uint8_t* is_con, const double* ubc, double* vals,
+                                double* lift, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   TFEM_REQUIRE(node_ptr && adj && indptr && src_ptr && src && k && vals, "assemble: null pointer");
   TFEM_REQUIRE(n_nod > 0 && nn > 0, "assemble: bad sizes");
-  const unsigned grid = (unsigned)((n_nod + kWarps - 1) / kWarps);
+  TFEM_REQUIRE(!lift || (is_con && ubc), "assemble: the Dirichlet lifting needs is_con and the prescribed values");
   switch (dpn) {
-    case 1:
-      k_assemble<1><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, vals);
-      break;
-    case 2:
-      k_assemble<2><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, vals);
-      break;
-    case 3:
-      k_assemble<3><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, vals);
-      break;
-    default:
-      set_last_error("invalid argument", "assemble: dofs per node must be 1, 2 or 3");
-      return TFEM_ERR_INVALID;
+    case 1: return launch_assemble<1>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
+    case 2: return launch_assemble<2>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
+    case 3: return launch_assemble<3>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
   }
-  TFEM_LAUNCH_CHECK();
-  return TFEM_OK;
+  set_last_error("invalid argument", "assemble: dofs per node must be 1, 2 or 3");
+  return TFEM_ERR_INVALID;
+}
+
+extern "C" int tfem_assemble(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
+                             const int64_t* indptr, const int64_t* src_ptr, const int32_t* src,
+                             const double* k, const uint8_t* is_con, double* vals, void* stream_) {
+  return tfem_assemble_bc(n_nod, nn, dpn, node_ptr, adj, indptr, src_ptr, src, k, is_con, nullptr, vals, nullptr,
+                          stream_);
 }

@@ -4,11 +4,14 @@
 // (src/torchfem/base.py:293-314 eval_shape_functions: einsum + batched LU det/inv; base.py:1086-1090 /
 // :1272-1278: 3-operand einsum + compute_k + accumulate) and its [n_int,n_elem,d,nn] temporaries.
 //
-// Mapping: one thread per (element, row node p, column node r); it owns the dpn x dpn block of k_e.
-// Per element the node coordinates, the physical gradients B_q = J_q^-1 b_q of all Gauss points, w_q detJ_q
-// and the material tangent are staged in shared memory (the reference-space table b_q and the weights come
-// in as a __grid_constant__ kernel parameter, so the call is re-entrant across streams). The finished
-// element matrix is staged in shared memory and written with fully coalesced stores: HBM traffic is
+// Mapping: one thread per (element, matrix row (a,i), chunk of CB = 8 column nodes); it owns 8 dpn entries of one
+// row of k_e and contracts in two stages per Gauss point — U[k,L] = sum_J (w detJ B[J,a]) C[i,J,k,L] once, then
+// k[(a,i),(b,k)] += sum_L U[k,L] B[L,b] for its columns — 19 kFMA per Hexa1 element instead of the 52 kFMA of
+// the direct triple product, and ~1.8 FMA per shared-memory load instead of 1 (the direct form was bound by
+// the LDS pipe), at ~100 registers. Per element the node coordinates, the physical gradients B_q = J_q^-1 b_q of all Gauss points,
+// w_q detJ_q and the material tangent are staged in shared memory (the reference-space table b_q and the
+// weights come in as a __grid_constant__ kernel parameter, so the call is re-entrant across streams). The
+// finished element matrix is staged in shared memory and written with fully coalesced stores: HBM traffic is
 // the 8*(nn*dpn)^2 B/element output plus ~1 kB/element of inputs.
 #include "common.cuh"
 
@@ -54,8 +57,10 @@ __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&i
   return det;
 }
 
+constexpr int kCB = 8;  // column nodes per thread
+
 template <int KIND, int DIM, int NN, int NINT, int EPC, bool PERGP>
-__global__ void __launch_bounds__(((EPC * NN * NN + 31) / 32) * 32)
+__global__ void __launch_bounds__(((EPC * NN * ((KIND == TFEM_KIND_MECH) ? DIM : 1) * ((NN + kCB - 1) / kCB) + 31) / 32) * 32)
     k_integrate(const __grid_constant__ Tables<DIM, NN, NINT> tab, const double* __restrict__ nodes,
                 const int64_t* __restrict__ elements, int64_t n_elem,
                 const double* __restrict__ tangent, const double* __restrict__ scale,
@@ -64,7 +69,8 @@ __global__ void __launch_bounds__(((EPC * NN * NN + 31) / 32) * 32)
   constexpr int ND = NN * DPN;
   constexpr int TS = (KIND == TFEM_KIND_MECH) ? DIM * DIM * DIM * DIM : DIM * DIM;
   constexpr int NQC = PERGP ? NINT : 1;
-  constexpr int TPE = NN * NN;  // threads per element
+  constexpr int NCH = (NN + kCB - 1) / kCB;
+  constexpr int TPE = ND * NCH;  // threads per element
   // per-element shared layout (doubles)
   constexpr int OFF_X = 0;
   constexpr int OFF_B = OFF_X + NN * DIM;
@@ -94,8 +100,7 @@ __global__ void __launch_bounds__(((EPC * NN * NN + 31) / 32) * 32)
   }
   __syncthreads();
 
-  if (active && pr < NINT) {
-    const int q = pr;
+  for (int q = pr; active && q < NINT; q += TPE) {
     double J[DIM][DIM], inv[DIM][DIM];
 #pragma unroll
     for (int i = 0; i < DIM; ++i)
@@ -122,57 +127,56 @@ __global__ void __launch_bounds__(((EPC * NN * NN + 31) / 32) * 32)
   __syncthreads();
 
   if (active) {
-    const int p = pr / NN, r = pr - p * NN;
-    double acc[DPN][DPN];
+    const int row = pr / NCH, b0 = (pr - row * NCH) * kCB;  // my matrix row (a, i) and first column node
+    const int a = row / DPN, i = row - a * DPN;
+    double acc[kCB][DPN];
 #pragma unroll
-    for (int i = 0; i < DPN; ++i)
+    for (int c = 0; c < kCB; ++c)
 #pragma unroll
-      for (int k = 0; k < DPN; ++k) acc[i][k] = 0.0;
+      for (int k = 0; k < DPN; ++k) acc[c][k] = 0.0;
 
 #pragma unroll 1
     for (int q = 0; q < NINT; ++q) {
-      const double* Cq = S + OFF_C + (PERGP ? q * TS : 0);
-      double bp[DIM], br[DIM];
-#pragma unroll
-      for (int j = 0; j < DIM; ++j) {
-        bp[j] = S[OFF_B + (q * DIM + j) * NN + p];
-        br[j] = S[OFF_B + (q * DIM + j) * NN + r];
-      }
+      // mechanics: row i of the tangent, C[i, :, :, :] (DIM^3 doubles); heat: kappa
+      const double* Cq = S + OFF_C + (PERGP ? q * TS : 0) + ((KIND == TFEM_KIND_MECH) ? i * DIM * DIM * DIM : 0);
       const double wd = S[OFF_WD + q];
-      if (KIND == TFEM_KIND_MECH) {
-        double s[DPN][DPN];
+      double bp[DIM];
 #pragma unroll
-        for (int i = 0; i < DPN; ++i)
+      for (int j = 0; j < DIM; ++j) bp[j] = wd * S[OFF_B + (q * DIM + j) * NN + a];
+      // stage 1: U[k][L] = sum_J (w detJ B[J,a]) C[i,J,k,L]   (heat: U[0][L] = sum_J (w detJ B[J,a]) kappa[J,L])
+      double U[DPN][DIM];
 #pragma unroll
-          for (int k = 0; k < DPN; ++k) s[i][k] = 0.0;
+      for (int k = 0; k < DPN; ++k)
 #pragma unroll
-        for (int Jx = 0; Jx < DIM; ++Jx)
+        for (int L = 0; L < DIM; ++L) {
+          double u = 0.0;
 #pragma unroll
-          for (int L = 0; L < DIM; ++L) {
-            const double bb = bp[Jx] * br[L];
+          for (int Jx = 0; Jx < DIM; ++Jx) u = fma(bp[Jx], Cq[(Jx * DPN + k) * DIM + L], u);
+          U[k][L] = u;
+        }
+      // stage 2: my columns
 #pragma unroll
-            for (int i = 0; i < DPN; ++i)
+      for (int c = 0; c < kCB; ++c) {
+        if (b0 + c < NN) {
+          double br[DIM];
 #pragma unroll
-              for (int k = 0; k < DPN; ++k)
-                s[i][k] = fma(bb, Cq[((i * DIM + Jx) * DIM + k) * DIM + L], s[i][k]);
+          for (int L = 0; L < DIM; ++L) br[L] = S[OFF_B + (q * DIM + L) * NN + b0 + c];
+#pragma unroll
+          for (int k = 0; k < DPN; ++k) {
+            double t = acc[c][k];
+#pragma unroll
+            for (int L = 0; L < DIM; ++L) t = fma(U[k][L], br[L], t);
+            acc[c][k] = t;
           }
-#pragma unroll
-        for (int i = 0; i < DPN; ++i)
-#pragma unroll
-          for (int k = 0; k < DPN; ++k) acc[i][k] = fma(wd, s[i][k], acc[i][k]);
-      } else {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < DIM; ++i)
-#pragma unroll
-          for (int j = 0; j < DIM; ++j) s = fma(Cq[i * DIM + j] * bp[i], br[j], s);
-        acc[0][0] = fma(wd, s, acc[0][0]);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < DPN; ++i)
+    for (int c = 0; c < kCB; ++c)
+      if (b0 + c < NN) {
 #pragma unroll
-      for (int k = 0; k < DPN; ++k) S[OFF_K + (p * DPN + i) * ND + r * DPN + k] = acc[i][k];
+        for (int k = 0; k < DPN; ++k) S[OFF_K + row * ND + (b0 + c) * DPN + k] = acc[c][k];
+      }
   }
   __syncthreads();
 
@@ -189,8 +193,8 @@ template <int KIND, int DIM, int NN, int NINT>
 int launch(const double* bref, const double* w, const double* nodes, const int64_t* elements,
            int64_t n_elem, const double* tangent, int per_gp, const double* scale, double* k_out,
            int32_t* neg_jac, cudaStream_t st) {
-  constexpr int TPE = NN * NN;
-  constexpr int EPC = (256 / TPE) > 0 ? (256 / TPE) : 1;
+  constexpr int TPE = NN * ((KIND == TFEM_KIND_MECH) ? DIM : 1) * ((NN + kCB - 1) / kCB);
+  constexpr int EPC = (128 / TPE) > 0 ? (128 / TPE) : 1;
   constexpr int THREADS = ((EPC * TPE + 31) / 32) * 32;
   constexpr int DPN = (KIND == TFEM_KIND_MECH) ? DIM : 1;
   constexpr int ND = NN * DPN;
