@@ -177,7 +177,7 @@ def run_ours(args):
     from torchfem_b200 import csr
     from oracle import fem_oracle as O  # tables only (bref/w are 200 numbers) + cpu_baseline leg
 
-    if world > 1:
+    if world > 1 or args.config == "C":
         from torchfem_b200 import distributed as D
         return D.bench_multi_gpu(args, METRIC, UNIT, RTOL)
 
@@ -384,13 +384,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--edge", type=int, default=150, help="elements per cube edge (150 = BASELINE configs[1])")
+    ap.add_argument("--edge", type=int, default=None,
+                    help="elements per cube edge (default 150 = BASELINE configs[1]; 120 for --config C)")
+    ap.add_argument("--config", default="B", choices=["B", "C"],
+                    help="B: Hexa1 cube, weak scaling over GPUs (default, the metric's config). C: Hexa2 cube of "
+                         "BASELINE configs[2], one global mesh partitioned over the GPUs (strong scaling)")
     ap.add_argument("--cpu-edge", type=int, default=40, help="elements per edge of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-api", action="store_true", help="skip the Solid.solve end-to-end leg")
     ap.add_argument("--dist-cg", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-to-peer CG (tfem_dcg_solve) or the host-driven NCCL variant")
     args = ap.parse_args()
+    if args.edge is None:
+        args.edge = 120 if args.config == "C" else 150
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -168,3 +168,29 @@ def test_node_ranges_and_general_partition():
     assert int(touching.sum()) == len(m.element_ids)
     plan = D.build_halo_plan(m, [(0, 9), (9, 27), (27, 36)], 1, 3)  # world==1 process: only `need` side is exercised
     assert plan.neighbours == [0, 2]
+
+
+def test_coordinate_partition_of_a_quadratic_mesh():
+    """Config C in small: linear_to_quadratic appends the mid-side nodes after the corner nodes, so node blocks of
+    the mesh's own numbering are not slabs; the x-coordinate renumbering makes them slabs with <= 2 neighbours."""
+    torch.set_default_dtype(torch.float64)
+    from torchfem_b200 import distributed as D
+    from torchfem_b200.elements import linear_to_quadratic
+    from torchfem_b200.mesh import cube_hexa
+
+    with torch.device("cpu"):
+        n, e = linear_to_quadratic(*cube_hexa(9, 4, 4, 2.0, 1.0, 1.0))
+    world = 3
+    seen = torch.zeros(n.shape[0], dtype=torch.int64)
+    for r in range(world):
+        nh, m, ranges, perm = D.coordinate_partition(n, e, world, r)
+        g = m.global_nodes
+        assert torch.equal(torch.sort(perm).values, torch.arange(n.shape[0]))      # a permutation
+        assert bool((n[perm][1:, 0] >= n[perm][:-1, 0]).all())                     # sorted by x
+        assert torch.equal(n[perm[g]], nh)                                          # local coordinates
+        assert torch.equal(perm[g][m.elements], e[m.element_ids])                   # local connectivity
+        owned = perm[g[m.lo:m.lo + m.n_owned]]
+        seen[owned] += 1
+        plan = D.build_halo_plan(m, ranges, r, 3)
+        assert plan.neighbours == [s for s in (r - 1, r + 1) if 0 <= s < world]
+    assert bool((seen == 1).all())                                                  # every node owned exactly once

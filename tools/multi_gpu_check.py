@@ -23,6 +23,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--edge", type=int, default=24)
     ap.add_argument("--general", action="store_true", help="force index-list halos instead of contiguous ranges")
+    ap.add_argument("--hexa2", action="store_true",
+                    help="20-node hexahedra from linear_to_quadratic, x-coordinate partition (config C in small)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
@@ -31,15 +33,16 @@ def main():
     torch.set_default_dtype(torch.float64)
     import torchfem_b200 as T
     from torchfem_b200 import _lib as L, csr, distributed as D
-    from torchfem_b200.elements import Hexa1
+    from torchfem_b200.elements import Hexa1, Hexa2, linear_to_quadratic
     from torchfem_b200.materials import IsotropicElasticity3D
     from torchfem_b200.mesh import cube_hexa
 
     E = a.edge
     Ex = E * world
     h = 1.0 / E
-    bref = Hexa1.B(Hexa1.ipoints.to(torch.float64).cpu())
-    w = Hexa1.iweights.to(torch.float64).cpu()
+    ET = Hexa2 if a.hexa2 else Hexa1
+    bref = ET.B(ET.ipoints.to(torch.float64).cpu())
+    w = ET.iweights.to(torch.float64).cpu()
     C1 = IsotropicElasticity3D(1000.0, 0.3).C.to(torch.float64).cpu()
 
     def system(nodes_h, elements_h):
@@ -59,7 +62,13 @@ def main():
         rhs.masked_fill_(is_con.bool(), 0.0)
         return p, A, rhs
 
-    nodes_h, mesh, ranges, dims = D.cube_slab(Ex, E, E, h, world, rank)
+    perm = None
+    if a.hexa2:
+        with torch.device("cpu"):
+            nodes_g, elements_g = linear_to_quadratic(*cube_hexa(Ex + 1, E + 1, E + 1, Ex * h, 1.0, 1.0))
+        nodes_h, mesh, ranges, perm = D.coordinate_partition(nodes_g, elements_g, world, rank)
+    else:
+        nodes_h, mesh, ranges, dims = D.cube_slab(Ex, E, E, h, world, rank)
     plan = D.build_halo_plan(mesh, ranges, rank, 3)
     if a.general:
         plan.contiguous.clear()
@@ -109,12 +118,17 @@ def main():
     parts = [padded[i][:3 * (r1 - r0)] for i, (r0, r1) in enumerate(ranges)] if rank == 0 else None
     ok, line = True, None
     if rank == 0:
-        nodes_g, elements_g = cube_hexa(Ex + 1, E + 1, E + 1, Ex * h, 1.0, 1.0)
+        if not a.hexa2:
+            nodes_g, elements_g = cube_hexa(Ex + 1, E + 1, E + 1, Ex * h, 1.0, 1.0)
         pg, Ag, rhs_g = system(nodes_g.cpu(), elements_g.cpu())
         xg, _, info_g = csr.krylov_solve(Ag, rhs_g, method="cg", rtol=1e-10)
         xf = torch.cat(parts)
+        if perm is not None:  # parts are in the partition's numbering: back to the mesh's own
+            xo = torch.empty_like(xf)
+            xo.view(-1, 3)[perm.to(dev)] = xf.view(-1, 3)
+            xf = xo
         d_g = float((xf - xg).abs().max() / xg.abs().max())
-        line = {"world": world, "edge": E, "n_dofs": int(xg.numel()), "general_halo": a.general,
+        line = {"world": world, "edge": E, "n_dofs": int(xg.numel()), "general_halo": a.general, "hexa2": a.hexa2, "neighbours": plan.neighbours,
                 "iters_fused": info_f["iterations"], "iters_nccl": info_n["iterations"],
                 "iters_single": info_g["iterations"], "rel_fused_vs_nccl": d_fn / nrm,
                 "rel_fused_vs_single": d_g, "bitwise_reproducible": repro, "interior": list(cg.interior),

@@ -395,6 +395,24 @@ def cube_slab(Ex: int, Ey: int, Ez: int, h: float, world: int, rank: int):
     return nodes, mesh, ranges, (Nx, Ny, Nz)
 
 
+def coordinate_partition(nodes: Tensor, elements: Tensor, world: int, rank: int, axis: int = 0):
+    """Rank-local part of an arbitrary mesh (host tensors): nodes are renumbered by (coordinate along `axis`, old
+    id) so that contiguous blocks of the new numbering are slabs, then cut into `world` equal node blocks.
+    Returns (local node coordinates, LocalMesh in the NEW numbering, ranges, perm) with perm[new id] = old id.
+    Used for meshes whose numbering is not slab-contiguous, e.g. `linear_to_quadratic` output (config C), where
+    the mid-side nodes are appended after the corner nodes. Halos are index lists, not ranges."""
+    nodes, elements = nodes.cpu(), elements.cpu()
+    key = nodes[:, axis].contiguous()
+    perm = torch.sort(key, stable=True).indices          # stable: ties keep the old order
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(perm.numel())
+    el_new = inv[elements]
+    ranges = node_ranges(nodes.shape[0], world)
+    n0, n1 = ranges[rank]
+    mesh = local_mesh(el_new, n0, n1)
+    return nodes[perm[mesh.global_nodes]].contiguous(), mesh, ranges, perm
+
+
 def weak_scaling_edge(E: int, world: int) -> int:
     """Edge (in elements) of the global cube that gives every rank a config-sized share: E * world^(1/3)."""
     return int(round(E * world ** (1.0 / 3.0)))
@@ -408,17 +426,48 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
     distributed PCG."""
     from . import _lib as L
     from . import csr
-    from .elements import Hexa1
     from .materials import IsotropicElasticity3D
 
-    rank, world = dist.get_rank(), dist.get_world_size()
+    multi = dist.is_initialized()
+
+    def _barrier():
+        if multi:
+            dist.barrier()
+
+    def _allreduce(t, op=dist.ReduceOp.SUM):
+        if multi:
+            dist.all_reduce(t, op=op)
+
+    rank, world = (dist.get_rank(), dist.get_world_size()) if multi else (0, 1)
     dev = torch.device("cuda", torch.cuda.current_device())
     E = args.edge
-    Eg = weak_scaling_edge(E, world)
-    h = 1.0 / E
-    nodes_h, mesh, ranges, (Nx, Ny, Nz) = cube_slab(Eg, Eg, Eg, h, world, rank)
-    Lx = Eg * h
-    n_dofs_global = Nx * Ny * Nz * 3
+    config_c = getattr(args, "config", "B") == "C"
+    if config_c:
+        # BASELINE configs[2]: Hexa2 (20-node serendipity) cube, strong scaling of ONE global mesh. The mesh is
+        # made once per rank on the host with the reference-order generator, then cut by x-coordinate.
+        from .elements import Hexa2 as EType, linear_to_quadratic
+        from .mesh import cube_hexa
+
+        with torch.device("cpu"):
+            nodes_g, elements_g = linear_to_quadratic(*cube_hexa(E + 1, E + 1, E + 1))
+        nodes_h, mesh, ranges, _ = coordinate_partition(nodes_g, elements_g, world, rank)
+        n_dofs_global = 3 * nodes_g.shape[0]
+        n_elem_global = elements_g.shape[0]
+        del nodes_g, elements_g
+        Eg, Lx = E, 1.0
+        workload = (f"linear-elastic Hexa2 (20-node) cube {E}^3 elements ({n_dofs_global} DOFs), x-coordinate partition "
+                    f"into {world} node blocks, Jacobi-PCG to 1e-8 (BASELINE configs[2]; strong scaling)")
+    else:
+        from .elements import Hexa1 as EType
+
+        Eg = weak_scaling_edge(E, world)
+        h = 1.0 / E
+        nodes_h, mesh, ranges, (Nx, Ny, Nz) = cube_slab(Eg, Eg, Eg, h, world, rank)
+        Lx = Eg * h
+        n_dofs_global = Nx * Ny * Nz * 3
+        n_elem_global = Eg ** 3
+        workload = (f"linear-elastic Hexa1 cube {Eg}^3 elements (= {world} x {E}^3, weak scaling of BASELINE "
+                    f"configs[1]), {world} slabs of x-planes, Jacobi-PCG to 1e-8")
     con_h = torch.zeros(mesh.n_local, 3, dtype=torch.bool)
     disp_h = torch.zeros(mesh.n_local, 3, dtype=torch.float64)
     con_h[nodes_h[:, 0] == 0.0, :] = True
@@ -431,8 +480,8 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
             torch.full((len(mesh.elements),), 1000.0), torch.full((len(mesh.elements),), 0.3)]
     host = [t.pin_memory() for t in host]
     nodes, elements, is_con, disp, E_mod, nu = (t.to(dev) for t in host)
-    ip = Hexa1.ipoints.to(torch.float64).cpu()
-    bref, w = Hexa1.B(ip), Hexa1.iweights.to(torch.float64).cpu()
+    ip = EType.ipoints.to(torch.float64).cpu()
+    bref, w = EType.B(ip), EType.iweights.to(torch.float64).cpu()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -479,46 +528,46 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
     sampler = ClockSampler(torch.cuda.current_device())
     if rank == 0:
         sampler.start()
-    dist.barrier()
+    _barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    dist.barrier()
+    _barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    _allreduce(t, dist.ReduceOp.MAX)
     ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
     # end to end: every rank's inputs come from pinned host memory, its part of the solution goes back
     step_e2e()
-    dist.barrier()
+    _barrier()
     torch.cuda.synchronize()
     n_e2e = max(1, min(args.steps, 2))
     e0.record()
     for _ in range(n_e2e):
         step_e2e()
     e1.record()
-    dist.barrier()
+    _barrier()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    _allreduce(t, dist.ReduceOp.MAX)
     ms_e2e = float(t.item())
     io = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host), 8 * n_owned], dtype=torch.int64, device=dev)
-    dist.all_reduce(io)
+    _allreduce(io)
 
     # true global relative residual of the last solve
     A, rhs, x, info = state["A"], state["rhs"], state["x"], state["info"]
     halo(x)
     r = (rhs - A.matvec(x))[row_lo:row_lo + n_owned]
     num = torch.stack([(r * r).sum(), (rhs[row_lo:row_lo + n_owned] ** 2).sum()])
-    dist.all_reduce(num)
+    _allreduce(num)
     true_res = float((num[0] / num[1]).sqrt())
     nnz_owned = torch.tensor([int(pattern.indptr[row_lo + n_owned] - pattern.indptr[row_lo])], device=dev)
-    dist.all_reduce(nnz_owned)
+    _allreduce(nnz_owned)
 
     # SpMV kernel time on this rank (local rows), for the per-GPU roofline
     xs = torch.randn(A.n, dtype=torch.float64, device=dev)
@@ -541,16 +590,15 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
         line = {
             "metric": metric, "value": n_dofs_global / (ms / 1e3), "unit": unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"linear-elastic Hexa1 cube {Eg}^3 elements (= {world} x {E}^3, weak scaling of "
-                                   f"BASELINE configs[1]), {world} slabs of x-planes, Jacobi-PCG to 1e-8",
-                       "n_dofs": int(n_dofs_global), "nnz": int(nnz_owned.item()), "rtol": rtol,
+            "scaling": "strong" if config_c else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_dofs": int(n_dofs_global), "n_elem": int(n_elem_global),
+                       "nnz": int(nnz_owned.item()), "rtol": rtol,
                        "cg_iterations": info["iterations"], "true_rel_residual": true_res,
                        "per_rank_local_dofs": int(A.n), "halo_bytes_per_exchange": plan.bytes_per_exchange(),
                        "collectives_per_iteration": ("fused into the kernels: halo = peer stores of the direction "
                                                      "update, 2 all-reduces = peer stores + flags (tfem_dcg_solve)")
                        if fused else "NCCL: 1 halo exchange (P2P send/recv) + 2 all-reduces (1 and 2 doubles)",
-                       "l2_policy": "inputs larger than L2 (per-rank CSR matrix ~10 GB vs 126 MB L2)",
+                       "l2_policy": f"inputs larger than L2 (per-rank SELL matrix {8.5e-9 * pattern.nnz:.1f} GB vs 126 MB L2)",
                        "setup_ms_pattern": setup_ms,
                        "note": "Jacobi-PCG iterations grow with the cube edge (~N^(1/3)), so DOF/s per GPU "
                                "falls with N even at perfect per-iteration scaling; per_iteration_ms is the "
@@ -569,5 +617,6 @@ def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
         print(json.dumps(line))
     if cg is not None:
         cg.close()
-    dist.barrier()
-    dist.destroy_process_group()
+    _barrier()
+    if multi:
+        dist.destroy_process_group()
