@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "DOFs solved/sec (assembly+PCG)"
 UNIT = "DOF/s"
 RTOL = 1e-8
+NCU_SPMV_DRAM_BYTES_CONFIG_B = 7233025000 + 76604160
 
 
 def measured_peaks():
@@ -371,7 +372,11 @@ def run_ours(args):
                      "csr_chunk_kernel_ms": spmv_csr_ms,
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "frac_of_spec_8000": achieved / 8000.0,
-                     "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms, "traffic": None},
+                     "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at config B from the committed
+                     # `ncu --set full` capture (profiles/r1_d_bsell_spmv_ncu.txt); other sizes: not captured
+                     "traffic": NCU_SPMV_DRAM_BYTES_CONFIG_B if E == 150 else None,
+                     "traffic_source": "profiles/r1_d_bsell_spmv_ncu.txt (7.233 GB read + 0.077 GB written)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }

@@ -111,6 +111,24 @@ int tfem_integrate_k(int kind, int dim, int nn, int n_int, const double* bref_ho
                      const double* scale_dev, double* k_dev, int32_t* neg_jac_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * K9/K10 — geometry contractions of the RESIDUAL evaluation, all Gauss points in one launch. The material
+ * update between them stays with the caller (torch; the adjoint differentiates through it, sparse.py:689-705).
+ *   tfem_elem_grad :  H[q,e,i,J] = s * sum_n u_e[e,n,i] B_q[e,J,n]        replaces `du @ B[i]^T` inside the Gauss
+ *                     loop (base.py:1052; heat base.py:1241-1243) and eval_shape_functions (base.py:293-314)
+ *   tfem_elem_force:  f_e[e,n,i] = sum_q s * sum_J B_q[e,J,n] P[q,e,i,J]  replaces `f += w * compute_f(detJ, B, P)`
+ *                     (base.py:1082-1083; solid.py:56-58, planar.py:90-92)
+ * s = 1 if !weighted, else w_q * detJ_q * scale[e] (scale_dev may be NULL). Each call is the transpose of the
+ * other with the same `weighted` on the other side, so they are also each other's backward.
+ * u_e_dev: double [n_elem, nn, dpn]; H_dev / P_dev: double [n_int, n_elem, dpn, dim]; f_e_dev: [n_elem, nn, dpn];
+ * dpn = dim (mechanics) or 1 (heat). neg_jac_dev as in tfem_integrate_k. Element types as tfem_integrate_k. */
+int tfem_elem_grad(int dim, int nn, int n_int, int dpn, const double* bref_host, const double* w_host,
+                   const double* nodes_dev, const int64_t* elements_dev, int64_t n_elem, const double* u_e_dev,
+                   const double* scale_dev, int weighted, double* H_dev, int32_t* neg_jac_dev, void* stream);
+int tfem_elem_force(int dim, int nn, int n_int, int dpn, const double* bref_host, const double* w_host,
+                    const double* nodes_dev, const int64_t* elements_dev, int64_t n_elem, const double* P_dev,
+                    const double* scale_dev, int weighted, double* f_e_dev, int32_t* neg_jac_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * K2/K3 — deterministic assembly.  Replaces FEM.assemble_matrix (base.py:398-426): index_add_ scatter
  * (atomics on CUDA) becomes a gather over the precomputed `src` permutation with a fixed summation
  * order (element order), fused with the Dirichlet masking (rows/cols of constrained DOFs zeroed, unit

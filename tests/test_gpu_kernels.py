@@ -136,6 +136,45 @@ def test_assemble(T, tag):
     assert np.all(got[is_con.astype(bool)] == 0.0)
 
 
+@pytest.mark.parametrize("tag", MECH_CASES + HEAT_CASES)
+def test_residual_contractions(T, tag, tables):
+    """K9/K10 (`tfem_elem_grad` / `tfem_elem_force`) against the reference formulas evaluated with torch on the
+    shape gradients B = J^-1 b (base.py:306-314, 1052, 1082-1083; solid.py:56-58), for every element type; and
+    the pair is each other's transpose (that is their autograd backward)."""
+    from torchfem_b200 import residual as R
+
+    c = load_case(f"case_{tag}.npz")
+    et = str(c["etype"])
+    heat = tag.startswith("heat")
+    nodes, elements = dev(c["nodes"]), dev(c["elements"])
+    bref, w = torch.as_tensor(tables[f"{et}.B_ip"]), torch.as_tensor(tables[f"{et}.iweights"]).to(torch.float64)
+    n_int, dim, nn = bref.shape
+    dpn = 1 if heat else dim
+    g = R.Geometry(bref, w, nodes, elements, dpn)
+    X = nodes[elements]                                            # [n_elem, nn, dim]
+    J = torch.einsum("qiN,eNj->qeij", bref.cuda(), X)
+    B = torch.einsum("qeij,qjN->qeiN", torch.linalg.inv(J), bref.cuda())   # [q, e, dim, nn]
+    detJ = torch.linalg.det(J)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    u_e = torch.randn(len(elements), nn, dpn, device="cuda", generator=gen, requires_grad=True)
+    P = torch.randn(n_int, len(elements), dpn, dim, device="cuda", generator=gen, requires_grad=True)
+    H = R.elem_grad(g, u_e)
+    H_ref = torch.einsum("eni,qeJn->qeiJ", u_e, B)
+    assert float((H - H_ref).detach().abs().max()) <= 1e-12 * float(H_ref.detach().abs().max())
+    f = R.elem_force(g, P)
+    f_ref = torch.einsum("q,qe,qeJn,qeiJ->eni", w.cuda(), detJ, B, P)
+    assert float((f - f_ref).detach().abs().max()) <= 1e-12 * float(f_ref.detach().abs().max())
+    g.check()
+    # autograd: gradients equal those of the torch formulas
+    gH, gf = torch.randn_like(H), torch.randn_like(f)
+    (gu,) = torch.autograd.grad(H, u_e, gH)
+    (gu_ref,) = torch.autograd.grad(H_ref, u_e, gH)
+    assert float((gu - gu_ref).abs().max()) <= 1e-12 * float(gu_ref.abs().max())
+    (gP,) = torch.autograd.grad(f, P, gf)
+    (gP_ref,) = torch.autograd.grad(f_ref, P, gf)
+    assert float((gP - gP_ref).abs().max()) <= 1e-12 * float(gP_ref.abs().max())
+
+
 def _cube_system(T, N, tables):
     nodes, elements = O.cube_hexa(N, N, N)
     bref, w = O.hexa1_tables()

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "tfem_pattern_coo_rows": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_integrate_k": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfem_elem_grad": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "tfem_elem_force": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tfem_assemble": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 9),
     "tfem_assemble_bc": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 11),
     "tfem_spmv_num_chunks": (c_int64, [c_int64]),

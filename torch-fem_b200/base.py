@@ -28,6 +28,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import csr as _csr
+from . import residual as _res
 from .elements import Element
 from .materials import Material
 from .sparse import CachedSolve, describe_method, differentiable_sparse_solve, newton_solve  # noqa: F401
@@ -209,6 +210,22 @@ class FEM(ABC):
         if self._shape_cache is None or self._shape_cache[0] != key:
             self._shape_cache = (key, self.eval_shape_functions(self.etype.ipoints))
         return self._shape_cache[1]
+
+    def _geometry(self) -> "_res.Geometry | None":
+        """Kernel-side geometry of the residual contractions (K9/K10), or None when the node coordinates are
+        being differentiated (shape optimisation keeps the torch path)."""
+        if self.nodes.requires_grad or self.nodes.dtype != torch.float64:
+            return None
+        key = (self.nodes.data_ptr(), self.nodes._version, self.elements.data_ptr())
+        if getattr(self, "_geom_cache", None) is None or self._geom_cache[0] != key:
+            bref, w = self._tables()
+            self._geom_cache = (key, _res.Geometry(bref, w, self.nodes, self.elements, self.n_dof_per_node))
+        return self._geom_cache[1]
+
+    @property
+    def _f_scale(self) -> Tensor | None:
+        """Per-element factor of compute_f beyond w detJ (thickness; differentiable), applied in torch."""
+        return None
 
     def _tables(self) -> tuple[Tensor, Tensor]:
         ip = self.etype.ipoints.to(torch.float64)
@@ -498,22 +515,44 @@ class Mechanics(FEM, ABC):
         assert self.material is not None
         d = self.n_flux[0]
         nd = self.etype.nodes * self.n_dof_per_node
-        du_e = du.view(-1, self.n_dof_per_node)[self.elements].reshape(self.n_elem, -1, d).transpose(-1, -2)
         need_k = compute_stiffness and (self.K.numel() == 0 or self.n_state != 0 or nlgeom)
-        _, B, detJ = self._ip_shape()
-        f = torch.zeros(self.n_elem, nd, dtype=du.dtype, device=du.device)
+        geom = self._geometry() if du.dtype == torch.float64 else None
         grads, fluxes, states, tangents = [], [], [], []
         cl = self.char_lengths
-        for q, w in enumerate(self.etype.iweights):
-            H_inc = du_e @ B[q].transpose(-1, -2)
-            F_new = grad_prev[q] + H_inc
-            P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
-            grads.append(F_new)
-            fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
-            states.append(alpha)
-            f = f + float(w) * self.compute_f(detJ[q], B[q], P).reshape(-1, nd)
-            if need_k:
-                tangents.append(ddsdde)
+        if geom is not None:
+            # kernels K9/K10: gradient at all Gauss points in one launch, forces in another; the material update
+            # in between is the caller's torch code (base.py:1050-1083 does ~6 small-matrix launches per point)
+            H_all = _res.elem_grad(geom, du.view(-1, self.n_dof_per_node)[self.elements])
+            Ps = []
+            for q in range(self.n_int):
+                H_inc = H_all[q]
+                F_new = grad_prev[q] + H_inc
+                P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+                grads.append(F_new)
+                fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
+                states.append(alpha)
+                Ps.append(P)
+                if need_k:
+                    tangents.append(ddsdde)
+            f = _res.elem_force(geom, torch.stack(Ps))
+            geom.check()
+            if self._f_scale is not None:
+                f = f * self._f_scale[:, None, None]
+            f = f.reshape(self.n_elem, nd)
+        else:
+            du_e = du.view(-1, self.n_dof_per_node)[self.elements].reshape(self.n_elem, -1, d).transpose(-1, -2)
+            _, B, detJ = self._ip_shape()
+            f = torch.zeros(self.n_elem, nd, dtype=du.dtype, device=du.device)
+            for q, w in enumerate(self.etype.iweights):
+                H_inc = du_e @ B[q].transpose(-1, -2)
+                F_new = grad_prev[q] + H_inc
+                P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+                grads.append(F_new)
+                fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
+                states.append(alpha)
+                f = f + float(w) * self.compute_f(detJ[q], B[q], P).reshape(-1, nd)
+                if need_k:
+                    tangents.append(ddsdde)
         k = None
         if need_k:
             same = all(t is tangents[0] for t in tangents)  # elastic: one tensor for every Gauss point
@@ -563,19 +602,36 @@ class Heat(FEM, ABC):
         nn = self.etype.nodes
         du_e = du.view(-1, 1)[self.elements].reshape(self.n_elem, -1, 1)
         need_k = compute_stiffness and (self.K.numel() == 0 or self.n_state != 0)
-        _, B, detJ = self._ip_shape()
-        f = torch.zeros(self.n_elem, nn, dtype=du.dtype, device=du.device)
+        geom = self._geometry() if du.dtype == torch.float64 else None
         grads, fluxes, states, tangents = [], [], [], []
         cl = self.char_lengths
-        for q, w in enumerate(self.etype.iweights):
-            g_inc = torch.einsum("...ij,...jk->...ki", B[q], du_e)
-            grads.append(grad_prev[q] + g_inc)
-            flux_q, state_q, kappa = self.material.step(g_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
-            fluxes.append(flux_q)
-            states.append(state_q)
-            f = f + float(w) * self.compute_f(detJ[q], B[q], flux_q).reshape(-1, nn)
-            if need_k:
-                tangents.append(kappa)
+        if geom is not None:  # kernels K9/K10, see Mechanics.integrate_material
+            g_all = _res.elem_grad(geom, du_e)
+            for q in range(self.n_int):
+                g_inc = g_all[q]
+                grads.append(grad_prev[q] + g_inc)
+                flux_q, state_q, kappa = self.material.step(g_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+                fluxes.append(flux_q)
+                states.append(state_q)
+                if need_k:
+                    tangents.append(kappa)
+            f = _res.elem_force(geom, torch.stack(fluxes))
+            geom.check()
+            if self._f_scale is not None:
+                f = f * self._f_scale[:, None, None]
+            f = f.reshape(self.n_elem, nn)
+        else:
+            _, B, detJ = self._ip_shape()
+            f = torch.zeros(self.n_elem, nn, dtype=du.dtype, device=du.device)
+            for q, w in enumerate(self.etype.iweights):
+                g_inc = torch.einsum("...ij,...jk->...ki", B[q], du_e)
+                grads.append(grad_prev[q] + g_inc)
+                flux_q, state_q, kappa = self.material.step(g_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
+                fluxes.append(flux_q)
+                states.append(state_q)
+                f = f + float(w) * self.compute_f(detJ[q], B[q], flux_q).reshape(-1, nn)
+                if need_k:
+                    tangents.append(kappa)
         k = None
         if need_k:
             same = all(t is tangents[0] for t in tangents)

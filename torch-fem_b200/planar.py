@@ -45,6 +45,10 @@ class PlanarGeometry(FEM):
     def _k_scale(self) -> Tensor:
         return self.thickness.detach()
 
+    @property
+    def _f_scale(self) -> Tensor:
+        return self.thickness
+
     def compute_k(self, detJ: Tensor, BCB: Tensor) -> Tensor:
         """thickness * detJ * BCB (reference planar.py:86-88); kernel K1 applies the same factors."""
         return (self.thickness * detJ)[:, None, None] * BCB
