@@ -15,6 +15,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--edge", type=int, default=150)
     ap.add_argument("--rows", type=int, default=45)
+    ap.add_argument("--backward", action="store_true", help="forces as differentiable parameter + u.sum().backward()")
+    ap.add_argument("--stol", type=float, default=1e-8)
     a = ap.parse_args()
     torch.set_default_dtype(torch.float64)
     import torchfem_b200 as T
@@ -34,10 +36,21 @@ def main():
     disp[model.nodes[:, 0] == 1.0, 0] = 0.1
     model.constraints, model.displacements = con, disp
 
+    if a.backward:
+        model.forces = torch.zeros_like(model.nodes, requires_grad=True)
+
     def run():
         torch.cuda.synchronize()
         t = time.perf_counter()
-        u, *_ = model.solve(method="cg", stol=1e-8, rtol=1e-6)
+        if a.backward:
+            u, *_ = model.solve(method="cg", stol=a.stol, differentiable_parameters=model.forces)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            u.sum().backward()
+            torch.cuda.synchronize()
+            print("   fwd %.3f s  bwd %.3f s" % (t1 - t, time.perf_counter() - t1))
+        else:
+            u, *_ = model.solve(method="cg", stol=a.stol, rtol=1e-6)
         torch.cuda.synchronize()
         return time.perf_counter() - t
 

@@ -42,6 +42,17 @@ def _cuda_device(t: Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _step_points(material, H_all, F_all, stress_all, state_all, de0, cl, iter, need_tangent):
+    """Material update at all Gauss points: the material's own batched `step_points` if it has one, else the
+    reference's per-point loop over `step` (any duck-typed material works)."""
+    fn = getattr(material, "step_points", None)
+    if fn is not None:
+        return fn(H_all, F_all, stress_all, state_all, de0, cl, iter, need_tangent=need_tangent)
+    from .materials import step_points_loop
+
+    return step_points_loop(material, H_all, F_all, stress_all, state_all, de0, cl, iter)
+
+
 def _det_inv(J: Tensor) -> tuple[Tensor, Tensor]:
     """Closed-form determinant and inverse of batched 2x2 / 3x3 matrices (differentiable)."""
     d = J.shape[-1]
@@ -523,22 +534,16 @@ class Mechanics(FEM, ABC):
             # kernels K9/K10: gradient at all Gauss points in one launch, forces in another; the material update
             # in between is the caller's torch code (base.py:1050-1083 does ~6 small-matrix launches per point)
             H_all = _res.elem_grad(geom, du.view(-1, self.n_dof_per_node)[self.elements])
-            Ps = []
-            for q in range(self.n_int):
-                H_inc = H_all[q]
-                F_new = grad_prev[q] + H_inc
-                P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
-                grads.append(F_new)
-                fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
-                states.append(alpha)
-                Ps.append(P)
-                if need_k:
-                    tangents.append(ddsdde)
-            f = _res.elem_force(geom, torch.stack(Ps))
+            P_all, alpha_all, tangent = _step_points(self.material, H_all, grad_prev, flux_prev, state_prev, de0,
+                                                     cl, iter, need_k)
+            F_all = grad_prev + H_all
+            flux_all = (F_all @ P_all) / torch.det(F_all)[..., None, None] if nlgeom else P_all
+            f = _res.elem_force(geom, P_all)
             geom.check()
             if self._f_scale is not None:
                 f = f * self._f_scale[:, None, None]
-            f = f.reshape(self.n_elem, nd)
+            k = self._integrate_k(tangent) if need_k else None
+            return k, f.reshape(self.n_elem, nd), F_all, flux_all, alpha_all
         else:
             du_e = du.view(-1, self.n_dof_per_node)[self.elements].reshape(self.n_elem, -1, d).transpose(-1, -2)
             _, B, detJ = self._ip_shape()
@@ -607,19 +612,14 @@ class Heat(FEM, ABC):
         cl = self.char_lengths
         if geom is not None:  # kernels K9/K10, see Mechanics.integrate_material
             g_all = _res.elem_grad(geom, du_e)
-            for q in range(self.n_int):
-                g_inc = g_all[q]
-                grads.append(grad_prev[q] + g_inc)
-                flux_q, state_q, kappa = self.material.step(g_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
-                fluxes.append(flux_q)
-                states.append(state_q)
-                if need_k:
-                    tangents.append(kappa)
-            f = _res.elem_force(geom, torch.stack(fluxes))
+            flux_all, state_all, tangent = _step_points(self.material, g_all, grad_prev, flux_prev, state_prev, de0,
+                                                        cl, iter, need_k)
+            f = _res.elem_force(geom, flux_all)
             geom.check()
             if self._f_scale is not None:
                 f = f * self._f_scale[:, None, None]
-            f = f.reshape(self.n_elem, nn)
+            k = self._integrate_k(tangent) if need_k else None
+            return k, f.reshape(self.n_elem, nn), grad_prev + g_all, flux_all, state_all
         else:
             _, B, detJ = self._ip_shape()
             f = torch.zeros(self.n_elem, nn, dtype=du.dtype, device=du.device)

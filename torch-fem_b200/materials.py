@@ -55,8 +55,28 @@ class Material:
     def step(self, H_inc, F, stress, state, de0, cl, iter):
         raise NotImplementedError
 
+    def step_points(self, H_all, F_all, stress_all, state_all, de0, cl, iter, need_tangent: bool = True):
+        """`step` at all Gauss points: inputs stacked over the leading integration-point axis. Returns
+        (stress [n_int, ...], state [n_int, ...], tangent) where tangent is ONE per-element tensor if `step`
+        returned the same object at every point (elastic) and a stack otherwise. The default is the reference's
+        loop (base.py:1050-1058); materials whose update is launch-bound override it with one batched call."""
+        return step_points_loop(self, H_all, F_all, stress_all, state_all, de0, cl, iter)
+
     def rotate(self, R: Tensor) -> "Material":
         return self
+
+
+def step_points_loop(material, H_all, F_all, stress_all, state_all, de0, cl, iter):
+    """One `material.step` per Gauss point, exactly as the reference's Gauss loop calls it; works for any object
+    with the `step` contract (reference materials/base.py:50-91)."""
+    Ps, sts, tans = [], [], []
+    for q in range(H_all.shape[0]):
+        P, a, t = material.step(H_all[q], F_all[q], stress_all[q], state_all[q], de0, cl, iter)
+        Ps.append(P)
+        sts.append(a)
+        tans.append(t)
+    same = all(t is tans[0] for t in tans)
+    return torch.stack(Ps), torch.stack(sts), (tans[0] if same else torch.stack(tans))
 
 
 def _ddot(C: Tensor, e: Tensor) -> Tensor:
@@ -129,18 +149,43 @@ class Hyperelastic3D(Material):
             tangent = vmap(jacrev(jacrev(self.psi)))(F_new, self.params)
         return P, state, tangent
 
+    def _psi_point(self):
+        return self.psi
+
+    def step_points(self, H_all, F_all, stress_all, state_all, de0, cl, iter, need_tangent: bool = True):
+        """All Gauss points in ONE vmap call (the per-point calls of the reference loop are launch-bound: a few
+        hundred tiny kernels each); the tangent is skipped when the caller does not integrate a stiffness."""
+        n_int, n_elem = H_all.shape[:2]
+        psi = self._psi_point()
+        params = self.params
+        if params.dim() == 1:
+            params = params.expand(n_elem, -1)
+        params = params.expand(n_int, *params.shape).reshape(n_int * n_elem, -1)
+        with torch.enable_grad():
+            F_new = (F_all + H_all).reshape(n_int * n_elem, *H_all.shape[2:]).requires_grad_(True)
+            P = vmap(jacrev(psi))(F_new, params)
+            tangent = vmap(jacrev(jacrev(psi)))(F_new, params) if need_tangent else None
+        P = P.reshape(H_all.shape)
+        if tangent is not None:
+            tangent = tangent.reshape(n_int, n_elem, *tangent.shape[1:])
+        return P, state_all, tangent
+
 
 class HyperelasticPlaneStrain(Hyperelastic3D):
     """Plane strain: psi is evaluated on the 3x3 embedding diag(F2d, 1), so stress and tangent are the
     in-plane derivatives (reference hyperelasticity.py:309-355)."""
 
-    def step(self, H_inc, F, stress, state, de0, cl, iter):
+    def _psi_point(self):
         def psi2(F2, p):
             F3 = torch.zeros(3, 3, dtype=F2.dtype, device=F2.device)
             F3 = F3 + torch.nn.functional.pad(F2, (0, 1, 0, 1))
             F3 = F3 + torch.diag(torch.tensor([0.0, 0.0, 1.0], dtype=F2.dtype, device=F2.device))
             return self.psi(F3, p)
 
+        return psi2
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        psi2 = self._psi_point()
         with torch.enable_grad():
             F_new = (F + H_inc).requires_grad_(True)
             P = vmap(jacrev(psi2))(F_new, self.params)
