@@ -305,6 +305,41 @@ def hyper_small():
                         increments=npy(increments))
 
 
+def heat_transient():
+    """`Heat.time_integration` (base.py:1288-1553; tests/test_time_integration.py:9-18 heated plate) and a small
+    SolidHeat cube: temperatures / fluxes at the output times, and the gradient of the final temperatures w.r.t.
+    the nodal heat flux (flows through `differentiable_sparse_solve`)."""
+    from torchfem import PlanarHeat, SolidHeat
+
+    out = {}
+    model = PlanarHeat(*mesh.rect_quad(5, 5, 1.0, 1.0), M.IsotropicConductivity2D(kappa=400.0, rho=1.0e5))
+    west = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].min())
+    east = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].max())
+    model.constraints[west | east] = True
+    model.temperatures[west, 0] = 5.0
+    model.temperatures[east, 0] = 20.0
+    hf = torch.zeros(model.n_nod, 1)
+    hf[12, 0] = 3.0
+    model.heat_flux = hf.clone().requires_grad_(True)
+    t_out = torch.tensor([0.0, 6.0, 12.0, 18.0, 24.0])
+    temp, rfl, flux, grad, state = model.time_integration(t_out, delta_t=1.0)
+    temp[-1].sum().backward()
+    out.update({"plate.t_out": npy(t_out), "plate.temp": npy(temp), "plate.rfl": npy(rfl), "plate.flux": npy(flux),
+                "plate.grad": npy(grad), "plate.heat_flux": npy(hf), "plate.grad_heat_flux": npy(model.heat_flux.grad)})
+    late, *_ = model.time_integration(torch.tensor([5.0, 10.0]), delta_t=0.5)
+    out["plate.late"] = npy(late)
+
+    nodes, elements = mesh.cube_hexa(4, 4, 4)
+    cube = SolidHeat(nodes, elements, M.IsotropicConductivity3D(kappa=2.0, rho=30.0))
+    cube.constraints[nodes[:, 0] == 0.0] = True
+    cube.temperatures[nodes[:, 0] == 0.0, 0] = 1.0
+    cube.heat_flux[nodes[:, 0] == 1.0, 0] = 0.05
+    t3 = torch.tensor([0.0, 1.0, 3.0])
+    temp3, _, flux3, grad3, _ = cube.time_integration(t3, delta_t=0.25)
+    out.update({"cube.t_out": npy(t3), "cube.temp": npy(temp3), "cube.flux": npy(flux3), "cube.grad": npy(grad3)})
+    np.savez_compressed(os.path.join(OUT, "heat_transient.npz"), **out)
+
+
 def sparse_small():
     """tests/test_sparse.py-style systems: SPD and non-symmetric 6x6 COO with dense solutions."""
     g = torch.Generator().manual_seed(42)
@@ -334,5 +369,6 @@ if __name__ == "__main__":
     topopt_small()
     hyper_small()
     sparse_small()
+    heat_transient()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

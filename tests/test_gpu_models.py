@@ -332,3 +332,63 @@ class TestBase:
             (u ** 2).sum().backward()
             grads.append(th.grad.clone())
         assert torch.allclose(grads[0], grads[1], atol=1e-9, rtol=1e-7)
+
+
+class TestHeatTransient:
+    """`Heat.time_integration` (reference base.py:1288-1553, tests/test_time_integration.py) against vectors
+    generated from the unmodified reference (oracle/make_golden.py::heat_transient)."""
+
+    def _plate(self, T):
+        from torchfem_b200.materials import IsotropicConductivity2D
+        from torchfem_b200.mesh import rect_quad
+
+        model = T.PlanarHeat(*rect_quad(5, 5, 1.0, 1.0), IsotropicConductivity2D(kappa=400.0, rho=1.0e5))
+        west = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].min())
+        east = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].max())
+        model.constraints[west | east] = True
+        model.temperatures[west, 0] = 5.0
+        model.temperatures[east, 0] = 20.0
+        return model
+
+    @pytest.mark.parametrize("method", [None, "cg"])
+    def test_plate_matches_reference_and_heat_flux_gradient(self, T, method):
+        g = load_case("heat_transient.npz")
+        model = self._plate(T)
+        model.heat_flux = torch.tensor(g["plate.heat_flux"]).requires_grad_(True)
+        temp, rfl, flux, grad, state = model.time_integration(torch.tensor(g["plate.t_out"]), delta_t=1.0,
+                                                              method=method, stol=1e-12)
+        for got, key in ((temp, "plate.temp"), (rfl, "plate.rfl"), (flux, "plate.flux"), (grad, "plate.grad")):
+            ref = g[key]
+            assert got.shape == ref.shape
+            assert np.abs(got.detach().cpu().numpy() - ref).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+        assert state.shape[0] == 5
+        temp[-1].sum().backward()
+        gh = model.heat_flux.grad.cpu().numpy()
+        assert np.abs(gh - g["plate.grad_heat_flux"]).max() <= 1e-8 * np.abs(g["plate.grad_heat_flux"]).max()
+
+    def test_late_start_single_time_and_invalid_times(self, T):
+        g = load_case("heat_transient.npz")
+        model = self._plate(T)
+        model.heat_flux = torch.tensor(g["plate.heat_flux"])
+        late, *_ = model.time_integration(torch.tensor([5.0, 10.0]), delta_t=0.5)
+        assert np.abs(late.cpu().numpy() - g["plate.late"]).max() <= 1e-8 * np.abs(g["plate.late"]).max()
+        one, _, fl, gr, _ = model.time_integration(torch.tensor([10.0]), delta_t=1.0)
+        assert one.shape[0] == fl.shape[0] == gr.shape[0] == 1
+        for bad in (torch.tensor([]), torch.tensor([-1.0, 1.0]), torch.tensor([0.0, 2.0, 2.0])):
+            with pytest.raises(ValueError, match="t_output must"):
+                model.time_integration(bad)
+        assert bool(model.constraints.sum() == 10)  # boundary conditions restored
+
+    def test_solid_heat_cube(self, T):
+        from torchfem_b200.materials import IsotropicConductivity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        g = load_case("heat_transient.npz")
+        nodes, elements = cube_hexa(4, 4, 4)
+        cube = T.SolidHeat(nodes, elements, IsotropicConductivity3D(kappa=2.0, rho=30.0))
+        cube.constraints[nodes[:, 0] == 0.0] = True
+        cube.temperatures[nodes[:, 0] == 0.0, 0] = 1.0
+        cube.heat_flux[nodes[:, 0] == 1.0, 0] = 0.05
+        temp, _, flux, grad, _ = cube.time_integration(torch.tensor(g["cube.t_out"]), delta_t=0.25)
+        for got, key in ((temp, "cube.temp"), (flux, "cube.flux"), (grad, "cube.grad")):
+            assert np.abs(got.cpu().numpy() - g[key]).max() <= 1e-8 * max(1.0, np.abs(g[key]).max())

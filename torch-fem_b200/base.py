@@ -637,3 +637,111 @@ class Heat(FEM, ABC):
             same = all(t is tangents[0] for t in tangents)
             k = self._integrate_k(tangents[0] if same else torch.stack(tangents))
         return k, f, torch.stack(grads), torch.stack(fluxes), torch.stack(states)
+
+    def time_integration(self, t_output: Tensor | None = None, delta_t: float = 1.0e-1, max_iter: int = 100,
+                         verbose: bool = False, rtol: float = 1e-8, atol: float = 1e-6, stol: float = 1e-10,
+                         device: str | None = None, method: str | None = None,
+                         aggregate_integration_points: bool = True, use_cached_solve: bool = False,
+                         differentiable_parameters: Tensor | Iterable[Tensor] | None = None):
+        """Implicit (trapezoidal) time integration of the heat equation (reference base.py:1288-1553): an
+        equilibrium state at t = 0 under the current boundary conditions, then steps of at most `delta_t` to
+        every requested output time. Same arguments, return values, error messages and stepping rules as the
+        reference. Per step: Newton on  M du + dt/2 (f_int_old + f_int + f_ext) = 0  with the linear solves
+        `differentiable_sparse_solve(M + dt/2 K, -residual)` on the device CSR (M, K assembled once by kernel
+        K2/K3; the combination is an entry-wise sum on the shared pattern). Gradients flow through the right-hand
+        sides (loads, previous states); matrix VALUES carry no gradient here (they come from the kernels)."""
+        kw = dict(dtype=self.nodes.dtype, device=self.device)
+        t_output = torch.tensor([0.0, 1.0]) if t_output is None else t_output
+        t_output = t_output.detach().to("cpu", torch.float64)
+        if t_output.numel() == 0:
+            raise ValueError("t_output must contain at least one time.")
+        if t_output.min() < 0.0:
+            raise ValueError("t_output must not contain negative times.")
+        if (t_output[1:] <= t_output[:-1]).any():
+            raise ValueError("t_output must be strictly increasing.")
+
+        # initial conditions: every DOF held at its prescribed value (base.py:1348-1358)
+        bc_constraints = self._constraints.clone()
+        self._constraints = torch.ones_like(bc_constraints)
+        try:
+            temp_eq, _, flux_eq, grad_eq, alpha_eq = self.solve(
+                aggregate_integration_points=False, use_cached_solve=use_cached_solve,
+                differentiable_parameters=differentiable_parameters)
+        finally:
+            self._constraints = bc_constraints
+
+        # internal time grid: integration starts at t = 0 even if it is not an output time (base.py:1360-1387)
+        t_list = [float(v) for v in t_output.tolist()]
+        knots = t_list if t_list[0] <= 0.0 else [0.0] + t_list
+        times, rows, row = [knots[0]], ([] if t_list[0] > 0.0 else [0]), 0
+        for t0, t1 in zip(knots[:-1], knots[1:]):
+            ratio = (t1 - t0) / delta_t
+            n_sub = max(1, math.ceil(ratio - 1e-9 * max(1.0, ratio)))
+            sub = torch.linspace(t0, t1, n_sub + 1, dtype=torch.float64, device="cpu")[1:].tolist()
+            sub[-1] = t1                                   # linspace can miss the knot by an ulp
+            times += sub
+            row += n_sub
+            rows.append(row)
+        dts = [b_ - a_ for a_, b_ in zip(times[:-1], times[1:])]
+        n_steps = len(times)
+
+        B = self.compute_B()
+        con = torch.nonzero(self._constraints.ravel(), as_tuple=False).ravel()
+        dpn, shape4 = self.n_dof_per_node, (self.n_int, self.n_elem, self.n_dof_per_node, self.n_dim)
+        u0 = temp_eq.clone()
+        u0.view(-1)[con] = self._dirichlet.view(-1)[con]       # base.py:1452
+        u = [u0]
+        f = [torch.zeros(self.n_nod, dpn, **kw)]
+        flux, grad, state = [flux_eq.reshape(shape4)], [grad_eq.reshape(shape4)], [alpha_eq]
+
+        self.K = torch.empty(0, device=self.device)
+        self.M = None
+        m = self.integrate_mass()
+        if verbose:
+            print(f"torch-fem_b200 | time integration | {type(self).__name__} | {self.n_dofs:,} dof | "
+                  f"{n_steps - 1} steps | dt <= {delta_t:g} | {describe_method(self.n_dofs, 'cuda', method)}")
+
+        for n in range(1, n_steps):
+            u_guess = u[n - 1].clone()
+            dt_n = dts[n - 1]
+            f_old = f[n - 1]
+            res_norm = res_norm0 = None
+            f_int = grad_n = flux_n = state_n = None
+            for it in range(max_iter):
+                du = u_guess - u[n - 1]
+                k, f_e, grad_n, flux_n, state_n = self.integrate_material(
+                    u[n - 1], grad[n - 1], flux[n - 1], state[n - 1], du, self._external_gradient, it, False)
+                f_int = self.assemble_rhs(f_e)
+                if k is not None:
+                    self.K = self.assemble_matrix(k, con)
+                if self.M is None:
+                    self.M = self.assemble_matrix(m, con)
+                residual = (self.M @ du.reshape(-1)) + 0.5 * dt_n * (f_old.reshape(-1) + f_int + self._neumann.ravel())
+                mask = torch.ones_like(residual)
+                mask[con] = 0.0
+                residual = residual * mask
+                res_norm = torch.linalg.norm(residual.detach())
+                if it == 0:
+                    res_norm0 = res_norm
+                if res_norm < rtol * res_norm0 or res_norm < atol:
+                    break
+                cached = self.cached_solve if (it == 0 and use_cached_solve) else CachedSolve()
+                step = differentiable_sparse_solve(self.M + 0.5 * dt_n * self.K, -residual, B, stol, device, method,
+                                                   None, cached, it == 0)
+                u_guess = u_guess + step.reshape(-1, dpn)
+            if res_norm > rtol * res_norm0 and res_norm > atol:
+                raise RuntimeError("Newton-Raphson iteration did not converge.")
+            u.append(u_guess)
+            f.append(f_int.reshape(-1, dpn))
+            grad.append(grad_n)
+            flux.append(flux_n)
+            state.append(state_n)
+            if verbose:
+                print(f"  step {n:5d}  t = {times[n]:.6g}  |res| = {float(res_norm):.3e}")
+
+        pick = lambda seq: torch.stack([seq[i] for i in rows])  # noqa: E731
+        out_u, out_f, out_flux, out_grad, out_state = pick(u), pick(f), pick(flux), pick(grad), pick(state)
+        if aggregate_integration_points:
+            out_grad, out_flux, out_state = out_grad.mean(dim=1), out_flux.mean(dim=1), out_state.mean(dim=1)
+        out_flux, out_grad = out_flux.squeeze((-2, -1)), out_grad.squeeze((-2, -1))
+        return out_u, out_f, out_flux, out_grad, out_state

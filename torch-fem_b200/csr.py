@@ -358,7 +358,38 @@ class CSRMatrix:
         return y
 
     def __matmul__(self, x: Tensor) -> Tensor:
-        return self.matvec(x)
+        """A @ x, differentiable w.r.t. x (the reference's `self.M @ du` on a sparse COO tensor, base.py:1483)."""
+        shape = x.shape
+        y = _Matvec.apply(x.reshape(-1), self) if x.requires_grad else self.matvec(x.reshape(-1).contiguous())
+        return y.reshape(shape)
+
+    # ---- linear combinations of matrices on the SAME pattern (e.g. `M + 0.5*dt*K`, reference base.py:1513; the
+    # reference lets torch / scipy sum the duplicate COO entries, here the values are combined entry by entry)
+    def _like(self, values: Tensor) -> "CSRMatrix":
+        return CSRMatrix(self.indptr, self.indices, values, self.n, chunk_rows=self.chunk_rows,
+                         diag_pos=self._diag_pos, symmetric=self.symmetric, coo_indices=self._coo,
+                         sell_struct=self._sell_struct)
+
+    def __mul__(self, c) -> "CSRMatrix":
+        return self._like(self.values_ * float(c))
+
+    __rmul__ = __mul__
+
+    def __neg__(self) -> "CSRMatrix":
+        return self._like(-self.values_)
+
+    def __add__(self, other: "CSRMatrix") -> "CSRMatrix":
+        if not isinstance(other, CSRMatrix):
+            return NotImplemented
+        if other.indices.data_ptr() != self.indices.data_ptr() and not (
+                other.nnz == self.nnz and torch.equal(other.indptr, self.indptr) and torch.equal(other.indices, self.indices)):
+            raise ValueError("CSRMatrix addition needs both matrices on the same sparsity pattern")
+        out = self._like(self.values_ + other.values_)
+        out.symmetric = self.symmetric and other.symmetric
+        return out
+
+    def __sub__(self, other: "CSRMatrix") -> "CSRMatrix":
+        return self + (-other)
 
     # ---- construction from what the reference passes around
     @staticmethod
@@ -378,6 +409,19 @@ class CSRMatrix:
         indptr[1:] = torch.cumsum(counts, 0)
         return CSRMatrix(indptr, col.to(torch.int32).contiguous(), vals, n,
                          coo_indices=A.indices())
+
+
+class _Matvec(torch.autograd.Function):
+    """y = A x with dy/dx^T g = A^T g; A itself carries no gradient (its values come from the kernels)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, A: "CSRMatrix"):
+        ctx.A = A
+        return A.matvec(x.detach().to(torch.float64).contiguous())
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return _Matvec.apply(g, ctx.A.T) if g.requires_grad else ctx.A.T.matvec(g.contiguous()), None
 
 
 def integrate_k(kind: int, bref: Tensor, w: Tensor, nodes: Tensor, elements: Tensor, tangent: Tensor,
