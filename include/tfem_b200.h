@@ -237,6 +237,29 @@ int tfem_krylov_solve(int method, const tfem_sell_t* A, const double* dinv_dev, 
                       double* x_dev, double* work_dev, double* info_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * K8 — matrix-free (element-by-element) operator on stored element matrices (optional operator of the Krylov
+ * solve; the reference has none):  y = sum_e P_e^T k_e P_e x  with the Dirichlet masking of tfem_assemble applied
+ * on the fly (constrained rows / columns dropped, unit diagonal). Deterministic gather over the node -> element
+ * incidence lists of tfem_pattern_phase1; no pattern values, no assembly, no format conversion. Reads all of k per
+ * product (8 nd^2 B per element), so it pays off when few Krylov iterations are spent per tangent. */
+typedef struct tfem_ebe {
+  int64_t n_nod;
+  int32_t nn, dpn;
+  const int32_t* inc_ptr;    /* [n_nod+1]      (tfem_pattern_phase1) */
+  const int32_t* inc_list;   /* [n_elem*nn]    slots e*nn + a, ascending per node */
+  const int64_t* elements;   /* [n_elem*nn] */
+  const double* k;           /* [n_elem, nn*dpn, nn*dpn] */
+  const uint8_t* is_con;     /* [n_nod*dpn] or NULL */
+} tfem_ebe_t;
+int tfem_ebe_spmv(const tfem_ebe_t* A, const double* x_dev, double* y_dev, void* stream);
+/* diag[row] = sum of the diagonal entries of the incident element matrices (1 on constrained rows). */
+int tfem_ebe_diag(const tfem_ebe_t* A, double* diag_dev, void* stream);
+/* tfem_krylov_solve with the element operator in place of the assembled matrix (same arguments otherwise). */
+int tfem_krylov_solve_ebe(int method, const tfem_ebe_t* A, const double* dinv_dev, const double* b_dev,
+                          const double* x0_dev, double rtol, double atol, int64_t maxiter, int check_every,
+                          double* x_dev, double* work_dev, double* info_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Multi-GPU Jacobi-PCG, one call per stage. The reference has no multi-GPU path; the partitioning
  * (contiguous node blocks, ghost elements integrated redundantly) is described in DESIGN.md §multi-GPU.
  * The host (torch-fem_b200/distributed.py) interleaves the NCCL collectives:

@@ -296,6 +296,40 @@ def test_fused_peer_cg_world1_equals_single_gpu_driver(T, tables):
         cg.close()
 
 
+@pytest.mark.parametrize("tag", ["hexa1", "hexa2", "tetra2", "quad1", "heat_hexa1", "heat_quad2"])
+def test_element_operator_equals_assembled_matrix(T, tag):
+    """K8 matrix-free operator == the assembled, Dirichlet-masked matrix (product and diagonal)."""
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    n_dofs = dpn * c["nodes"].shape[0]
+    p = build_pattern(T, c, dpn)
+    is_con = np.zeros(n_dofs, dtype=np.uint8)
+    is_con[c["con"]] = 1
+    k = dev(c["k"])
+    A = p.matrix(T.csr.assemble(p, k, dev(is_con)))
+    x = dev(np.random.default_rng(1).standard_normal(n_dofs))
+    for con in (dev(is_con), None):
+        Aop = T.csr.ElementOperator(p, k, con)
+        Aref = A if con is not None else p.matrix(T.csr.assemble(p, k, None))
+        y, yr = Aop.matvec(x), Aref.matvec(x, fmt="csr")
+        assert float((y - yr).abs().max()) <= 1e-12 * float(yr.abs().max())
+        assert float((Aop.diagonal() - Aref.diagonal()).abs().max()) <= 1e-12 * float(Aref.diagonal().abs().max())
+    assert torch.equal(Aop.matvec(x), Aop.matvec(x))  # deterministic
+
+
+def test_element_operator_cg_matches_assembled_cg(T, tables):
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 11, tables)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
+    b = dev(ref["res"])
+    x, M, info = T.csr.krylov_solve(A, b, method="cg", rtol=1e-10)
+    Aop = T.csr.ElementOperator(p, k, dev(con_mask.ravel().astype(np.uint8)))
+    for method in ("cg", "minres"):
+        x2, M2, info2 = T.csr.krylov_solve(Aop, b, method=method, rtol=1e-10)
+        assert float((x2 - x).abs().max()) <= 1e-8 * float(x.abs().max())
+        if method == "cg":
+            assert abs(info2["iterations"] - info["iterations"]) <= 1
+
+
 def test_cg_warm_start_and_zero_rhs(T, tables):
     nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 6, tables)
     ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)

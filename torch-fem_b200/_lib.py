@@ -36,6 +36,15 @@ class SellStruct(ctypes.Structure):
 _SELL_P = ctypes.POINTER(SellStruct)
 
 
+class EbeStruct(ctypes.Structure):
+    """`tfem_ebe_t` of include/tfem_b200.h."""
+    _fields_ = [("n_nod", c_int64), ("nn", ctypes.c_int32), ("dpn", ctypes.c_int32), ("inc_ptr", c_void_p),
+                ("inc_list", c_void_p), ("elements", c_void_p), ("k", c_void_p), ("is_con", c_void_p)]
+
+
+_EBE_P = ctypes.POINTER(EbeStruct)
+
+
 class HaloSendStruct(ctypes.Structure):
     """`tfem_halo_send_t` of include/tfem_b200.h."""
     _fields_ = [("peer", ctypes.c_int32), ("count", c_int64), ("src_idx", c_void_p), ("dst_idx", c_void_p),
@@ -66,6 +75,10 @@ _SIGNATURES = {
     "tfem_krylov_work_doubles": (c_int64, [c_int64]),
     "tfem_krylov_solve": (c_int, [c_int, _SELL_P] + [c_void_p] * 3 + [c_double, c_double, c_int64, c_int]
                           + [c_void_p] * 4),
+    "tfem_ebe_spmv": (c_int, [_EBE_P, c_void_p, c_void_p, c_void_p]),
+    "tfem_ebe_diag": (c_int, [_EBE_P, c_void_p, c_void_p]),
+    "tfem_krylov_solve_ebe": (c_int, [c_int, _EBE_P] + [c_void_p] * 3 + [c_double, c_double, c_int64, c_int]
+                              + [c_void_p] * 4),
     "tfem_bsell_slice_ptr": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "tfem_bsell_fill": (c_int, [c_int64, c_int, c_int64] + [c_void_p] * 5),
     "tfem_sell_slice_ptr": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),

@@ -54,6 +54,7 @@ class Pattern:
         L.check(L.lib.tfem_pattern_phase1(self.n_nod, self.n_elem, self.nn, self.dpn, L.ptr(elements),
                                           L.ptr(inc_ptr), L.ptr(inc_list), L.ptr(blk_cnt),
                                           L.ptr(totals), st))
+        self.inc_ptr, self.inc_list = inc_ptr, inc_list   # node -> (element, local node) incidence (kept for K8)
         nnzb, nnz, max_blk, max_inc = (int(v) for v in totals.tolist())
         self.nnzb, self.nnz = nnzb, nnz
         self.max_blocks_per_node, self.max_elements_per_node = max_blk, max_inc
@@ -488,21 +489,71 @@ def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | N
     return vals
 
 
+class ElementOperator:
+    """Matrix-free operator y = sum_e P_e^T k_e P_e x on stored element matrices (kernel K8) with the Dirichlet
+    masking of `assemble` applied on the fly — the optional operator of the Krylov solve: no assembly, no SELL
+    copy. Accepted by `krylov_solve` in place of a `CSRMatrix`. Symmetric by construction."""
+
+    def __init__(self, pattern: Pattern, k: Tensor, is_con: Tensor | None = None):
+        L.require_cuda(k)
+        nd = pattern.nn * pattern.dpn
+        if k.dtype != torch.float64 or tuple(k.shape) != (pattern.n_elem, nd, nd):
+            raise ValueError(f"k must be float64 with shape {(pattern.n_elem, nd, nd)}")
+        self.pattern, self.k = pattern, k.contiguous()
+        self.is_con = None if is_con is None else is_con.to(torch.uint8).contiguous()
+        self.n = pattern.n_dofs
+        self.shape = torch.Size((self.n, self.n))
+        self.device = k.device
+        self.symmetric = True
+        self.struct = L.EbeStruct()
+        self.struct.n_nod, self.struct.nn, self.struct.dpn = pattern.n_nod, pattern.nn, pattern.dpn
+        self.struct.inc_ptr, self.struct.inc_list = L.ptr(pattern.inc_ptr), L.ptr(pattern.inc_list)
+        self.struct.elements, self.struct.k = L.ptr(pattern.elements), L.ptr(self.k)
+        self.struct.is_con = L.ptr(self.is_con)
+
+    @property
+    def ref(self):
+        import ctypes
+
+        return ctypes.byref(self.struct)
+
+    @property
+    def T(self):
+        return self
+
+    def matvec(self, x: Tensor, out: Tensor | None = None) -> Tensor:
+        L.require_cuda(x)
+        x = x.contiguous()
+        y = out if out is not None else torch.empty_like(x)
+        L.check(L.lib.tfem_ebe_spmv(self.ref, L.ptr(x), L.ptr(y), L.stream()))
+        return y
+
+    __matmul__ = matvec
+
+    def diagonal(self) -> Tensor:
+        d = torch.empty(self.n, dtype=torch.float64, device=self.device)
+        L.check(L.lib.tfem_ebe_diag(self.ref, L.ptr(d), L.stream()))
+        return d
+
+
 class JacobiPreconditioner:
     """M = diag(A)^-1 (reference GPU path: `cupy_diags(1.0 / A_cp.diagonal())`, sparse.py:408-409).
     Returned by `sparse_solve` as `M` and accepted back, like the reference's preconditioner object."""
 
-    def __init__(self, A: CSRMatrix):
-        self.dinv = torch.empty(A.n, dtype=torch.float64, device=A.device)
-        L.check(L.lib.tfem_jacobi_setup(A.n, L.ptr(A.values_), L.ptr(A.diag_pos), L.ptr(self.dinv),
-                                        L.stream()))
+    def __init__(self, A):
+        if isinstance(A, ElementOperator):
+            self.dinv = 1.0 / A.diagonal()
+        else:
+            self.dinv = torch.empty(A.n, dtype=torch.float64, device=A.device)
+            L.check(L.lib.tfem_jacobi_setup(A.n, L.ptr(A.values_), L.ptr(A.diag_pos), L.ptr(self.dinv),
+                                            L.stream()))
         self.shape = (A.n, A.n)
 
 
 _WORK_CACHE: dict = {}
 
 
-def krylov_solve(A: CSRMatrix, b: Tensor, method: str = "cg", rtol: float = 1e-10, atol: float = 0.0,
+def krylov_solve(A: "CSRMatrix | ElementOperator", b: Tensor, method: str = "cg", rtol: float = 1e-10, atol: float = 0.0,
                  x0: Tensor | None = None, M: JacobiPreconditioner | None = None, maxiter: int = 0,
                  check_every: int = 0):
     """Jacobi-preconditioned CG / MINRES on the device (kernels K5+K6). Returns (x, M, info dict).
@@ -525,10 +576,15 @@ def krylov_solve(A: CSRMatrix, b: Tensor, method: str = "cg", rtol: float = 1e-1
     meth = {"cg": L.METHOD_CG, "minres": L.METHOD_MINRES}[method]
     if x0 is not None:
         x0 = x0.to(device=b.device, dtype=torch.float64).contiguous()
-    S = A.sell()
-    rc = L.lib.tfem_krylov_solve(meth, S.ref, L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
-                                 int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
-                                 info.ctypes.data, L.stream())
+    if isinstance(A, ElementOperator):
+        rc = L.lib.tfem_krylov_solve_ebe(meth, A.ref, L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
+                                         int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
+                                         info.ctypes.data, L.stream())
+    else:
+        S = A.sell()
+        rc = L.lib.tfem_krylov_solve(meth, S.ref, L.ptr(M.dinv), L.ptr(b), L.ptr(x0), float(rtol), float(atol),
+                                     int(maxiter), int(check_every), L.ptr(x), L.ptr(work),
+                                     info.ctypes.data, L.stream())
     stats = {"iterations": int(info[0]), "resnorm": float(info[1]), "bnorm": float(info[2]),
              "converged": bool(info[3]), "spmv": int(info[4]), "launches": int(info[5])}
     if rc in (L.ERR_NOT_CONVERGED, L.ERR_BREAKDOWN):

@@ -13,7 +13,7 @@
 
 #include <cub/device/device_scan.cuh>
 
-#include "sell.cuh"
+#include "ebe.cuh"
 
 namespace tfem {
 
@@ -199,6 +199,22 @@ int launch_sell(const Sell& A, const double* x, double* y, const double* sc, dou
   if (A.dpn == 3) return launch_sell_t<3, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
   if (A.dpn == 2) return launch_sell_t<2, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
   return launch_sell_t<0, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
+}
+
+// The linear operator of a Krylov solve: the assembled matrix in SELL-32 form, or the matrix-free element
+// operator (ebe.cuh).
+struct Op {
+  bool ebe = false;
+  Sell sell;
+  Ebe el;
+  int64_t n = 0;
+};
+
+template <bool DOT>
+int apply_op(const Op& op, const double* x, double* y, const double* sc, double* partials, unsigned int* ticket,
+             double* out_scalar, cudaStream_t st) {
+  if (op.ebe) return launch_ebe<DOT>(op.el, x, y, sc, partials, ticket, out_scalar, st);
+  return launch_sell<DOT>(op.sell, x, y, sc, partials, ticket, out_scalar, st);
 }
 
 // ------------------------------------------------------------------------------------------ CG
@@ -755,19 +771,15 @@ extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
   return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
 }
 
-extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double* dinv, const double* b,
-                                 const double* x0, double rtol, double atol, int64_t maxiter,
-                                 int check_every, double* x, double* work, double* info, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  int rc0 = check_sell(a);
-  if (rc0 != TFEM_OK) return rc0;
+static int krylov_solve_impl(int method, const Op& A, const double* dinv, const double* b, const double* x0,
+                             double rtol, double atol, int64_t maxiter, int check_every, double* x,
+                             double* work, double* info, cudaStream_t st) {
   TFEM_REQUIRE(dinv && b && x && work && info, "krylov_solve: null pointer");
   TFEM_REQUIRE(method == TFEM_METHOD_CG || method == TFEM_METHOD_MINRES, "krylov_solve: unknown method");
-  const int64_t n = a->n_rows;
+  const int64_t n = A.n;
   if (maxiter <= 0) maxiter = (method == TFEM_METHOD_CG ? 10 : 5) * n;
   if (check_every <= 0) check_every = 32;
 
-  Sell A = make_sell(a);
   Work w = carve(work, n);
   const int vg = vec_grid(n);
   TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
@@ -778,7 +790,7 @@ extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double*
   TFEM_LAUNCH_CHECK();
   const double* q0 = nullptr;
   if (x0) {
-    int rc = launch_sell<false>(A, x, w.q, nullptr, nullptr, nullptr, nullptr, st);
+    int rc = apply_op<false>(A, x, w.q, nullptr, nullptr, nullptr, nullptr, st);
     if (rc != TFEM_OK) return rc;
     q0 = w.q;
     spmvs += 1;
@@ -796,7 +808,7 @@ extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double*
       if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
       int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
       for (int64_t it = 0; it < batch; ++it) {
-        int rc = launch_sell<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
+        int rc = apply_op<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
         if (rc != TFEM_OK) return rc;
         k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket, nullptr);
         k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
@@ -819,7 +831,7 @@ extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double*
       int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
       for (int64_t it = 0; it < batch; ++it) {
         k_mr_v<<<vg, kVecThreads, 0, st>>>(n, w.y, w.v, w.sc);
-        int rc = launch_sell<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
+        int rc = apply_op<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
         if (rc != TFEM_OK) return rc;
         k_mr_alfa<<<vg, kVecThreads, 0, st>>>(n, w.v, w.y, w.r1, w.sc, w.partials, w.ticket);
         k_mr_lanczos<<<vg, kVecThreads, 0, st>>>(n, dinv, w.y, w.r1, w.r2, w.sc, rtol, w.partials, w.ticket);
@@ -847,6 +859,52 @@ extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double*
     set_last_error("not converged", "iteration limit reached");
     return TFEM_ERR_NOT_CONVERGED;
   }
+  return TFEM_OK;
+}
+
+extern "C" int tfem_krylov_solve(int method, const tfem_sell_t* a, const double* dinv, const double* b,
+                                 const double* x0, double rtol, double atol, int64_t maxiter,
+                                 int check_every, double* x, double* work, double* info, void* stream_) {
+  int rc0 = check_sell(a);
+  if (rc0 != TFEM_OK) return rc0;
+  Op op;
+  op.sell = make_sell(a);
+  op.n = a->n_rows;
+  return krylov_solve_impl(method, op, dinv, b, x0, rtol, atol, maxiter, check_every, x, work, info,
+                           (cudaStream_t)stream_);
+}
+
+extern "C" int tfem_krylov_solve_ebe(int method, const tfem_ebe_t* a, const double* dinv, const double* b,
+                                     const double* x0, double rtol, double atol, int64_t maxiter,
+                                     int check_every, double* x, double* work, double* info, void* stream_) {
+  int rc0 = check_ebe(a);
+  if (rc0 != TFEM_OK) return rc0;
+  Op op;
+  op.ebe = true;
+  op.el = make_ebe(a);
+  op.n = a->n_nod * a->dpn;
+  return krylov_solve_impl(method, op, dinv, b, x0, rtol, atol, maxiter, check_every, x, work, info,
+                           (cudaStream_t)stream_);
+}
+
+extern "C" int tfem_ebe_spmv(const tfem_ebe_t* a, const double* x, double* y, void* stream_) {
+  int rc0 = check_ebe(a);
+  if (rc0 != TFEM_OK) return rc0;
+  TFEM_REQUIRE(x && y, "ebe_spmv: null pointer");
+  return launch_ebe<false>(make_ebe(a), x, y, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream_);
+}
+
+extern "C" int tfem_ebe_diag(const tfem_ebe_t* a, double* diag, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc0 = check_ebe(a);
+  if (rc0 != TFEM_OK) return rc0;
+  TFEM_REQUIRE(diag, "ebe_diag: null pointer");
+  const Ebe A = make_ebe(a);
+  const unsigned grid = grid_for(A.n_nod, 256);
+  if (A.dpn == 3) k_ebe_diag<3><<<grid, 256, 0, st>>>(A, diag);
+  else if (A.dpn == 2) k_ebe_diag<2><<<grid, 256, 0, st>>>(A, diag);
+  else k_ebe_diag<1><<<grid, 256, 0, st>>>(A, diag);
+  TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
 

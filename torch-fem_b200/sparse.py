@@ -21,7 +21,7 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import csr as _csr
-from .csr import CSRMatrix, JacobiPreconditioner
+from .csr import CSRMatrix, ElementOperator, JacobiPreconditioner
 
 available_backends = ["tfem_b200"]
 
@@ -63,8 +63,8 @@ class CachedSolve:
         self.previous_x = None if x is None else x.detach().clone()
 
 
-def _as_csr(A) -> CSRMatrix:
-    if isinstance(A, CSRMatrix):
+def _as_csr(A):
+    if isinstance(A, (CSRMatrix, ElementOperator)):
         return A
     if not A.is_cuda:
         raise RuntimeError(ERR_NO_CPU)
@@ -80,7 +80,7 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
     Raises ValueError for a non-square A or an unknown method and RuntimeError when the Krylov solver
     fails — the type `FEM.solve` catches to cut a load step back (reference base.py:831).
     """
-    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+    if len(A.shape) != 2 or A.shape[0] != A.shape[1]:
         raise ValueError("A should be a square 2D matrix.")
     if method is not None and method not in METHODS:
         raise ValueError(f"Method {method} is not supported. "
@@ -97,6 +97,8 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
         raise RuntimeError("Pardiso backend is not available on GPU.")
     if method == "amgx":
         raise RuntimeError(ERR_AMGX_MISSING)
+    if isinstance(Ac, ElementOperator) and method == "spsolve":
+        method = "cg"  # the matrix-free operator (kernel K8) has no entries to factorise
     if method == "spsolve":
         if n > 4 * DIRECT_LIMIT:
             raise RuntimeError(f"spsolve is a dense LU here and is limited to {4 * DIRECT_LIMIT} DOFs; "
