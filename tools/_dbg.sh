@@ -1,7 +1,3 @@
-N=${1:-4}
-RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 mkdir -p gpurun_out
-timeout 200 $RUN --master-port 29511 tools/multi_gpu_check.py --edge 6 --hexa2 2>&1 | grep -E "^\{|Error" | head
-timeout 800 $RUN --master-port 29513 bench.py --gpus $N --config C --steps 2 --warmup 2 2>gpurun_out/r1k_bench_c_n$N.err > gpurun_out/r1k_bench_c_n$N.json
-cat gpurun_out/r1k_bench_c_n$N.json
-tail -3 gpurun_out/r1k_bench_c_n$N.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 260 --csv --log-file gpurun_out/r1l_launches.csv python tools/prof_driver.py --edge 150 --iters 64 > gpurun_out/r1l_prof.log 2>&1
+tail -4 gpurun_out/r1l_prof.log

@@ -51,11 +51,18 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         print(f"spmv {fmt}: {e0.elapsed_time(e1) / 10:.4f} ms")
-    try:
-        csr.krylov_solve(A, rhs, method=a.method, rtol=1e-8, maxiter=a.iters, check_every=a.iters)
-    except RuntimeError as e:
-        print("expected:", e)
-    torch.cuda.synchronize()
+    for rep in range(2):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        try:
+            csr.krylov_solve(A, rhs, method=a.method, rtol=1e-8, maxiter=a.iters, check_every=a.iters)
+        except RuntimeError as e:
+            if rep == 0:
+                print("expected:", e)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{a.method} per iteration ({a.iters} its incl. init): {e0.elapsed_time(e1) / a.iters:.4f} ms")
     print("done", p.nnz)
 
 

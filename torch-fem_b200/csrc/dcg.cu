@@ -244,7 +244,7 @@ __global__ void k_dcg_scalars_init(double* sc, Peers P, unsigned long long ep_re
 // neighbour's halo flag has reached ep_halo; by then the flags are normally long set, so the exchange is
 // hidden behind the interior rows. p.q over owned rows -> set A.
 template <int DPN>
-__global__ void __launch_bounds__(kSellWarps * 32)
+__global__ void __launch_bounds__(kSellWarps * 32, 8)
     k_dcg_spmv(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
                double* __restrict__ q, double* sc, double* partials, unsigned int* ticket, Peers P, Halo H,
                unsigned long long ep_halo, unsigned long long ep_red) {
@@ -258,11 +258,13 @@ __global__ void __launch_bounds__(kSellWarps * 32)
   int64_t j = (int64_t)blockIdx.x * kSellWarps + warp;
   for (; j < n_int; j += stride) {
     const int64_t t = ti_lo + j;
-    const double acc = slice_row<DPN>(A, t, p, lane);
     const int64_t row = t * 32 + lane;
-    if (row >= A.dot_lo && row < A.dot_hi) {
+    const bool mine = row >= A.dot_lo && row < A.dot_hi;
+    const double pr = mine ? __ldg(p + row) : 0.0;   // requested before the row is streamed (see krylov.cu)
+    const double acc = slice_row<DPN>(A, t, p, lane);
+    if (mine) {
       q[row] = acc;
-      dot = fma(acc, __ldg(p + row), dot);
+      dot = fma(acc, pr, dot);
     }
   }
   if (j < n_all) {
@@ -279,11 +281,13 @@ __global__ void __launch_bounds__(kSellWarps * 32)
       const int64_t t = jb < n_low ? ts_lo + jb : ti_hi + (jb - n_low);
       // halo entries were written by a peer while this kernel may already have been running: read them from
       // L2 (ld.global.cg), never through an L1 sector an interior row could have pulled in earlier
-      const double acc = slice_row<DPN, true>(A, t, p, lane);
       const int64_t row = t * 32 + lane;
-      if (row >= A.dot_lo && row < A.dot_hi) {
+      const bool mine = row >= A.dot_lo && row < A.dot_hi;
+      const double pr = mine ? __ldg(p + row) : 0.0;
+      const double acc = slice_row<DPN, true>(A, t, p, lane);
+      if (mine) {
         q[row] = acc;
-        dot = fma(acc, __ldg(p + row), dot);
+        dot = fma(acc, pr, dot);
       }
     }
   }

@@ -131,7 +131,7 @@ __global__ void k_sell_fill(int64_t n, int64_t n_slices, const int64_t* __restri
 // band of the matrix (the gathered x window stays in L2). DPN = 0: scalar columns, 2/3: node-block columns.
 // DOT fuses x.y over the rows [dot_lo, dot_hi) (fixed-order reduction, last CTA writes *out_scalar).
 template <int DPN, bool DOT>
-__global__ void __launch_bounds__(kSellWarps * 32)
+__global__ void __launch_bounds__(kSellWarps * 32, 8)
     k_sell_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
                 double* partials, unsigned int* ticket, double* out_scalar) {
   __shared__ double s_red[kSellWarps];
@@ -140,11 +140,15 @@ __global__ void __launch_bounds__(kSellWarps * 32)
   double dot = 0.0;
   for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices;
        t += (int64_t)gridDim.x * kSellWarps) {
-    const double acc = slice_row<DPN>(A, t, x, lane);
     const int64_t row = t * 32 + lane;
+    // x[row] for the fused dot is requested BEFORE the row is streamed: asked for afterwards it costs every
+    // warp one exposed memory latency per slice (64 us of a 1.2 ms launch at config B)
+    double xr = 0.0;
+    if (DOT && row < A.n && row >= A.dot_lo && row < A.dot_hi) xr = __ldg(x + row);
+    const double acc = slice_row<DPN>(A, t, x, lane);
     if (row < A.n) {
       y[row] = acc;
-      if (DOT && row >= A.dot_lo && row < A.dot_hi) dot = fma(acc, __ldg(x + row), dot);
+      if (DOT) dot = fma(acc, xr, dot);
     }
   }
   if (DOT) {

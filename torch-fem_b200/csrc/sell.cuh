@@ -17,6 +17,8 @@
 // dpn 2). Padding repeats the node's last block (values there are 0.0). Matrices with unreferenced nodes
 // (rows of length 1) keep scalar columns.
 #pragma once
+#include <stdlib.h>
+
 #include "spmv.cuh"
 
 namespace tfem {
@@ -209,6 +211,10 @@ inline int resident_ctas(K kernel, int threads) {
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   const int sms = num_sms() < kSMs ? num_sms() : kSMs;
+  if (const char* cap = getenv("TFEM_CTAS_PER_SM")) {  // tuning knob for experiments (tools/prof_driver.py)
+    const int c = atoi(cap);
+    if (c >= 1 && c < per_sm) per_sm = c;
+  }
   return sms * (per_sm > 8 ? 8 : per_sm);
 }
 
