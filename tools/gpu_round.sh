@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU call: parity tests, bench, launch list, one full ncu capture of the dominant kernel.
+# One GPU call: parity tests, bench (both arms), launch list, full ncu captures of the kernels of a step.
 # usage: tools/gpu_round.sh TAG
 TAG=${1:-x}
 mkdir -p gpurun_out
@@ -11,8 +11,12 @@ echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
    --log-file gpurun_out/${TAG}_launches.csv python tools/prof_driver.py --edge 150 --iters 20 > gpurun_out/${TAG}_prof.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_sell_spmv -s 30 -c 1 \
-   -o gpurun_out/${TAG}_bsell_spmv -f python tools/prof_driver.py --edge 150 --iters 3 > gpurun_out/${TAG}_ncu_full.log 2>&1
+# integrate + the two assemblies of the driver
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_integrate|k_assemble' -c 3 \
+   -o gpurun_out/${TAG}_integrate_assemble -f python tools/prof_driver.py --edge 150 --iters 3 > gpurun_out/${TAG}_ncu_ia.log 2>&1
+# the kernels of a CG iteration (26 k_sell_spmv launches of the SpMV timing loops are skipped)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell_spmv|k_cg_update|k_cg_direction' -s 28 -c 6 \
+   -o gpurun_out/${TAG}_cg_iteration -f python tools/prof_driver.py --edge 150 --iters 3 > gpurun_out/${TAG}_ncu_cg.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log
 cat gpurun_out/${TAG}_bench.json
 tail -3 gpurun_out/${TAG}_bench.err
