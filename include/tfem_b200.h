@@ -178,6 +178,12 @@ int tfem_sell_fill(int64_t n_rows, const int64_t* indptr_dev, const int32_t* ind
                    const double* vals_dev, const int64_t* slice_ptr_dev, int32_t* sell_cols_dev,
                    double* sell_vals_dev, void* stream);
 
+/* The same for a rectangular operator with n_cols columns (AMG prolongation / restriction): the column index of a
+ * padding entry is clamped to n_cols-1 so that it never reads past the end of x. */
+int tfem_sell_fill_rect(int64_t n_rows, int64_t n_cols, const int64_t* indptr_dev, const int32_t* indices_dev,
+                        const double* vals_dev, const int64_t* slice_ptr_dev, int32_t* sell_cols_dev,
+                        double* sell_vals_dev, void* stream);
+
 /* Node-block column indices (optional, dpn = 2 or 3): FEM rows come in groups of dpn that share their column
  * blocks (column of entry k = dpn*adj[k/dpn] + k%dpn), so one int32 per (node, block) replaces one per entry
  * and the index stream drops from 4 to 4/dpn^2 bytes per nonzero (8.5 instead of 12 B/nnz for dpn = 3).
@@ -322,6 +328,96 @@ int tfem_dcg_solve(void* comm, const tfem_sell_t* A_local, int64_t row_lo, int64
                    int n_recv, const int32_t* recv_peers_host, const double* dinv_dev, const double* b_dev,
                    double* x_dev, double* work_dev, double rtol, double atol, int64_t maxiter, int check_every,
                    double timeout_s, double* info_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K11-K16 — aggregation algebraic multigrid (smoothed aggregation on the node graph) and AMG-preconditioned CG.
+ * Replaces the reference's third-party AMG back ends: pyamg smoothed_aggregation_solver(A, B, smooth="jacobi") + scipy
+ * cg/minres on the CPU (src/torchfem/sparse.py:493-512) and the AmgX aggregation-AMG solver on the GPU
+ * (src/torchfem/amgx.py:71-98 config: V cycle, 1 pre / 1 post sweep, dense coarse solve; sparse.py:422-442).
+ *
+ * Operators are block CSR over nodes with d x d blocks (d = DOFs per node, 1..3): bptr int64 [nb+1], bcol int32 sorted
+ * per row, values in the scalar-CSR order of the assembled matrix: block row I with m blocks owns d*d*m doubles at
+ * d*d*bptr[I], entry (row DOF a, s-th block, column DOF c) at (a*m + s)*d + c. Level 0 is (node_ptr, adj, vals) of
+ * tfem_pattern_phase2 / tfem_assemble unchanged. The host (torch-fem_b200/amg.py) owns all buffers and drives the
+ * setup level by level:
+ *   row_info -> rho -> aggregate -> prolongator_count/fill -> transpose_structure/values -> spgemm (A P, then R (A P)).
+ * Everything is deterministic (integer atomics only; floating-point sums in a fixed order).
+ * ------------------------------------------------------------------------------------------------- */
+
+/* dinv[i] = 1/A_ii; iso[i] = 1 if every off-diagonal entry of row i is zero (Dirichlet rows after the masking of
+ * tfem_assemble, base.py:414-419). fix_zero_diag != 0 (coarse levels): a zero diagonal (aggregate made of isolated
+ * DOFs only) is replaced by 1 in vals_dev. */
+int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, double* vals_dev,
+                      int fix_zero_diag, double* dinv_dev, uint8_t* iso_dev, void* stream);
+
+/* Spectral radius of D^-1 A by `iterations` steps of the power method from a fixed start vector (synchronises).
+ * work_dev: double [tfem_amg_work_doubles(n)]. */
+int64_t tfem_amg_work_doubles(int64_t n_rows);
+int tfem_amg_rho(const tfem_sell_t* A, const double* dinv_dev, int iterations, double* work_dev, double* rho_host,
+                 void* stream);
+
+/* Aggregation: maximal independent set of the node graph in Luby rounds with fixed pseudo-random keys, then every
+ * node joins the adjacent root with the largest key; aggregates are numbered in root order. agg_dev: int32 [nb] out.
+ * state_work int8 [nb], flag_work uint8 [nb], index_work int32 [nb]: scratch. Synchronises (one flag per round). */
+int tfem_amg_aggregate(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, int8_t* state_work_dev,
+                       uint8_t* flag_work_dev, int32_t* index_work_dev, int32_t* agg_dev, int64_t* n_agg_host,
+                       int32_t* rounds_host, void* stream);
+
+/* Smoothed prolongator P = (I - omega D^-1 A) T, T[i, agg(i)] = diag(1 - iso_i). count: pptr_dev int64 [nb+1] out
+ * (offsets); fill: pcol_dev int32 [pptr[nb]] (sorted per row), pvals_dev double [d*d*pptr[nb]].
+ * TFEM_ERR_CAPACITY if a node has more than 1024 neighbours. */
+int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,
+                               const int32_t* agg_dev, int64_t* pptr_dev, void* stream);
+int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,
+                              const double* vals_dev, const int32_t* agg_dev, const double* dinv_dev,
+                              const uint8_t* iso_dev, double omega, const int64_t* pptr_dev, int32_t* pcol_dev,
+                              double* pvals_dev, void* stream);
+
+/* Block transpose. structure: tptr int64 [n_cols+1], tcol int32 [nblk] sorted per row, tsrc int32 [nblk] = index of
+ * the source block; values: tvals = transposed blocks gathered through tsrc (a values-only refresh repeats only this). */
+int tfem_amg_transpose_structure(int64_t n_rows, int64_t n_cols, const int64_t* ptr_dev, const int32_t* col_dev,
+                                 int64_t nblk, int64_t* tptr_dev, int32_t* tcol_dev, int32_t* tsrc_dev, void* stream);
+int tfem_amg_transpose_values(int d, int64_t n_cols, const int64_t* ptr_dev, const double* vals_dev,
+                              const int64_t* tptr_dev, const int32_t* tcol_dev, const int32_t* tsrc_dev,
+                              double* tvals_dev, void* stream);
+
+/* Block SpGEMM C = X Y. count: cptr int64 [nx+1] out; fill: ccol int32 sorted per row; numeric: cvals with every
+ * entry summed in the order of X's row (fixed order). max_row = longest row of C (blocks).
+ * TFEM_ERR_CAPACITY if a row of C has more than 12288 distinct block columns. */
+int tfem_amg_spgemm_count(int64_t nx, const int64_t* xptr_dev, const int32_t* xcol_dev, const int64_t* yptr_dev,
+                          const int32_t* ycol_dev, int64_t* cptr_dev, void* stream);
+int tfem_amg_spgemm_fill(int64_t nx, const int64_t* xptr_dev, const int32_t* xcol_dev, const int64_t* yptr_dev,
+                         const int32_t* ycol_dev, const int64_t* cptr_dev, int32_t* ccol_dev, void* stream);
+int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr_dev, const int32_t* xcol_dev,
+                            const double* xvals_dev, const int64_t* yptr_dev, const int32_t* ycol_dev,
+                            const double* yvals_dev, const int64_t* cptr_dev, const int32_t* ccol_dev,
+                            double* cvals_dev, int max_row, void* stream);
+
+/* One level of the hierarchy as the cycle takes it. P / R are unused on the coarsest level. x, b, t: work vectors of
+ * the level's length (b unused on level 0). */
+#define TFEM_AMG_MAX_LEVELS 16
+typedef struct tfem_amg_level {
+  tfem_sell_t A;        /* level operator (SELL-32) */
+  tfem_sell_t P;        /* prolongation from the next coarser level: n_rows = this level */
+  tfem_sell_t R;        /* restriction to the next coarser level:   n_rows = next level */
+  const double* dinv;   /* 1 / diag(A) */
+  double omega;         /* damped-Jacobi weight 4 / (3 rho(D^-1 A)) */
+  double* x;
+  double* b;
+  double* t;
+} tfem_amg_level_t;
+
+/* z = M r: V(1,1) cycle with damped Jacobi, dense inverse (coarse_inv_dev, row-major [n_c, n_c]) on the coarsest
+ * level. Symmetric positive definite for SPD A, hence a valid CG preconditioner. r and z must not alias. */
+int tfem_amg_vcycle(const tfem_amg_level_t* levels_host, int n_levels, const double* coarse_inv_dev,
+                    const double* r_dev, double* z_dev, void* stream);
+
+/* CG preconditioned with the V cycle; stopping rule, maxiter and info_host as tfem_krylov_solve (CG). The r.z and p.q
+ * dot products are fused into the last smoother / the SpMV. The host polls the convergence flag every iteration (one
+ * iteration is a whole cycle). work_dev: double [tfem_amg_work_doubles(n)]. */
+int tfem_amg_pcg_solve(const tfem_amg_level_t* levels_host, int n_levels, const double* coarse_inv_dev,
+                       const double* b_dev, const double* x0_dev, double rtol, double atol, int64_t maxiter,
+                       double* x_dev, double* work_dev, double* info_host, void* stream);
 
 /* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
  * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */

@@ -1,0 +1,78 @@
+"""AMG-PCG on the benchmark cube: setup / solve timings, iteration counts and the hierarchy, next to Jacobi-PCG.
+    python tools/amg_check.py --edge 64 100 150
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+
+def timed(fn):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize()
+    return out, (time.perf_counter() - t0) * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--edge", type=int, nargs="+", default=[64])
+    ap.add_argument("--rtol", type=float, default=1e-8)
+    ap.add_argument("--jacobi", action="store_true")
+    a = ap.parse_args()
+    torch.set_default_dtype(torch.float64)
+    import torchfem_b200 as T
+    from torchfem_b200 import csr
+    from torchfem_b200.amg import AMGPreconditioner
+    from oracle import fem_oracle as O
+
+    dev = torch.device("cuda", 0)
+    for E in a.edge:
+        nodes, elements, con, disp = bench.build_problem(T, torch, E, dev)
+        bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
+        C = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous().to(dev)
+        nodes, elements = nodes.to(dev), elements.to(dev)
+        is_con = con.ravel().to(torch.uint8).to(dev)
+        ubc = (disp.ravel() * con.ravel()).to(dev)
+        p = csr.Pattern(elements, nodes.shape[0], 3)
+        k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C)
+        lift = torch.empty(p.n_dofs, device=dev)
+        vals = csr.assemble(p, k, is_con, ubc=ubc, lift=lift)
+        del k
+        A = p.matrix(vals)
+        b = lift
+        A.sell()
+        out = {"edge": E, "n_dofs": p.n_dofs, "nnz": p.nnz}
+        for rep in range(2):
+            amg, t_setup = timed(lambda: AMGPreconditioner(A))
+            (x, st), t_solve = timed(lambda: amg.solve(b, rtol=a.rtol))
+        _, t_resetup = timed(lambda: amg._setup(A, symbolic=False))
+        (x, st), t_solve2 = timed(lambda: amg.solve(b, rtol=a.rtol))
+        res = float((A.matvec(x) - b).norm() / b.norm())
+        out.update({"amg_setup_ms": t_setup, "amg_resetup_ms": t_resetup, "amg_solve_ms": t_solve2,
+                    "amg_iterations": st["iterations"], "amg_ms_per_iteration": t_solve2 / max(st["iterations"], 1),
+                    "true_rel_residual": res, "levels": [(lv.n, lv.op.nblk * lv.d ** 2) for lv in amg.levels],
+                    "operator_complexity": amg.operator_complexity,
+                    "mis_rounds": [getattr(lv, "mis_rounds", None) for lv in amg.levels[:-1]],
+                    "rho": [getattr(lv, "rho", None) for lv in amg.levels[:-1]],
+                    "launches": st["launches"],
+                    "amg_dofs_per_s_setup_plus_solve": p.n_dofs / ((t_setup + t_solve2) * 1e-3)})
+        if a.jacobi:
+            for rep in range(2):
+                (xj, _, sj), t_j = timed(lambda: csr.krylov_solve(A, b, method="cg", rtol=a.rtol))
+            out.update({"jacobi_solve_ms": t_j, "jacobi_iterations": sj["iterations"],
+                        "rel_diff_amg_vs_jacobi": float((x - xj).norm() / xj.norm())})
+        print(json.dumps(out), flush=True)
+        del amg, A, p, vals, x
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,6 +45,15 @@ class EbeStruct(ctypes.Structure):
 _EBE_P = ctypes.POINTER(EbeStruct)
 
 
+class AmgLevelStruct(ctypes.Structure):
+    """`tfem_amg_level_t` of include/tfem_b200.h."""
+    _fields_ = [("A", SellStruct), ("P", SellStruct), ("R", SellStruct), ("dinv", c_void_p), ("omega", c_double),
+                ("x", c_void_p), ("b", c_void_p), ("t", c_void_p)]
+
+
+_AMG_P = ctypes.POINTER(AmgLevelStruct)
+
+
 class HaloSendStruct(ctypes.Structure):
     """`tfem_halo_send_t` of include/tfem_b200.h."""
     _fields_ = [("peer", ctypes.c_int32), ("count", c_int64), ("src_idx", c_void_p), ("dst_idx", c_void_p),
@@ -83,7 +92,23 @@ _SIGNATURES = {
     "tfem_bsell_fill": (c_int, [c_int64, c_int, c_int64] + [c_void_p] * 5),
     "tfem_sell_slice_ptr": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_sell_fill": (c_int, [c_int64] + [c_void_p] * 7),
+    "tfem_sell_fill_rect": (c_int, [c_int64, c_int64] + [c_void_p] * 7),
     "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
+    "tfem_amg_row_info": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "tfem_amg_work_doubles": (c_int64, [c_int64]),
+    "tfem_amg_rho": (c_int, [_SELL_P, c_void_p, c_int, c_void_p, ctypes.POINTER(c_double), c_void_p]),
+    "tfem_amg_aggregate": (c_int, [c_int64] + [c_void_p] * 6 + [ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_int32),
+                                                              c_void_p]),
+    "tfem_amg_prolongator_count": (c_int, [c_int, c_int64] + [c_void_p] * 5),
+    "tfem_amg_prolongator_fill": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double] + [c_void_p] * 4),
+    "tfem_amg_transpose_structure": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int64] + [c_void_p] * 4),
+    "tfem_amg_transpose_values": (c_int, [c_int, c_int64] + [c_void_p] * 7),
+    "tfem_amg_spgemm_count": (c_int, [c_int64] + [c_void_p] * 6),
+    "tfem_amg_spgemm_fill": (c_int, [c_int64] + [c_void_p] * 7),
+    "tfem_amg_spgemm_numeric": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_int, c_void_p]),
+    "tfem_amg_vcycle": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfem_amg_pcg_solve": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),
     "tfem_cg_stage": (c_int, [c_int, _SELL_P, c_int64, c_int64] + [c_void_p] * 5 + [c_double, c_double, c_void_p]),
     "tfem_comm_create": (c_int, [c_int, c_int, c_int64, ctypes.POINTER(c_void_p), c_void_p]),

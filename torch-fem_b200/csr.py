@@ -131,8 +131,9 @@ class SellStructure:
     indices (4 B/nnz) or node-block column indices (4/dpn^2 B/nnz, only for patterns built from a mesh
     with dpn in {2,3} and no unreferenced nodes). Built lazily, shared by every matrix on the pattern."""
 
-    def __init__(self, indptr: Tensor, indices: Tensor, n: int, block=None):
+    def __init__(self, indptr: Tensor, indices: Tensor, n: int, block=None, n_cols: int | None = None):
         self.indptr, self.indices, self.n = indptr, indices, int(n)
+        self.n_cols = int(n) if n_cols is None else int(n_cols)   # rectangular operators (AMG P / R)
         n_slices = (self.n + 31) // 32
         self.slice_ptr = _i64(n_slices + 1, indptr.device)
         L.check(L.lib.tfem_sell_slice_ptr(self.n, L.ptr(indptr), L.ptr(self.slice_ptr), L.stream()))
@@ -145,8 +146,8 @@ class SellStructure:
     def cols(self) -> Tensor:
         if self._cols is None:
             self._cols = _i32(max(self.padded, 4), self.indptr.device)
-            L.check(L.lib.tfem_sell_fill(self.n, L.ptr(self.indptr), L.ptr(self.indices), None,
-                                         L.ptr(self.slice_ptr), L.ptr(self._cols), None, L.stream()))
+            L.check(L.lib.tfem_sell_fill_rect(self.n, self.n_cols, L.ptr(self.indptr), L.ptr(self.indices), None,
+                                              L.ptr(self.slice_ptr), L.ptr(self._cols), None, L.stream()))
         return self._cols
 
     @property

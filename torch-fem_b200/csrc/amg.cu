@@ -1,0 +1,1000 @@
+// K11-K16 — aggregation algebraic multigrid: setup kernels, V cycle and AMG-preconditioned CG.
+//
+// Replaces the two third-party AMG back ends of the reference: pyamg `smoothed_aggregation_solver(A, B,
+// smooth="jacobi")` + scipy cg on the CPU (src/torchfem/sparse.py:493-512) and the AmgX aggregation-AMG solver on the
+// GPU (src/torchfem/amgx.py:71-98, sparse.py:422-442; V cycle, one pre/post sweep, dense solve on the coarsest
+// level). The algorithm is smoothed aggregation (Vanek/Mandel/Brezina) on the NODE graph with d x d blocks:
+//   K11 row info        dinv, "isolated" DOFs (Dirichlet rows), zero-diagonal repair on coarse levels
+//   K12 aggregation     maximal independent set with fixed pseudo-random keys (Luby rounds), members join the
+//                       adjacent root with the largest key                       — integer only, deterministic
+//   K13 prolongator     P = (I - w D^-1 A) T, T = masked piecewise-constant translations; pattern + values per row
+//   K14 transpose       R = P^T (counting sort on columns, rows sorted by rank; values gathered through `src`)
+//   K15 SpGEMM          C = X Y on block-CSR operands: symbolic (shared-memory hash set per row, rank sort) and
+//                       numeric (shared-memory accumulators, contributions added in the order of X's row — fixed
+//                       summation order, no FP atomics); used for A P and R (A P)
+//   K16 V cycle / PCG   SELL-32 SpMV (sell.cuh) with fused epilogues: residual, damped-Jacobi update, prolongation
+//                       add, and the r.z / p.q dot products of CG
+//
+// Every operator of the hierarchy (A_l, P_l, R_l) is a block-CSR matrix over nodes (bptr int64, bcol int32 sorted)
+// whose values are stored in the SCALAR CSR order of the assembled matrix: block row I with m blocks owns
+// d*d*m values at d*d*bptr[I]; entry (a, s, c) = row DOF a, s-th block, column DOF c sits at (a*m + s)*d + c.
+// That is exactly the layout tfem_assemble writes, so level 0 is the assembled matrix itself and every level can be
+// handed to the SELL-32 converter unchanged.
+#include <math.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "sell.cuh"
+
+namespace tfem {
+namespace {
+
+constexpr int kRowCap = 1024;  // blocks per block row the prolongator kernel can hold in shared memory
+
+__device__ __forceinline__ uint32_t hash32(uint32_t h) {  // MurmurHash3 finaliser, as oracle/amg_oracle.py
+  h += 0x9E3779B9u;
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ uint64_t mis_key(int64_t i) {
+  return ((uint64_t)hash32((uint32_t)i) << 32) | (uint64_t)(i + 1);
+}
+
+// ------------------------------------------------------------------------------------------ K11 row info
+template <int D>
+__global__ void k_row_info(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                           double* vals, int fix_zero_diag, double* __restrict__ dinv,
+                           uint8_t* __restrict__ iso) {
+  const int lane = threadIdx.x & 31;
+  const int64_t I = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (I >= nb) return;
+  const int64_t b0 = bptr[I];
+  const int m = (int)(bptr[I + 1] - b0);
+  for (int a = 0; a < D; ++a) {
+    double* row = vals + D * D * b0 + (int64_t)a * m * D;
+    double diag = 0.0;
+    int dpos = -1;
+    bool off = false;
+    for (int e = lane; e < m * D; e += 32) {
+      const int s = e / D, c = e - s * D;
+      const double v = row[e];
+      if (bcol[b0 + s] == (int32_t)I && c == a) {
+        diag = v;
+        dpos = e;
+      } else if (v != 0.0) {
+        off = true;
+      }
+    }
+    off = __any_sync(0xffffffffu, off);
+    const double dsum = warp_sum(diag);  // exactly one lane holds it
+    if (fix_zero_diag && dsum == 0.0 && dpos >= 0) row[dpos] = 1.0;
+    if (lane == 0) {
+      dinv[I * D + a] = 1.0 / ((fix_zero_diag && dsum == 0.0) ? 1.0 : dsum);
+      iso[I * D + a] = off ? 0 : 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ power iteration
+__global__ void k_pw_init(int64_t n, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = 1.0 + (double)(hash32((uint32_t)i) & 1023u) / 1024.0;
+}
+
+// y <- dinv*y ; sums y.y and x.x
+__global__ void __launch_bounds__(kVecThreads)
+    k_pw_step(int64_t n, const double* __restrict__ dinv, const double* __restrict__ x, double* __restrict__ y,
+              double* sc, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  double yy = 0.0, xx = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+    const double yi = dinv[i] * y[i], xi = x[i];
+    y[i] = yi;
+    yy = fma(yi, yi, yy);
+    xx = fma(xi, xi, xx);
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<kVecThreads>(yy, s_red);
+  mine[1] = block_sum<kVecThreads>(xx, s_red);
+  if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    sc[0] = tot[0];
+    sc[1] = tot[1];
+  }
+}
+
+__global__ void k_pw_scale(int64_t n, const double* __restrict__ y, double* __restrict__ x, const double* sc) {
+  const double s = 1.0 / sqrt(sc[0]);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = s * y[i];
+}
+
+// ------------------------------------------------------------------------------------------ K12 aggregation
+__global__ void k_mis_select(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                             const int8_t* __restrict__ state, uint8_t* __restrict__ newroot) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  uint8_t nr = 0;
+  if (state[i] == 0) {
+    const uint64_t me = mis_key(i);
+    nr = 1;
+    for (int64_t k = bptr[i]; k < bptr[i + 1]; ++k) {
+      const int32_t j = bcol[k];
+      if (j != i && state[j] == 0 && mis_key(j) > me) {
+        nr = 0;
+        break;
+      }
+    }
+  }
+  newroot[i] = nr;
+}
+
+__global__ void k_mis_apply(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                            int8_t* __restrict__ state, const uint8_t* __restrict__ newroot, int* n_undecided) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb || state[i] != 0) return;
+  if (newroot[i]) {
+    state[i] = 1;
+    return;
+  }
+  for (int64_t k = bptr[i]; k < bptr[i + 1]; ++k)
+    if (newroot[bcol[k]]) {
+      state[i] = 2;
+      return;
+    }
+  atomicAdd(n_undecided, 1);
+}
+
+__global__ void k_mis_flags(int64_t nb, const int8_t* __restrict__ state, int32_t* __restrict__ flag) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nb) flag[i] = state[i] == 1 ? 1 : 0;
+}
+
+__global__ void k_mis_assign(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                             const int8_t* __restrict__ state, const int32_t* __restrict__ root_index,
+                             int32_t* __restrict__ agg) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  uint64_t best = state[i] == 1 ? mis_key(i) : 0ull;
+  for (int64_t k = bptr[i]; k < bptr[i + 1]; ++k) {
+    const int32_t j = bcol[k];
+    if (state[j] == 1) {
+      const uint64_t kj = mis_key(j);
+      if (kj > best) best = kj;
+    }
+  }
+  const int64_t root = (int64_t)(best & 0xFFFFFFFFull) - 1;
+  agg[i] = root >= 0 ? root_index[root] : -1;
+}
+
+// ------------------------------------------------------------------------------------------ K13 prolongator
+// One warp per fine node: the distinct aggregates of its neighbours, sorted (rank by counting in shared memory),
+// then  P[i,J] = delta(J, agg i) diag(1-iso_i) - w Dinv_i sum_{j in adj(i), agg j = J} A_ij diag(1-iso_j)
+// with the sum taken in adjacency order.
+template <int D, bool FILL>
+__global__ void __launch_bounds__(128)
+    k_prolongator(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                  const double* __restrict__ vals, const int32_t* __restrict__ agg,
+                  const double* __restrict__ dinv, const uint8_t* __restrict__ iso, double omega,
+                  int64_t* __restrict__ pcount, const int64_t* __restrict__ pptr, int32_t* __restrict__ pcol,
+                  double* __restrict__ pvals, int* err) {
+  __shared__ int s_key[4][kRowCap];
+  __shared__ int s_ukey[4][kRowCap];
+  __shared__ short s_rank[4][kRowCap];
+  __shared__ unsigned char s_first[4][kRowCap];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t I = blockIdx.x * 4ll + w;
+  if (I >= nb) return;
+  const int64_t b0 = bptr[I];
+  const int L = (int)(bptr[I + 1] - b0);
+  if (L > kRowCap) {
+    if (lane == 0) *err = 1;
+    return;
+  }
+  int* key = s_key[w];
+  for (int e = lane; e < L; e += 32) key[e] = agg[bcol[b0 + e]];
+  __syncwarp();
+  int firsts = 0;
+  for (int e = lane; e < L; e += 32) {
+    const int k = key[e];
+    bool first = true;
+    for (int e2 = 0; e2 < e; ++e2)
+      if (key[e2] == k) {
+        first = false;
+        break;
+      }
+    s_first[w][e] = first ? 1 : 0;
+    firsts += first ? 1 : 0;
+  }
+  const int m = warp_sum_int(firsts);
+  if (!FILL) {
+    if (lane == 0) pcount[I] = m;
+    return;
+  }
+  __syncwarp();
+  for (int e = lane; e < L; e += 32) {
+    const int k = key[e];
+    int r = 0;
+    for (int e2 = 0; e2 < L; ++e2) r += (s_first[w][e2] && key[e2] < k) ? 1 : 0;
+    s_rank[w][e] = (short)r;
+    if (s_first[w][e]) s_ukey[w][r] = k;
+  }
+  __syncwarp();
+  const int64_t p0 = pptr[I];
+  for (int r = lane; r < m; r += 32) pcol[p0 + r] = s_ukey[w][r];
+  const int mine = agg[I];
+  const double* arow = vals + D * D * b0;
+  double* prow = pvals + D * D * p0;
+  for (int o = lane; o < m * D * D; o += 32) {
+    const int r = o / (D * D), a = (o / D) % D, c = o % D;
+    double sum = 0.0;
+    for (int e = 0; e < L; ++e)
+      if (s_rank[w][e] == r) {
+        const int64_t j = bcol[b0 + e];
+        if (!iso[j * D + c]) sum += arow[((int64_t)a * L + e) * D + c];
+      }
+    double v = -omega * dinv[I * D + a] * sum;
+    if (s_ukey[w][r] == mine && a == c && !iso[I * D + a]) v += 1.0;
+    prow[((int64_t)a * m + r) * D + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K14 transpose
+__global__ void k_bt_count(int64_t nblk, const int32_t* __restrict__ col, int64_t* __restrict__ tptr) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k < nblk) atomicAdd((unsigned long long*)&tptr[col[k] + 1], 1ull);
+}
+__global__ void k_bt_fill(int64_t nrows, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col,
+                          const int64_t* __restrict__ tptr, int32_t* __restrict__ cursor,
+                          int32_t* __restrict__ tcol_tmp, int32_t* __restrict__ tsrc_tmp) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nrows) return;
+  for (int64_t k = ptr[i]; k < ptr[i + 1]; ++k) {
+    const int32_t c = col[k];
+    const int64_t dst = tptr[c] + atomicAdd(&cursor[c], 1);
+    tcol_tmp[dst] = (int32_t)i;
+    tsrc_tmp[dst] = (int32_t)k;
+  }
+}
+// one warp per transposed row: rank sort by (unique) column
+__global__ void k_bt_sort(int64_t ntrows, const int64_t* __restrict__ tptr, const int32_t* __restrict__ tcol_tmp,
+                          const int32_t* __restrict__ tsrc_tmp, int32_t* __restrict__ tcol,
+                          int32_t* __restrict__ tsrc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t J = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (J >= ntrows) return;
+  const int64_t b = tptr[J];
+  const int L = (int)(tptr[J + 1] - b);
+  for (int e = lane; e < L; e += 32) {
+    const int32_t k = tcol_tmp[b + e];
+    int r = 0;
+    for (int e2 = 0; e2 < L; ++e2) r += tcol_tmp[b + e2] < k ? 1 : 0;
+    tcol[b + r] = k;
+    tsrc[b + r] = tsrc_tmp[b + e];
+  }
+}
+template <int D>
+__global__ void k_bt_vals(int64_t ntrows, const int64_t* __restrict__ ptr, const double* __restrict__ vals,
+                          const int64_t* __restrict__ tptr, const int32_t* __restrict__ tcol,
+                          const int32_t* __restrict__ tsrc, double* __restrict__ tvals) {
+  const int lane = threadIdx.x & 31;
+  const int64_t J = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (J >= ntrows) return;
+  const int64_t b = tptr[J];
+  const int L = (int)(tptr[J + 1] - b);
+  for (int o = lane; o < L * D * D; o += 32) {
+    const int t = o / (D * D), c = (o / D) % D, a = o % D;  // transposed entry (c, a) <- source entry (a, c)
+    const int64_t i = tcol[b + t];
+    const int64_t p0 = ptr[i];
+    const int mi = (int)(ptr[i + 1] - p0);
+    const int s = (int)(tsrc[b + t] - p0);
+    tvals[D * D * b + ((int64_t)c * L + t) * D + a] = vals[D * D * p0 + ((int64_t)a * mi + s) * D + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K15 SpGEMM
+// symbolic: one warp per row of C = X Y; the distinct columns are collected in a shared-memory hash set (integer CAS;
+// the resulting SET does not depend on the insertion order), compacted and rank-sorted.
+template <int HC, bool FILL>
+__global__ void k_spgemm_sym(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
+                             const int64_t* __restrict__ yptr, const int32_t* __restrict__ ycol,
+                             int64_t* __restrict__ ccount, const int64_t* __restrict__ cptr,
+                             int32_t* __restrict__ ccol, int* err) {
+  extern __shared__ int s_dyn[];
+  const int W = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* table = s_dyn + (size_t)w * HC;
+  int* list = s_dyn + (size_t)W * HC + (size_t)w * HC;
+  int* counter = s_dyn + (size_t)2 * W * HC + w;
+  for (int64_t i = blockIdx.x * (int64_t)W + w; i < nx; i += (int64_t)gridDim.x * W) {
+    for (int e = lane; e < HC; e += 32) table[e] = -1;
+    if (lane == 0) *counter = 0;
+    __syncwarp();
+    bool overflow = false;
+    for (int64_t kx = xptr[i]; kx < xptr[i + 1]; ++kx) {
+      const int64_t j = xcol[kx];
+      const int64_t y0 = yptr[j];
+      const int LY = (int)(yptr[j + 1] - y0);
+      for (int e = lane; e < LY; e += 32) {
+        const int key = ycol[y0 + e];
+        unsigned h = ((unsigned)key * 2654435761u) & (HC - 1);
+        int probes = 0;
+        while (true) {
+          const int old = atomicCAS(&table[h], -1, key);
+          if (old == -1) {
+            atomicAdd(counter, 1);
+            break;
+          }
+          if (old == key) break;
+          h = (h + 1) & (HC - 1);
+          if (++probes >= HC) {
+            overflow = true;
+            break;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const int m = *counter;
+    if (__any_sync(0xffffffffu, overflow) || m > (HC / 4) * 3) {
+      if (lane == 0) *err = 1;
+      if (!FILL && lane == 0) ccount[i] = 0;
+      __syncwarp();
+      continue;
+    }
+    if (!FILL) {
+      if (lane == 0) ccount[i] = m;
+      __syncwarp();
+      continue;
+    }
+    int off = 0;
+    for (int base = 0; base < HC; base += 32) {
+      const int v = table[base + lane];
+      const unsigned mask = __ballot_sync(0xffffffffu, v != -1);
+      if (v != -1) list[off + __popc(mask & ((1u << lane) - 1u))] = v;
+      off += __popc(mask);
+    }
+    __syncwarp();
+    const int64_t c0 = cptr[i];
+    for (int e = lane; e < m; e += 32) {
+      const int k = list[e];
+      int r = 0;
+      for (int e2 = 0; e2 < m; ++e2) r += list[e2] < k ? 1 : 0;
+      ccol[c0 + r] = k;
+    }
+    __syncwarp();
+  }
+}
+
+// numeric: one warp per row of C; accumulators for the row live in shared memory. X's row is walked sequentially,
+// the lanes spread over (entry of Y's row, row DOF): every accumulator receives its contributions in the order of
+// X's row, one per step — a fixed summation order.
+template <int D>
+__global__ void k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
+                             const double* __restrict__ xvals, const int64_t* __restrict__ yptr,
+                             const int32_t* __restrict__ ycol, const double* __restrict__ yvals,
+                             const int64_t* __restrict__ cptr, const int32_t* __restrict__ ccol,
+                             double* __restrict__ cvals, int MC) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int DD = D * D;
+  const int W = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* acc = reinterpret_cast<double*>(s_raw) + (size_t)w * MC * DD;
+  int* cc = reinterpret_cast<int*>(reinterpret_cast<double*>(s_raw) + (size_t)W * MC * DD) + (size_t)w * MC;
+  for (int64_t i = blockIdx.x * (int64_t)W + w; i < nx; i += (int64_t)gridDim.x * W) {
+    const int64_t c0 = cptr[i];
+    const int m = (int)(cptr[i + 1] - c0);
+    for (int e = lane; e < m; e += 32) cc[e] = ccol[c0 + e];
+    for (int e = lane; e < m * DD; e += 32) acc[e] = 0.0;
+    __syncwarp();
+    const int64_t x0 = xptr[i];
+    const int LX = (int)(xptr[i + 1] - x0);
+    for (int kx = 0; kx < LX; ++kx) {
+      const int64_t j = xcol[x0 + kx];
+      const int64_t y0 = yptr[j];
+      const int LY = (int)(yptr[j + 1] - y0);
+      for (int o = lane; o < LY * D; o += 32) {
+        const int t = o / D, a = o - t * D;
+        const int key = ycol[y0 + t];
+        int lo = 0, hi = m - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (cc[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        double xa[D];
+#pragma unroll
+        for (int b = 0; b < D; ++b) xa[b] = xvals[DD * x0 + ((int64_t)a * LX + kx) * D + b];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          double s = 0.0;
+#pragma unroll
+          for (int b = 0; b < D; ++b) s = fma(xa[b], yvals[DD * y0 + ((int64_t)b * LY + t) * D + c], s);
+          acc[lo * DD + a * D + c] += s;
+        }
+      }
+      __syncwarp();
+    }
+    for (int o = lane; o < m * DD; o += 32) {
+      const int pos = o / DD, a = (o / D) % D, c = o % D;
+      cvals[DD * c0 + ((int64_t)a * m + pos) * D + c] = acc[pos * DD + a * D + c];
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K16 V cycle
+enum { M_AX = 0, M_RES = 1, M_JAC = 2, M_ADD = 3 };
+
+// y = A x (M_AX) | b - A x (M_RES) | x + w dinv (b - A x) (M_JAC, y != x) | y + A x (M_ADD), one warp per SELL
+// slice, persistent grid. DOT: x.(A x) for M_AX, b.y for M_JAC (fixed-order reduction, last CTA writes *out_scalar).
+template <int DPN, int MODE, bool DOT>
+__global__ void __launch_bounds__(kSellWarps * 32, (MODE == M_JAC || DOT) ? 6 : 8)
+    k_amg_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+               const double* __restrict__ dinv, double omega, double* partials, unsigned int* ticket,
+               double* out_scalar) {
+  __shared__ double s_red[kSellWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double dot = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices; t += (int64_t)gridDim.x * kSellWarps) {
+    const int64_t row = t * 32 + lane;
+    const bool live = row < A.n;
+    double xr = 0.0, br = 0.0, dr = 0.0;
+    if (live) {
+      if (MODE == M_JAC || (MODE == M_AX && DOT)) xr = __ldg(x + row);
+      if (MODE == M_RES || MODE == M_JAC) br = __ldg(b + row);
+      if (MODE == M_JAC) dr = __ldg(dinv + row);
+      if (MODE == M_ADD) br = y[row];
+    }
+    const double acc = slice_row<DPN>(A, t, x, lane);
+    if (live) {
+      double v;
+      if (MODE == M_AX) v = acc;
+      else if (MODE == M_RES) v = br - acc;
+      else if (MODE == M_JAC) v = fma(omega * dr, br - acc, xr);
+      else v = br + acc;
+      y[row] = v;
+      if (DOT) dot = fma(MODE == M_AX ? xr : br, v, dot);
+    }
+  }
+  if (DOT) {
+    const double s = block_sum<kSellWarps * 32>(dot, s_red);
+    double mine[1] = {s}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
+  }
+}
+
+template <int DPN, int MODE, bool DOT>
+int launch_amg_spmv_t(const Sell& A, const double* x, double* y, const double* b, const double* dinv, double omega,
+                      double* partials, unsigned int* ticket, double* out_scalar, cudaStream_t st) {
+  static int g = 0;  // per instantiation
+  if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT>, kSellWarps * 32);
+  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+  k_amg_spmv<DPN, MODE, DOT><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
+                                                                                    partials, ticket, out_scalar);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <int MODE, bool DOT>
+int launch_amg_spmv(const Sell& A, const double* x, double* y, const double* b, const double* dinv, double omega,
+                    double* partials, unsigned int* ticket, double* out_scalar, cudaStream_t st) {
+  if (A.dpn == 3) return launch_amg_spmv_t<3, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
+  if (A.dpn == 2) return launch_amg_spmv_t<2, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
+  return launch_amg_spmv_t<0, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
+}
+
+// x = w dinv b  (one damped-Jacobi sweep from the zero vector)
+__global__ void __launch_bounds__(kVecThreads)
+    k_jacobi_first(int64_t n, double omega, const double* __restrict__ dinv, const double* __restrict__ b,
+                   double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+    x[i] = omega * dinv[i] * b[i];
+}
+
+// coarsest level: x = Ainv b, dense row-major, one warp per row
+__global__ void k_dense_mv(int n, const double* __restrict__ Minv, const double* __restrict__ b,
+                           double* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int r = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+  if (r >= n) return;
+  double s = 0.0;
+  for (int k = lane; k < n; k += 32) s = fma(Minv[(int64_t)r * n + k], b[k], s);
+  s = warp_sum(s);
+  if (lane == 0) x[r] = s;
+}
+
+// ---- AMG-PCG scalars (indices into the device scalar block)
+enum { P_RHO = 0, P_RHO_NEW, P_PQ, P_RR, P_TOL, P_BNRM, P_DONE, P_ITERS, P_COUNT = 16 };
+
+// r = b - q (q = A x0) or r = b ; rr, bb ; tolerance and the convergence test of the initial iterate
+__global__ void __launch_bounds__(kVecThreads)
+    k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q_or_null, double* __restrict__ r,
+               double* sc, double rtol, double atol, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  double rr = 0.0, bb = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+    const double bi = b[i];
+    const double ri = q_or_null ? bi - q_or_null[i] : bi;
+    r[i] = ri;
+    rr = fma(ri, ri, rr);
+    bb = fma(bi, bi, bb);
+  }
+  double mine[2], tot[2];
+  mine[0] = block_sum<kVecThreads>(rr, s_red);
+  mine[1] = block_sum<kVecThreads>(bb, s_red);
+  if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    const double bnrm = sqrt(tot[1]);
+    const double tol = fmax(atol, rtol * bnrm);
+    sc[P_RR] = tot[0];
+    sc[P_BNRM] = bnrm;
+    sc[P_TOL] = tol;
+    sc[P_ITERS] = 0.0;
+    sc[P_DONE] = (bnrm == 0.0 || sqrt(tot[0]) < tol) ? 1.0 : 0.0;
+  }
+}
+
+// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; rr = r.r ; convergence test (scipy cg: ||r|| < tol)
+__global__ void __launch_bounds__(kVecThreads)
+    k_pcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
+                 double* __restrict__ r, double* sc, double* partials, unsigned int* ticket) {
+  __shared__ double s_red[kVecThreads / 32];
+  const double pq = sc[P_PQ];
+  const double alpha = sc[P_RHO] / pq;
+  double rr = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+    x[i] = fma(alpha, p[i], x[i]);
+    const double ri = fma(-alpha, q[i], r[i]);
+    r[i] = ri;
+    rr = fma(ri, ri, rr);
+  }
+  double mine[1], tot[1];
+  mine[0] = block_sum<kVecThreads>(rr, s_red);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
+    sc[P_RR] = tot[0];
+    sc[P_ITERS] += 1.0;
+    if (!isfinite(tot[0]) || !(pq > 0.0)) sc[P_DONE] = 2.0;  // breakdown: A or the preconditioner is not SPD
+    else if (sqrt(tot[0]) < sc[P_TOL]) sc[P_DONE] = 1.0;
+  }
+}
+
+// p = z + (rho_new / rho) p   (first: p = z)
+__global__ void __launch_bounds__(kVecThreads)
+    k_pcg_direction(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* sc, int first) {
+  const double beta = first ? 0.0 : sc[P_RHO_NEW] / sc[P_RHO];
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+    p[i] = first ? z[i] : fma(beta, p[i], z[i]);
+}
+__global__ void k_pcg_roll(double* sc) { sc[P_RHO] = sc[P_RHO_NEW]; }
+
+struct Level {
+  Sell A, P, R;
+  int64_t n;
+  const double* dinv;
+  double omega;
+  double *x, *b, *t;
+};
+
+int make_levels(const tfem_amg_level_t* lv, int n_levels, Level* out) {
+  for (int l = 0; l < n_levels; ++l) {
+    int rc = check_sell(&lv[l].A);
+    if (rc != TFEM_OK) return rc;
+    out[l].A = make_sell(&lv[l].A);
+    out[l].n = lv[l].A.n_rows;
+    out[l].dinv = lv[l].dinv;
+    out[l].omega = lv[l].omega;
+    out[l].x = lv[l].x;
+    out[l].b = lv[l].b;
+    out[l].t = lv[l].t;
+    if (l + 1 < n_levels) {
+      if ((rc = check_sell(&lv[l].P)) != TFEM_OK || (rc = check_sell(&lv[l].R)) != TFEM_OK) return rc;
+      out[l].P = make_sell(&lv[l].P);
+      out[l].R = make_sell(&lv[l].R);
+      TFEM_REQUIRE(lv[l].dinv && lv[l].x && lv[l].t, "amg level: null work vector");
+      TFEM_REQUIRE(out[l].P.n == out[l].n && out[l].R.n == lv[l + 1].A.n_rows, "amg level: P / R shapes");
+      TFEM_REQUIRE(lv[l + 1].b && lv[l + 1].x, "amg level: null work vector");
+    }
+  }
+  return TFEM_OK;
+}
+
+// z = M r. Level l > 0 reads its right-hand side from L[l].b; the result of a non-coarsest level lands in L[l].t,
+// of the coarsest in L[l].x. At level 0 the input is `r`, the output `z`; dot != nullptr fuses r.z into the last
+// kernel.
+int vcycle(const Level* L, int n_levels, const double* coarse_inv, const double* r, double* z, double* partials,
+           unsigned int* ticket, double* dot_out, int64_t* launches, cudaStream_t st) {
+  int rc;
+  for (int l = 0; l < n_levels - 1; ++l) {  // downward leg
+    const Level& v = L[l];
+    const double* b = l == 0 ? r : v.b;
+    k_jacobi_first<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, v.omega, v.dinv, b, v.x);
+    if ((rc = launch_amg_spmv<M_RES, false>(v.A, v.x, v.t, b, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = launch_amg_spmv<M_AX, false>(v.R, v.t, L[l + 1].b, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st)))
+      return rc;
+    *launches += 3;
+  }
+  {
+    const Level& c = L[n_levels - 1];
+    const double* b = n_levels == 1 ? r : c.b;
+    double* x = n_levels == 1 ? z : c.x;
+    k_dense_mv<<<grid_for(c.n * 32, 256), 256, 0, st>>>((int)c.n, coarse_inv, b, x);
+    *launches += 1;
+  }
+  for (int l = n_levels - 2; l >= 0; --l) {  // upward leg
+    const Level& v = L[l];
+    const double* b = l == 0 ? r : v.b;
+    const double* xc = (l + 1 == n_levels - 1) ? L[l + 1].x : L[l + 1].t;
+    double* out = l == 0 ? z : v.t;
+    if ((rc = launch_amg_spmv<M_ADD, false>(v.P, xc, v.x, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    if (l == 0 && dot_out)
+      rc = launch_amg_spmv<M_JAC, true>(v.A, v.x, out, b, v.dinv, v.omega, partials, ticket, dot_out, st);
+    else
+      rc = launch_amg_spmv<M_JAC, false>(v.A, v.x, out, b, v.dinv, v.omega, nullptr, nullptr, nullptr, st);
+    if (rc) return rc;
+    *launches += 2;
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+int scan_in_place(int64_t* ptr, int64_t n, cudaStream_t st) {  // ptr[0] = 0, ptr[1..n] counts -> inclusive sums
+  TFEM_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int64_t), st));
+  size_t bytes = 0;
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, ptr + 1, ptr + 1, (int)n, st));
+  void* tmp = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, ptr + 1, ptr + 1, (int)n, st));
+  TFEM_CUDA(cudaFreeAsync(tmp, st));
+  return TFEM_OK;
+}
+
+int read_flag(int* dev_flag, int* host, cudaStream_t st) {
+  TFEM_CUDA(cudaMemcpyAsync(host, dev_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  return TFEM_OK;
+}
+
+}  // namespace
+}  // namespace tfem
+
+using namespace tfem;
+
+extern "C" int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol, double* vals,
+                                 int fix_zero_diag, double* dinv, uint8_t* iso, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(bptr && bcol && vals && dinv && iso && nb > 0, "amg_row_info: bad arguments");
+  TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
+  const unsigned grid = grid_for(nb * 32, 256);
+  if (d == 3) k_row_info<3><<<grid, 256, 0, st>>>(nb, bptr, bcol, vals, fix_zero_diag, dinv, iso);
+  else if (d == 2) k_row_info<2><<<grid, 256, 0, st>>>(nb, bptr, bcol, vals, fix_zero_diag, dinv, iso);
+  else k_row_info<1><<<grid, 256, 0, st>>>(nb, bptr, bcol, vals, fix_zero_diag, dinv, iso);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int64_t tfem_amg_work_doubles(int64_t n_rows) { return 4 * pad32(n_rows) + P_COUNT + kMaxPartials + 32; }
+
+extern "C" int tfem_amg_rho(const tfem_sell_t* a, const double* dinv, int iterations, double* work,
+                            double* rho_host, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = check_sell(a);
+  if (rc != TFEM_OK) return rc;
+  TFEM_REQUIRE(dinv && work && rho_host && iterations > 0, "amg_rho: bad arguments");
+  const Sell A = make_sell(a);
+  const int64_t n = A.n, np = pad32(n);
+  double *x = work, *y = work + np, *sc = work + 4 * np, *partials = sc + P_COUNT;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + kMaxPartials);
+  TFEM_CUDA(cudaMemsetAsync(sc, 0, (P_COUNT + kMaxPartials + 32) * sizeof(double), st));
+  const int vg = vec_grid(n);
+  k_pw_init<<<vg, kVecThreads, 0, st>>>(n, x);
+  for (int it = 0; it < iterations; ++it) {
+    if ((rc = launch_amg_spmv<M_AX, false>(A, x, y, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    k_pw_step<<<vg, kVecThreads, 0, st>>>(n, dinv, x, y, sc, partials, ticket);
+    if (it + 1 < iterations) k_pw_scale<<<vg, kVecThreads, 0, st>>>(n, y, x, sc);
+  }
+  TFEM_LAUNCH_CHECK();
+  double h[2];
+  TFEM_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  *rho_host = sqrt(h[0]) / sqrt(h[1]);
+  return TFEM_OK;
+}
+
+extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t* bcol, int8_t* state_work,
+                                  uint8_t* flag_work, int32_t* index_work, int32_t* agg, int64_t* n_agg_host,
+                                  int32_t* rounds_host, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(bptr && bcol && state_work && flag_work && index_work && agg && n_agg_host && nb > 0,
+               "amg_aggregate: bad arguments");
+  TFEM_REQUIRE(nb < (int64_t)INT32_MAX, "amg_aggregate: too many nodes");
+  int* counter = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&counter, sizeof(int), st));
+  TFEM_CUDA(cudaMemsetAsync(state_work, 0, nb, st));
+  const unsigned grid = grid_for(nb, 256);
+  int rounds = 0, undecided = 1;
+  while (undecided > 0) {
+    if (rounds >= 200) {  // Luby rounds finish in O(log n) with overwhelming probability
+      cudaFreeAsync(counter, st);
+      set_last_error("capacity", "amg_aggregate: independent set did not finish in 200 rounds");
+      return TFEM_ERR_CAPACITY;
+    }
+    TFEM_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    k_mis_select<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work);
+    k_mis_apply<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work, counter);
+    TFEM_LAUNCH_CHECK();
+    int rc = read_flag(counter, &undecided, st);
+    if (rc != TFEM_OK) return rc;
+    ++rounds;
+  }
+  TFEM_CUDA(cudaFreeAsync(counter, st));
+  k_mis_flags<<<grid, 256, 0, st>>>(nb, state_work, index_work);
+  TFEM_LAUNCH_CHECK();
+  int32_t last_flag = 0, last_idx = 0;
+  TFEM_CUDA(cudaMemcpyAsync(&last_flag, index_work + nb - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  size_t bytes = 0;
+  TFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, index_work, index_work, (int)nb, st));
+  void* tmp = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, index_work, index_work, (int)nb, st));
+  TFEM_CUDA(cudaFreeAsync(tmp, st));
+  TFEM_CUDA(cudaMemcpyAsync(&last_idx, index_work + nb - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  k_mis_assign<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, index_work, agg);
+  TFEM_LAUNCH_CHECK();
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  *n_agg_host = (int64_t)last_idx + last_flag;
+  if (rounds_host) *rounds_host = rounds;
+  return TFEM_OK;
+}
+
+template <bool FILL>
+static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol, const double* vals,
+                              const int32_t* agg, const double* dinv, const uint8_t* iso, double omega,
+                              int64_t* pcount, const int64_t* pptr, int32_t* pcol, double* pvals, cudaStream_t st) {
+  int* err = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&err, sizeof(int), st));
+  TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+  const unsigned grid = grid_for(nb, 4);
+  if (d == 3) k_prolongator<3, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  else k_prolongator<1, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  TFEM_LAUNCH_CHECK();
+  int h = 0;
+  int rc = read_flag(err, &h, st);
+  cudaFreeAsync(err, st);
+  if (rc != TFEM_OK) return rc;
+  if (h) {
+    set_last_error("capacity", "amg_prolongator: a node has more than 1024 neighbours");
+    return TFEM_ERR_CAPACITY;
+  }
+  return TFEM_OK;
+}
+
+extern "C" int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol,
+                                          const int32_t* agg, int64_t* pptr, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(bptr && bcol && agg && pptr && nb > 0 && d >= 1 && d <= 3, "amg_prolongator_count: bad arguments");
+  int rc = prolongator_launch<false>(d, nb, bptr, bcol, nullptr, agg, nullptr, nullptr, 0.0, pptr + 1, nullptr,
+                                     nullptr, nullptr, st);
+  if (rc != TFEM_OK) return rc;
+  return scan_in_place(pptr, nb, st);
+}
+
+extern "C" int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol,
+                                         const double* vals, const int32_t* agg, const double* dinv,
+                                         const uint8_t* iso, double omega, const int64_t* pptr, int32_t* pcol,
+                                         double* pvals, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(bptr && bcol && vals && agg && dinv && iso && pptr && pcol && pvals && nb > 0 && d >= 1 && d <= 3,
+               "amg_prolongator_fill: bad arguments");
+  return prolongator_launch<true>(d, nb, bptr, bcol, vals, agg, dinv, iso, omega, nullptr, pptr, pcol, pvals, st);
+}
+
+extern "C" int tfem_amg_transpose_structure(int64_t n_rows, int64_t n_cols, const int64_t* ptr, const int32_t* col,
+                                            int64_t nblk, int64_t* tptr, int32_t* tcol, int32_t* tsrc,
+                                            void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(ptr && col && tptr && tcol && tsrc && n_rows > 0 && n_cols > 0, "amg_transpose_structure: bad arguments");
+  TFEM_REQUIRE(nblk < (int64_t)INT32_MAX, "amg_transpose_structure: too many blocks");
+  TFEM_CUDA(cudaMemsetAsync(tptr, 0, (n_cols + 1) * sizeof(int64_t), st));
+  if (nblk == 0) return TFEM_OK;
+  k_bt_count<<<grid_for(nblk, 256), 256, 0, st>>>(nblk, col, tptr);
+  TFEM_LAUNCH_CHECK();
+  int rc = scan_in_place(tptr, n_cols, st);
+  if (rc != TFEM_OK) return rc;
+  int32_t *cursor = nullptr, *tmp = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&cursor, n_cols * sizeof(int32_t), st));
+  TFEM_CUDA(cudaMallocAsync(&tmp, 2 * nblk * sizeof(int32_t), st));
+  TFEM_CUDA(cudaMemsetAsync(cursor, 0, n_cols * sizeof(int32_t), st));
+  k_bt_fill<<<grid_for(n_rows, 128), 128, 0, st>>>(n_rows, ptr, col, tptr, cursor, tmp, tmp + nblk);
+  k_bt_sort<<<grid_for(n_cols * 32, 256), 256, 0, st>>>(n_cols, tptr, tmp, tmp + nblk, tcol, tsrc);
+  TFEM_LAUNCH_CHECK();
+  TFEM_CUDA(cudaFreeAsync(cursor, st));
+  TFEM_CUDA(cudaFreeAsync(tmp, st));
+  return TFEM_OK;
+}
+
+extern "C" int tfem_amg_transpose_values(int d, int64_t n_cols, const int64_t* ptr, const double* vals,
+                                         const int64_t* tptr, const int32_t* tcol, const int32_t* tsrc,
+                                         double* tvals, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(ptr && vals && tptr && tcol && tsrc && tvals && n_cols > 0 && d >= 1 && d <= 3,
+               "amg_transpose_values: bad arguments");
+  const unsigned grid = grid_for(n_cols * 32, 256);
+  if (d == 3) k_bt_vals<3><<<grid, 256, 0, st>>>(n_cols, ptr, vals, tptr, tcol, tsrc, tvals);
+  else if (d == 2) k_bt_vals<2><<<grid, 256, 0, st>>>(n_cols, ptr, vals, tptr, tcol, tsrc, tvals);
+  else k_bt_vals<1><<<grid, 256, 0, st>>>(n_cols, ptr, vals, tptr, tcol, tsrc, tvals);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <bool FILL>
+static int spgemm_sym_launch(int64_t nx, const int64_t* xptr, const int32_t* xcol, const int64_t* yptr,
+                             const int32_t* ycol, int64_t* ccount, const int64_t* cptr, int32_t* ccol,
+                             cudaStream_t st) {
+  int* err = nullptr;
+  TFEM_CUDA(cudaMallocAsync(&err, sizeof(int), st));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    if (attempt == 0) {
+      constexpr int HC = 1024, W = 4;
+      const size_t smem = (2 * W * HC + W) * sizeof(int);
+      const int64_t want = (nx + W - 1) / W;
+      const int64_t cap = (int64_t)num_sms() * 6;
+      k_spgemm_sym<HC, FILL><<<(unsigned)(want < cap ? want : cap), W * 32, smem, st>>>(nx, xptr, xcol, yptr, ycol,
+                                                                                        ccount, cptr, ccol, err);
+    } else {
+      constexpr int HC = 16384, W = 1;
+      const size_t smem = (2 * W * HC + W) * sizeof(int);
+      TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_sym<HC, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int64_t cap = (int64_t)num_sms();
+      k_spgemm_sym<HC, FILL><<<(unsigned)(nx < cap ? nx : cap), W * 32, smem, st>>>(nx, xptr, xcol, yptr, ycol, ccount,
+                                                                                    cptr, ccol, err);
+    }
+    TFEM_LAUNCH_CHECK();
+    int h = 0;
+    int rc = read_flag(err, &h, st);
+    if (rc != TFEM_OK) return rc;
+    if (!h) {
+      cudaFreeAsync(err, st);
+      return TFEM_OK;
+    }
+  }
+  cudaFreeAsync(err, st);
+  set_last_error("capacity", "amg_spgemm: a product row has more than 12288 distinct block columns");
+  return TFEM_ERR_CAPACITY;
+}
+
+extern "C" int tfem_amg_spgemm_count(int64_t nx, const int64_t* xptr, const int32_t* xcol, const int64_t* yptr,
+                                     const int32_t* ycol, int64_t* cptr, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(xptr && xcol && yptr && ycol && cptr && nx > 0, "amg_spgemm_count: bad arguments");
+  int rc = spgemm_sym_launch<false>(nx, xptr, xcol, yptr, ycol, cptr + 1, nullptr, nullptr, st);
+  if (rc != TFEM_OK) return rc;
+  return scan_in_place(cptr, nx, st);
+}
+
+extern "C" int tfem_amg_spgemm_fill(int64_t nx, const int64_t* xptr, const int32_t* xcol, const int64_t* yptr,
+                                    const int32_t* ycol, const int64_t* cptr, int32_t* ccol, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(xptr && xcol && yptr && ycol && cptr && ccol && nx > 0, "amg_spgemm_fill: bad arguments");
+  return spgemm_sym_launch<true>(nx, xptr, xcol, yptr, ycol, nullptr, cptr, ccol, st);
+}
+
+template <int D>
+static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xcol, const double* xvals,
+                             const int64_t* yptr, const int32_t* ycol, const double* yvals, const int64_t* cptr,
+                             const int32_t* ccol, double* cvals, int max_row, cudaStream_t st) {
+  const size_t per_warp = (size_t)max_row * (D * D * sizeof(double) + sizeof(int));
+  const size_t budget = 160 * 1024;
+  if (per_warp > 200 * 1024) {
+    set_last_error("capacity", "amg_spgemm_numeric: a product row does not fit in shared memory");
+    return TFEM_ERR_CAPACITY;
+  }
+  int W = (int)(budget / (per_warp ? per_warp : 1));
+  W = W < 1 ? 1 : (W > 8 ? 8 : W);
+  const size_t smem = W * per_warp + 16;
+  if (smem > 48 * 1024)
+    TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_num<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spgemm_num<D>, W * 32, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  const int64_t want = (nx + W - 1) / W;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  k_spgemm_num<D><<<(unsigned)(want < cap ? want : cap), W * 32, smem, st>>>(nx, xptr, xcol, xvals, yptr, ycol, yvals,
+                                                                             cptr, ccol, cvals, max_row);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, const int32_t* xcol,
+                                       const double* xvals, const int64_t* yptr, const int32_t* ycol,
+                                       const double* yvals, const int64_t* cptr, const int32_t* ccol, double* cvals,
+                                       int max_row, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(xptr && xcol && xvals && yptr && ycol && yvals && cptr && ccol && cvals && nx > 0 && max_row > 0,
+               "amg_spgemm_numeric: bad arguments");
+  if (d == 3) return spgemm_num_launch<3>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
+  if (d == 2) return spgemm_num_launch<2>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
+  if (d == 1) return spgemm_num_launch<1>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
+  set_last_error("invalid argument", "amg: 1, 2 or 3 DOFs per node");
+  return TFEM_ERR_INVALID;
+}
+
+extern "C" int tfem_amg_vcycle(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv,
+                               const double* r, double* z, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= TFEM_AMG_MAX_LEVELS && coarse_inv && r && z && r != z,
+               "amg_vcycle: bad arguments");
+  Level L[TFEM_AMG_MAX_LEVELS];
+  int rc = make_levels(levels, n_levels, L);
+  if (rc != TFEM_OK) return rc;
+  int64_t launches = 0;
+  return vcycle(L, n_levels, coarse_inv, r, z, nullptr, nullptr, nullptr, &launches, st);
+}
+
+extern "C" int tfem_amg_pcg_solve(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv,
+                                  const double* b, const double* x0, double rtol, double atol, int64_t maxiter,
+                                  double* x, double* work, double* info, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= TFEM_AMG_MAX_LEVELS && coarse_inv && b && x && work && info,
+               "amg_pcg_solve: bad arguments");
+  Level L[TFEM_AMG_MAX_LEVELS];
+  int rc = make_levels(levels, n_levels, L);
+  if (rc != TFEM_OK) return rc;
+  const Sell& A = L[0].A;
+  const int64_t n = A.n, np = pad32(n);
+  if (maxiter <= 0) maxiter = 10 * n;
+  double *r = work, *p = work + np, *q = work + 2 * np, *z = work + 3 * np, *sc = work + 4 * np;
+  double* partials = sc + P_COUNT;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + kMaxPartials);
+  TFEM_CUDA(cudaMemsetAsync(sc, 0, (P_COUNT + kMaxPartials + 32) * sizeof(double), st));
+  const int vg = vec_grid(n);
+  int64_t launches = 0, spmvs = 0;
+
+  if (x0) TFEM_CUDA(cudaMemcpyAsync(x, x0, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  else TFEM_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+  const double* q0 = nullptr;
+  if (x0) {
+    if ((rc = launch_amg_spmv<M_AX, false>(A, x, q, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    q0 = q;
+    ++spmvs;
+    ++launches;
+  }
+  k_pcg_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, r, sc, rtol, atol, partials, ticket);
+  TFEM_LAUNCH_CHECK();
+  ++launches;
+  double h[P_COUNT];
+  TFEM_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  int64_t it = 0;
+  while (h[P_DONE] == 0.0 && it < maxiter) {
+    if ((rc = vcycle(L, n_levels, coarse_inv, r, z, partials, ticket, sc + P_RHO_NEW, &launches, st))) return rc;
+    k_pcg_direction<<<vg, kVecThreads, 0, st>>>(n, z, p, sc, it == 0 ? 1 : 0);
+    k_pcg_roll<<<1, 1, 0, st>>>(sc);
+    if ((rc = launch_amg_spmv<M_AX, true>(A, p, q, nullptr, nullptr, 0.0, partials, ticket, sc + P_PQ, st))) return rc;
+    k_pcg_update<<<vg, kVecThreads, 0, st>>>(n, p, q, x, r, sc, partials, ticket);
+    TFEM_LAUNCH_CHECK();
+    launches += 4;
+    spmvs += 3;
+    ++it;
+    TFEM_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TFEM_CUDA(cudaStreamSynchronize(st));
+  }
+  info[0] = h[P_ITERS];
+  info[1] = sqrt(h[P_RR]);
+  info[2] = h[P_BNRM];
+  info[3] = h[P_DONE] == 1.0 ? 1.0 : 0.0;
+  info[4] = (double)spmvs;
+  info[5] = (double)launches;
+  info[6] = h[P_DONE];
+  info[7] = 0.0;
+  if (h[P_DONE] == 2.0) {
+    set_last_error("breakdown", "non-finite residual or non-positive curvature (matrix or preconditioner not SPD?)");
+    return TFEM_ERR_BREAKDOWN;
+  }
+  if (h[P_DONE] != 1.0) {
+    set_last_error("not converged", "iteration limit reached");
+    return TFEM_ERR_NOT_CONVERGED;
+  }
+  return TFEM_OK;
+}

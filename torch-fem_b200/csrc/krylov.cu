@@ -100,7 +100,7 @@ __global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __rest
 }
 
 // one warp per slice; output-coalesced transposition CSR -> SELL (cols and/or vals)
-__global__ void k_sell_fill(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
+__global__ void k_sell_fill(int64_t n, int64_t n_cols, int64_t n_slices, const int64_t* __restrict__ indptr,
                             const int32_t* __restrict__ cols, const double* __restrict__ vals,
                             const int64_t* __restrict__ slice_ptr, int32_t* __restrict__ s_cols,
                             double* __restrict__ s_vals) {
@@ -121,6 +121,7 @@ __global__ void k_sell_fill(int64_t n, int64_t n_slices, const int64_t* __restri
     if (s_cols) {
       int64_t own = t * 32 + rl;
       if (own >= n) own = n - 1;
+      if (own >= n_cols) own = n_cols - 1;  // rectangular operators (AMG prolongation / restriction)
       s_cols[base + o] = real ? cols[beg + k] : (int32_t)own;
     }
     if (s_vals) s_vals[base + o] = real ? vals[beg + k] : 0.0;
@@ -719,16 +720,23 @@ extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_
   return TFEM_OK;
 }
 
+extern "C" int tfem_sell_fill_rect(int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* cols,
+                                   const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
+                                   double* sell_vals, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0 && n_cols > 0, "sell_fill: bad arguments");
+  TFEM_REQUIRE((!sell_cols || cols) && (!sell_vals || vals), "sell_fill: output without input");
+  const int64_t ns = (n_rows + 31) / 32;
+  k_sell_fill<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, n_cols, ns, indptr, cols, vals, slice_ptr, sell_cols,
+                                                      sell_vals);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
 extern "C" int tfem_sell_fill(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
                               const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
                               double* sell_vals, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0, "sell_fill: bad arguments");
-  TFEM_REQUIRE((!sell_cols || cols) && (!sell_vals || vals), "sell_fill: output without input");
-  const int64_t ns = (n_rows + 31) / 32;
-  k_sell_fill<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, ns, indptr, cols, vals, slice_ptr, sell_cols, sell_vals);
-  TFEM_LAUNCH_CHECK();
-  return TFEM_OK;
+  return tfem_sell_fill_rect(n_rows, n_rows, indptr, cols, vals, slice_ptr, sell_cols, sell_vals, stream_);
 }
 
 extern "C" int tfem_bsell_slice_ptr(int64_t n_rows, int dpn, const int64_t* slice_ptr,

@@ -8,7 +8,8 @@ Public names, signatures, error types and messages follow the reference:
 
 What is different underneath: the matrix is a device CSR (`csr.CSRMatrix`, or any torch sparse tensor,
 which is converted), iterative methods run the fused Jacobi-PCG / MINRES kernels of libtfem_b200.so
-(`csr.krylov_solve`) instead of CuPy, and nothing ever leaves the GPU. `method="spsolve"` (the policy
+(`csr.krylov_solve`) instead of CuPy, `method="amgx"` runs this library's own aggregation-AMG-preconditioned CG
+(`amg.AMGPreconditioner`, kernels K11-K16) instead of the AmgX library, and nothing ever leaves the GPU. `method="spsolve"` (the policy
 default below 10,000 DOFs, sparse.py:78-81) is a dense LU of the small system on the GPU
 (`torch.linalg.solve`); a sparse direct factorisation is out of scope. There is no CPU path.
 """
@@ -21,14 +22,16 @@ from torch import Tensor
 from torch.autograd import Function
 
 from . import csr as _csr
+from .amg import AMGPreconditioner
 from .csr import CSRMatrix, ElementOperator, JacobiPreconditioner
 
-available_backends = ["tfem_b200"]
+# "amgx" names the reference's GPU AMG method (sparse.py:422-442); here it is served by the in-house AMG kernels.
+available_backends = ["tfem_b200", "amgx"]
 
 METHODS = ["spsolve", "minres", "cg", "pardiso", "amgx"]
 DIRECT_LIMIT = 10000  # reference policy: below this many DOFs solve directly (sparse.py:78)
 
-ERR_AMGX_MISSING = "AmgX is not available in torch-fem_b200 (AMG preconditioning is out of scope of this path)."
+ERR_AMG_OPERATOR = "method='amgx' needs an assembled matrix; the matrix-free element operator has no entries to coarsen."
 ERR_NO_CPU = ("torch-fem_b200 has no CPU path: pass CUDA tensors (e.g. torch.set_default_device('cuda')). "
               "The CPU oracle under oracle/ is test infrastructure only.")
 
@@ -44,7 +47,7 @@ def resolve_method(n_dofs: int, device: str, method: str | None) -> str:
 def describe_method(n_dofs: int, device: str, method: str | None) -> str:
     """`<method> | <kind> | <library> | <device>` like reference sparse.py:87-100."""
     resolved = resolve_method(n_dofs, device, method)
-    kind = "iterative | jacobi" if resolved in ("minres", "cg") else "direct"
+    kind = {"minres": "iterative | jacobi", "cg": "iterative | jacobi", "amgx": "iterative | amg"}.get(resolved, "direct")
     library = "torch.linalg (dense LU)" if resolved == "spsolve" else "tfem_b200"
     return f"{resolved} | {kind} | {library} | {device}"
 
@@ -96,7 +99,16 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
     if method == "pardiso":
         raise RuntimeError("Pardiso backend is not available on GPU.")
     if method == "amgx":
-        raise RuntimeError(ERR_AMGX_MISSING)
+        # reference sparse.py:422-442: hierarchy built on the first solve, coefficients refreshed when the solver
+        # object comes back in as M
+        if isinstance(Ac, ElementOperator):
+            raise RuntimeError(ERR_AMG_OPERATOR)
+        if isinstance(M, AMGPreconditioner) and M.n == n:
+            M.resetup(Ac)
+        else:
+            M = AMGPreconditioner(Ac)
+        x, _ = M.solve(rhs, x0=None if x0 is None else x0.detach(), rtol=stol)
+        return x.to(device=out_device, dtype=b.dtype), M
     if isinstance(Ac, ElementOperator) and method == "spsolve":
         method = "cg"  # the matrix-free operator (kernel K8) has no entries to factorise
     if method == "spsolve":
@@ -106,6 +118,8 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
         x = torch.linalg.solve(Ac.to_dense(), rhs)
         M_out = None
     else:
+        if isinstance(M, AMGPreconditioner):
+            M = None  # a hierarchy from an earlier method="amgx" call does not apply to the Jacobi kernels
         if M is not None and not isinstance(M, JacobiPreconditioner):
             raise TypeError("M must be a JacobiPreconditioner returned by a previous sparse_solve")
         if x0 is not None:
