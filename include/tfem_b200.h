@@ -350,12 +350,6 @@ int tfem_dcg_solve(void* comm, const tfem_sell_t* A_local, int64_t row_lo, int64
 int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, double* vals_dev,
                       int fix_zero_diag, double* dinv_dev, uint8_t* iso_dev, void* stream);
 
-/* Spectral radius of D^-1 A by `iterations` steps of the power method from a fixed start vector (synchronises).
- * work_dev: double [tfem_amg_work_doubles(n)]. */
-int64_t tfem_amg_work_doubles(int64_t n_rows);
-int tfem_amg_rho(const tfem_sell_t* A, const double* dinv_dev, int iterations, double* work_dev, double* rho_host,
-                 void* stream);
-
 /* Aggregation: maximal independent set of the node graph in Luby rounds with fixed pseudo-random keys, then every
  * node joins the adjacent root with the largest key; aggregates are numbered in root order. agg_dev: int32 [nb] out.
  * state_work int8 [nb], flag_work uint8 [nb], index_work int32 [nb]: scratch. Synchronises (one flag per round). */
@@ -382,7 +376,8 @@ int tfem_amg_transpose_values(int d, int64_t n_cols, const int64_t* ptr_dev, con
                               double* tvals_dev, void* stream);
 
 /* Block SpGEMM C = X Y. count: cptr int64 [nx+1] out; fill: ccol int32 sorted per row; numeric: cvals with every
- * entry summed in the order of X's row (fixed order). max_row = longest row of C (blocks).
+ * entry summed in the order of X's row (fixed order). max_row = longest row of C (blocks); threads_per_row = 32 (a warp
+ * per row of C) or 256 (a CTA per row: few, long rows).
  * TFEM_ERR_CAPACITY if a row of C has more than 12288 distinct block columns. */
 int tfem_amg_spgemm_count(int64_t nx, const int64_t* xptr_dev, const int32_t* xcol_dev, const int64_t* yptr_dev,
                           const int32_t* ycol_dev, int64_t* cptr_dev, void* stream);
@@ -391,21 +386,45 @@ int tfem_amg_spgemm_fill(int64_t nx, const int64_t* xptr_dev, const int32_t* xco
 int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr_dev, const int32_t* xcol_dev,
                             const double* xvals_dev, const int64_t* yptr_dev, const int32_t* ycol_dev,
                             const double* yvals_dev, const int64_t* cptr_dev, const int32_t* ccol_dev,
-                            double* cvals_dev, int max_row, void* stream);
+                            double* cvals_dev, int max_row, int threads_per_row, void* stream);
+
+/* A block-CSR operator as the coarse-level SpMV takes it (nb_rows == 0: not given). */
+typedef struct tfem_bcsr {
+  int64_t nb_rows;
+  int64_t n_blocks;
+  const int64_t* bptr;
+  const int32_t* bcol;
+  const double* vals;
+  int32_t d;
+} tfem_bcsr_t;
+
+/* An operator of the hierarchy: SELL-32 (one row per lane; right for many short rows — the fine levels) or, if
+ * bcsr.nb_rows > 0, block CSR with 8 / 32 / 256 threads per block row (few, long rows — the coarse levels and their
+ * restrictions). The finest-level operator must be SELL-32. */
+typedef struct tfem_amg_operator {
+  tfem_sell_t sell;
+  tfem_bcsr_t bcsr;
+} tfem_amg_operator_t;
 
 /* One level of the hierarchy as the cycle takes it. P / R are unused on the coarsest level. x, b, t: work vectors of
  * the level's length (b unused on level 0). */
 #define TFEM_AMG_MAX_LEVELS 16
 typedef struct tfem_amg_level {
-  tfem_sell_t A;        /* level operator (SELL-32) */
-  tfem_sell_t P;        /* prolongation from the next coarser level: n_rows = this level */
-  tfem_sell_t R;        /* restriction to the next coarser level:   n_rows = next level */
-  const double* dinv;   /* 1 / diag(A) */
-  double omega;         /* damped-Jacobi weight 4 / (3 rho(D^-1 A)) */
+  tfem_amg_operator_t A; /* level operator */
+  tfem_amg_operator_t P; /* prolongation from the next coarser level: rows = this level */
+  tfem_amg_operator_t R; /* restriction to the next coarser level:   rows = next level */
+  const double* dinv;    /* 1 / diag(A) */
+  double omega;          /* damped-Jacobi weight 4 / (3 rho(D^-1 A)) */
   double* x;
   double* b;
   double* t;
 } tfem_amg_level_t;
+
+/* Spectral radius of D^-1 A by `iterations` steps of the power method from a fixed start vector (synchronises).
+ * work_dev: double [tfem_amg_work_doubles(n)]. */
+int64_t tfem_amg_work_doubles(int64_t n_rows);
+int tfem_amg_rho(const tfem_amg_operator_t* A, const double* dinv_dev, int iterations, double* work_dev,
+                 double* rho_host, void* stream);
 
 /* z = M r: V(1,1) cycle with damped Jacobi, dense inverse (coarse_inv_dev, row-major [n_c, n_c]) on the coarsest
  * level. Symmetric positive definite for SPD A, hence a valid CG preconditioner. r and z must not alias. */

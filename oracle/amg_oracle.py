@@ -111,8 +111,8 @@ def row_info(A: sp.csr_matrix):
     diag = A.diagonal()
     zero = diag == 0.0
     if zero.any():
-        A = (A + sp.diags(zero.astype(np.float64))).tocsr()
-        diag = A.diagonal()
+        diag[zero] = 1.0
+        A.setdiag(diag)            # the diagonal is stored (explicit zeros), so the structure does not change
     off = A - sp.diags(diag)
     iso = np.asarray(abs(off).sum(axis=1)).ravel() == 0.0
     return A, diag, iso

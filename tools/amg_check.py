@@ -53,12 +53,21 @@ def main():
         for rep in range(2):
             amg, t_setup = timed(lambda: AMGPreconditioner(A))
             (x, st), t_solve = timed(lambda: amg.solve(b, rtol=a.rtol))
+        os.environ["TFEM_AMG_TIMING"] = "1"
+        amg_t = AMGPreconditioner(A)
+        out["setup_phases_ms"] = {k: round(v, 2) for k, v in amg_t._timing.items()}
+        amg_t._setup(A, symbolic=False)
+        out["resetup_phases_ms"] = {k: round(v, 2) for k, v in amg_t._timing.items()}
+        del amg_t
+        os.environ.pop("TFEM_AMG_TIMING")
         _, t_resetup = timed(lambda: amg._setup(A, symbolic=False))
         (x, st), t_solve2 = timed(lambda: amg.solve(b, rtol=a.rtol))
         res = float((A.matvec(x) - b).norm() / b.norm())
         out.update({"amg_setup_ms": t_setup, "amg_resetup_ms": t_resetup, "amg_solve_ms": t_solve2,
                     "amg_iterations": st["iterations"], "amg_ms_per_iteration": t_solve2 / max(st["iterations"], 1),
-                    "true_rel_residual": res, "levels": [(lv.n, lv.op.nblk * lv.d ** 2) for lv in amg.levels],
+                    "true_rel_residual": res, "levels": [(lv.n, lv.op.nblk * lv.d ** 2, "bcsr" if lv.op.use_bcsr else "sell") for lv in amg.levels],
+                    "PR": [(lv.P.nblk, "bcsr" if lv.P.use_bcsr else "sell", "bcsr" if lv.R.use_bcsr else "sell")
+                           for lv in amg.levels[:-1]],
                     "operator_complexity": amg.operator_complexity,
                     "mis_rounds": [getattr(lv, "mis_rounds", None) for lv in amg.levels[:-1]],
                     "rho": [getattr(lv, "rho", None) for lv in amg.levels[:-1]],

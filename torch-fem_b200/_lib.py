@@ -45,10 +45,21 @@ class EbeStruct(ctypes.Structure):
 _EBE_P = ctypes.POINTER(EbeStruct)
 
 
+class BcsrStruct(ctypes.Structure):
+    """`tfem_bcsr_t` of include/tfem_b200.h."""
+    _fields_ = [("nb_rows", c_int64), ("n_blocks", c_int64), ("bptr", c_void_p), ("bcol", c_void_p),
+                ("vals", c_void_p), ("d", ctypes.c_int32)]
+
+
+class AmgOperatorStruct(ctypes.Structure):
+    """`tfem_amg_operator_t` of include/tfem_b200.h."""
+    _fields_ = [("sell", SellStruct), ("bcsr", BcsrStruct)]
+
+
 class AmgLevelStruct(ctypes.Structure):
     """`tfem_amg_level_t` of include/tfem_b200.h."""
-    _fields_ = [("A", SellStruct), ("P", SellStruct), ("R", SellStruct), ("dinv", c_void_p), ("omega", c_double),
-                ("x", c_void_p), ("b", c_void_p), ("t", c_void_p)]
+    _fields_ = [("A", AmgOperatorStruct), ("P", AmgOperatorStruct), ("R", AmgOperatorStruct), ("dinv", c_void_p),
+                ("omega", c_double), ("x", c_void_p), ("b", c_void_p), ("t", c_void_p)]
 
 
 _AMG_P = ctypes.POINTER(AmgLevelStruct)
@@ -96,7 +107,8 @@ _SIGNATURES = {
     "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_row_info": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_work_doubles": (c_int64, [c_int64]),
-    "tfem_amg_rho": (c_int, [_SELL_P, c_void_p, c_int, c_void_p, ctypes.POINTER(c_double), c_void_p]),
+    "tfem_amg_rho": (c_int, [ctypes.POINTER(AmgOperatorStruct), c_void_p, c_int, c_void_p, ctypes.POINTER(c_double),
+                             c_void_p]),
     "tfem_amg_aggregate": (c_int, [c_int64] + [c_void_p] * 6 + [ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_int32),
                                                               c_void_p]),
     "tfem_amg_prolongator_count": (c_int, [c_int, c_int64] + [c_void_p] * 5),
@@ -105,7 +117,7 @@ _SIGNATURES = {
     "tfem_amg_transpose_values": (c_int, [c_int, c_int64] + [c_void_p] * 7),
     "tfem_amg_spgemm_count": (c_int, [c_int64] + [c_void_p] * 6),
     "tfem_amg_spgemm_fill": (c_int, [c_int64] + [c_void_p] * 7),
-    "tfem_amg_spgemm_numeric": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_int, c_void_p]),
+    "tfem_amg_spgemm_numeric": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_int, c_int, c_void_p]),
     "tfem_amg_vcycle": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_pcg_solve": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -16,6 +16,8 @@ oracle/amg_oracle.py (tests only).
 from __future__ import annotations
 
 import ctypes
+import os
+import time
 
 import numpy as np
 import torch
@@ -29,6 +31,8 @@ RHO_SAFETY = 1.1
 MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 DENSE_LIMIT = 12000  # largest coarsest level a dense inverse is accepted for
+BCSR_MAX_ROWS = 20000   # operators with fewer block rows than this ...
+BCSR_MIN_AVG = 96       # ... or more blocks per row than this are streamed as block CSR instead of SELL-32
 
 
 def _empty(n, dtype, device):
@@ -51,6 +55,34 @@ class BlockOperator:
     @property
     def nblk(self) -> int:
         return int(self.bcol.shape[0])
+
+    @property
+    def use_bcsr(self) -> bool:
+        """Layout the cycle streams this operator in: SELL-32 (a row per lane) suits many short rows, the block-CSR
+        kernel (8 / 32 / 256 threads per block row) few long ones — coarse levels and their restrictions."""
+        if self._sell is not None and self._sell_struct is None:
+            return False                                   # level 0: the assembled matrix's own SELL copy
+        return self.nbr < BCSR_MAX_ROWS or self.nblk > BCSR_MIN_AVG * self.nbr
+
+    def operator_struct(self):
+        """`tfem_amg_operator_t` (plus the objects that keep its pointers alive)."""
+        o = L.AmgOperatorStruct()
+        if self.use_bcsr:
+            o.bcsr.nb_rows, o.bcsr.n_blocks, o.bcsr.d = self.nbr, self.nblk, self.d
+            o.bcsr.bptr, o.bcsr.bcol, o.bcsr.vals = L.ptr(self.bptr), L.ptr(self.bcol), L.ptr(self.vals)
+            return o, (self.bptr, self.bcol, self.vals)
+        S = self.sell()
+        o.sell = S.struct
+        return o, S
+
+    def prepare(self) -> None:
+        """Build (first call) or refresh (later calls) the layout the cycle uses."""
+        if self.use_bcsr:
+            return
+        if self._sell is None:
+            self.sell()
+        else:
+            self.refresh_sell()
 
     @property
     def indptr(self) -> Tensor:
@@ -130,9 +162,10 @@ def spgemm(d: int, X: BlockOperator, Y: BlockOperator, structure=None, out_vals:
     cptr, ccol, max_row = structure
     nv = d * d * ccol.shape[0]
     cvals = out_vals if out_vals is not None else _empty(nv, torch.float64, dev)[:nv]
+    tpr = 256 if Y.nblk * d >= 192 * Y.nbr else 32      # tasks per step of X's row = blocks of Y's row x d
     L.check(L.lib.tfem_amg_spgemm_numeric(d, X.nbr, L.ptr(X.bptr), L.ptr(X.bcol), L.ptr(X.vals), L.ptr(Y.bptr),
                                           L.ptr(Y.bcol), L.ptr(Y.vals), L.ptr(cptr), L.ptr(ccol), L.ptr(cvals),
-                                          max_row, st))
+                                          max_row, tpr, st))
     return BlockOperator(d, X.nbr, Y.nbc, cptr, ccol, cvals), structure
 
 
@@ -157,6 +190,7 @@ class AMGPreconditioner:
         self.device = A.device
         self.levels: list[_Level] = []
         self._work = None
+        self._timing = None
         self._setup(A, symbolic=True)
 
     # ------------------------------------------------------------------------------------------ setup
@@ -179,8 +213,21 @@ class AMGPreconditioner:
         lv.R = None
         return True
 
+    def _tick(self, name: str) -> None:
+        """Per-phase wall times of the setup (TFEM_AMG_TIMING=1; synchronises, for tools/amg_check.py only)."""
+        if self._timing is None:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self._timing[name] = self._timing.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
     def _setup(self, A: CSRMatrix, symbolic: bool) -> None:
         dev, st = self.device, L.stream()
+        self._timing = {} if os.environ.get("TFEM_AMG_TIMING") else None
+        if self._timing is not None:
+            torch.cuda.synchronize()
+            self._t_last = time.perf_counter()
         self._pattern_key = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n)
         self._values_key = (A.values_.data_ptr(), A.values_._version)
         self._A = A   # keeps the level-0 buffers alive
@@ -203,7 +250,8 @@ class AMGPreconditioner:
             L.check(L.lib.tfem_amg_row_info(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals), 1 if li > 0 else 0,
                                             L.ptr(lv.dinv), L.ptr(lv.iso), st))
             if li > 0:
-                op.sell() if symbolic else op.refresh_sell()   # after the zero-diagonal repair
+                op.prepare()                                   # after the zero-diagonal repair
+            self._tick("row_info+layout")
             if symbolic:
                 if lv.n <= self.max_coarse or len(self.levels) >= self.max_levels:
                     break
@@ -211,12 +259,16 @@ class AMGPreconditioner:
                 break
             work = _empty(int(L.lib.tfem_amg_work_doubles(lv.n)), torch.float64, dev)
             rho = ctypes.c_double(0.0)
-            L.check(L.lib.tfem_amg_rho(op.sell().ref, L.ptr(lv.dinv), self.power_its, L.ptr(work), ctypes.byref(rho), st))
-            del work
+            ostruct, okeep = op.operator_struct()
+            L.check(L.lib.tfem_amg_rho(ctypes.byref(ostruct), L.ptr(lv.dinv), self.power_its, L.ptr(work),
+                                       ctypes.byref(rho), st))
+            del work, okeep
+            self._tick("rho")
             lv.rho = rho.value * self.rho_safety
             lv.omega = 4.0 / (3.0 * lv.rho)
             if symbolic and not self._aggregate(lv):
                 break                                          # coarsening stalled: this level is the coarsest
+            self._tick("aggregate+P pattern")
             P = lv.P
             L.check(L.lib.tfem_amg_prolongator_fill(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals), L.ptr(lv.agg),
                                                     L.ptr(lv.dinv), L.ptr(lv.iso), lv.omega, L.ptr(P.bptr), L.ptr(P.bcol),
@@ -231,15 +283,19 @@ class AMGPreconditioner:
             R = lv.R
             L.check(L.lib.tfem_amg_transpose_values(d, lv.n_agg, L.ptr(P.bptr), L.ptr(P.vals), L.ptr(R.bptr), L.ptr(R.bcol),
                                                     L.ptr(lv.tsrc), L.ptr(R.vals), st))
+            self._tick("P values + R")
+            P.prepare(), R.prepare()
+            self._tick("P/R layout")
             if symbolic:
-                P.sell(), R.sell()
                 AP, lv.ap_structure = spgemm(d, op, P)
+                self._tick("A*P")
                 op, lv.ac_structure = spgemm(d, R, AP)
             else:
-                P.refresh_sell(), R.refresh_sell()
                 AP, _ = spgemm(d, op, P, lv.ap_structure)
+                self._tick("A*P")
                 spgemm(d, R, AP, lv.ac_structure, out_vals=self.levels[li + 1].op.vals)
             del AP
+            self._tick("R*(AP)")
             li += 1
         # coarsest level: dense inverse (tiny; a library call like method="spsolve")
         c = self.levels[-1]
@@ -248,19 +304,19 @@ class AMGPreconditioner:
                                f"and is limited to {DENSE_LIMIT}")
         c.inv = torch.linalg.inv(_dense(c.op)).contiguous()
         self._build_structs()
+        self._tick("coarse inverse")
 
     def _build_structs(self) -> None:
         n_levels = len(self.levels)
         arr = (L.AmgLevelStruct * n_levels)()
         keep = []
         for i, lv in enumerate(self.levels):
-            S = lv.op.sell()
-            keep.append(S)
-            arr[i].A = S.struct
+            arr[i].A, k = lv.op.operator_struct()
+            keep.append(k)
             if i + 1 < n_levels:
-                SP, SR = lv.P.sell(), lv.R.sell()
-                keep += [SP, SR]
-                arr[i].P, arr[i].R = SP.struct, SR.struct
+                arr[i].P, kp = lv.P.operator_struct()
+                arr[i].R, kr = lv.R.operator_struct()
+                keep += [kp, kr]
                 arr[i].omega = lv.omega
             arr[i].dinv = L.ptr(lv.dinv)
             arr[i].x, arr[i].b, arr[i].t = L.ptr(lv.x), L.ptr(lv.b), L.ptr(lv.t)

@@ -182,9 +182,10 @@ __global__ void __launch_bounds__(128)
                   int64_t* __restrict__ pcount, const int64_t* __restrict__ pptr, int32_t* __restrict__ pcol,
                   double* __restrict__ pvals, int* err) {
   __shared__ int s_key[4][kRowCap];
-  __shared__ int s_ukey[4][kRowCap];
+  __shared__ int s_ukey[4][FILL ? 128 : 1];
   __shared__ short s_rank[4][kRowCap];
   __shared__ unsigned char s_first[4][kRowCap];
+  __shared__ int s_start[4][FILL ? 128 : 1];   // FILL: m <= 127 distinct aggregates per row (checked below)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t I = blockIdx.x * 4ll + w;
   if (I >= nb) return;
@@ -214,6 +215,10 @@ __global__ void __launch_bounds__(128)
     if (lane == 0) pcount[I] = m;
     return;
   }
+  if (m > 127) {
+    if (lane == 0) *err = 2;
+    return;
+  }
   __syncwarp();
   for (int e = lane; e < L; e += 32) {
     const int k = key[e];
@@ -225,17 +230,37 @@ __global__ void __launch_bounds__(128)
   __syncwarp();
   const int64_t p0 = pptr[I];
   for (int r = lane; r < m; r += 32) pcol[p0 + r] = s_ukey[w][r];
+  // entries grouped by aggregate, adjacency order kept inside a group: lane r collects the entries of rank r
+  // (s_key is free now: it becomes the permutation, s_first/s_rank stay), group r = perm[start[r] .. start[r+1])
+  int* perm = s_key[w];
+  int* start = s_start[w];
+  for (int r = lane; r < m; r += 32) {
+    int cnt = 0;
+    for (int e = 0; e < L; ++e) cnt += s_rank[w][e] == r ? 1 : 0;
+    start[r + 1] = cnt;
+  }
+  if (lane == 0) start[0] = 0;
+  __syncwarp();
+  if (lane == 0)
+    for (int r = 0; r < m; ++r) start[r + 1] += start[r];
+  __syncwarp();
+  for (int r = lane; r < m; r += 32) {
+    int at = start[r];
+    for (int e = 0; e < L; ++e)
+      if (s_rank[w][e] == r) perm[at++] = e;
+  }
+  __syncwarp();
   const int mine = agg[I];
   const double* arow = vals + D * D * b0;
   double* prow = pvals + D * D * p0;
   for (int o = lane; o < m * D * D; o += 32) {
     const int r = o / (D * D), a = (o / D) % D, c = o % D;
     double sum = 0.0;
-    for (int e = 0; e < L; ++e)
-      if (s_rank[w][e] == r) {
-        const int64_t j = bcol[b0 + e];
-        if (!iso[j * D + c]) sum += arow[((int64_t)a * L + e) * D + c];
-      }
+    for (int q = start[r]; q < start[r + 1]; ++q) {
+      const int e = perm[q];
+      const int64_t j = bcol[b0 + e];
+      if (!iso[j * D + c]) sum += arow[((int64_t)a * L + e) * D + c];
+    }
     double v = -omega * dinv[I * D + a] * sum;
     if (s_ukey[w][r] == mine && a == c && !iso[I * D + a]) v += 1.0;
     prow[((int64_t)a * m + r) * D + c] = v;
@@ -368,33 +393,41 @@ __global__ void k_spgemm_sym(int64_t nx, const int64_t* __restrict__ xptr, const
   }
 }
 
-// numeric: one warp per row of C; accumulators for the row live in shared memory. X's row is walked sequentially,
-// the lanes spread over (entry of Y's row, row DOF): every accumulator receives its contributions in the order of
-// X's row, one per step — a fixed summation order.
-template <int D>
-__global__ void k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
-                             const double* __restrict__ xvals, const int64_t* __restrict__ yptr,
-                             const int32_t* __restrict__ ycol, const double* __restrict__ yvals,
-                             const int64_t* __restrict__ cptr, const int32_t* __restrict__ ccol,
-                             double* __restrict__ cvals, int MC) {
+// numeric: one group of G threads (a warp, or the whole CTA for long rows) per row of C; accumulators for the row
+// live in shared memory. X's row is walked sequentially, the threads spread over (entry of Y's row, row DOF): every
+// accumulator receives its contributions in the order of X's row, one per step — a fixed summation order.
+template <int G>
+__device__ __forceinline__ void group_sync() {
+  if constexpr (G == 32) __syncwarp();
+  else __syncthreads();
+}
+
+template <int D, int G>
+__global__ void __launch_bounds__(256)
+    k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
+                 const double* __restrict__ xvals, const int64_t* __restrict__ yptr,
+                 const int32_t* __restrict__ ycol, const double* __restrict__ yvals,
+                 const int64_t* __restrict__ cptr, const int32_t* __restrict__ ccol,
+                 double* __restrict__ cvals, int MC) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   constexpr int DD = D * D;
-  const int W = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = blockDim.x / G, w = threadIdx.x / G, lane = threadIdx.x % G;
   double* acc = reinterpret_cast<double*>(s_raw) + (size_t)w * MC * DD;
   int* cc = reinterpret_cast<int*>(reinterpret_cast<double*>(s_raw) + (size_t)W * MC * DD) + (size_t)w * MC;
+  // G == 256: one row per CTA, the loop bound is uniform over the CTA (barriers inside)
   for (int64_t i = blockIdx.x * (int64_t)W + w; i < nx; i += (int64_t)gridDim.x * W) {
     const int64_t c0 = cptr[i];
     const int m = (int)(cptr[i + 1] - c0);
-    for (int e = lane; e < m; e += 32) cc[e] = ccol[c0 + e];
-    for (int e = lane; e < m * DD; e += 32) acc[e] = 0.0;
-    __syncwarp();
+    for (int e = lane; e < m; e += G) cc[e] = ccol[c0 + e];
+    for (int e = lane; e < m * DD; e += G) acc[e] = 0.0;
+    group_sync<G>();
     const int64_t x0 = xptr[i];
     const int LX = (int)(xptr[i + 1] - x0);
     for (int kx = 0; kx < LX; ++kx) {
       const int64_t j = xcol[x0 + kx];
       const int64_t y0 = yptr[j];
       const int LY = (int)(yptr[j + 1] - y0);
-      for (int o = lane; o < LY * D; o += 32) {
+      for (int o = lane; o < LY * D; o += G) {
         const int t = o / D, a = o - t * D;
         const int key = ycol[y0 + t];
         int lo = 0, hi = m - 1;
@@ -407,19 +440,19 @@ __global__ void k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const
         for (int b = 0; b < D; ++b) xa[b] = xvals[DD * x0 + ((int64_t)a * LX + kx) * D + b];
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          double s = 0.0;
+          double sum = 0.0;
 #pragma unroll
-          for (int b = 0; b < D; ++b) s = fma(xa[b], yvals[DD * y0 + ((int64_t)b * LY + t) * D + c], s);
-          acc[lo * DD + a * D + c] += s;
+          for (int b = 0; b < D; ++b) sum = fma(xa[b], yvals[DD * y0 + ((int64_t)b * LY + t) * D + c], sum);
+          acc[lo * DD + a * D + c] += sum;
         }
       }
-      __syncwarp();
+      group_sync<G>();
     }
-    for (int o = lane; o < m * DD; o += 32) {
+    for (int o = lane; o < m * DD; o += G) {
       const int pos = o / DD, a = (o / D) % D, c = o % D;
       cvals[DD * c0 + ((int64_t)a * m + pos) * D + c] = acc[pos * DD + a * D + c];
     }
-    __syncwarp();
+    group_sync<G>();
   }
 }
 
@@ -482,6 +515,120 @@ int launch_amg_spmv(const Sell& A, const double* x, double* y, const double* b, 
   if (A.dpn == 3) return launch_amg_spmv_t<3, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
   if (A.dpn == 2) return launch_amg_spmv_t<2, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
   return launch_amg_spmv_t<0, MODE, DOT>(A, x, y, b, dinv, omega, partials, ticket, out_scalar, st);
+}
+
+// The same operations on a block-CSR operator, TPR threads per block row (d scalar rows at once): for the coarse
+// levels, whose rows are few and long (hundreds to thousands of blocks) — one row per lane (SELL) would leave the
+// GPU idle there. Lanes stride over the blocks of the row, partial sums are combined in a fixed tree.
+struct Bcsr {
+  int64_t nbr = 0, nblk = 0;
+  const int64_t* bptr = nullptr;
+  const int32_t* bcol = nullptr;
+  const double* vals = nullptr;
+  int d = 0;
+};
+
+template <int D, int MODE, int TPR>
+__global__ void __launch_bounds__(256)
+    k_bcsr_spmv(Bcsr A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
+                const double* __restrict__ dinv, double omega) {
+  constexpr int RPC = 256 / TPR;
+  __shared__ double s_part[D][8];
+  const int g = threadIdx.x / TPR, l = threadIdx.x % TPR;
+  // the loop bound is uniform over the CTA (shuffles / barriers inside); groups past the end idle with m = 0
+  for (int64_t base = blockIdx.x * (int64_t)RPC; base < A.nbr; base += (int64_t)gridDim.x * RPC) {
+    const int64_t I = base + g;
+    const bool active = I < A.nbr;
+    const int64_t b0 = active ? A.bptr[I] : 0;
+    const int m = active ? (int)(A.bptr[I + 1] - b0) : 0;
+    const double* v = A.vals + D * D * b0;
+    double acc[D];
+#pragma unroll
+    for (int a = 0; a < D; ++a) acc[a] = 0.0;
+    for (int s = l; s < m; s += TPR) {
+      const int64_t col = A.bcol[b0 + s];
+      double xs[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) xs[c] = x[col * D + c];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[a] = fma(v[((int64_t)a * m + s) * D + c], xs[c], acc[a]);
+    }
+    constexpr int SW = TPR < 32 ? TPR : 32;
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+      for (int o = SW / 2; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+    if constexpr (TPR == 256) {
+      __syncthreads();  // s_part of the previous row has been consumed
+      if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int a = 0; a < D; ++a) s_part[a][threadIdx.x >> 5] = acc[a];
+      __syncthreads();
+      if (l < D) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += s_part[l][q];
+        acc[0] = t;  // thread l < D holds row DOF l in acc[0]
+      }
+    }
+    if (active && l < D) {
+      double sum = acc[0];
+      if constexpr (TPR != 256) {
+#pragma unroll
+        for (int a = 1; a < D; ++a)
+          if (l == a) sum = acc[a];
+      }
+      const int64_t row = I * D + l;
+      double out;
+      if (MODE == M_AX) out = sum;
+      else if (MODE == M_RES) out = b[row] - sum;
+      else if (MODE == M_JAC) out = fma(omega * dinv[row], b[row] - sum, x[row]);
+      else out = y[row] + sum;
+      y[row] = out;
+    }
+  }
+}
+
+template <int D, int MODE>
+int launch_bcsr_d(const Bcsr& A, const double* x, double* y, const double* b, const double* dinv, double omega,
+                  cudaStream_t st) {
+  const double avg = (double)A.nblk / (double)(A.nbr > 0 ? A.nbr : 1);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (avg > 1024.0 || A.nbr < 2048) {
+    k_bcsr_spmv<D, MODE, 256><<<(unsigned)(A.nbr < cap ? A.nbr : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
+  } else if (avg > 16.0) {
+    const int64_t want = (A.nbr + 7) / 8;
+    k_bcsr_spmv<D, MODE, 32><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
+  } else {
+    const int64_t want = (A.nbr + 31) / 32;
+    k_bcsr_spmv<D, MODE, 8><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <int MODE>
+int launch_bcsr(const Bcsr& A, const double* x, double* y, const double* b, const double* dinv, double omega,
+                cudaStream_t st) {
+  if (A.d == 3) return launch_bcsr_d<3, MODE>(A, x, y, b, dinv, omega, st);
+  if (A.d == 2) return launch_bcsr_d<2, MODE>(A, x, y, b, dinv, omega, st);
+  return launch_bcsr_d<1, MODE>(A, x, y, b, dinv, omega, st);
+}
+
+// an operator of the hierarchy in whichever layout the host chose for it
+struct Oper {
+  bool bcsr = false;
+  Sell sell;
+  Bcsr blk;
+  int64_t n = 0;  // scalar rows
+};
+
+template <int MODE>
+int apply_oper(const Oper& A, const double* x, double* y, const double* b, const double* dinv, double omega,
+               cudaStream_t st) {
+  if (A.bcsr) return launch_bcsr<MODE>(A.blk, x, y, b, dinv, omega, st);
+  return launch_amg_spmv<MODE, false>(A.sell, x, y, b, dinv, omega, nullptr, nullptr, nullptr, st);
 }
 
 // x = w dinv b  (one damped-Jacobi sweep from the zero vector)
@@ -567,33 +714,66 @@ __global__ void __launch_bounds__(kVecThreads)
 }
 __global__ void k_pcg_roll(double* sc) { sc[P_RHO] = sc[P_RHO_NEW]; }
 
+// *out = a.b (single-level "hierarchy": the dense solve has no smoother to fuse the dot into)
+__global__ void __launch_bounds__(kVecThreads)
+    k_dot(int64_t n, const double* __restrict__ a, const double* __restrict__ b, double* partials,
+          unsigned int* ticket, double* out) {
+  __shared__ double s_red[kVecThreads / 32];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+    s = fma(a[i], b[i], s);
+  double mine[1], tot[1];
+  mine[0] = block_sum<kVecThreads>(s, s_red);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out = tot[0];
+}
+
 struct Level {
-  Sell A, P, R;
+  Oper A, P, R;
   int64_t n;
   const double* dinv;
   double omega;
   double *x, *b, *t;
 };
 
+int make_oper(const tfem_amg_operator_t* o, Oper* out) {
+  if (o->bcsr.nb_rows > 0) {
+    TFEM_REQUIRE(o->bcsr.bptr && o->bcsr.bcol && o->bcsr.vals && o->bcsr.d >= 1 && o->bcsr.d <= 3,
+                 "amg operator: bad block-CSR descriptor");
+    out->bcsr = true;
+    out->blk.nbr = o->bcsr.nb_rows;
+    out->blk.nblk = o->bcsr.n_blocks;
+    out->blk.bptr = o->bcsr.bptr;
+    out->blk.bcol = o->bcsr.bcol;
+    out->blk.vals = o->bcsr.vals;
+    out->blk.d = o->bcsr.d;
+    out->n = o->bcsr.nb_rows * o->bcsr.d;
+    return TFEM_OK;
+  }
+  int rc = check_sell(&o->sell);
+  if (rc != TFEM_OK) return rc;
+  out->bcsr = false;
+  out->sell = make_sell(&o->sell);
+  out->n = o->sell.n_rows;
+  return TFEM_OK;
+}
+
 int make_levels(const tfem_amg_level_t* lv, int n_levels, Level* out) {
+  int rc;
   for (int l = 0; l < n_levels; ++l) {
-    int rc = check_sell(&lv[l].A);
-    if (rc != TFEM_OK) return rc;
-    out[l].A = make_sell(&lv[l].A);
-    out[l].n = lv[l].A.n_rows;
+    if ((rc = make_oper(&lv[l].A, &out[l].A)) != TFEM_OK) return rc;
+    out[l].n = out[l].A.n;
     out[l].dinv = lv[l].dinv;
     out[l].omega = lv[l].omega;
     out[l].x = lv[l].x;
     out[l].b = lv[l].b;
     out[l].t = lv[l].t;
-    if (l + 1 < n_levels) {
-      if ((rc = check_sell(&lv[l].P)) != TFEM_OK || (rc = check_sell(&lv[l].R)) != TFEM_OK) return rc;
-      out[l].P = make_sell(&lv[l].P);
-      out[l].R = make_sell(&lv[l].R);
-      TFEM_REQUIRE(lv[l].dinv && lv[l].x && lv[l].t, "amg level: null work vector");
-      TFEM_REQUIRE(out[l].P.n == out[l].n && out[l].R.n == lv[l + 1].A.n_rows, "amg level: P / R shapes");
-      TFEM_REQUIRE(lv[l + 1].b && lv[l + 1].x, "amg level: null work vector");
-    }
+  }
+  TFEM_REQUIRE(!out[0].A.bcsr, "amg: the finest level must be given in SELL-32 form");
+  for (int l = 0; l + 1 < n_levels; ++l) {
+    if ((rc = make_oper(&lv[l].P, &out[l].P)) != TFEM_OK || (rc = make_oper(&lv[l].R, &out[l].R)) != TFEM_OK) return rc;
+    TFEM_REQUIRE(lv[l].dinv && lv[l].x && lv[l].t, "amg level: null work vector");
+    TFEM_REQUIRE(out[l].P.n == out[l].n && out[l].R.n == out[l + 1].n, "amg level: P / R shapes");
+    TFEM_REQUIRE(lv[l + 1].b && lv[l + 1].x, "amg level: null work vector");
   }
   return TFEM_OK;
 }
@@ -608,9 +788,8 @@ int vcycle(const Level* L, int n_levels, const double* coarse_inv, const double*
     const Level& v = L[l];
     const double* b = l == 0 ? r : v.b;
     k_jacobi_first<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, v.omega, v.dinv, b, v.x);
-    if ((rc = launch_amg_spmv<M_RES, false>(v.A, v.x, v.t, b, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
-    if ((rc = launch_amg_spmv<M_AX, false>(v.R, v.t, L[l + 1].b, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st)))
-      return rc;
+    if ((rc = apply_oper<M_RES>(v.A, v.x, v.t, b, nullptr, 0.0, st))) return rc;
+    if ((rc = apply_oper<M_AX>(v.R, v.t, L[l + 1].b, nullptr, nullptr, 0.0, st))) return rc;
     *launches += 3;
   }
   {
@@ -619,17 +798,21 @@ int vcycle(const Level* L, int n_levels, const double* coarse_inv, const double*
     double* x = n_levels == 1 ? z : c.x;
     k_dense_mv<<<grid_for(c.n * 32, 256), 256, 0, st>>>((int)c.n, coarse_inv, b, x);
     *launches += 1;
+    if (n_levels == 1 && dot_out) {
+      k_dot<<<vec_grid(c.n), kVecThreads, 0, st>>>(c.n, r, z, partials, ticket, dot_out);
+      *launches += 1;
+    }
   }
   for (int l = n_levels - 2; l >= 0; --l) {  // upward leg
     const Level& v = L[l];
     const double* b = l == 0 ? r : v.b;
     const double* xc = (l + 1 == n_levels - 1) ? L[l + 1].x : L[l + 1].t;
     double* out = l == 0 ? z : v.t;
-    if ((rc = launch_amg_spmv<M_ADD, false>(v.P, xc, v.x, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = apply_oper<M_ADD>(v.P, xc, v.x, nullptr, nullptr, 0.0, st))) return rc;
     if (l == 0 && dot_out)
-      rc = launch_amg_spmv<M_JAC, true>(v.A, v.x, out, b, v.dinv, v.omega, partials, ticket, dot_out, st);
+      rc = launch_amg_spmv<M_JAC, true>(v.A.sell, v.x, out, b, v.dinv, v.omega, partials, ticket, dot_out, st);
     else
-      rc = launch_amg_spmv<M_JAC, false>(v.A, v.x, out, b, v.dinv, v.omega, nullptr, nullptr, nullptr, st);
+      rc = apply_oper<M_JAC>(v.A, v.x, out, b, v.dinv, v.omega, st);
     if (rc) return rc;
     *launches += 2;
   }
@@ -674,13 +857,13 @@ extern "C" int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr, const i
 
 extern "C" int64_t tfem_amg_work_doubles(int64_t n_rows) { return 4 * pad32(n_rows) + P_COUNT + kMaxPartials + 32; }
 
-extern "C" int tfem_amg_rho(const tfem_sell_t* a, const double* dinv, int iterations, double* work,
+extern "C" int tfem_amg_rho(const tfem_amg_operator_t* a, const double* dinv, int iterations, double* work,
                             double* rho_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  int rc = check_sell(a);
+  TFEM_REQUIRE(a && dinv && work && rho_host && iterations > 0, "amg_rho: bad arguments");
+  Oper A;
+  int rc = make_oper(a, &A);
   if (rc != TFEM_OK) return rc;
-  TFEM_REQUIRE(dinv && work && rho_host && iterations > 0, "amg_rho: bad arguments");
-  const Sell A = make_sell(a);
   const int64_t n = A.n, np = pad32(n);
   double *x = work, *y = work + np, *sc = work + 4 * np, *partials = sc + P_COUNT;
   unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + kMaxPartials);
@@ -688,7 +871,7 @@ extern "C" int tfem_amg_rho(const tfem_sell_t* a, const double* dinv, int iterat
   const int vg = vec_grid(n);
   k_pw_init<<<vg, kVecThreads, 0, st>>>(n, x);
   for (int it = 0; it < iterations; ++it) {
-    if ((rc = launch_amg_spmv<M_AX, false>(A, x, y, nullptr, nullptr, 0.0, nullptr, nullptr, nullptr, st))) return rc;
+    if ((rc = apply_oper<M_AX>(A, x, y, nullptr, nullptr, 0.0, st))) return rc;
     k_pw_step<<<vg, kVecThreads, 0, st>>>(n, dinv, x, y, sc, partials, ticket);
     if (it + 1 < iterations) k_pw_scale<<<vg, kVecThreads, 0, st>>>(n, y, x, sc);
   }
@@ -763,7 +946,8 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
   cudaFreeAsync(err, st);
   if (rc != TFEM_OK) return rc;
   if (h) {
-    set_last_error("capacity", "amg_prolongator: a node has more than 1024 neighbours");
+    set_last_error("capacity", h == 1 ? "amg_prolongator: a node has more than 1024 neighbours"
+                                      : "amg_prolongator: a node touches more than 127 aggregates");
     return TFEM_ERR_CAPACITY;
   }
   return TFEM_OK;
@@ -880,28 +1064,30 @@ extern "C" int tfem_amg_spgemm_fill(int64_t nx, const int64_t* xptr, const int32
   return spgemm_sym_launch<true>(nx, xptr, xcol, yptr, ycol, nullptr, cptr, ccol, st);
 }
 
-template <int D>
+template <int D, int G>
 static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xcol, const double* xvals,
                              const int64_t* yptr, const int32_t* ycol, const double* yvals, const int64_t* cptr,
                              const int32_t* ccol, double* cvals, int max_row, cudaStream_t st) {
-  const size_t per_warp = (size_t)max_row * (D * D * sizeof(double) + sizeof(int));
-  const size_t budget = 160 * 1024;
-  if (per_warp > 200 * 1024) {
+  const size_t per_group = (size_t)max_row * (D * D * sizeof(double) + sizeof(int));
+  if (per_group > 200 * 1024) {
     set_last_error("capacity", "amg_spgemm_numeric: a product row does not fit in shared memory");
     return TFEM_ERR_CAPACITY;
   }
-  int W = (int)(budget / (per_warp ? per_warp : 1));
-  W = W < 1 ? 1 : (W > 8 ? 8 : W);
-  const size_t smem = W * per_warp + 16;
+  int W = 256 / G;
+  if (G == 32) {
+    const int fit = (int)((40 * 1024) / (per_group ? per_group : 1));  // ~5 CTAs per SM
+    W = fit < 1 ? 1 : (fit > 8 ? 8 : fit);
+  }
+  const size_t smem = W * per_group + 16;
   if (smem > 48 * 1024)
-    TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_num<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
+    TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_num<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spgemm_num<D>, W * 32, smem) != cudaSuccess || per_sm < 1)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spgemm_num<D, G>, W * G, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   const int64_t want = (nx + W - 1) / W;
   const int64_t cap = (int64_t)num_sms() * per_sm;
-  k_spgemm_num<D><<<(unsigned)(want < cap ? want : cap), W * 32, smem, st>>>(nx, xptr, xcol, xvals, yptr, ycol, yvals,
-                                                                             cptr, ccol, cvals, max_row);
+  k_spgemm_num<D, G><<<(unsigned)(want < cap ? want : cap), W * G, smem, st>>>(nx, xptr, xcol, xvals, yptr, ycol,
+                                                                               yvals, cptr, ccol, cvals, max_row);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -909,14 +1095,21 @@ static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
 extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, const int32_t* xcol,
                                        const double* xvals, const int64_t* yptr, const int32_t* ycol,
                                        const double* yvals, const int64_t* cptr, const int32_t* ccol, double* cvals,
-                                       int max_row, void* stream_) {
+                                       int max_row, int threads_per_row, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   TFEM_REQUIRE(xptr && xcol && xvals && yptr && ycol && yvals && cptr && ccol && cvals && nx > 0 && max_row > 0,
                "amg_spgemm_numeric: bad arguments");
-  if (d == 3) return spgemm_num_launch<3>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
-  if (d == 2) return spgemm_num_launch<2>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
-  if (d == 1) return spgemm_num_launch<1>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
-  set_last_error("invalid argument", "amg: 1, 2 or 3 DOFs per node");
+  TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
+  // a warp per row cannot hold rows whose accumulators exceed ~40 KB: those go to the CTA-per-row variant too
+  const bool cta = threads_per_row > 32 || (size_t)max_row * (d * d * 8 + 4) > 40 * 1024;
+#define TFEM_SPGEMM_CASE(D)                                                                                         \
+  if (d == D)                                                                                                       \
+    return cta ? spgemm_num_launch<D, 256>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st) \
+               : spgemm_num_launch<D, 32>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st);
+  TFEM_SPGEMM_CASE(3)
+  TFEM_SPGEMM_CASE(2)
+  TFEM_SPGEMM_CASE(1)
+#undef TFEM_SPGEMM_CASE
   return TFEM_ERR_INVALID;
 }
 
@@ -941,7 +1134,7 @@ extern "C" int tfem_amg_pcg_solve(const tfem_amg_level_t* levels, int n_levels, 
   Level L[TFEM_AMG_MAX_LEVELS];
   int rc = make_levels(levels, n_levels, L);
   if (rc != TFEM_OK) return rc;
-  const Sell& A = L[0].A;
+  const Sell& A = L[0].A.sell;
   const int64_t n = A.n, np = pad32(n);
   if (maxiter <= 0) maxiter = 10 * n;
   double *r = work, *p = work + np, *q = work + 2 * np, *z = work + 3 * np, *sc = work + 4 * np;
