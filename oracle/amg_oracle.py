@@ -29,8 +29,8 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse as sp
 
-POWER_ITS = 12
-RHO_SAFETY = 1.1
+POWER_ITS = 8
+RHO_SAFETY = 1.15
 MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 

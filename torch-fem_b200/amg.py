@@ -26,8 +26,8 @@ from torch import Tensor
 from . import _lib as L
 from .csr import CSRMatrix, SellMatrix, SellStructure
 
-POWER_ITS = 12
-RHO_SAFETY = 1.1
+POWER_ITS = 8
+RHO_SAFETY = 1.15
 MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 DENSE_LIMIT = 12000  # largest coarsest level a dense inverse is accepted for
@@ -162,7 +162,9 @@ def spgemm(d: int, X: BlockOperator, Y: BlockOperator, structure=None, out_vals:
     cptr, ccol, max_row = structure
     nv = d * d * ccol.shape[0]
     cvals = out_vals if out_vals is not None else _empty(nv, torch.float64, dev)[:nv]
-    tpr = 256 if Y.nblk * d >= 192 * Y.nbr else 32      # tasks per step of X's row = blocks of Y's row x d
+    # a CTA per row of C when the steps over X's row are wide (blocks of Y's row x d tasks each) or the rows of C are
+    # too few to fill the GPU with one warp each
+    tpr = 256 if (Y.nblk * d >= 192 * Y.nbr or X.nbr < 40000) else 32
     L.check(L.lib.tfem_amg_spgemm_numeric(d, X.nbr, L.ptr(X.bptr), L.ptr(X.bcol), L.ptr(X.vals), L.ptr(Y.bptr),
                                           L.ptr(Y.bcol), L.ptr(Y.vals), L.ptr(cptr), L.ptr(ccol), L.ptr(cvals),
                                           max_row, tpr, st))

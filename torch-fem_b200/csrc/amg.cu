@@ -333,17 +333,40 @@ __global__ void k_spgemm_sym(int64_t nx, const int64_t* __restrict__ xptr, const
   int* table = s_dyn + (size_t)w * HC;
   int* list = s_dyn + (size_t)W * HC + (size_t)w * HC;
   int* counter = s_dyn + (size_t)2 * W * HC + w;
+  __shared__ int s_prefix[8][32];
+  __shared__ long long s_y0s[8][32];
+  int* prefix = s_prefix[w];
+  long long* y0s = s_y0s[w];
   for (int64_t i = blockIdx.x * (int64_t)W + w; i < nx; i += (int64_t)gridDim.x * W) {
     for (int e = lane; e < HC; e += 32) table[e] = -1;
     if (lane == 0) *counter = 0;
     __syncwarp();
     bool overflow = false;
-    for (int64_t kx = xptr[i]; kx < xptr[i + 1]; ++kx) {
-      const int64_t j = xcol[kx];
-      const int64_t y0 = yptr[j];
-      const int LY = (int)(yptr[j + 1] - y0);
-      for (int e = lane; e < LY; e += 32) {
-        const int key = ycol[y0 + e];
+    const int64_t x0 = xptr[i];
+    const int LX = (int)(xptr[i + 1] - x0);
+    for (int kc = 0; kc < LX; kc += 32) {
+      // 32 entries of X's row at a time: their Y rows are flattened over the lanes (insertion order is irrelevant
+      // for a set), prefix[k] = entries of the first k+1 Y rows
+      int64_t my_y0 = 0;
+      int my_ly = 0;
+      if (kc + lane < LX) {
+        const int64_t j = xcol[x0 + kc + lane];
+        my_y0 = yptr[j];
+        my_ly = (int)(yptr[j + 1] - my_y0);
+      }
+      const int incl = warp_scan_incl(my_ly, lane);
+      prefix[lane] = incl;
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      y0s[lane] = my_y0;
+      __syncwarp();
+      for (int q = lane; q < total; q += 32) {
+        int lo = 0, hi = 31;  // first k with prefix[k] > q
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (prefix[mid] > q) hi = mid; else lo = mid + 1;
+        }
+        const int e = q - (lo ? prefix[lo - 1] : 0);
+        const int key = ycol[y0s[lo] + e];
         unsigned h = ((unsigned)key * 2654435761u) & (HC - 1);
         int probes = 0;
         while (true) {
@@ -360,6 +383,7 @@ __global__ void k_spgemm_sym(int64_t nx, const int64_t* __restrict__ xptr, const
           }
         }
       }
+      __syncwarp();
     }
     __syncwarp();
     const int m = *counter;
@@ -410,6 +434,8 @@ __global__ void __launch_bounds__(256)
                  const int64_t* __restrict__ cptr, const int32_t* __restrict__ ccol,
                  double* __restrict__ cvals, int MC) {
   extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ long long s_y0[256];  // Y-row offsets / lengths of a chunk of X's row (one entry per thread), so that
+  __shared__ int s_ly[256];        // the walk over X's row costs one memory round trip per step instead of three
   constexpr int DD = D * D;
   const int W = blockDim.x / G, w = threadIdx.x / G, lane = threadIdx.x % G;
   double* acc = reinterpret_cast<double*>(s_raw) + (size_t)w * MC * DD;
@@ -420,33 +446,54 @@ __global__ void __launch_bounds__(256)
     const int m = (int)(cptr[i + 1] - c0);
     for (int e = lane; e < m; e += G) cc[e] = ccol[c0 + e];
     for (int e = lane; e < m * DD; e += G) acc[e] = 0.0;
-    group_sync<G>();
     const int64_t x0 = xptr[i];
     const int LX = (int)(xptr[i + 1] - x0);
-    for (int kx = 0; kx < LX; ++kx) {
-      const int64_t j = xcol[x0 + kx];
-      const int64_t y0 = yptr[j];
-      const int LY = (int)(yptr[j + 1] - y0);
-      for (int o = lane; o < LY * D; o += G) {
-        const int t = o / D, a = o - t * D;
-        const int key = ycol[y0 + t];
-        int lo = 0, hi = m - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (cc[mid] < key) lo = mid + 1; else hi = mid;
-        }
-        double xa[D];
-#pragma unroll
-        for (int b = 0; b < D; ++b) xa[b] = xvals[DD * x0 + ((int64_t)a * LX + kx) * D + b];
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-          double sum = 0.0;
-#pragma unroll
-          for (int b = 0; b < D; ++b) sum = fma(xa[b], yvals[DD * y0 + ((int64_t)b * LY + t) * D + c], sum);
-          acc[lo * DD + a * D + c] += sum;
-        }
+    for (int kc = 0; kc < LX; kc += G) {
+      if (kc + lane < LX) {
+        const int64_t j = xcol[x0 + kc + lane];
+        const int64_t y0 = yptr[j];
+        s_y0[w * G + lane] = y0;
+        s_ly[w * G + lane] = (int)(yptr[j + 1] - y0);
       }
       group_sync<G>();
+      const int kend = LX - kc < G ? LX - kc : G;
+      for (int kk = 0; kk < kend; ++kk) {
+        const int kx = kc + kk;
+        const int64_t y0 = s_y0[w * G + kk];
+        const int LY = s_ly[w * G + kk];
+        // task = (entry t of Y's row, row DOFs [a0, a1)): a whole block per thread while the row fits the group
+        // in one pass that way, one row DOF per thread otherwise
+        const bool whole = LY * D > G && LY <= G;
+        const int per = whole ? 1 : D;
+        for (int o = lane; o < LY * per; o += G) {
+          const int t = o / per;
+          const int a0 = whole ? 0 : o - t * per, a1 = whole ? D : a0 + 1;
+          const int key = ycol[y0 + t];
+          double yb[D][D];
+#pragma unroll
+          for (int b = 0; b < D; ++b)
+#pragma unroll
+            for (int c = 0; c < D; ++c) yb[b][c] = yvals[DD * y0 + ((int64_t)b * LY + t) * D + c];
+          int lo = 0, hi = m - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cc[mid] < key) lo = mid + 1; else hi = mid;
+          }
+          for (int a = a0; a < a1; ++a) {
+            double xa[D];
+#pragma unroll
+            for (int b = 0; b < D; ++b) xa[b] = xvals[DD * x0 + ((int64_t)a * LX + kx) * D + b];
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              double sum = 0.0;
+#pragma unroll
+              for (int b = 0; b < D; ++b) sum = fma(xa[b], yb[b][c], sum);
+              acc[lo * DD + a * D + c] += sum;
+            }
+          }
+        }
+        group_sync<G>();
+      }
     }
     for (int o = lane; o < m * DD; o += G) {
       const int pos = o / DD, a = (o / D) % D, c = o % D;
@@ -1101,7 +1148,7 @@ extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, c
                "amg_spgemm_numeric: bad arguments");
   TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
   // a warp per row cannot hold rows whose accumulators exceed ~40 KB: those go to the CTA-per-row variant too
-  const bool cta = threads_per_row > 32 || (size_t)max_row * (d * d * 8 + 4) > 40 * 1024;
+  const bool cta = threads_per_row > 32 || (size_t)max_row * (d * d * 8 + 4) > 20 * 1024;
 #define TFEM_SPGEMM_CASE(D)                                                                                         \
   if (d == D)                                                                                                       \
     return cta ? spgemm_num_launch<D, 256>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st) \
