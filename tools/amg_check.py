@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--edge", type=int, nargs="+", default=[64])
     ap.add_argument("--rtol", type=float, default=1e-8)
     ap.add_argument("--jacobi", action="store_true")
+    ap.add_argument("--hostprof", action="store_true", help="wall time per C-ABI / torch call of an un-synchronised setup")
     a = ap.parse_args()
     torch.set_default_dtype(torch.float64)
     import torchfem_b200 as T
@@ -73,6 +74,44 @@ def main():
                     "rho": [getattr(lv, "rho", None) for lv in amg.levels[:-1]],
                     "launches": st["launches"],
                     "amg_dofs_per_s_setup_plus_solve": p.n_dofs / ((t_setup + t_solve2) * 1e-3)})
+        if a.hostprof:
+            import collections
+            from torchfem_b200 import _lib as LL, amg as amg_mod
+
+            acc = collections.defaultdict(float)
+
+            class Wrap:
+                def __init__(self, lib):
+                    self._lib = lib
+
+                def __getattr__(self, name):
+                    fn = getattr(self._lib, name)
+
+                    def call(*args):
+                        t0 = time.perf_counter()
+                        r = fn(*args)
+                        acc[name] += (time.perf_counter() - t0) * 1e3
+                        return r
+                    return call
+
+            real_lib, real_empty, real_inv, real_zeros = LL.lib, torch.empty, torch.linalg.inv, torch.zeros
+
+            def t_wrap(fn, name):
+                def call(*args, **kw):
+                    t0 = time.perf_counter()
+                    r = fn(*args, **kw)
+                    acc[name] += (time.perf_counter() - t0) * 1e3
+                    return r
+                return call
+            LL.lib = Wrap(real_lib)
+            torch.empty, torch.zeros = t_wrap(real_empty, "torch.empty"), t_wrap(real_zeros, "torch.zeros")
+            torch.linalg.inv = t_wrap(real_inv, "torch.linalg.inv")
+            try:
+                _, t_un = timed(lambda: AMGPreconditioner(A))
+            finally:
+                LL.lib, torch.empty, torch.zeros, torch.linalg.inv = real_lib, real_empty, real_zeros, real_inv
+            out["hostprof_total_ms"] = t_un
+            out["hostprof_ms"] = {k: round(v, 2) for k, v in sorted(acc.items(), key=lambda kv: -kv[1])[:14]}
         if a.jacobi:
             for rep in range(2):
                 (xj, _, sj), t_j = timed(lambda: csr.krylov_solve(A, b, method="cg", rtol=a.rtol))

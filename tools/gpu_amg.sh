@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_amg.py -q > gpurun_out/${TAG}_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
 tail -40 gpurun_out/${TAG}_pytest.log
-timeout 600 python tools/amg_check.py --edge 64 150 --jacobi > gpurun_out/${TAG}_check.jsonl 2> gpurun_out/${TAG}_check.err
+timeout 600 python tools/amg_check.py --edge 64 150 --jacobi --hostprof > gpurun_out/${TAG}_check.jsonl 2> gpurun_out/${TAG}_check.err
 echo "check rc=$?"
 cat gpurun_out/${TAG}_check.jsonl
 tail -20 gpurun_out/${TAG}_check.err

@@ -427,7 +427,7 @@ __device__ __forceinline__ void group_sync() {
 }
 
 template <int D, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
     k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
                  const double* __restrict__ xvals, const int64_t* __restrict__ yptr,
                  const int32_t* __restrict__ ycol, const double* __restrict__ yvals,
