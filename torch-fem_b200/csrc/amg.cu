@@ -872,7 +872,7 @@ int scan_in_place(int64_t* ptr, int64_t n, cudaStream_t st) {  // ptr[0] = 0, pt
   size_t bytes = 0;
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, ptr + 1, ptr + 1, (int)n, st));
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, bytes ? bytes : 16, st));
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, ptr + 1, ptr + 1, (int)n, st));
   TFEM_CUDA(cudaFreeAsync(tmp, st));
   return TFEM_OK;
@@ -938,7 +938,7 @@ extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t
                "amg_aggregate: bad arguments");
   TFEM_REQUIRE(nb < (int64_t)INT32_MAX, "amg_aggregate: too many nodes");
   int* counter = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&counter, sizeof(int), st));
+  TFEM_CUDA(malloc_async(&counter, sizeof(int), st));
   TFEM_CUDA(cudaMemsetAsync(state_work, 0, nb, st));
   const unsigned grid = grid_for(nb, 256);
   int rounds = 0, undecided = 1;
@@ -964,7 +964,7 @@ extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t
   size_t bytes = 0;
   TFEM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, index_work, index_work, (int)nb, st));
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, bytes ? bytes : 16, st));
   TFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, index_work, index_work, (int)nb, st));
   TFEM_CUDA(cudaFreeAsync(tmp, st));
   TFEM_CUDA(cudaMemcpyAsync(&last_idx, index_work + nb - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -981,7 +981,7 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
                               const int32_t* agg, const double* dinv, const uint8_t* iso, double omega,
                               int64_t* pcount, const int64_t* pptr, int32_t* pcol, double* pvals, cudaStream_t st) {
   int* err = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&err, sizeof(int), st));
+  TFEM_CUDA(malloc_async(&err, sizeof(int), st));
   TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
   const unsigned grid = grid_for(nb, 4);
   if (d == 3) k_prolongator<3, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
@@ -1033,8 +1033,8 @@ extern "C" int tfem_amg_transpose_structure(int64_t n_rows, int64_t n_cols, cons
   int rc = scan_in_place(tptr, n_cols, st);
   if (rc != TFEM_OK) return rc;
   int32_t *cursor = nullptr, *tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&cursor, n_cols * sizeof(int32_t), st));
-  TFEM_CUDA(cudaMallocAsync(&tmp, 2 * nblk * sizeof(int32_t), st));
+  TFEM_CUDA(malloc_async(&cursor, n_cols * sizeof(int32_t), st));
+  TFEM_CUDA(malloc_async(&tmp, 2 * nblk * sizeof(int32_t), st));
   TFEM_CUDA(cudaMemsetAsync(cursor, 0, n_cols * sizeof(int32_t), st));
   k_bt_fill<<<grid_for(n_rows, 128), 128, 0, st>>>(n_rows, ptr, col, tptr, cursor, tmp, tmp + nblk);
   k_bt_sort<<<grid_for(n_cols * 32, 256), 256, 0, st>>>(n_cols, tptr, tmp, tmp + nblk, tcol, tsrc);
@@ -1063,7 +1063,7 @@ static int spgemm_sym_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
                              const int32_t* ycol, int64_t* ccount, const int64_t* cptr, int32_t* ccol,
                              cudaStream_t st) {
   int* err = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&err, sizeof(int), st));
+  TFEM_CUDA(malloc_async(&err, sizeof(int), st));
   for (int attempt = 0; attempt < 2; ++attempt) {
     TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
     if (attempt == 0) {

@@ -46,6 +46,26 @@ inline int num_sms() {
   return sms;
 }
 
+// Stream-ordered scratch allocations come from the device's default memory pool. Its default release threshold is 0:
+// every stream synchronisation hands unused pool memory back to the driver and the next allocation maps it again
+// (measured: stalls of 10-300 ms inside setup calls that allocate a 4-byte flag). Keep the pool's memory instead.
+inline void keep_pool_memory() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+  uint64_t threshold = UINT64_MAX;
+  cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+}
+
+template <typename P>
+inline cudaError_t malloc_async(P** ptr, size_t bytes, cudaStream_t st) {
+  keep_pool_memory();
+  return cudaMallocAsync(reinterpret_cast<void**>(ptr), bytes, st);
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 __device__ __forceinline__ double warp_sum(double v) {

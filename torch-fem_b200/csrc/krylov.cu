@@ -693,7 +693,7 @@ extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
   k_tr_scan_serial<<<1, 1, 0, st>>>(n_cols, t_indptr);
   TFEM_LAUNCH_CHECK();
   int64_t* cursor = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&cursor, n_cols * sizeof(int64_t), st));
+  TFEM_CUDA(malloc_async(&cursor, n_cols * sizeof(int64_t), st));
   TFEM_CUDA(cudaMemsetAsync(cursor, 0, n_cols * sizeof(int64_t), st));
   k_tr_fill<<<grid_for(n_rows, 128), 128, 0, st>>>(n_rows, indptr, cols, vals, t_indptr, cursor, t_cols, t_vals);
   TFEM_LAUNCH_CHECK();
@@ -714,7 +714,7 @@ extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_
   size_t bytes = 0;
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, slice_ptr + 1, slice_ptr + 1, (int)ns, st));
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, bytes ? bytes : 16, st));
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, slice_ptr + 1, slice_ptr + 1, (int)ns, st));
   TFEM_CUDA(cudaFreeAsync(tmp, st));
   return TFEM_OK;
@@ -751,7 +751,7 @@ extern "C" int tfem_bsell_slice_ptr(int64_t n_rows, int dpn, const int64_t* slic
   size_t bytes = 0;
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, bslice_ptr + 1, bslice_ptr + 1, (int)ns, st));
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, bytes ? bytes : 16, st));
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, bytes, bslice_ptr + 1, bslice_ptr + 1, (int)ns, st));
   TFEM_CUDA(cudaFreeAsync(tmp, st));
   return TFEM_OK;

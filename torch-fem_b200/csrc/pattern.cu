@@ -268,7 +268,7 @@ extern "C" int tfem_pattern_phase1(int64_t n_nod, int64_t n_elem, int nn, int dp
     return TFEM_ERR_CAPACITY;
   }
   int32_t* bad = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&bad, sizeof(int32_t), st));
+  TFEM_CUDA(malloc_async(&bad, sizeof(int32_t), st));
   TFEM_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
   TFEM_CUDA(cudaMemsetAsync(inc_ptr, 0, (n_nod + 1) * sizeof(int32_t), st));
   TFEM_CUDA(cudaMemsetAsync(blk_cnt, 0, n_nod * sizeof(int32_t), st));
@@ -280,7 +280,7 @@ extern "C" int tfem_pattern_phase1(int64_t n_nod, int64_t n_elem, int nn, int dp
   size_t tmp_bytes = 0;
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, inc_ptr, inc_ptr, (int)(n_nod + 1), st));
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, tmp_bytes ? tmp_bytes : 16, st));
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, inc_ptr, inc_ptr, (int)(n_nod + 1), st));
   if (n_slots > 0) {
     k_fill_incidence<<<grid_for(n_slots, 256), 256, 0, st>>>(n_slots, n_nod, elements, inc_ptr, blk_cnt,
@@ -319,7 +319,7 @@ extern "C" int tfem_pattern_phase2(int64_t n_nod, int64_t n_elem, int nn, int dp
                    diag_map && src_ptr && src, "pattern: null pointer");
   // exclusive scans over nodes: block offsets and scalar-entry offsets (n_nod+1 outputs each)
   int64_t* node_base = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&node_base, (n_nod + 1) * sizeof(int64_t), st));
+  TFEM_CUDA(malloc_async(&node_base, (n_nod + 1) * sizeof(int64_t), st));
   auto it_blk = thrust::make_transform_iterator(blk_cnt, BlkToI64());
   auto it_nnz = thrust::make_transform_iterator(blk_cnt, NodeNnz{dpn});
   size_t b1 = 0, b2 = 0;
@@ -327,7 +327,7 @@ extern "C" int tfem_pattern_phase2(int64_t n_nod, int64_t n_elem, int nn, int dp
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, b2, it_nnz, node_base + 1, (int)n_nod, st));
   size_t tmp_bytes = b1 > b2 ? b1 : b2;
   void* tmp = nullptr;
-  TFEM_CUDA(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st));
+  TFEM_CUDA(malloc_async(&tmp, tmp_bytes ? tmp_bytes : 16, st));
   TFEM_CUDA(cudaMemsetAsync(node_ptr, 0, sizeof(int64_t), st));
   TFEM_CUDA(cudaMemsetAsync(node_base, 0, sizeof(int64_t), st));
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, it_blk, node_ptr + 1, (int)n_nod, st));
