@@ -59,7 +59,7 @@ def _on_boundary(nodes):
 
 class TestPatch:
     @pytest.mark.parametrize("etype", ETYPES)
-    @pytest.mark.parametrize("method", [None, "cg"])
+    @pytest.mark.parametrize("method", [None, "cg", "amgx"])
     def test_reproduces_a_linear_displacement_field(self, T, etype, method):
         """First-order patch test for all 8 element types (reference tests/test_models.py:54-71),
         through the default direct method and through the Jacobi-CG kernels at stol 1e-14."""
@@ -97,7 +97,7 @@ class TestConfigA:
         cube.displacements[nodes[:, 0] == 1.0, 0] = 0.1
         return cube
 
-    @pytest.mark.parametrize("method", ["spsolve", "cg", "minres"])
+    @pytest.mark.parametrize("method", ["spsolve", "cg", "minres", "amgx"])
     def test_forward_and_adjoint(self, T, method):
         g = load_case("config_a.npz")
         cube = self._cube(T)
@@ -207,7 +207,7 @@ class TestSparse:
     def _sp(self, dense):
         return dense.to_sparse_coo().coalesce()
 
-    @pytest.mark.parametrize("method", [None, "spsolve", "cg", "minres"])
+    @pytest.mark.parametrize("method", [None, "spsolve", "cg", "minres", "amgx"])
     def test_matches_dense_solution(self, T, method):
         A = self._spd(6, 0)
         b = torch.randn(6)
@@ -262,6 +262,10 @@ class TestSparse:
         assert T.sparse.resolve_method(10000, "cuda", None) == "minres"
         assert T.sparse.resolve_method(5, "cuda", "cg") == "cg"
         assert T.sparse.describe_method(10000, "cuda", None) == "minres | iterative | jacobi | tfem_b200 | cuda"
+        # AMG (the reference's CUDA default when its AMG backend is installed) above the measured crossover
+        assert T.sparse.resolve_method(T.sparse.AMG_MIN_DOFS, "cuda", None) == "amgx"
+        assert T.sparse.describe_method(3_000_000, "cuda", None) == "amgx | iterative | amg | tfem_b200 | cuda"
+        assert "amgx" in T.sparse.available_backends
 
 
 class TestBase:
@@ -392,3 +396,68 @@ class TestHeatTransient:
         temp, _, flux, grad, _ = cube.time_integration(torch.tensor(g["cube.t_out"]), delta_t=0.25)
         for got, key in ((temp, "cube.temp"), (flux, "cube.flux"), (grad, "cube.grad")):
             assert np.abs(got.cpu().numpy() - g[key]).max() <= 1e-8 * max(1.0, np.abs(g[key]).max())
+
+
+class TestModelsWithAMG:
+    """method="amgx" through the model API on problems large enough for a multi-level hierarchy, against the
+    Jacobi-CG kernels at the same tolerance (both validated against the reference on config A)."""
+
+    def test_heat_cube_scalar_blocks(self, T):
+        from torchfem_b200.materials import IsotropicConductivity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(23, 23, 23)          # 12,167 unknowns, d = 1
+        out = {}
+        for method in ("cg", "amgx"):
+            m = T.SolidHeat(nodes, elements, IsotropicConductivity3D(10.0))
+            m.constraints[nodes[:, 0] == 0.0, 0] = True
+            m.constraints[nodes[:, 0] == 1.0, 0] = True
+            m.temperatures[nodes[:, 0] == 1.0, 0] = 100.0
+            m.heat_flux[nodes[:, 1] == 1.0, 0] = 3.0
+            out[method], *_ = m.solve(method=method, stol=1e-12)
+        assert float((out["amgx"] - out["cg"]).abs().max()) <= 1e-8 * float(out["cg"].abs().max())
+
+    def test_planar_two_dofs_per_node_and_gradient(self, T):
+        from torchfem_b200.materials import IsotropicElasticityPlaneStress
+        from torchfem_b200.mesh import rect_quad
+
+        nodes, elements = rect_quad(81, 41, 2.0, 1.0)      # 6,642 DOFs, d = 2
+        res = {}
+        for method in ("cg", "amgx"):
+            th = torch.full((len(elements),), 0.5, requires_grad=True)
+            m = T.Planar(nodes, elements, IsotropicElasticityPlaneStress(1000.0, 0.3), thickness=th)
+            m.constraints[nodes[:, 0] == 0.0, :] = True
+            m.forces[nodes[:, 0] == 2.0, 1] = -0.01
+            u, *_ = m.solve(differentiable_parameters=th, method=method, stol=1e-12)
+            (u ** 2).sum().backward()
+            res[method] = (u.detach(), th.grad.clone())
+        assert float((res["amgx"][0] - res["cg"][0]).abs().max()) <= 1e-8 * float(res["cg"][0].abs().max())
+        assert float((res["amgx"][1] - res["cg"][1]).abs().max()) <= 1e-7 * float(res["cg"][1].abs().max())
+
+    def test_newton_loop_refreshes_the_hierarchy(self, T):
+        """Neo-Hookean block, nlgeom, two increments: every Newton iteration hands the solver object back
+        (reference sparse.py:438-441 `resetup`) and the tangent changes — the numeric phase is repeated on the
+        stored aggregates; result equal to the Jacobi-CG path."""
+        from torchfem_b200.materials import Hyperelastic3D
+        from torchfem_b200.mesh import cube_hexa
+
+        En, NU = 1000.0, 0.3
+        LBD = En * NU / ((1.0 + NU) * (1.0 - 2.0 * NU))
+        MU = En / (2.0 * (1.0 + NU))
+
+        def psi(F, params):
+            Cg = F.transpose(-1, -2) @ F
+            logJ = 0.5 * torch.logdet(Cg)
+            return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+
+        nodes, elements = cube_hexa(17, 9, 9, 2.0, 1.0, 1.0)     # 4,131 DOFs
+        out = {}
+        for method in ("cg", "amgx"):
+            box = T.Solid(nodes, elements, Hyperelastic3D(psi, torch.tensor([MU, LBD])))
+            left, right = nodes[:, 0] == 0.0, nodes[:, 0] == 2.0
+            box.constraints[left, :] = True
+            box.constraints[right, 0] = True
+            box.displacements[right, 0] = 0.4
+            u, f, *_ = box.solve(increments=torch.tensor([0.0, 0.5, 1.0]), nlgeom=True, method=method, stol=1e-11)
+            out[method] = u
+        assert float((out["amgx"] - out["cg"]).abs().max()) <= 1e-7 * float(out["cg"].abs().max())

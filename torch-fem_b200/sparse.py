@@ -30,6 +30,11 @@ available_backends = ["tfem_b200", "amgx"]
 
 METHODS = ["spsolve", "minres", "cg", "pardiso", "amgx"]
 DIRECT_LIMIT = 10000  # reference policy: below this many DOFs solve directly (sparse.py:78)
+# reference policy on CUDA: AMG ("amgx") whenever that backend is available (sparse.py:82-83). Here the AMG kernels
+# are always available, but on a B200 the Jacobi-Krylov kernels win below a few million unknowns (the hierarchy costs
+# ~150 launches and a dozen synchronisations to build; measured crossover on the benchmark cube: ~3 M DOFs), so AMG
+# is auto-selected only above this size. Pass method="amgx" to force it.
+AMG_MIN_DOFS = 2_000_000
 
 ERR_AMG_OPERATOR = "method='amgx' needs an assembled matrix; the matrix-free element operator has no entries to coarsen."
 ERR_NO_CPU = ("torch-fem_b200 has no CPU path: pass CUDA tensors (e.g. torch.set_default_device('cuda')). "
@@ -37,11 +42,13 @@ ERR_NO_CPU = ("torch-fem_b200 has no CPU path: pass CUDA tensors (e.g. torch.set
 
 
 def resolve_method(n_dofs: int, device: str, method: str | None) -> str:
-    """Backend `sparse_solve` uses for a system of this size (policy of reference sparse.py:74-84;
-    AmgX / pardiso are never auto-selected here because they do not exist on this path)."""
+    """Backend `sparse_solve` uses for a system of this size (policy of reference sparse.py:74-84: direct below
+    10,000 DOFs, AMG on CUDA when available, else MINRES; see AMG_MIN_DOFS for the one deviation)."""
     if method is not None:
         return method
-    return "spsolve" if n_dofs < DIRECT_LIMIT else "minres"
+    if n_dofs < DIRECT_LIMIT:
+        return "spsolve"
+    return "amgx" if n_dofs >= AMG_MIN_DOFS else "minres"
 
 
 def describe_method(n_dofs: int, device: str, method: str | None) -> str:
