@@ -362,7 +362,39 @@ def sparse_small():
     np.savez_compressed(os.path.join(OUT, "sparse_small.npz"), **out)
 
 
+def modal():
+    """`solve_modes` (reference base.py:1097-1129; scipy eigsh shift-invert) for a clamped solid block and a planar
+    strip with per-element E and rho: omega^2, and d(sum omega^2)/dE, /drho through the Rayleigh-quotient adjoint."""
+    out = {}
+    nodes, elements = mesh.cube_hexa(6, 4, 4, 2.0, 1.0, 1.0)
+    n_elem = len(elements)
+    E_ = (1000.0 * (1.0 + 0.2 * torch.sin(torch.arange(n_elem, dtype=torch.float64)))).requires_grad_(True)
+    rho = (2.0 + 0.5 * torch.cos(torch.arange(n_elem, dtype=torch.float64))).requires_grad_(True)
+    box = Solid(nodes, elements, M.IsotropicElasticity3D(E=E_, nu=torch.full((n_elem,), 0.3), rho=rho))
+    box.constraints[nodes[:, 0] == 0.0, :] = True
+    omega_sq, modes = box.solve_modes(n_modes=6)
+    omega_sq.sum().backward()
+    out.update({"solid.omega_sq": npy(omega_sq), "solid.modes": npy(modes), "solid.grad_E": npy(E_.grad),
+                "solid.grad_rho": npy(rho.grad)})
+    nodes, elements = mesh.rect_quad(9, 4, 2.0, 0.5)
+    n_elem = len(elements)
+    E_ = (500.0 * (1.0 + 0.1 * torch.cos(torch.arange(n_elem, dtype=torch.float64)))).requires_grad_(True)
+    strip = Planar(nodes, elements, M.IsotropicElasticityPlaneStress(E=E_, nu=torch.full((n_elem,), 0.25),
+                                                                      rho=torch.full((n_elem,), 3.0)),
+                   thickness=torch.full((n_elem,), 0.1))
+    strip.constraints[nodes[:, 0] == 0.0, :] = True
+    omega_sq, modes = strip.solve_modes(n_modes=5)
+    omega_sq[0].backward()
+    out.update({"planar.omega_sq": npy(omega_sq), "planar.grad_E": npy(E_.grad)})
+    np.savez_compressed(os.path.join(OUT, "modal.npz"), **out)
+    print("modal: solid omega^2", out["solid.omega_sq"], "planar", out["planar.omega_sq"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     element_tables()
     small_cases()
     config_a()
@@ -370,5 +402,6 @@ if __name__ == "__main__":
     hyper_small()
     sparse_small()
     heat_transient()
+    modal()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -461,3 +461,143 @@ class TestModelsWithAMG:
             u, f, *_ = box.solve(increments=torch.tensor([0.0, 0.5, 1.0]), nlgeom=True, method=method, stol=1e-11)
             out[method] = u
         assert float((out["amgx"] - out["cg"]).abs().max()) <= 1e-7 * float(out["cg"].abs().max())
+
+
+class TestModal:
+    """`modal_eigsolve` / `differentiable_modal_eigsolve` (reference tests/test_sparse.py:208-306) and
+    `solve_modes` against vectors generated from the unmodified reference (oracle/make_golden.py::modal,
+    scipy eigsh shift-invert): eigenvalues <= 1e-8 relative, sensitivities <= 1e-6."""
+
+    N_MODES = 3
+
+    @staticmethod
+    def _spd(n, seed):
+        torch.manual_seed(seed)
+        A = torch.randn(n, n, device="cpu")
+        return (A @ A.T + n * torch.eye(n, device="cpu")).cuda()
+
+    def _problem(self, n=8):
+        K_dense, M_dense = self._spd(n, 0), self._spd(n, 1)
+        return K_dense, M_dense, K_dense.to_sparse_coo().coalesce(), M_dense.to_sparse_coo().coalesce(), torch.arange(2, n)
+
+    def test_matches_dense_generalized_eigenproblem(self, T):
+        import scipy.linalg
+
+        K_dense, M_dense, K, M, free = self._problem()
+        values, vectors = T.sparse.modal_eigsolve(K, M, self.N_MODES, free)
+        f = free.cpu().numpy()
+        ref = scipy.linalg.eigh(K_dense.cpu().numpy()[f][:, f], M_dense.cpu().numpy()[f][:, f], eigvals_only=True)
+        assert np.allclose(values.cpu().numpy(), ref[: self.N_MODES], rtol=1e-8)
+        assert bool((values[1:] >= values[:-1]).all())
+        assert vectors.shape == (8, self.N_MODES) and bool((vectors[:2] == 0).all())
+        # M-normalised like eigsh
+        assert torch.allclose((vectors.T @ M_dense @ vectors), torch.eye(self.N_MODES), atol=1e-10)
+
+    @pytest.mark.parametrize("which", ["K", "M"])
+    def test_eigenvalue_gradients_match_finite_differences(self, T, which):
+        n, eps = 8, 1e-6
+        K_dense, M_dense, K, M, free = self._problem(n)
+        torch.manual_seed(7)
+        D = torch.randn(n, n)
+        D = 0.5 * (D + D.T)
+        base = K_dense if which == "K" else M_dense
+        idx = base.to_sparse_coo().coalesce().indices()
+        values = base[idx[0], idx[1]].clone().requires_grad_(True)
+        A = torch.sparse_coo_tensor(idx, values, (n, n)).coalesce()
+        lambdas, phis = T.sparse.differentiable_modal_eigsolve(A if which == "K" else K, M if which == "K" else A,
+                                                               self.N_MODES, free)
+        assert lambdas.requires_grad and not phis.requires_grad
+        (grad,) = torch.autograd.grad(lambdas.sum(), [values])
+
+        def solve(pert):
+            P = (base + pert).to_sparse_coo().coalesce()
+            v, _ = T.sparse.modal_eigsolve(P if which == "K" else K, M if which == "K" else P, self.N_MODES, free)
+            return v.sum()
+
+        fd = (solve(eps * D) - solve(-eps * D)) / (2 * eps)
+        assert torch.allclose(torch.dot(grad, D[idx[0], idx[1]]), fd, rtol=1e-5)
+
+    @staticmethod
+    def _aligned(a, b):
+        return min(np.linalg.norm(a - b), np.linalg.norm(a + b)) / np.linalg.norm(b)
+
+    def test_solve_modes_solid_matches_reference(self, T):
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        g = load_case("modal.npz")
+        nodes, elements = cube_hexa(6, 4, 4, 2.0, 1.0, 1.0)
+        n_elem = len(elements)
+        E_ = (1000.0 * (1.0 + 0.2 * torch.sin(torch.arange(n_elem, dtype=torch.float64)))).requires_grad_(True)
+        rho = (2.0 + 0.5 * torch.cos(torch.arange(n_elem, dtype=torch.float64))).requires_grad_(True)
+        box = T.Solid(nodes, elements, IsotropicElasticity3D(E=E_, nu=torch.full((n_elem,), 0.3), rho=rho))
+        box.constraints[nodes[:, 0] == 0.0, :] = True
+        omega_sq, modes = box.solve_modes(n_modes=6)
+        assert modes.shape == (6, box.n_nod, 3) and not modes.requires_grad
+        assert np.allclose(omega_sq.detach().cpu().numpy(), g["solid.omega_sq"], rtol=1e-8)
+        for i in range(6):
+            assert self._aligned(modes[i].cpu().numpy(), g["solid.modes"][i]) <= 1e-6
+        omega_sq.sum().backward()
+        assert np.allclose(E_.grad.cpu().numpy(), g["solid.grad_E"], rtol=1e-6, atol=1e-9 * np.abs(g["solid.grad_E"]).max())
+        assert np.allclose(rho.grad.cpu().numpy(), g["solid.grad_rho"], rtol=1e-6, atol=1e-9 * np.abs(g["solid.grad_rho"]).max())
+
+    def test_solve_modes_planar_matches_reference(self, T):
+        from torchfem_b200.materials import IsotropicElasticityPlaneStress
+        from torchfem_b200.mesh import rect_quad
+
+        g = load_case("modal.npz")
+        nodes, elements = rect_quad(9, 4, 2.0, 0.5)
+        n_elem = len(elements)
+        E_ = (500.0 * (1.0 + 0.1 * torch.cos(torch.arange(n_elem, dtype=torch.float64)))).requires_grad_(True)
+        strip = T.Planar(nodes, elements, IsotropicElasticityPlaneStress(E=E_, nu=torch.full((n_elem,), 0.25),
+                                                                          rho=torch.full((n_elem,), 3.0)),
+                         thickness=torch.full((n_elem,), 0.1))
+        strip.constraints[nodes[:, 0] == 0.0, :] = True
+        omega_sq, _ = strip.solve_modes(n_modes=5)
+        assert np.allclose(omega_sq.detach().cpu().numpy(), g["planar.omega_sq"], rtol=1e-8)
+        omega_sq[0].backward()
+        assert np.allclose(E_.grad.cpu().numpy(), g["planar.grad_E"], rtol=1e-6, atol=1e-9 * np.abs(g["planar.grad_E"]).max())
+
+    def test_lobpcg_with_amg_matches_the_dense_path(self, T):
+        """The large-system route (AMG-preconditioned LOBPCG on the device CSR) forced on a model small enough for the
+        dense route: same eigenvalues (<= 1e-8), same invariant subspace."""
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(13, 7, 7, 2.0, 1.0, 1.0)           # 1,911 DOFs
+        box = T.Solid(nodes, elements, IsotropicElasticity3D(E=1000.0, nu=0.3, rho=2.0))
+        box.constraints[nodes[:, 0] == 0.0, :] = True
+        con = torch.nonzero(box.constraints.ravel()).ravel()
+        free = torch.nonzero(~box.constraints.ravel()).ravel()
+        K = box.assemble_matrix(box.k0(), con)
+        M = box.assemble_matrix(box.integrate_mass(), con)
+        vd, Xd = T.sparse.modal_eigsolve(K, M, 6, free, method="dense")
+        vl, Xl = T.sparse.modal_eigsolve(K, M, 6, free, method="lobpcg")
+        assert torch.allclose(vl, vd, rtol=1e-8)
+        assert bool((Xl[con] == 0).all())
+        # the bending pair is nearly degenerate: compare the subspaces through M-inner products
+        G = Xd.T @ torch.stack([M.matvec(Xl[:, j].contiguous()) for j in range(6)], dim=1)
+        assert torch.allclose(G @ G.T, torch.eye(6), atol=1e-6)
+
+    def test_lobpcg_at_scale(self, T):
+        """Beyond the dense limit (46,875 DOFs): residuals of the returned pairs and agreement with the analytic
+        scaling omega^2 ~ E / rho."""
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(41, 21, 21, 2.0, 1.0, 1.0)
+        vals = []
+        for E_ in (1000.0, 4000.0):
+            box = T.Solid(nodes, elements, IsotropicElasticity3D(E=E_, nu=0.3, rho=2.0))
+            box.constraints[nodes[:, 0] == 0.0, :] = True
+            omega_sq, modes = box.solve_modes(n_modes=4)
+            vals.append(omega_sq)
+            con = torch.nonzero(box.constraints.ravel()).ravel()
+            K = box.assemble_matrix(box.k0(), con)
+            Mm = box.assemble_matrix(box.integrate_mass(), con)
+            for i in range(4):
+                x = modes[i].reshape(-1).contiguous()
+                r = K.matvec(x) - omega_sq[i] * Mm.matvec(x)
+                r[con] = 0.0
+                assert float(r.norm()) <= 1e-6 * float(K.matvec(x).norm())
+        assert torch.allclose(vals[1], 4.0 * vals[0], rtol=1e-7)

@@ -78,6 +78,37 @@ def _det_inv(J: Tensor) -> tuple[Tensor, Tensor]:
     return det, inv
 
 
+class _IntegrateK(torch.autograd.Function):
+    """k_e = sum_q w_q detJ_q s_e B_q^T C B_q (kernel K1) with the adjoint contraction for the tangent:
+    dL/dC[e,i,J,k,L] = sum_q w detJ s sum_{p,r} B_q[J,p] B_q[L,r] dL/dk[e,(p,i),(r,k)]  (mechanics, base.py:1088),
+    dL/dkappa[e,i,j] = sum_q w detJ s sum_{p,r} B_q[i,p] B_q[j,r] dL/dk[e,p,r]            (heat, base.py:1274).
+    The backward runs in torch: it is only reached by eigenvalue sensitivities, never by the solve path."""
+
+    @staticmethod
+    def forward(ctx, tangent: Tensor, model: "FEM"):
+        ctx.model = model
+        ctx.per_gp = tangent.dim() == (6 if model.KIND == L.KIND_MECH else 4)
+        return model._integrate_k_raw(tangent)
+
+    @staticmethod
+    def backward(ctx, gk: Tensor):
+        model = ctx.model
+        _, B, detJ = model._ip_shape()
+        w = model.etype.iweights.to(device=gk.device, dtype=gk.dtype)
+        scale = model._k_scale
+        nn, d = model.etype.nodes, model.n_dof_per_node
+        out = []
+        for q in range(B.shape[0]):
+            f = w[q] * detJ[q] * (scale if scale is not None else 1.0)
+            if model.KIND == L.KIND_MECH:
+                g = gk.reshape(model.n_elem, nn, d, nn, d)
+                out.append(torch.einsum("e,eJp,epirk,eLr->eiJkL", f, B[q], g, B[q]))
+            else:
+                out.append(torch.einsum("e,eip,epr,ejr->eij", f, B[q], gk, B[q]))
+        grad = torch.stack(out) if ctx.per_gp else torch.stack(out).sum(0)
+        return grad, None
+
+
 class FEM(ABC):
     """Abstract finite-element model (reference base.py:23-132)."""
 
@@ -244,7 +275,14 @@ class FEM(ABC):
 
     def _integrate_k(self, tangent: Tensor) -> Tensor:
         """Element matrices from the material tangent with kernel K1. `tangent` is one tensor per
-        element or a stack over Gauss points."""
+        element or a stack over Gauss points. When the tangent carries a graph (differentiable material
+        parameters) the result does too: k is linear in the tangent and `_IntegrateK.backward` applies the transposed
+        contraction (needed by `solve_modes`, whose eigenvalue sensitivities flow through k; `FEM.solve` detaches K)."""
+        if torch.is_grad_enabled() and tangent.requires_grad and not self.nodes.requires_grad:
+            return _IntegrateK.apply(tangent, self)
+        return self._integrate_k_raw(tangent)
+
+    def _integrate_k_raw(self, tangent: Tensor) -> Tensor:
         bref, w = self._tables()
         return _csr.integrate_k(self.KIND, bref, w, self.nodes.detach(), self.elements,
                                 tangent.detach().to(torch.float64), self._k_scale)
@@ -489,6 +527,19 @@ class Mechanics(FEM, ABC):
     @property
     def initial_grad(self) -> Tensor:
         return torch.eye(self.n_flux[0])
+
+    def solve_modes(self, n_modes: int) -> tuple[Tensor, Tensor]:
+        """Natural frequencies and mode shapes, K phi = omega^2 M phi (reference base.py:1097-1129). Returns
+        `(omega_sq [n_modes], differentiable w.r.t. material parameters; modes [n_modes, n_nod, n_dof_per_node],
+        detached)`. Solved on the free-DOF subspace: dense `eigh` for small models, AMG-preconditioned LOBPCG on the
+        device CSR otherwise (`modal.py`)."""
+        from .modal import ModesFromElements
+
+        k = self.k0()
+        m = self.integrate_mass()
+        omega_sq, phis = ModesFromElements.apply(k, m, self, n_modes)
+        modes = phis.detach().T.reshape(n_modes, self.n_nod, self.n_dof_per_node)
+        return omega_sq, modes
 
     @property
     def forces(self) -> Tensor:

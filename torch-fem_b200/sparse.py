@@ -270,3 +270,7 @@ def newton_solve(eval_residual: Callable, du: Tensor, B, max_iter: int, rtol: fl
     if out is None:
         raise RuntimeError("Solve.apply returned None, expected a Tensor.")
     return out
+
+
+# modal analysis (reference sparse.py:798-1011) lives in modal.py; re-exported under the reference's names
+from .modal import Eigensolve, differentiable_modal_eigsolve, modal_eigsolve  # noqa: E402,F401
