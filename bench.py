@@ -359,11 +359,24 @@ def run_ours(args):
             return u.cpu()
 
         ms_api, u_api = timed(step_api, max(1, min(args.steps, 2)), 1)
+        api_amg = None
+        if not args.no_amg:
+            def step_api_amg():
+                model.material = IsotropicElasticity3D(E_h.to(device, non_blocking=True), nu_h.to(device, non_blocking=True))
+                model.constraints = con_bool_h.to(device, non_blocking=True)
+                model.displacements = disp2_h.to(device, non_blocking=True)
+                u, *_ = model.solve(method="amgx", stol=RTOL, rtol=1e-6)
+                return u.cpu()
+
+            ms_api_amg, u_amg = timed(step_api_amg, max(1, min(args.steps, 2)), 1)
+            api_amg = {"value": n_dofs / (ms_api_amg / 1e3), "unit": UNIT, "ms_per_step": ms_api_amg,
+                       "call": "Solid.solve(method='amgx', stol=1e-8)",
+                       "rel_diff_vs_kernel_path": float((u_amg.ravel() - u_h.ravel()).norm() / u_h.norm())}
         err = float((u_api.ravel() - u_h.ravel()).norm() / u_h.norm())
         api = {"value": n_dofs / (ms_api / 1e3), "unit": UNIT, "ms_per_step": ms_api,
                "h2d_bytes_per_step": int(2 * E_h.numel() * 8 + con_bool_h.numel() + disp2_h.numel() * 8),
                "d2h_bytes_per_step": int(d2h), "call": "Solid.solve(method='cg', stol=1e-8)",
-               "rel_diff_vs_kernel_path": err}
+               "rel_diff_vs_kernel_path": err, "with_amg": api_amg}
 
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N=1 only
     cpu = None
