@@ -1,7 +1,7 @@
 #!/bin/bash
 # AMG tuning knobs on the GPU box (per-iteration time of AMG-PCG at config B).
 mkdir -p gpurun_out
-for cfg in "" "TFEM_AMG_OCC8=1" "TFEM_AMG_BCSR_MIN_AVG=48" "TFEM_AMG_OCC8=1 TFEM_AMG_BCSR_MIN_AVG=48"; do
+for cfg in "" "TFEM_AMG_OCC6=1" "TFEM_AMG_BCSR_MIN_AVG=96" "TFEM_AMG_BCSR_MIN_AVG=24"; do
   echo "== $cfg"
   env $cfg timeout 300 python tools/amg_check.py --edge 150 2>&1 | python -c "
 import sys, json

@@ -32,7 +32,7 @@ MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 DENSE_LIMIT = 12000  # largest coarsest level a dense inverse is accepted for
 BCSR_MAX_ROWS = int(os.environ.get("TFEM_AMG_BCSR_MAX_ROWS", 20000))   # operators with fewer block rows than this ...
-BCSR_MIN_AVG = int(os.environ.get("TFEM_AMG_BCSR_MIN_AVG", 96))         # ... or more blocks per row than this are
+BCSR_MIN_AVG = int(os.environ.get("TFEM_AMG_BCSR_MIN_AVG", 48))         # ... or more blocks per row than this are
 #                                                                         streamed as block CSR instead of SELL-32
 
 

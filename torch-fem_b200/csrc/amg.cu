@@ -508,7 +508,7 @@ enum { M_AX = 0, M_RES = 1, M_JAC = 2, M_ADD = 3 };
 
 // y = A x (M_AX) | b - A x (M_RES) | x + w dinv (b - A x) (M_JAC, y != x) | y + A x (M_ADD), one warp per SELL
 // slice, persistent grid. DOT: x.(A x) for M_AX, b.y for M_JAC (fixed-order reduction, last CTA writes *out_scalar).
-template <int DPN, int MODE, bool DOT, int MINB = ((MODE == M_JAC || DOT) ? 6 : 8)>
+template <int DPN, int MODE, bool DOT, int MINB = 8>
 __global__ void __launch_bounds__(kSellWarps * 32, MINB)
     k_amg_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ b,
                const double* __restrict__ dinv, double omega, double* partials, unsigned int* ticket,
@@ -548,13 +548,13 @@ template <int DPN, int MODE, bool DOT>
 int launch_amg_spmv_t(const Sell& A, const double* x, double* y, const double* b, const double* dinv, double omega,
                       double* partials, unsigned int* ticket, double* out_scalar, cudaStream_t st) {
   static int g = 0;  // per instantiation
-  // tuning knob (tools/amg_check.py): TFEM_AMG_OCC8=1 compiles the epilogue-heavy variants for 8 CTAs per SM
-  // (32 registers, a few spills) instead of 6 (40 registers)
-  static const bool occ8 = getenv("TFEM_AMG_OCC8") && atoi(getenv("TFEM_AMG_OCC8")) != 0;
+  // 8 CTAs per SM (32 registers; the epilogue-heavy variants spill ~80 bytes outside the streaming loop) beat 6 CTAs
+  // with 40 registers: 5.92 -> 5.55 ms per AMG-PCG iteration at config B. TFEM_AMG_OCC6=1 selects the latter.
+  static const bool occ6 = getenv("TFEM_AMG_OCC6") && atoi(getenv("TFEM_AMG_OCC6")) != 0;
   const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
-  if (occ8) {
-    if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT, 8>, kSellWarps * 32);
-    k_amg_spmv<DPN, MODE, DOT, 8><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
+  if (occ6) {
+    if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT, 6>, kSellWarps * 32);
+    k_amg_spmv<DPN, MODE, DOT, 6><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
                                                                                          partials, ticket, out_scalar);
   } else {
     if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT>, kSellWarps * 32);
