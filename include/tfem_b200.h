@@ -128,6 +128,17 @@ int tfem_elem_force(int dim, int nn, int n_int, int dpn, const double* bref_host
                     const double* nodes_dev, const int64_t* elements_dev, int64_t n_elem, const double* P_dev,
                     const double* scale_dev, int weighted, double* f_e_dev, int32_t* neg_jac_dev, void* stream);
 
+/* K17 — tangent contraction of the elastic stress update, all Gauss points in one launch:
+ *   out[q,e,i] = sum_k C[e,i,k] E[q,e,k]   (transpose != 0: C[e,k,i]),   i, k = flattened index pairs, m = d*d
+ * replaces `einsum("...ijkl,...kl->...ij", C, de)` inside Material.step (materials/elasticity.py:119-127), which the
+ * reference evaluates per Gauss point with a temporary of the size of C per point. C_dev: double [n_elem, m, m];
+ * E_dev / out_dev: double [n_q, n_elem, m]. tfem_ddot_outer is its backward with respect to C:
+ *   gC[e,i,k] = sum_q G[q,e,i] E[q,e,k]. */
+int tfem_ddot(int m, int64_t n_q, int64_t n_elem, const double* C_dev, const double* E_dev, int transpose,
+              double* out_dev, void* stream);
+int tfem_ddot_outer(int m, int64_t n_q, int64_t n_elem, const double* G_dev, const double* E_dev, double* gC_dev,
+                    void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * K2/K3 — deterministic assembly.  Replaces FEM.assemble_matrix (base.py:398-426): index_add_ scatter
  * (atomics on CUDA) becomes a gather over the precomputed `src` permutation with a fixed summation

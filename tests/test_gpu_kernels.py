@@ -406,3 +406,25 @@ def test_full_size_properties(T, tables):
     true_res = float(torch.linalg.norm(rhs - Ac.matvec(xs)) / torch.linalg.norm(rhs))
     assert info["converged"] and true_res <= 2e-8
     assert 250 <= info["iterations"] <= 400  # ~5(N-1)+2
+
+
+@pytest.mark.parametrize("d,n_q", [(3, 8), (3, 1), (2, 4)])
+def test_tangent_contraction_kernel(T, d, n_q):
+    """K17 `tfem_ddot` / `tfem_ddot_outer` behind `materials._ddot` vs the reference's einsum
+    (materials/elasticity.py:119-127), forward and both gradients, <= 1e-14 relative."""
+    from torchfem_b200.materials import _ddot
+
+    gen = torch.Generator(device="cuda").manual_seed(d * 10 + n_q)
+    n_elem = 1237
+    C = torch.randn(n_elem, d, d, d, d, device="cuda", generator=gen, requires_grad=True)
+    shape = (n_q, n_elem, d, d) if n_q > 1 else (n_elem, d, d)
+    e = torch.randn(*shape, device="cuda", generator=gen, requires_grad=True)
+    out = _ddot(C, e)
+    ref = torch.einsum("eijkl,...ekl->...eij", C, e)
+    assert out.shape == ref.shape
+    assert float((out - ref).abs().max()) <= 1e-14 * float(ref.abs().max()) * d * d
+    g = torch.randn_like(out)
+    gC, ge = torch.autograd.grad(out, (C, e), g)
+    gC_ref, ge_ref = torch.autograd.grad(ref, (C, e), g)
+    assert float((gC - gC_ref).abs().max()) <= 1e-13 * float(gC_ref.abs().max())
+    assert float((ge - ge_ref).abs().max()) <= 1e-13 * float(ge_ref.abs().max())

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--rows", type=int, default=45)
     ap.add_argument("--backward", action="store_true", help="forces as differentiable parameter + u.sum().backward()")
     ap.add_argument("--stol", type=float, default=1e-8)
+    ap.add_argument("--method", default="cg")
     a = ap.parse_args()
     torch.set_default_dtype(torch.float64)
     import torchfem_b200 as T
@@ -43,14 +44,14 @@ def main():
         torch.cuda.synchronize()
         t = time.perf_counter()
         if a.backward:
-            u, *_ = model.solve(method="cg", stol=a.stol, differentiable_parameters=model.forces)
+            u, *_ = model.solve(method=a.method, stol=a.stol, differentiable_parameters=model.forces)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             u.sum().backward()
             torch.cuda.synchronize()
             print("   fwd %.3f s  bwd %.3f s" % (t1 - t, time.perf_counter() - t1))
         else:
-            u, *_ = model.solve(method="cg", stol=a.stol, rtol=1e-6)
+            u, *_ = model.solve(method=a.method, stol=a.stol, rtol=1e-6)
         torch.cuda.synchronize()
         return time.perf_counter() - t
 

@@ -255,6 +255,53 @@ int dispatch_pair(bool grad, int dim, int nn, int n_int, int dpn, const double* 
   return TFEM_ERR_INVALID;
 }
 
+// ------------------------------------------------------------------------------------------ K17 tangent contraction
+// out[q,e,i] = sum_k C[e,i,k] E[q,e,k]   (TRANSPOSE: C[e,k,i]) with M = d*d flattened index pairs — the elastic stress
+// update sigma = C : eps at every Gauss point (reference elasticity.py:119-127 `einsum("...ijkl,...kl->...ij")`) and,
+// transposed, its backward with respect to the strain. One thread per (element, row) keeps its row of C in registers
+// and walks the Gauss points: C is read once, E / out once each (bytes: 8 M^2 + 16 Q M per element).
+template <int M, bool TRANSPOSE>
+__global__ void __launch_bounds__(256)
+    k_ddot(int64_t n_q, int64_t n_elem, const double* __restrict__ C, const double* __restrict__ E,
+           double* __restrict__ out) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t / M;
+  const int i = (int)(t - e * M);
+  if (e >= n_elem) return;
+  double c[M];
+#pragma unroll
+  for (int k = 0; k < M; ++k) c[k] = TRANSPOSE ? C[(e * M + k) * M + i] : C[(e * M + i) * M + k];
+  for (int64_t q = 0; q < n_q; ++q) {
+    const double* h = E + (q * n_elem + e) * M;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < M; ++k) s = fma(c[k], h[k], s);
+    out[(q * n_elem + e) * M + i] = s;
+  }
+}
+
+// gC[e,i,k] = sum_q G[q,e,i] E[q,e,k]  — the backward of k_ddot with respect to the tangent
+template <int M>
+__global__ void __launch_bounds__(256)
+    k_ddot_outer(int64_t n_q, int64_t n_elem, const double* __restrict__ G, const double* __restrict__ E,
+                 double* __restrict__ gC) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t e = t / M;
+  const int i = (int)(t - e * M);
+  if (e >= n_elem) return;
+  double acc[M];
+#pragma unroll
+  for (int k = 0; k < M; ++k) acc[k] = 0.0;
+  for (int64_t q = 0; q < n_q; ++q) {
+    const double g = G[(q * n_elem + e) * M + i];
+    const double* h = E + (q * n_elem + e) * M;
+#pragma unroll
+    for (int k = 0; k < M; ++k) acc[k] = fma(g, h[k], acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < M; ++k) gC[(e * M + i) * M + k] = acc[k];
+}
+
 }  // namespace
 }  // namespace tfem
 
@@ -276,4 +323,38 @@ extern "C" int tfem_elem_force(int dim, int nn, int n_int, int dpn, const double
   if (n_elem <= 0) return TFEM_OK;
   return dispatch_pair(false, dim, nn, n_int, dpn, bref_host, w_host, nodes, elements, n_elem, P, scale, weighted, f_e,
                        neg_jac, (cudaStream_t)stream_);
+}
+
+extern "C" int tfem_ddot(int m, int64_t n_q, int64_t n_elem, const double* C, const double* E, int transpose,
+                         double* out, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(C && E && out && n_q >= 0, "ddot: null pointer");
+  TFEM_REQUIRE(m == 1 || m == 4 || m == 9, "ddot: m must be 1, 4 or 9 (d*d)");
+  if (n_elem <= 0 || n_q == 0) return TFEM_OK;
+  const unsigned grid = (unsigned)((n_elem * m + 255) / 256);
+#define TFEM_DDOT(M)                                                                  \
+  if (m == M) {                                                                       \
+    if (transpose) k_ddot<M, true><<<grid, 256, 0, st>>>(n_q, n_elem, C, E, out);     \
+    else k_ddot<M, false><<<grid, 256, 0, st>>>(n_q, n_elem, C, E, out);              \
+  }
+  TFEM_DDOT(9)
+  TFEM_DDOT(4)
+  TFEM_DDOT(1)
+#undef TFEM_DDOT
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+extern "C" int tfem_ddot_outer(int m, int64_t n_q, int64_t n_elem, const double* G, const double* E, double* gC,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  TFEM_REQUIRE(G && E && gC && n_q >= 0, "ddot_outer: null pointer");
+  TFEM_REQUIRE(m == 1 || m == 4 || m == 9, "ddot_outer: m must be 1, 4 or 9 (d*d)");
+  if (n_elem <= 0) return TFEM_OK;
+  const unsigned grid = (unsigned)((n_elem * m + 255) / 256);
+  if (m == 9) k_ddot_outer<9><<<grid, 256, 0, st>>>(n_q, n_elem, G, E, gC);
+  else if (m == 4) k_ddot_outer<4><<<grid, 256, 0, st>>>(n_q, n_elem, G, E, gC);
+  else k_ddot_outer<1><<<grid, 256, 0, st>>>(n_q, n_elem, G, E, gC);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
 }
