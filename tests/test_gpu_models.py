@@ -417,6 +417,31 @@ class TestModelsWithAMG:
             out[method], *_ = m.solve(method=method, stol=1e-12)
         assert float((out["amgx"] - out["cg"]).abs().max()) <= 1e-8 * float(out["cg"].abs().max())
 
+    def test_hierarchy_is_cached_with_the_pattern_across_load_cases(self, T):
+        """Second solve on the same model with other Dirichlet conditions: the hierarchy kept with the pattern is
+        refreshed (new isolated-DOF mask, same aggregates), the result still equals the Jacobi-CG path."""
+        from torchfem_b200.amg import AMGPreconditioner
+        from torchfem_b200.materials import IsotropicElasticity3D
+        from torchfem_b200.mesh import cube_hexa
+
+        nodes, elements = cube_hexa(13, 9, 9, 2.0, 1.0, 1.0)
+        box = T.Solid(nodes, elements, IsotropicElasticity3D(1000.0, 0.3))
+        cases = [(nodes[:, 0] == 0.0, nodes[:, 0] == 2.0, 0), (nodes[:, 2] == 0.0, nodes[:, 2] == 1.0, 2)]
+        cached = []
+        for fixed, pulled, axis in cases:
+            out = {}
+            for method in ("cg", "amgx"):
+                box.constraints = torch.zeros_like(nodes, dtype=torch.bool)
+                box.displacements = torch.zeros_like(nodes)
+                box.constraints[fixed, :] = True
+                box.constraints[pulled, axis] = True
+                box.displacements[pulled, axis] = 0.05
+                out[method], *_ = box.solve(method=method, stol=1e-11)
+            assert float((out["amgx"] - out["cg"]).abs().max()) <= 1e-8 * float(out["cg"].abs().max())
+            cached.append(box.pattern.sell_structure.amg_cache)
+            assert isinstance(cached[-1], AMGPreconditioner)
+        assert cached[0] is cached[1]
+
     def test_planar_two_dofs_per_node_and_gradient(self, T):
         from torchfem_b200.materials import IsotropicElasticityPlaneStress
         from torchfem_b200.mesh import rect_quad

@@ -18,7 +18,10 @@ namespace {
 constexpr int kWarps = 8;
 
 // NN = nodes per element as a compile-time constant (0: run-time value) so the slot decoding needs no
-// integer division. Up to 4 contributions are in flight per entry (independent loads), added in slot order.
+// integer division. One lane per node BLOCK (neighbour p of the node): it decodes every contribution once and
+// accumulates the whole dpn x dpn block (the previous version decoded it once per scalar entry and was bound by
+// instruction issue: 71 % of the issue slots at config B); each entry still receives its contributions in slot
+// order, two contributions in flight.
 template <int DPN, int NN>
 __global__ void __launch_bounds__(kWarps * 32)
     k_assemble(int64_t n_nod, int nn_rt, const int64_t* __restrict__ node_ptr,
@@ -42,42 +45,70 @@ __global__ void __launch_bounds__(kWarps * 32)
   }
   const int nd = nn * DPN;
   const int64_t nd2 = (int64_t)nd * nd;
-  const int rowlen = cnt * DPN;
+  bool row_con[DPN];
+  int64_t rp[DPN];
+  double lsum[DPN];
 #pragma unroll
   for (int i = 0; i < DPN; ++i) {
-    const int64_t row = row0 + i;
-    const int64_t rp = indptr[row];
-    const bool row_con = is_con && is_con[row];
-    double lsum = 0.0;
-    for (int t = lane; t < rowlen; t += 32) {
-      const int p = t / DPN, j = t - p * DPN;
-      const int64_t sb = src_ptr[nb + p], se = src_ptr[nb + p + 1];
-      double acc = 0.0;
-      for (int64_t s = sb; s < se; s += 4) {
-        int c[4];
-        double v[4];
+    row_con[i] = is_con && is_con[row0 + i];
+    rp[i] = indptr[row0 + i];
+    lsum[i] = 0.0;
+  }
+  for (int p = lane; p < cnt; p += 32) {
+    const int64_t sb = src_ptr[nb + p], se = src_ptr[nb + p + 1];
+    double acc[DPN][DPN];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) c[u] = (s + u < se) ? src[s + u] : -1;  // e*nn*nn + a*nn + b
+    for (int i = 0; i < DPN; ++i)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int cc = c[u] < 0 ? 0 : c[u];
+      for (int j = 0; j < DPN; ++j) acc[i][j] = 0.0;
+    for (int64_t s = sb; s < se; s += 2) {
+      const double* kb[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cc = (s + u < se) ? src[s + u] : -1;  // e*nn*nn + a*nn + b
+        if (cc < 0) {
+          kb[u] = nullptr;
+        } else {
           const int ea = cc / nn, bq = cc - ea * nn;
           const int e = ea / nn, aq = ea - e * nn;
-          v[u] = c[u] < 0 ? 0.0 : k[e * nd2 + (int64_t)(aq * DPN + i) * nd + bq * DPN + j];
+          kb[u] = k + e * nd2 + (int64_t)(aq * DPN) * nd + bq * DPN;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc += v[u];  // + 0.0 for the missing ones: exact
       }
-      const int64_t col = (int64_t)adj[nb + p] * DPN + j;
-      const bool col_con = is_con && is_con[col];
-      // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
-      if (lift && col_con && !row_con) lsum = fma(acc, ubc[col], lsum);
-      if (row_con || col_con) acc = (col == row) ? 1.0 : 0.0;
-      vals[rp + t] = acc;
+      double v[2][DPN][DPN];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int i = 0; i < DPN; ++i)
+#pragma unroll
+          for (int j = 0; j < DPN; ++j) v[u][i][j] = kb[u] ? kb[u][i * nd + j] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)  // + 0.0 for the missing one: exact
+#pragma unroll
+        for (int i = 0; i < DPN; ++i)
+#pragma unroll
+          for (int j = 0; j < DPN; ++j) acc[i][j] += v[u][i][j];
     }
-    if (lift) {
-      lsum = warp_sum(lsum);
-      if (lane == 0) lift[row] = lsum;
+    const int64_t col0 = (int64_t)adj[nb + p] * DPN;
+#pragma unroll
+    for (int j = 0; j < DPN; ++j) {
+      const int64_t col = col0 + j;
+      const bool col_con = is_con && is_con[col];
+      const double uc = (lift && col_con) ? ubc[col] : 0.0;
+#pragma unroll
+      for (int i = 0; i < DPN; ++i) {
+        double a = acc[i][j];
+        // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
+        if (lift && col_con && !row_con[i]) lsum[i] = fma(a, uc, lsum[i]);
+        if (row_con[i] || col_con) a = (col == row0 + i) ? 1.0 : 0.0;
+        vals[rp[i] + (int64_t)p * DPN + j] = a;
+      }
+    }
+  }
+  if (lift) {
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) {
+      const double t = warp_sum(lsum[i]);
+      if (lane == 0) lift[row0 + i] = t;
     }
   }
 }

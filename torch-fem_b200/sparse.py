@@ -110,10 +110,17 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
         # object comes back in as M
         if isinstance(Ac, ElementOperator):
             raise RuntimeError(ERR_AMG_OPERATOR)
+        if not (isinstance(M, AMGPreconditioner) and M.n == n):
+            # aggregates and the patterns of P, R, A_c depend on the sparsity pattern only: a hierarchy built for an
+            # earlier matrix on the same mesh (previous load case, design iteration, Newton solve) is kept with the
+            # pattern-level SELL structure and only refreshed
+            M = getattr(Ac._sell_struct, "amg_cache", None) if Ac._sell_struct is not None else None
         if isinstance(M, AMGPreconditioner) and M.n == n:
             M.resetup(Ac)
         else:
             M = AMGPreconditioner(Ac)
+            if Ac._sell_struct is not None:
+                Ac._sell_struct.amg_cache = M
         x, _ = M.solve(rhs, x0=None if x0 is None else x0.detach(), rtol=stol)
         return x.to(device=out_device, dtype=b.dtype), M
     if isinstance(Ac, ElementOperator) and method == "spsolve":
