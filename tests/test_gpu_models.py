@@ -264,6 +264,7 @@ class TestSparse:
         assert T.sparse.describe_method(10000, "cuda", None) == "minres | iterative | jacobi | tfem_b200 | cuda"
         # AMG (the reference's CUDA default when its AMG backend is installed) above the measured crossover
         assert T.sparse.resolve_method(T.sparse.AMG_MIN_DOFS, "cuda", None) == "amgx"
+        assert T.sparse.resolve_method(T.sparse.AMG_MIN_DOFS - 1, "cuda", None) == "minres"
         assert T.sparse.describe_method(3_000_000, "cuda", None) == "amgx | iterative | amg | tfem_b200 | cuda"
         assert "amgx" in T.sparse.available_backends
 

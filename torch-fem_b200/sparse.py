@@ -31,10 +31,11 @@ available_backends = ["tfem_b200", "amgx"]
 METHODS = ["spsolve", "minres", "cg", "pardiso", "amgx"]
 DIRECT_LIMIT = 10000  # reference policy: below this many DOFs solve directly (sparse.py:78)
 # reference policy on CUDA: AMG ("amgx") whenever that backend is available (sparse.py:82-83). Here the AMG kernels
-# are always available, but on a B200 the Jacobi-Krylov kernels win below a few million unknowns (the hierarchy costs
-# ~150 launches and a dozen synchronisations to build; measured crossover on the benchmark cube: ~3 M DOFs), so AMG
-# is auto-selected only above this size. Pass method="amgx" to force it.
-AMG_MIN_DOFS = 2_000_000
+# are always available, but on a B200 the Jacobi-Krylov kernels win on small systems (the hierarchy costs ~500 launches
+# and a dozen synchronisations to build). Measured on the benchmark cube: 0.82 M DOFs 51 ms AMG vs 39 ms Jacobi-PCG
+# (stol 1e-8); 1.5 M DOFs 86 vs 113 ms (stol 1e-10); 10.3 M DOFs 0.32 vs 0.92 s. AMG is auto-selected from 1 M
+# unknowns; pass method="amgx" to force it.
+AMG_MIN_DOFS = 1_000_000
 
 ERR_AMG_OPERATOR = "method='amgx' needs an assembled matrix; the matrix-free element operator has no entries to coarsen."
 ERR_NO_CPU = ("torch-fem_b200 has no CPU path: pass CUDA tensors (e.g. torch.set_default_device('cuda')). "
