@@ -1,0 +1,41 @@
+"""Device time of integrate_k and assemble at config B (CUDA events)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+import torchfem_b200 as T  # noqa: E402
+from torchfem_b200 import csr  # noqa: E402
+from oracle import fem_oracle as O  # noqa: E402
+
+dev = torch.device("cuda", 0)
+E = int(sys.argv[1]) if len(sys.argv) > 1 else 150
+nodes, elements, con, disp = bench.build_problem(T, torch, E, dev)
+bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
+C = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous().to(dev)
+nodes, elements = nodes.to(dev), elements.to(dev)
+is_con = con.ravel().to(torch.uint8).to(dev)
+p = csr.Pattern(elements, nodes.shape[0], 3)
+
+
+def ev(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
+vals = torch.empty(p.nnz, device=dev)
+print("integrate_k %.3f ms   assemble %.3f ms" % (
+    ev(lambda: csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)),
+    ev(lambda: csr.assemble(p, k, is_con, out=vals))))

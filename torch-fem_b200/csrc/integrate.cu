@@ -58,9 +58,13 @@ __device__ __forceinline__ double inv_det<3>(const double (&J)[3][3], double (&i
 }
 
 constexpr int kCB = 8;  // column nodes per thread
+#ifndef TFEM_K1_MINB
+#define TFEM_K1_MINB 1     // minimum resident CTAs per SM the register allocation must allow (tuning: tools/time_k1.py)
+#endif
 
 template <int KIND, int DIM, int NN, int NINT, int EPC, bool PERGP>
-__global__ void __launch_bounds__(((EPC * NN * ((KIND == TFEM_KIND_MECH) ? DIM : 1) * ((NN + kCB - 1) / kCB) + 31) / 32) * 32)
+__global__ void __launch_bounds__(((EPC * NN * ((KIND == TFEM_KIND_MECH) ? DIM : 1) * ((NN + kCB - 1) / kCB) + 31) / 32) * 32,
+                                  TFEM_K1_MINB)
     k_integrate(const __grid_constant__ Tables<DIM, NN, NINT> tab, const double* __restrict__ nodes,
                 const int64_t* __restrict__ elements, int64_t n_elem,
                 const double* __restrict__ tangent, const double* __restrict__ scale,
