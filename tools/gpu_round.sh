@@ -18,12 +18,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_i
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_sell_spmv|k_cg_update|k_cg_direction' -s 28 -c 6 \
    -o gpurun_out/${TAG}_cg_iteration -f python tools/prof_driver.py --edge 150 --iters 3 > gpurun_out/${TAG}_ncu_cg.log 2>&1
 # AMG: launch list of one hierarchy build + 2 PCG iterations, full captures of the numeric SpGEMMs and of one V cycle
-# (the 24 k_amg_spmv launches of the power iterations are skipped)
+# (the 8 k_amg_spmv launches of the level-0 power iteration are skipped)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
    --log-file gpurun_out/${TAG}_amg_launches.csv python tools/prof_amg.py > gpurun_out/${TAG}_amg_prof.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_spgemm_num|k_prolongator' -c 4 \
    -o gpurun_out/${TAG}_amg_setup -f python tools/prof_amg.py > gpurun_out/${TAG}_ncu_amg_setup.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_amg_spmv' -s 24 -c 9 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_amg_spmv' -s 8 -c 6 \
    -o gpurun_out/${TAG}_amg_cycle -f python tools/prof_amg.py > gpurun_out/${TAG}_ncu_amg_cycle.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log
 cat gpurun_out/${TAG}_bench.json
