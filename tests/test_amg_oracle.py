@@ -64,3 +64,24 @@ def test_isolated_rows_stay_out_of_the_coarse_space():
     P = L0.P.tocsr()
     assert abs(P[np.nonzero(L0.iso)[0]]).sum() == 0.0
     assert all((L.A.diagonal() != 0).all() for L in lv)
+
+
+def test_block_operator_layout_matches_scalar_csr():
+    """Host logic of torch-fem_b200/amg.py (no kernel call): the block-CSR value layout (entry (a, s, c) of block row
+    I at d*d*bptr[I] + (a*m + s)*d + c) is the scalar CSR order of the assembled matrix, so `indptr`, `to_scipy` and
+    the dense copy agree with scipy's CSR of the same matrix."""
+    import torch
+
+    from torchfem_b200.amg import BlockOperator, _dense
+
+    r, _, _ = _system(4)
+    A = r["A"].tocsr()
+    A.sort_indices()
+    d = 3
+    ptr, adj, _ = M.block_graph(A, d)
+    op = BlockOperator(d, len(ptr) - 1, len(ptr) - 1, torch.as_tensor(ptr), torch.as_tensor(adj),
+                       torch.as_tensor(A.data.copy()))
+    assert np.array_equal(op.indptr.numpy(), A.indptr)
+    assert abs(op.to_scipy() - A).max() == 0.0
+    assert np.array_equal(_dense(op).numpy(), A.toarray())
+    assert op.use_bcsr        # few rows: the coarse-level layout
