@@ -426,26 +426,54 @@ __device__ __forceinline__ void group_sync() {
   else __syncthreads();
 }
 
+// position of block column `key` in the sorted column list cc[0..m) of the row: binary search (CTA variant, long
+// rows) or — warp variant — a lookup in a small open-addressing table built once per row (the search was 36 % of
+// the stall samples and 24 % of the instructions of A*P at config B)
+__device__ __forceinline__ int find_sorted(const int* cc, int m, int key) {
+  int lo = 0, hi = m - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cc[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 template <int D, int G>
 __global__ void __launch_bounds__(256, 4)
     k_spgemm_num(int64_t nx, const int64_t* __restrict__ xptr, const int32_t* __restrict__ xcol,
                  const double* __restrict__ xvals, const int64_t* __restrict__ yptr,
                  const int32_t* __restrict__ ycol, const double* __restrict__ yvals,
                  const int64_t* __restrict__ cptr, const int32_t* __restrict__ ccol,
-                 double* __restrict__ cvals, int MC) {
+                 double* __restrict__ cvals, int MC, int HT) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ long long s_y0[256];  // Y-row offsets / lengths of a chunk of X's row (one entry per thread), so that
   __shared__ int s_ly[256];        // the walk over X's row costs one memory round trip per step instead of three
   constexpr int DD = D * D;
+  constexpr bool HASH = G == 32;
   const int W = blockDim.x / G, w = threadIdx.x / G, lane = threadIdx.x % G;
   double* acc = reinterpret_cast<double*>(s_raw) + (size_t)w * MC * DD;
   int* cc = reinterpret_cast<int*>(reinterpret_cast<double*>(s_raw) + (size_t)W * MC * DD) + (size_t)w * MC;
+  // warp variant: hash table of HT (power of two >= 2 MC) entries per warp: key in the high, position in the low half
+  long long* table = reinterpret_cast<long long*>(reinterpret_cast<int*>(reinterpret_cast<double*>(s_raw) +
+                                                  (size_t)W * MC * DD) + (size_t)W * MC + ((W * MC) & 1)) + (size_t)w * HT;
   // G == 256: one row per CTA, the loop bound is uniform over the CTA (barriers inside)
   for (int64_t i = blockIdx.x * (int64_t)W + w; i < nx; i += (int64_t)gridDim.x * W) {
     const int64_t c0 = cptr[i];
     const int m = (int)(cptr[i + 1] - c0);
-    for (int e = lane; e < m; e += G) cc[e] = ccol[c0 + e];
     for (int e = lane; e < m * DD; e += G) acc[e] = 0.0;
+    if constexpr (HASH) {
+      for (int e = lane; e < HT; e += G) table[e] = -1;
+      __syncwarp();
+      for (int e = lane; e < m; e += G) {
+        const int key = ccol[c0 + e];
+        unsigned h = ((unsigned)key * 2654435761u) & (unsigned)(HT - 1);
+        const long long entry = ((long long)key << 32) | (unsigned)e;
+        while (atomicCAS(reinterpret_cast<unsigned long long*>(&table[h]), ~0ull, (unsigned long long)entry) != ~0ull)
+          h = (h + 1) & (unsigned)(HT - 1);
+      }
+    } else {
+      for (int e = lane; e < m; e += G) cc[e] = ccol[c0 + e];
+    }
     const int64_t x0 = xptr[i];
     const int LX = (int)(xptr[i + 1] - x0);
     for (int kc = 0; kc < LX; kc += G) {
@@ -461,34 +489,44 @@ __global__ void __launch_bounds__(256, 4)
         const int kx = kc + kk;
         const int64_t y0 = s_y0[w * G + kk];
         const int LY = s_ly[w * G + kk];
-        // task = (entry t of Y's row, row DOFs [a0, a1)): a whole block per thread while the row fits the group
-        // in one pass that way, one row DOF per thread otherwise
+        const double* xrow = xvals + DD * x0 + (int64_t)kx * D;   // + a*LX*D + b
+        // task = (entry t of Y's row, row DOFs): a whole block per thread while the row fits the group in one pass
+        // that way, one row DOF per thread otherwise
         const bool whole = LY * D > G && LY <= G;
-        const int per = whole ? 1 : D;
-        for (int o = lane; o < LY * per; o += G) {
-          const int t = o / per;
-          const int a0 = whole ? 0 : o - t * per, a1 = whole ? D : a0 + 1;
+        const int ntask = whole ? LY : LY * D;
+        for (int o = lane; o < ntask; o += G) {
+          const int t = whole ? o : o / D;
+          const int a0 = whole ? 0 : o - t * D, a1 = whole ? D : a0 + 1;
           const int key = ycol[y0 + t];
+          const double* yb0 = yvals + DD * y0 + (int64_t)t * D;     // + b*LY*D + c
           double yb[D][D];
 #pragma unroll
           for (int b = 0; b < D; ++b)
 #pragma unroll
-            for (int c = 0; c < D; ++c) yb[b][c] = yvals[DD * y0 + ((int64_t)b * LY + t) * D + c];
-          int lo = 0, hi = m - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cc[mid] < key) lo = mid + 1; else hi = mid;
+            for (int c = 0; c < D; ++c) yb[b][c] = yb0[(int64_t)b * LY * D + c];
+          int pos;
+          if constexpr (HASH) {
+            unsigned h = ((unsigned)key * 2654435761u) & (unsigned)(HT - 1);
+            long long entry = table[h];
+            while ((int)(entry >> 32) != key) {
+              h = (h + 1) & (unsigned)(HT - 1);
+              entry = table[h];
+            }
+            pos = (int)(entry & 0xffffffffll);
+          } else {
+            pos = find_sorted(cc, m, key);
           }
+          double* dst = acc + pos * DD;
           for (int a = a0; a < a1; ++a) {
             double xa[D];
 #pragma unroll
-            for (int b = 0; b < D; ++b) xa[b] = xvals[DD * x0 + ((int64_t)a * LX + kx) * D + b];
+            for (int b = 0; b < D; ++b) xa[b] = xrow[(int64_t)a * LX * D + b];
 #pragma unroll
             for (int c = 0; c < D; ++c) {
               double sum = 0.0;
 #pragma unroll
               for (int b = 0; b < D; ++b) sum = fma(xa[b], yb[b][c], sum);
-              acc[lo * DD + a * D + c] += sum;
+              dst[a * D + c] += sum;
             }
           }
         }
@@ -1126,17 +1164,22 @@ template <int D, int G>
 static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xcol, const double* xvals,
                              const int64_t* yptr, const int32_t* ycol, const double* yvals, const int64_t* cptr,
                              const int32_t* ccol, double* cvals, int max_row, cudaStream_t st) {
-  const size_t per_group = (size_t)max_row * (D * D * sizeof(double) + sizeof(int));
+  int ht = 0;  // hash-table entries per warp (warp variant only): power of two >= 2 max_row
+  if (G == 32) {
+    ht = 16;
+    while (ht < 2 * max_row) ht <<= 1;
+  }
+  const size_t per_group = (size_t)max_row * (D * D * sizeof(double) + sizeof(int)) + (size_t)ht * sizeof(long long);
   if (per_group > 200 * 1024) {
     set_last_error("capacity", "amg_spgemm_numeric: a product row does not fit in shared memory");
     return TFEM_ERR_CAPACITY;
   }
   int W = 256 / G;
   if (G == 32) {
-    const int fit = (int)((40 * 1024) / (per_group ? per_group : 1));  // ~5 CTAs per SM
+    const int fit = (int)((48 * 1024) / (per_group ? per_group : 1));  // ~4 CTAs per SM
     W = fit < 1 ? 1 : (fit > 8 ? 8 : fit);
   }
-  const size_t smem = W * per_group + 16;
+  const size_t smem = W * per_group + 32;
   if (smem > 48 * 1024)
     TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_num<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
   int per_sm = 1;
@@ -1145,7 +1188,7 @@ static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
   const int64_t want = (nx + W - 1) / W;
   const int64_t cap = (int64_t)num_sms() * per_sm;
   k_spgemm_num<D, G><<<(unsigned)(want < cap ? want : cap), W * G, smem, st>>>(nx, xptr, xcol, xvals, yptr, ycol,
-                                                                               yvals, cptr, ccol, cvals, max_row);
+                                                                               yvals, cptr, ccol, cvals, max_row, ht);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -1159,7 +1202,7 @@ extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, c
                "amg_spgemm_numeric: bad arguments");
   TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
   // a warp per row cannot hold rows whose accumulators exceed ~40 KB: those go to the CTA-per-row variant too
-  const bool cta = threads_per_row > 32 || (size_t)max_row * (d * d * 8 + 4) > 20 * 1024;
+  const bool cta = threads_per_row > 32 || (size_t)max_row * (d * d * 8 + 4 + 32) > 24 * 1024;
 #define TFEM_SPGEMM_CASE(D)                                                                                         \
   if (d == D)                                                                                                       \
     return cta ? spgemm_num_launch<D, 256>(nx, xptr, xcol, xvals, yptr, ycol, yvals, cptr, ccol, cvals, max_row, st) \
