@@ -361,16 +361,20 @@ int tfem_dcg_solve(void* comm, const tfem_sell_t* A_local, int64_t row_lo, int64
 int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, double* vals_dev,
                       int fix_zero_diag, double* dinv_dev, uint8_t* iso_dev, void* stream);
 
-/* Aggregation: maximal independent set of the node graph in Luby rounds with fixed pseudo-random keys, then every
- * node joins the adjacent root with the largest key; aggregates are numbered in root order. agg_dev: int32 [nb] out.
- * state_work int8 [nb], flag_work uint8 [nb], index_work int32 [nb]: scratch. Synchronises (one flag per round). */
-int tfem_amg_aggregate(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, int8_t* state_work_dev,
-                       uint8_t* flag_work_dev, int32_t* index_work_dev, int32_t* agg_dev, int64_t* n_agg_host,
-                       int32_t* rounds_host, void* stream);
+/* Aggregation: maximal independent set of the node graph in Luby rounds with fixed pseudo-random keys; aggregates are
+ * numbered in root order. distance = 1: roots pairwise non-adjacent, every node joins the adjacent root with the
+ * largest key (radius-1 aggregates, ~12 nodes on Hexa1). distance = 2: roots more than two steps apart, nodes one step
+ * from a root join it, the others join the aggregate of their neighbour with the largest key (radius-2 aggregates: for
+ * graphs of low degree such as Tetra1, where radius 1 gives ~3 nodes per aggregate and the coarse operators fill in).
+ * agg_dev: int32 [nb] out. state_work int8 [nb], flag_work uint8 [nb], index_work int32 [nb]: scratch. Synchronises
+ * (one flag per round). */
+int tfem_amg_aggregate(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, int distance,
+                       int8_t* state_work_dev, uint8_t* flag_work_dev, int32_t* index_work_dev, int32_t* agg_dev,
+                       int64_t* n_agg_host, int32_t* rounds_host, void* stream);
 
 /* Smoothed prolongator P = (I - omega D^-1 A) T, T[i, agg(i)] = diag(1 - iso_i). count: pptr_dev int64 [nb+1] out
  * (offsets); fill: pcol_dev int32 [pptr[nb]] (sorted per row), pvals_dev double [d*d*pptr[nb]].
- * TFEM_ERR_CAPACITY if a node has more than 1024 neighbours. */
+ * TFEM_ERR_CAPACITY if a node has more than 768 neighbours or touches more than 255 aggregates. */
 int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,
                                const int32_t* agg_dev, int64_t* pptr_dev, void* stream);
 int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,

@@ -17,7 +17,9 @@ the choices below — step by step, so that the CUDA kernels can be checked agai
     Dirichlet rows after the reference's masking, base.py:414-419);
   * aggregation = maximal independent set of the node graph with fixed pseudo-random priorities (parallel,
     deterministic): every root collects the neighbours that prefer it (largest key). Aggregates have radius 1, which
-    is what one step of prolongator smoothing can cover (distance-2 sets were tried: 37 instead of 23 iterations);
+    is what one step of prolongator smoothing can cover (distance-2 sets on Hexa1: 37 instead of 23 iterations);
+    where radius 1 gives fewer than 6 nodes per aggregate (graphs of low degree: Tetra1) the distance-2 variant is
+    used instead (Tetra1 20^3: operator complexity 3.2 -> 1.15, 22 -> 33 iterations);
   * prolongator smoothing P = (I - w D^-1 A) T, w = 4 / (3 rho), rho = spectral-radius estimate of D^-1 A
     (power iteration with a fixed start vector, times a safety factor);
   * Galerkin coarse operator A_c = P^T A P; zero diagonal entries (aggregates made of isolated DOFs only) become 1;
@@ -31,6 +33,7 @@ import scipy.sparse as sp
 
 POWER_ITS = 8
 RHO_SAFETY = 1.15
+MIN_AGG_SIZE = 6          # nodes per aggregate below which radius-2 aggregates replace radius-1 ones
 MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 
@@ -74,6 +77,36 @@ def mis_aggregate(ptr: np.ndarray, adj: np.ndarray):
     best = _seg_max(np.where(is_root, key, np.uint64(0))[adj], ptr)      # key of the chosen root
     root = (best & np.uint64(0xFFFFFFFF)).astype(np.int64) - 1
     return agg_of_root[root].astype(np.int32), int(is_root.sum()), rounds
+
+
+def mis2_aggregate(ptr: np.ndarray, adj: np.ndarray):
+    """The distance-2 variant for graphs of low degree (Tetra1: radius-1 aggregates hold ~3 nodes there and the coarse
+    operators fill in): roots are more than two steps apart (largest key among the undecided nodes within distance
+    2), nodes one step from a root join it, the others join the aggregate of their neighbour with the largest key."""
+    n = len(ptr) - 1
+    ids = np.arange(n, dtype=np.uint64)
+    key = (hash32(ids) << np.uint64(32)) | (ids + np.uint64(1))
+    state = np.zeros(n, dtype=np.int8)
+    rounds = 0
+    while (state == 0).any():
+        k = np.where(state == 0, key, np.uint64(0))
+        t1 = np.maximum(_seg_max(k[adj], ptr), k)
+        new_root = (state == 0) & (np.maximum(_seg_max(t1[adj], ptr), t1) == key)
+        state[new_root] = 1
+        near1 = new_root | (_seg_max(new_root[adj].astype(np.int8), ptr) > 0)
+        near2 = near1 | (_seg_max(near1[adj].astype(np.int8), ptr) > 0)
+        state[(state == 0) & near2] = 2
+        rounds += 1
+    is_root = state == 1
+    agg_of_root = np.cumsum(is_root) - 1
+    best = np.maximum(_seg_max(np.where(is_root, key, np.uint64(0))[adj], ptr), np.where(is_root, key, np.uint64(0)))
+    root = (best & np.uint64(0xFFFFFFFF)).astype(np.int64) - 1
+    agg1 = np.where(root >= 0, agg_of_root[np.maximum(root, 0)], -1)
+    best2 = _seg_max(np.where(agg1 >= 0, key, np.uint64(0))[adj], ptr)
+    nb = (best2 & np.uint64(0xFFFFFFFF)).astype(np.int64) - 1
+    agg = np.where(agg1 >= 0, agg1, agg1[np.maximum(nb, 0)])
+    assert (agg >= 0).all()
+    return agg.astype(np.int32), int(is_root.sum()), rounds
 
 
 def block_graph(A: sp.csr_matrix, d: int):
@@ -134,7 +167,8 @@ class Level:
     pass
 
 
-def build_hierarchy(A: sp.csr_matrix, d: int, max_coarse=MAX_COARSE_DOFS, max_levels=MAX_LEVELS):
+def build_hierarchy(A: sp.csr_matrix, d: int, max_coarse=MAX_COARSE_DOFS, max_levels=MAX_LEVELS,
+                    aggregation: str = "auto"):
     levels = []
     while True:
         L = Level()
@@ -147,7 +181,12 @@ def build_hierarchy(A: sp.csr_matrix, d: int, max_coarse=MAX_COARSE_DOFS, max_le
         L.rho = rho_estimate(A, L.dinv)
         L.omega = 4.0 / (3.0 * L.rho)
         ptr, adj, Gb = block_graph(A, d)
-        agg, n_agg, _ = mis_aggregate(ptr, adj)
+        n_nod = L.n // d
+        L.agg_distance = 2 if aggregation == "mis2" else 1
+        agg, n_agg, _ = (mis2_aggregate if aggregation == "mis2" else mis_aggregate)(ptr, adj)
+        if aggregation == "auto" and n_nod < MIN_AGG_SIZE * n_agg:
+            agg, n_agg, _ = mis2_aggregate(ptr, adj)
+            L.agg_distance = 2
         if n_agg * d >= 0.8 * L.n:          # coarsening stalled
             break
         L.agg, L.n_agg = agg, n_agg

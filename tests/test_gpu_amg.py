@@ -32,6 +32,7 @@ def _compare_hierarchy(amg, lv_ref, tol=1e-11):
         if ref is lv_ref[-1]:
             break
         assert abs(lv.rho - ref.rho) <= 1e-9 * ref.rho
+        assert lv.agg_distance == ref.agg_distance
         assert np.array_equal(lv.agg.cpu().numpy()[: lv.op.nbr], ref.agg) and lv.n_agg == ref.n_agg
         P, R = lv.P.to_scipy(), lv.R.to_scipy()
         Pd, Pr = P.toarray(), ref.P.toarray()
@@ -89,7 +90,8 @@ def _spd_on_pattern(c, n, seed=3):
 
 
 @pytest.mark.parametrize("tag,max_coarse", [("heat_hexa1", 10), ("heat_hexa1", 100), ("quad1", 12), ("tetra2", 40),
-                                            ("hexa2", 40), ("hexa1_orphan", 20), ("heat_tetra2", 20)])
+                                            ("hexa2", 40), ("hexa1_orphan", 20), ("heat_tetra2", 20), ("tetra1", 20),
+                                            ("tria1", 10)])
 @pytest.mark.parametrize("layout", ["auto", "sell"])
 def test_hierarchy_other_block_sizes(T, tag, max_coarse, layout, monkeypatch):
     """d = 1 (heat, and the scalar fall-back for patterns with unreferenced nodes), d = 2 (planar), longer rows, and a
@@ -120,6 +122,23 @@ def test_hierarchy_other_block_sizes(T, tag, max_coarse, layout, monkeypatch):
     assert abs(info["iterations"] - its_ref) <= 1
     assert np.linalg.norm(A_ref @ x.cpu().numpy() - b) <= 1e-9 * np.linalg.norm(b)
     assert rel(x.cpu().numpy(), x_ref) <= 1e-8
+
+
+@pytest.mark.parametrize("aggregation", ["mis1", "mis2"])
+def test_aggregation_variants_match_oracle(T, tables, aggregation):
+    """Radius-1 and radius-2 aggregates forced on the Hexa1 cube (the automatic rule picks radius 2 only where
+    radius 1 leaves fewer than 6 nodes per aggregate, e.g. on the Tetra1 fixture above)."""
+    from torchfem_b200.amg import AMGPreconditioner
+
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 9, tables)
+    A = p.matrix(A.values_)
+    amg = AMGPreconditioner(A, max_coarse=100, aggregation=aggregation)
+    A_ref = O.to_csr(A.values_.cpu().numpy(), p.glob_idx.cpu().numpy(), p.n_dofs)
+    lv_ref = M.build_hierarchy(A_ref, 3, max_coarse=100, aggregation=aggregation)
+    assert amg.levels[0].agg_distance == (1 if aggregation == "mis1" else 2)
+    _compare_hierarchy(amg, lv_ref)
+    r = np.random.default_rng(1).standard_normal(p.n_dofs)
+    assert rel(amg.apply(dev(r)).cpu().numpy(), M.vcycle(lv_ref, r)) <= 1e-10
 
 
 def test_amgx_method_reproduces_reference_solution_config_a(T, tables):

@@ -31,6 +31,7 @@ RHO_SAFETY = 1.15
 MAX_COARSE_DOFS = 1500
 MAX_LEVELS = 12
 DENSE_LIMIT = 12000  # largest coarsest level a dense inverse is accepted for
+MIN_AGG_SIZE = 6        # nodes per aggregate below which radius-2 aggregates replace radius-1 ones (aggregation="auto")
 BCSR_MAX_ROWS = int(os.environ.get("TFEM_AMG_BCSR_MAX_ROWS", 20000))   # operators with fewer block rows than this ...
 BCSR_MIN_AVG = int(os.environ.get("TFEM_AMG_BCSR_MIN_AVG", 48))         # ... or more blocks per row than this are
 #                                                                         streamed as block CSR instead of SELL-32
@@ -183,11 +184,16 @@ class AMGPreconditioner:
     (sparse.py:438-441): passing it back refreshes the coefficients (`resetup`) on the stored aggregates/patterns."""
 
     def __init__(self, A: CSRMatrix, max_coarse: int = MAX_COARSE_DOFS, max_levels: int = MAX_LEVELS,
-                 power_its: int = POWER_ITS, rho_safety: float = RHO_SAFETY):
+                 power_its: int = POWER_ITS, rho_safety: float = RHO_SAFETY, aggregation: str | None = None):
         if not isinstance(A, CSRMatrix):
             raise TypeError("the AMG preconditioner needs an assembled CSRMatrix")
         self.max_coarse, self.max_levels = int(max_coarse), min(int(max_levels), 16)
         self.power_its, self.rho_safety = int(power_its), float(rho_safety)
+        if aggregation is None:
+            aggregation = os.environ.get("TFEM_AMG_AGGREGATION", "auto")
+        if aggregation not in ("auto", "mis1", "mis2"):
+            raise ValueError("aggregation must be 'auto', 'mis1' or 'mis2'")
+        self.aggregation = aggregation
         self.shape = (A.n, A.n)
         self.n = A.n
         self.device = A.device
@@ -203,8 +209,13 @@ class AMGPreconditioner:
         agg = _empty(nb, torch.int32, dev)
         state, flag, index = _empty(nb, torch.int8, dev), _empty(nb, torch.uint8, dev), _empty(nb, torch.int32, dev)
         n_agg, rounds = ctypes.c_int64(0), ctypes.c_int32(0)
-        L.check(L.lib.tfem_amg_aggregate(nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(state), L.ptr(flag), L.ptr(index),
-                                         L.ptr(agg), ctypes.byref(n_agg), ctypes.byref(rounds), st))
+        # radius-1 aggregates; on graphs of low degree (Tetra1: ~3 nodes per aggregate) radius 2 instead
+        for distance in ((1, 2) if self.aggregation == "auto" else ((1,) if self.aggregation == "mis1" else (2,))):
+            L.check(L.lib.tfem_amg_aggregate(nb, L.ptr(op.bptr), L.ptr(op.bcol), distance, L.ptr(state), L.ptr(flag),
+                                             L.ptr(index), L.ptr(agg), ctypes.byref(n_agg), ctypes.byref(rounds), st))
+            lv.agg_distance = distance
+            if nb >= MIN_AGG_SIZE * n_agg.value:
+                break
         if n_agg.value * d >= 0.8 * lv.n:
             return False
         lv.agg, lv.n_agg, lv.mis_rounds = agg, int(n_agg.value), int(rounds.value)

@@ -29,7 +29,8 @@
 namespace tfem {
 namespace {
 
-constexpr int kRowCap = 1024;  // blocks per block row the prolongator kernel can hold in shared memory
+constexpr int kRowCap = 768;   // blocks per block row the prolongator kernel can hold in shared memory
+constexpr int kAggCap = 256;   // distinct aggregates one row of P may touch (+1)
 
 __device__ __forceinline__ uint32_t hash32(uint32_t h) {  // MurmurHash3 finaliser, as oracle/amg_oracle.py
   h += 0x9E3779B9u;
@@ -170,6 +171,81 @@ __global__ void k_mis_assign(int64_t nb, const int64_t* __restrict__ bptr, const
   agg[i] = root >= 0 ? root_index[root] : -1;
 }
 
+// distance-2 variant (graphs of low degree — Tetra1: a radius-1 aggregate holds only ~3 nodes there, the coarse
+// operators fill in and the complexity explodes; radius-2 aggregates hold ~20): a node becomes a root if its key is
+// the largest among the undecided nodes within distance 2, everything within distance 2 of a root is covered.
+__global__ void k_mis2_t1(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                          const int8_t* __restrict__ state, unsigned long long* __restrict__ t1) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  unsigned long long best = state[i] == 0 ? mis_key(i) : 0ull;
+  for (int64_t k = bptr[i]; k < bptr[i + 1]; ++k) {
+    const int32_t j = bcol[k];
+    if (state[j] == 0) {
+      const unsigned long long kj = mis_key(j);
+      if (kj > best) best = kj;
+    }
+  }
+  t1[i] = best;
+}
+__global__ void k_mis2_select(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                              const int8_t* __restrict__ state, const unsigned long long* __restrict__ t1,
+                              uint8_t* __restrict__ newroot) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  uint8_t nr = 0;
+  if (state[i] == 0) {
+    const unsigned long long me = mis_key(i);
+    nr = t1[i] == me ? 1 : 0;
+    for (int64_t k = bptr[i]; nr && k < bptr[i + 1]; ++k)
+      if (t1[bcol[k]] > me) nr = 0;
+  }
+  newroot[i] = nr;
+}
+__global__ void k_mis2_near(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                            const uint8_t* __restrict__ newroot, uint8_t* __restrict__ near1) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  uint8_t c = newroot[i];
+  for (int64_t k = bptr[i]; !c && k < bptr[i + 1]; ++k) c = newroot[bcol[k]];
+  near1[i] = c;
+}
+__global__ void k_mis2_apply(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                             int8_t* __restrict__ state, const uint8_t* __restrict__ newroot,
+                             const uint8_t* __restrict__ near1, int* n_undecided) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb || state[i] != 0) return;
+  if (newroot[i]) {
+    state[i] = 1;
+    return;
+  }
+  uint8_t c = near1[i];
+  for (int64_t k = bptr[i]; !c && k < bptr[i + 1]; ++k) c = near1[bcol[k]];
+  if (c) state[i] = 2;
+  else atomicAdd(n_undecided, 1);
+}
+// nodes two steps away from every root join the aggregate of the neighbour (one step from a root) with the largest key
+__global__ void k_mis2_assign_far(int64_t nb, const int64_t* __restrict__ bptr, const int32_t* __restrict__ bcol,
+                                  const int32_t* __restrict__ agg1, int32_t* __restrict__ agg) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nb) return;
+  int32_t a = agg1[i];
+  if (a < 0) {
+    unsigned long long best = 0ull;
+    for (int64_t k = bptr[i]; k < bptr[i + 1]; ++k) {
+      const int32_t j = bcol[k];
+      if (agg1[j] >= 0) {
+        const unsigned long long kj = mis_key(j);
+        if (kj > best) {
+          best = kj;
+          a = agg1[j];
+        }
+      }
+    }
+  }
+  agg[i] = a;
+}
+
 // ------------------------------------------------------------------------------------------ K13 prolongator
 // One warp per fine node: the distinct aggregates of its neighbours, sorted (rank by counting in shared memory),
 // then  P[i,J] = delta(J, agg i) diag(1-iso_i) - w Dinv_i sum_{j in adj(i), agg j = J} A_ij diag(1-iso_j)
@@ -182,10 +258,10 @@ __global__ void __launch_bounds__(128)
                   int64_t* __restrict__ pcount, const int64_t* __restrict__ pptr, int32_t* __restrict__ pcol,
                   double* __restrict__ pvals, int* err) {
   __shared__ int s_key[4][kRowCap];
-  __shared__ int s_ukey[4][FILL ? 128 : 1];
+  __shared__ int s_ukey[4][FILL ? kAggCap : 1];
   __shared__ short s_rank[4][kRowCap];
   __shared__ unsigned char s_first[4][kRowCap];
-  __shared__ int s_start[4][FILL ? 128 : 1];   // FILL: m <= 127 distinct aggregates per row (checked below)
+  __shared__ int s_start[4][FILL ? kAggCap : 1];   // FILL: m < kAggCap distinct aggregates per row (checked below)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t I = blockIdx.x * 4ll + w;
   if (I >= nb) return;
@@ -215,7 +291,7 @@ __global__ void __launch_bounds__(128)
     if (lane == 0) pcount[I] = m;
     return;
   }
-  if (m > 127) {
+  if (m > kAggCap - 1) {
     if (lane == 0) *err = 2;
     return;
   }
@@ -979,33 +1055,57 @@ extern "C" int tfem_amg_rho(const tfem_amg_operator_t* a, const double* dinv, in
   return TFEM_OK;
 }
 
-extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t* bcol, int8_t* state_work,
-                                  uint8_t* flag_work, int32_t* index_work, int32_t* agg, int64_t* n_agg_host,
-                                  int32_t* rounds_host, void* stream_) {
+extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t* bcol, int distance,
+                                  int8_t* state_work, uint8_t* flag_work, int32_t* index_work, int32_t* agg,
+                                  int64_t* n_agg_host, int32_t* rounds_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   TFEM_REQUIRE(bptr && bcol && state_work && flag_work && index_work && agg && n_agg_host && nb > 0,
                "amg_aggregate: bad arguments");
+  TFEM_REQUIRE(distance == 1 || distance == 2, "amg_aggregate: distance must be 1 or 2");
   TFEM_REQUIRE(nb < (int64_t)INT32_MAX, "amg_aggregate: too many nodes");
   int* counter = nullptr;
+  unsigned long long* t1 = nullptr;
+  uint8_t* near1 = nullptr;
+  int32_t* agg1 = nullptr;
   TFEM_CUDA(malloc_async(&counter, sizeof(int), st));
+  if (distance == 2) {
+    TFEM_CUDA(malloc_async(&t1, nb * sizeof(unsigned long long), st));
+    TFEM_CUDA(malloc_async(&near1, nb, st));
+    TFEM_CUDA(malloc_async(&agg1, nb * sizeof(int32_t), st));
+  }
+  auto release = [&]() {
+    cudaFreeAsync(counter, st);
+    if (t1) cudaFreeAsync(t1, st);
+    if (near1) cudaFreeAsync(near1, st);
+    if (agg1) cudaFreeAsync(agg1, st);
+  };
   TFEM_CUDA(cudaMemsetAsync(state_work, 0, nb, st));
   const unsigned grid = grid_for(nb, 256);
   int rounds = 0, undecided = 1;
   while (undecided > 0) {
     if (rounds >= 200) {  // Luby rounds finish in O(log n) with overwhelming probability
-      cudaFreeAsync(counter, st);
+      release();
       set_last_error("capacity", "amg_aggregate: independent set did not finish in 200 rounds");
       return TFEM_ERR_CAPACITY;
     }
     TFEM_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    k_mis_select<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work);
-    k_mis_apply<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work, counter);
+    if (distance == 1) {
+      k_mis_select<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work);
+      k_mis_apply<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work, counter);
+    } else {
+      k_mis2_t1<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, t1);
+      k_mis2_select<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, t1, flag_work);
+      k_mis2_near<<<grid, 256, 0, st>>>(nb, bptr, bcol, flag_work, near1);
+      k_mis2_apply<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, flag_work, near1, counter);
+    }
     TFEM_LAUNCH_CHECK();
     int rc = read_flag(counter, &undecided, st);
-    if (rc != TFEM_OK) return rc;
+    if (rc != TFEM_OK) {
+      release();
+      return rc;
+    }
     ++rounds;
   }
-  TFEM_CUDA(cudaFreeAsync(counter, st));
   k_mis_flags<<<grid, 256, 0, st>>>(nb, state_work, index_work);
   TFEM_LAUNCH_CHECK();
   int32_t last_flag = 0, last_idx = 0;
@@ -1017,9 +1117,15 @@ extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t
   TFEM_CUDA(cub::DeviceScan::ExclusiveSum(tmp, bytes, index_work, index_work, (int)nb, st));
   TFEM_CUDA(cudaFreeAsync(tmp, st));
   TFEM_CUDA(cudaMemcpyAsync(&last_idx, index_work + nb - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  k_mis_assign<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, index_work, agg);
+  if (distance == 1) {
+    k_mis_assign<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, index_work, agg);
+  } else {
+    k_mis_assign<<<grid, 256, 0, st>>>(nb, bptr, bcol, state_work, index_work, agg1);
+    k_mis2_assign_far<<<grid, 256, 0, st>>>(nb, bptr, bcol, agg1, agg);
+  }
   TFEM_LAUNCH_CHECK();
   TFEM_CUDA(cudaStreamSynchronize(st));
+  release();
   *n_agg_host = (int64_t)last_idx + last_flag;
   if (rounds_host) *rounds_host = rounds;
   return TFEM_OK;
@@ -1042,8 +1148,8 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
   cudaFreeAsync(err, st);
   if (rc != TFEM_OK) return rc;
   if (h) {
-    set_last_error("capacity", h == 1 ? "amg_prolongator: a node has more than 1024 neighbours"
-                                      : "amg_prolongator: a node touches more than 127 aggregates");
+    set_last_error("capacity", h == 1 ? "amg_prolongator: a node has more than 768 neighbours"
+                                      : "amg_prolongator: a node touches more than 255 aggregates");
     return TFEM_ERR_CAPACITY;
   }
   return TFEM_OK;
