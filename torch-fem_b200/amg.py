@@ -339,8 +339,8 @@ class AMGPreconditioner:
     def resetup(self, A: CSRMatrix) -> None:
         """New coefficients: on the same sparsity pattern only the numeric phase is repeated (aggregates, patterns of
         P / R / A_c and the SELL structures are kept) — AmgX `resetup` in the reference (sparse.py:440-441)."""
-        if (A.values_.data_ptr(), A.values_._version) == self._values_key:
-            return   # the very same coefficients (e.g. the adjoint solve with the converged tangent)
+        if A is self._A and (A.values_.data_ptr(), A.values_._version) == self._values_key:
+            return   # the very same matrix object and coefficients (e.g. the adjoint solve with the converged tangent)
         same = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n) == self._pattern_key
         self._setup(A, symbolic=not same)
 
