@@ -783,14 +783,53 @@ extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
   return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
 }
 
+// A batch of `check_every` Krylov iterations captured once into a CUDA graph and replayed: below a few hundred
+// thousand unknowns the three (CG) / five (MINRES) kernels of an iteration take less time than their launches, and a
+// graph launch removes the per-kernel launch gap. Stream capture is not possible on the legacy default stream (which is
+// what torch hands over by default), so such solves run on a private non-blocking stream fenced with an event.
+struct BatchGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  ~BatchGraph() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+constexpr int64_t kGraphMaxRows = 3000000;  // larger systems are bandwidth-bound: launch gaps do not matter there
+
+static cudaStream_t private_stream() {
+  static thread_local cudaStream_t ps = nullptr;
+  if (!ps && cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking) != cudaSuccess) ps = nullptr;
+  return ps;
+}
+
 static int krylov_solve_impl(int method, const Op& A, const double* dinv, const double* b, const double* x0,
                              double rtol, double atol, int64_t maxiter, int check_every, double* x,
-                             double* work, double* info, cudaStream_t st) {
+                             double* work, double* info, cudaStream_t st_caller) {
   TFEM_REQUIRE(dinv && b && x && work && info, "krylov_solve: null pointer");
   TFEM_REQUIRE(method == TFEM_METHOD_CG || method == TFEM_METHOD_MINRES, "krylov_solve: unknown method");
   const int64_t n = A.n;
   if (maxiter <= 0) maxiter = (method == TFEM_METHOD_CG ? 10 : 5) * n;
   if (check_every <= 0) check_every = 32;
+
+  // work stream: the caller's, unless batches are to be replayed as graphs and the caller's stream cannot capture
+  static const bool graphs_off = getenv("TFEM_CG_GRAPH") && atoi(getenv("TFEM_CG_GRAPH")) == 0;
+  bool use_graph = !graphs_off && n <= kGraphMaxRows;
+  cudaStream_t st = st_caller;
+  if (use_graph && (st_caller == nullptr || st_caller == cudaStreamLegacy)) {
+    cudaStream_t ps = private_stream();
+    cudaEvent_t ev = nullptr;
+    if (ps && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      TFEM_CUDA(cudaEventRecord(ev, st_caller));
+      TFEM_CUDA(cudaStreamWaitEvent(ps, ev, 0));
+      TFEM_CUDA(cudaEventDestroy(ev));
+      st = ps;  // the solve ends with a host synchronisation of this stream, so the caller sees finished results
+    } else {
+      use_graph = false;
+    }
+  }
+  BatchGraph bg;
 
   Work w = carve(work, n);
   const int vg = vec_grid(n);
@@ -808,52 +847,60 @@ static int krylov_solve_impl(int method, const Op& A, const double* dinv, const 
     spmvs += 1;
     launches += 1;
   }
+  const int per_it = method == TFEM_METHOD_CG ? 3 : 5;
+  auto iteration = [&]() -> int {
+    if (method == TFEM_METHOD_CG) {
+      int rc = apply_op<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
+      if (rc != TFEM_OK) return rc;
+      k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket, nullptr);
+      k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
+    } else {
+      // MINRES vectors: r1=w.r, r2=w.p, y=w.q, v, w1, w2
+      k_mr_v<<<vg, kVecThreads, 0, st>>>(n, w.y, w.v, w.sc);
+      int rc = apply_op<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
+      if (rc != TFEM_OK) return rc;
+      k_mr_alfa<<<vg, kVecThreads, 0, st>>>(n, w.v, w.y, w.r1, w.sc, w.partials, w.ticket);
+      k_mr_lanczos<<<vg, kVecThreads, 0, st>>>(n, dinv, w.y, w.r1, w.r2, w.sc, rtol, w.partials, w.ticket);
+      k_mr_xupdate<<<vg, kVecThreads, 0, st>>>(n, w.v, w.w1, w.w2, x, w.sc, rtol, (double)maxiter, w.partials, w.ticket);
+    }
+    return TFEM_OK;
+  };
   double sc_host[SC_COUNT];
   int64_t issued = 0;
-  if (method == TFEM_METHOD_CG) {
+  if (method == TFEM_METHOD_CG)
     k_cg_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r, w.p, w.sc, rtol, atol, w.partials, w.ticket, nullptr);
-    TFEM_LAUNCH_CHECK();
-    launches += 2;
-    while (true) {
-      TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
-      TFEM_CUDA(cudaStreamSynchronize(st));
-      if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
-      int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
-      for (int64_t it = 0; it < batch; ++it) {
-        int rc = apply_op<true>(A, w.p, w.q, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
-        if (rc != TFEM_OK) return rc;
-        k_cg_update<<<vg, kVecThreads, 0, st>>>(n, w.p, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket, nullptr);
-        k_cg_direction<<<vg, kVecThreads, 0, st>>>(n, w.r, dinv, w.p, w.sc);
-      }
-      TFEM_LAUNCH_CHECK();
-      issued += batch;
-      launches += 3.0 * batch;
-      spmvs += batch;
-    }
-  } else {
-    // MINRES vectors: r1=w.r, r2=w.p, y=w.q, v, w1, w2
+  else  // the first SpMV consumes q0's storage (y), which k_mr_init has already folded into r1
     k_mr_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r1, w.r2, w.y, w.w1, w.w2, w.sc, w.partials, w.ticket);
-    TFEM_LAUNCH_CHECK();
-    launches += 2;
-    // the first SpMV consumes q0's storage (y), which k_mr_init has already folded into r1
-    while (true) {
-      TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
-      TFEM_CUDA(cudaStreamSynchronize(st));
-      if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
-      int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
-      for (int64_t it = 0; it < batch; ++it) {
-        k_mr_v<<<vg, kVecThreads, 0, st>>>(n, w.y, w.v, w.sc);
-        int rc = apply_op<true>(A, w.v, w.y, w.sc, w.partials, w.ticket, w.sc + SC_PQ, st);
+  TFEM_LAUNCH_CHECK();
+  launches += 2;
+  while (true) {
+    TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
+    TFEM_CUDA(cudaStreamSynchronize(st));
+    if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
+    const int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
+    // the first batch is launched kernel by kernel (it also runs the one-time occupancy queries); full batches after
+    // it replay the captured graph
+    if (use_graph && issued > 0 && batch == check_every) {
+      if (!bg.exec) {
+        TFEM_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = TFEM_OK;
+        for (int64_t it = 0; it < batch && rc == TFEM_OK; ++it) rc = iteration();
+        const cudaError_t ce = cudaStreamEndCapture(st, &bg.graph);
         if (rc != TFEM_OK) return rc;
-        k_mr_alfa<<<vg, kVecThreads, 0, st>>>(n, w.v, w.y, w.r1, w.sc, w.partials, w.ticket);
-        k_mr_lanczos<<<vg, kVecThreads, 0, st>>>(n, dinv, w.y, w.r1, w.r2, w.sc, rtol, w.partials, w.ticket);
-        k_mr_xupdate<<<vg, kVecThreads, 0, st>>>(n, w.v, w.w1, w.w2, x, w.sc, rtol, (double)maxiter, w.partials, w.ticket);
+        TFEM_CUDA(ce);
+        TFEM_CUDA(cudaGraphInstantiate(&bg.exec, bg.graph, 0));
+      }
+      TFEM_CUDA(cudaGraphLaunch(bg.exec, st));
+    } else {
+      for (int64_t it = 0; it < batch; ++it) {
+        int rc = iteration();
+        if (rc != TFEM_OK) return rc;
       }
       TFEM_LAUNCH_CHECK();
-      issued += batch;
-      launches += 5.0 * batch;
-      spmvs += batch;
     }
+    issued += batch;
+    launches += (double)per_it * batch;
+    spmvs += batch;
   }
   info[0] = sc_host[SC_ITERS];
   info[1] = sqrt(sc_host[SC_RR]);
