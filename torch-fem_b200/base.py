@@ -752,7 +752,7 @@ class Heat(FEM, ABC):
             print(f"torch-fem_b200 | time integration | {type(self).__name__} | {self.n_dofs:,} dof | "
                   f"{n_steps - 1} steps | dt <= {delta_t:g} | {describe_method(self.n_dofs, 'cuda', method)}")
 
-        sys_cache = (None, None)
+        sys_cache = (None, None, None, None)
         for n in range(1, n_steps):
             u_guess = u[n - 1].clone()
             dt_n = dts[n - 1]
@@ -781,10 +781,9 @@ class Heat(FEM, ABC):
                 # the system matrix M + dt/2 K (reference base.py:1513 re-forms it in every iteration) is kept while
                 # the step size and both matrices are unchanged: its SELL copy — and, with method="amgx", the
                 # refreshed hierarchy — are then reused by every step
-                sys_key = (float(dt_n), id(self.M), id(self.K))
-                if sys_cache[0] != sys_key:
-                    sys_cache = (sys_key, self.M + 0.5 * dt_n * self.K)
-                step = differentiable_sparse_solve(sys_cache[1], -residual, B, stol, device, method,
+                if not (sys_cache[0] == float(dt_n) and sys_cache[1] is self.M and sys_cache[2] is self.K):
+                    sys_cache = (float(dt_n), self.M, self.K, self.M + 0.5 * dt_n * self.K)
+                step = differentiable_sparse_solve(sys_cache[3], -residual, B, stol, device, method,
                                                    None, cached, it == 0)
                 u_guess = u_guess + step.reshape(-1, dpn)
             if res_norm > rtol * res_norm0 and res_norm > atol:
