@@ -102,6 +102,7 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
     out_device = b.device
     Ac = _as_csr(A)
     rhs = b.detach().to(device=Ac.device, dtype=torch.float64).contiguous()
+    auto_selected = method is None
     method = resolve_method(n, "cuda", method)
 
     if method == "pardiso":
@@ -111,19 +112,28 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
         # object comes back in as M
         if isinstance(Ac, ElementOperator):
             raise RuntimeError(ERR_AMG_OPERATOR)
-        if not (isinstance(M, AMGPreconditioner) and M.n == n):
-            # aggregates and the patterns of P, R, A_c depend on the sparsity pattern only: a hierarchy built for an
-            # earlier matrix on the same mesh (previous load case, design iteration, Newton solve) is kept with the
-            # pattern-level SELL structure and only refreshed
-            M = getattr(Ac._sell_struct, "amg_cache", None) if Ac._sell_struct is not None else None
-        if isinstance(M, AMGPreconditioner) and M.n == n:
-            M.resetup(Ac)
-        else:
-            M = AMGPreconditioner(Ac)
-            if Ac._sell_struct is not None:
-                Ac._sell_struct.amg_cache = M
-        x, _ = M.solve(rhs, x0=None if x0 is None else x0.detach(), rtol=stol)
-        return x.to(device=out_device, dtype=b.dtype), M
+        try:
+            if not (isinstance(M, AMGPreconditioner) and M.n == n):
+                # aggregates and the patterns of P, R, A_c depend on the sparsity pattern only: a hierarchy built for
+                # an earlier matrix on the same mesh (previous load case, design iteration, Newton solve) is kept with
+                # the pattern-level SELL structure and only refreshed
+                M = getattr(Ac._sell_struct, "amg_cache", None) if Ac._sell_struct is not None else None
+            if isinstance(M, AMGPreconditioner) and M.n == n:
+                M.resetup(Ac)
+            else:
+                M = AMGPreconditioner(Ac)
+                if Ac._sell_struct is not None:
+                    Ac._sell_struct.amg_cache = M
+            x, _ = M.solve(rhs, x0=None if x0 is None else x0.detach(), rtol=stol)
+            return x.to(device=out_device, dtype=b.dtype), M
+        except RuntimeError:
+            # AMG-preconditioned CG needs an SPD matrix (and a hierarchy within the kernels' static limits). When the
+            # method was chosen by the size policy (not by the caller) an indefinite or singular-but-consistent system
+            # still gets the reference's own default for that case, Jacobi-MINRES (sparse.py:406-413), before the
+            # failure reaches FEM.solve's cutback.
+            if not auto_selected:
+                raise
+            method, M = "minres", None
     if isinstance(Ac, ElementOperator) and method == "spsolve":
         method = "cg"  # the matrix-free operator (kernel K8) has no entries to factorise
     if method == "spsolve":
