@@ -217,3 +217,29 @@ def test_full_size_property_amg_beats_jacobi(T, tables):
     assert res <= 1.5e-8
     assert float((xa - xj).norm() / xj.norm()) <= 1e-6
     assert Mp.operator_complexity < 1.6
+
+
+def test_auto_selected_amg_falls_back_to_minres_on_failure(T, tables, monkeypatch):
+    """Size policy picks AMG; if AMG-PCG fails (indefinite / singular system) the solve is retried with the reference's
+    default Krylov method instead of failing — but an explicitly requested method="amgx" still raises."""
+    from torchfem_b200.amg import AMGPreconditioner
+
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, 11, tables)
+    A = p.matrix(A.values_)
+    ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
+    b = dev(ref["res"])
+    monkeypatch.setattr(T.sparse, "AMG_MIN_DOFS", 1000)
+    monkeypatch.setattr(T.sparse, "DIRECT_LIMIT", 100)
+    assert T.sparse.resolve_method(A.n, "cuda", None) == "amgx"
+    x_amg, M1 = T.sparse.sparse_solve(A, b, stol=1e-10)
+    assert isinstance(M1, AMGPreconditioner)
+
+    def boom(self, *a, **k):
+        raise RuntimeError("CG failed with exit code -1")
+
+    monkeypatch.setattr(AMGPreconditioner, "solve", boom)
+    x_mr, M2 = T.sparse.sparse_solve(A, b, stol=1e-10)
+    assert not isinstance(M2, AMGPreconditioner)
+    assert float((x_mr - x_amg).norm() / x_amg.norm()) <= 1e-8
+    with pytest.raises(RuntimeError, match="CG failed"):
+        T.sparse.sparse_solve(A, b, stol=1e-10, method="amgx")
