@@ -31,6 +31,8 @@ from . import csr as _csr
 from . import residual as _res
 from .elements import Element
 from .materials import Material
+from .materials import small_det as _small_det
+from .materials import small_matmul as _small_matmul
 from .sparse import CachedSolve, describe_method, differentiable_sparse_solve, newton_solve  # noqa: F401
 
 
@@ -588,7 +590,7 @@ class Mechanics(FEM, ABC):
             P_all, alpha_all, tangent = _step_points(self.material, H_all, grad_prev, flux_prev, state_prev, de0,
                                                      cl, iter, need_k)
             F_all = grad_prev + H_all
-            flux_all = (F_all @ P_all) / torch.det(F_all)[..., None, None] if nlgeom else P_all
+            flux_all = _small_matmul(F_all, P_all) / _small_det(F_all)[..., None, None] if nlgeom else P_all
             f = _res.elem_force(geom, P_all)
             geom.check()
             if self._f_scale is not None:
@@ -604,7 +606,7 @@ class Mechanics(FEM, ABC):
                 F_new = grad_prev[q] + H_inc
                 P, alpha, ddsdde = self.material.step(H_inc, grad_prev[q], flux_prev[q], state_prev[q], de0, cl, iter)
                 grads.append(F_new)
-                fluxes.append((F_new @ P) / torch.det(F_new)[:, None, None] if nlgeom else P)
+                fluxes.append(_small_matmul(F_new, P) / _small_det(F_new)[:, None, None] if nlgeom else P)
                 states.append(alpha)
                 f = f + float(w) * self.compute_f(detJ[q], B[q], P).reshape(-1, nd)
                 if need_k:
