@@ -11,6 +11,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 
 #include "ebe.cuh"
@@ -324,6 +325,138 @@ __global__ void __launch_bounds__(kVecThreads)
   for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n;
        i += (int64_t)gridDim.x * kVecThreads)
     p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+// ---- small systems: the whole CG loop in ONE cooperative kernel.
+// Below ~1 M rows an iteration of the three-kernel driver costs ~38 us whatever the size: three dependent launches,
+// each ending in a "last CTA" reduction. Here the grid stays resident and the phases of an iteration are separated
+// by grid-wide barriers (~2-3 us each); every CTA sums the per-CTA partials itself in the same fixed order, so all
+// CTAs see bit-identical scalars and take the same decisions without a broadcast. A thread owns the same rows in
+// every phase (row = 32 t + lane of its slices), so x, r, q and its entries of p are only ever read by their writer;
+// the one cross-thread read, the gather of p inside the SpMV, goes to L2 (ld.global.cg: an L1 line could predate
+// another CTA's store of the same iteration).
+__device__ __forceinline__ double grid_total(const double* partials, int nb, double* s_bcast) {
+  __syncthreads();  // s_bcast of the previous reduction has been consumed
+  if (threadIdx.x < 32) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nb; i += 32) s += __ldcg(partials + i);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *s_bcast = s;
+  }
+  __syncthreads();
+  return *s_bcast;
+}
+
+template <int DPN>
+__global__ void __launch_bounds__(kSellWarps * 32, 4)
+    k_cg_coop(Sell A, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* p,
+              double* __restrict__ q, double* sc, double* partials, int batch) {
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  __shared__ double s_red[kSellWarps];
+  __shared__ double s_bcast;
+  const int nb = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t0 = (int64_t)blockIdx.x * kSellWarps + warp, stride = (int64_t)nb * kSellWarps;
+  if (sc[SC_DONE] != 0.0) return;  // read-only so far: uniform over the grid
+  double rho = sc[SC_RHO], iters = sc[SC_ITERS], rr_tot = sc[SC_RR], done = 0.0;
+  const double tol = sc[SC_TOL];
+  for (int it = 0; it < batch; ++it) {
+    // q = A p on my slices, partial p.q
+    double dot = 0.0;
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      const double acc = slice_row<DPN, true>(A, t, p, lane);
+      if (row < A.n) {
+        q[row] = acc;
+        dot = fma(acc, p[row], dot);
+      }
+    }
+    double bs = block_sum<kSellWarps * 32>(dot, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    grid.sync();
+    const double alpha = rho / grid_total(partials, nb, &s_bcast);
+    // x += alpha p ; r -= alpha q ; partial r.r and r.(D^-1 r)
+    double rr = 0.0, rz = 0.0;
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      if (row < A.n) {
+        x[row] = fma(alpha, p[row], x[row]);
+        const double ri = fma(-alpha, q[row], r[row]);
+        r[row] = ri;
+        rr = fma(ri, ri, rr);
+        rz = fma(ri * dinv[row], ri, rz);
+      }
+    }
+    bs = block_sum<kSellWarps * 32>(rr, s_red);
+    if (threadIdx.x == 0) partials[nb + blockIdx.x] = bs;
+    bs = block_sum<kSellWarps * 32>(rz, s_red);
+    if (threadIdx.x == 0) partials[2 * nb + blockIdx.x] = bs;
+    grid.sync();
+    rr_tot = grid_total(partials + nb, nb, &s_bcast);
+    const double rz_tot = grid_total(partials + 2 * nb, nb, &s_bcast);
+    const double beta = rz_tot / rho;
+    rho = rz_tot;
+    iters += 1.0;
+    if (!isfinite(rr_tot)) done = 2.0;  // breakdown (scipy would iterate on NaNs to maxiter)
+    else if (sqrt(rr_tot) < tol) done = 1.0;
+    if (done != 0.0) break;  // identical in every CTA
+    // p = D^-1 r + beta p
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      if (row < A.n) p[row] = fma(beta, p[row], dinv[row] * r[row]);
+    }
+    grid.sync();
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[SC_RHO] = rho;
+    sc[SC_RR] = rr_tot;
+    sc[SC_ITERS] = iters;
+    sc[SC_DONE] = done;
+  }
+}
+
+constexpr int64_t kCoopMaxRows = 1000000;
+
+// Launches batches of the cooperative kernel until convergence / maxiter. Returns TFEM_ERR_INVALID (and touches
+// nothing) if the device cannot launch cooperatively, so that the caller falls back to the three-kernel driver.
+template <int DPN>
+int cg_coop_batches(const Sell& A, const double* dinv, double* x, const Work& w, int64_t maxiter, double* sc_host,
+                    double* launches, double* spmvs, cudaStream_t st) {
+  static int coop = -1, per_sm = 0;
+  if (coop < 0) {
+    int dev = 0, attr = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
+    if (attr && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop<DPN>, kSellWarps * 32, 0) == cudaSuccess &&
+        per_sm >= 1)
+      coop = 1;
+    else
+      coop = 0;
+  }
+  if (!coop) return TFEM_ERR_INVALID;
+  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  const int grid = (int)(want < cap ? want : cap);
+  if (3 * (int64_t)grid > kMaxPartials) return TFEM_ERR_INVALID;
+  int64_t issued = 0;
+  while (true) {
+    TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TFEM_CUDA(cudaStreamSynchronize(st));
+    if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
+    int batch = (int)(maxiter - issued < 256 ? maxiter - issued : 256);
+    Sell a = A;
+    const double* dv = dinv;
+    double *xx = x, *rr = w.r, *pp = w.p, *qq = w.q, *scp = w.sc, *part = w.partials;
+    void* args[] = {&a, &dv, &xx, &rr, &pp, &qq, &scp, &part, &batch};
+    TFEM_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_coop<DPN>, dim3(grid), dim3(kSellWarps * 32), args, 0, st));
+    const int64_t before = (int64_t)sc_host[SC_ITERS];
+    issued += batch;
+    *launches += 1;
+    (void)before;
+  }
+  *spmvs += sc_host[SC_ITERS];
+  return TFEM_OK;
 }
 
 __global__ void k_copy_or_zero(int64_t n, const double* __restrict__ src, double* __restrict__ dst) {
@@ -873,7 +1006,18 @@ static int krylov_solve_impl(int method, const Op& A, const double* dinv, const 
     k_mr_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r1, w.r2, w.y, w.w1, w.w2, w.sc, w.partials, w.ticket);
   TFEM_LAUNCH_CHECK();
   launches += 2;
-  while (true) {
+  // small systems, CG on the assembled matrix: the whole loop in one cooperative kernel (see k_cg_coop)
+  static const bool coop_off = getenv("TFEM_CG_COOP") && atoi(getenv("TFEM_CG_COOP")) == 0;
+  bool coop_done = false;
+  if (method == TFEM_METHOD_CG && !A.ebe && !coop_off && n <= kCoopMaxRows) {
+    int rc = TFEM_ERR_INVALID;
+    if (A.sell.dpn == 3) rc = cg_coop_batches<3>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+    else if (A.sell.dpn == 2) rc = cg_coop_batches<2>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+    else rc = cg_coop_batches<0>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+    if (rc == TFEM_OK) coop_done = true;
+    else if (rc != TFEM_ERR_INVALID) return rc;
+  }
+  while (!coop_done) {
     TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
     TFEM_CUDA(cudaStreamSynchronize(st));
     if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
