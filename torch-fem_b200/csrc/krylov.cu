@@ -418,27 +418,29 @@ __global__ void __launch_bounds__(kSellWarps * 32, 4)
 
 constexpr int64_t kCoopMaxRows = 1000000;
 
-// Launches batches of the cooperative kernel until convergence / maxiter. Returns TFEM_ERR_INVALID (and touches
-// nothing) if the device cannot launch cooperatively, so that the caller falls back to the three-kernel driver.
+// Launches batches of a cooperative kernel until convergence / maxiter. Returns TFEM_ERR_INVALID (and touches nothing)
+// if the device cannot launch cooperatively, so that the caller falls back to the kernel-per-phase driver.
+template <typename K>
+int coop_grid(K kernel, const Sell& A, int* grid_out) {
+  int dev = 0, attr = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !attr)
+    return TFEM_ERR_INVALID;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSellWarps * 32, 0) != cudaSuccess || per_sm < 1)
+    return TFEM_ERR_INVALID;
+  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  const int64_t grid = want < cap ? want : cap;
+  if (3 * grid > kMaxPartials) return TFEM_ERR_INVALID;
+  *grid_out = (int)grid;
+  return TFEM_OK;
+}
+
 template <int DPN>
 int cg_coop_batches(const Sell& A, const double* dinv, double* x, const Work& w, int64_t maxiter, double* sc_host,
                     double* launches, double* spmvs, cudaStream_t st) {
-  static int coop = -1, per_sm = 0;
-  if (coop < 0) {
-    int dev = 0, attr = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&attr, cudaDevAttrCooperativeLaunch, dev);
-    if (attr && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cg_coop<DPN>, kSellWarps * 32, 0) == cudaSuccess &&
-        per_sm >= 1)
-      coop = 1;
-    else
-      coop = 0;
-  }
-  if (!coop) return TFEM_ERR_INVALID;
-  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
-  const int64_t cap = (int64_t)num_sms() * per_sm;
-  const int grid = (int)(want < cap ? want : cap);
-  if (3 * (int64_t)grid > kMaxPartials) return TFEM_ERR_INVALID;
+  int g = 0;
+  if (coop_grid(k_cg_coop<DPN>, A, &g) != TFEM_OK) return TFEM_ERR_INVALID;
   int64_t issued = 0;
   while (true) {
     TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -449,11 +451,9 @@ int cg_coop_batches(const Sell& A, const double* dinv, double* x, const Work& w,
     const double* dv = dinv;
     double *xx = x, *rr = w.r, *pp = w.p, *qq = w.q, *scp = w.sc, *part = w.partials;
     void* args[] = {&a, &dv, &xx, &rr, &pp, &qq, &scp, &part, &batch};
-    TFEM_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_coop<DPN>, dim3(grid), dim3(kSellWarps * 32), args, 0, st));
-    const int64_t before = (int64_t)sc_host[SC_ITERS];
+    TFEM_CUDA(cudaLaunchCooperativeKernel((void*)k_cg_coop<DPN>, dim3(g), dim3(kSellWarps * 32), args, 0, st));
     issued += batch;
     *launches += 1;
-    (void)before;
   }
   *spmvs += sc_host[SC_ITERS];
   return TFEM_OK;
@@ -529,6 +529,84 @@ __global__ void __launch_bounds__(kVecThreads)
     v[i] = s * y[i];
 }
 
+// scalar recurrences of one MINRES iteration (scipy minres.py main loop), on the scalar block `sc` (global memory in
+// the kernel-per-phase driver, a per-CTA shared-memory copy in the cooperative kernel); ry = r2 . (D^-1 r2)
+__device__ __forceinline__ void mr_scalars_lanczos(double* sc, double ry) {
+    const double eps = 2.220446049250313e-16;
+    const double itn = sc[SC_ITERS] + 1.0;
+    const double alfa = sc[SC_M_ALFA];
+    const double oldb = sc[SC_M_BETA];
+    if (ry < 0.0 || !isfinite(ry)) {
+      sc[SC_DONE] = 2.0;
+      return;
+    }
+    const double beta = sqrt(ry);
+    const double beta1 = sc[SC_M_BETA1];
+    double tnorm2 = sc[SC_M_TNORM2] + alfa * alfa + oldb * oldb + beta * beta;
+    double istop = 0.0;
+    if (itn == 1.0 && beta / beta1 <= 10.0 * eps) istop = -1.0;
+    const double cs0 = sc[SC_M_CS], sn0 = sc[SC_M_SN], dbar0 = sc[SC_M_DBAR];
+    const double oldeps = sc[SC_M_EPSLN];
+    const double delta = cs0 * dbar0 + sn0 * alfa;
+    const double gbar = sn0 * dbar0 - cs0 * alfa;
+    const double epsln = sn0 * beta;
+    const double dbar = -cs0 * beta;
+    const double root = hypot(gbar, dbar);
+    double gamma = hypot(gbar, beta);
+    gamma = fmax(gamma, eps);
+    const double cs = gbar / gamma, sn = beta / gamma;
+    const double phibar0 = sc[SC_M_PHIBAR];
+    const double phi = cs * phibar0;
+    const double phibar = sn * phibar0;
+    sc[SC_M_OLDB] = oldb;
+    sc[SC_M_BETA] = beta;
+    sc[SC_M_TNORM2] = tnorm2;
+    sc[SC_M_DBAR] = dbar;
+    sc[SC_M_EPSLN] = epsln;
+    sc[SC_M_CS] = cs;
+    sc[SC_M_SN] = sn;
+    sc[SC_M_PHIBAR] = phibar;
+    sc[SC_M_PHI] = phi;
+    sc[SC_M_DENOM] = 1.0 / gamma;
+    sc[SC_M_OLDEPS] = oldeps;
+    sc[SC_M_DELTA] = delta;
+    const double gmax = fmax(sc[SC_M_GMAX], gamma), gmin = fmin(sc[SC_M_GMIN], gamma);
+    sc[SC_M_GMAX] = gmax;
+    sc[SC_M_GMIN] = gmin;
+    sc[SC_M_RNORM] = phibar;
+    sc[SC_ITERS] = itn;
+    sc[SC_M_ISTOP] = istop;
+    // the ||x||-dependent stopping tests are finished in k_mr_xupdate (needs the new x)
+    sc[SC_RHO] = root;  // reused slot: root for test2
+}
+
+// the ||x||-dependent stopping tests of scipy minres; xx = x . x
+__device__ __forceinline__ void mr_scalars_xupdate(double* sc, double xx, double rtol, double maxiter) {
+    const double eps = 2.220446049250313e-16;
+    const double Anorm = sqrt(sc[SC_M_TNORM2]);
+    const double ynorm = sqrt(xx);
+    const double epsx = Anorm * ynorm * eps;
+    const double rnorm = sc[SC_M_RNORM];
+    const double root = sc[SC_RHO];
+    const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
+    const double test2 = (Anorm == 0.0) ? INFINITY : root / Anorm;
+    const double Acond = sc[SC_M_GMAX] / sc[SC_M_GMIN];
+    double istop = sc[SC_M_ISTOP];
+    if (istop == 0.0) {
+      const double t1 = 1.0 + test1, t2 = 1.0 + test2;
+      if (t2 <= 1.0) istop = 2.0;
+      if (t1 <= 1.0) istop = 1.0;
+      if (sc[SC_ITERS] >= maxiter) istop = 6.0;
+      if (Acond >= 0.1 / eps) istop = 4.0;
+      if (epsx >= sc[SC_M_BETA1]) istop = 3.0;
+      if (test2 <= rtol) istop = 2.0;
+      if (test1 <= rtol) istop = 1.0;
+    }
+    sc[SC_M_ISTOP] = istop;
+    sc[SC_RR] = rnorm * rnorm;
+    if (istop != 0.0) sc[SC_DONE] = (istop == 6.0) ? 3.0 : 1.0;
+}
+
 // after y = A v and alfa_raw = v.(A v) (from the SpMV kernel, stored in SC_PQ):
 //   y -= (beta/oldb) r1 (itn>=2) ; alfa = v.y ; y -= (alfa/beta) r2 ; r1 = r2 ; r2 = y ; y = dinv*r2 ;
 //   beta_new^2 = r2.y
@@ -576,55 +654,7 @@ __global__ void __launch_bounds__(kVecThreads)
   }
   double mine[1], tot[1];
   mine[0] = block_sum<kVecThreads>(ry, s_red);
-  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    // scalar recurrences of one MINRES iteration (scipy minres.py main loop)
-    const double eps = 2.220446049250313e-16;
-    const double itn = sc[SC_ITERS] + 1.0;
-    const double alfa = sc[SC_M_ALFA];
-    const double oldb = sc[SC_M_BETA];
-    if (tot[0] < 0.0 || !isfinite(tot[0])) {
-      sc[SC_DONE] = 2.0;
-      return;
-    }
-    const double beta = sqrt(tot[0]);
-    const double beta1 = sc[SC_M_BETA1];
-    double tnorm2 = sc[SC_M_TNORM2] + alfa * alfa + oldb * oldb + beta * beta;
-    double istop = 0.0;
-    if (itn == 1.0 && beta / beta1 <= 10.0 * eps) istop = -1.0;
-    const double cs0 = sc[SC_M_CS], sn0 = sc[SC_M_SN], dbar0 = sc[SC_M_DBAR];
-    const double oldeps = sc[SC_M_EPSLN];
-    const double delta = cs0 * dbar0 + sn0 * alfa;
-    const double gbar = sn0 * dbar0 - cs0 * alfa;
-    const double epsln = sn0 * beta;
-    const double dbar = -cs0 * beta;
-    const double root = hypot(gbar, dbar);
-    double gamma = hypot(gbar, beta);
-    gamma = fmax(gamma, eps);
-    const double cs = gbar / gamma, sn = beta / gamma;
-    const double phibar0 = sc[SC_M_PHIBAR];
-    const double phi = cs * phibar0;
-    const double phibar = sn * phibar0;
-    sc[SC_M_OLDB] = oldb;
-    sc[SC_M_BETA] = beta;
-    sc[SC_M_TNORM2] = tnorm2;
-    sc[SC_M_DBAR] = dbar;
-    sc[SC_M_EPSLN] = epsln;
-    sc[SC_M_CS] = cs;
-    sc[SC_M_SN] = sn;
-    sc[SC_M_PHIBAR] = phibar;
-    sc[SC_M_PHI] = phi;
-    sc[SC_M_DENOM] = 1.0 / gamma;
-    sc[SC_M_OLDEPS] = oldeps;
-    sc[SC_M_DELTA] = delta;
-    const double gmax = fmax(sc[SC_M_GMAX], gamma), gmin = fmin(sc[SC_M_GMIN], gamma);
-    sc[SC_M_GMAX] = gmax;
-    sc[SC_M_GMIN] = gmin;
-    sc[SC_M_RNORM] = phibar;
-    sc[SC_ITERS] = itn;
-    sc[SC_M_ISTOP] = istop;
-    // the ||x||-dependent stopping tests are finished in k_mr_xupdate (needs the new x)
-    sc[SC_RHO] = root;  // reused slot: root for test2
-  }
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) mr_scalars_lanczos(sc, tot[0]);
 }
 
 // w = (v - oldeps*w1 - delta*w2)/gamma ; x += phi*w ; ynorm^2 = x.x ; then the stopping tests
@@ -650,31 +680,145 @@ __global__ void __launch_bounds__(kVecThreads)
   }
   double mine[1], tot[1];
   mine[0] = block_sum<kVecThreads>(xx, s_red);
-  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    const double eps = 2.220446049250313e-16;
-    const double Anorm = sqrt(sc[SC_M_TNORM2]);
-    const double ynorm = sqrt(tot[0]);
-    const double epsx = Anorm * ynorm * eps;
-    const double rnorm = sc[SC_M_RNORM];
-    const double root = sc[SC_RHO];
-    const double test1 = (ynorm == 0.0 || Anorm == 0.0) ? INFINITY : rnorm / (Anorm * ynorm);
-    const double test2 = (Anorm == 0.0) ? INFINITY : root / Anorm;
-    const double Acond = sc[SC_M_GMAX] / sc[SC_M_GMIN];
-    double istop = sc[SC_M_ISTOP];
-    if (istop == 0.0) {
-      const double t1 = 1.0 + test1, t2 = 1.0 + test2;
-      if (t2 <= 1.0) istop = 2.0;
-      if (t1 <= 1.0) istop = 1.0;
-      if (sc[SC_ITERS] >= maxiter) istop = 6.0;
-      if (Acond >= 0.1 / eps) istop = 4.0;
-      if (epsx >= sc[SC_M_BETA1]) istop = 3.0;
-      if (test2 <= rtol) istop = 2.0;
-      if (test1 <= rtol) istop = 1.0;
+  if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) mr_scalars_xupdate(sc, tot[0], rtol, maxiter);
+}
+
+// MINRES the same way: one cooperative kernel, three grid barriers per iteration (after the SpMV + alfa pass, after
+// the Lanczos pass, after the x update). Every CTA carries its own copy of the scalar recurrences in shared memory and
+// advances it from the same reduction totals, so no scalar ever has to be broadcast; CTA 0 writes the block back at
+// the end. v ping-pongs between two buffers: the x update of iteration k also writes v_{k+1} = y / beta_{k+1}, so the
+// barrier that ends the iteration is also the one the next SpMV's gather needs.
+template <int DPN>
+__global__ void __launch_bounds__(kSellWarps * 32, 4)
+    k_mr_coop(Sell A, const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r1,
+              double* __restrict__ r2, double* __restrict__ y, double* va, double* vb, double* __restrict__ w1,
+              double* __restrict__ w2, double* sc, double* partials, double rtol, double maxiter, int batch) {
+  namespace cgr = cooperative_groups;
+  cgr::grid_group grid = cgr::this_grid();
+  __shared__ double s_red[kSellWarps];
+  __shared__ double s_bcast;
+  __shared__ double s_sc[SC_COUNT];
+  const int nb = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t t0 = (int64_t)blockIdx.x * kSellWarps + warp, stride = (int64_t)nb * kSellWarps;
+  if (threadIdx.x < SC_COUNT) s_sc[threadIdx.x] = sc[threadIdx.x];
+  __syncthreads();
+  if (s_sc[SC_DONE] != 0.0) return;  // uniform over the grid
+  double* v_cur = va;
+  double* v_nxt = vb;
+  {  // v = y / beta for the first iteration of this launch
+    const double s0 = 1.0 / s_sc[SC_M_BETA];
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      if (row < A.n) v_cur[row] = s0 * y[row];
     }
-    sc[SC_M_ISTOP] = istop;
-    sc[SC_RR] = rnorm * rnorm;
-    if (istop != 0.0) sc[SC_DONE] = (istop == 6.0) ? 3.0 : 1.0;
+    grid.sync();
   }
+  for (int it = 0; it < batch; ++it) {
+    // y = A v ; y -= (beta/oldb) r1 (from the second iteration on) ; partial v.y
+    const bool second = s_sc[SC_ITERS] >= 1.0;
+    const double f = second ? s_sc[SC_M_BETA] / s_sc[SC_M_OLDB] : 0.0;
+    double a = 0.0;
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      const double acc = slice_row<DPN, true>(A, t, v_cur, lane);
+      if (row < A.n) {
+        const double yi = second ? acc - f * r1[row] : acc;
+        y[row] = yi;
+        a += v_cur[row] * yi;
+      }
+    }
+    double bs = block_sum<kSellWarps * 32>(a, s_red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = bs;
+    grid.sync();
+    const double alfa = grid_total(partials, nb, &s_bcast);
+    // y -= (alfa/beta) r2 ; r1 = r2 ; r2 = y ; y = D^-1 r2 ; partial r2.y
+    const double f2 = alfa / s_sc[SC_M_BETA];
+    double ry = 0.0;
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      if (row < A.n) {
+        const double r2i = r2[row];
+        const double yi = y[row] - f2 * r2i;
+        r1[row] = r2i;
+        r2[row] = yi;
+        const double zi = dinv[row] * yi;
+        y[row] = zi;
+        ry += yi * zi;
+      }
+    }
+    bs = block_sum<kSellWarps * 32>(ry, s_red);
+    if (threadIdx.x == 0) partials[nb + blockIdx.x] = bs;
+    grid.sync();
+    const double ry_tot = grid_total(partials + nb, nb, &s_bcast);
+    if (threadIdx.x == 0) {
+      s_sc[SC_M_ALFA] = alfa;
+      mr_scalars_lanczos(s_sc, ry_tot);
+    }
+    __syncthreads();
+    if (s_sc[SC_DONE] != 0.0) break;  // breakdown; identical in every CTA
+    // w = (v - oldeps w1 - delta w2) / gamma ; x += phi w ; partial x.x ; next v = y / beta
+    const double oldeps = s_sc[SC_M_OLDEPS], delta = s_sc[SC_M_DELTA], denom = s_sc[SC_M_DENOM];
+    const double phi = s_sc[SC_M_PHI], sv = 1.0 / s_sc[SC_M_BETA];
+    double xx = 0.0;
+    for (int64_t t = t0; t < A.n_slices; t += stride) {
+      const int64_t row = t * 32 + lane;
+      if (row < A.n) {
+        const double wk2 = w1[row], wk1 = w2[row];
+        const double wn = (v_cur[row] - oldeps * wk2 - delta * wk1) * denom;
+        w1[row] = wk1;
+        w2[row] = wn;
+        const double xi = fma(phi, wn, x[row]);
+        x[row] = xi;
+        xx = fma(xi, xi, xx);
+        v_nxt[row] = sv * y[row];
+      }
+    }
+    bs = block_sum<kSellWarps * 32>(xx, s_red);
+    if (threadIdx.x == 0) partials[2 * nb + blockIdx.x] = bs;
+    grid.sync();
+    const double xx_tot = grid_total(partials + 2 * nb, nb, &s_bcast);
+    if (threadIdx.x == 0) mr_scalars_xupdate(s_sc, xx_tot, rtol, maxiter);
+    __syncthreads();
+    if (s_sc[SC_DONE] != 0.0) break;
+    double* tmp = v_cur;
+    v_cur = v_nxt;
+    v_nxt = tmp;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x < SC_COUNT) sc[threadIdx.x] = s_sc[threadIdx.x];
+}
+
+template <int DPN>
+int mr_coop_batches(const Sell& A, const double* dinv, double* x, const Work& w, double rtol, int64_t maxiter,
+                    double* sc_host, double* launches, double* spmvs, cudaStream_t st) {
+  int g = 0;
+  if (coop_grid(k_mr_coop<DPN>, A, &g) != TFEM_OK) return TFEM_ERR_INVALID;
+  double* vb = nullptr;  // second v buffer (ping-pong)
+  TFEM_CUDA(malloc_async(&vb, pad32(A.n) * sizeof(double), st));
+  int64_t issued = 0;
+  int rc = TFEM_OK;
+  while (true) {
+    if ((rc = check_cuda(cudaMemcpyAsync(sc_host, w.sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st), "memcpy")))
+      break;
+    if ((rc = check_cuda(cudaStreamSynchronize(st), "sync"))) break;
+    if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
+    int batch = (int)(maxiter - issued < 256 ? maxiter - issued : 256);
+    Sell a = A;
+    const double* dv = dinv;
+    double *xx = x, *r1 = w.r1, *r2 = w.r2, *yy = w.y, *va = w.v, *w1 = w.w1, *w2 = w.w2, *scp = w.sc, *part = w.partials;
+    double rt = rtol, mi = (double)maxiter;
+    void* args[] = {&a, &dv, &xx, &r1, &r2, &yy, &va, &vb, &w1, &w2, &scp, &part, &rt, &mi, &batch};
+    if ((rc = check_cuda(cudaLaunchCooperativeKernel((void*)k_mr_coop<DPN>, dim3(g), dim3(kSellWarps * 32), args, 0, st),
+                         "cooperative launch")))
+      break;
+    issued += batch;
+    *launches += 1;
+  }
+  cudaFreeAsync(vb, st);
+  if (rc != TFEM_OK) return rc;
+  *spmvs += sc_host[SC_ITERS];
+  return TFEM_OK;
 }
 
 // ------------------------------------------------------------------------------------------ misc
@@ -1006,14 +1150,20 @@ static int krylov_solve_impl(int method, const Op& A, const double* dinv, const 
     k_mr_init<<<vg, kVecThreads, 0, st>>>(n, b, q0, dinv, w.r1, w.r2, w.y, w.w1, w.w2, w.sc, w.partials, w.ticket);
   TFEM_LAUNCH_CHECK();
   launches += 2;
-  // small systems, CG on the assembled matrix: the whole loop in one cooperative kernel (see k_cg_coop)
+  // small systems on the assembled matrix: the whole loop in one cooperative kernel (see k_cg_coop / k_mr_coop)
   static const bool coop_off = getenv("TFEM_CG_COOP") && atoi(getenv("TFEM_CG_COOP")) == 0;
   bool coop_done = false;
-  if (method == TFEM_METHOD_CG && !A.ebe && !coop_off && n <= kCoopMaxRows) {
+  if (!A.ebe && !coop_off && n <= kCoopMaxRows) {
     int rc = TFEM_ERR_INVALID;
-    if (A.sell.dpn == 3) rc = cg_coop_batches<3>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
-    else if (A.sell.dpn == 2) rc = cg_coop_batches<2>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
-    else rc = cg_coop_batches<0>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+    if (method == TFEM_METHOD_CG) {
+      if (A.sell.dpn == 3) rc = cg_coop_batches<3>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+      else if (A.sell.dpn == 2) rc = cg_coop_batches<2>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+      else rc = cg_coop_batches<0>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);
+    } else {
+      if (A.sell.dpn == 3) rc = mr_coop_batches<3>(A.sell, dinv, x, w, rtol, maxiter, sc_host, &launches, &spmvs, st);
+      else if (A.sell.dpn == 2) rc = mr_coop_batches<2>(A.sell, dinv, x, w, rtol, maxiter, sc_host, &launches, &spmvs, st);
+      else rc = mr_coop_batches<0>(A.sell, dinv, x, w, rtol, maxiter, sc_host, &launches, &spmvs, st);
+    }
     if (rc == TFEM_OK) coop_done = true;
     else if (rc != TFEM_ERR_INVALID) return rc;
   }
