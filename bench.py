@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 METRIC = "DOFs solved/sec (assembly+PCG)"
 UNIT = "DOF/s"
 RTOL = 1e-8
-NCU_SPMV_DRAM_BYTES_CONFIG_B = 7234103000 + 86337280
+NCU_SPMV_DRAM_BYTES_CONFIG_B = 7233556000 + 85765120
 
 
 def measured_peaks():
@@ -424,9 +424,9 @@ def run_ours(args):
                      "peak_source": peak_src, "frac_of_spec_8000": achieved / 8000.0,
                      "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at config B from the committed
-                     # `ncu --set full` capture (profiles/r1_l_cg_iteration_ncu.txt); other sizes: not captured
+                     # `ncu --set full` capture (profiles/r1_t_cg_iteration_ncu.txt); other sizes: not captured
                      "traffic": NCU_SPMV_DRAM_BYTES_CONFIG_B if E == 150 else None,
-                     "traffic_source": "profiles/r1_l_cg_iteration_ncu.txt (k_sell_spmv<3,1>: 7.234 GB read + 0.086 GB written per launch)"},
+                     "traffic_source": "profiles/r1_t_cg_iteration_ncu.txt (k_sell_spmv<3,1>: 7.234 GB read + 0.086 GB written per launch)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
