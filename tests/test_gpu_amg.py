@@ -171,13 +171,15 @@ def test_amgx_method_reproduces_reference_solution_config_a(T, tables):
     assert st4["iterations"] == 0 and torch.equal(x4, x3)
 
 
-def test_spgemm_against_scipy(T):
-    """K15 on random block operators (d = 2): pattern bit-exact, values to round-off."""
+@pytest.mark.parametrize("d,nx,m,ny,px,py", [(2, 300, 200, 150, 9, 7), (3, 40, 600, 4000, 48, 40), (1, 64, 300, 9000, 60, 90)])
+def test_spgemm_against_scipy(T, d, nx, m, ny, px, py):
+    """K15 on random block operators: pattern bit-exact, values to round-off. The second and third shapes have product
+    rows of 1,000-3,000 distinct columns: the symbolic kernel overflows its 1,024-slot hash set and reruns with the
+    16,384-slot one, the numeric kernel takes the CTA-per-row variant."""
     import scipy.sparse as sp
     from torchfem_b200.amg import BlockOperator, spgemm
 
     rng = np.random.default_rng(5)
-    d, nx, m, ny = 2, 300, 200, 150
 
     def rand_block(nr, nc, per_row):
         ptr, col, val = [0], [], []
@@ -189,7 +191,7 @@ def test_spgemm_against_scipy(T):
         vals = rng.standard_normal(d * d * len(col))
         return BlockOperator(d, nr, nc, dev(ptr), dev(col), dev(vals))
 
-    X, Y = rand_block(nx, m, 9), rand_block(m, ny, 7)
+    X, Y = rand_block(nx, m, px), rand_block(m, ny, py)
     C, _ = spgemm(d, X, Y)
     ref = (X.to_scipy() @ Y.to_scipy()).tocsr()
     got = C.to_scipy()
