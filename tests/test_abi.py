@@ -45,3 +45,26 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "fem_oracle" not in text, fn
+
+
+def test_solver_policy_and_amg_refuses_cpu():
+    """Host logic without a device: the size policy of `resolve_method` (reference sparse.py:74-84 + the AMG threshold),
+    the reference's method names / error messages, and the AMG preconditioner's refusal to run on CPU tensors."""
+    import torchfem_b200 as T
+    from torchfem_b200.amg import AMGPreconditioner
+
+    S = T.sparse
+    assert S.resolve_method(S.DIRECT_LIMIT - 1, "cuda", None) == "spsolve"
+    assert S.resolve_method(S.DIRECT_LIMIT, "cuda", None) == "minres"
+    assert S.resolve_method(S.AMG_MIN_DOFS, "cuda", None) == "amgx"
+    assert S.resolve_method(10, "cuda", "cg") == "cg"
+    assert S.describe_method(5 * S.AMG_MIN_DOFS, "cuda", None) == "amgx | iterative | amg | tfem_b200 | cuda"
+    assert S.METHODS == ["spsolve", "minres", "cg", "pardiso", "amgx"] and "amgx" in S.available_backends
+    with pytest.raises(TypeError, match="assembled CSRMatrix"):
+        AMGPreconditioner(torch.eye(3))
+    A = torch.eye(4).to_sparse_coo()
+    with pytest.raises(ValueError, match="is not supported"):
+        S.sparse_solve(A, torch.ones(4), method="multigrid")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            S.sparse_solve(A, torch.ones(4), method="amgx")
