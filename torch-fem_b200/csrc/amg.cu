@@ -637,9 +637,6 @@ __global__ void __launch_bounds__(kSellWarps * 32, MINB)
     if (live) {
       if (MODE == M_JAC || (MODE == M_AX && DOT)) xr = __ldg(x + row);
       if (MODE == M_RES || MODE == M_JAC) br = __ldg(b + row);
-      // the variants that read x[row] up front also pull the row's own x sector in before the neighbouring rows
-      // gather it (L2 hit rate 18-20 % vs 8 %, 1.11-1.14 vs 1.23 ms in ncu); the residual variant asks for it explicitly
-      if (MODE == M_RES) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + row));
       if (MODE == M_JAC) dr = __ldg(dinv + row);
       if (MODE == M_ADD) br = y[row];
     }
