@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kRowCap = 768;   // blocks per block row the prolongator kernel can hold in shared memory
 constexpr int kAggCap = 256;   // distinct aggregates one row of P may touch (+1)
+constexpr int kStage = 48;     // blocks of a block row the prolongator kernel stages in shared memory (longer rows: global loads)
 
 __device__ __forceinline__ uint32_t hash32(uint32_t h) {  // MurmurHash3 finaliser, as oracle/amg_oracle.py
   h += 0x9E3779B9u;
@@ -329,13 +330,28 @@ __global__ void __launch_bounds__(128)
   const int mine = agg[I];
   const double* arow = vals + D * D * b0;
   double* prow = pvals + D * D * p0;
+  // the block row of A is staged in shared memory with coalesced loads (read straight from global memory the
+  // per-output walk below issues scattered 8-byte loads: 44 % of the kernel's stall samples), and the isolated-DOF
+  // flags of the neighbours are packed into one byte per entry (s_first is free after the ranking)
+  extern __shared__ double s_stage[];
+  double* sa = s_stage + (size_t)w * kStage * D * D;
+  const bool staged = L <= kStage;
+  if (staged)
+    for (int o = lane; o < L * D * D; o += 32) sa[o] = arow[o];
+  for (int e = lane; e < L; e += 32) {
+    const int64_t j = bcol[b0 + e];
+    unsigned char flags = 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) flags |= (unsigned char)((iso[j * D + c] ? 1 : 0) << c);
+    s_first[w][e] = flags;
+  }
+  __syncwarp();
   for (int o = lane; o < m * D * D; o += 32) {
     const int r = o / (D * D), a = (o / D) % D, c = o % D;
     double sum = 0.0;
     for (int q = start[r]; q < start[r + 1]; ++q) {
       const int e = perm[q];
-      const int64_t j = bcol[b0 + e];
-      if (!iso[j * D + c]) sum += arow[((int64_t)a * L + e) * D + c];
+      if (!((s_first[w][e] >> c) & 1)) sum += staged ? sa[(a * L + e) * D + c] : arow[((int64_t)a * L + e) * D + c];
     }
     double v = -omega * dinv[I * D + a] * sum;
     if (s_ukey[w][r] == mine && a == c && !iso[I * D + a]) v += 1.0;
@@ -1139,9 +1155,19 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
   TFEM_CUDA(malloc_async(&err, sizeof(int), st));
   TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
   const unsigned grid = grid_for(nb, 4);
-  if (d == 3) k_prolongator<3, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
-  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
-  else k_prolongator<1, FILL><<<grid, 128, 0, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  const size_t stage = FILL ? (size_t)4 * kStage * d * d * sizeof(double) : 0;  // static (~30 KB) + staging > 48 KB
+  if (FILL) {
+    static bool attr_set[4] = {false, false, false, false};
+    if (!attr_set[d]) {
+      if (d == 3) TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<3, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      else if (d == 2) TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<2, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      else TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<1, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set[d] = true;
+    }
+  }
+  if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  else k_prolongator<1, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
   TFEM_LAUNCH_CHECK();
   int h = 0;
   int rc = read_flag(err, &h, st);
