@@ -373,14 +373,15 @@ int tfem_amg_aggregate(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_
                        int64_t* n_agg_host, int32_t* rounds_host, void* stream);
 
 /* Smoothed prolongator P = (I - omega D^-1 A) T, T[i, agg(i)] = diag(1 - iso_i). count: pptr_dev int64 [nb+1] out
- * (offsets); fill: pcol_dev int32 [pptr[nb]] (sorted per row), pvals_dev double [d*d*pptr[nb]].
+ * (offsets); fill: pcol_dev int32 [pptr[nb]] (sorted per row), pvals_dev double [d*d*pptr[nb]]; max_row = longest
+ * block row of A (rows up to 160 blocks are staged in shared memory; 0 = do not stage).
  * TFEM_ERR_CAPACITY if a node has more than 768 neighbours or touches more than 255 aggregates. */
 int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,
                                const int32_t* agg_dev, int64_t* pptr_dev, void* stream);
 int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev,
                               const double* vals_dev, const int32_t* agg_dev, const double* dinv_dev,
                               const uint8_t* iso_dev, double omega, const int64_t* pptr_dev, int32_t* pcol_dev,
-                              double* pvals_dev, void* stream);
+                              double* pvals_dev, int max_row, void* stream);
 
 /* Block transpose. structure: tptr int64 [n_cols+1], tcol int32 [nblk] sorted per row, tsrc int32 [nblk] = index of
  * the source block; values: tvals = transposed blocks gathered through tsrc (a values-only refresh repeats only this). */

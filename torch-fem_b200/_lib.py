@@ -114,7 +114,8 @@ _SIGNATURES = {
     "tfem_amg_aggregate": (c_int, [c_int64, c_void_p, c_void_p, c_int] + [c_void_p] * 4
                            + [ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_int32), c_void_p]),
     "tfem_amg_prolongator_count": (c_int, [c_int, c_int64] + [c_void_p] * 5),
-    "tfem_amg_prolongator_fill": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double] + [c_void_p] * 4),
+    "tfem_amg_prolongator_fill": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double] + [c_void_p] * 3
+                                  + [c_int, c_void_p]),
     "tfem_amg_transpose_structure": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_int64] + [c_void_p] * 4),
     "tfem_amg_transpose_values": (c_int, [c_int, c_int64] + [c_void_p] * 7),
     "tfem_amg_spgemm_count": (c_int, [c_int64] + [c_void_p] * 6),

@@ -219,6 +219,7 @@ class AMGPreconditioner:
         if n_agg.value * d >= 0.8 * lv.n:
             return False
         lv.agg, lv.n_agg, lv.mis_rounds = agg, int(n_agg.value), int(rounds.value)
+        lv.max_row = int((op.bptr[1:] - op.bptr[:-1]).max().item())     # longest block row (staging capacity of K13)
         pptr = _empty(nb + 1, torch.int64, dev)
         L.check(L.lib.tfem_amg_prolongator_count(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(agg), L.ptr(pptr), st))
         npb = int(pptr[-1].item())
@@ -286,7 +287,7 @@ class AMGPreconditioner:
             P = lv.P
             L.check(L.lib.tfem_amg_prolongator_fill(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals), L.ptr(lv.agg),
                                                     L.ptr(lv.dinv), L.ptr(lv.iso), lv.omega, L.ptr(P.bptr), L.ptr(P.bcol),
-                                                    L.ptr(P.vals), st))
+                                                    L.ptr(P.vals), lv.max_row, st))
             if lv.R is None:
                 npb = P.nblk
                 tptr = _empty(lv.n_agg + 1, torch.int64, dev)

@@ -31,7 +31,7 @@ namespace {
 
 constexpr int kRowCap = 768;   // blocks per block row the prolongator kernel can hold in shared memory
 constexpr int kAggCap = 256;   // distinct aggregates one row of P may touch (+1)
-constexpr int kStage = 48;     // blocks of a block row the prolongator kernel stages in shared memory (longer rows: global loads)
+constexpr int kStageMax = 160;  // most blocks of a block row the prolongator kernel stages in shared memory (longer rows: global loads)
 
 __device__ __forceinline__ uint32_t hash32(uint32_t h) {  // MurmurHash3 finaliser, as oracle/amg_oracle.py
   h += 0x9E3779B9u;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(128)
                   const double* __restrict__ vals, const int32_t* __restrict__ agg,
                   const double* __restrict__ dinv, const uint8_t* __restrict__ iso, double omega,
                   int64_t* __restrict__ pcount, const int64_t* __restrict__ pptr, int32_t* __restrict__ pcol,
-                  double* __restrict__ pvals, int* err) {
+                  double* __restrict__ pvals, int* err, int stage_cap) {
   __shared__ int s_key[4][kRowCap];
   __shared__ int s_ukey[4][FILL ? kAggCap : 1];
   __shared__ short s_rank[4][kRowCap];
@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(128)
   // per-output walk below issues scattered 8-byte loads: 44 % of the kernel's stall samples), and the isolated-DOF
   // flags of the neighbours are packed into one byte per entry (s_first is free after the ranking)
   extern __shared__ double s_stage[];
-  double* sa = s_stage + (size_t)w * kStage * D * D;
-  const bool staged = L <= kStage;
+  double* sa = s_stage + (size_t)w * stage_cap * D * D;
+  const bool staged = L <= stage_cap;
   if (staged)
     for (int o = lane; o < L * D * D; o += 32) sa[o] = arow[o];
   for (int e = lane; e < L; e += 32) {
@@ -1150,12 +1150,15 @@ extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t
 template <bool FILL>
 static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol, const double* vals,
                               const int32_t* agg, const double* dinv, const uint8_t* iso, double omega,
-                              int64_t* pcount, const int64_t* pptr, int32_t* pcol, double* pvals, cudaStream_t st) {
+                              int64_t* pcount, const int64_t* pptr, int32_t* pcol, double* pvals, int max_row,
+                              cudaStream_t st) {
   int* err = nullptr;
   TFEM_CUDA(malloc_async(&err, sizeof(int), st));
   TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
   const unsigned grid = grid_for(nb, 4);
-  const size_t stage = FILL ? (size_t)4 * kStage * d * d * sizeof(double) : 0;  // static (~30 KB) + staging > 48 KB
+  // staging capacity = the longest block row, up to kStageMax (static ~30 KB + staging may exceed 48 KB: opt in)
+  const int stage_cap = FILL ? (max_row < 8 ? 8 : (max_row > kStageMax ? kStageMax : max_row)) : 0;
+  const size_t stage = FILL ? (size_t)4 * stage_cap * d * d * sizeof(double) : 0;
   if (FILL) {
     static bool attr_set[4] = {false, false, false, false};
     if (!attr_set[d]) {
@@ -1165,9 +1168,9 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
       attr_set[d] = true;
     }
   }
-  if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
-  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
-  else k_prolongator<1, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err);
+  if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
+  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
+  else k_prolongator<1, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
   TFEM_LAUNCH_CHECK();
   int h = 0;
   int rc = read_flag(err, &h, st);
@@ -1186,7 +1189,7 @@ extern "C" int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr
   cudaStream_t st = (cudaStream_t)stream_;
   TFEM_REQUIRE(bptr && bcol && agg && pptr && nb > 0 && d >= 1 && d <= 3, "amg_prolongator_count: bad arguments");
   int rc = prolongator_launch<false>(d, nb, bptr, bcol, nullptr, agg, nullptr, nullptr, 0.0, pptr + 1, nullptr,
-                                     nullptr, nullptr, st);
+                                     nullptr, nullptr, 0, st);
   if (rc != TFEM_OK) return rc;
   return scan_in_place(pptr, nb, st);
 }
@@ -1194,11 +1197,11 @@ extern "C" int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr
 extern "C" int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol,
                                          const double* vals, const int32_t* agg, const double* dinv,
                                          const uint8_t* iso, double omega, const int64_t* pptr, int32_t* pcol,
-                                         double* pvals, void* stream_) {
+                                         double* pvals, int max_row, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   TFEM_REQUIRE(bptr && bcol && vals && agg && dinv && iso && pptr && pcol && pvals && nb > 0 && d >= 1 && d <= 3,
                "amg_prolongator_fill: bad arguments");
-  return prolongator_launch<true>(d, nb, bptr, bcol, vals, agg, dinv, iso, omega, nullptr, pptr, pcol, pvals, st);
+  return prolongator_launch<true>(d, nb, bptr, bcol, vals, agg, dinv, iso, omega, nullptr, pptr, pcol, pvals, max_row, st);
 }
 
 extern "C" int tfem_amg_transpose_structure(int64_t n_rows, int64_t n_cols, const int64_t* ptr, const int32_t* col,
