@@ -390,6 +390,130 @@ def modal():
     print("modal: solid omega^2", out["solid.omega_sq"], "planar", out["planar.omega_sq"])
 
 
+def assembly_cases():
+    """`Assembly` (reference assembly.py:113-608; the set-ups follow reference tests/test_assembly.py:54-77, 128-184,
+    255-272, 351-392, 415-455): per-part displacement / force, the retained-to-all map T of `_build_T`, the rigid
+    modes, and an adjoint gradient through the constrained solve."""
+    from torchfem import Assembly, ReferencePoint, ReferencePointHeat
+    from torchfem.elements import linear_to_quadratic
+
+    solid_mat = M.IsotropicElasticity3D(1000.0, 0.3)
+    plane_mat = M.IsotropicElasticityPlaneStress(1000.0, 0.3)
+    out = {}
+
+    def store(tag, res, asm=None):
+        u, f, flux, grad, _ = res
+        for j in range(len(u)):
+            out[f"{tag}.u{j}"], out[f"{tag}.f{j}"] = npy(u[j]), npy(f[j])
+            out[f"{tag}.flux{j}"], out[f"{tag}.grad{j}"] = npy(flux[j]), npy(grad[j])
+        if asm is not None:
+            T, retained = asm._build_T()
+            out[f"{tag}.T_idx"], out[f"{tag}.T_val"] = npy(T._indices()), npy(T._values())
+            out[f"{tag}.retained"], out[f"{tag}.modes"] = npy(retained), npy(asm._rigid_modes())
+
+    # two distorted 3x3x2-element blocks stacked in z and tied at z = 1
+    n_a, e_a = mesh.cube_hexa(4, 4, 3, 1.0, 1.0, 1.0)
+    n_b, e_b = mesh.cube_hexa(4, 4, 4, 1.0, 1.0, 1.0)
+    n_b = n_b + torch.tensor([0.0, 0.0, 1.0])
+    a, b = Solid(n_a, e_a, solid_mat), Solid(n_b, e_b, solid_mat)
+    a.constraints[n_a[:, 2] == 0.0] = True
+    b.forces[n_b[:, 2] == 2.0, 2] = 25.0 / 16
+    b.forces[n_b[:, 2] == 2.0, 0] = 5.0 / 16
+    asm = Assembly([a, b])
+    asm.coupling(b, n_b[:, 2] == 1.0, a, n_a[:, 2] == 1.0)
+    store("tie", asm.solve(), asm)
+    inc = torch.linspace(0.0, 1.0, 4)
+    every = asm.solve(increments=inc, return_intermediate=True)
+    out["tie.every_u1"], out["tie.every_f0"] = npy(every[0][1]), npy(every[1][0])
+
+    # clamped cube driven by a reference point: force and moment
+    nodes, elements = mesh.cube_hexa(4, 4, 4)
+    solid = Solid(nodes, elements, solid_mat)
+    solid.constraints[nodes[:, 2] == 0.0] = True
+    point = ReferencePoint([0.5, 0.5, 2.0])
+    point.forces[0, 3] = 50.0
+    point.forces[0, 5] = -20.0
+    point.forces[0, 0] = 10.0
+    asm = Assembly([solid, point])
+    asm.coupling(solid, nodes[:, 2] == 1.0, point)
+    store("point", asm.solve(), asm)
+
+    # only u_z coupled, point fully prescribed
+    solid = Solid(nodes, elements, solid_mat)
+    solid.constraints[nodes[:, 2] == 0.0] = True
+    point = ReferencePoint([0.5, 0.5, 2.0])
+    point.constraints[0, :] = True
+    point.displacements[0, 2] = 0.1
+    asm = Assembly([solid, point])
+    asm.coupling(solid, nodes[:, 2] == 1.0, point, dofs=[2])
+    store("subset", asm.solve(), asm)
+
+    # quadratic solid (Hexa2) tied to a linear one through the nearest-node pairing
+    n_q, e_q = linear_to_quadratic(*mesh.cube_hexa(3, 3, 3))
+    n_l, e_l = mesh.cube_hexa(3, 3, 3)
+    n_l = n_l + torch.tensor([0.0, 0.0, 1.0])
+    q, l = Solid(n_q, e_q, solid_mat), Solid(n_l, e_l, solid_mat)
+    q.constraints[n_q[:, 2] == 0.0] = True
+    l.forces[n_l[:, 2] == 2.0, 1] = 1.0
+    asm = Assembly([q, l])
+    asm.coupling(l, n_l[:, 2] == 1.0, q, n_q[:, 2] == 1.0)
+    store("mixed", asm.solve(), asm)
+
+    # heat: two bars tied, the top held isothermal by a thermal point with a heat source
+    cond = M.IsotropicConductivity3D(1.5)
+    n_a, e_a = mesh.cube_hexa(3, 3, 3)
+    n_b, e_b = mesh.cube_hexa(3, 3, 4)
+    n_b = n_b + torch.tensor([0.0, 0.0, 1.0])
+    ha, hb = SolidHeat(n_a, e_a, cond), SolidHeat(n_b, e_b, cond)
+    ha.constraints[n_a[:, 2] == 0.0] = True
+    hp = ReferencePointHeat([0.5, 0.5, 2.5])
+    hp.heat_flux[0, 0] = 4.0
+    asm = Assembly([ha, hb, hp])
+    asm.coupling(hb, n_b[:, 2] == 1.0, ha, n_a[:, 2] == 1.0)
+    asm.coupling(hb, n_b[:, 2] == 2.0, hp)
+    store("heat", asm.solve(), asm)
+
+    # planar: two quad meshes tied, and a planar point carrying a moment about z
+    n_a, e_a = mesh.rect_quad(4, 4, 1.0, 1.0)
+    n_b, e_b = mesh.rect_quad(4, 4, 1.0, 1.0)
+    n_b = n_b + torch.tensor([1.0, 0.0])
+    pa, pb = Planar(n_a, e_a, plane_mat), Planar(n_b, e_b, plane_mat)
+    pa.constraints[n_a[:, 0] == 0.0] = True
+    pp = ReferencePoint([2.5, 0.5])
+    pp.forces[0, 2] = 20.0
+    pp.forces[0, 1] = -1.0
+    asm = Assembly([pa, pb, pp])
+    asm.coupling(pb, n_b[:, 0] == 1.0, pa, n_a[:, 0] == 1.0)
+    asm.coupling(pb, n_b[:, 0] == 2.0, pp)
+    store("planar", asm.solve(), asm)
+
+    # adjoint: d(work)/d(rho) with a SIMP-scaled stiffness in part a (the reference differentiates a shell thickness,
+    # tests/test_assembly.py:187-212; shells are outside the hot path)
+    n_a, e_a = mesh.cube_hexa(4, 3, 3, 1.0, 1.0, 1.0)
+    n_b, e_b = mesh.cube_hexa(4, 3, 3, 1.0, 1.0, 1.0)
+    n_b = n_b + torch.tensor([1.0, 0.0, 0.0])
+    rng = np.random.default_rng(3)
+    values = np.clip(0.6 + 0.2 * rng.standard_normal(len(e_a)), 0.1, 1.0)
+    rho = torch.tensor(values, requires_grad=True)
+    mat = M.IsotropicElasticity3D(E=1000.0, nu=0.3).vectorize(len(e_a))
+    mat.C = (rho ** 3.0)[:, None, None, None, None] * mat.C
+    a, b = Solid(n_a, e_a, mat), Solid(n_b, e_b, solid_mat)
+    a.constraints[n_a[:, 0] == 0.0] = True
+    point = ReferencePoint([2.5, 0.5, 0.5])
+    point.forces[0, 2] = -3.0
+    point.forces[0, 3] = 1.0
+    asm = Assembly([a, b, point])
+    asm.coupling(b, n_b[:, 0] == 1.0, a, n_a[:, 0] == 1.0)
+    asm.coupling(b, n_b[:, 0] == 2.0, point)
+    u, *_ = asm.solve(differentiable_parameters=rho)
+    work = torch.inner(point.forces.ravel(), u[2].ravel())
+    work.backward()
+    out["adjoint.rho"], out["adjoint.work"], out["adjoint.grad_rho"] = values, npy(work), npy(rho.grad)
+    out["adjoint.u2"] = npy(u[2])
+    np.savez_compressed(os.path.join(OUT, "assembly.npz"), **out)
+    print("assembly: point u", out["point.u1"], "work", out["adjoint.work"])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
         for name in sys.argv[1:]:
@@ -403,5 +527,6 @@ if __name__ == "__main__":
     sparse_small()
     heat_transient()
     modal()
+    assembly_cases()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

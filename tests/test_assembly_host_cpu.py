@@ -1,0 +1,279 @@
+"""`Assembly.solve` end to end on the CPU with every kernel call replaced by a numpy stand-in: the orchestration
+(stacking of the parts, elimination, Dirichlet handling, carried state, coupling forces, the adjoint through the
+constrained Newton solve) is checked against fixtures from the unmodified reference
+(`oracle/make_golden.py::assembly_cases`). The kernels themselves are checked on the GPU
+(tests/test_gpu_assembly.py runs the same cases through them; tests/test_gpu_amg.py the SpGEMM, tests/test_gpu_kernels.py
+the SpMV). Stand-ins: element matrices and assembly from `oracle/fem_oracle.py`, dense numpy products for K15 / K5,
+a dense solve for `sparse_solve`."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_case
+from oracle import fem_oracle as O
+
+
+class _HostMatrix:
+    """What the assembly reads of `csr.CSRMatrix`."""
+
+    def __init__(self, indptr, indices, values, n, symmetric=False, **_):
+        self.indptr, self.indices, self.values_, self.n = indptr, indices, values, int(n)
+        self.symmetric = symmetric
+
+    shape = property(lambda self: torch.Size((self.n, self.n)))
+
+    def numel(self):
+        return self.n * self.n
+
+    def _values(self):
+        return self.values_
+
+    def _indices(self):
+        rows = torch.repeat_interleave(torch.arange(self.n), self.indptr[1:] - self.indptr[:-1])
+        return torch.stack([rows, self.indices.to(torch.int64)])
+
+    @property
+    def diag_pos(self):
+        r, c = self._indices()
+        pos = torch.full((self.n,), -1, dtype=torch.int64)
+        on = torch.nonzero(r == c).ravel()
+        pos[r[on]] = on
+        return pos
+
+    def _like(self, values):
+        return _HostMatrix(self.indptr, self.indices, values, self.n, self.symmetric)
+
+    @property
+    def T(self):
+        assert self.symmetric
+        return self
+
+    def dense(self):
+        r, c = self._indices()
+        out = np.zeros((self.n, self.n))
+        out[r.numpy(), c.numpy()] = self.values_.numpy()
+        return out
+
+
+def _dense_block(op):
+    out = np.zeros((op.nbr, op.nbc))
+    mask = np.zeros((op.nbr, op.nbc), dtype=bool)
+    ptr, col, val = op.bptr.numpy(), op.bcol.numpy(), op.vals.numpy()
+    rows = np.repeat(np.arange(op.nbr), np.diff(ptr))
+    out[rows, col] = val
+    mask[rows, col] = True
+    return out, mask
+
+
+def _spgemm(d, X, Y, structure=None, out_vals=None):
+    """Structural product pattern (explicit zeros kept), like K15."""
+    from torchfem_b200.amg import BlockOperator
+
+    assert d == 1
+    (xv, xm), (yv, ym) = _dense_block(X), _dense_block(Y)
+    pat = (xm.astype(np.int64) @ ym.astype(np.int64)) > 0
+    if structure is not None:
+        cptr, ccol, _ = structure
+        assert np.array_equal(np.nonzero(pat)[1], ccol.numpy())
+    rows, cols = np.nonzero(pat)
+    cptr = torch.zeros(X.nbr + 1, dtype=torch.int64)
+    cptr[1:] = torch.from_numpy(np.cumsum(pat.sum(1)))
+    ccol = torch.from_numpy(cols.astype(np.int32))
+    vals = torch.from_numpy((xv @ yv)[rows, cols])
+    return BlockOperator(1, X.nbr, Y.nbc, cptr, ccol, vals), (cptr, ccol, int(pat.sum(1).max()))
+
+
+def _host_matvec(self, x):
+    rows = torch.repeat_interleave(torch.arange(self.n_rows), self.indptr[1:] - self.indptr[:-1])
+    y = torch.zeros(self.n_rows, dtype=torch.float64)
+    return y.index_add_(0, rows, self.values * x.detach()[self.indices.to(torch.int64)])
+
+
+def _sparse_solve(A, b, B=None, stol=1e-10, device=None, method=None, M=None, x0=None):
+    return torch.from_numpy(np.linalg.solve(A.dense(), b.detach().numpy())), None
+
+
+@pytest.fixture()
+def host(monkeypatch):
+    """torchfem_b200.assembly with the kernels swapped for the stand-ins, and a factory for CPU models."""
+    import torchfem_b200 as T
+    import torchfem_b200.assembly as A
+    from torchfem_b200.sparse import CachedSolve
+
+    monkeypatch.setattr(A.L, "require_cuda", lambda *t: None)
+    monkeypatch.setattr(A, "spmv_plan", lambda *a: None)
+    monkeypatch.setattr(A, "spgemm", _spgemm)
+    monkeypatch.setattr(A, "CSRMatrix", _HostMatrix)
+    monkeypatch.setattr(A._RectCSR, "matvec", _host_matvec)
+    monkeypatch.setattr(T.sparse, "sparse_solve", _sparse_solve)
+
+    def model(cls, nodes, elements, material):
+        class Host(cls):
+            def __init__(self):
+                self.device = nodes.device
+                self.nodes, self.elements = nodes, elements
+                self.n_nod, self.n_dim = nodes.shape
+                dpn = self.n_dof_per_node
+                self.n_dofs, self.n_elem = dpn * self.n_nod, len(elements)
+                self.n_int = len(self.etype.iweights)
+                self._neumann = torch.zeros(self.n_nod, dpn)
+                self._dirichlet = torch.zeros(self.n_nod, dpn)
+                self._constraints = torch.zeros(self.n_nod, dpn, dtype=torch.bool)
+                self._external_gradient = torch.zeros(self.n_elem, *self.n_flux)
+                self.idx = torch.from_numpy(O.dof_map(elements.numpy(), dpn))
+                self._glob_idx, self._k_map, self._diag_map = O.pattern(self.idx.numpy(), self.n_dofs)
+                indptr, indices = O.csr_from_glob_idx(self._glob_idx, self.n_dofs)
+                self.pattern = type("P", (), {"indptr": torch.from_numpy(indptr), "indices": torch.from_numpy(indices)})
+                self.material = material if material.is_vectorized else material.vectorize(self.n_elem)
+                self.cached_solve = CachedSolve()
+                self.K = torch.empty(0)
+                self._shape_cache = None
+                self.thickness = torch.ones(self.n_elem)   # planar models
+
+            def _geometry(self):
+                return None   # torch formulation of the residual
+
+            def _integrate_k_raw(self, tangent):
+                bref, w = self._tables()
+                fn = O.integrate_k_mech if self.KIND == T._lib.KIND_MECH else O.integrate_k_heat
+                return torch.from_numpy(fn(nodes.numpy(), elements.numpy(), bref.numpy(), w.numpy(),
+                                           tangent.detach().numpy(), self.thickness.numpy()))
+
+            def assemble_matrix(self, k, con):
+                val = O.assemble_values(k.detach().numpy(), self._k_map, self._glob_idx, self._diag_map,
+                                        con.numpy(), self.n_dofs)
+                return _HostMatrix(self.pattern.indptr, self.pattern.indices, torch.from_numpy(val), self.n_dofs, True)
+
+        return Host()
+
+    return T, A, model
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_case("assembly.npz")
+
+
+def _close(res, gold, tag, tol=1e-9):
+    u, f, flux, grad, _ = res
+    for j in range(len(u)):
+        for name, got in (("u", u[j]), ("f", f[j]), ("flux", flux[j]), ("grad", grad[j])):
+            ref = gold[f"{tag}.{name}{j}"]
+            assert tuple(got.shape) == ref.shape, (tag, name, j)
+            if ref.size:
+                scale = max(np.abs(gold[f"{tag}.{name}0"]).max(), np.abs(ref).max(), 1e-300)
+                assert np.abs(got.numpy() - ref).max() <= tol * scale, (tag, name, j)
+
+
+def test_tied_solids_and_increments(host, gold):
+    T, A, model = host
+    from torchfem_b200.materials import IsotropicElasticity3D
+    from torchfem_b200.mesh import cube_hexa
+
+    mat = IsotropicElasticity3D(1000.0, 0.3)
+    n_a, e_a = cube_hexa(4, 4, 3, 1.0, 1.0, 1.0)
+    n_b, e_b = cube_hexa(4, 4, 4, 1.0, 1.0, 1.0)
+    n_b = n_b + torch.tensor([0.0, 0.0, 1.0])
+    a, b = model(T.Solid, n_a, e_a, mat), model(T.Solid, n_b, e_b, mat)
+    a.constraints[n_a[:, 2] == 0.0] = True
+    b.forces[n_b[:, 2] == 2.0, 2] = 25.0 / 16
+    b.forces[n_b[:, 2] == 2.0, 0] = 5.0 / 16
+    asm = A.Assembly([a, b])
+    asm.coupling(b, n_b[:, 2] == 1.0, a, n_a[:, 2] == 1.0)
+    res = asm.solve()
+    _close(res, gold, "tie")
+    assert torch.equal(res[0][1][n_b[:, 2] == 1.0], res[0][0][n_a[:, 2] == 1.0])   # the tie is exact
+    every = asm.solve(increments=torch.linspace(0.0, 1.0, 4), return_intermediate=True)
+    assert np.abs(every[0][1].numpy() - gold["tie.every_u1"]).max() <= 1e-9 * np.abs(gold["tie.every_u1"]).max()
+    assert np.abs(every[1][0].numpy() - gold["tie.every_f0"]).max() <= 1e-9 * np.abs(gold["tie.every_f0"]).max()
+
+
+def test_reference_point_load_and_prescribed_motion(host, gold):
+    T, A, model = host
+    from torchfem_b200.materials import IsotropicElasticity3D
+    from torchfem_b200.mesh import cube_hexa
+
+    mat = IsotropicElasticity3D(1000.0, 0.3)
+    nodes, elements = cube_hexa(4, 4, 4)
+    solid = model(T.Solid, nodes, elements, mat)
+    solid.constraints[nodes[:, 2] == 0.0] = True
+    point = A.ReferencePoint([0.5, 0.5, 2.0])
+    point.forces[0, 3], point.forces[0, 5], point.forces[0, 0] = 50.0, -20.0, 10.0
+    asm = A.Assembly([solid, point])
+    asm.coupling(solid, nodes[:, 2] == 1.0, point)
+    res = asm.solve()
+    _close(res, gold, "point")
+    assert res[2][1].shape == (0,) and res[4][1].shape == (0,)
+    assert float(res[1][1][0, 3]) == pytest.approx(50.0)      # the point's force is what the coupling transmits
+
+    solid = model(T.Solid, nodes, elements, mat)
+    solid.constraints[nodes[:, 2] == 0.0] = True
+    point = A.ReferencePoint([0.5, 0.5, 2.0])
+    point.constraints[0, :] = True
+    point.displacements[0, 2] = 0.1
+    asm = A.Assembly([solid, point])
+    asm.coupling(solid, nodes[:, 2] == 1.0, point, dofs=[2])
+    _close(asm.solve(), gold, "subset")
+
+    solid.constraints[nodes[:, 2] == 1.0] = True
+    with pytest.raises(ValueError, match="constrained DOF is eliminated"):
+        asm.solve()
+
+
+def test_heat_and_planar(host, gold):
+    T, A, model = host
+    from torchfem_b200.materials import IsotropicConductivity3D, IsotropicElasticityPlaneStress
+    from torchfem_b200.mesh import cube_hexa, rect_quad
+
+    cond = IsotropicConductivity3D(1.5)
+    n_a, e_a = cube_hexa(3, 3, 3)
+    n_b, e_b = cube_hexa(3, 3, 4)
+    n_b = n_b + torch.tensor([0.0, 0.0, 1.0])
+    ha, hb = model(T.SolidHeat, n_a, e_a, cond), model(T.SolidHeat, n_b, e_b, cond)
+    ha.constraints[n_a[:, 2] == 0.0] = True
+    hp = A.ReferencePointHeat([0.5, 0.5, 2.5])
+    hp.heat_flux[0, 0] = 4.0
+    asm = A.Assembly([ha, hb, hp])
+    asm.coupling(hb, n_b[:, 2] == 1.0, ha, n_a[:, 2] == 1.0)
+    asm.coupling(hb, n_b[:, 2] == 2.0, hp)
+    _close(asm.solve(), gold, "heat")
+
+    plane = IsotropicElasticityPlaneStress(1000.0, 0.3)
+    n_a, e_a = rect_quad(4, 4, 1.0, 1.0)
+    n_b, e_b = rect_quad(4, 4, 1.0, 1.0)
+    n_b = n_b + torch.tensor([1.0, 0.0])
+    pa, pb = model(T.Planar, n_a, e_a, plane), model(T.Planar, n_b, e_b, plane)
+    pa.constraints[n_a[:, 0] == 0.0] = True
+    pp = A.ReferencePoint([2.5, 0.5])
+    pp.forces[0, 2], pp.forces[0, 1] = 20.0, -1.0
+    asm = A.Assembly([pa, pb, pp])
+    asm.coupling(pb, n_b[:, 0] == 1.0, pa, n_a[:, 0] == 1.0)
+    asm.coupling(pb, n_b[:, 0] == 2.0, pp)
+    _close(asm.solve(), gold, "planar")
+
+
+def test_adjoint_through_the_constrained_solve(host, gold):
+    T, A, model = host
+    from torchfem_b200.materials import IsotropicElasticity3D
+    from torchfem_b200.mesh import cube_hexa
+
+    n_a, e_a = cube_hexa(4, 3, 3, 1.0, 1.0, 1.0)
+    n_b, e_b = cube_hexa(4, 3, 3, 1.0, 1.0, 1.0)
+    n_b = n_b + torch.tensor([1.0, 0.0, 0.0])
+    rho = torch.tensor(gold["adjoint.rho"], requires_grad=True)
+    mat = IsotropicElasticity3D(E=1000.0, nu=0.3).vectorize(len(e_a))
+    mat.C = (rho ** 3.0)[:, None, None, None, None] * mat.C
+    a, b = model(T.Solid, n_a, e_a, mat), model(T.Solid, n_b, e_b, IsotropicElasticity3D(1000.0, 0.3))
+    a.constraints[n_a[:, 0] == 0.0] = True
+    point = A.ReferencePoint([2.5, 0.5, 0.5])
+    point.forces[0, 2], point.forces[0, 3] = -3.0, 1.0
+    asm = A.Assembly([a, b, point])
+    asm.coupling(b, n_b[:, 0] == 1.0, a, n_a[:, 0] == 1.0)
+    asm.coupling(b, n_b[:, 0] == 2.0, point)
+    u, *_ = asm.solve(differentiable_parameters=rho)
+    work = torch.inner(point.forces.ravel(), u[2].ravel())
+    work.backward()
+    assert abs(float(work.detach()) - float(gold["adjoint.work"])) <= 1e-9 * abs(float(gold["adjoint.work"]))
+    assert np.abs(u[2].detach().numpy() - gold["adjoint.u2"]).max() <= 1e-9 * np.abs(gold["adjoint.u2"]).max()
+    g = rho.grad.numpy()
+    assert np.linalg.norm(g - gold["adjoint.grad_rho"]) <= 1e-8 * np.linalg.norm(gold["adjoint.grad_rho"])

@@ -132,9 +132,13 @@ def _worker(rank, world, port, N, out):
 
 def test_partitioned_cg_matches_global_oracle():
     N, world = 5, 2
-    mgr = mp.Manager()
-    out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), N, out), nprocs=world, join=True)
+    # a spawned manager: forking this process (the default start method) once BLAS / OpenMP thread pools exist leaves
+    # later LAPACK calls in the same pytest process hanging
+    mgr = mp.get_context("spawn").Manager()
+    shared = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), N, shared), nprocs=world, join=True)
+    out = dict(shared)
+    mgr.shutdown()
     nodes, elements, bref, w, C, con_mask, disp = _global_problem(N)
     ref = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=1e-10)
     x = np.zeros(nodes.size)
