@@ -55,32 +55,30 @@ class _HostMatrix:
         return out
 
 
-def _dense_block(op):
-    out = np.zeros((op.nbr, op.nbc))
-    mask = np.zeros((op.nbr, op.nbc), dtype=bool)
-    ptr, col, val = op.bptr.numpy(), op.bcol.numpy(), op.vals.numpy()
-    rows = np.repeat(np.arange(op.nbr), np.diff(ptr))
-    out[rows, col] = val
-    mask[rows, col] = True
-    return out, mask
+def _block_pattern(op):
+    mask = np.zeros((op.nbr, op.nbc), dtype=np.int64)
+    mask[np.repeat(np.arange(op.nbr), np.diff(op.bptr.numpy())), op.bcol.numpy()] = 1
+    return mask
 
 
 def _spgemm(d, X, Y, structure=None, out_vals=None):
-    """Structural product pattern (explicit zeros kept), like K15."""
+    """Structural product pattern over d x d blocks (explicit zeros kept) and values in the block layout, like K15."""
     from torchfem_b200.amg import BlockOperator
 
-    assert d == 1
-    (xv, xm), (yv, ym) = _dense_block(X), _dense_block(Y)
-    pat = (xm.astype(np.int64) @ ym.astype(np.int64)) > 0
-    if structure is not None:
-        cptr, ccol, _ = structure
-        assert np.array_equal(np.nonzero(pat)[1], ccol.numpy())
+    pat = (_block_pattern(X) @ _block_pattern(Y)) > 0
     rows, cols = np.nonzero(pat)
-    cptr = torch.zeros(X.nbr + 1, dtype=torch.int64)
-    cptr[1:] = torch.from_numpy(np.cumsum(pat.sum(1)))
-    ccol = torch.from_numpy(cols.astype(np.int32))
-    vals = torch.from_numpy((xv @ yv)[rows, cols])
-    return BlockOperator(1, X.nbr, Y.nbc, cptr, ccol, vals), (cptr, ccol, int(pat.sum(1).max()))
+    if structure is not None:
+        assert np.array_equal(cols, structure[1].numpy())
+    cnt = pat.sum(1)
+    ptr = np.concatenate([[0], np.cumsum(cnt)])
+    dense = (X.to_scipy() @ Y.to_scipy()).toarray()
+    vals = np.zeros(d * d * len(cols))
+    slot = np.arange(len(cols)) - ptr[rows]
+    for a in range(d):
+        for c in range(d):
+            vals[d * d * ptr[rows] + (a * cnt[rows] + slot) * d + c] = dense[rows * d + a, cols * d + c]
+    cptr, ccol = torch.from_numpy(ptr.astype(np.int64)), torch.from_numpy(cols.astype(np.int32))
+    return BlockOperator(d, X.nbr, Y.nbc, cptr, ccol, torch.from_numpy(vals)), (cptr, ccol, int(cnt.max()))
 
 
 def _host_matvec(self, x):
@@ -103,6 +101,7 @@ def host(monkeypatch):
     monkeypatch.setattr(A.L, "require_cuda", lambda *t: None)
     monkeypatch.setattr(A, "spmv_plan", lambda *a: None)
     monkeypatch.setattr(A, "spgemm", _spgemm)
+    monkeypatch.setattr(A, "sell_structure", lambda *a: None)
     monkeypatch.setattr(A, "CSRMatrix", _HostMatrix)
     monkeypatch.setattr(A._RectCSR, "matvec", _host_matvec)
     monkeypatch.setattr(T.sparse, "sparse_solve", _sparse_solve)
@@ -123,7 +122,12 @@ def host(monkeypatch):
                 self.idx = torch.from_numpy(O.dof_map(elements.numpy(), dpn))
                 self._glob_idx, self._k_map, self._diag_map = O.pattern(self.idx.numpy(), self.n_dofs)
                 indptr, indices = O.csr_from_glob_idx(self._glob_idx, self.n_dofs)
-                self.pattern = type("P", (), {"indptr": torch.from_numpy(indptr), "indices": torch.from_numpy(indices)})
+                blocks = np.unique((self._glob_idx[0] // dpn) * self.n_nod + self._glob_idx[1] // dpn)   # node graph
+                node_ptr = np.concatenate([[0], np.cumsum(np.bincount(blocks // self.n_nod, minlength=self.n_nod))])
+                self.pattern = type("P", (), {
+                    "indptr": torch.from_numpy(indptr), "indices": torch.from_numpy(indices), "nnz": len(indices),
+                    "nnzb": len(blocks), "node_ptr": torch.from_numpy(node_ptr.astype(np.int64)),
+                    "adj": torch.from_numpy((blocks % self.n_nod).astype(np.int32))})
                 self.material = material if material.is_vectorized else material.vectorize(self.n_elem)
                 self.cached_solve = CachedSolve()
                 self.K = torch.empty(0)
@@ -165,7 +169,8 @@ def _close(res, gold, tag, tol=1e-9):
                 assert np.abs(got.numpy() - ref).max() <= tol * scale, (tag, name, j)
 
 
-def test_tied_solids_and_increments(host, gold):
+@pytest.mark.parametrize("node_blocks", [True, False])
+def test_tied_solids_and_increments(host, gold, node_blocks):
     T, A, model = host
     from torchfem_b200.materials import IsotropicElasticity3D
     from torchfem_b200.mesh import cube_hexa
@@ -179,8 +184,10 @@ def test_tied_solids_and_increments(host, gold):
     b.forces[n_b[:, 2] == 2.0, 2] = 25.0 / 16
     b.forces[n_b[:, 2] == 2.0, 0] = 5.0 / 16
     asm = A.Assembly([a, b])
+    asm.node_blocks = node_blocks
     asm.coupling(b, n_b[:, 2] == 1.0, a, n_a[:, 2] == 1.0)
     res = asm.solve()
+    assert asm._elimination.d == (3 if node_blocks else 1)
     _close(res, gold, "tie")
     assert torch.equal(res[0][1][n_b[:, 2] == 1.0], res[0][0][n_a[:, 2] == 1.0])   # the tie is exact
     every = asm.solve(increments=torch.linspace(0.0, 1.0, 4), return_intermediate=True)
@@ -202,6 +209,7 @@ def test_reference_point_load_and_prescribed_motion(host, gold):
     asm = A.Assembly([solid, point])
     asm.coupling(solid, nodes[:, 2] == 1.0, point)
     res = asm.solve()
+    assert asm._elimination.d == 3        # the point's six DOFs are two node blocks
     _close(res, gold, "point")
     assert res[2][1].shape == (0,) and res[4][1].shape == (0,)
     assert float(res[1][1][0, 3]) == pytest.approx(50.0)      # the point's force is what the coupling transmits
@@ -214,6 +222,7 @@ def test_reference_point_load_and_prescribed_motion(host, gold):
     asm = A.Assembly([solid, point])
     asm.coupling(solid, nodes[:, 2] == 1.0, point, dofs=[2])
     _close(asm.solve(), gold, "subset")
+    assert asm._elimination.d == 1        # partial nodes are eliminated: scalar operators
 
     solid.constraints[nodes[:, 2] == 1.0] = True
     with pytest.raises(ValueError, match="constrained DOF is eliminated"):
@@ -250,6 +259,17 @@ def test_heat_and_planar(host, gold):
     asm.coupling(pb, n_b[:, 0] == 1.0, pa, n_a[:, 0] == 1.0)
     asm.coupling(pb, n_b[:, 0] == 2.0, pp)
     _close(asm.solve(), gold, "planar")
+    assert asm._elimination.d == 1        # a 2-D point has three DOFs: not a whole number of 2-DOF nodes
+    # the tie alone is 2 x 2-blocked: both layouts give the same solution
+    pb.forces[n_b[:, 0] == 2.0, 1] = -0.25
+    sols = []
+    for node_blocks in (True, False):
+        asm = A.Assembly([pa, pb])
+        asm.node_blocks = node_blocks
+        asm.coupling(pb, n_b[:, 0] == 1.0, pa, n_a[:, 0] == 1.0)
+        sols.append(asm.solve()[0])
+        assert asm._elimination.d == (2 if node_blocks else 1)
+    assert all(torch.allclose(x, y, rtol=0, atol=1e-13) for x, y in zip(*sols))
 
 
 def test_adjoint_through_the_constrained_solve(host, gold):
@@ -271,6 +291,7 @@ def test_adjoint_through_the_constrained_solve(host, gold):
     asm.coupling(b, n_b[:, 0] == 1.0, a, n_a[:, 0] == 1.0)
     asm.coupling(b, n_b[:, 0] == 2.0, point)
     u, *_ = asm.solve(differentiable_parameters=rho)
+    assert asm._elimination.d == 3
     work = torch.inner(point.forces.ravel(), u[2].ravel())
     work.backward()
     assert abs(float(work.detach()) - float(gold["adjoint.work"])) <= 1e-9 * abs(float(gold["adjoint.work"]))

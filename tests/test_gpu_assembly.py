@@ -60,8 +60,10 @@ def _tie(T):
     return asm, n_a, n_b
 
 
-def test_elimination_operators_match_the_reference(T, gold):
-    """T and T^T on the device (CSR, kernel K5) against the reference's COO map, and T^T K T against a dense product."""
+@pytest.mark.parametrize("node_blocks", [True, False])
+def test_elimination_operators_match_the_reference(T, gold, node_blocks):
+    """T and T^T on the device (CSR, kernel K5) against the reference's COO map, and T^T K T against a dense product,
+    with the products on 3 x 3 node blocks and on scalar entries."""
     asm, n_a, n_b = _tie(T)
     Tcoo, retained = asm._build_T()
     assert np.array_equal(Tcoo._indices().cpu().numpy(), gold["tie.T_idx"])
@@ -69,7 +71,8 @@ def test_elimination_operators_match_the_reference(T, gold):
     assert np.array_equal(retained.cpu().numpy(), gold["tie.retained"])
     from torchfem_b200.assembly import EMPTY, _Elimination
 
-    elim = _Elimination(asm)
+    elim = _Elimination(asm, node_blocks)
+    assert elim.d == (3 if node_blocks else 1)
     Td = Tcoo.to_dense()
     q = torch.randn(elim.n_retained, generator=torch.Generator(device="cuda").manual_seed(0))
     v = torch.randn(asm.n_dofs, generator=torch.Generator(device="cuda").manual_seed(1))
@@ -89,6 +92,10 @@ def test_elimination_operators_match_the_reference(T, gold):
     ref[con, con] = 1.0
     assert float((K.to_dense() - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
     assert elim.reduced(blocks, con) is K              # same part matrices, same constraints: reused
+    assert (K._sell_struct.block is not None) == node_blocks     # node-block column indices for the Krylov kernels
+    x = torch.randn(elim.n_retained, generator=torch.Generator(device="cuda").manual_seed(2))
+    for fmt in ("sell", "csr"):
+        assert float((K.matvec(x, fmt=fmt) - ref @ x).abs().max()) <= 1e-12 * float(ref.abs().max()) * float(x.abs().max())
     K2 = elim.reduced([blocks[0] * 2.0, blocks[1]], con)   # numeric phase only, on the stored patterns
     ref2 = Td.T @ torch.block_diag(2.0 * blocks[0].to_dense(), blocks[1].to_dense()) @ Td
     ref2[con, :] = 0.0
@@ -97,13 +104,16 @@ def test_elimination_operators_match_the_reference(T, gold):
     assert float((K2.to_dense() - ref2).abs().max()) <= 1e-12 * float(ref2.abs().max())
 
 
-@pytest.mark.parametrize("method", [None, "cg", "minres"])
-def test_tied_solids(T, gold, method):
+@pytest.mark.parametrize("method,node_blocks", [(None, True), (None, False), ("cg", True), ("cg", False),
+                                                ("minres", True), ("amgx", True)])
+def test_tied_solids(T, gold, method, node_blocks):
     asm, n_a, n_b = _tie(T)
+    asm.node_blocks = node_blocks
     res = asm.solve(method=method)
+    assert asm._elimination.d == (3 if node_blocks else 1)
     _close(res, gold, "tie", 1e-8 if method is None else 1e-6)    # dense LU / Krylov at the default stol = 1e-10
     assert torch.equal(res[0][1][n_b[:, 2] == 1.0], res[0][0][n_a[:, 2] == 1.0])      # the tie is exact
-    if method is None:
+    if method is None and node_blocks:
         inc = torch.linspace(0.0, 1.0, 4)
         every = asm.solve(increments=inc, return_intermediate=True)
         assert [x.shape[0] for x in every[0]] == [4, 4]
@@ -127,6 +137,7 @@ def test_reference_point_moment_and_rigid_relation(T, gold):
     top = nodes[:, 2] == 1.0
     asm.coupling(solid, top, point)
     res = asm.solve()
+    assert asm._elimination.d == 3          # the point's six DOFs are two node blocks (translations, rotations)
     _close(res, gold, "point")
     u, f = res[0], res[1]
     u_p, theta = u[1][0, :3], u[1][0, 3:]
@@ -145,6 +156,7 @@ def test_reference_point_moment_and_rigid_relation(T, gold):
     asm = T.Assembly([solid, point])
     asm.coupling(solid, top, point, dofs=[2])
     res = asm.solve()
+    assert asm._elimination.d == 1          # partial nodes are eliminated: scalar operators
     _close(res, gold, "subset")
     assert torch.allclose(res[0][0][top][:, 2], torch.full((int(top.sum()),), 0.1))
     solid.constraints[top] = True
@@ -265,6 +277,7 @@ def test_larger_assembly_iterative_equals_monolithic(T):
     b.forces[n_b[:, 2] == 2.0, 2] = 1.0 / N ** 2
     b.forces[n_b[:, 2] == 2.0, 0] = 0.2 / N ** 2
     u, f, *_ = asm.solve()
+    assert asm._elimination.d == 3
     scale = float(u_ref.abs().max())
     lower = nodes[:, 2] <= 1.0 + 1e-12
     upper = nodes[:, 2] >= 1.0 - 1e-12
@@ -274,3 +287,6 @@ def test_larger_assembly_iterative_equals_monolithic(T):
     assert torch.equal(u[1][interface], u[0][top])
     # the eliminated interface DOFs of b carry b's own internal force, which balances the load on its top face
     assert float(f[1][interface][:, 2].sum() + f[1][n_b[:, 2] == 2.0][:, 2].sum()) == pytest.approx(0.0, abs=1e-6)
+    # the reduced matrix keeps 3 x 3 node blocks, so the AMG kernels coarsen it like a single model's tangent
+    ua = asm.solve(method="amgx")[0]
+    assert float((ua[0] - u_ref[lower]).abs().max()) <= 1e-6 * scale and float((ua[1] - u_ref[upper]).abs().max()) <= 1e-6 * scale

@@ -34,7 +34,7 @@ from torch import Tensor
 from . import _lib as L
 from .amg import BlockOperator, spgemm
 from .base import FEM, Heat
-from .csr import CSRMatrix, spmv_plan
+from .csr import CSRMatrix, sell_structure, spmv_plan
 from .sparse import describe_method, newton_solve
 
 
@@ -174,11 +174,43 @@ class _RectMatvec(torch.autograd.Function):
         return ctx.op.transposed @ g, None
 
 
+def _blocks_from_coo(rows: Tensor, cols: Tensor, values: Tensor, nbr: int, nbc: int, d: int) -> BlockOperator:
+    """Block-CSR operator (d x d blocks, `BlockOperator` value layout) from scalar COO entries without duplicates;
+    blocks are created wherever an entry falls and padded with zeros."""
+    I, a = rows // d, rows % d
+    J, c = cols // d, cols % d
+    ukey, inv = torch.unique(I * nbc + J, return_inverse=True)          # sorted by (block row, block column)
+    bptr = torch.zeros(nbr + 1, dtype=torch.int64, device=rows.device)
+    bptr[1:] = torch.cumsum(torch.bincount(ukey // nbc, minlength=nbr), 0)
+    m = (bptr[1:] - bptr[:-1])[I]                                      # blocks in the entry's block row
+    pos = d * d * bptr[I] + (a * m + (inv - bptr[I])) * d + c
+    vals = torch.zeros(d * d * int(ukey.shape[0]), dtype=torch.float64, device=rows.device)
+    vals.index_add_(0, pos, values.to(torch.float64))
+    return BlockOperator(d, nbr, nbc, bptr, (ukey % nbc).to(torch.int32).contiguous(), vals)
+
+
+def _scalar_columns(op: BlockOperator) -> Tensor:
+    """int32 scalar CSR column indices of a block operator, in its value order (block row I with m blocks: scalar
+    row a holds the columns d*J_s + c for s = 0..m-1, c = 0..d-1)."""
+    d, dev = op.d, op.bptr.device
+    cnt = op.bptr[1:] - op.bptr[:-1]
+    row_cols = (op.bcol.to(torch.int64)[:, None] * d + torch.arange(d, device=dev)).reshape(-1)   # one scalar row each
+    I = torch.repeat_interleave(torch.arange(op.nbr, device=dev), cnt * (d * d))
+    off = torch.arange(I.shape[0], device=dev) - (d * d) * op.bptr[I]
+    return row_cols[d * op.bptr[I] + off % (cnt[I] * d)].to(torch.int32).contiguous()
+
+
 class _Elimination:
     """Everything about `u = T q` that depends on the meshes and couplings only: T and T^T on the device, the
-    block-diagonal pattern of the part tangents in global numbering, and the symbolic phases of K T and T^T (K T)."""
+    block-diagonal pattern of the part tangents in global numbering, and the symbolic phases of K T and T^T (K T).
 
-    def __init__(self, asm: "Assembly"):
+    When every part has d = 2 or 3 DOFs per node (a 3-D reference point counts as two nodes of three) and the couplings
+    eliminate whole nodes, all operators are d x d-blocked over nodes: the products then run on node blocks (`d` below),
+    and the reduced matrix keeps the node-block SELL-32 layout (4/d^2 B of index per nonzero) and a block structure the
+    AMG kernels can coarsen. Otherwise (`dofs=[...]` subsets, thermal parts, a 2-D point next to 2-DOF nodes) the
+    operators are scalar CSR (d = 1)."""
+
+    def __init__(self, asm: "Assembly", allow_blocks: bool = True):
         dev = asm.device
         rows, cols, vals, retained = asm._triplets()
         n, n_ret = asm.n_dofs, int(retained.shape[0])
@@ -187,30 +219,70 @@ class _Elimination:
         self.T = _RectCSR.from_coo(rows, cols, vals, n, n_ret)
         self.Tt = _RectCSR.from_coo(cols, rows, vals, n_ret, n)
         self.T.transposed, self.Tt.transposed = self.Tt, self.T
+        self.n = n
+        d = self.d = self._block_size(asm, retained) if allow_blocks else 1
 
         ptr_parts, col_parts, self._segments = [], [], []
-        nnz = 0
+        nblk = 0
         for part, offset in zip(asm.parts, asm.offsets):
             if isinstance(part, FEM):
-                indptr, indices = part.pattern.indptr, part.pattern.indices
+                if d == 1:
+                    ptr, col = part.pattern.indptr, part.pattern.indices
+                else:
+                    ptr, col = part.pattern.node_ptr, part.pattern.adj
                 self._segments.append(None)
-            else:   # stiffness-free point: explicit zero diagonal
-                indptr = torch.arange(part.n_dofs + 1, dtype=torch.int64, device=dev)
-                indices = torch.arange(part.n_dofs, dtype=torch.int32, device=dev)
-                self._segments.append(torch.zeros(part.n_dofs, dtype=torch.float64, device=dev))
-            ptr_parts.append(indptr[:-1] + nnz)
-            col_parts.append(indices.to(torch.int64) + offset)
-            nnz += int(indices.shape[0])
-        ptr_parts.append(torch.tensor([nnz], dtype=torch.int64, device=dev))
+            else:   # stiffness-free point: explicit zero diagonal (blocks)
+                rows_here = part.n_dofs // d
+                ptr = torch.arange(rows_here + 1, dtype=torch.int64, device=dev)
+                col = torch.arange(rows_here, dtype=torch.int32, device=dev)
+                self._segments.append(torch.zeros(d * d * rows_here, dtype=torch.float64, device=dev))
+            ptr_parts.append(ptr[:-1] + nblk)
+            col_parts.append(col.to(torch.int64) + offset // d)
+            nblk += int(col.shape[0])
+        ptr_parts.append(torch.tensor([nblk], dtype=torch.int64, device=dev))
         self.kptr = torch.cat(ptr_parts).contiguous()
         self.kcol = torch.cat(col_parts).to(torch.int32).contiguous()
-        self.n = n
+        if d == 1:
+            self._Tb, self._Ttb = self.T.block_operator(), self.Tt.block_operator()
+        else:
+            self._Tb = _blocks_from_coo(rows, cols, vals, n // d, n_ret // d, d)
+            self._Ttb = _blocks_from_coo(cols, rows, vals, n_ret // d, n // d, d)
         self._kt_struct = None
         self._a_struct = None
         self._template: CSRMatrix | None = None
         self._mask_key = None
         self._mask = None
         self._last = None   # (part matrices, con key, reduced matrix) of the latest product
+
+    @staticmethod
+    def _block_size(asm: "Assembly", retained: Tensor) -> int:
+        sizes = {part.n_dof_per_node for part in asm.parts if isinstance(part, FEM)}
+        if len(sizes) != 1:
+            return 1
+        d = sizes.pop()
+        if d not in (2, 3):
+            return 1
+        for part in asm.parts:
+            if isinstance(part, FEM):
+                if part.pattern.nnz != d * d * part.pattern.nnzb:     # nodes no element references: lone diagonals
+                    return 1
+            elif part.n_dofs % d:
+                return 1
+        if retained.shape[0] % d:
+            return 1
+        nodes = retained.view(-1, d)           # ascending: whole nodes are runs d*k, d*k+1, ...
+        whole = (nodes[:, 0] % d == 0) & (nodes[:, -1] - nodes[:, 0] == d - 1)
+        return d if bool(whole.all()) else 1
+
+    def _matrix(self, A: BlockOperator) -> CSRMatrix:
+        """The first reduced matrix: scalar CSR view of the product, with the SELL-32 structure (node-block columns when
+        d > 1) that every later matrix on the pattern shares through `_like`."""
+        n, d = self.n_retained, self.d
+        if d == 1:
+            return CSRMatrix(A.bptr, A.bcol, A.vals, n, symmetric=True, sell_struct=sell_structure(A.bptr, A.bcol, n))
+        indptr, indices = A.indptr.contiguous(), _scalar_columns(A)
+        return CSRMatrix(indptr, indices, A.vals, n, symmetric=True,
+                         sell_struct=sell_structure(indptr, indices, n, (d, A.nbr, A.bptr, A.bcol)))
 
     def forget(self) -> None:
         """Drop the value-level caches (latest reduced matrix, Dirichlet mask); the symbolic phases stay."""
@@ -226,11 +298,12 @@ class _Elimination:
                 a is b for a, b in zip(self._last[0], blocks)):
             return self._last[2]
         vals = torch.cat([seg if seg is not None else K._values() for seg, K in zip(self._segments, blocks)])
-        Kop = BlockOperator(1, self.n, self.n, self.kptr, self.kcol, vals.contiguous())
-        KT, self._kt_struct = spgemm(1, Kop, self.T.block_operator(), structure=self._kt_struct)
-        A, self._a_struct = spgemm(1, self.Tt.block_operator(), KT, structure=self._a_struct)
+        d = self.d
+        Kop = BlockOperator(d, self.n // d, self.n // d, self.kptr, self.kcol, vals.contiguous())
+        KT, self._kt_struct = spgemm(d, Kop, self._Tb, structure=self._kt_struct)
+        A, self._a_struct = spgemm(d, self._Ttb, KT, structure=self._a_struct)
         if self._template is None:
-            self._template = CSRMatrix(A.bptr, A.bcol, A.vals, self.n_retained, symmetric=True)
+            self._template = self._matrix(A)
         if self._mask_key != key:
             idx = self._template._indices()
             is_con = torch.zeros(self.n_retained, dtype=torch.bool, device=vals.device)
@@ -282,6 +355,7 @@ class Assembly:
         self._rows: list[tuple[Tensor, Tensor, Tensor]] = []   # (secondary DOF, primary DOF, coefficient)
         self._links: list[tuple[tuple[Part, Tensor], tuple[Part, Tensor]]] = []
         self._elimination: _Elimination | None = None
+        self.node_blocks = True   # run the reduction on d x d node blocks where the couplings allow (see _Elimination)
 
     def __repr__(self) -> str:
         return f"<torch-fem assembly ({len(self.parts)} parts, {self.n_dofs} dofs)>"
@@ -416,7 +490,7 @@ class Assembly:
         track = any(p.requires_grad for p in params)
 
         if self._elimination is None:
-            self._elimination = _Elimination(self)
+            self._elimination = _Elimination(self, self.node_blocks)
         elim = self._elimination
         elim.forget()   # constraints and materials may have changed since the last solve; the patterns have not
         T, Tt, retained = elim.T, elim.Tt, elim.retained
