@@ -10,49 +10,7 @@ import pytest
 import torch
 
 from conftest import load_case
-from oracle import fem_oracle as O
-
-
-class _HostMatrix:
-    """What the assembly reads of `csr.CSRMatrix`."""
-
-    def __init__(self, indptr, indices, values, n, symmetric=False, **_):
-        self.indptr, self.indices, self.values_, self.n = indptr, indices, values, int(n)
-        self.symmetric = symmetric
-
-    shape = property(lambda self: torch.Size((self.n, self.n)))
-
-    def numel(self):
-        return self.n * self.n
-
-    def _values(self):
-        return self.values_
-
-    def _indices(self):
-        rows = torch.repeat_interleave(torch.arange(self.n), self.indptr[1:] - self.indptr[:-1])
-        return torch.stack([rows, self.indices.to(torch.int64)])
-
-    @property
-    def diag_pos(self):
-        r, c = self._indices()
-        pos = torch.full((self.n,), -1, dtype=torch.int64)
-        on = torch.nonzero(r == c).ravel()
-        pos[r[on]] = on
-        return pos
-
-    def _like(self, values):
-        return _HostMatrix(self.indptr, self.indices, values, self.n, self.symmetric)
-
-    @property
-    def T(self):
-        assert self.symmetric
-        return self
-
-    def dense(self):
-        r, c = self._indices()
-        out = np.zeros((self.n, self.n))
-        out[r.numpy(), c.numpy()] = self.values_.numpy()
-        return out
+from host_standins import HostMatrix, dense_sparse_solve, host_model
 
 
 def _block_pattern(op):
@@ -87,68 +45,22 @@ def _host_matvec(self, x):
     return y.index_add_(0, rows, self.values * x.detach()[self.indices.to(torch.int64)])
 
 
-def _sparse_solve(A, b, B=None, stol=1e-10, device=None, method=None, M=None, x0=None):
-    return torch.from_numpy(np.linalg.solve(A.dense(), b.detach().numpy())), None
-
-
 @pytest.fixture()
 def host(monkeypatch):
     """torchfem_b200.assembly with the kernels swapped for the stand-ins, and a factory for CPU models."""
     import torchfem_b200 as T
     import torchfem_b200.assembly as A
-    from torchfem_b200.sparse import CachedSolve
 
     monkeypatch.setattr(A.L, "require_cuda", lambda *t: None)
     monkeypatch.setattr(A, "spmv_plan", lambda *a: None)
     monkeypatch.setattr(A, "spgemm", _spgemm)
     monkeypatch.setattr(A, "sell_structure", lambda *a: None)
-    monkeypatch.setattr(A, "CSRMatrix", _HostMatrix)
+    monkeypatch.setattr(A, "CSRMatrix", HostMatrix)
     monkeypatch.setattr(A._RectCSR, "matvec", _host_matvec)
-    monkeypatch.setattr(T.sparse, "sparse_solve", _sparse_solve)
+    monkeypatch.setattr(T.sparse, "sparse_solve", dense_sparse_solve)
 
     def model(cls, nodes, elements, material):
-        class Host(cls):
-            def __init__(self):
-                self.device = nodes.device
-                self.nodes, self.elements = nodes, elements
-                self.n_nod, self.n_dim = nodes.shape
-                dpn = self.n_dof_per_node
-                self.n_dofs, self.n_elem = dpn * self.n_nod, len(elements)
-                self.n_int = len(self.etype.iweights)
-                self._neumann = torch.zeros(self.n_nod, dpn)
-                self._dirichlet = torch.zeros(self.n_nod, dpn)
-                self._constraints = torch.zeros(self.n_nod, dpn, dtype=torch.bool)
-                self._external_gradient = torch.zeros(self.n_elem, *self.n_flux)
-                self.idx = torch.from_numpy(O.dof_map(elements.numpy(), dpn))
-                self._glob_idx, self._k_map, self._diag_map = O.pattern(self.idx.numpy(), self.n_dofs)
-                indptr, indices = O.csr_from_glob_idx(self._glob_idx, self.n_dofs)
-                blocks = np.unique((self._glob_idx[0] // dpn) * self.n_nod + self._glob_idx[1] // dpn)   # node graph
-                node_ptr = np.concatenate([[0], np.cumsum(np.bincount(blocks // self.n_nod, minlength=self.n_nod))])
-                self.pattern = type("P", (), {
-                    "indptr": torch.from_numpy(indptr), "indices": torch.from_numpy(indices), "nnz": len(indices),
-                    "nnzb": len(blocks), "node_ptr": torch.from_numpy(node_ptr.astype(np.int64)),
-                    "adj": torch.from_numpy((blocks % self.n_nod).astype(np.int32))})
-                self.material = material if material.is_vectorized else material.vectorize(self.n_elem)
-                self.cached_solve = CachedSolve()
-                self.K = torch.empty(0)
-                self._shape_cache = None
-                self.thickness = torch.ones(self.n_elem)   # planar models
-
-            def _geometry(self):
-                return None   # torch formulation of the residual
-
-            def _integrate_k_raw(self, tangent):
-                bref, w = self._tables()
-                fn = O.integrate_k_mech if self.KIND == T._lib.KIND_MECH else O.integrate_k_heat
-                return torch.from_numpy(fn(nodes.numpy(), elements.numpy(), bref.numpy(), w.numpy(),
-                                           tangent.detach().numpy(), self.thickness.numpy()))
-
-            def assemble_matrix(self, k, con):
-                val = O.assemble_values(k.detach().numpy(), self._k_map, self._glob_idx, self._diag_map,
-                                        con.numpy(), self.n_dofs)
-                return _HostMatrix(self.pattern.indptr, self.pattern.indices, torch.from_numpy(val), self.n_dofs, True)
-
-        return Host()
+        return host_model(cls, nodes, elements, material)
 
     return T, A, model
 
