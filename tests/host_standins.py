@@ -43,6 +43,10 @@ class HostMatrix:
         assert self.symmetric
         return self
 
+    def matvec(self, x, fmt="auto"):
+        r, c = self._indices()
+        return torch.zeros(self.n, dtype=torch.float64).index_add_(0, r, self.values_ * x[c])
+
     def dense(self):
         r, c = self._indices()
         out = np.zeros((self.n, self.n))
