@@ -25,6 +25,12 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_s
    -o gpurun_out/${TAG}_amg_setup -f python tools/prof_amg.py > gpurun_out/${TAG}_ncu_amg_setup.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_amg_spmv' -s 8 -c 6 \
    -o gpurun_out/${TAG}_amg_cycle -f python tools/prof_amg.py > gpurun_out/${TAG}_ncu_amg_cycle.log 2>&1
+# Assembly at 1.35 M DOFs: tie and tie + reference point, node blocks; then the opt-in bordered PCG on the point case
+timeout 120 python tools/assembly_check.py --nodes 61 --method cg > gpurun_out/${TAG}_assembly_check.jsonl 2> gpurun_out/${TAG}_assembly_check.err
+TFEM_TEST_BORDERED=1 timeout 120 python -m pytest tests/test_gpu_assembly.py -q -k bordered > gpurun_out/${TAG}_pytest_bordered.log 2>&1
+timeout 120 python tools/assembly_check.py --nodes 61 --method cg --cases point --long-rows 2000 >> gpurun_out/${TAG}_assembly_check.jsonl 2>> gpurun_out/${TAG}_assembly_check.err
 tail -3 gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest_bordered.log
+cat gpurun_out/${TAG}_assembly_check.jsonl
 cat gpurun_out/${TAG}_bench.json
 tail -3 gpurun_out/${TAG}_bench.err
