@@ -514,6 +514,68 @@ def assembly_cases():
     print("assembly: point u", out["point.u1"], "work", out["adjoint.work"])
 
 
+def orthotropic():
+    """Orthotropic / transversely isotropic elasticity and orthotropic conductivity (reference elasticity.py:324-793,
+    conductivity.py:143-242): stiffness tensors, rotated tensors and re-extracted engineering constants, one `step`,
+    and a small clamped block solved with a rotated per-element orthotropic material."""
+    g = torch.Generator().manual_seed(7)
+    out = {}
+
+    def rot3(n):
+        q, _ = torch.linalg.qr(torch.randn(n, 3, 3, generator=g))
+        return q * torch.sign(torch.linalg.det(q))[:, None, None]
+
+    def rot2(n):
+        a = torch.rand(n, generator=g) * 3.0
+        return torch.stack([torch.stack([a.cos(), -a.sin()], -1), torch.stack([a.sin(), a.cos()], -1)], -2)
+
+    def consts(m, names):
+        return np.stack([npy(getattr(m, k)) for k in names])
+
+    p3 = dict(E_1=150.0, E_2=12.0, E_3=9.0, nu_12=0.3, nu_13=0.25, nu_23=0.4, G_12=5.0, G_13=4.0, G_23=3.0)
+    m = M.OrthotropicElasticity3D(**p3)
+    R = rot3(4)
+    out["o3.C"], out["o3.R"] = npy(m.C), npy(R)
+    mv = m.vectorize(4).rotate(R)
+    out["o3.C_rot"] = npy(mv.C)
+    out["o3.consts_rot"] = consts(mv, ["E_1", "E_2", "E_3", "nu_12", "nu_13", "nu_23", "G_12", "G_13", "G_23"])
+    H = 1e-3 * torch.randn(4, 3, 3, generator=g)
+    s0 = torch.randn(4, 3, 3, generator=g)
+    de0 = 1e-4 * torch.randn(4, 3, 3, generator=g)
+    sig, _, dd = mv.step(H, torch.eye(3).expand(4, 3, 3), s0, torch.zeros(4, 0), de0, torch.ones(4, 1), 0)
+    out["o3.H"], out["o3.s0"], out["o3.de0"], out["o3.sig"] = npy(H), npy(s0), npy(de0), npy(sig)
+    # batched parameters
+    E1 = torch.tensor([150.0, 80.0, 40.0])
+    mb = M.OrthotropicElasticity3D(E1, 0.1 * E1, 0.08 * E1, 0.3, 0.25, 0.4, 0.04 * E1, 0.03 * E1, 0.02 * E1)
+    out["o3.E1_batch"], out["o3.C_batch"] = npy(E1), npy(mb.C)
+    ti = M.TransverseIsotropicElasticity3D(E_L=140.0, E_T=10.0, nu_L=0.28, nu_T=0.42, G_L=5.5)
+    out["ti.C"] = npy(ti.C)
+    ps = M.OrthotropicElasticityPlaneStress(E_1=150.0, E_2=12.0, nu_12=0.3, G_12=5.0)
+    R2 = rot2(3)
+    psr = ps.vectorize(3).rotate(R2)
+    out["ps.C"], out["ps.R"], out["ps.C_rot"] = npy(ps.C), npy(R2), npy(psr.C)
+    out["ps.consts_rot"] = consts(psr, ["E_1", "E_2", "nu_12", "G_12"])
+    pe = M.OrthotropicElasticityPlaneStrain(E_1=150.0, E_2=12.0, E_3=9.0, nu_12=0.3, nu_13=0.25, nu_23=0.4, G_12=5.0)
+    per = pe.vectorize(3).rotate(R2)
+    out["pe.C"], out["pe.C_rot"] = npy(pe.C), npy(per.C)
+    out["pe.consts_rot"] = consts(per, ["E_1", "E_2", "nu_12", "G_12"])
+    k3 = M.OrthotropicConductivity3D(10.0, 2.0, 0.5)
+    out["k3.K"], out["k3.K_rot"] = npy(k3.KAPPA), npy(k3.vectorize(4).rotate(R).KAPPA)
+    k2 = M.OrthotropicConductivity2D(torch.tensor([10.0, 4.0, 1.0]), torch.tensor([2.0, 1.0, 0.5]))
+    out["k2.K"], out["k2.K_rot"] = npy(k2.KAPPA), npy(k2.rotate(R2).KAPPA)
+
+    # model level: clamped 3x2x2-element block, fibre direction rotated element by element
+    nodes, elements = mesh.cube_hexa(4, 3, 3, 1.5, 1.0, 1.0)
+    Re = rot3(len(elements))
+    model = Solid(nodes, elements, M.OrthotropicElasticity3D(**p3).vectorize(len(elements)).rotate(Re))
+    model.constraints[nodes[:, 0] == 0.0, :] = True
+    model.forces[nodes[:, 0] == 1.5, 2] = -0.1
+    u, f, sigma, eps, _ = model.solve(method="spsolve")
+    out["solid.R"], out["solid.u"], out["solid.sigma"] = npy(Re), npy(u), npy(sigma)
+    np.savez_compressed(os.path.join(OUT, "orthotropic.npz"), **out)
+    print("orthotropic: C_1111", out["o3.C"][0, 0, 0, 0], "u max", np.abs(out["solid.u"]).max())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
         for name in sys.argv[1:]:
@@ -528,5 +590,6 @@ if __name__ == "__main__":
     heat_transient()
     modal()
     assembly_cases()
+    orthotropic()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

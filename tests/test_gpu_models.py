@@ -627,3 +627,22 @@ class TestModal:
                 r[con] = 0.0
                 assert float(r.norm()) <= 1e-6 * float(K.matvec(x).norm())
         assert torch.allclose(vals[1], 4.0 * vals[0], rtol=1e-7)
+
+
+def test_block_with_rotated_orthotropic_material(T):
+    """an orthotropic tangent rotated element by element goes through K1 / K17 like any per-element
+    `ddsdde`; displacements and stresses of the reference (`oracle/make_golden.py::orthotropic`)."""
+    from torchfem_b200.materials import OrthotropicElasticity3D
+    from torchfem_b200.mesh import cube_hexa
+
+    g = load_case("orthotropic.npz")
+    nodes, elements = cube_hexa(4, 3, 3, 1.5, 1.0, 1.0)
+    material = OrthotropicElasticity3D(E_1=150.0, E_2=12.0, E_3=9.0, nu_12=0.3, nu_13=0.25, nu_23=0.4, G_12=5.0,
+                                       G_13=4.0, G_23=3.0).vectorize(len(elements)).rotate(torch.tensor(g["solid.R"]))
+    model = T.Solid(nodes, elements, material)
+    model.constraints[nodes[:, 0] == 0.0, :] = True
+    model.forces[nodes[:, 0] == 1.5, 2] = -0.1
+    for method, tol in (("spsolve", 1e-8), ("cg", 1e-6)):
+        u, f, sigma, eps, _ = model.solve(method=method)
+        assert np.abs(u.cpu().numpy() - g["solid.u"]).max() <= tol * np.abs(g["solid.u"]).max()
+        assert np.abs(sigma.cpu().numpy() - g["solid.sigma"]).max() <= 10 * tol * np.abs(g["solid.sigma"]).max()

@@ -71,3 +71,4 @@ def test_hyperelastic_and_conductivity(mods):
         gi, f0 = torch.rand(4, 1, d, generator=g), torch.rand(4, 1, d, generator=g)
         for x, y in zip(ka.step(gi, f0, f0, torch.zeros(4, 0), 0 * gi, None, 0), kb.step(gi, f0, f0, torch.zeros(4, 0), 0 * gi, None, 0)):
             assert torch.allclose(x, y, atol=1e-12)
+

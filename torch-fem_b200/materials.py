@@ -201,18 +201,9 @@ def _isotropic_tensor(lbd: Tensor, G: Tensor, d: int) -> Tensor:
     return lbd[..., None, None, None, None] * vol + G[..., None, None, None, None] * sym
 
 
-class IsotropicElasticity3D(Material):
-    """Small-strain isotropic elasticity; `C` is [..., 3,3,3,3] (reference elasticity.py:11-127)."""
-
-    def __init__(self, E, nu, rho=1.0):
-        self.E = torch.as_tensor(E)
-        self.nu = torch.as_tensor(nu)
-        self.rho = torch.as_tensor(rho)
-        self.n_state = 0
-        self.is_vectorized = self.E.dim() > 0
-        self.lbd = self.E * self.nu / ((1.0 + self.nu) * (1.0 - 2.0 * self.nu))
-        self.G = self.E / (2.0 * (1.0 + self.nu))
-        self.C = _isotropic_tensor(self.lbd, self.G, 3)
+class _LinearElasticity(Material):
+    """Small-strain linear elasticity with a constant stiffness tensor `C` [..., d,d,d,d]: the stress update shared by
+    the isotropic and orthotropic materials."""
 
     def step(self, H_inc, F, stress, state, de0, cl, iter):
         """sigma_{n+1} = sigma_n + C : (sym(dH) - de0); tangent = C (elasticity.py:119-127)."""
@@ -226,6 +217,20 @@ class IsotropicElasticity3D(Material):
             return step_points_loop(self, H_all, F_all, stress_all, state_all, de0, cl, iter)
         de = 0.5 * (H_all + H_all.transpose(-1, -2)) - de0
         return stress_all + _ddot(self.C, de), state_all, self.C
+
+
+class IsotropicElasticity3D(_LinearElasticity):
+    """Small-strain isotropic elasticity; `C` is [..., 3,3,3,3] (reference elasticity.py:11-127)."""
+
+    def __init__(self, E, nu, rho=1.0):
+        self.E = torch.as_tensor(E)
+        self.nu = torch.as_tensor(nu)
+        self.rho = torch.as_tensor(rho)
+        self.n_state = 0
+        self.is_vectorized = self.E.dim() > 0
+        self.lbd = self.E * self.nu / ((1.0 + self.nu) * (1.0 - 2.0 * self.nu))
+        self.G = self.E / (2.0 * (1.0 + self.nu))
+        self.C = _isotropic_tensor(self.lbd, self.G, 3)
 
 
 class IsotropicElasticityPlaneStress(IsotropicElasticity3D):
@@ -308,6 +313,139 @@ class HyperelasticPlaneStrain(Hyperelastic3D):
         return P, state, tangent
 
 
+# ------------------------------------------------------------------------------------------------ orthotropy
+_VOIGT_PAIRS = {2: ((0, 0), (1, 1), (0, 1)), 3: ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))}
+
+
+def _voigt_matrix(C: Tensor) -> Tensor:
+    """[..., d,d,d,d] -> Voigt matrix [..., m, m] (m = 3 or 6; component order 11, 22, (33, 23, 13,) 12 as in the
+    reference's utils.stiffness2voigt)."""
+    pairs = _VOIGT_PAIRS[C.shape[-1]]
+    return torch.stack([torch.stack([C[..., i, j, k, l] for (k, l) in pairs], -1) for (i, j) in pairs], -2)
+
+
+def _tensor_from_voigt(V: Tensor, d: int) -> Tensor:
+    """Voigt matrix [..., m, m] -> tensor [..., d,d,d,d] with minor symmetries."""
+    pairs = _VOIGT_PAIRS[d]
+    lookup = {}
+    for a, (i, j) in enumerate(pairs):
+        lookup[(i, j)] = lookup[(j, i)] = a
+    rows = []
+    for i in range(d):
+        for j in range(d):
+            rows.append(torch.stack([V[..., lookup[(i, j)], lookup[(k, l)]] for k in range(d) for l in range(d)], -1))
+    return torch.stack(rows, -2).reshape(*V.shape[:-2], d, d, d, d)
+
+
+def _rotate4(C: Tensor, R: Tensor) -> Tensor:
+    """C'_mnop = R_mi R_nj R_ok R_pl C_ijkl, two indices at a time."""
+    half = torch.einsum("...mi,...nj,...ijkl->...mnkl", R, R, C)
+    return torch.einsum("...ok,...pl,...mnkl->...mnop", R, R, half)
+
+
+class OrthotropicElasticity3D(_LinearElasticity):
+    """Small-strain orthotropic elasticity from nine engineering constants (reference elasticity.py:324-522). The
+    normal block of the stiffness is the inverse of the 3x3 compliance block (1/E_i on the diagonal, -nu_ij/E_i off
+    it); the shear moduli fill the rest. `rotate(R)` turns the material axes; the engineering constants of the
+    result are the apparent ones along the global axes, read off the rotated compliance."""
+
+    _dim = 3
+
+    def __init__(self, E_1, E_2, E_3, nu_12, nu_13, nu_23, G_12, G_13, G_23, rho=1.0):
+        t = torch.as_tensor
+        self.E_1, self.E_2, self.E_3 = t(E_1), t(E_2), t(E_3)
+        self.nu_12, self.nu_13, self.nu_23 = t(nu_12), t(nu_13), t(nu_23)
+        self.nu_21 = self.E_2 / self.E_1 * self.nu_12
+        self.nu_31 = self.E_3 / self.E_1 * self.nu_13
+        self.nu_32 = self.E_3 / self.E_2 * self.nu_23
+        self.G_12, self.G_13, self.G_23 = t(G_12), t(G_13), t(G_23)
+        self.rho = t(rho)
+        self.n_state = 0
+        self.is_vectorized = self.E_1.dim() > 0
+        one = torch.ones_like(self.E_1 * self.E_2 * self.E_3 * self.nu_12 * self.nu_13 * self.nu_23, dtype=torch.get_default_dtype())
+        S = torch.stack([
+            torch.stack([one / self.E_1, -self.nu_12 / self.E_1 * one, -self.nu_13 / self.E_1 * one], -1),
+            torch.stack([-self.nu_12 / self.E_1 * one, one / self.E_2, -self.nu_23 / self.E_2 * one], -1),
+            torch.stack([-self.nu_13 / self.E_1 * one, -self.nu_23 / self.E_2 * one, one / self.E_3], -1)], -2)
+        normal = torch.linalg.inv(S)
+        V = torch.zeros(*one.shape, 6, 6, dtype=normal.dtype)
+        V[..., :3, :3] = normal
+        V[..., 3, 3], V[..., 4, 4], V[..., 5, 5] = self.G_23 * one, self.G_13 * one, self.G_12 * one
+        self.C = _tensor_from_voigt(V, 3)
+
+    def rotate(self, R: Tensor):
+        d = self._dim
+        if R.shape[-2] != d or R.shape[-1] != d:
+            raise ValueError(f"Rotation matrix must be a {d}x{d} tensor.")
+        out = copy.copy(self)
+        out.C = _rotate4(self.C, R.to(self.C))
+        S = torch.linalg.inv(_voigt_matrix(out.C))
+        out.E_1, out.E_2 = 1.0 / S[..., 0, 0], 1.0 / S[..., 1, 1]
+        out.nu_12 = -S[..., 0, 1] / S[..., 0, 0]
+        if d == 3:
+            out.E_3 = 1.0 / S[..., 2, 2]
+            out.nu_13, out.nu_23 = -S[..., 0, 2] / S[..., 0, 0], -S[..., 1, 2] / S[..., 1, 1]
+            out.G_23, out.G_13, out.G_12 = 1.0 / S[..., 3, 3], 1.0 / S[..., 4, 4], 1.0 / S[..., 5, 5]
+        else:
+            out.G_12 = 1.0 / S[..., 2, 2]
+        return out
+
+
+class TransverseIsotropicElasticity3D(OrthotropicElasticity3D):
+    """Axis 1 is the symmetry axis, the 2-3 plane is isotropic: five constants (reference elasticity.py:525-571)."""
+
+    def __init__(self, E_L, E_T, nu_L, nu_T, G_L, rho=1.0):
+        if bool(torch.any(torch.as_tensor(G_L) > torch.as_tensor(E_L) / (2 * (1 + torch.as_tensor(nu_L))))):
+            raise ValueError("G must be less than E_L/(2*(1+nu_L))")
+        G_T = torch.as_tensor(E_T) / (2 * (1 + torch.as_tensor(nu_T)))
+        super().__init__(E_L, E_T, E_T, nu_L, nu_L, nu_T, G_L, G_L, G_T, rho)
+
+
+class OrthotropicElasticityPlaneStress(OrthotropicElasticity3D):
+    """sigma_33 = 0 (reference elasticity.py:574-676): the in-plane stiffness is the inverse of the 2x2 in-plane
+    compliance. `G_13` / `G_23` do not enter it; they are kept when given (the reference's shells read them)."""
+
+    _dim = 2
+
+    def __init__(self, E_1, E_2, nu_12, G_12, G_13=None, G_23=None, rho=1.0):
+        t = torch.as_tensor
+        self.E_1, self.E_2, self.nu_12, self.G_12 = t(E_1), t(E_2), t(nu_12), t(G_12)
+        self.nu_21 = self.E_2 / self.E_1 * self.nu_12
+        if G_13 is not None:
+            self.G_13 = t(G_13)
+        if G_23 is not None:
+            self.G_23 = t(G_23)
+        self.rho = t(rho)
+        self.n_state = 0
+        self.is_vectorized = self.E_1.dim() > 0
+        one = torch.ones_like(self.E_1 * self.E_2 * self.nu_12 * self.G_12, dtype=torch.get_default_dtype())
+        S = torch.stack([torch.stack([one / self.E_1, -self.nu_12 / self.E_1 * one], -1),
+                         torch.stack([-self.nu_12 / self.E_1 * one, one / self.E_2], -1)], -2)
+        V = torch.zeros(*one.shape, 3, 3, dtype=S.dtype)
+        V[..., :2, :2] = torch.linalg.inv(S)
+        V[..., 2, 2] = self.G_12 * one
+        self.C = _tensor_from_voigt(V, 2)
+
+
+class OrthotropicElasticityPlaneStrain(OrthotropicElasticity3D):
+    """eps_33 = 0 (reference elasticity.py:679-793): the in-plane part of the 3-D orthotropic stiffness."""
+
+    _dim = 2
+
+    def __init__(self, E_1, E_2, E_3, nu_12, nu_13, nu_23, G_12, G_13=None, G_23=None, rho=1.0):
+        full = OrthotropicElasticity3D(E_1, E_2, E_3, nu_12, nu_13, nu_23, G_12,
+                                       G_12 if G_13 is None else G_13, G_12 if G_23 is None else G_23, rho)
+        for name in ("E_1", "E_2", "E_3", "nu_12", "nu_21", "nu_13", "nu_31", "nu_23", "nu_32", "G_12", "rho"):
+            setattr(self, name, getattr(full, name))
+        if G_13 is not None:
+            self.G_13 = full.G_13
+        if G_23 is not None:
+            self.G_23 = full.G_23
+        self.n_state = 0
+        self.is_vectorized = full.is_vectorized
+        self.C = full.C[..., :2, :2, :2, :2].clone()
+
+
 class _IsotropicConductivity(Material):
     """Fourier conduction q = kappa grad T; `KAPPA` is [..., d, d] (reference conductivity.py:11-240)."""
 
@@ -338,8 +476,49 @@ class IsotropicConductivity1D(_IsotropicConductivity):
     _dim = 1
 
 
+class _OrthotropicConductivity(_IsotropicConductivity):
+    """Conductivities along the material axes, KAPPA = diag(kappa_i); `rotate(R)` gives R KAPPA R^T (reference
+    conductivity.py:143-242)."""
+
+    def __init__(self, *kappas, rho=1.0):
+        if len(kappas) != self._dim:
+            raise TypeError(f"expected {self._dim} conductivities")
+        ks = [torch.as_tensor(k) for k in kappas]
+        for i, k in enumerate(ks):
+            setattr(self, f"kappa_{i + 1}", k)
+        self.rho = torch.as_tensor(rho)
+        self.n_state = 0
+        self.is_vectorized = ks[0].dim() > 0
+        self.KAPPA = torch.diag_embed(torch.stack(torch.broadcast_tensors(*ks), -1).to(torch.get_default_dtype()))
+
+    def rotate(self, R: Tensor):
+        d = self._dim
+        if R.shape[-2] != d or R.shape[-1] != d:
+            raise ValueError(f"Rotation matrix must be a {d}x{d} tensor.")
+        out = copy.copy(self)
+        R = R.to(self.KAPPA)
+        out.KAPPA = R @ self.KAPPA @ R.transpose(-1, -2)
+        return out
+
+
+class OrthotropicConductivity3D(_OrthotropicConductivity):
+    _dim = 3
+
+    def __init__(self, kappa_1, kappa_2, kappa_3, rho=1.0):
+        super().__init__(kappa_1, kappa_2, kappa_3, rho=rho)
+
+
+class OrthotropicConductivity2D(_OrthotropicConductivity):
+    _dim = 2
+
+    def __init__(self, kappa_1, kappa_2, rho=1.0):
+        super().__init__(kappa_1, kappa_2, rho=rho)
+
+
 __all__ = [
     "Material", "IsotropicElasticity3D", "IsotropicElasticityPlaneStress", "IsotropicElasticityPlaneStrain",
     "Hyperelastic3D", "HyperelasticPlaneStrain", "IsotropicConductivity3D", "IsotropicConductivity2D",
-    "IsotropicConductivity1D",
+    "IsotropicConductivity1D", "OrthotropicElasticity3D", "TransverseIsotropicElasticity3D",
+    "OrthotropicElasticityPlaneStress", "OrthotropicElasticityPlaneStrain", "OrthotropicConductivity3D",
+    "OrthotropicConductivity2D",
 ]
