@@ -576,6 +576,59 @@ def orthotropic():
     print("orthotropic: C_1111", out["o3.C"][0, 0, 0, 0], "u max", np.abs(out["solid.u"]).max())
 
 
+def loads():
+    """Consistent nodal loads (reference base.py:452-568; set-ups after reference tests/test_loads.py): body, surface
+    (scalar pressure and traction vector) and line loads on distorted linear / quadratic meshes, heat flux on a face."""
+    from torchfem.elements import linear_to_quadratic
+
+    out = {}
+    solid_mat = M.IsotropicElasticity3D(1000.0, 0.3)
+    plane_mat = M.IsotropicElasticityPlaneStress(1000.0, 0.3)
+    for tag, gen, quadratic in (("hexa1", mesh.cube_hexa, False), ("hexa2", mesh.cube_hexa, True),
+                                ("tetra1", mesh.cube_tetra, False), ("tetra2", mesh.cube_tetra, True)):
+        nodes, elements = gen(4, 3, 3, 1.5, 1.0, 1.0)
+        on_top = nodes[:, 2] == 1.0
+        boundary = (nodes[:, 0] == 0.0) | (nodes[:, 0] == 1.5) | (nodes[:, 1] == 0.0) | (nodes[:, 1] == 1.0) \
+            | (nodes[:, 2] == 0.0) | (nodes[:, 2] == 1.0)
+        inner = ~boundary
+        nodes = nodes.clone()
+        nodes[inner] = distort(nodes, 0.1, 11)[inner]
+        if quadratic:
+            top_xy = nodes[on_top][:, :2]
+            nodes, elements = linear_to_quadratic(nodes, elements)
+            on_top = torch.isclose(nodes[:, 2], torch.tensor(1.0))
+            boundary = torch.zeros(len(nodes), dtype=torch.bool)
+            for c, hi in ((0, 1.5), (1, 1.0), (2, 1.0)):
+                boundary |= torch.isclose(nodes[:, c], torch.tensor(0.0)) | torch.isclose(nodes[:, c], torch.tensor(hi))
+        model = Solid(nodes, elements, solid_mat)
+        out[f"{tag}.nodes"], out[f"{tag}.elements"] = npy(nodes), npy(elements)
+        out[f"{tag}.top"], out[f"{tag}.boundary"] = npy(on_top), npy(boundary)
+        out[f"{tag}.body"] = npy(model.integrate_body_load(torch.tensor([0.0, 0.0, -9.81])))
+        out[f"{tag}.pressure_top"] = npy(model.integrate_surface_load(on_top, -2.5))
+        out[f"{tag}.traction_top"] = npy(model.integrate_surface_load(on_top, torch.tensor([1.0, 0.5, -0.25])))
+        out[f"{tag}.pressure_all"] = npy(model.integrate_surface_load(boundary, 1.0))
+        out[f"{tag}.facets_top"] = npy(model._boundary_facets(on_top))
+    for tag, gen, quadratic in (("quad1", mesh.rect_quad, False), ("quad2", mesh.rect_quad, True),
+                                ("tria1", mesh.rect_tri, False), ("tria2", mesh.rect_tri, True)):
+        nodes, elements = gen(5, 4, 2.0, 1.0)
+        if quadratic:
+            nodes, elements = linear_to_quadratic(nodes, elements)
+        right = torch.isclose(nodes[:, 0], torch.tensor(2.0))
+        thickness = 0.5 + 0.1 * torch.arange(len(elements)) / len(elements)
+        model = Planar(nodes, elements, plane_mat, thickness=thickness)
+        out[f"{tag}.nodes"], out[f"{tag}.elements"], out[f"{tag}.right"] = npy(nodes), npy(elements), npy(right)
+        out[f"{tag}.thickness"] = npy(thickness)
+        out[f"{tag}.body"] = npy(model.integrate_body_load(torch.tensor([0.0, -9.81])))
+        out[f"{tag}.pressure_right"] = npy(model.integrate_line_load(right, 3.0))
+        out[f"{tag}.traction_right"] = npy(model.integrate_line_load(right, torch.tensor([1.0, -2.0])))
+    nodes, elements = mesh.cube_hexa(3, 3, 3)
+    heat = SolidHeat(nodes, elements, M.IsotropicConductivity3D(1.0))
+    out["heat.flux_top"] = npy(heat.integrate_surface_load(nodes[:, 2] == 1.0, 4.0))
+    out["heat.source"] = npy(heat.integrate_body_load(2.0))
+    np.savez_compressed(os.path.join(OUT, "loads.npz"), **out)
+    print("loads: hexa1 pressure_top sum", out["hexa1.pressure_top"].sum(0), "tria2 line", out["tria2.pressure_right"].sum(0))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
         for name in sys.argv[1:]:
@@ -591,5 +644,6 @@ if __name__ == "__main__":
     modal()
     assembly_cases()
     orthotropic()
+    loads()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

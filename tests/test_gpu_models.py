@@ -646,3 +646,36 @@ def test_block_with_rotated_orthotropic_material(T):
         u, f, sigma, eps, _ = model.solve(method=method)
         assert np.abs(u.cpu().numpy() - g["solid.u"]).max() <= tol * np.abs(g["solid.u"]).max()
         assert np.abs(sigma.cpu().numpy() - g["solid.sigma"]).max() <= 10 * tol * np.abs(g["solid.sigma"]).max()
+
+
+@pytest.mark.parametrize("tag", ["hexa2", "tetra1", "tria2", "quad1"])
+def test_consistent_nodal_loads(T, tag):
+    """`integrate_body_load` / `integrate_surface_load` / `integrate_line_load` (reference base.py:446-568) on the
+    device against the reference's vectors (`oracle/make_golden.py::loads`); tests/test_loads_host_cpu.py covers all
+    element types on the CPU."""
+    from torchfem_b200.materials import IsotropicElasticity3D, IsotropicElasticityPlaneStress
+
+    g = load_case("loads.npz")
+    nodes, elements = torch.tensor(g[f"{tag}.nodes"]), torch.tensor(g[f"{tag}.elements"])
+
+    def close(got, ref):
+        assert np.abs(got.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+
+    if nodes.shape[1] == 3:
+        model = T.Solid(nodes, elements, IsotropicElasticity3D(1000.0, 0.3))
+        top = torch.tensor(g[f"{tag}.top"])
+        assert np.array_equal(model._boundary_facets(top).cpu().numpy(), g[f"{tag}.facets_top"])
+        close(model.integrate_body_load(torch.tensor([0.0, 0.0, -9.81])), g[f"{tag}.body"])
+        close(model.integrate_surface_load(top, -2.5), g[f"{tag}.pressure_top"])
+        close(model.integrate_surface_load(top, torch.tensor([1.0, 0.5, -0.25])), g[f"{tag}.traction_top"])
+        model.forces = model.integrate_surface_load(top, -2.5)          # a load vector is what `forces` takes
+        model.constraints[nodes[:, 2] == 0.0, :] = True
+        u = model.solve()[0]
+        assert float(u[top][:, 2].mean()) < 0.0
+    else:
+        model = T.Planar(nodes, elements, IsotropicElasticityPlaneStress(1000.0, 0.3),
+                         thickness=torch.tensor(g[f"{tag}.thickness"]))
+        right = torch.tensor(g[f"{tag}.right"])
+        close(model.integrate_body_load(torch.tensor([0.0, -9.81])), g[f"{tag}.body"])
+        close(model.integrate_line_load(right, 3.0), g[f"{tag}.pressure_right"])
+        close(model.integrate_line_load(right, torch.tensor([1.0, -2.0])), g[f"{tag}.traction_right"])

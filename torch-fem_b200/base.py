@@ -337,6 +337,71 @@ class FEM(ABC):
             m += float(w) * blk.reshape(self.n_elem, nn * dpn, nn * dpn)
         return m
 
+    # ---- consistent nodal loads (reference base.py:446-568); host-side torch, differentiable w.r.t. the load
+    def _nodal_sum(self, conn: Tensor, contrib: Tensor) -> Tensor:
+        """Sum per-node contributions [n, nodes per entity, k] of elements or facets into [n_nod, k]."""
+        out = torch.zeros(self.n_nod, contrib.shape[-1], dtype=contrib.dtype, device=self.device)
+        return out.index_add_(0, conn.reshape(-1), contrib.reshape(-1, contrib.shape[-1]))
+
+    def _boundary_facets(self, mask: Tensor) -> Tensor:
+        """Facets whose nodes all lie in the nodal mask and that belong to one element only (an interior facet is
+        listed by both neighbours), in the winding of the element that owns them (reference base.py:452-470)."""
+        table = self.etype.facets.to(self.device)
+        facets = self.elements[:, table].reshape(-1, table.shape[1])
+        facets = facets[mask.to(self.device)[facets].all(dim=1)]
+        _, inverse, count = torch.unique(facets.sort(dim=1).values, dim=0, return_inverse=True, return_counts=True)
+        order = torch.argsort(inverse, stable=True)             # occurrences grouped by facet, first occurrence first
+        start = torch.cumsum(count, 0) - count
+        return facets[order[start[count == 1]]]
+
+    def _integrate_facet_load(self, conn: Tensor, ftype: type[Element], load: Tensor) -> Tensor:
+        kw = dict(dtype=self.nodes.dtype, device=self.device)
+        xi = ftype.ipoints.to(**kw)
+        w, N = ftype.iweights.to(**kw), ftype.N(xi)
+        J = torch.einsum("qaN,eNj->qeaj", ftype.B(xi), self.nodes[conn])      # tangent vectors of the facet
+        # outward normal scaled by the facet metric: t_1 x t_2 on a face, the tangent turned clockwise on an edge
+        if J.shape[-2] == 2:
+            normal = torch.linalg.cross(J[..., 0, :], J[..., 1, :], dim=-1)
+        else:
+            normal = torch.stack([J[..., 0, 1], -J[..., 0, 0]], dim=-1)
+        metric = torch.linalg.norm(normal, dim=-1)
+        if load.dim() == 0 and self.n_dof_per_node > 1:
+            # a scalar on a vector field is a pressure along the outward normal
+            value = load * normal / metric[..., None]
+        else:
+            per_facet = load if load.dim() == 2 else load.reshape(1, -1)
+            value = per_facet.expand(len(conn), -1).expand(len(xi), -1, -1)
+        return self._nodal_sum(conn, torch.einsum("q,qn,qe,qek->enk", w, N, metric, value))
+
+    def integrate_body_load(self, load: float | Tensor) -> Tensor:
+        """Consistent nodal loads [n_nod, k] of a load per unit volume: a vector [k] for the whole model or one per
+        element [n_elem, k] (gravity, heat source); planar models include their thickness (base.py:496-513)."""
+        load = torch.as_tensor(load, dtype=self.nodes.dtype, device=self.device)
+        per_elem = load if load.dim() == 2 else load.reshape(1, -1)
+        weights = self.integrate_shape_functions() * self.volume_scale[:, None]
+        return self._nodal_sum(self.elements, weights[:, :, None] * per_elem.expand(self.n_elem, -1)[:, None, :])
+
+    def integrate_surface_load(self, mask: Tensor, load: float | Tensor) -> Tensor:
+        """Consistent nodal loads of a load per unit area on the boundary faces inside a nodal mask: a scalar is a
+        pressure along the outward normal (a flux for scalar fields), a vector a traction in global coordinates, a
+        [n_facets, k] tensor one value per face (base.py:515-539)."""
+        if self.etype.iso_dim != 3:
+            raise NotImplementedError(f"{type(self).__name__} has no surfaces to load. "
+                                      "Use integrate_line_load(...) or integrate_body_load(...) instead.")
+        load = torch.as_tensor(load, dtype=self.nodes.dtype, device=self.device)
+        return self._integrate_facet_load(self._boundary_facets(mask), self.etype.facet_type, load)
+
+    def integrate_line_load(self, mask: Tensor, load: float | Tensor) -> Tensor:
+        """The same per unit length on the boundary edges of a planar model (base.py:541-568)."""
+        if self.etype.iso_dim != 2:
+            raise NotImplementedError(f"{type(self).__name__} has no edges to load. "
+                                      "Use integrate_surface_load(...) or integrate_body_load(...) instead.")
+        load = torch.as_tensor(load, dtype=self.nodes.dtype, device=self.device)
+        if load.dim() == 0 and self.n_dim == 3:
+            raise ValueError("A line in 3D has no unique normal, so a scalar load is ambiguous. "
+                             "Pass a load vector instead.")
+        return self._integrate_facet_load(self._boundary_facets(mask), self.etype.facet_type, load)
+
     # ---- element matrices / assembly
     def k0(self) -> Tensor:
         """Element matrix of the reference state, [n_elem, nd, nd] (reference base.py:228-245)."""

@@ -77,6 +77,40 @@ class Element:
         return cls
 
     @classmethod
+    def _corner_facets(cls) -> list[list[int]]:
+        """Corner nodes of every codimension-1 facet, wound so that the normal points out of the element."""
+        raise NotImplementedError
+
+    @_classproperty
+    def facets(cls) -> Tensor:
+        """Facet connectivity (edges of a planar element, faces of a solid one), corner nodes first in outward
+        winding, then — on quadratic elements — the mid-side node after each corner (reference elements.py
+        `facets`, e.g. :954-966 for Hexa1); derived here from the reference coordinates."""
+        iso = np.asarray(cls._ISO, dtype=float)
+        nc = cls._n_corner()
+        rows = []
+        for corners in cls._corner_facets():
+            row = list(corners)
+            if cls.nodes > nc:
+                ring = corners if len(corners) > 2 else corners[:1]     # an edge has one mid node, a face one per side
+                for k, a in enumerate(ring):
+                    b = corners[(k + 1) % len(corners)]
+                    mid = 0.5 * (iso[a] + iso[b])
+                    row.append(next(m for m in range(nc, cls.nodes) if np.allclose(iso[m], mid)))
+            rows.append(row)
+        return torch.tensor(rows)
+
+    @_classproperty
+    def facet_type(cls) -> type["Element"]:
+        """Element type of a facet: Bar for planar elements, Tria / Quad for tetrahedra / hexahedra, of the same order."""
+        quadratic = cls.nodes > cls._n_corner()
+        if cls.iso_dim == 2:
+            return Bar2 if quadratic else Bar1
+        if issubclass(cls, _Simplex):
+            return Tria2 if quadratic else Tria1
+        return Quad2 if quadratic else Quad1
+
+    @classmethod
     def N(cls, xi: Tensor) -> Tensor:
         raise NotImplementedError
 
@@ -96,6 +130,13 @@ class _Box(Element):
     @classmethod
     def _n_corner(cls):
         return 2 ** cls.iso_dim
+
+    @classmethod
+    def _corner_facets(cls):
+        if cls.iso_dim == 2:     # the four sides in node order (counter-clockwise numbering: outward normals)
+            return [[k, (k + 1) % 4] for k in range(4)]
+        # bottom seen from below, top seen from above, then the four sides around the axis
+        return [[0, 3, 2, 1], [4, 5, 6, 7]] + [[k, (k + 1) % 4, (k + 1) % 4 + 4, k + 4] for k in range(4)]
 
     @classmethod
     def N(cls, xi: Tensor) -> Tensor:
@@ -222,6 +263,18 @@ class _Simplex(Element):
         return cls.iso_dim + 1
 
     @classmethod
+    def _corner_facets(cls):
+        if cls.iso_dim == 2:
+            return [[0, 1], [1, 2], [2, 0]]
+        iso = np.asarray(cls._ISO[:4], dtype=float)
+        faces = []
+        for opposite in (3, 2, 0, 1):      # the face opposite each vertex, lowest node first, normal pointing away from it
+            a, b, c = [v for v in range(4) if v != opposite]
+            normal = np.cross(iso[b] - iso[a], iso[c] - iso[a])
+            faces.append([a, b, c] if normal @ (iso[a] - iso[opposite]) > 0 else [a, c, b])
+        return faces
+
+    @classmethod
     def _lambda(cls, xi: Tensor) -> Tensor:
         return torch.cat([1.0 - xi.sum(-1, keepdim=True), xi], dim=-1)  # [..., d+1]
 
@@ -326,6 +379,63 @@ class Tetra2(Tetra1):
     @_classproperty
     def iweights(cls) -> Tensor:
         return torch.tensor([0.041666667] * 4)  # sic (elements.py:921-922)
+
+
+# ------------------------------------------------------------------------------------------ line facets
+class Bar1(Element):
+    """Two-node line: the facet of linear planar elements (reference elements.py:174-235). Facet use only — bar
+    *models* (trusses) are outside this package."""
+
+    iso_volume, iso_dim, nodes = 2.0, 1, 2
+    _ISO = [[-1.0], [1.0]]
+
+    @classmethod
+    def _n_corner(cls):
+        return 2
+
+    @classmethod
+    def N(cls, xi: Tensor) -> Tensor:
+        x = xi[..., 0]
+        return torch.stack([0.5 * (1.0 - x), 0.5 * (1.0 + x)], dim=-1)
+
+    @classmethod
+    def B(cls, xi: Tensor) -> Tensor:
+        x = xi[..., 0]
+        return torch.stack([-0.5 + 0.0 * x, 0.5 + 0.0 * x], dim=-1).unsqueeze(-2)
+
+    @_classproperty
+    def ipoints(cls) -> Tensor:
+        return torch.tensor([[0.0]])
+
+    @_classproperty
+    def iweights(cls) -> Tensor:
+        return torch.tensor([2.0])
+
+
+class Bar2(Bar1):
+    """Three-node line (end nodes, then the mid node): the facet of quadratic planar elements (elements.py:238-300)."""
+
+    nodes = 3
+    _ISO = [[-1.0], [1.0], [0.0]]
+
+    @classmethod
+    def N(cls, xi: Tensor) -> Tensor:
+        x = xi[..., 0]
+        return torch.stack([0.5 * x * (x - 1.0), 0.5 * x * (x + 1.0), 1.0 - x * x], dim=-1)
+
+    @classmethod
+    def B(cls, xi: Tensor) -> Tensor:
+        x = xi[..., 0]
+        return torch.stack([x - 0.5, x + 0.5, -2.0 * x], dim=-1).unsqueeze(-2)
+
+    @_classproperty
+    def ipoints(cls) -> Tensor:
+        g = 1.0 / sqrt(3.0)
+        return torch.tensor([[-g], [g]])
+
+    @_classproperty
+    def iweights(cls) -> Tensor:
+        return torch.tensor([1.0, 1.0])
 
 
 def linear_etype(nodes: Tensor, elements: Tensor) -> type[Element]:
