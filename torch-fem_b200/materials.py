@@ -368,7 +368,7 @@ class OrthotropicElasticity3D(_LinearElasticity):
             torch.stack([-self.nu_12 / self.E_1 * one, one / self.E_2, -self.nu_23 / self.E_2 * one], -1),
             torch.stack([-self.nu_13 / self.E_1 * one, -self.nu_23 / self.E_2 * one, one / self.E_3], -1)], -2)
         normal = torch.linalg.inv(S)
-        V = torch.zeros(*one.shape, 6, 6, dtype=normal.dtype)
+        V = torch.zeros(*one.shape, 6, 6, dtype=normal.dtype, device=normal.device)
         V[..., :3, :3] = normal
         V[..., 3, 3], V[..., 4, 4], V[..., 5, 5] = self.G_23 * one, self.G_13 * one, self.G_12 * one
         self.C = _tensor_from_voigt(V, 3)
@@ -421,7 +421,7 @@ class OrthotropicElasticityPlaneStress(OrthotropicElasticity3D):
         one = torch.ones_like(self.E_1 * self.E_2 * self.nu_12 * self.G_12, dtype=torch.get_default_dtype())
         S = torch.stack([torch.stack([one / self.E_1, -self.nu_12 / self.E_1 * one], -1),
                          torch.stack([-self.nu_12 / self.E_1 * one, one / self.E_2], -1)], -2)
-        V = torch.zeros(*one.shape, 3, 3, dtype=S.dtype)
+        V = torch.zeros(*one.shape, 3, 3, dtype=S.dtype, device=S.device)
         V[..., :2, :2] = torch.linalg.inv(S)
         V[..., 2, 2] = self.G_12 * one
         self.C = _tensor_from_voigt(V, 2)
