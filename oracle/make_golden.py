@@ -629,6 +629,41 @@ def loads():
     print("loads: hexa1 pressure_top sum", out["hexa1.pressure_top"].sum(0), "tria2 line", out["tria2.pressure_right"].sum(0))
 
 
+def hyper_plane_stress():
+    """`HyperelasticPlaneStress` (reference hyperelasticity.py:130-269): one material update on random states, and a
+    Neo-Hookean strip stretched by 30 % in three increments with `nlgeom=True` (state = thickness stretch - 1)."""
+    g = torch.Generator().manual_seed(21)
+    mu, lbd = 384.6153846153846, 576.9230769230769
+
+    def psi(F, params):
+        Cg = F.transpose(-1, -2) @ F
+        logJ = 0.5 * torch.logdet(Cg)
+        return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+
+    out = {}
+    n = 6
+    mat = M.HyperelasticPlaneStress(psi, torch.tensor([mu, lbd])).vectorize(n)
+    F = torch.eye(2).expand(n, 2, 2) + 0.1 * torch.randn(n, 2, 2, generator=g)
+    H = 0.02 * torch.randn(n, 2, 2, generator=g)
+    state = 0.01 * torch.randn(n, 1, generator=g)
+    P, st, dd = mat.step(H, F, torch.zeros(n, 2, 2), state, torch.zeros(n, 2, 2), torch.ones(n, 1), 0)
+    out["F"], out["H"], out["state"] = npy(F), npy(H), npy(state)
+    out["P"], out["state_new"], out["ddsdde"] = npy(P), npy(st), npy(dd)
+
+    nodes, elements = mesh.rect_quad(5, 3, 2.0, 1.0)
+    strip = Planar(nodes, elements, M.HyperelasticPlaneStress(psi, torch.tensor([mu, lbd])))
+    left, right = nodes[:, 0] == 0.0, nodes[:, 0] == 2.0
+    strip.constraints[left, 0] = True
+    strip.constraints[right, 0] = True
+    strip.constraints[nodes[:, 1] == 0.5, 1] = True
+    strip.displacements[right, 0] = 0.6
+    inc = torch.linspace(0.0, 1.0, 4)
+    u, f, sigma, Fd, alpha = strip.solve(increments=inc, nlgeom=True, method="spsolve")
+    out["strip.u"], out["strip.f"], out["strip.sigma"], out["strip.state"] = npy(u), npy(f), npy(sigma), npy(alpha)
+    np.savez_compressed(os.path.join(OUT, "hyper_plane_stress.npz"), **out)
+    print("hyper plane stress: reaction", float(f[right, 0].sum()), "thickness stretch", float(alpha.mean()) + 1.0)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
         for name in sys.argv[1:]:
@@ -645,5 +680,6 @@ if __name__ == "__main__":
     assembly_cases()
     orthotropic()
     loads()
+    hyper_plane_stress()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -679,3 +679,30 @@ def test_consistent_nodal_loads(T, tag):
         close(model.integrate_body_load(torch.tensor([0.0, -9.81])), g[f"{tag}.body"])
         close(model.integrate_line_load(right, 3.0), g[f"{tag}.pressure_right"])
         close(model.integrate_line_load(right, torch.tensor([1.0, -2.0])), g[f"{tag}.traction_right"])
+
+
+def test_hyperelastic_plane_stress_strip(T):
+    """`HyperelasticPlaneStress` (reference hyperelasticity.py:130-269): Neo-Hookean strip stretched
+    by 30 % in three `nlgeom` increments, thickness stretch carried as a state variable; the device path updates all
+    Gauss points in one batch (`step_points`), the reference one Gauss point at a time — the local Newton iteration
+    stops at |P_33| < 1e-5, so the two agree to that tolerance's effect, not to round-off."""
+    from torchfem_b200.materials import HyperelasticPlaneStress
+    from torchfem_b200.mesh import rect_quad
+
+    def psi(F, params):
+        Cg = F.transpose(-1, -2) @ F
+        logJ = 0.5 * torch.logdet(Cg)
+        return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+
+    g = load_case("hyper_plane_stress.npz")
+    nodes, elements = rect_quad(5, 3, 2.0, 1.0)
+    strip = T.Planar(nodes, elements, HyperelasticPlaneStress(psi, torch.tensor([384.6153846153846, 576.9230769230769])))
+    left, right = nodes[:, 0] == 0.0, nodes[:, 0] == 2.0
+    strip.constraints[left, 0] = True
+    strip.constraints[right, 0] = True
+    strip.constraints[nodes[:, 1] == 0.5, 1] = True
+    strip.displacements[right, 0] = 0.6
+    u, f, sigma, F, alpha = strip.solve(increments=torch.linspace(0.0, 1.0, 4), nlgeom=True, method="spsolve")
+    assert np.abs(u.cpu().numpy() - g["strip.u"]).max() <= 1e-6 * np.abs(g["strip.u"]).max()
+    assert np.abs(alpha.cpu().numpy() - g["strip.state"]).max() <= 1e-5 * np.abs(g["strip.state"]).max()
+    assert abs(float(f[right, 0].sum()) - float(g["strip.f"][np.isclose(nodes.cpu().numpy()[:, 0], 2.0), 0].sum())) <= 1e-5 * 250.0

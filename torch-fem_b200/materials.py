@@ -313,6 +313,58 @@ class HyperelasticPlaneStrain(Hyperelastic3D):
         return P, state, tangent
 
 
+class HyperelasticPlaneStress(Hyperelastic3D):
+    """Plane stress: the thickness stretch lambda_z is a state variable found by a local Newton iteration on
+    P_33(F_2d, lambda_z) = 0, and the in-plane tangent is condensed, C_abcd - C_ab33 C_33cd / C_3333 (reference
+    hyperelasticity.py:130-269; same iteration: every point is updated until all satisfy |P_33| < tolerance, at most
+    `max_iter` times). `n_state = 1`: state = lambda_z - 1."""
+
+    def __init__(self, psi: Callable, params, rho=1.0, tolerance: float = 1e-5, max_iter: int = 10):
+        super().__init__(psi, params, rho)
+        self.tolerance, self.max_iter = tolerance, max_iter
+        self.n_state = 1
+
+    def _evaluate(self, F2: Tensor, stretch: Tensor, params: Tensor):
+        """P and tangent of the 3-D energy at diag(F2, stretch), batched over the leading axis."""
+        F3 = torch.nn.functional.pad(F2, (0, 1, 0, 1))
+        F3 = F3 + stretch[:, None, None] * torch.nn.functional.one_hot(torch.tensor(8, device=F2.device), 9).reshape(3, 3).to(F2)
+        with torch.enable_grad(), small_matrix_mode(F3):
+            F3 = F3.requires_grad_(True) if not F3.requires_grad else F3
+            P = vmap(jacrev(self.psi))(F3, params)
+            tangent = vmap(jacrev(jacrev(self.psi)))(F3, params)
+        return P, tangent
+
+    def step(self, H_inc, F, stress, state, de0, cl, iter):
+        batch = H_inc.shape[:-2]
+        F2 = (F + H_inc).reshape(-1, 2, 2)
+        stretch = (1.0 + state[..., 0]).reshape(-1)
+        params = self.params
+        if params.dim() == 1:
+            params = params.expand(F2.shape[0], -1)
+        else:   # one set per element, shared by the Gauss points when the batch is [n_int, n_elem]
+            params = params.expand(*batch, params.shape[-1]).reshape(-1, params.shape[-1])
+        residual = None
+        for _ in range(self.max_iter):
+            P, tangent = self._evaluate(F2, stretch, params)
+            residual = P[:, 2, 2]
+            stretch = stretch - residual / tangent[:, 2, 2, 2, 2]
+            if bool((residual.abs() < self.tolerance).all()):
+                break
+        if bool((residual.abs() > self.tolerance).any()):
+            print("Local Newton iteration did not converge.")
+        condensed = tangent[:, :2, :2, :2, :2] - (tangent[:, :2, :2, 2, 2, None, None] * tangent[:, None, None, 2, 2, :2, :2]
+                                                  / tangent[:, 2, 2, 2, 2, None, None, None, None])
+        return (P[:, :2, :2].reshape(*batch, 2, 2), (stretch - 1.0).reshape(*batch, 1),
+                condensed.reshape(*batch, 2, 2, 2, 2))
+
+    def step_points(self, H_all, F_all, stress_all, state_all, de0, cl, iter, need_tangent: bool = True):
+        """All Gauss points in one batch. (The reference iterates each Gauss point's batch until that batch has
+        converged; here the convergence test spans all points, so a point may receive an extra Newton update —
+        a difference below the tolerance the iteration stops at.)"""
+        P, state, tangent = self.step(H_all, F_all, stress_all, state_all, de0, cl, iter)
+        return P, state, tangent
+
+
 # ------------------------------------------------------------------------------------------------ orthotropy
 _VOIGT_PAIRS = {2: ((0, 0), (1, 1), (0, 1)), 3: ((0, 0), (1, 1), (2, 2), (1, 2), (0, 2), (0, 1))}
 
@@ -517,7 +569,7 @@ class OrthotropicConductivity2D(_OrthotropicConductivity):
 
 __all__ = [
     "Material", "IsotropicElasticity3D", "IsotropicElasticityPlaneStress", "IsotropicElasticityPlaneStrain",
-    "Hyperelastic3D", "HyperelasticPlaneStrain", "IsotropicConductivity3D", "IsotropicConductivity2D",
+    "Hyperelastic3D", "HyperelasticPlaneStrain", "HyperelasticPlaneStress", "IsotropicConductivity3D", "IsotropicConductivity2D",
     "IsotropicConductivity1D", "OrthotropicElasticity3D", "TransverseIsotropicElasticity3D",
     "OrthotropicElasticityPlaneStress", "OrthotropicElasticityPlaneStrain", "OrthotropicConductivity3D",
     "OrthotropicConductivity2D",
