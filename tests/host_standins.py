@@ -43,6 +43,21 @@ class HostMatrix:
         assert self.symmetric
         return self
 
+    # the linear algebra `Heat.time_integration` does on matrices of one pattern (M + dt/2 K, M @ du)
+    def __mul__(self, c):
+        return self._like(self.values_ * float(c))
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        assert other.indices is self.indices
+        return self._like(self.values_ + other.values_)
+
+    def __matmul__(self, x):
+        if x.requires_grad:
+            return _HostMatvec.apply(x, self)
+        return self.matvec(x.reshape(-1)).reshape(x.shape)
+
     def matvec(self, x, fmt="auto"):
         r, c = self._indices()
         return torch.zeros(self.n, dtype=torch.float64).index_add_(0, r, self.values_ * x[c])
@@ -52,6 +67,17 @@ class HostMatrix:
         out = np.zeros((self.n, self.n))
         out[r.numpy(), c.numpy()] = self.values_.numpy()
         return out
+
+
+class _HostMatvec(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, A):
+        ctx.A = A
+        return A.matvec(x.detach().reshape(-1)).reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.A.T.matvec(g.reshape(-1)).reshape(g.shape), None
 
 
 def dense_sparse_solve(A, b, B=None, stol=1e-10, device=None, method=None, M=None, x0=None):

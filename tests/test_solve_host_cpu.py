@@ -22,6 +22,7 @@ def T(monkeypatch):
     import torchfem_b200 as TT
 
     monkeypatch.setattr(TT.sparse, "sparse_solve", dense_sparse_solve)
+    monkeypatch.setattr(TT.sparse, "_as_csr", lambda A: A)      # `Solve.backward` converts torch tensors only
 
     def make(cls):
         return lambda nodes, elements, material, thickness=1.0: host_model(cls, nodes, elements, material, thickness)
@@ -68,3 +69,13 @@ def test_hyperelastic_increments_and_parameter_gradient(T):
 
 def test_thickness_gradient_through_increments(T):
     GM.TestBase().test_planar_thickness_gradient_incremental_equals_single(T)
+
+
+@pytest.mark.parametrize("method", [None])
+def test_heat_transient_plate_and_flux_gradient(T, method):
+    GM.TestHeatTransient().test_plate_matches_reference_and_heat_flux_gradient(T, method)
+
+
+def test_heat_transient_late_start_and_solid_cube(T):
+    GM.TestHeatTransient().test_late_start_single_time_and_invalid_times(T)
+    GM.TestHeatTransient().test_solid_heat_cube(T)
