@@ -681,6 +681,10 @@ def test_consistent_nodal_loads(T, tag):
         close(model.integrate_line_load(right, torch.tensor([1.0, -2.0])), g[f"{tag}.traction_right"])
 
 
+@pytest.mark.xfail(strict=False, reason="first execution on the device pending: besides the new material it is the first "
+                                        "test to run kernel K1 with per-Gauss-point tangents on a planar element "
+                                        "(Hexa1 is covered by case_hyper_hexa1); CPU-validated in "
+                                        "tests/test_hyper_plane_stress_cpu.py — remove this mark once it has passed")
 def test_hyperelastic_plane_stress_strip(T):
     """`HyperelasticPlaneStress` (reference hyperelasticity.py:130-269): Neo-Hookean strip stretched
     by 30 % in three `nlgeom` increments, thickness stretch carried as a state variable; the device path updates all
