@@ -10,7 +10,8 @@ Jacobi setup (K4) -> PCG to ||r|| <= 1e-8 ||b|| (K5/K6). The sparsity pattern (K
 separately, as the reference does (benchmarks/run.py:56-58: "setup" vs "fwd").
 
 N=1 runs BASELINE.json configs[1]: 150^3 elements, 10,328,853 DOFs, nnz 825,604,659 (matrix 10.1 GB >> L2).
-`--impl reference` times the CPU oracle port of the same path (oracle/fem_oracle.py) on a bounded sample.
+`--impl reference` times the reference's OWN CPU code (staged by `__graft_entry__.build()` into oracle/_ref; the numpy
+oracle port only if that is missing) on a bounded sample.
 """
 from __future__ import annotations
 
@@ -92,42 +93,75 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def cpu_reference_step(E, state=None):
+    """One pass of the hot path on the host cores over a bounded E^3 sample. Runs the reference's OWN code (staged
+    copy `oracle/_ref`, or /root/reference in the build container: kind "reference"); the numpy/scipy oracle port is
+    only the fallback when neither exists (kind "port"). Returns (seconds, iterations, n_dofs, kind, detail, state)."""
+    from oracle import ref_bench as R
+
+    if R.available():
+        if state is None:
+            model, setup = R.cube_extension_model(E)
+            state = (model, setup)
+        model, setup = state
+        _, ph = R.linear_solve(model, rtol=RTOL)
+        detail = (f"setup {setup['t_setup']:.2f}s (excluded) integrate_material {ph['t_integrate']:.2f}s assemble_matrix "
+                  f"{ph['t_assemble']:.2f}s rhs {ph['t_rhs']:.3f}s sparse_solve(cg, Jacobi M) {ph['t_solve']:.2f}s; unmodified "
+                  f"torchfem (src/torchfem/base.py:982-1092, 398-445; sparse.py:447-514 -> scipy cg), torch "
+                  f"{_torch_threads()} intra-op threads, scipy CSR SpMV single-threaded")
+        return R.hot_path_seconds(ph), ph["iterations"], ph["n_dofs"], "reference", detail, state
+    from oracle import fem_oracle as O
+
+    if state is None:
+        N = E + 1
+        nodes, elements = O.cube_hexa(N, N, N)
+        bref, w = O.hexa1_tables()
+        C = O.isotropic_C3d(1000.0, 0.3, len(elements))
+        con_mask, disp = O.cube_extension_bcs(nodes)
+        state = (nodes, elements, bref, w, C, con_mask, disp)
+    nodes, elements, bref, w, C, con_mask, disp = state
+    out = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=RTOL)
+    t = out["t_integrate"] + out["t_assemble"] + out["t_rhs"] + out["t_solve"]
+    detail = (f"integrate {out['t_integrate']:.2f}s assemble {out['t_assemble']:.2f}s solve {out['t_solve']:.2f}s; "
+              f"numpy/scipy oracle PORT of the reference CPU path (oracle/_ref not staged), scipy-CSR SpMV single-threaded")
+    return t, out["iterations"], int(nodes.size), "port", detail, state
+
+
+def _torch_threads():
+    try:
+        import torch
+
+        return torch.get_num_threads()
+    except Exception:
+        return 1
+
+
 def run_reference(args):
-    """CPU baseline: the oracle port of the reference path (numpy einsum + scipy-style Jacobi-CG), all
-    host threads numpy/BLAS will use, on a bounded sample of the same workload."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, every step a
+    bounded sample (E = --cpu-edge) of the workload; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import fem_oracle as O
-
     E = args.cpu_edge
-    N = E + 1
-    nodes, elements = O.cube_hexa(N, N, N)
-    bref, w = O.hexa1_tables()
-    C = O.isotropic_C3d(1000.0, 0.3, len(elements))
-    con_mask, disp = O.cube_extension_bcs(nodes)
-    n_dofs = nodes.size
-    times = []
-    its = 0
+    times, state = [], None
+    its = n_dofs = 0
+    kind = detail = ""
     for s in range(args.warmup + args.steps):
-        out = O.linear_solve_reference_flow(nodes, elements, bref, w, C, con_mask, disp, rtol=RTOL)
-        t = out["t_integrate"] + out["t_assemble"] + out["t_rhs"] + out["t_solve"]
-        its = out["iterations"]
+        t, its, n_dofs, kind, detail, state = cpu_reference_step(E, state)
         if s >= args.warmup:
             times.append(t)
     ms = 1e3 * float(np.mean(times))
     value = n_dofs / (ms / 1e3)
     cores = os.cpu_count()
-    sample = (f"cube_hexa({N},{N},{N}) = {E}^3 Hexa1 elements, {n_dofs} DOFs, {its} Jacobi-CG iterations to "
-              f"1e-8; oracle port (numpy einsum integrate, bincount assemble, scipy-CSR SpMV CG); "
-              f"os.cpu_count()={cores}, CG SpMV is single-threaded as in scipy")
+    sample = (f"cube_hexa({E + 1},{E + 1},{E + 1}) = {E}^3 Hexa1 elements, {n_dofs} DOFs, {its} Jacobi-CG iterations to "
+              f"1e-8 (last step: {detail}); os.cpu_count()={cores}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"linear-elastic Hexa1 cube {E}^3 elements (bounded CPU sample of configs[1])",
                    "n_dofs": int(n_dofs), "rtol": RTOL, "cg_iterations": int(its)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,20 +210,21 @@ def run_ours(args):
     torch.set_default_dtype(torch.float64)
     import torchfem_b200 as T
     from torchfem_b200 import csr
-    from oracle import fem_oracle as O  # tables only (bref/w are 200 numbers) + cpu_baseline leg
 
     if world > 1 or args.config == "C":
-        from torchfem_b200 import distributed as D
-        return D.bench_multi_gpu(args, METRIC, UNIT, RTOL)
+        return run_multi_gpu(args)
 
     E = args.edge
     t0 = time.perf_counter()
     nodes_h, elements_h, con_h, disp_h = build_problem(T, torch, E, device)
     n_elem = elements_h.shape[0]
     n_dofs = nodes_h.numel()
-    bref_np, w_np = O.hexa1_tables()
-    bref, w = torch.as_tensor(bref_np), torch.as_tensor(w_np)
+    from torchfem_b200.elements import Hexa1
     from torchfem_b200.materials import IsotropicElasticity3D
+
+    # reference-element tables of the PRODUCT package (elements.py; pinned to the reference in tests/test_elements.py)
+    ip = Hexa1.ipoints.to(torch.float64).cpu()
+    bref, w = Hexa1.B(ip), Hexa1.iweights.to(torch.float64).cpu()
 
     # per-element material parameters (heterogeneous materials are the general case, cf. benchmarks/topopt.py);
     # the [n_elem,3,3,3,3] tangent is built from them ON THE DEVICE, as the reference's vectorised material does
@@ -336,7 +371,16 @@ def run_ours(args):
                     "levels": [int(lv.n) for lv in Mp.levels], "operator_complexity": Mp.operator_complexity,
                     "dofs_per_s_integrate_assemble_setup_solve": n_dofs / ((k_ms + asm_ms + amg_setup_ms + amg_solve_ms) * 1e-3),
                     "speedup_vs_jacobi_pcg_solve": solve_ms / (amg_setup_ms + amg_solve_ms)}
-        del Mp, xa
+        # parity statement at the benchmark size: the two product solvers, both iterated to stol 1e-12, must give the
+        # same displacement to <= 1e-8 (north_star's displacement bar) although they stop on residuals
+        xj12, _, ij12 = csr.krylov_solve(A, rhs, method="cg", rtol=1e-12)
+        xa12, sa12 = Mp.solve(rhs, rtol=1e-12)
+        amg_info["cross_check_stol_1e-12"] = {
+            "rel_diff_jacobi_pcg_vs_amg_pcg": float((xa12 - xj12).norm() / xj12.norm()),
+            "iterations_jacobi": ij12["iterations"], "iterations_amg": sa12["iterations"],
+            "rel_diff_stol_1e-8_vs_1e-12_jacobi": float((x2 - xj12).norm() / xj12.norm()),
+            "bar": 1e-8}
+        del Mp, xa, xj12, xa12
 
     # ---- the same through the public model API (`Solid.solve`, the call a torch-fem user makes):
     # the model (mesh + pattern) is setup; per step the material tangent and the boundary conditions
@@ -378,21 +422,12 @@ def run_ours(args):
                "d2h_bytes_per_step": int(d2h), "call": "Solid.solve(method='cg', stol=1e-8)",
                "rel_diff_vs_kernel_path": err, "with_amg": api_amg}
 
-    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N=1 only
+    # ---- CPU baseline: the reference's own code (oracle/_ref) on a bounded sample, rank 0 / N=1 only
     cpu = None
     if not args.no_cpu_baseline:
-        Ec = args.cpu_edge
-        Nc = Ec + 1
-        nd_c, el_c = O.cube_hexa(Nc, Nc, Nc)
-        Cc = O.isotropic_C3d(1000.0, 0.3, len(el_c))
-        cm, dp = O.cube_extension_bcs(nd_c)
-        out = O.linear_solve_reference_flow(nd_c, el_c, bref_np, w_np, Cc, cm, dp, rtol=RTOL)
-        t_cpu = out["t_integrate"] + out["t_assemble"] + out["t_rhs"] + out["t_solve"]
-        cpu = {"value": nd_c.size / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": (f"{Ec}^3 Hexa1 elements, {nd_c.size} DOFs, {out['iterations']} CG its to 1e-8: "
-                          f"setup {out['t_setup']:.2f}s (excluded) integrate {out['t_integrate']:.2f}s "
-                          f"assemble {out['t_assemble']:.2f}s solve {out['t_solve']:.2f}s; numpy/scipy oracle "
-                          f"port of the reference CPU path, scipy-CSR SpMV single-threaded")}
+        t_cpu, its_c, n_c, kind_c, detail_c, _ = cpu_reference_step(args.cpu_edge)
+        cpu = {"value": n_c / t_cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": kind_c,
+               "sample": f"{args.cpu_edge}^3 Hexa1 elements, {n_c} DOFs, {its_c} CG its to 1e-8: {detail_c}"}
 
     launches = info["launches"] + 1 + 1 + 1 + 1  # integrate, assemble(+lifting), SELL fill, jacobi
     line = {
@@ -405,8 +440,8 @@ def run_ours(args):
                    "cg_iterations": info["iterations"], "true_rel_residual": true_res,
                    "l2_policy": "inputs larger than L2 (CSR matrix 10.1 GB, k_e 15.6 GB vs 126 MB L2)",
                    "setup_ms_pattern": t_setup_ms, "phases_ms": {"integrate_k": k_ms, "assemble": asm_ms,
-                                                                 "pcg_solve": solve_ms,
-                                                                 "per_cg_iteration": solve_ms / max(1, info2["iterations"])},
+                                                                 "pcg_solve": solve_ms},
+                   "per_iteration_ms": solve_ms / max(1, info2["iterations"]),   # solve only (same key at N > 1)
                    "amg_pcg": amg_info},
         "e2e": {"value": n_dofs / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e,
@@ -433,6 +468,330 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------------ N > 1 / config C
+def run_multi_gpu(args):
+    """N > 1 (launched by torchrun, one rank per GPU): weak scaling of the cube benchmark — the global mesh is the
+    cube with N times the elements of the single-GPU config (edge E*N^(1/3): 189^3, 238^3, 300^3 elements for
+    N = 2, 4, 8 at E = 150), cut into N slabs of x-planes, so every rank holds ~E^3 elements. `--config C`: the Hexa2
+    cube of BASELINE configs[2], one global mesh cut by x-coordinate (strong scaling). value = global DOFs /
+    max-over-ranks device time of integrate + assemble + rhs + distributed Jacobi-PCG."""
+    import torch
+    import torch.distributed as dist
+
+    from torchfem_b200 import _lib as L
+    from torchfem_b200 import csr
+    from torchfem_b200 import distributed as D
+    from torchfem_b200.materials import IsotropicElasticity3D
+
+    multi = dist.is_initialized()
+
+    def _barrier():
+        if multi:
+            dist.barrier()
+
+    def _allreduce(t, op=None):
+        if multi:
+            dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM)
+
+    rank, world = (dist.get_rank(), dist.get_world_size()) if multi else (0, 1)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    E = args.edge
+    rtol = args.rtol
+    config_c = args.config == "C"
+    if config_c:
+        # BASELINE configs[2]: Hexa2 (20-node serendipity) cube, strong scaling of ONE global mesh. The mesh is
+        # made once per rank on the host with the reference-order generator, then cut by x-coordinate.
+        from torchfem_b200.elements import Hexa2 as EType, linear_to_quadratic
+        from torchfem_b200.mesh import cube_hexa
+
+        with torch.device("cpu"):
+            nodes_g, elements_g = linear_to_quadratic(*cube_hexa(E + 1, E + 1, E + 1))
+        nodes_h, mesh, ranges, perm = D.coordinate_partition(nodes_g, elements_g, world, rank)
+        n_dofs_global = 3 * nodes_g.shape[0]
+        n_elem_global = elements_g.shape[0]
+        del nodes_g, elements_g
+        Lx = 1.0
+        workload = (f"linear-elastic Hexa2 (20-node) cube {E}^3 elements ({n_dofs_global} DOFs), x-coordinate partition "
+                    f"into {world} node blocks, Jacobi-PCG to {rtol:g} (BASELINE configs[2]; strong scaling)")
+    else:
+        from torchfem_b200.elements import Hexa1 as EType
+
+        Eg = D.weak_scaling_edge(E, world)
+        h = 1.0 / E
+        nodes_h, mesh, ranges, (Nx, Ny, Nz) = D.cube_slab(Eg, Eg, Eg, h, world, rank)
+        Lx = Eg * h
+        n_dofs_global = Nx * Ny * Nz * 3
+        n_elem_global = Eg ** 3
+        workload = (f"linear-elastic Hexa1 cube {Eg}^3 elements (= {world} x {E}^3, weak scaling of BASELINE "
+                    f"configs[1]), {world} slabs of x-planes, Jacobi-PCG to {rtol:g}")
+    con_h = torch.zeros(mesh.n_local, 3, dtype=torch.bool)
+    disp_h = torch.zeros(mesh.n_local, 3, dtype=torch.float64)
+    con_h[nodes_h[:, 0] == 0.0, :] = True
+    right = (nodes_h[:, 0] - Lx).abs() < 1e-12
+    con_h[right, 0] = True
+    disp_h[right, 0] = 0.1
+    plan = D.build_halo_plan(mesh, ranges, rank, 3)
+    halo = D.HaloExchanger(plan, dev)
+    host = [nodes_h.contiguous(), mesh.elements.contiguous(), con_h.ravel().to(torch.uint8), disp_h.ravel().contiguous(),
+            torch.full((len(mesh.elements),), 1000.0), torch.full((len(mesh.elements),), 0.3)]
+    host = [t.pin_memory() for t in host]
+    nodes, elements, is_con, disp, E_mod, nu = (t.to(dev) for t in host)
+    ip = EType.ipoints.to(torch.float64).cpu()
+    bref, w = EType.B(ip), EType.iweights.to(torch.float64).cpu()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    pattern = csr.Pattern(elements, mesh.n_local, 3)
+    ev1.record()
+    torch.cuda.synchronize()
+    setup_ms = ev0.elapsed_time(ev1)
+    row_lo, n_owned = 3 * mesh.lo, 3 * mesh.n_owned
+    own = slice(row_lo, row_lo + n_owned)
+    vals = torch.empty(pattern.nnz, dtype=torch.float64, device=dev)
+    rhs_buf = torch.empty(pattern.n_dofs, dtype=torch.float64, device=dev)
+    state = {}
+    fused = args.dist_cg == "fused"
+    cg = D.FusedCG(pattern.indptr, pattern.indices, pattern.n_dofs, row_lo, n_owned, plan, dev) if fused else None
+
+    def build_system(nodes, elements, is_con, disp, E_mod, nu):
+        # per-element material -> tangent on the device, as the reference's vectorised material does
+        C = IsotropicElasticity3D(E_mod, nu).C
+        k = csr.integrate_k(L.KIND_MECH, bref, w, nodes, elements, C, check=False)
+        del C
+        rhs = rhs_buf   # local halo values of du_bc come from the BC data, so the lifting needs no exchange
+        csr.assemble(pattern, k, is_con, out=vals, ubc=disp, lift=rhs)
+        del k
+        A = pattern.matrix(vals)
+        return A, rhs, csr.JacobiPreconditioner(A)
+
+    def solve(A, rhs, M, tol):
+        if fused:
+            return cg.solve(A, M.dinv, rhs, rtol=tol)
+        return D.distributed_cg(A, M.dinv, rhs, row_lo, n_owned, halo, rtol=tol)
+
+    def hot_path(*inputs):
+        A, rhs, M = build_system(*inputs)
+        x, info = solve(A, rhs, M, rtol)
+        state.update(A=A, rhs=rhs, x=x, info=info, M=M)
+        return x
+
+    def step():
+        return hot_path(nodes, elements, is_con, disp, E_mod, nu)
+
+    def step_e2e():
+        d = [t.to(dev, non_blocking=True) for t in host]
+        x = hot_path(*d)
+        return x[own].cpu()
+
+    def timed_max(fn, reps):
+        """mean device ms of `reps` calls, bracketed by barrier + synchronize, max over ranks"""
+        _barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        _barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        _allreduce(t, dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    ms = timed_max(step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: every rank's inputs come from pinned host memory, its part of the solution goes back
+    step_e2e()
+    ms_e2e = timed_max(step_e2e, max(1, min(args.steps, 2)))
+    io = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host), 8 * n_owned], dtype=torch.int64, device=dev)
+    _allreduce(io)
+
+    # true global relative residual of the last solve
+    A, rhs, x, info, M = state["A"], state["rhs"], state["x"], state["info"], state["M"]
+    iterations = info["iterations"]
+
+    def global_res(xv):
+        xv = xv.clone()
+        halo(xv)
+        r = (rhs - A.matvec(xv))[own]
+        num = torch.stack([(r * r).sum(), (rhs[own] ** 2).sum()])
+        _allreduce(num)
+        return float((num[0] / num[1]).sqrt())
+
+    true_res = global_res(x)
+    nnz_owned = torch.tensor([int(pattern.indptr[row_lo + n_owned] - pattern.indptr[row_lo])], device=dev)
+    nnz_mine = int(nnz_owned.item())
+    _allreduce(nnz_owned)
+
+    # phases on this rank (max over ranks): the SOLVE alone gives the per-iteration figure (same key at N = 1)
+    solve_ms = timed_max(lambda: solve(A, rhs, M, rtol), 1)
+    build_ms = timed_max(lambda: build_system(nodes, elements, is_con, disp, E_mod, nu), 1)
+    A, rhs, M = build_system(nodes, elements, is_con, disp, E_mod, nu)
+
+    # the dominant kernel, k_dcg_spmv (owned rows, halo wait inside), timed by CUDA events INSIDE the solve on the
+    # solve's stream (tfem_comm_set_trace time_spmv): mean of the 32 launches of the second batch; max over ranks
+    spmv_ms, trace_summary = None, None
+    if fused:
+        n_tr = 64 if args.trace else 0
+        tr = cg.comm.set_trace(n_tr, first_iteration=64, time_spmv=True)
+        _, info_t = solve(A, rhs, M, rtol)
+        cg.comm.set_trace(0)
+        t = torch.tensor([info_t["spmv_ms"]], dtype=torch.float64, device=dev)
+        _allreduce(t, dist.ReduceOp.MAX)
+        spmv_ms = float(t.item())
+        if n_tr:
+            trace_summary = summarize_trace(tr.cpu().numpy(), rank)
+            gathered = [None] * world
+            if multi:
+                dist.all_gather_object(gathered, trace_summary)
+            else:
+                gathered = [trace_summary]
+            trace_summary = gathered
+    else:
+        xs = torch.randn(A.n, dtype=torch.float64, device=dev)
+        ys = torch.empty_like(xs)
+        spmv_ms = timed_max(lambda: A.matvec(xs, out=ys, fmt="sell"), 10)
+    spmv_bytes = 12 * nnz_mine + 20 * n_owned      # §8(d) algorithmic bytes of the rows this rank multiplies
+
+    # distributed AMG-PCG beside the Jacobi headline (like the N = 1 line)
+    amg_info = None
+    if not args.no_amg and multi_amg_available():
+        amg_info = bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, row_lo, n_owned, x, solve,
+                                         global_res, timed_max, n_dofs_global, build_ms)
+
+    probe = None
+    if config_c or args.probe:
+        # partition-independent fingerprint of the solution (compare runs at different N: tools/compare_probe.py)
+        u = torch.where(is_con.bool(), disp, -x)[own]
+        sums = torch.stack([u.sum(), (u * u).sum(), u.abs().max()])
+        mx = sums[2:].clone()
+        _allreduce(sums)
+        _allreduce(mx, dist.ReduceOp.MAX)
+        xyz = nodes[mesh.lo:mesh.lo + mesh.n_owned]
+        wgt = torch.stack([torch.sin(3.0 * xyz[:, 0] + 1.0), torch.cos(2.0 * xyz[:, 1]) * xyz[:, 2], xyz[:, 0] * xyz[:, 1]], 1)
+        mom = (u.view(-1, 3) * wgt).sum(0)
+        _allreduce(mom)
+        probe = {"sum_u": float(sums[0]), "norm2_u": float(sums[1].sqrt()), "max_abs_u": float(mx[0]),
+                 "weighted_moments": [float(v) for v in mom], "rtol": rtol}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": n_dofs_global / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong" if config_c else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_dofs": int(n_dofs_global), "n_elem": int(n_elem_global),
+                       "nnz": int(nnz_owned.item()), "rtol": rtol,
+                       "cg_iterations": iterations, "true_rel_residual": true_res,
+                       "per_rank_local_dofs": int(A.n), "halo_bytes_per_exchange": plan.bytes_per_exchange(),
+                       "collectives_per_iteration": ("fused into the kernels: halo = peer stores of the direction "
+                                                     "update, 2 all-reduces = LL-protocol peer stores (tfem_dcg_solve)")
+                       if fused else "NCCL: 1 halo exchange (P2P send/recv) + 2 all-reduces (1 and 2 doubles)",
+                       "l2_policy": f"inputs larger than L2 (per-rank SELL matrix {8.5e-9 * pattern.nnz:.1f} GB vs 126 MB L2)",
+                       "setup_ms_pattern": setup_ms,
+                       "phases_ms": {"integrate_assemble_jacobi": build_ms, "pcg_solve": solve_ms},
+                       "per_iteration_ms": solve_ms / max(1, iterations),   # solve only, max over ranks
+                       "note": "Jacobi-PCG iterations grow with the cube edge (~N^(1/3)), so DOF/s per GPU "
+                               "falls with N even at perfect per-iteration scaling; per_iteration_ms (solve only) is "
+                               "the kernel/communication scaling figure",
+                       "amg_pcg": amg_info, "solution_probe": probe, "wait_trace": trace_summary},
+            "e2e": {"value": n_dofs_global / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
+                    "call": "C-ABI ops on per-rank host buffers (H2D mesh + per-element E, nu + BCs -> tangent -> "
+                            "integrate -> assemble -> distributed PCG -> D2H owned u)"},
+            "gpu_launches": int(info["launches"] + 6),
+            "roofline": {"bound": "hbm",
+                         "kernel": "k_dcg_spmv<3> (this rank's owned rows, halo wait inside; CUDA events inside the solve, "
+                                   "max over ranks)" if fused else "k_sell_spmv (per rank, standalone)",
+                         "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms, "traffic": None},
+            "cpu_baseline": None, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if cg is not None:
+        cg.close()
+    _barrier()
+    if multi:
+        dist.destroy_process_group()
+
+
+def summarize_trace(tr, rank):
+    """Median durations (us) between the trace points of tfem_comm_set_trace over the traced iterations."""
+    tr = tr.astype(np.float64)
+    ok = (tr[:, 0] > 0) & (tr[:, 9] > 0)
+    tr = tr[ok]
+    if len(tr) < 2:
+        return {"rank": rank, "iterations": int(len(tr))}
+    med = lambda v: float(np.median(v)) / 1e3  # noqa: E731
+    return {
+        "rank": rank, "iterations": int(len(tr)),
+        "spmv_kernel_us": med(tr[:, 2] - tr[:, 0]), "spmv_longest_halo_wait_us": med(tr[:, 1]),
+        "gap_spmv_to_update_us": med(tr[:, 3] - tr[:, 2]), "update_wait_allreduce_us": med(tr[:, 4] - tr[:, 3]),
+        "update_stream_us": med(tr[:, 5] - tr[:, 4]), "gap_update_to_direction_us": med(tr[:, 6] - tr[:, 5]),
+        "direction_wait_allreduce_us": med(tr[:, 7] - tr[:, 6]), "direction_halo_released_after_us": med(tr[:, 8] - tr[:, 7]),
+        "direction_stream_us": med(tr[:, 9] - tr[:, 7]),
+        "gap_direction_to_next_spmv_us": med(tr[1:, 0] - tr[:-1, 9]),
+        "iteration_us": med(tr[1:, 0] - tr[:-1, 0]),
+    }
+
+
+def multi_amg_available():
+    try:
+        from torchfem_b200 import damg  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, row_lo, n_owned, x_jacobi, solve,
+                          global_res, timed_max, n_dofs_global, build_ms):
+    import torch
+    import torch.distributed as dist
+
+    from torchfem_b200 import damg
+
+    own = slice(row_lo, row_lo + n_owned)
+    state = {}
+
+    def setup():
+        state["H"] = damg.DistributedAMG(A, pattern, mesh, plan, ranges)
+
+    def run(tol):
+        xa, st = state["H"].solve(rhs, rtol=tol)
+        state.update(x=xa, st=st)
+
+    setup()
+    run(args.rtol)                   # first call grows pools
+    state["H"].close()
+    setup_ms = timed_max(setup, 1)
+    solve_ms = timed_max(lambda: run(args.rtol), 1)
+    st, xa = state["st"], state["x"]
+    res = global_res(xa)
+    # parity at stol 1e-12: distributed AMG-PCG vs distributed Jacobi-PCG
+    xj12, _ = solve(A, rhs, M, 1e-12)
+    run(1e-12)
+    num = torch.stack([((state["x"] - xj12)[own] ** 2).sum(), (xj12[own] ** 2).sum()])
+    if dist.is_initialized():
+        dist.all_reduce(num)
+    out = {"call": "damg.DistributedAMG: rank-local aggregates, distributed Galerkin levels, V(1,1) + CG over peer memory",
+           "setup_ms": setup_ms, "solve_ms": solve_ms, "iterations": st["iterations"],
+           "ms_per_iteration": solve_ms / max(1, st["iterations"]), "true_rel_residual": res,
+           "levels": state["H"].level_sizes, "rel_diff_vs_jacobi_pcg_stol_1e-12": float((num[0] / num[1]).sqrt()),
+           "iterations_stol_1e-12": state["st"]["iterations"],
+           "dofs_per_s_integrate_assemble_setup_solve": n_dofs_global / ((build_ms + setup_ms + solve_ms) * 1e-3)}
+    state["H"].close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,6 +809,10 @@ def main():
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG report beside the Jacobi-PCG headline")
     ap.add_argument("--dist-cg", default="fused", choices=["fused", "nccl"],
                     help="N>1: fused peer-to-peer CG (tfem_dcg_solve) or the host-driven NCCL variant")
+    ap.add_argument("--rtol", type=float, default=RTOL, help="N>1 / config C only: relative residual of the PCG "
+                    "(the metric's value is 1e-8; other values are for the parity legs)")
+    ap.add_argument("--trace", action="store_true", help="N>1: in-kernel %%globaltimer profile of the cross-GPU waits")
+    ap.add_argument("--probe", action="store_true", help="N>1: add the partition-independent solution fingerprint")
     args = ap.parse_args()
     if args.edge is None:
         args.edge = 120 if args.config == "C" else 150

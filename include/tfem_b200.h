@@ -307,15 +307,29 @@ int tfem_krylov_state(int64_t n_rows, const double* work_dev, double* info_host,
  * stores of <= 3 doubles plus a flag, summed in rank order by every consumer (bit-identical on all ranks).
  * Replaces the same reference loop as tfem_krylov_solve (cupy_cg, sparse.py:414-421).
  *
- * Setup: every rank calls tfem_comm_create (allocates its buffer: header + 2 vectors of vec_doubles — the SAME
- * vec_doubles on every rank, >= the longest local vector — and returns a 64-byte IPC handle), the host exchanges the handles (e.g. torch.distributed.all_gather), every rank calls
- * tfem_comm_connect with all `world` handles in rank order, then a host barrier. world <= 16.
+ * Setup: every rank calls tfem_comm_create (allocates its buffer: an 8 KB header of flags + a heap of 2*vec_doubles
+ * doubles — the SAME vec_doubles on every rank, >= the longest local vector — and returns a 64-byte IPC handle), the
+ * host exchanges the handles (e.g. torch.distributed.all_gather), every rank calls tfem_comm_connect with all `world`
+ * handles in rank order, then a host barrier. world <= 16. The heap is symmetric: the same offset means the same
+ * vector on every rank, so a kernel stores halo entries straight into a peer's copy (tfem_dcg_solve keeps its two
+ * copies of p there; tfem_damg_* carve it into the vectors of the multigrid levels).
  * ------------------------------------------------------------------------------------------------- */
 #define TFEM_IPC_HANDLE_BYTES 64
 #define TFEM_MAX_NEIGHBOURS 8
+#define TFEM_TRACE_SLOTS 16
 int tfem_comm_create(int rank, int world, int64_t vec_doubles, void** comm_out, void* ipc_handle_out);
 int tfem_comm_connect(void* comm, const void* all_handles /* world * TFEM_IPC_HANDLE_BYTES, host */);
 int tfem_comm_destroy(void* comm);
+/* This rank's heap (device pointer) and its length in doubles. */
+int tfem_comm_heap(void* comm, void** heap_dev_out, int64_t* heap_doubles_out);
+/* In-kernel profile of the cross-GPU waits (nsys is not available and ncu serialises kernels): with trace_dev != NULL
+ * (device uint64 [n_iterations * TFEM_TRACE_SLOTS], zeroed by the caller) the kernels of iterations
+ * [first_iteration, first_iteration + n_iterations) of the following solves stamp %globaltimer (ns) at fixed points:
+ * slot 0 SpMV begin, 1 longest halo wait inside the SpMV (duration), 2 SpMV last CTA, 3 update begin, 4 update
+ * reduction arrived, 5 update last CTA, 6 direction begin, 7 direction reduction arrived, 8 halo flags released,
+ * 9 direction last CTA. time_spmv != 0: tfem_dcg_solve also times the SpMV launches of its second batch with CUDA
+ * events and returns their mean (ms) in info_host[7]. trace_dev == NULL switches the trace off. */
+int tfem_comm_set_trace(void* comm, void* trace_dev, int64_t first_iteration, int n_iterations, int time_spmv);
 
 /* One entry per neighbour this rank sends halo values to: `count` entries of the local vector, taken at
  * src_idx[k] (device int32, local numbering) or src_start + k if src_idx is NULL, stored at dst_idx[k] (device

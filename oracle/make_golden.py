@@ -337,6 +337,23 @@ def heat_transient():
     t3 = torch.tensor([0.0, 1.0, 3.0])
     temp3, _, flux3, grad3, _ = cube.time_integration(t3, delta_t=0.25)
     out.update({"cube.t_out": npy(t3), "cube.temp": npy(temp3), "cube.flux": npy(flux3), "cube.grad": npy(grad3)})
+
+    # sensitivities w.r.t. per-element MATERIAL parameters: they flow through the system matrix M + dt/2 K of every step
+    # (Solve.backward's sparse gradA, sparse.py:212-216, back through assemble_matrix) and through M @ du (base.py:1483)
+    n_el = model.n_elem
+    gen = torch.Generator().manual_seed(5)
+    kappa = (300.0 + 200.0 * torch.rand(n_el, generator=gen)).requires_grad_(True)
+    rho = (0.5e5 + 1.0e5 * torch.rand(n_el, generator=gen)).requires_grad_(True)
+    het = PlanarHeat(*mesh.rect_quad(5, 5, 1.0, 1.0), M.IsotropicConductivity2D(kappa=kappa, rho=rho))
+    het.constraints[west | east] = True
+    het.temperatures[west, 0] = 5.0
+    het.temperatures[east, 0] = 20.0
+    het.heat_flux = hf.clone()
+    t_het = torch.tensor([0.0, 4.0, 8.0])
+    temp_h, *_ = het.time_integration(t_het, delta_t=1.0, differentiable_parameters=[kappa, rho])
+    (temp_h[-1] ** 2).sum().backward()
+    out.update({"het.kappa": npy(kappa), "het.rho": npy(rho), "het.t_out": npy(t_het), "het.temp": npy(temp_h),
+                "het.grad_kappa": npy(kappa.grad), "het.grad_rho": npy(rho.grad)})
     np.savez_compressed(os.path.join(OUT, "heat_transient.npz"), **out)
 
 
@@ -664,6 +681,23 @@ def hyper_plane_stress():
     print("hyper plane stress: reaction", float(f[right, 0].sum()), "thickness stretch", float(alpha.mean()) + 1.0)
 
 
+def near_null_space():
+    """`FEM.compute_B` (base.py:316-344) of a distorted solid, a planar and a thermal model: the rigid-body modes the
+    reference hands to its AMG back ends (sparse.py:493-512)."""
+    n3, e3 = mesh.cube_hexa(4, 3, 3, 1.5, 1.0, 1.0)
+    n3 = distort(n3, 0.08, 1)
+    n2, e2 = mesh.rect_quad(5, 4, 2.0, 1.0)
+    n2 = distort(n2, 0.06, 3)
+    solid = Solid(n3, e3, M.IsotropicElasticity3D(E=1000.0, nu=0.3))
+    planar = Planar(n2, e2, M.IsotropicElasticityPlaneStress(E=1000.0, nu=0.3))
+    heat = SolidHeat(n3, e3, M.IsotropicConductivity3D(kappa=2.0, rho=1.0))
+    out = {"solid.nodes": npy(n3), "solid.elements": npy(e3), "solid.B": npy(solid.compute_B()), "solid.idx": npy(solid.idx),
+           "planar.nodes": npy(n2), "planar.elements": npy(e2), "planar.B": npy(planar.compute_B()),
+           "planar.idx": npy(planar.idx), "heat.B": npy(heat.compute_B()), "heat.idx": npy(heat.idx)}
+    np.savez_compressed(os.path.join(OUT, "compute_B.npz"), **out)
+    print("compute_B:", {k: v.shape for k, v in out.items() if k.endswith(".B")})
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:          # regenerate selected fixtures only: python oracle/make_golden.py modal
         for name in sys.argv[1:]:
@@ -681,5 +715,6 @@ if __name__ == "__main__":
     orthotropic()
     loads()
     hyper_plane_stress()
+    near_null_space()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY — imports the *unmodified* reference torch-fem from /root/reference.
 
-Used only in the build container (the reference tree does not exist on the GPU box) by
-`oracle/make_golden.py` to generate the committed fixtures under `tests/golden/` and by
-`tests/test_oracle_vs_reference.py` (skipped when /root/reference is absent).
+Used by `oracle/make_golden.py` (build container) to generate the committed fixtures under `tests/golden/`, by
+`tests/test_reference_parity.py` and by `bench.py`'s `--impl reference` / `cpu_baseline` legs. The package is looked
+for at $TFEM_REFERENCE_SRC, then `/root/reference/src` (build container), then `oracle/_ref` (the untracked offline
+install `oracle/build_ref.py` stages so that the reference travels to the GPU box with the snapshot).
 
 The reference imports matplotlib / pyvista / pyamg / meshio at module import time; none of them is
 installed offline, so permissive stub modules are registered first (recipe: SURVEY.md Appendix A).
@@ -14,7 +15,15 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = os.environ.get("TFEM_REFERENCE_SRC", "/root/reference/src")
+def _find_reference():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for cand in (os.environ.get("TFEM_REFERENCE_SRC"), "/root/reference/src", os.path.join(here, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "torchfem")):
+            return cand
+    return os.path.join(here, "_ref")
+
+
+REFERENCE_SRC = _find_reference()
 
 
 class _Stub(types.ModuleType):

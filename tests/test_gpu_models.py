@@ -102,6 +102,8 @@ class TestConfigA:
         g = load_case("config_a.npz")
         cube = self._cube(T)
         assert cube.idx.dtype == torch.int32 and cube.k_map.dtype == torch.int32
+        import hashlib
+        assert hashlib.sha256(cube.idx.cpu().numpy().tobytes()).hexdigest()[:16] == str(g["sha_idx"])
         u, f, sigma, eps, state = cube.solve(differentiable_parameters=cube.forces, method=method, stol=1e-10)
         nrm = np.linalg.norm(g["u"])
         assert np.linalg.norm(u.detach().cpu().numpy() - g["u"]) / nrm <= 1e-8
@@ -270,6 +272,27 @@ class TestSparse:
 
 
 class TestBase:
+    @pytest.mark.parametrize("kind", ["solid", "planar", "heat"])
+    def test_compute_B_and_idx_match_reference(self, T, kind):
+        """`FEM.compute_B` (rigid-body near-null space, reference base.py:316-344) and the DOF map `idx`
+        (base.py:73-76,119) against the unmodified reference (fixture compute_B.npz, oracle/make_golden.py)."""
+        from torchfem_b200.materials import (IsotropicConductivity3D, IsotropicElasticity3D,
+                                             IsotropicElasticityPlaneStress)
+
+        g = load_case("compute_B.npz")
+        src = "planar" if kind == "planar" else "solid"
+        nodes, elements = torch.as_tensor(g[f"{src}.nodes"]).cuda(), torch.as_tensor(g[f"{src}.elements"]).cuda()
+        if kind == "solid":
+            model = T.Solid(nodes, elements, IsotropicElasticity3D(E=1000.0, nu=0.3))
+        elif kind == "planar":
+            model = T.Planar(nodes, elements, IsotropicElasticityPlaneStress(E=1000.0, nu=0.3))
+        else:
+            model = T.SolidHeat(nodes, elements, IsotropicConductivity3D(kappa=2.0, rho=1.0))
+        B = model.compute_B()
+        assert B.shape == g[f"{kind}.B"].shape and B.dtype == torch.float64
+        assert np.array_equal(B.cpu().numpy(), g[f"{kind}.B"])          # copies of coordinates: exact
+        assert model.idx.dtype == torch.int32 and np.array_equal(model.idx.cpu().numpy(), g[f"{kind}.idx"])
+
     def test_inverted_element_raises(self, T):
         from torchfem_b200.materials import IsotropicElasticity3D
         from torchfem_b200.mesh import cube_hexa
@@ -370,6 +393,30 @@ class TestHeatTransient:
         temp[-1].sum().backward()
         gh = model.heat_flux.grad.cpu().numpy()
         assert np.abs(gh - g["plate.grad_heat_flux"]).max() <= 1e-8 * np.abs(g["plate.grad_heat_flux"]).max()
+
+    def test_material_parameter_gradients(self, T):
+        """d(sum T_end^2)/d(kappa_e, rho_e): flows through the system matrix M + dt/2 K of every step and through
+        M @ du (reference: differentiable assemble_matrix + Solve.backward's gradA, sparse.py:212-216)."""
+        from torchfem_b200.materials import IsotropicConductivity2D
+        from torchfem_b200.mesh import rect_quad
+
+        g = load_case("heat_transient.npz")
+        kappa = torch.tensor(g["het.kappa"]).requires_grad_(True)
+        rho = torch.tensor(g["het.rho"]).requires_grad_(True)
+        model = T.PlanarHeat(*rect_quad(5, 5, 1.0, 1.0), IsotropicConductivity2D(kappa=kappa, rho=rho))
+        west = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].min())
+        east = torch.isclose(model.nodes[:, 0], model.nodes[:, 0].max())
+        model.constraints[west | east] = True
+        model.temperatures[west, 0] = 5.0
+        model.temperatures[east, 0] = 20.0
+        model.heat_flux = torch.tensor(g["plate.heat_flux"])
+        temp, *_ = model.time_integration(torch.tensor(g["het.t_out"]), delta_t=1.0, stol=1e-13,
+                                          differentiable_parameters=[kappa, rho])
+        assert np.abs(temp.detach().cpu().numpy() - g["het.temp"]).max() <= 1e-8 * np.abs(g["het.temp"]).max()
+        (temp[-1] ** 2).sum().backward()
+        for got, key in ((kappa.grad, "het.grad_kappa"), (rho.grad, "het.grad_rho")):
+            ref = g[key]
+            assert np.abs(got.cpu().numpy() - ref).max() <= 1e-6 * np.abs(ref).max(), key
 
     def test_late_start_single_time_and_invalid_times(self, T):
         g = load_case("heat_transient.npz")
@@ -681,10 +728,6 @@ def test_consistent_nodal_loads(T, tag):
         close(model.integrate_line_load(right, torch.tensor([1.0, -2.0])), g[f"{tag}.traction_right"])
 
 
-@pytest.mark.xfail(strict=False, reason="first execution on the device pending: besides the new material it is the first "
-                                        "test to run kernel K1 with per-Gauss-point tangents on a planar element "
-                                        "(Hexa1 is covered by case_hyper_hexa1); CPU-validated in "
-                                        "tests/test_hyper_plane_stress_cpu.py — remove this mark once it has passed")
 def test_hyperelastic_plane_stress_strip(T):
     """`HyperelasticPlaneStress` (reference hyperelasticity.py:130-269): Neo-Hookean strip stretched
     by 30 % in three `nlgeom` increments, thickness stretch carried as a state variable; the device path updates all

@@ -76,6 +76,10 @@ def test_heat_transient_plate_and_flux_gradient(T, method):
     GM.TestHeatTransient().test_plate_matches_reference_and_heat_flux_gradient(T, method)
 
 
+def test_heat_transient_material_parameter_gradients(T):
+    GM.TestHeatTransient().test_material_parameter_gradients(T)
+
+
 def test_heat_transient_late_start_and_solid_cube(T):
     GM.TestHeatTransient().test_late_start_single_time_and_invalid_times(T)
     GM.TestHeatTransient().test_solid_heat_cube(T)

@@ -23,6 +23,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libtfem_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_CONVERGED, ERR_BREAKDOWN, ERR_NCCL, ERR_COMM = range(8)
 IPC_HANDLE_BYTES = 64
 MAX_NEIGHBOURS = 8
+TRACE_SLOTS = 16
 KIND_MECH, KIND_HEAT = 0, 1
 METHOD_CG, METHOD_MINRES = 0, 1
 SPMV_CHUNK = 512
@@ -129,6 +130,8 @@ _SIGNATURES = {
     "tfem_comm_create": (c_int, [c_int, c_int, c_int64, ctypes.POINTER(c_void_p), c_void_p]),
     "tfem_comm_connect": (c_int, [c_void_p, c_void_p]),
     "tfem_comm_destroy": (c_int, [c_void_p]),
+    "tfem_comm_heap": (c_int, [c_void_p, ctypes.POINTER(c_void_p), ctypes.POINTER(c_int64)]),
+    "tfem_comm_set_trace": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int]),
     "tfem_dcg_solve": (c_int, [c_void_p, _SELL_P, c_int64, c_int64, c_int64, c_int64, c_int,
                                ctypes.POINTER(HaloSendStruct), c_int, c_void_p] + [c_void_p] * 4
                        + [c_double, c_double, c_int64, c_int, c_double, c_void_p, c_void_p]),

@@ -111,6 +111,71 @@ class _IntegrateK(torch.autograd.Function):
         return grad, None
 
 
+class _ElementSystemSolve(torch.autograd.Function):
+    """x = A^-1 b for A = c_m M(m_e) + c_k K(k_e) assembled by the kernels, with gradients to b AND to the element
+    matrices:  dL/dk_e[a,b] = -c_k lam[idx[e,a]] x[idx[e,b]],  dL/dm_e likewise with c_m  (lam = A^-T dL/dx).
+    This is what the reference obtains by back-propagating `Solve.backward`'s sparse gradA (sparse.py:212-216) through
+    the `index_add_` of `assemble_matrix` (base.py:407-419); entries of constrained rows / columns carry no gradient
+    there either (they are overwritten by constants, base.py:414-419), hence the masks."""
+
+    @staticmethod
+    def forward(ctx, b, k_e, m_e, A, idx, free, c_k, c_m, cfg):
+        from .sparse import sparse_solve
+
+        B, stol, device, method, cached, update_cache = cfg
+        x0 = cached.previous_x if cached is not None else None
+        x, M = sparse_solve(A, b, B, stol, device, method, None, x0)
+        if update_cache and cached is not None:
+            cached.update_x(x)
+        ctx.save_for_backward(x)
+        ctx.A, ctx.idx, ctx.free, ctx.c, ctx.cfg, ctx.M = A, idx, free, (c_k, c_m), cfg, M
+        ctx.needs = (k_e is not None and k_e.requires_grad, m_e is not None and m_e.requires_grad)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        from .sparse import sparse_solve
+
+        (x,) = ctx.saved_tensors
+        B, stol, device, method, cached, update_cache = ctx.cfg
+        x0 = cached.previous_grad if cached is not None else None
+        lam, _ = sparse_solve(ctx.A.T, g, B, stol, device, method, ctx.M, x0)
+        if update_cache and cached is not None:
+            cached.update_grad(lam)
+        gk = gm = None
+        if any(ctx.needs):
+            idx = ctx.idx.long()
+            outer = -(lam * ctx.free)[idx][:, :, None] * (x * ctx.free)[idx][:, None, :]
+            if ctx.needs[0]:
+                gk = ctx.c[0] * outer
+            if ctx.needs[1]:
+                gm = ctx.c[1] * outer
+        return lam, gk, gm, None, None, None, None, None, None
+
+
+class _ElementMatvec(torch.autograd.Function):
+    """y = M(m_e) x on the kernel-assembled CSR, differentiable w.r.t. x and the element matrices
+    (dL/dm_e[a,b] = g[idx[e,a]] x[idx[e,b]] off the constrained rows / columns) — the reference's `self.M @ du` on a
+    differentiable sparse tensor (base.py:1483)."""
+
+    @staticmethod
+    def forward(ctx, x, m_e, A, idx, free):
+        ctx.save_for_backward(x)
+        ctx.A, ctx.idx, ctx.free = A, idx, free
+        ctx.need_m = m_e.requires_grad
+        return A.matvec(x.detach().to(torch.float64).contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        gx = ctx.A.T.matvec(g.contiguous())
+        gm = None
+        if ctx.need_m:
+            idx = ctx.idx.long()
+            gm = (g * ctx.free)[idx][:, :, None] * (x * ctx.free)[idx][:, None, :]
+        return gx, gm, None, None, None
+
+
 class FEM(ABC):
     """Abstract finite-element model (reference base.py:23-132)."""
 
@@ -248,22 +313,30 @@ class FEM(ABC):
     def _ip_shape(self) -> tuple[Tensor, Tensor, Tensor]:
         """Shape data at the integration points, cached while `nodes` is the same non-differentiable
         tensor (the reference recomputes it on every `integrate_material` call, base.py:1048)."""
-        key = (self.nodes.data_ptr(), self.nodes._version, self.elements.data_ptr())
         if self.nodes.requires_grad:
             return self.eval_shape_functions(self.etype.ipoints)
-        if self._shape_cache is None or self._shape_cache[0] != key:
-            self._shape_cache = (key, self.eval_shape_functions(self.etype.ipoints))
+        if not self._cache_valid(self._shape_cache):
+            self._shape_cache = (self._cache_key(), self.eval_shape_functions(self.etype.ipoints))
         return self._shape_cache[1]
+
+    def _cache_key(self):
+        # the tensors themselves (kept alive by the entry, so their addresses cannot be recycled) + the in-place version
+        return (self.nodes, self.nodes._version, self.elements, self.elements._version)
+
+    def _cache_valid(self, entry) -> bool:
+        if entry is None:
+            return False
+        nodes, nv, elements, ev = entry[0]
+        return nodes is self.nodes and elements is self.elements and nv == nodes._version and ev == elements._version
 
     def _geometry(self) -> "_res.Geometry | None":
         """Kernel-side geometry of the residual contractions (K9/K10), or None when the node coordinates are
         being differentiated (shape optimisation keeps the torch path)."""
         if self.nodes.requires_grad or self.nodes.dtype != torch.float64:
             return None
-        key = (self.nodes.data_ptr(), self.nodes._version, self.elements.data_ptr())
-        if getattr(self, "_geom_cache", None) is None or self._geom_cache[0] != key:
+        if not self._cache_valid(getattr(self, "_geom_cache", None)):
             bref, w = self._tables()
-            self._geom_cache = (key, _res.Geometry(bref, w, self.nodes, self.elements, self.n_dof_per_node))
+            self._geom_cache = (self._cache_key(), _res.Geometry(bref, w, self.nodes, self.elements, self.n_dof_per_node))
         return self._geom_cache[1]
 
     @property
@@ -431,7 +504,7 @@ class FEM(ABC):
         self.is_constrained = is_con
         vals = _csr.assemble(self.pattern, k.detach().to(torch.float64),
                              is_con.to(torch.uint8) if con.numel() else None)
-        return self.pattern.matrix(vals, symmetric=True)
+        return self.pattern.matrix(vals, symmetric=bool(getattr(self.material, "symmetric_tangent", True)))
 
     def assemble_rhs(self, f: Tensor) -> Tensor:
         """Global vector from element vectors; differentiable (reference base.py:428-445)."""
@@ -767,7 +840,9 @@ class Heat(FEM, ABC):
         reference. Per step: Newton on  M du + dt/2 (f_int_old + f_int + f_ext) = 0  with the linear solves
         `differentiable_sparse_solve(M + dt/2 K, -residual)` on the device CSR (M, K assembled once by kernel
         K2/K3; the combination is an entry-wise sum on the shared pattern). Gradients flow through the right-hand
-        sides (loads, previous states); matrix VALUES carry no gradient here (they come from the kernels)."""
+        sides (loads, previous states) and — when a material parameter is differentiated — through the system matrix
+        and `M @ du` as per-element contractions (`_ElementSystemSolve`, `_ElementMatvec`), like the reference's
+        differentiable `assemble_matrix` + `Solve.backward`."""
         kw = dict(dtype=self.nodes.dtype, device=self.device)
         t_output = torch.tensor([0.0, 1.0]) if t_output is None else t_output
         t_output = t_output.detach().to("cpu", torch.float64)
@@ -815,6 +890,8 @@ class Heat(FEM, ABC):
         self.K = torch.empty(0, device=self.device)
         self.M = None
         m = self.integrate_mass()
+        k_el = None                                   # element conductivity matrices behind self.K (keep their graph)
+        free = (~self._constraints.ravel()).to(kw["dtype"])
         if verbose:
             print(f"torch-fem_b200 | time integration | {type(self).__name__} | {self.n_dofs:,} dof | "
                   f"{n_steps - 1} steps | dt <= {delta_t:g} | {describe_method(self.n_dofs, 'cuda', method)}")
@@ -833,9 +910,13 @@ class Heat(FEM, ABC):
                 f_int = self.assemble_rhs(f_e)
                 if k is not None:
                     self.K = self.assemble_matrix(k, con)
+                    k_el = k
                 if self.M is None:
                     self.M = self.assemble_matrix(m, con)
-                residual = (self.M @ du.reshape(-1)) + 0.5 * dt_n * (f_old.reshape(-1) + f_int + self._neumann.ravel())
+                elem_grad = torch.is_grad_enabled() and (m.requires_grad or (k_el is not None and k_el.requires_grad))
+                Mdu = (_ElementMatvec.apply(du.reshape(-1), m, self.M, self.idx, free) if elem_grad and m.requires_grad
+                       else self.M @ du.reshape(-1))
+                residual = Mdu + 0.5 * dt_n * (f_old.reshape(-1) + f_int + self._neumann.ravel())
                 mask = torch.ones_like(residual)
                 mask[con] = 0.0
                 residual = residual * mask
@@ -850,8 +931,12 @@ class Heat(FEM, ABC):
                 # refreshed hierarchy — are then reused by every step
                 if not (sys_cache[0] == float(dt_n) and sys_cache[1] is self.M and sys_cache[2] is self.K):
                     sys_cache = (float(dt_n), self.M, self.K, self.M + 0.5 * dt_n * self.K)
-                step = differentiable_sparse_solve(sys_cache[3], -residual, B, stol, device, method,
-                                                   None, cached, it == 0)
+                if elem_grad:
+                    step = _ElementSystemSolve.apply(-residual, k_el, m, sys_cache[3], self.idx, free, 0.5 * dt_n, 1.0,
+                                                     (B, stol, device, method, cached, it == 0))
+                else:
+                    step = differentiable_sparse_solve(sys_cache[3], -residual, B, stol, device, method,
+                                                       None, cached, it == 0)
                 u_guess = u_guess + step.reshape(-1, dpn)
             if res_norm > rtol * res_norm0 and res_norm > atol:
                 raise RuntimeError("Newton-Raphson iteration did not converge.")

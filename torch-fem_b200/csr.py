@@ -597,8 +597,13 @@ def krylov_solve(A: "CSRMatrix | ElementOperator", b: Tensor, method: str = "cg"
 
 def adjoint_matrix_grad(A: CSRMatrix, lam: Tensor, x: Tensor) -> Tensor:
     """g[p] = -lam[row(p)] * x[col(p)] on A's pattern (kernel K7; reference sparse.py:212-216)."""
+    L.require_cuda(lam, x)
+    if lam.shape != (A.n,) or x.shape != (A.n,):
+        raise ValueError("adjoint_matrix_grad expects two vectors of length n")
+    # the kernel reads float64: a float32 solve (b.dtype float32) must not be reinterpreted
+    lam = lam.detach().to(device=A.device, dtype=torch.float64).contiguous()
+    x = x.detach().to(device=A.device, dtype=torch.float64).contiguous()
     g = torch.empty(A.nnz, dtype=torch.float64, device=A.device)
-    L.check(L.lib.tfem_adjoint_matrix_grad(A.n, L.ptr(A.indptr), L.ptr(A.indices),
-                                           L.ptr(lam.contiguous()), L.ptr(x.contiguous()), L.ptr(g),
+    L.check(L.lib.tfem_adjoint_matrix_grad(A.n, L.ptr(A.indptr), L.ptr(A.indices), L.ptr(lam), L.ptr(x), L.ptr(g),
                                            L.stream()))
     return g

@@ -1,25 +1,24 @@
 // Multi-GPU Jacobi-PCG with the two exchange steps of the path fused INTO the compute kernels, over peer
 // memory (CUDA IPC mappings, NVLink 5 / NVSwitch stores) — no NCCL call and no host involvement inside
-// the iteration.
+// the iteration. Peer-memory primitives: peer.cuh.
 //
 // The reference is single-GPU; its Krylov loop is cupy_cg (src/torchfem/sparse.py:414-421).
 // Partitioning (torch-fem_b200/distributed.py): rank r owns a contiguous block of rows
 // [row_lo, row_lo + n_owned) of its LOCAL numbering [low halo | owned | high halo]; owned rows are complete.
 //
-// Every rank allocates one communication buffer (header + two copies of the search direction p) and maps
-// the buffers of all peers. Per iteration `it` (epochs are monotone counters, never reset):
-//   k_dcg_spmv       q = A p over owned rows. Interior slices first; then the CTA waits until every
-//                    neighbour's halo flag has reached the epoch of this iteration and does the slices
-//                    that read halo entries. Fused p.q; the last CTA STORES the local sum into slot
-//                    [my rank] of reduction set A in every rank's buffer, then releases a flag there.
-//   k_dcg_update     waits for all `world` flags of set A, sums the slots in rank order (bit-identical on
-//                    every rank), alpha = rho / p.q; x += alpha p; r -= alpha q; r.r and r.(D^-1 r);
-//                    the last CTA publishes both sums to set B of every rank.
-//   k_dcg_direction  waits for set B, beta = rho' / rho, convergence test; p' = D^-1 r + beta p into the OTHER
-//                    p buffer and, for the entries a neighbour needs, straight into that neighbour's p' halo
-//                    (peer stores); the last CTA releases the halo flags of the next epoch on the neighbours.
-// All-reduce = world stores of <= 3 doubles + a flag per rank (latency of one NVLink store, ~2 us) instead
-// of an NCCL kernel (~15-25 us at 8 GPUs); halo exchange = the direction kernel's own stores.
+// Every rank's communication buffer holds two copies of the search direction p in its symmetric heap.
+// Per iteration `it` (epochs are monotone counters, never reset):
+//   k_dcg_spmv       q = A p over owned rows. Interior slices first; a warp that reaches the slices reading halo
+//                    entries waits (once) for the neighbours' halo flags of this iteration. Fused p.q; the last
+//                    CTA stores the local sum into slot [my rank] of LL set 0 on every rank (data + epoch in the
+//                    same 8-byte words: one NVLink store, no fence, no separate flag).
+//   k_dcg_update     one warp per CTA polls set 0 until all `world` slots carry this epoch, sums them in rank
+//                    order (bit-identical on every rank), alpha = rho / p.q; x += alpha p; r -= alpha q; r.r and
+//                    r.(D^-1 r); the last CTA publishes both sums to set 1 of every rank.
+//   k_dcg_direction  waits for set 1, beta = rho' / rho, convergence test; p' = D^-1 r + beta p into the OTHER
+//                    p buffer. The FIRST CTAs of the grid store the entries a neighbour needs straight into that
+//                    neighbour's p' halo, fence once per CTA, and the last of them releases the halo flag — while
+//                    the rest of the grid is still streaming, so the exchange overlaps the kernel.
 // Hazards: the p buffers ping-pong and each reduction set is consumed before the barrier-like reduction of
 // the other set completes, so no slot is overwritten while a peer may still read it.
 // Every spin is bounded by `timeout_s`: on expiry the solve ends with TFEM_ERR_COMM on every rank instead of
@@ -28,132 +27,25 @@
 #include <string.h>
 
 #include "sell.cuh"
+#include "peer.cuh"
 
 namespace tfem {
 namespace {
 
-constexpr int kMaxRanks = 16;
-constexpr int kMaxNbr = TFEM_MAX_NEIGHBOURS;
-// header layout of a communication buffer (bytes)
-constexpr int64_t OFF_HALO_FLAG = 0;     // uint64 [kMaxRanks]  epoch of the last halo delivered by rank s
-constexpr int64_t OFF_RED_FLAG = 256;    // uint64 [2][kMaxRanks]
-constexpr int64_t OFF_RED_VAL = 1024;    // double [2][kMaxRanks][4]
-constexpr int64_t HEADER_BYTES = 4096;
-
-struct Comm {
-  int rank = 0, world = 1;
-  int64_t vec = 0;  // doubles per p buffer (padded)
-  char* base[kMaxRanks] = {};
-  bool opened[kMaxRanks] = {};
-  unsigned long long epoch = 0;
-  bool broken = false;
-  bool connected = false;
+// trace slots of one CG iteration (ns of %globaltimer; *_WAIT_MAX are durations, maximum over the waiting threads)
+enum Trace {
+  TR_SPMV_BEGIN = 0, TR_SPMV_HALO_WAIT_MAX, TR_SPMV_LAST_CTA, TR_UPD_BEGIN, TR_UPD_WAITED, TR_UPD_LAST_CTA,
+  TR_DIR_BEGIN, TR_DIR_WAITED, TR_DIR_HALO_RELEASED, TR_DIR_LAST_CTA
 };
+static_assert(TR_DIR_LAST_CTA < kTraceSlots, "trace slots");
 
-struct Peers {
-  int rank, world;
-  int64_t vec;
-  char* base[kMaxRanks];
-  unsigned long long timeout_ns;
-};
+constexpr int CH_P = 0;  // halo channel of the search direction
 
-struct Halo {
-  int n_send;
-  int send_peer[kMaxNbr];
-  int64_t send_count[kMaxNbr];
-  const int32_t* send_src[kMaxNbr];  // local indices, or nullptr: contiguous from src0
-  const int32_t* send_dst[kMaxNbr];  // indices in the peer's local numbering, or nullptr: contiguous from dst0
-  int64_t src0[kMaxNbr], dst0[kMaxNbr];
-  int n_recv;
-  int recv_peer[kMaxNbr];
-};
-
-__device__ __forceinline__ double* p_buf(const Peers& P, int r, int which) {
-  return reinterpret_cast<double*>(P.base[r] + HEADER_BYTES) + (int64_t)which * P.vec;
-}
-__device__ __forceinline__ unsigned long long* halo_flag(const Peers& P, int r) {
-  return reinterpret_cast<unsigned long long*>(P.base[r] + OFF_HALO_FLAG);
-}
-__device__ __forceinline__ unsigned long long* red_flag(const Peers& P, int r, int set) {
-  return reinterpret_cast<unsigned long long*>(P.base[r] + OFF_RED_FLAG) + set * kMaxRanks;
-}
-__device__ __forceinline__ double* red_val(const Peers& P, int r, int set) {
-  return reinterpret_cast<double*>(P.base[r] + OFF_RED_VAL) + set * kMaxRanks * 4;
+__device__ __forceinline__ double* p_buf(const Peers& P, int r, int which, int64_t vec) {
+  return heap(P, r) + (int64_t)which * vec;
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-// one thread: spin until *flag >= epoch; false on timeout
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long epoch,
-                                           unsigned long long t0, unsigned long long timeout_ns) {
-  while (ld_acquire_sys(flag) < epoch) {
-    if (global_ns() - t0 > timeout_ns) return false;
-    __nanosleep(40);
-  }
-  return true;
-}
-
-// Whole CTA: wait until every rank has published reduction `set` for `epoch`, sum the slots in rank order.
-// Returns false (in all threads) on timeout; sc[SC_DONE] is then 4.
-template <int K>
-__device__ __forceinline__ bool reduce_wait(const Peers& P, int set, unsigned long long epoch, double (&out)[K],
-                                            double* sc) {
-  __shared__ double s_out[4];
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) {
-    const unsigned long long t0 = global_ns();
-    const unsigned long long* fl = red_flag(P, P.rank, set);
-    bool ok = true;
-    for (int r = 0; r < P.world && ok; ++r) ok = spin_until(fl + r, epoch, t0, P.timeout_ns);
-    if (ok) {
-      const double* v = red_val(P, P.rank, set);
-#pragma unroll
-      for (int j = 0; j < K; ++j) {
-        double s = 0.0;
-        for (int r = 0; r < P.world; ++r) s += __ldcv(v + r * 4 + j);
-        s_out[j] = s;
-      }
-    } else {
-      sc[SC_DONE] = 4.0;
-    }
-    s_ok = ok ? 1 : 0;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < K; ++j) out[j] = s_out[j];
-  const bool ok = s_ok != 0;
-  __syncthreads();
-  return ok;
-}
-
-// warp 0 of the last CTA: lane r stores this rank's sums into rank r's slot and releases the flag there
-template <int K>
-__device__ __forceinline__ void reduce_publish(const Peers& P, int set, unsigned long long epoch,
-                                               const double (&tot)[K]) {
-  const int lane = threadIdx.x & 31;
-  if (lane < P.world) {
-    double* v = red_val(P, lane, set) + P.rank * 4;
-#pragma unroll
-    for (int j = 0; j < K; ++j) v[j] = tot[j];
-    __threadfence_system();
-    st_release_sys(red_flag(P, lane, set) + P.rank, epoch);
-  }
-}
-
-// true in every thread of the CTA that takes the last ticket; all peer stores of the grid are then visible
-// system-wide once the caller has executed __threadfence_system()
+// true in every thread of the CTA that takes the last ticket
 __device__ __forceinline__ bool last_cta(unsigned int* ticket) {
   __shared__ bool s_last;
   __syncthreads();
@@ -164,41 +56,18 @@ __device__ __forceinline__ bool last_cta(unsigned int* ticket) {
     if (s_last) *ticket = 0u;
   }
   __syncthreads();
-  if (s_last) __threadfence_system();
   return s_last;
 }
 
-__device__ __forceinline__ void release_halo_flags(const Peers& P, const Halo& H, unsigned long long epoch) {
-  const int lane = threadIdx.x;
-  if (lane < H.n_send) st_release_sys(halo_flag(P, H.send_peer[lane]) + P.rank, epoch);
-}
-
-// value(i) for every entry a neighbour needs -> the neighbour's p buffer `which`
-template <typename F>
-__device__ __forceinline__ void halo_send(const Peers& P, const Halo& H, int which, F value) {
-  bool stored = false;
-  for (int s = 0; s < H.n_send; ++s) {
-    double* dst = p_buf(P, H.send_peer[s], which);
-    const int32_t* si = H.send_src[s];
-    const int32_t* di = H.send_dst[s];
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < H.send_count[s];
-         k += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t i = si ? (int64_t)si[k] : H.src0[s] + k;
-      const int64_t d = di ? (int64_t)di[k] : H.dst0[s] + k;
-      dst[d] = value(i);
-      stored = true;
-    }
-  }
-  if (stored) __threadfence_system();  // my peer stores are visible system-wide before I take a ticket
-}
-
-// x = 0 ; r = b ; p0 = D^-1 b (owned rows [o, o+n)) ; halo of p0 to the neighbours ; (r.r, r.z, b.b) -> set B
+// x = 0 ; r = b ; p0 = D^-1 b (owned rows [o, o+n)) ; halo of p0 to the neighbours ; (r.r, r.z, b.b) -> set 1
 __global__ void __launch_bounds__(kVecThreads)
-    k_dcg_init(int64_t o, int64_t n, const double* __restrict__ b, const double* __restrict__ dinv,
+    k_dcg_init(int64_t o, int64_t n, int64_t vec, const double* __restrict__ b, const double* __restrict__ dinv,
                double* __restrict__ r, double* __restrict__ x, double* partials, unsigned int* ticket,
-               Peers P, Halo H, unsigned long long ep_halo, unsigned long long ep_red) {
+               Peers P, Halo H, int n_halo_ctas, unsigned long long ep_halo, unsigned long long ep_red) {
   __shared__ double s_red[kVecThreads / 32];
-  double* p = p_buf(P, P.rank, 0);
+  double* p = p_buf(P, P.rank, 0, vec);
+  if ((int)blockIdx.x < n_halo_ctas)
+    halo_send_and_release(P, H, 0, CH_P, ep_halo, n_halo_ctas, ticket + 1, [&](int64_t i) { return dinv[i] * b[i]; });
   double rr = 0.0, rho = 0.0;
   for (int64_t k = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; k < n; k += (int64_t)gridDim.x * kVecThreads) {
     const int64_t i = o + k;
@@ -210,22 +79,24 @@ __global__ void __launch_bounds__(kVecThreads)
     rr = fma(bi, bi, rr);
     rho = fma(bi, zi, rho);
   }
-  halo_send(P, H, 0, [&](int64_t i) { return dinv[i] * b[i]; });
   double mine[2], tot[2];
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   mine[1] = block_sum<kVecThreads>(rho, s_red);
   if (publish_and_reduce<2>(mine, partials, ticket, tot)) {
-    __threadfence_system();
     const double out[3] = {tot[0], tot[1], tot[0]};
-    reduce_publish<3>(P, 1, ep_red, out);
-    release_halo_flags(P, H, ep_halo);
+    ll_publish<3>(P, 1, ep_red, out);
   }
 }
 
 // scalar state after the initial reduction (same on every rank)
 __global__ void k_dcg_scalars_init(double* sc, Peers P, unsigned long long ep_red, double rtol, double atol) {
+  __shared__ double s_out[4];
+  __shared__ int s_ok;
   double tot[3];
-  if (!reduce_wait<3>(P, 1, ep_red, tot, sc)) return;
+  if (!ll_wait_sum<3>(P, 1, ep_red, tot, s_out, &s_ok)) {
+    if (threadIdx.x == 0) sc[SC_DONE] = 4.0;
+    return;
+  }
   if (threadIdx.x == 0) {
     const double bnrm = sqrt(tot[2]);
     const double tol = fmax(atol, rtol * bnrm);
@@ -242,15 +113,16 @@ __global__ void k_dcg_scalars_init(double* sc, Peers P, unsigned long long ep_re
 // q = A p over the owned slices [ts_lo, ts_hi). One strided index space: the interior slices [ti_lo, ti_hi)
 // first, then the slices that read halo entries. A warp that reaches the second part waits (once) until every
 // neighbour's halo flag has reached ep_halo; by then the flags are normally long set, so the exchange is
-// hidden behind the interior rows. p.q over owned rows -> set A.
+// hidden behind the interior rows. p.q over owned rows -> LL set 0 of every rank.
 template <int DPN>
 __global__ void __launch_bounds__(kSellWarps * 32, 8)
-    k_dcg_spmv(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
+    k_dcg_spmv(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which, int64_t vec,
                double* __restrict__ q, double* sc, double* partials, unsigned int* ticket, Peers P, Halo H,
-               unsigned long long ep_halo, unsigned long long ep_red) {
+               long long it, unsigned long long ep_halo, unsigned long long ep_red) {
   __shared__ double s_red[kSellWarps];
   if (sc[SC_DONE] != 0.0) return;
-  const double* __restrict__ p = p_buf(P, P.rank, which);
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_SPMV_BEGIN);
+  const double* __restrict__ p = p_buf(P, P.rank, which, vec);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * kSellWarps;
   const int64_t n_int = ti_hi - ti_lo, n_low = ti_lo - ts_lo, n_all = ts_hi - ts_lo;
@@ -271,9 +143,9 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
     int ok = 1;
     if (lane == 0) {
       const unsigned long long t0 = global_ns();
-      const unsigned long long* fl = halo_flag(P, P.rank);
-      for (int s = 0; s < H.n_recv && ok; ++s) ok = spin_until(fl + H.recv_peer[s], ep_halo, t0, P.timeout_ns) ? 1 : 0;
+      ok = halo_wait_thread(P, H, CH_P, ep_halo) ? 1 : 0;
       if (!ok) sc[SC_DONE] = 4.0;
+      trace_max(P, it, TR_SPMV_HALO_WAIT_MAX, global_ns() - t0);
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
     for (; ok && j < n_all; j += stride) {
@@ -293,19 +165,30 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
   }
   const double bsum = block_sum<kSellWarps * 32>(dot, s_red);
   double mine[1] = {bsum}, tot[1];
-  if (publish_and_reduce<1>(mine, partials, ticket, tot)) reduce_publish<1>(P, 0, ep_red, tot);
+  if (publish_and_reduce<1>(mine, partials, ticket, tot)) {
+    ll_publish<1>(P, 0, ep_red, tot);
+    if (threadIdx.x == 0) trace_mark(P, it, TR_SPMV_LAST_CTA);
+  }
 }
 
-// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; (r.r, r.D^-1 r) -> set B
-__global__ void __launch_bounds__(kVecThreads)
-    k_dcg_update(int64_t o, int64_t n, int which, const double* __restrict__ q, const double* __restrict__ dinv,
-                 double* __restrict__ x, double* __restrict__ r, double* sc, double* partials,
-                 unsigned int* ticket, Peers P, unsigned long long ep_wait, unsigned long long ep_red) {
+// alpha = rho / p.q ; x += alpha p ; r -= alpha q ; (r.r, r.D^-1 r) -> LL set 1
+__global__ void __launch_bounds__(kVecThreads, 8)
+    k_dcg_update(int64_t o, int64_t n, int which, int64_t vec, const double* __restrict__ q,
+                 const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* sc,
+                 double* partials, unsigned int* ticket, Peers P, long long it, unsigned long long ep_wait,
+                 unsigned long long ep_red) {
   __shared__ double s_red[kVecThreads / 32];
+  __shared__ double s_out[4];
+  __shared__ int s_ok;
   if (sc[SC_DONE] != 0.0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_UPD_BEGIN);
   double pq[1];
-  if (!reduce_wait<1>(P, 0, ep_wait, pq, sc)) return;
-  const double* __restrict__ p = p_buf(P, P.rank, which);
+  if (!ll_wait_sum<1>(P, 0, ep_wait, pq, s_out, &s_ok)) {
+    if (threadIdx.x == 0) sc[SC_DONE] = 4.0;
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_UPD_WAITED);
+  const double* __restrict__ p = p_buf(P, P.rank, which, vec);
   const double alpha = sc[SC_RHO] / pq[0];
   double rr = 0.0, rho = 0.0;
   for (int64_t k = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; k < n; k += (int64_t)gridDim.x * kVecThreads) {
@@ -320,69 +203,95 @@ __global__ void __launch_bounds__(kVecThreads)
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   mine[1] = block_sum<kVecThreads>(rho, s_red);
   if (publish_and_reduce<2>(mine, partials, ticket, tot)) {
-    reduce_publish<2>(P, 1, ep_red, tot);
+    ll_publish<2>(P, 1, ep_red, tot);
     if (threadIdx.x == 0) {
       sc[SC_PQ] = pq[0];
       sc[SC_ALPHA] = alpha;
+      trace_mark(P, it, TR_UPD_LAST_CTA);
     }
   }
 }
 
-// beta = rho' / rho ; p' = D^-1 r + beta p (other buffer) + peer stores of the halo entries ; scalar state
-__global__ void __launch_bounds__(kVecThreads)
-    k_dcg_direction(int64_t o, int64_t n, int which, const double* __restrict__ r,
+// beta = rho' / rho ; p' = D^-1 r + beta p (other buffer) ; the FIRST CTAs store the entries the neighbours need
+// straight into their p' halos and release the halo flag while the rest of the grid is still updating p'
+__global__ void __launch_bounds__(kVecThreads, 8)
+    k_dcg_direction(int64_t o, int64_t n, int which, int64_t vec, const double* __restrict__ r,
                     const double* __restrict__ dinv, double* sc, unsigned int* ticket, Peers P, Halo H,
-                    unsigned long long ep_wait, unsigned long long ep_halo) {
+                    int n_halo_ctas, long long it, unsigned long long ep_wait, unsigned long long ep_halo) {
+  __shared__ double s_out[4];
+  __shared__ int s_ok;
   if (sc[SC_DONE] != 0.0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_DIR_BEGIN);
   double t2[2];
-  if (!reduce_wait<2>(P, 1, ep_wait, t2, sc)) return;
+  if (!ll_wait_sum<2>(P, 1, ep_wait, t2, s_out, &s_ok)) {
+    if (threadIdx.x == 0) sc[SC_DONE] = 4.0;
+    return;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_DIR_WAITED);
   const double rho_prev = sc[SC_RHO];
   const double beta = t2[1] / rho_prev;
-  const double* __restrict__ p = p_buf(P, P.rank, which);
-  double* __restrict__ pn = p_buf(P, P.rank, which ^ 1);
+  const double* __restrict__ p = p_buf(P, P.rank, which, vec);
+  double* __restrict__ pn = p_buf(P, P.rank, which ^ 1, vec);
+  if ((int)blockIdx.x < n_halo_ctas) {
+    const bool released = halo_send_and_release(P, H, (int64_t)(which ^ 1) * vec, CH_P, ep_halo, n_halo_ctas,
+                                                ticket + 1, [&](int64_t i) { return fma(beta, p[i], dinv[i] * r[i]); });
+    if (released && threadIdx.x == 0) trace_mark(P, it, TR_DIR_HALO_RELEASED);
+  }
   for (int64_t k = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; k < n; k += (int64_t)gridDim.x * kVecThreads) {
     const int64_t i = o + k;
     pn[i] = fma(beta, p[i], dinv[i] * r[i]);
   }
-  halo_send(P, H, which ^ 1, [&](int64_t i) { return fma(beta, p[i], dinv[i] * r[i]); });
-  if (last_cta(ticket)) {
-    if (threadIdx.x < 32) release_halo_flags(P, H, ep_halo);
-    if (threadIdx.x == 0) {
-      sc[SC_RHO_PREV] = rho_prev;
-      sc[SC_RHO] = t2[1];
-      sc[SC_RR] = t2[0];
-      sc[SC_BETA] = beta;
-      sc[SC_ITERS] += 1.0;
-      if (!isfinite(t2[0])) sc[SC_DONE] = 2.0;
-      else if (sqrt(t2[0]) < sc[SC_TOL]) sc[SC_DONE] = 1.0;
-    }
+  if (last_cta(ticket) && threadIdx.x == 0) {
+    sc[SC_RHO_PREV] = rho_prev;
+    sc[SC_RHO] = t2[1];
+    sc[SC_RR] = t2[0];
+    sc[SC_BETA] = beta;
+    sc[SC_ITERS] += 1.0;
+    if (!isfinite(t2[0])) sc[SC_DONE] = 2.0;
+    else if (sqrt(t2[0]) < sc[SC_TOL]) sc[SC_DONE] = 1.0;
+    trace_mark(P, it, TR_DIR_LAST_CTA);
   }
 }
 
 // barrier at the end of a solve: nobody starts the next solve (whose first kernel overwrites reduction slots
 // and p halos on its peers) before every rank has finished the last kernel of this one
-__global__ void k_dcg_finish(double* sc, Peers P, unsigned long long ep) {
-  if (sc[SC_DONE] == 4.0) return;
-  if (threadIdx.x < P.world) st_release_sys(red_flag(P, threadIdx.x, 0) + P.rank, ep);
+__global__ void k_comm_barrier(double* sc, Peers P, unsigned long long ep) {
+  if (sc && sc[SC_DONE] == 4.0) return;
+  if (threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(barrier_flag(P, threadIdx.x) + P.rank, ep);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long t0 = global_ns();
-    const unsigned long long* fl = red_flag(P, P.rank, 0);
+    const unsigned long long* fl = barrier_flag(P, P.rank);
     bool ok = true;
     for (int r = 0; r < P.world && ok; ++r) ok = spin_until(fl + r, ep, t0, P.timeout_ns);
-    if (!ok) sc[SC_DONE] = 4.0;
+    if (ok) fence_acq_rel_sys();
+    if (!ok && sc) sc[SC_DONE] = 4.0;
   }
+}
+
+// grids are cached per (instantiation, device): one process may drive several devices
+template <typename K>
+int cached_resident_ctas(K kernel, int threads) {
+  static int g[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g[dev]) g[dev] = resident_ctas(kernel, threads);
+  return g[dev];
 }
 
 template <int DPN>
 int launch_dcg_spmv(const Sell& A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
-                    double* q, double* sc, double* partials, unsigned int* ticket, const Peers& P,
-                    const Halo& H, unsigned long long ep_halo, unsigned long long ep_red, cudaStream_t st) {
-  static int g = 0;
-  if (!g) g = resident_ctas(k_dcg_spmv<DPN>, kSellWarps * 32);
+                    int64_t vec, double* q, double* sc, double* partials, unsigned int* ticket, const Peers& P,
+                    const Halo& H, long long it, unsigned long long ep_halo, unsigned long long ep_red,
+                    cudaStream_t st) {
+  const int g = cached_resident_ctas(k_dcg_spmv<DPN>, kSellWarps * 32);
   const int64_t want = (ts_hi - ts_lo + kSellWarps - 1) / kSellWarps;
   k_dcg_spmv<DPN><<<(int)(want < g ? (want > 0 ? want : 1) : g), kSellWarps * 32, 0, st>>>(
-      A, ts_lo, ts_hi, ti_lo, ti_hi, which, q, sc, partials, ticket, P, H, ep_halo, ep_red);
+      A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, q, sc, partials, ticket, P, H, it, ep_halo, ep_red);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -401,8 +310,8 @@ extern "C" int tfem_comm_create(int rank, int world, int64_t vec_doubles, void**
   Comm* c = new Comm();
   c->rank = rank;
   c->world = world;
-  c->vec = pad32(vec_doubles);
-  const size_t bytes = (size_t)HEADER_BYTES + 2 * (size_t)c->vec * sizeof(double);
+  c->heap_doubles = 2 * pad32(vec_doubles);
+  const size_t bytes = (size_t)HEADER_BYTES + (size_t)c->heap_doubles * sizeof(double);
   void* mem = nullptr;
   int rc = check_cuda(cudaMalloc(&mem, bytes), "cudaMalloc(comm buffer)");
   if (rc != TFEM_OK) { delete c; return rc; }
@@ -448,6 +357,26 @@ extern "C" int tfem_comm_destroy(void* comm) {
   return TFEM_OK;
 }
 
+extern "C" int tfem_comm_heap(void* comm, void** heap_dev_out, int64_t* heap_doubles_out) {
+  Comm* c = static_cast<Comm*>(comm);
+  TFEM_REQUIRE(c && heap_dev_out && heap_doubles_out, "comm_heap: null pointer");
+  *heap_dev_out = c->base[c->rank] + HEADER_BYTES;
+  *heap_doubles_out = c->heap_doubles;
+  return TFEM_OK;
+}
+
+extern "C" int tfem_comm_set_trace(void* comm, void* trace_dev, int64_t first_iteration, int n_iterations,
+                                   int time_spmv) {
+  Comm* c = static_cast<Comm*>(comm);
+  TFEM_REQUIRE(c, "comm_set_trace: null communicator");
+  TFEM_REQUIRE(!trace_dev || n_iterations > 0, "comm_set_trace: empty trace window");
+  c->trace = static_cast<unsigned long long*>(trace_dev);
+  c->trace_it0 = first_iteration;
+  c->trace_n = trace_dev ? n_iterations : 0;
+  c->time_spmv = time_spmv;
+  return TFEM_OK;
+}
+
 extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, int64_t n_owned,
                               int64_t interior_lo, int64_t interior_hi, int n_sends,
                               const tfem_halo_send_t* sends, int n_recv, const int32_t* recv_peers,
@@ -462,37 +391,17 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
   if (rc0 != TFEM_OK) return rc0;
   TFEM_REQUIRE(dinv && b && x && work && info, "dcg_solve: null pointer");
   const int64_t n_local = a->n_rows;
+  const int64_t vec = c->heap_doubles / 2;
   TFEM_REQUIRE(n_owned > 0 && row_lo >= 0 && row_lo + n_owned <= n_local, "dcg_solve: bad row range");
-  TFEM_REQUIRE(n_local <= c->vec, "dcg_solve: communicator vectors are too short for this matrix");
-  TFEM_REQUIRE(n_sends >= 0 && n_sends <= kMaxNbr && n_recv >= 0 && n_recv <= kMaxNbr && (n_sends == 0 || sends) &&
-                   (n_recv == 0 || recv_peers), "dcg_solve: bad halo plan");
+  TFEM_REQUIRE(n_local <= vec, "dcg_solve: communicator vectors are too short for this matrix");
   if (maxiter <= 0) maxiter = 10 * n_local * c->world;
   if (check_every <= 0) check_every = 32;
   if (!(timeout_s > 0.0)) timeout_s = 20.0;
 
-  Peers P;
-  P.rank = c->rank;
-  P.world = c->world;
-  P.vec = c->vec;
-  for (int r = 0; r < kMaxRanks; ++r) P.base[r] = c->base[r];
-  P.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  const Peers P = make_peers(c, timeout_s);
   Halo H;
-  memset(&H, 0, sizeof(H));
-  H.n_send = n_sends;
-  for (int s = 0; s < n_sends; ++s) {
-    TFEM_REQUIRE(sends[s].peer >= 0 && sends[s].peer < c->world && sends[s].peer != c->rank, "dcg_solve: bad peer");
-    H.send_peer[s] = sends[s].peer;
-    H.send_count[s] = sends[s].count;
-    H.send_src[s] = sends[s].src_idx;
-    H.send_dst[s] = sends[s].dst_idx;
-    H.src0[s] = sends[s].src_start;
-    H.dst0[s] = sends[s].dst_start;
-  }
-  H.n_recv = n_recv;
-  for (int s = 0; s < n_recv; ++s) {
-    TFEM_REQUIRE(recv_peers[s] >= 0 && recv_peers[s] < c->world, "dcg_solve: bad peer");
-    H.recv_peer[s] = recv_peers[s];
-  }
+  rc0 = fill_halo(H, c, n_sends, sends, n_recv, recv_peers);
+  if (rc0 != TFEM_OK) return rc0;
 
   Sell A = make_sell(a);
   const int64_t row_hi = row_lo + n_owned;
@@ -508,44 +417,68 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
 
   Work w = carve(work, n_local);
   const int vg = vec_grid(n_owned);
+  int hc = halo_ctas(H.send_total, kVecThreads);
+  if (hc > vg) hc = vg;
   const unsigned long long E0 = c->epoch;
   TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
-  k_dcg_init<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, b, dinv, w.r, x, w.partials, w.ticket, P, H, E0 + 1, E0 + 1);
+  k_dcg_init<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, vec, b, dinv, w.r, x, w.partials, w.ticket, P, H, hc,
+                                        E0 + 1, E0 + 1);
   TFEM_LAUNCH_CHECK();
   k_dcg_scalars_init<<<1, 32, 0, st>>>(w.sc, P, E0 + 1, rtol, atol);
   TFEM_LAUNCH_CHECK();
   double launches = 2, sc_host[SC_COUNT];
   int64_t issued = 0;
   int rc = TFEM_OK;
+  // optional CUDA-event timing of the SpMV launches of the second batch (the kernel the roofline is quoted on)
+  const int kEv = 32;
+  cudaEvent_t ev[2 * kEv] = {};
+  int n_ev = 0;
+  double spmv_ms = 0.0;
   while (true) {
     TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
     TFEM_CUDA(cudaStreamSynchronize(st));
+    if (n_ev > 0 && spmv_ms == 0.0) {
+      float acc = 0.f, ms = 0.f;
+      for (int e = 0; e < n_ev; ++e)
+        if (cudaEventElapsedTime(&ms, ev[2 * e], ev[2 * e + 1]) == cudaSuccess) acc += ms;
+      spmv_ms = acc / n_ev;
+    }
     if (sc_host[SC_DONE] != 0.0 || issued >= maxiter) break;
     const int64_t batch = maxiter - issued < check_every ? maxiter - issued : check_every;
+    const bool timed = c->time_spmv && issued > 0 && n_ev == 0;
     for (int64_t k = 0; k < batch; ++k) {
-      const unsigned long long it = (unsigned long long)(issued + k);
+      const long long it = (long long)(issued + k);
       const int which = (int)(it & 1);
+      const unsigned long long e1 = E0 + 1 + (unsigned long long)it, e2 = e1 + 1;
+      const bool tm = timed && k < kEv;
+      if (tm) {
+        cudaEventCreate(&ev[2 * n_ev]);
+        cudaEventCreate(&ev[2 * n_ev + 1]);
+        cudaEventRecord(ev[2 * n_ev], st);
+      }
       if (A.dpn == 3)
-        rc = launch_dcg_spmv<3>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, w.q, w.sc, w.partials, w.ticket, P, H, E0 + 1 + it, E0 + 1 + it, st);
+        rc = launch_dcg_spmv<3>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       else if (A.dpn == 2)
-        rc = launch_dcg_spmv<2>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, w.q, w.sc, w.partials, w.ticket, P, H, E0 + 1 + it, E0 + 1 + it, st);
+        rc = launch_dcg_spmv<2>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       else
-        rc = launch_dcg_spmv<0>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, w.q, w.sc, w.partials, w.ticket, P, H, E0 + 1 + it, E0 + 1 + it, st);
+        rc = launch_dcg_spmv<0>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       if (rc != TFEM_OK) { c->broken = true; return rc; }
-      k_dcg_update<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, w.q, dinv, x, w.r, w.sc, w.partials, w.ticket, P,
-                                              E0 + 1 + it, E0 + 2 + it);
-      k_dcg_direction<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, w.r, dinv, w.sc, w.ticket, P, H, E0 + 2 + it,
-                                                 E0 + 2 + it);
+      if (tm) cudaEventRecord(ev[2 * n_ev++ + 1], st);
+      k_dcg_update<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, vec, w.q, dinv, x, w.r, w.sc, w.partials,
+                                              w.ticket, P, it, e1, e2);
+      k_dcg_direction<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, vec, w.r, dinv, w.sc, w.ticket, P, H, hc,
+                                                 it, e2, e2);
     }
     rc = check_cuda(cudaGetLastError(), "dcg launch");
     if (rc != TFEM_OK) { c->broken = true; return rc; }
     issued += batch;
     launches += 3.0 * batch;
   }
+  for (int e = 0; e < 2 * n_ev; ++e) cudaEventDestroy(ev[e]);
   c->epoch = E0 + (unsigned long long)issued + 2;
   if (sc_host[SC_DONE] != 4.0) {
     const double done = sc_host[SC_DONE];
-    k_dcg_finish<<<1, 32, 0, st>>>(w.sc, P, c->epoch);
+    k_comm_barrier<<<1, 32, 0, st>>>(w.sc, P, ++c->barrier_epoch);
     TFEM_LAUNCH_CHECK();
     TFEM_CUDA(cudaMemcpyAsync(sc_host, w.sc, sizeof(sc_host), cudaMemcpyDeviceToHost, st));
     TFEM_CUDA(cudaStreamSynchronize(st));
@@ -559,7 +492,7 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
   info[4] = (double)issued;
   info[5] = launches;
   info[6] = sc_host[SC_DONE];
-  info[7] = 0.0;
+  info[7] = spmv_ms;
   if (sc_host[SC_DONE] == 4.0) {
     c->broken = true;
     set_last_error("communication", "a peer did not deliver its halo / reduction within the timeout");

@@ -21,9 +21,6 @@ is covered by world_size-2 gloo tests on CPU (tests/test_distributed_cpu.py).
 """
 from __future__ import annotations
 
-import json
-import os
-import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -292,6 +289,30 @@ class PeerComm:
             L.check(L.lib.tfem_comm_connect(self.handle, b"".join(handles)))
             dist.barrier(group=group)  # every buffer is zeroed and mapped before anybody stores into a peer
 
+    def set_trace(self, n_iterations: int = 0, first_iteration: int = 0, time_spmv: bool = False):
+        """In-kernel profile of the cross-GPU waits (`tfem_comm_set_trace`): the kernels of the next solves stamp
+        %globaltimer at fixed points of iterations [first, first + n). `n_iterations = 0` switches it off. Returns
+        the device buffer [n, TRACE_SLOTS] (int64 ns), to be read after the solve."""
+        from . import _lib as L
+
+        self.trace = None
+        if n_iterations > 0:
+            self.trace = torch.zeros(n_iterations, L.TRACE_SLOTS, dtype=torch.int64,
+                                     device=torch.device("cuda", torch.cuda.current_device()))
+        L.check(L.lib.tfem_comm_set_trace(self.handle, L.ptr(self.trace), int(first_iteration), int(n_iterations),
+                                          1 if time_spmv else 0))
+        return self.trace
+
+    def heap(self) -> Tensor:
+        """This rank's symmetric heap as a float64 tensor view (no copy)."""
+        import ctypes
+
+        from . import _lib as L
+
+        p, n = ctypes.c_void_p(), ctypes.c_int64()
+        L.check(L.lib.tfem_comm_heap(self.handle, ctypes.byref(p), ctypes.byref(n)))
+        return _tensor_from_ptr(p.value, int(n.value), torch.device("cuda", torch.cuda.current_device()))
+
     def close(self):
         from . import _lib as L
 
@@ -300,6 +321,15 @@ class PeerComm:
                 dist.barrier()  # nobody unmaps while a peer may still store into this buffer
             L.check(L.lib.tfem_comm_destroy(self.handle))
             self.handle = None
+
+
+def _tensor_from_ptr(ptr: int, n: int, device) -> Tensor:
+    """float64 tensor view of `n` doubles of device memory owned by the library (lifetime: the communicator's)."""
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    return torch.as_tensor(_Mem(), device=device)
 
 
 class FusedCG:
@@ -357,7 +387,7 @@ class FusedCG:
                                   int(maxiter if maxiter > 0 else self.default_maxiter), int(check_every),
                                   float(timeout_s), info.ctypes.data, L.stream())
         stats = {"iterations": int(info[0]), "resnorm": float(info[1]), "bnorm": float(info[2]),
-                 "converged": bool(info[3]), "launches": int(info[5])}
+                 "converged": bool(info[3]), "launches": int(info[5]), "spmv_ms": float(info[7])}
         if rc in (L.ERR_NOT_CONVERGED, L.ERR_BREAKDOWN):
             raise RuntimeError(f"CG failed with exit code {stats['iterations'] if rc == L.ERR_NOT_CONVERGED else -1}")
         L.check(rc)
@@ -416,207 +446,3 @@ def coordinate_partition(nodes: Tensor, elements: Tensor, world: int, rank: int,
 def weak_scaling_edge(E: int, world: int) -> int:
     """Edge (in elements) of the global cube that gives every rank a config-sized share: E * world^(1/3)."""
     return int(round(E * world ** (1.0 / 3.0)))
-
-
-def bench_multi_gpu(args, metric: str, unit: str, rtol: float):
-    """bench.py body for N > 1 (launched by torchrun, one rank per GPU): weak scaling of the cube benchmark —
-    the global mesh is the cube with N times the elements of the single-GPU config (edge E*N^(1/3): 189^3,
-    238^3, 300^3 elements for N = 2, 4, 8 at E = 150), cut into N slabs of x-planes, so every rank holds
-    ~E^3 elements. value = global DOFs / max-over-ranks device time of integrate + assemble + rhs +
-    distributed PCG."""
-    from . import _lib as L
-    from . import csr
-    from .materials import IsotropicElasticity3D
-
-    multi = dist.is_initialized()
-
-    def _barrier():
-        if multi:
-            dist.barrier()
-
-    def _allreduce(t, op=dist.ReduceOp.SUM):
-        if multi:
-            dist.all_reduce(t, op=op)
-
-    rank, world = (dist.get_rank(), dist.get_world_size()) if multi else (0, 1)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    E = args.edge
-    config_c = getattr(args, "config", "B") == "C"
-    if config_c:
-        # BASELINE configs[2]: Hexa2 (20-node serendipity) cube, strong scaling of ONE global mesh. The mesh is
-        # made once per rank on the host with the reference-order generator, then cut by x-coordinate.
-        from .elements import Hexa2 as EType, linear_to_quadratic
-        from .mesh import cube_hexa
-
-        with torch.device("cpu"):
-            nodes_g, elements_g = linear_to_quadratic(*cube_hexa(E + 1, E + 1, E + 1))
-        nodes_h, mesh, ranges, _ = coordinate_partition(nodes_g, elements_g, world, rank)
-        n_dofs_global = 3 * nodes_g.shape[0]
-        n_elem_global = elements_g.shape[0]
-        del nodes_g, elements_g
-        Eg, Lx = E, 1.0
-        workload = (f"linear-elastic Hexa2 (20-node) cube {E}^3 elements ({n_dofs_global} DOFs), x-coordinate partition "
-                    f"into {world} node blocks, Jacobi-PCG to 1e-8 (BASELINE configs[2]; strong scaling)")
-    else:
-        from .elements import Hexa1 as EType
-
-        Eg = weak_scaling_edge(E, world)
-        h = 1.0 / E
-        nodes_h, mesh, ranges, (Nx, Ny, Nz) = cube_slab(Eg, Eg, Eg, h, world, rank)
-        Lx = Eg * h
-        n_dofs_global = Nx * Ny * Nz * 3
-        n_elem_global = Eg ** 3
-        workload = (f"linear-elastic Hexa1 cube {Eg}^3 elements (= {world} x {E}^3, weak scaling of BASELINE "
-                    f"configs[1]), {world} slabs of x-planes, Jacobi-PCG to 1e-8")
-    con_h = torch.zeros(mesh.n_local, 3, dtype=torch.bool)
-    disp_h = torch.zeros(mesh.n_local, 3, dtype=torch.float64)
-    con_h[nodes_h[:, 0] == 0.0, :] = True
-    right = (nodes_h[:, 0] - Lx).abs() < 1e-12
-    con_h[right, 0] = True
-    disp_h[right, 0] = 0.1
-    plan = build_halo_plan(mesh, ranges, rank, 3)
-    halo = HaloExchanger(plan, dev)
-    host = [nodes_h.contiguous(), mesh.elements.contiguous(), con_h.ravel().to(torch.uint8), disp_h.ravel().contiguous(),
-            torch.full((len(mesh.elements),), 1000.0), torch.full((len(mesh.elements),), 0.3)]
-    host = [t.pin_memory() for t in host]
-    nodes, elements, is_con, disp, E_mod, nu = (t.to(dev) for t in host)
-    ip = EType.ipoints.to(torch.float64).cpu()
-    bref, w = EType.B(ip), EType.iweights.to(torch.float64).cpu()
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    pattern = csr.Pattern(elements, mesh.n_local, 3)
-    ev1.record()
-    torch.cuda.synchronize()
-    setup_ms = ev0.elapsed_time(ev1)
-    row_lo, n_owned = 3 * mesh.lo, 3 * mesh.n_owned
-    vals = torch.empty(pattern.nnz, dtype=torch.float64, device=dev)
-    rhs_buf = torch.empty(pattern.n_dofs, dtype=torch.float64, device=dev)
-    state = {}
-    fused = getattr(args, "dist_cg", "fused") == "fused"
-    cg = FusedCG(pattern.indptr, pattern.indices, pattern.n_dofs, row_lo, n_owned, plan, dev) if fused else None
-
-    def hot_path(nodes, elements, is_con, disp, E_mod, nu):
-        # per-element material -> tangent on the device, as the reference's vectorised material does
-        C = IsotropicElasticity3D(E_mod, nu).C
-        k = csr.integrate_k(L.KIND_MECH, bref, w, nodes, elements, C, check=False)
-        del C
-        rhs = rhs_buf   # local halo values of du_bc come from the BC data, so the lifting needs no exchange
-        csr.assemble(pattern, k, is_con, out=vals, ubc=disp, lift=rhs)
-        del k
-        A = pattern.matrix(vals)
-        M = csr.JacobiPreconditioner(A)
-        if fused:
-            x, info = cg.solve(A, M.dinv, rhs, rtol=rtol)
-        else:
-            x, info = distributed_cg(A, M.dinv, rhs, row_lo, n_owned, halo, rtol=rtol)
-        state.update(A=A, rhs=rhs, x=x, info=info)
-        return x
-
-    def step():
-        return hot_path(nodes, elements, is_con, disp, E_mod, nu)
-
-    def step_e2e():
-        d = [t.to(dev, non_blocking=True) for t in host]
-        x = hot_path(*d)
-        return x[row_lo:row_lo + n_owned].cpu()
-
-    from bench import ClockSampler  # bench.py is the entry script; reuse its sampler
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
-    _barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    _barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
-    _allreduce(t, dist.ReduceOp.MAX)
-    ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-
-    # end to end: every rank's inputs come from pinned host memory, its part of the solution goes back
-    step_e2e()
-    _barrier()
-    torch.cuda.synchronize()
-    n_e2e = max(1, min(args.steps, 2))
-    e0.record()
-    for _ in range(n_e2e):
-        step_e2e()
-    e1.record()
-    _barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / n_e2e], dtype=torch.float64, device=dev)
-    _allreduce(t, dist.ReduceOp.MAX)
-    ms_e2e = float(t.item())
-    io = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host), 8 * n_owned], dtype=torch.int64, device=dev)
-    _allreduce(io)
-
-    # true global relative residual of the last solve
-    A, rhs, x, info = state["A"], state["rhs"], state["x"], state["info"]
-    halo(x)
-    r = (rhs - A.matvec(x))[row_lo:row_lo + n_owned]
-    num = torch.stack([(r * r).sum(), (rhs[row_lo:row_lo + n_owned] ** 2).sum()])
-    _allreduce(num)
-    true_res = float((num[0] / num[1]).sqrt())
-    nnz_owned = torch.tensor([int(pattern.indptr[row_lo + n_owned] - pattern.indptr[row_lo])], device=dev)
-    _allreduce(nnz_owned)
-
-    # SpMV kernel time on this rank (local rows), for the per-GPU roofline
-    xs = torch.randn(A.n, dtype=torch.float64, device=dev)
-    ys = torch.empty_like(xs)
-    A.matvec(xs, out=ys, fmt="sell")
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10):
-        A.matvec(xs, out=ys, fmt="sell")
-    b.record()
-    torch.cuda.synchronize()
-    spmv_ms = a.elapsed_time(b) / 10
-    spmv_bytes = 12 * pattern.nnz + 20 * A.n
-    if rank == 0:
-        from bench import measured_peaks
-
-        peak, peak_src = measured_peaks()
-        achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
-        line = {
-            "metric": metric, "value": n_dofs_global / (ms / 1e3), "unit": unit, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong" if config_c else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload, "n_dofs": int(n_dofs_global), "n_elem": int(n_elem_global),
-                       "nnz": int(nnz_owned.item()), "rtol": rtol,
-                       "cg_iterations": info["iterations"], "true_rel_residual": true_res,
-                       "per_rank_local_dofs": int(A.n), "halo_bytes_per_exchange": plan.bytes_per_exchange(),
-                       "collectives_per_iteration": ("fused into the kernels: halo = peer stores of the direction "
-                                                     "update, 2 all-reduces = peer stores + flags (tfem_dcg_solve)")
-                       if fused else "NCCL: 1 halo exchange (P2P send/recv) + 2 all-reduces (1 and 2 doubles)",
-                       "l2_policy": f"inputs larger than L2 (per-rank SELL matrix {8.5e-9 * pattern.nnz:.1f} GB vs 126 MB L2)",
-                       "setup_ms_pattern": setup_ms,
-                       "note": "Jacobi-PCG iterations grow with the cube edge (~N^(1/3)), so DOF/s per GPU "
-                               "falls with N even at perfect per-iteration scaling; per_iteration_ms is the "
-                               "kernel/communication scaling figure",
-                       "per_iteration_ms": ms / max(1, info["iterations"])},
-            "e2e": {"value": n_dofs_global / (ms_e2e / 1e3), "unit": unit, "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(io[0].item()), "d2h_bytes_per_step": int(io[1].item()),
-                    "call": "C-ABI ops on per-rank host buffers (H2D mesh + per-element E, nu + BCs -> tangent -> "
-                            "integrate -> assemble -> distributed PCG -> D2H owned u)"},
-            "gpu_launches": int(info["launches"] + 6),
-            "roofline": {"bound": "hbm", "kernel": "k_sell_spmv (per rank)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms, "traffic": None},
-            "cpu_baseline": None, "clocks": clocks,
-        }
-        print(json.dumps(line))
-    if cg is not None:
-        cg.close()
-    _barrier()
-    if multi:
-        dist.destroy_process_group()

@@ -88,6 +88,10 @@ class Material:
 
     n_state: int = 0
     is_vectorized: bool = False
+    # False for a material whose algorithmic tangent is not major-symmetric (non-associated plasticity, damage with
+    # a secant / consistent mix ...): the assembled K is then tagged non-symmetric, so the adjoint solves with a real
+    # transpose (reference sparse.py:671 `K.T`) and CG / AMG (SPD methods) are not auto-selected for it
+    symmetric_tangent: bool = True
 
     def __init__(self):
         self.n_state = 0
@@ -106,7 +110,15 @@ class Material:
         return out
 
     def to(self, device) -> "Material":
-        """Copy with every tensor attribute on `device` (the models keep their material on the GPU)."""
+        """The material with every tensor attribute on `device` (the models keep their material on the GPU): the
+        object itself when nothing has to move — like the reference, which keeps the user's object when it is already
+        vectorized (materials/base.py:43-47), so re-assigning `material.C = ...` still reaches the model — else a
+        shallow copy."""
+        dev = torch.device(device)
+        if dev.type == "cuda" and dev.index is None and torch.cuda.is_available():
+            dev = torch.device("cuda", torch.cuda.current_device())
+        if all(v.device == dev for v in vars(self).values() if isinstance(v, Tensor)):
+            return self
         out = copy.copy(self)
         for name, val in list(vars(out).items()):
             if isinstance(val, Tensor):
