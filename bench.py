@@ -211,7 +211,7 @@ def run_ours(args):
     import torchfem_b200 as T
     from torchfem_b200 import csr
 
-    if world > 1 or args.config == "C":
+    if world > 1 or args.config == "C" or args.dist_path:
         return run_multi_gpu(args)
 
     E = args.edge
@@ -639,7 +639,7 @@ def run_multi_gpu(args):
     # solve's stream (tfem_comm_set_trace time_spmv): mean of the 32 launches of the second batch; max over ranks
     spmv_ms, trace_summary = None, None
     if fused:
-        n_tr = 64 if args.trace else 0
+        n_tr = 256 if args.trace else 0
         tr = cg.comm.set_trace(n_tr, first_iteration=64, time_spmv=True)
         _, info_t = solve(A, rhs, M, rtol)
         cg.comm.set_trace(0)
@@ -741,6 +741,11 @@ def summarize_trace(tr, rank):
         "direction_stream_us": med(tr[:, 9] - tr[:, 7]),
         "gap_direction_to_next_spmv_us": med(tr[1:, 0] - tr[:-1, 9]),
         "iteration_us": med(tr[1:, 0] - tr[:-1, 0]),
+        # the host polls the convergence flag every 32 iterations: the gaps there are the outliers of the distribution
+        "iteration_us_mean": float(np.mean(tr[1:, 0] - tr[:-1, 0])) / 1e3,
+        "iteration_us_max": float(np.max(tr[1:, 0] - tr[:-1, 0])) / 1e3,
+        "gap_direction_to_next_spmv_us_max": float(np.max(tr[1:, 0] - tr[:-1, 9])) / 1e3,
+        "gaps_over_20us": int(np.sum((tr[1:, 0] - tr[:-1, 9]) > 20e3)),
     }
 
 
@@ -762,8 +767,10 @@ def bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, 
     own = slice(row_lo, row_lo + n_owned)
     state = {}
 
+    node_plan = D.build_halo_plan(mesh, ranges, dist.get_rank() if dist.is_initialized() else 0, 1)
+
     def setup():
-        state["H"] = damg.DistributedAMG(A, pattern, mesh, plan, ranges)
+        state["H"] = damg.DistributedAMG(A, mesh.lo, mesh.n_owned, mesh.global_nodes, node_plan)
 
     def run(tol):
         xa, st = state["H"].solve(rhs, rtol=tol)
@@ -772,6 +779,8 @@ def bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, 
     setup()
     run(args.rtol)                   # first call grows pools
     state["H"].close()
+    state.pop("H")
+    torch.cuda.synchronize()
     setup_ms = timed_max(setup, 1)
     solve_ms = timed_max(lambda: run(args.rtol), 1)
     st, xa = state["st"], state["x"]
@@ -812,6 +821,8 @@ def main():
     ap.add_argument("--rtol", type=float, default=RTOL, help="N>1 / config C only: relative residual of the PCG "
                     "(the metric's value is 1e-8; other values are for the parity legs)")
     ap.add_argument("--trace", action="store_true", help="N>1: in-kernel %%globaltimer profile of the cross-GPU waits")
+    ap.add_argument("--dist-path", action="store_true", help="run the N>1 code path (slab + tfem_dcg_solve) even at N=1: "
+                    "the single-rank reference point of the wait trace")
     ap.add_argument("--probe", action="store_true", help="N>1: add the partition-independent solution fingerprint")
     args = ap.parse_args()
     if args.edge is None:

@@ -385,6 +385,12 @@ int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr_dev, const int32_t*
 int tfem_amg_aggregate(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, int distance,
                        int8_t* state_work_dev, uint8_t* flag_work_dev, int32_t* index_work_dev, int32_t* agg_dev,
                        int64_t* n_agg_host, int32_t* rounds_host, void* stream);
+/* The same on the subgraph of the nodes with exclude_dev[i] == 0 (uint8 [nb], NULL = none): excluded nodes (the halo
+ * nodes of a partitioned mesh) are never roots and join nothing; their agg entries are undefined. */
+int tfem_amg_aggregate_masked(int64_t nb, const int64_t* bptr_dev, const int32_t* bcol_dev, int distance,
+                              const uint8_t* exclude_dev, int8_t* state_work_dev, uint8_t* flag_work_dev,
+                              int32_t* index_work_dev, int32_t* agg_dev, int64_t* n_agg_host, int32_t* rounds_host,
+                              void* stream);
 
 /* Smoothed prolongator P = (I - omega D^-1 A) T, T[i, agg(i)] = diag(1 - iso_i). count: pptr_dev int64 [nb+1] out
  * (offsets); fill: pcol_dev int32 [pptr[nb]] (sorted per row), pvals_dev double [d*d*pptr[nb]]; max_row = longest
@@ -396,6 +402,17 @@ int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr_dev, const 
                               const double* vals_dev, const int32_t* agg_dev, const double* dinv_dev,
                               const uint8_t* iso_dev, double omega, const int64_t* pptr_dev, int32_t* pcol_dev,
                               double* pvals_dev, int max_row, void* stream);
+
+/* The same for the block rows [row0, row0 + n_rows) only (the rows a rank owns): agg / dinv / iso are indexed like the
+ * operator's rows and columns (halo columns included; agg values are arbitrary ints, e.g. GLOBAL aggregate numbers),
+ * pptr [n_rows+1] / pcol / pvals are numbered from 0. */
+int tfem_amg_prolongator_count_rows(int d, int64_t row0, int64_t n_rows, const int64_t* bptr_dev,
+                                    const int32_t* bcol_dev, const int32_t* agg_dev, int64_t* pptr_dev, void* stream);
+int tfem_amg_prolongator_fill_rows(int d, int64_t row0, int64_t n_rows, const int64_t* bptr_dev,
+                                   const int32_t* bcol_dev, const double* vals_dev, const int32_t* agg_dev,
+                                   const double* dinv_dev, const uint8_t* iso_dev, double omega,
+                                   const int64_t* pptr_dev, int32_t* pcol_dev, double* pvals_dev, int max_row,
+                                   void* stream);
 
 /* Block transpose. structure: tptr int64 [n_cols+1], tcol int32 [nblk] sorted per row, tsrc int32 [nblk] = index of
  * the source block; values: tvals = transposed blocks gathered through tsrc (a values-only refresh repeats only this). */
@@ -467,6 +484,46 @@ int tfem_amg_vcycle(const tfem_amg_level_t* levels_host, int n_levels, const dou
 int tfem_amg_pcg_solve(const tfem_amg_level_t* levels_host, int n_levels, const double* coarse_inv_dev,
                        const double* b_dev, const double* x0_dev, double rtol, double atol, int64_t maxiter,
                        double* x_dev, double* work_dev, double* info_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Distributed AMG-PCG (SURVEY §8(f)-3 x §8(e)): the hierarchy of tfem_amg_* partitioned by rows over the ranks of a
+ * tfem_comm. Aggregates are local to a rank, the prolongator smoothing and the Galerkin products are the global ones
+ * (the host exchanges halo rows of P and A P at setup, torch-fem_b200/damg.py), levels below a size limit are gathered
+ * and continued redundantly on every rank (`tail`, an ordinary tfem_amg_level_t hierarchy over the GLOBAL numbering of
+ * its finest level). All exchange steps of the cycle run over peer memory inside this call: halo entries are stored
+ * straight into the neighbours' copies of the vectors (which therefore live in the communicator's symmetric heap),
+ * dot products are LL-protocol all-reduces; no NCCL call, no host work besides the convergence poll.
+ *
+ * Level l (distributed): A = square operator over this rank's LOCAL numbering of the level ([halo | owned | halo];
+ * only the owned rows [own_lo, own_hi) are computed and written), P: rows = local numbering of level l, columns =
+ * index space of level l+1 (local numbering of the next distributed level, or the global numbering of the tail);
+ * R = rows of P^T for the owned coarse rows [c_own_lo, c_own_hi) of that index space, columns = local numbering of
+ * level l (halo columns included: the residual's halo is exchanged before the restriction). lv.x and lv.t MUST be
+ * vectors of the communicator's heap at the same offset on every rank; sends / recv_peers: halo plan of the level's
+ * vectors in scalar indices (as tfem_dcg_solve).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct tfem_damg_level {
+  tfem_amg_level_t lv;
+  int64_t own_lo, own_hi;
+  int64_t c_own_lo, c_own_hi;
+  int32_t n_sends;
+  const tfem_halo_send_t* sends;
+  int32_t n_recv;
+  const int32_t* recv_peers;
+} tfem_damg_level_t;
+
+/* CG on the distributed level-0 operator preconditioned with the distributed V(1,1) cycle. b, x: local-length device
+ * vectors of level 0 (owned entries meaningful), zero initial guess. p_heap: heap vector of level-0 length (search
+ * direction, exchanged every iteration). tail_b_heap: heap vector [tail_n] — the gathered right-hand side of the tail
+ * (every rank stores its owned segment [c_own_lo, c_own_hi) of the last distributed level into every rank's copy);
+ * tail_x: device vector [tail_n]. tail_levels / n_tail / tail_coarse_inv as tfem_amg_vcycle (the tail's finest level
+ * may be block CSR). work_dev: double [tfem_amg_work_doubles(n_local of level 0)]. Collective; maxiter must be equal on
+ * all ranks. info_host as tfem_krylov_solve. */
+int tfem_damg_pcg_solve(void* comm, const tfem_damg_level_t* levels_host, int n_levels,
+                        const tfem_amg_level_t* tail_levels_host, int n_tail, const double* tail_coarse_inv_dev,
+                        int64_t tail_n, double* tail_b_heap, double* tail_x_dev, const double* b_dev, double* x_dev,
+                        double* p_heap, double* work_dev, double rtol, double atol, int64_t maxiter, double timeout_s,
+                        double* info_host, void* stream);
 
 /* K7 — adjoint matrix gradient on the pattern: g[p] = -lambda[row(p)] * x[col(p)]
  * (sparse.py:212-216 `val = -gradb[row] * x[col]`). */

@@ -72,6 +72,13 @@ class HaloSendStruct(ctypes.Structure):
                 ("src_start", c_int64), ("dst_start", c_int64)]
 
 
+class DamgLevelStruct(ctypes.Structure):
+    """`tfem_damg_level_t` of include/tfem_b200.h."""
+    _fields_ = [("lv", AmgLevelStruct), ("own_lo", c_int64), ("own_hi", c_int64), ("c_own_lo", c_int64),
+                ("c_own_hi", c_int64), ("n_sends", ctypes.c_int32), ("sends", c_void_p), ("n_recv", ctypes.c_int32),
+                ("recv_peers", c_void_p)]
+
+
 _SIGNATURES = {
     "tfem_version": (c_int, []),
     "tfem_get_error_string": (c_int, [c_int, c_char_p, c_int]),
@@ -114,6 +121,13 @@ _SIGNATURES = {
                              c_void_p]),
     "tfem_amg_aggregate": (c_int, [c_int64, c_void_p, c_void_p, c_int] + [c_void_p] * 4
                            + [ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_int32), c_void_p]),
+    "tfem_amg_aggregate_masked": (c_int, [c_int64, c_void_p, c_void_p, c_int] + [c_void_p] * 5
+                                  + [ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_int32), c_void_p]),
+    "tfem_amg_prolongator_count_rows": (c_int, [c_int, c_int64, c_int64] + [c_void_p] * 5),
+    "tfem_amg_prolongator_fill_rows": (c_int, [c_int, c_int64, c_int64] + [c_void_p] * 6 + [c_double] + [c_void_p] * 3
+                                       + [c_int, c_void_p]),
+    "tfem_damg_pcg_solve": (c_int, [c_void_p, ctypes.POINTER(DamgLevelStruct), c_int, _AMG_P, c_int, c_void_p, c_int64]
+                            + [c_void_p] * 6 + [c_double, c_double, c_int64, c_double, c_void_p, c_void_p]),
     "tfem_amg_prolongator_count": (c_int, [c_int, c_int64] + [c_void_p] * 5),
     "tfem_amg_prolongator_fill": (c_int, [c_int, c_int64] + [c_void_p] * 6 + [c_double] + [c_void_p] * 3
                                   + [c_int, c_void_p]),

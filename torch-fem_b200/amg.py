@@ -202,6 +202,24 @@ class AMGPreconditioner:
         self._timing = None
         self._setup(A, symbolic=True)
 
+    @classmethod
+    def from_operator(cls, op: BlockOperator, max_coarse: int = MAX_COARSE_DOFS, max_levels: int = MAX_LEVELS,
+                      aggregation: str = "auto") -> "AMGPreconditioner":
+        """Hierarchy on a block operator that is itself a coarse operator (the gathered tail of the distributed
+        hierarchy, damg.py): zero diagonals are repaired and the layout of the cycle is chosen for level 0 too."""
+        self = cls.__new__(cls)
+        self.max_coarse, self.max_levels = int(max_coarse), min(int(max_levels), 16)
+        self.power_its, self.rho_safety = POWER_ITS, RHO_SAFETY
+        self.aggregation = aggregation
+        self.n = op.n_rows
+        self.shape = (self.n, self.n)
+        self.device = op.vals.device
+        self.levels = []
+        self._work = None
+        self._timing = None
+        self._setup(None, symbolic=True, op0=op)
+        return self
+
     # ------------------------------------------------------------------------------------------ setup
     def _aggregate(self, lv) -> bool:
         """K12 + the pattern of P and R for level `lv`; False if the coarsening stalled."""
@@ -237,16 +255,21 @@ class AMGPreconditioner:
         self._timing[name] = self._timing.get(name, 0.0) + (now - self._t_last) * 1e3
         self._t_last = now
 
-    def _setup(self, A: CSRMatrix, symbolic: bool) -> None:
+    def _setup(self, A: CSRMatrix | None, symbolic: bool, op0: BlockOperator | None = None) -> None:
         dev, st = self.device, L.stream()
         self._timing = {} if os.environ.get("TFEM_AMG_TIMING") else None
         if self._timing is not None:
             torch.cuda.synchronize()
             self._t_last = time.perf_counter()
-        self._pattern_key = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n)
-        self._values_key = (A.values_.data_ptr(), A.values_._version)
-        self._A = A   # keeps the level-0 buffers alive
-        op = _level0_operator(A)
+        if op0 is None:
+            self._pattern_key = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n)
+            self._values_key = (A.values_.data_ptr(), A.values_._version)
+            self._A = A   # keeps the level-0 buffers alive
+            op = _level0_operator(A)
+        else:
+            self._pattern_key = self._values_key = self._A = None
+            op = op0
+        coarse0 = op0 is not None
         if symbolic:
             self.levels = []
         li = 0
@@ -262,9 +285,9 @@ class AMGPreconditioner:
                 if li == 0:
                     lv.op = op
             op, d, nb = lv.op, lv.d, lv.op.nbr
-            L.check(L.lib.tfem_amg_row_info(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals), 1 if li > 0 else 0,
-                                            L.ptr(lv.dinv), L.ptr(lv.iso), st))
-            if li > 0:
+            L.check(L.lib.tfem_amg_row_info(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals),
+                                            1 if (li > 0 or coarse0) else 0, L.ptr(lv.dinv), L.ptr(lv.iso), st))
+            if li > 0 or coarse0:
                 op.prepare()                                   # after the zero-diagonal repair
             self._tick("row_info+layout")
             if symbolic:

@@ -24,7 +24,10 @@
 
 #include <cub/device/device_scan.cuh>
 
+#include <string.h>
+
 #include "sell.cuh"
+#include "peer.cuh"
 
 namespace tfem {
 namespace {
@@ -150,6 +153,12 @@ __global__ void k_mis_apply(int64_t nb, const int64_t* __restrict__ bptr, const 
   atomicAdd(n_undecided, 1);
 }
 
+// nodes a rank does not own (halo nodes of a partitioned mesh) take no part in the aggregation: state 3
+__global__ void k_mis_exclude(int64_t nb, const uint8_t* __restrict__ exclude, int8_t* __restrict__ state) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < nb && exclude[i]) state[i] = 3;
+}
+
 __global__ void k_mis_flags(int64_t nb, const int8_t* __restrict__ state, int32_t* __restrict__ flag) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < nb) flag[i] = state[i] == 1 ? 1 : 0;
@@ -257,15 +266,17 @@ __global__ void __launch_bounds__(128)
                   const double* __restrict__ vals, const int32_t* __restrict__ agg,
                   const double* __restrict__ dinv, const uint8_t* __restrict__ iso, double omega,
                   int64_t* __restrict__ pcount, const int64_t* __restrict__ pptr, int32_t* __restrict__ pcol,
-                  double* __restrict__ pvals, int* err, int stage_cap) {
+                  double* __restrict__ pvals, int* err, int stage_cap, int64_t row0) {
   __shared__ int s_key[4][kRowCap];
   __shared__ int s_ukey[4][FILL ? kAggCap : 1];
   __shared__ short s_rank[4][kRowCap];
   __shared__ unsigned char s_first[4][kRowCap];
   __shared__ int s_start[4][FILL ? kAggCap : 1];   // FILL: m < kAggCap distinct aggregates per row (checked below)
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t I = blockIdx.x * 4ll + w;
-  if (I >= nb) return;
+  // rows [row0, row0 + nb) of the operator; the outputs (pcount / pptr rows) are numbered from 0
+  const int64_t Io = blockIdx.x * 4ll + w;
+  if (Io >= nb) return;
+  const int64_t I = row0 + Io;
   const int64_t b0 = bptr[I];
   const int L = (int)(bptr[I + 1] - b0);
   if (L > kRowCap) {
@@ -289,7 +300,7 @@ __global__ void __launch_bounds__(128)
   }
   const int m = warp_sum_int(firsts);
   if (!FILL) {
-    if (lane == 0) pcount[I] = m;
+    if (lane == 0) pcount[Io] = m;
     return;
   }
   if (m > kAggCap - 1) {
@@ -305,7 +316,7 @@ __global__ void __launch_bounds__(128)
     if (s_first[w][e]) s_ukey[w][r] = k;
   }
   __syncwarp();
-  const int64_t p0 = pptr[I];
+  const int64_t p0 = pptr[Io];
   for (int r = lane; r < m; r += 32) pcol[p0 + r] = s_ukey[w][r];
   // entries grouped by aggregate, adjacency order kept inside a group: lane r collects the entries of rank r
   // (s_key is free now: it becomes the permutation, s_first/s_rank stay), group r = perm[start[r] .. start[r+1])
@@ -646,9 +657,10 @@ __global__ void __launch_bounds__(kSellWarps * 32, MINB)
   __shared__ double s_red[kSellWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double dot = 0.0;
-  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices; t += (int64_t)gridDim.x * kSellWarps) {
+  const int64_t t_hi = A.slice_hi < 0 ? A.n_slices : A.slice_hi;
+  for (int64_t t = A.slice_lo + (int64_t)blockIdx.x * kSellWarps + warp; t < t_hi; t += (int64_t)gridDim.x * kSellWarps) {
     const int64_t row = t * 32 + lane;
-    const bool live = row < A.n;
+    const bool live = row < A.n && row >= A.dot_lo && row < A.dot_hi;
     double xr = 0.0, br = 0.0, dr = 0.0;
     if (live) {
       if (MODE == M_JAC || (MODE == M_AX && DOT)) xr = __ldg(x + row);
@@ -681,7 +693,8 @@ int launch_amg_spmv_t(const Sell& A, const double* x, double* y, const double* b
   // 8 CTAs per SM (32 registers; the epilogue-heavy variants spill ~80 bytes outside the streaming loop) beat 6 CTAs
   // with 40 registers: 5.92 -> 5.55 ms per AMG-PCG iteration at config B. TFEM_AMG_OCC6=1 selects the latter.
   static const bool occ6 = getenv("TFEM_AMG_OCC6") && atoi(getenv("TFEM_AMG_OCC6")) != 0;
-  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
+  const int64_t n_sl = (A.slice_hi < 0 ? A.n_slices : A.slice_hi) - A.slice_lo;
+  const int64_t want = n_sl > 0 ? (n_sl + kSellWarps - 1) / kSellWarps : 1;
   if (occ6) {
     if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT, 6>, kSellWarps * 32);
     k_amg_spmv<DPN, MODE, DOT, 6><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
@@ -712,6 +725,7 @@ struct Bcsr {
   const int32_t* bcol = nullptr;
   const double* vals = nullptr;
   int d = 0;
+  int64_t row_lo = 0, row_hi = -1;  // block rows computed and written (-1: all); see Sell::slice_lo
 };
 
 template <int D, int MODE, int TPR>
@@ -722,9 +736,10 @@ __global__ void __launch_bounds__(256)
   __shared__ double s_part[D][8];
   const int g = threadIdx.x / TPR, l = threadIdx.x % TPR;
   // the loop bound is uniform over the CTA (shuffles / barriers inside); groups past the end idle with m = 0
-  for (int64_t base = blockIdx.x * (int64_t)RPC; base < A.nbr; base += (int64_t)gridDim.x * RPC) {
+  const int64_t I_hi = A.row_hi < 0 ? A.nbr : A.row_hi;
+  for (int64_t base = A.row_lo + blockIdx.x * (int64_t)RPC; base < I_hi; base += (int64_t)gridDim.x * RPC) {
     const int64_t I = base + g;
-    const bool active = I < A.nbr;
+    const bool active = I < I_hi;
     const int64_t b0 = active ? A.bptr[I] : 0;
     const int m = active ? (int)(A.bptr[I + 1] - b0) : 0;
     const double* v = A.vals + D * D * b0;
@@ -781,13 +796,15 @@ int launch_bcsr_d(const Bcsr& A, const double* x, double* y, const double* b, co
                   cudaStream_t st) {
   const double avg = (double)A.nblk / (double)(A.nbr > 0 ? A.nbr : 1);
   const int64_t cap = (int64_t)num_sms() * 8;
-  if (avg > 1024.0 || A.nbr < 2048) {
-    k_bcsr_spmv<D, MODE, 256><<<(unsigned)(A.nbr < cap ? A.nbr : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
+  int64_t rows = (A.row_hi < 0 ? A.nbr : A.row_hi) - A.row_lo;
+  if (rows < 1) rows = 1;
+  if (avg > 1024.0 || rows < 2048) {
+    k_bcsr_spmv<D, MODE, 256><<<(unsigned)(rows < cap ? rows : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
   } else if (avg > 16.0) {
-    const int64_t want = (A.nbr + 7) / 8;
+    const int64_t want = (rows + 7) / 8;
     k_bcsr_spmv<D, MODE, 32><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
   } else {
-    const int64_t want = (A.nbr + 31) / 32;
+    const int64_t want = (rows + 31) / 32;
     k_bcsr_spmv<D, MODE, 8><<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(A, x, y, b, dinv, omega);
   }
   TFEM_LAUNCH_CHECK();
@@ -840,10 +857,29 @@ __global__ void k_dense_mv(int n, const double* __restrict__ Minv, const double*
 // ---- AMG-PCG scalars (indices into the device scalar block)
 enum { P_RHO = 0, P_RHO_NEW, P_PQ, P_RR, P_TOL, P_BNRM, P_DONE, P_ITERS, P_COUNT = 16 };
 
+__device__ __forceinline__ void pcg_scalars_init(double* sc, double rr, double bb, double rtol, double atol) {
+  const double bnrm = sqrt(bb);
+  const double tol = fmax(atol, rtol * bnrm);
+  sc[P_RR] = rr;
+  sc[P_BNRM] = bnrm;
+  sc[P_TOL] = tol;
+  sc[P_ITERS] = 0.0;
+  sc[P_DONE] = (bnrm == 0.0 || sqrt(rr) < tol) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ void pcg_scalars_update(double* sc, double rr) {
+  sc[P_RR] = rr;
+  sc[P_ITERS] += 1.0;
+  // breakdown = a non-finite residual only, like scipy's cg and the Jacobi kernels: Newton tangents of a state that
+  // is not yet in equilibrium can be slightly indefinite (p.q < 0 in some iteration) and CG still gets through
+  if (!isfinite(rr)) sc[P_DONE] = 2.0;
+  else if (sqrt(rr) < sc[P_TOL]) sc[P_DONE] = 1.0;
+}
+
 // r = b - q (q = A x0) or r = b ; rr, bb ; tolerance and the convergence test of the initial iterate
 __global__ void __launch_bounds__(kVecThreads)
     k_pcg_init(int64_t n, const double* __restrict__ b, const double* __restrict__ q_or_null, double* __restrict__ r,
-               double* sc, double rtol, double atol, double* partials, unsigned int* ticket) {
+               double* sc, double rtol, double atol, double* partials, unsigned int* ticket, double* red = nullptr) {
   __shared__ double s_red[kVecThreads / 32];
   double rr = 0.0, bb = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
@@ -857,20 +893,19 @@ __global__ void __launch_bounds__(kVecThreads)
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   mine[1] = block_sum<kVecThreads>(bb, s_red);
   if (publish_and_reduce<2>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    const double bnrm = sqrt(tot[1]);
-    const double tol = fmax(atol, rtol * bnrm);
-    sc[P_RR] = tot[0];
-    sc[P_BNRM] = bnrm;
-    sc[P_TOL] = tol;
-    sc[P_ITERS] = 0.0;
-    sc[P_DONE] = (bnrm == 0.0 || sqrt(tot[0]) < tol) ? 1.0 : 0.0;
+    if (red) {  // distributed: local sums only, k_allreduce applies pcg_scalars_init to the global ones
+      red[0] = tot[0];
+      red[1] = tot[1];
+    } else {
+      pcg_scalars_init(sc, tot[0], tot[1], rtol, atol);
+    }
   }
 }
 
 // alpha = rho / p.q ; x += alpha p ; r -= alpha q ; rr = r.r ; convergence test (scipy cg: ||r|| < tol)
 __global__ void __launch_bounds__(kVecThreads)
     k_pcg_update(int64_t n, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
-                 double* __restrict__ r, double* sc, double* partials, unsigned int* ticket) {
+                 double* __restrict__ r, double* sc, double* partials, unsigned int* ticket, double* red = nullptr) {
   __shared__ double s_red[kVecThreads / 32];
   const double pq = sc[P_PQ];
   const double alpha = sc[P_RHO] / pq;
@@ -884,12 +919,8 @@ __global__ void __launch_bounds__(kVecThreads)
   double mine[1], tot[1];
   mine[0] = block_sum<kVecThreads>(rr, s_red);
   if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) {
-    sc[P_RR] = tot[0];
-    sc[P_ITERS] += 1.0;
-    // breakdown = a non-finite residual only, like scipy's cg and the Jacobi kernels: Newton tangents of a state that
-    // is not yet in equilibrium can be slightly indefinite (p.q < 0 in some iteration) and CG still gets through
-    if (!isfinite(tot[0])) sc[P_DONE] = 2.0;
-    else if (sqrt(tot[0]) < sc[P_TOL]) sc[P_DONE] = 1.0;
+    if (red) red[0] = tot[0];
+    else pcg_scalars_update(sc, tot[0]);
   }
 }
 
@@ -945,7 +976,7 @@ int make_oper(const tfem_amg_operator_t* o, Oper* out) {
   return TFEM_OK;
 }
 
-int make_levels(const tfem_amg_level_t* lv, int n_levels, Level* out) {
+int make_levels(const tfem_amg_level_t* lv, int n_levels, Level* out, bool need_sell0 = true) {
   int rc;
   for (int l = 0; l < n_levels; ++l) {
     if ((rc = make_oper(&lv[l].A, &out[l].A)) != TFEM_OK) return rc;
@@ -956,7 +987,7 @@ int make_levels(const tfem_amg_level_t* lv, int n_levels, Level* out) {
     out[l].b = lv[l].b;
     out[l].t = lv[l].t;
   }
-  TFEM_REQUIRE(!out[0].A.bcsr, "amg: the finest level must be given in SELL-32 form");
+  TFEM_REQUIRE(!need_sell0 || !out[0].A.bcsr, "amg: the finest level must be given in SELL-32 form");
   for (int l = 0; l + 1 < n_levels; ++l) {
     if ((rc = make_oper(&lv[l].P, &out[l].P)) != TFEM_OK || (rc = make_oper(&lv[l].R, &out[l].R)) != TFEM_OK) return rc;
     TFEM_REQUIRE(lv[l].dinv && lv[l].x && lv[l].t, "amg level: null work vector");
@@ -1033,6 +1064,7 @@ using namespace tfem;
 extern "C" int tfem_amg_row_info(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol, double* vals,
                                  int fix_zero_diag, double* dinv, uint8_t* iso, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(bptr && bcol && vals && dinv && iso && nb > 0, "amg_row_info: bad arguments");
   TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
   const unsigned grid = grid_for(nb * 32, 256);
@@ -1048,6 +1080,7 @@ extern "C" int64_t tfem_amg_work_doubles(int64_t n_rows) { return 4 * pad32(n_ro
 extern "C" int tfem_amg_rho(const tfem_amg_operator_t* a, const double* dinv, int iterations, double* work,
                             double* rho_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(a && dinv && work && rho_host && iterations > 0, "amg_rho: bad arguments");
   Oper A;
   int rc = make_oper(a, &A);
@@ -1074,7 +1107,16 @@ extern "C" int tfem_amg_rho(const tfem_amg_operator_t* a, const double* dinv, in
 extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t* bcol, int distance,
                                   int8_t* state_work, uint8_t* flag_work, int32_t* index_work, int32_t* agg,
                                   int64_t* n_agg_host, int32_t* rounds_host, void* stream_) {
+  return tfem_amg_aggregate_masked(nb, bptr, bcol, distance, nullptr, state_work, flag_work, index_work, agg,
+                                   n_agg_host, rounds_host, stream_);
+}
+
+extern "C" int tfem_amg_aggregate_masked(int64_t nb, const int64_t* bptr, const int32_t* bcol, int distance,
+                                         const uint8_t* exclude, int8_t* state_work, uint8_t* flag_work,
+                                         int32_t* index_work, int32_t* agg, int64_t* n_agg_host,
+                                         int32_t* rounds_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(bptr && bcol && state_work && flag_work && index_work && agg && n_agg_host && nb > 0,
                "amg_aggregate: bad arguments");
   TFEM_REQUIRE(distance == 1 || distance == 2, "amg_aggregate: distance must be 1 or 2");
@@ -1097,6 +1139,7 @@ extern "C" int tfem_amg_aggregate(int64_t nb, const int64_t* bptr, const int32_t
   };
   TFEM_CUDA(cudaMemsetAsync(state_work, 0, nb, st));
   const unsigned grid = grid_for(nb, 256);
+  if (exclude) k_mis_exclude<<<grid, 256, 0, st>>>(nb, exclude, state_work);
   int rounds = 0, undecided = 1;
   while (undecided > 0) {
     if (rounds >= 200) {  // Luby rounds finish in O(log n) with overwhelming probability
@@ -1151,7 +1194,7 @@ template <bool FILL>
 static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol, const double* vals,
                               const int32_t* agg, const double* dinv, const uint8_t* iso, double omega,
                               int64_t* pcount, const int64_t* pptr, int32_t* pcol, double* pvals, int max_row,
-                              cudaStream_t st) {
+                              cudaStream_t st, int64_t row0 = 0) {
   int* err = nullptr;
   TFEM_CUDA(malloc_async(&err, sizeof(int), st));
   TFEM_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
@@ -1168,9 +1211,9 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
       attr_set[d] = true;
     }
   }
-  if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
-  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
-  else k_prolongator<1, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap);
+  if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap, row0);
+  else if (d == 2) k_prolongator<2, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap, row0);
+  else k_prolongator<1, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap, row0);
   TFEM_LAUNCH_CHECK();
   int h = 0;
   int rc = read_flag(err, &h, st);
@@ -1187,6 +1230,7 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
 extern "C" int tfem_amg_prolongator_count(int d, int64_t nb, const int64_t* bptr, const int32_t* bcol,
                                           const int32_t* agg, int64_t* pptr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(bptr && bcol && agg && pptr && nb > 0 && d >= 1 && d <= 3, "amg_prolongator_count: bad arguments");
   int rc = prolongator_launch<false>(d, nb, bptr, bcol, nullptr, agg, nullptr, nullptr, 0.0, pptr + 1, nullptr,
                                      nullptr, nullptr, 0, st);
@@ -1199,15 +1243,44 @@ extern "C" int tfem_amg_prolongator_fill(int d, int64_t nb, const int64_t* bptr,
                                          const uint8_t* iso, double omega, const int64_t* pptr, int32_t* pcol,
                                          double* pvals, int max_row, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(bptr && bcol && vals && agg && dinv && iso && pptr && pcol && pvals && nb > 0 && d >= 1 && d <= 3,
                "amg_prolongator_fill: bad arguments");
   return prolongator_launch<true>(d, nb, bptr, bcol, vals, agg, dinv, iso, omega, nullptr, pptr, pcol, pvals, max_row, st);
+}
+
+// The same for the rows [row0, row0 + n_rows) of an operator whose other rows belong to other ranks (distributed
+// hierarchy): `agg`, `dinv`, `iso` are indexed like the operator's rows / columns, pptr / pcol / pvals from 0.
+extern "C" int tfem_amg_prolongator_count_rows(int d, int64_t row0, int64_t n_rows, const int64_t* bptr,
+                                               const int32_t* bcol, const int32_t* agg, int64_t* pptr, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  TFEM_REQUIRE(bptr && bcol && agg && pptr && n_rows > 0 && row0 >= 0 && d >= 1 && d <= 3,
+               "amg_prolongator_count_rows: bad arguments");
+  int rc = prolongator_launch<false>(d, n_rows, bptr, bcol, nullptr, agg, nullptr, nullptr, 0.0, pptr + 1, nullptr,
+                                     nullptr, nullptr, 0, st, row0);
+  if (rc != TFEM_OK) return rc;
+  return scan_in_place(pptr, n_rows, st);
+}
+
+extern "C" int tfem_amg_prolongator_fill_rows(int d, int64_t row0, int64_t n_rows, const int64_t* bptr,
+                                              const int32_t* bcol, const double* vals, const int32_t* agg,
+                                              const double* dinv, const uint8_t* iso, double omega,
+                                              const int64_t* pptr, int32_t* pcol, double* pvals, int max_row,
+                                              void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  TFEM_REQUIRE(bptr && bcol && vals && agg && dinv && iso && pptr && pcol && pvals && n_rows > 0 && row0 >= 0 &&
+                   d >= 1 && d <= 3, "amg_prolongator_fill_rows: bad arguments");
+  return prolongator_launch<true>(d, n_rows, bptr, bcol, vals, agg, dinv, iso, omega, nullptr, pptr, pcol, pvals,
+                                  max_row, st, row0);
 }
 
 extern "C" int tfem_amg_transpose_structure(int64_t n_rows, int64_t n_cols, const int64_t* ptr, const int32_t* col,
                                             int64_t nblk, int64_t* tptr, int32_t* tcol, int32_t* tsrc,
                                             void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(ptr && col && tptr && tcol && tsrc && n_rows > 0 && n_cols > 0, "amg_transpose_structure: bad arguments");
   TFEM_REQUIRE(nblk < (int64_t)INT32_MAX, "amg_transpose_structure: too many blocks");
   TFEM_CUDA(cudaMemsetAsync(tptr, 0, (n_cols + 1) * sizeof(int64_t), st));
@@ -1232,6 +1305,7 @@ extern "C" int tfem_amg_transpose_values(int d, int64_t n_cols, const int64_t* p
                                          const int64_t* tptr, const int32_t* tcol, const int32_t* tsrc,
                                          double* tvals, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(ptr && vals && tptr && tcol && tsrc && tvals && n_cols > 0 && d >= 1 && d <= 3,
                "amg_transpose_values: bad arguments");
   const unsigned grid = grid_for(n_cols * 32, 256);
@@ -1282,6 +1356,7 @@ static int spgemm_sym_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
 extern "C" int tfem_amg_spgemm_count(int64_t nx, const int64_t* xptr, const int32_t* xcol, const int64_t* yptr,
                                      const int32_t* ycol, int64_t* cptr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(xptr && xcol && yptr && ycol && cptr && nx > 0, "amg_spgemm_count: bad arguments");
   int rc = spgemm_sym_launch<false>(nx, xptr, xcol, yptr, ycol, cptr + 1, nullptr, nullptr, st);
   if (rc != TFEM_OK) return rc;
@@ -1291,6 +1366,7 @@ extern "C" int tfem_amg_spgemm_count(int64_t nx, const int64_t* xptr, const int3
 extern "C" int tfem_amg_spgemm_fill(int64_t nx, const int64_t* xptr, const int32_t* xcol, const int64_t* yptr,
                                     const int32_t* ycol, const int64_t* cptr, int32_t* ccol, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(xptr && xcol && yptr && ycol && cptr && ccol && nx > 0, "amg_spgemm_fill: bad arguments");
   return spgemm_sym_launch<true>(nx, xptr, xcol, yptr, ycol, nullptr, cptr, ccol, st);
 }
@@ -1333,6 +1409,7 @@ extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, c
                                        const double* yvals, const int64_t* cptr, const int32_t* ccol, double* cvals,
                                        int max_row, int threads_per_row, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(xptr && xcol && xvals && yptr && ycol && yvals && cptr && ccol && cvals && nx > 0 && max_row > 0,
                "amg_spgemm_numeric: bad arguments");
   TFEM_REQUIRE(d >= 1 && d <= 3, "amg: 1, 2 or 3 DOFs per node");
@@ -1352,6 +1429,7 @@ extern "C" int tfem_amg_spgemm_numeric(int d, int64_t nx, const int64_t* xptr, c
 extern "C" int tfem_amg_vcycle(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv,
                                const double* r, double* z, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= TFEM_AMG_MAX_LEVELS && coarse_inv && r && z && r != z,
                "amg_vcycle: bad arguments");
   Level L[TFEM_AMG_MAX_LEVELS];
@@ -1365,6 +1443,7 @@ extern "C" int tfem_amg_pcg_solve(const tfem_amg_level_t* levels, int n_levels, 
                                   const double* b, const double* x0, double rtol, double atol, int64_t maxiter,
                                   double* x, double* work, double* info, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= TFEM_AMG_MAX_LEVELS && coarse_inv && b && x && work && info,
                "amg_pcg_solve: bad arguments");
   Level L[TFEM_AMG_MAX_LEVELS];
@@ -1417,6 +1496,312 @@ extern "C" int tfem_amg_pcg_solve(const tfem_amg_level_t* levels, int n_levels, 
   info[5] = (double)launches;
   info[6] = h[P_DONE];
   info[7] = 0.0;
+  if (h[P_DONE] == 2.0) {
+    set_last_error("breakdown", "non-finite residual or non-positive curvature (matrix or preconditioner not SPD?)");
+    return TFEM_ERR_BREAKDOWN;
+  }
+  if (h[P_DONE] != 1.0) {
+    set_last_error("not converged", "iteration limit reached");
+    return TFEM_ERR_NOT_CONVERGED;
+  }
+  return TFEM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Distributed AMG-PCG: the cycle above with its exchange steps over peer memory (peer.cuh).
+// ---------------------------------------------------------------------------------------------------
+namespace tfem {
+namespace {
+
+enum { AR_INIT = 0, AR_RHO, AR_PQ, AR_RR };
+
+// One CTA: publish this rank's local sums (LL protocol), wait for all ranks, sum in rank order, apply the scalar
+// recurrence the single-GPU kernels apply in their last CTA. Bit-identical on every rank.
+template <int K>
+__global__ void k_allreduce(Peers P, int set, unsigned long long epoch, const double* local, double* sc, int op,
+                            double rtol, double atol) {
+  __shared__ double s_out[4];
+  __shared__ int s_ok;
+  if (sc[P_DONE] == 4.0) return;
+  if (threadIdx.x < 32) {
+    double v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] = local[j];
+    ll_publish<K>(P, set, epoch, v);
+  }
+  double tot[K];
+  if (!ll_wait_sum<K>(P, set, epoch, tot, s_out, &s_ok)) {
+    if (threadIdx.x == 0) sc[P_DONE] = 4.0;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    if (op == AR_INIT) pcg_scalars_init(sc, tot[0], K > 1 ? tot[K - 1] : 0.0, rtol, atol);
+    else if (op == AR_RHO) sc[P_RHO_NEW] = tot[0];
+    else if (op == AR_PQ) sc[P_PQ] = tot[0];
+    else pcg_scalars_update(sc, tot[0]);
+  }
+}
+
+// halo exchange of a heap vector, step 1: store my entries into the neighbours' copies, release the channel flag
+__global__ void __launch_bounds__(kVecThreads)
+    k_halo_push(Peers P, Halo H, int64_t vec_off, int channel, unsigned long long epoch, unsigned int* halo_ticket,
+                const double* sc) {
+  if (sc[P_DONE] == 4.0) return;
+  const double* v = heap(P, P.rank) + vec_off;
+  halo_send_and_release(P, H, vec_off, channel, epoch, (int)gridDim.x, halo_ticket, [&](int64_t i) { return v[i]; });
+}
+
+// step 2: the stream waits until every neighbour has delivered
+__global__ void k_halo_wait(Peers P, Halo H, int channel, unsigned long long epoch, double* sc) {
+  if (sc[P_DONE] == 4.0) return;
+  if (threadIdx.x == 0 && !halo_wait_thread(P, H, channel, epoch)) sc[P_DONE] = 4.0;
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    k_zero(int64_t n, double* __restrict__ x) {
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) x[i] = 0.0;
+}
+
+struct DLevel {
+  Level L;
+  int64_t lo, hi, c_lo, c_hi;
+  Halo H;
+  int64_t x_off, t_off;  // heap offsets of L.x / L.t
+};
+
+struct DCtx {
+  Comm* c;
+  Peers P;
+  double* heap_base;
+  double* sc;
+  unsigned int* halo_ticket;
+  cudaStream_t st;
+  int64_t launches;
+};
+
+void restrict_rows(Oper& A, int64_t lo, int64_t hi) {  // scalar rows [lo, hi) are computed and written
+  if (A.bcsr) {
+    const int d = A.blk.d;
+    A.blk.row_lo = lo / d;
+    A.blk.row_hi = (hi + d - 1) / d;
+  } else {
+    A.sell.dot_lo = lo;
+    A.sell.dot_hi = hi;
+    A.sell.slice_lo = lo / 32;
+    A.sell.slice_hi = (hi + 31) / 32;
+  }
+}
+
+int halo_exchange(DCtx& X, const Halo& H, int64_t vec_off, int channel) {
+  if (X.c->world == 1) return TFEM_OK;
+  const unsigned long long ep = ++X.c->chan_epoch[channel];
+  if (H.n_send > 0 && H.send_total > 0) {
+    int g = halo_ctas(H.send_total, kVecThreads);
+    if (g > 64) g = 64;
+    k_halo_push<<<g, kVecThreads, 0, X.st>>>(X.P, H, vec_off, channel, ep, X.halo_ticket, X.sc);
+    ++X.launches;
+  }
+  if (H.n_recv > 0) {
+    k_halo_wait<<<1, 32, 0, X.st>>>(X.P, H, channel, ep, X.sc);
+    ++X.launches;
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <int K>
+int allreduce(DCtx& X, const double* local, int op, double rtol, double atol) {
+  const unsigned long long ep = ++X.c->epoch;
+  k_allreduce<K><<<1, 32, 0, X.st>>>(X.P, (int)(ep & 1ull), ep, local, X.sc, op, rtol, atol);
+  ++X.launches;
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+constexpr int CH_CG_P = 0, CH_GATHER = 15;
+inline int ch_x(int l) { return 1 + 3 * l; }
+inline int ch_t(int l) { return 2 + 3 * l; }
+inline int ch_xc(int l) { return 3 + 3 * l; }   // level l's result vector as the coarse input of level l-1
+
+// z = M r with the distributed levels D[0..nd) and the replicated tail T[0..nt). r, z: level-0 local vectors.
+int dvcycle(DCtx& X, DLevel* D, int nd, const Level* T, int nt, const double* tail_inv, const Halo& gatherH,
+            int64_t tail_b_off, double* tail_b, double* tail_x, const double* r, double* z, double* partials,
+            unsigned int* ticket, double* dot_out) {
+  int rc;
+  cudaStream_t st = X.st;
+  for (int l = 0; l < nd; ++l) {  // downward leg
+    DLevel& d = D[l];
+    const Level& v = d.L;
+    const int64_t n = d.hi - d.lo;
+    const double* b = l == 0 ? r : v.b;
+    k_jacobi_first<<<vec_grid(n), kVecThreads, 0, st>>>(n, v.omega, v.dinv + d.lo, b + d.lo, v.x + d.lo);
+    if ((rc = halo_exchange(X, d.H, d.x_off, ch_x(l)))) return rc;
+    if ((rc = apply_oper<M_RES>(v.A, v.x, v.t, b, nullptr, 0.0, st))) return rc;
+    if ((rc = halo_exchange(X, d.H, d.t_off, ch_t(l)))) return rc;
+    double* nb = l + 1 < nd ? D[l + 1].L.b : tail_b;
+    if ((rc = apply_oper<M_AX>(v.R, v.t, nb, nullptr, nullptr, 0.0, st))) return rc;
+    X.launches += 3;
+  }
+  // the tail: every rank stores its segment of the right-hand side into every rank's copy, then solves redundantly
+  if ((rc = halo_exchange(X, gatherH, tail_b_off, CH_GATHER))) return rc;
+  if ((rc = vcycle(T, nt, tail_inv, tail_b, tail_x, nullptr, nullptr, nullptr, &X.launches, st))) return rc;
+  for (int l = nd - 1; l >= 0; --l) {  // upward leg
+    DLevel& d = D[l];
+    const Level& v = d.L;
+    const double* b = l == 0 ? r : v.b;
+    const double* xc = tail_x;
+    if (l + 1 < nd) {
+      xc = D[l + 1].L.t;
+      if ((rc = halo_exchange(X, D[l + 1].H, D[l + 1].t_off, ch_xc(l + 1)))) return rc;
+    }
+    if ((rc = apply_oper<M_ADD>(v.P, xc, v.x, nullptr, nullptr, 0.0, st))) return rc;
+    if ((rc = halo_exchange(X, d.H, d.x_off, ch_x(l)))) return rc;
+    double* out = l == 0 ? z : v.t;
+    if (l == 0 && dot_out)
+      rc = launch_amg_spmv<M_JAC, true>(v.A.sell, v.x, out, b, v.dinv, v.omega, partials, ticket, dot_out, st);
+    else
+      rc = apply_oper<M_JAC>(v.A, v.x, out, b, v.dinv, v.omega, st);
+    if (rc) return rc;
+    X.launches += 2;
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+}  // namespace
+}  // namespace tfem
+
+extern "C" int tfem_damg_pcg_solve(void* comm, const tfem_damg_level_t* levels, int n_levels,
+                                   const tfem_amg_level_t* tail_levels, int n_tail, const double* tail_inv,
+                                   int64_t tail_n, double* tail_b_heap, double* tail_x, const double* b, double* x,
+                                   double* p_heap, double* work, double rtol, double atol, int64_t maxiter,
+                                   double timeout_s, double* info, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  Comm* c = static_cast<Comm*>(comm);
+  TFEM_REQUIRE(c && c->connected, "damg_pcg_solve: communicator missing or not connected");
+  TFEM_REQUIRE(!c->broken, "damg_pcg_solve: communicator is out of step after a failed solve; create a new one");
+  TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= 4 && tail_levels && n_tail >= 1 && n_tail <= TFEM_AMG_MAX_LEVELS &&
+                   tail_inv && tail_b_heap && tail_x && b && x && p_heap && work && info && tail_n > 0,
+               "damg_pcg_solve: bad arguments");
+  TFEM_REQUIRE(c->world - 1 <= kMaxNbr, "damg_pcg_solve: the coarse gather supports at most 9 ranks");
+  if (!(timeout_s > 0.0)) timeout_s = 20.0;
+  double* heap_base = reinterpret_cast<double*>(c->base[c->rank] + HEADER_BYTES);
+  auto in_heap = [&](const double* p, int64_t n) {
+    return p >= heap_base && p + n <= heap_base + c->heap_doubles;
+  };
+
+  DLevel D[4];
+  Level T[TFEM_AMG_MAX_LEVELS];
+  int rc;
+  for (int l = 0; l < n_levels; ++l) {
+    const tfem_damg_level_t& dl = levels[l];
+    Level& v = D[l].L;
+    if ((rc = make_oper(&dl.lv.A, &v.A)) || (rc = make_oper(&dl.lv.P, &v.P)) || (rc = make_oper(&dl.lv.R, &v.R))) return rc;
+    v.n = v.A.n;
+    v.dinv = dl.lv.dinv;
+    v.omega = dl.lv.omega;
+    v.x = dl.lv.x;
+    v.b = dl.lv.b;
+    v.t = dl.lv.t;
+    TFEM_REQUIRE(v.dinv && v.x && v.t && (l == 0 || v.b), "damg level: null vector");
+    TFEM_REQUIRE(in_heap(v.x, v.n) && in_heap(v.t, v.n), "damg level: x and t must live in the communicator's heap");
+    TFEM_REQUIRE(dl.own_lo >= 0 && dl.own_lo < dl.own_hi && dl.own_hi <= v.n, "damg level: bad owned range");
+    TFEM_REQUIRE(v.P.n == v.n, "damg level: P must have the level's local rows");
+    D[l].lo = dl.own_lo;
+    D[l].hi = dl.own_hi;
+    D[l].c_lo = dl.c_own_lo;
+    D[l].c_hi = dl.c_own_hi;
+    D[l].x_off = v.x - heap_base;
+    D[l].t_off = v.t - heap_base;
+    if ((rc = fill_halo(D[l].H, c, dl.n_sends, dl.sends, dl.n_recv, dl.recv_peers))) return rc;
+    restrict_rows(v.A, dl.own_lo, dl.own_hi);
+    restrict_rows(v.P, dl.own_lo, dl.own_hi);
+    restrict_rows(v.R, dl.c_own_lo, dl.c_own_hi);
+    if (l > 0) TFEM_REQUIRE(D[l - 1].L.R.n == v.n && D[l - 1].c_lo == dl.own_lo && D[l - 1].c_hi == dl.own_hi,
+                            "damg level: R of the finer level does not match this level");
+  }
+  TFEM_REQUIRE(!D[0].L.A.bcsr, "damg: the finest level must be given in SELL-32 form");
+  if ((rc = make_levels(tail_levels, n_tail, T, false))) return rc;
+  TFEM_REQUIRE(T[0].n == tail_n && D[n_levels - 1].L.R.n == tail_n, "damg: tail size mismatch");
+  TFEM_REQUIRE(in_heap(tail_b_heap, tail_n), "damg: the gathered right-hand side must live in the heap");
+  TFEM_REQUIRE(in_heap(p_heap, D[0].L.n), "damg: p must live in the heap");
+
+  // the gather of the tail's right-hand side as a halo plan: my segment goes to every other rank, same offsets
+  Halo G;
+  memset(&G, 0, sizeof(G));
+  const int64_t seg_lo = D[n_levels - 1].c_lo, seg_n = D[n_levels - 1].c_hi - D[n_levels - 1].c_lo;
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    const int s = G.n_send++;
+    G.send_peer[s] = r;
+    G.send_count[s] = seg_n;
+    G.src0[s] = seg_lo;
+    G.dst0[s] = seg_lo;
+    G.send_total += seg_n;
+    G.recv_peer[G.n_recv++] = r;
+  }
+
+  const Sell& A = D[0].L.A.sell;
+  const int64_t n = D[0].L.n, np = pad32(n), lo = D[0].lo, no = D[0].hi - D[0].lo;
+  if (maxiter <= 0) maxiter = 10 * n * c->world;
+  double *r = work, *q = work + 2 * np, *z = work + 3 * np, *sc = work + 4 * np, *p = p_heap;
+  double* partials = sc + P_COUNT;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partials + kMaxPartials);
+  double* loc = sc + 8;   // P_COUNT = 16 scalars: slots 8..11 carry the local sums handed to k_allreduce
+  TFEM_CUDA(cudaMemsetAsync(sc, 0, (P_COUNT + kMaxPartials + 32) * sizeof(double), st));
+  DCtx X;
+  X.c = c;
+  X.P = make_peers(c, timeout_s);
+  X.heap_base = heap_base;
+  X.sc = sc;
+  X.halo_ticket = ticket + 1;
+  X.st = st;
+  X.launches = 0;
+  const int vg = vec_grid(no);
+  int64_t spmvs = 0;
+
+  k_zero<<<vg, kVecThreads, 0, st>>>(no, x + lo);
+  k_pcg_init<<<vg, kVecThreads, 0, st>>>(no, b + lo, nullptr, r + lo, sc, rtol, atol, partials, ticket, loc);
+  TFEM_LAUNCH_CHECK();
+  if ((rc = allreduce<2>(X, loc, AR_INIT, rtol, atol))) return rc;
+  X.launches += 2;
+  double h[P_COUNT];
+  TFEM_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TFEM_CUDA(cudaStreamSynchronize(st));
+  int64_t it = 0;
+  const int64_t tail_b_off = tail_b_heap - heap_base, p_off = p_heap - heap_base;
+  while (h[P_DONE] == 0.0 && it < maxiter) {
+    if ((rc = dvcycle(X, D, n_levels, T, n_tail, tail_inv, G, tail_b_off, tail_b_heap, tail_x, r, z, partials, ticket,
+                      loc))) { c->broken = true; return rc; }
+    if ((rc = allreduce<1>(X, loc, AR_RHO, rtol, atol))) return rc;
+    k_pcg_direction<<<vg, kVecThreads, 0, st>>>(no, z + lo, p + lo, sc, it == 0 ? 1 : 0);
+    k_pcg_roll<<<1, 1, 0, st>>>(sc);
+    if ((rc = halo_exchange(X, D[0].H, p_off, CH_CG_P))) return rc;
+    if ((rc = launch_amg_spmv<M_AX, true>(A, p, q, nullptr, nullptr, 0.0, partials, ticket, loc, st))) return rc;
+    if ((rc = allreduce<1>(X, loc, AR_PQ, rtol, atol))) return rc;
+    k_pcg_update<<<vg, kVecThreads, 0, st>>>(no, p + lo, q + lo, x + lo, r + lo, sc, partials, ticket, loc);
+    TFEM_LAUNCH_CHECK();
+    if ((rc = allreduce<1>(X, loc, AR_RR, rtol, atol))) return rc;
+    X.launches += 4;
+    spmvs += 3;
+    ++it;
+    TFEM_CUDA(cudaMemcpyAsync(h, sc, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TFEM_CUDA(cudaStreamSynchronize(st));
+  }
+  info[0] = h[P_ITERS];
+  info[1] = sqrt(h[P_RR]);
+  info[2] = h[P_BNRM];
+  info[3] = h[P_DONE] == 1.0 ? 1.0 : 0.0;
+  info[4] = (double)spmvs;
+  info[5] = (double)X.launches;
+  info[6] = h[P_DONE];
+  info[7] = 0.0;
+  if (h[P_DONE] == 4.0) {
+    c->broken = true;
+    set_last_error("communication", "a peer did not deliver its halo / reduction within the timeout");
+    return TFEM_ERR_COMM;
+  }
   if (h[P_DONE] == 2.0) {
     set_last_error("breakdown", "non-finite residual or non-positive curvature (matrix or preconditioner not SPD?)");
     return TFEM_ERR_BREAKDOWN;

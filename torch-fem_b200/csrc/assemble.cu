@@ -145,6 +145,7 @@ extern "C" int tfem_assemble_bc(int64_t n_nod, int nn, int dpn, const int64_t* n
                                 const double* k, const uint8_t* is_con, const double* ubc, double* vals,
                                 double* lift, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(node_ptr && adj && indptr && src_ptr && src && k && vals, "assemble: null pointer");
   TFEM_REQUIRE(n_nod > 0 && nn > 0, "assemble: bad sizes");
   TFEM_REQUIRE(!lift || (is_con && ubc), "assemble: the Dirichlet lifting needs is_con and the prescribed values");

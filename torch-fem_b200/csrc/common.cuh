@@ -17,10 +17,12 @@ inline int check_cuda(cudaError_t e, const char* what) {
   return TFEM_ERR_CUDA;
 }
 
-#define TFEM_CUDA(call)                                  \
-  do {                                                   \
-    int _rc = ::tfem::check_cuda((call), #call);         \
-    if (_rc != TFEM_OK) return _rc;                      \
+#define TFEM_STR2(x) #x
+#define TFEM_STR(x) TFEM_STR2(x)
+#define TFEM_CUDA(call)                                                             \
+  do {                                                                              \
+    int _rc = ::tfem::check_cuda((call), #call " at " __FILE__ ":" TFEM_STR(__LINE__)); \
+    if (_rc != TFEM_OK) return _rc;                                                 \
   } while (0)
 
 #define TFEM_LAUNCH_CHECK(name) TFEM_CUDA((cudaGetLastError()))

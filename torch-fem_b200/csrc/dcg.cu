@@ -8,10 +8,10 @@
 //
 // Every rank's communication buffer holds two copies of the search direction p in its symmetric heap.
 // Per iteration `it` (epochs are monotone counters, never reset):
-//   k_dcg_spmv       q = A p over owned rows. Interior slices first; a warp that reaches the slices reading halo
-//                    entries waits (once) for the neighbours' halo flags of this iteration. Fused p.q; the last
-//                    CTA stores the local sum into slot [my rank] of LL set 0 on every rank (data + epoch in the
-//                    same 8-byte words: one NVLink store, no fence, no separate flag).
+//   k_sell_spmv      q = A p over the interior slices (rows that read no halo entry): the single-GPU kernel itself
+//   k_dcg_spmv_halo  the slices that read halo entries: waits (once per warp) for the neighbours' halo flags of this
+//                    iteration, fused p.q; the last CTA stores interior + halo sum into slot [my rank] of LL set 0
+//                    on every rank (data + epoch in the same 8-byte words: one NVLink store, no fence, no flag).
 //   k_dcg_update     one warp per CTA polls set 0 until all `world` slots carry this epoch, sums them in rank
 //                    order (bit-identical on every rank), alpha = rho / p.q; x += alpha p; r -= alpha q; r.r and
 //                    r.(D^-1 r); the last CTA publishes both sums to set 1 of every rank.
@@ -110,36 +110,28 @@ __global__ void k_dcg_scalars_init(double* sc, Peers P, unsigned long long ep_re
   }
 }
 
-// q = A p over the owned slices [ts_lo, ts_hi). One strided index space: the interior slices [ti_lo, ti_hi)
-// first, then the slices that read halo entries. A warp that reaches the second part waits (once) until every
-// neighbour's halo flag has reached ep_halo; by then the flags are normally long set, so the exchange is
-// hidden behind the interior rows. p.q over owned rows -> LL set 0 of every rank.
+// q = A p over the owned rows, in two kernels. The INTERIOR slices [ti_lo, ti_hi) — rows that reference no halo
+// entry — go through the very kernel of the single-GPU driver (k_sell_spmv<DPN, true> on a slice range, sell.cuh; its
+// fused p.q lands in sc[SC_PQ]): 98 % of the rows at config B, and no wait of any kind. The slices that read halo
+// entries follow in k_dcg_spmv_halo: by then the neighbours' halo flags of this iteration are long set (they were
+// released during the neighbours' direction kernels, a whole SpMV ago), so the exchange is hidden behind the interior
+// rows. Keeping the halo logic out of the streaming kernel matters: fused into one kernel it cost 80 bytes of spills
+// inside the slice loop and 3.5 % of the SpMV (1184 vs 1143 us at config B, profiles/r2_*_wait_trace*).
+// p.q = interior sum + halo sum (fixed order) -> LL set 0 of every rank.
 template <int DPN>
 __global__ void __launch_bounds__(kSellWarps * 32, 8)
-    k_dcg_spmv(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which, int64_t vec,
-               double* __restrict__ q, double* sc, double* partials, unsigned int* ticket, Peers P, Halo H,
-               long long it, unsigned long long ep_halo, unsigned long long ep_red) {
+    k_dcg_spmv_halo(Sell A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which, int64_t vec,
+                    double* __restrict__ q, double* sc, double* partials, unsigned int* ticket, Peers P, Halo H,
+                    long long it, unsigned long long ep_halo, unsigned long long ep_red) {
   __shared__ double s_red[kSellWarps];
   if (sc[SC_DONE] != 0.0) return;
-  if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(P, it, TR_SPMV_BEGIN);
   const double* __restrict__ p = p_buf(P, P.rank, which, vec);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * kSellWarps;
-  const int64_t n_int = ti_hi - ti_lo, n_low = ti_lo - ts_lo, n_all = ts_hi - ts_lo;
+  const int64_t n_low = ti_lo - ts_lo, n_halo = n_low + (ts_hi - ti_hi);
   double dot = 0.0;
   int64_t j = (int64_t)blockIdx.x * kSellWarps + warp;
-  for (; j < n_int; j += stride) {
-    const int64_t t = ti_lo + j;
-    const int64_t row = t * 32 + lane;
-    const bool mine = row >= A.dot_lo && row < A.dot_hi;
-    const double pr = mine ? __ldg(p + row) : 0.0;   // requested before the row is streamed (see krylov.cu)
-    const double acc = slice_row<DPN>(A, t, p, lane);
-    if (mine) {
-      q[row] = acc;
-      dot = fma(acc, pr, dot);
-    }
-  }
-  if (j < n_all) {
+  if (j < n_halo) {
     int ok = 1;
     if (lane == 0) {
       const unsigned long long t0 = global_ns();
@@ -148,14 +140,13 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
       trace_max(P, it, TR_SPMV_HALO_WAIT_MAX, global_ns() - t0);
     }
     ok = __shfl_sync(0xffffffffu, ok, 0);
-    for (; ok && j < n_all; j += stride) {
-      const int64_t jb = j - n_int;
-      const int64_t t = jb < n_low ? ts_lo + jb : ti_hi + (jb - n_low);
-      // halo entries were written by a peer while this kernel may already have been running: read them from
-      // L2 (ld.global.cg), never through an L1 sector an interior row could have pulled in earlier
+    for (; ok && j < n_halo; j += stride) {
+      const int64_t t = j < n_low ? ts_lo + j : ti_hi + (j - n_low);
+      // halo entries were written by a peer while the interior kernel was running: read them from L2 (ld.global.cg),
+      // never through an L1 sector an interior row could have pulled in earlier
       const int64_t row = t * 32 + lane;
       const bool mine = row >= A.dot_lo && row < A.dot_hi;
-      const double pr = mine ? __ldg(p + row) : 0.0;
+      const double pr = mine ? __ldcg(p + row) : 0.0;
       const double acc = slice_row<DPN, true>(A, t, p, lane);
       if (mine) {
         q[row] = acc;
@@ -166,7 +157,9 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
   const double bsum = block_sum<kSellWarps * 32>(dot, s_red);
   double mine[1] = {bsum}, tot[1];
   if (publish_and_reduce<1>(mine, partials, ticket, tot)) {
-    ll_publish<1>(P, 0, ep_red, tot);
+    double out[1];
+    out[0] = sc[SC_PQ] + tot[0];   // interior + halo, the same order on every run
+    ll_publish<1>(P, 0, ep_red, out);
     if (threadIdx.x == 0) trace_mark(P, it, TR_SPMV_LAST_CTA);
   }
 }
@@ -233,13 +226,17 @@ __global__ void __launch_bounds__(kVecThreads, 8)
   const double* __restrict__ p = p_buf(P, P.rank, which, vec);
   double* __restrict__ pn = p_buf(P, P.rank, which ^ 1, vec);
   if ((int)blockIdx.x < n_halo_ctas) {
+    // dedicated halo CTAs (no share of the streaming loop, so they do not lengthen the kernel): the exchange
+    // overlaps the update of p'. The neighbours need these entries only at the END of their next SpMV.
     const bool released = halo_send_and_release(P, H, (int64_t)(which ^ 1) * vec, CH_P, ep_halo, n_halo_ctas,
                                                 ticket + 1, [&](int64_t i) { return fma(beta, p[i], dinv[i] * r[i]); });
     if (released && threadIdx.x == 0) trace_mark(P, it, TR_DIR_HALO_RELEASED);
-  }
-  for (int64_t k = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; k < n; k += (int64_t)gridDim.x * kVecThreads) {
-    const int64_t i = o + k;
-    pn[i] = fma(beta, p[i], dinv[i] * r[i]);
+  } else {
+    const int64_t nb = (int64_t)gridDim.x - n_halo_ctas, b0 = (int64_t)blockIdx.x - n_halo_ctas;
+    for (int64_t k = b0 * kVecThreads + threadIdx.x; k < n; k += nb * kVecThreads) {
+      const int64_t i = o + k;
+      pn[i] = fma(beta, p[i], dinv[i] * r[i]);
+    }
   }
   if (last_cta(ticket) && threadIdx.x == 0) {
     sc[SC_RHO_PREV] = rho_prev;
@@ -272,26 +269,30 @@ __global__ void k_comm_barrier(double* sc, Peers P, unsigned long long ep) {
   }
 }
 
-// grids are cached per (instantiation, device): one process may drive several devices
-template <typename K>
-int cached_resident_ctas(K kernel, int threads) {
-  static int g[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
-  if (!g[dev]) g[dev] = resident_ctas(kernel, threads);
-  return g[dev];
+__global__ void k_dcg_trace_begin(Peers P, long long it, const double* sc) {
+  if (sc[SC_DONE] == 0.0) trace_mark(P, it, TR_SPMV_BEGIN);
 }
 
 template <int DPN>
-int launch_dcg_spmv(const Sell& A, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
-                    int64_t vec, double* q, double* sc, double* partials, unsigned int* ticket, const Peers& P,
-                    const Halo& H, long long it, unsigned long long ep_halo, unsigned long long ep_red,
-                    cudaStream_t st) {
-  const int g = cached_resident_ctas(k_dcg_spmv<DPN>, kSellWarps * 32);
-  const int64_t want = (ts_hi - ts_lo + kSellWarps - 1) / kSellWarps;
-  k_dcg_spmv<DPN><<<(int)(want < g ? (want > 0 ? want : 1) : g), kSellWarps * 32, 0, st>>>(
-      A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, q, sc, partials, ticket, P, H, it, ep_halo, ep_red);
+int launch_dcg_spmv(const Sell& A0, int64_t ts_lo, int64_t ts_hi, int64_t ti_lo, int64_t ti_hi, int which,
+                    int64_t vec, const double* p, double* q, double* sc, double* partials, unsigned int* ticket,
+                    const Peers& P, const Halo& H, long long it, unsigned long long ep_halo,
+                    unsigned long long ep_red, cudaStream_t st) {
+  if (P.trace && it >= P.trace_it0 && it < P.trace_it0 + P.trace_n) k_dcg_trace_begin<<<1, 1, 0, st>>>(P, it, sc);
+  Sell A = A0;
+  A.slice_lo = ti_lo;
+  A.slice_hi = ti_hi;
+  if (ti_hi > ti_lo) {
+    int rc = launch_sell_t<DPN, true>(A, p, q, sc, partials, ticket, sc + SC_PQ, st);
+    if (rc != TFEM_OK) return rc;
+  } else {
+    TFEM_CUDA(cudaMemsetAsync(sc + SC_PQ, 0, sizeof(double), st));
+  }
+  const int g = cached_resident_ctas(k_dcg_spmv_halo<DPN>, kSellWarps * 32);
+  const int64_t n_halo = (ti_lo - ts_lo) + (ts_hi - ti_hi);
+  const int64_t want = (n_halo + kSellWarps - 1) / kSellWarps;
+  k_dcg_spmv_halo<DPN><<<(int)(want < g ? (want > 0 ? want : 1) : g), kSellWarps * 32, 0, st>>>(
+      A0, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, q, sc, partials, ticket, P, H, it, ep_halo, ep_red);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -384,6 +385,7 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
                               double atol, int64_t maxiter, int check_every, double timeout_s,
                               double* info, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   Comm* c = static_cast<Comm*>(comm);
   TFEM_REQUIRE(c && c->connected, "dcg_solve: communicator missing or not connected");
   TFEM_REQUIRE(!c->broken, "dcg_solve: communicator is out of step after a failed solve; create a new one");
@@ -417,8 +419,16 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
 
   Work w = carve(work, n_local);
   const int vg = vec_grid(n_owned);
+  const double* pbuf[2] = {reinterpret_cast<const double*>(c->base[c->rank] + HEADER_BYTES),
+                           reinterpret_cast<const double*>(c->base[c->rank] + HEADER_BYTES) + vec};
+  // init kernel: the first CTAs also send p0's halo; direction kernel: `hd` DEDICATED halo CTAs out of the grid
   int hc = halo_ctas(H.send_total, kVecThreads);
   if (hc > vg) hc = vg;
+  int hd = H.send_total > 0 ? (int)((H.send_total + 8191) / 8192) : 0;   // <= 32 entries per thread
+  if (hd > 32) hd = 32;
+  if (H.send_total > 0 && hd < 1) hd = 1;
+  const int vgd = vg + (vg + hd <= vec_grid_cap() ? hd : 0);             // stay within one resident wave
+  if (vgd == vg && hd >= vg) hd = vg > 1 ? vg - 1 : 0;
   const unsigned long long E0 = c->epoch;
   TFEM_CUDA(cudaMemsetAsync(w.sc, 0, (SC_COUNT + kMaxPartials + 32) * sizeof(double), st));
   k_dcg_init<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, vec, b, dinv, w.r, x, w.partials, w.ticket, P, H, hc,
@@ -457,22 +467,22 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
         cudaEventRecord(ev[2 * n_ev], st);
       }
       if (A.dpn == 3)
-        rc = launch_dcg_spmv<3>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
+        rc = launch_dcg_spmv<3>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, pbuf[which], w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       else if (A.dpn == 2)
-        rc = launch_dcg_spmv<2>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
+        rc = launch_dcg_spmv<2>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, pbuf[which], w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       else
-        rc = launch_dcg_spmv<0>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
+        rc = launch_dcg_spmv<0>(A, ts_lo, ts_hi, ti_lo, ti_hi, which, vec, pbuf[which], w.q, w.sc, w.partials, w.ticket, P, H, it, e1, e1, st);
       if (rc != TFEM_OK) { c->broken = true; return rc; }
       if (tm) cudaEventRecord(ev[2 * n_ev++ + 1], st);
       k_dcg_update<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, vec, w.q, dinv, x, w.r, w.sc, w.partials,
                                               w.ticket, P, it, e1, e2);
-      k_dcg_direction<<<vg, kVecThreads, 0, st>>>(row_lo, n_owned, which, vec, w.r, dinv, w.sc, w.ticket, P, H, hc,
-                                                 it, e2, e2);
+      k_dcg_direction<<<vgd, kVecThreads, 0, st>>>(row_lo, n_owned, which, vec, w.r, dinv, w.sc, w.ticket, P, H, hd,
+                                                  it, e2, e2);
     }
     rc = check_cuda(cudaGetLastError(), "dcg launch");
     if (rc != TFEM_OK) { c->broken = true; return rc; }
     issued += batch;
-    launches += 3.0 * batch;
+    launches += 4.0 * batch;
   }
   for (int e = 0; e < 2 * n_ev; ++e) cudaEventDestroy(ev[e]);
   c->epoch = E0 + (unsigned long long)issued + 2;

@@ -257,6 +257,7 @@ extern "C" int tfem_integrate_k(int kind, int dim, int nn, int n_int, const doub
                                 int64_t n_elem, const double* tangent, int tangent_per_gp,
                                 const double* scale, double* k_out, int32_t* neg_jac, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(bref_host && w_host && nodes && elements && tangent && k_out && neg_jac,
                "integrate_k: null pointer");
   TFEM_REQUIRE(n_elem >= 0, "integrate_k: negative n_elem");

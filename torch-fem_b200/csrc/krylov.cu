@@ -129,37 +129,6 @@ __global__ void k_sell_fill(int64_t n, int64_t n_cols, int64_t n_slices, const i
   }
 }
 
-// y = A x, one warp per slice, persistent grid with the slices strided over it so that all SMs walk the same
-// band of the matrix (the gathered x window stays in L2). DPN = 0: scalar columns, 2/3: node-block columns.
-// DOT fuses x.y over the rows [dot_lo, dot_hi) (fixed-order reduction, last CTA writes *out_scalar).
-template <int DPN, bool DOT>
-__global__ void __launch_bounds__(kSellWarps * 32, 8)
-    k_sell_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
-                double* partials, unsigned int* ticket, double* out_scalar) {
-  __shared__ double s_red[kSellWarps];
-  if (DOT && sc[SC_DONE] != 0.0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double dot = 0.0;
-  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices;
-       t += (int64_t)gridDim.x * kSellWarps) {
-    const int64_t row = t * 32 + lane;
-    // x[row] for the fused dot is requested BEFORE the row is streamed: asked for afterwards it costs every
-    // warp one exposed memory latency per slice (64 us of a 1.2 ms launch at config B)
-    double xr = 0.0;
-    if (DOT && row < A.n && row >= A.dot_lo && row < A.dot_hi) xr = __ldg(x + row);
-    const double acc = slice_row<DPN>(A, t, x, lane);
-    if (row < A.n) {
-      y[row] = acc;
-      if (DOT) dot = fma(acc, xr, dot);
-    }
-  }
-  if (DOT) {
-    const double b = block_sum<kSellWarps * 32>(dot, s_red);
-    double mine[1] = {b}, tot[1];
-    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
-  }
-}
-
 __global__ void k_bsell_widths(int64_t n_slices, int dpn, int nps, const int64_t* __restrict__ slice_ptr,
                                int64_t* __restrict__ out) {
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -185,26 +154,6 @@ __global__ void k_bsell_fill(int64_t n_slices, int64_t n_nod, int dpn, int nps,
     const int cnt = (int)(node_ptr[node + 1] - nb);
     bcols[base + o] = cnt > 0 ? adj[nb + (kb < cnt ? kb : cnt - 1)] : (int32_t)node;
   }
-}
-
-template <int DPN, bool DOT>
-int launch_sell_t(const Sell& A, const double* x, double* y, const double* sc, double* partials,
-                  unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  static int g = 0;  // per instantiation
-  if (!g) g = resident_ctas(k_sell_spmv<DPN, DOT>, kSellWarps * 32);
-  const int64_t want = (A.n_slices + kSellWarps - 1) / kSellWarps;
-  k_sell_spmv<DPN, DOT><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket,
-                                                                                out_scalar);
-  TFEM_LAUNCH_CHECK();
-  return TFEM_OK;
-}
-
-template <bool DOT>
-int launch_sell(const Sell& A, const double* x, double* y, const double* sc, double* partials,
-                unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  if (A.dpn == 3) return launch_sell_t<3, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
-  if (A.dpn == 2) return launch_sell_t<2, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
-  return launch_sell_t<0, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
 }
 
 // The linear operator of a Krylov solve: the assembled matrix in SELL-32 form, or the matrix-free element
@@ -911,6 +860,7 @@ extern "C" int64_t tfem_spmv_num_chunks(int64_t nnz) {
 extern "C" int tfem_spmv_plan(int64_t n_rows, int64_t nnz, const int64_t* indptr, int32_t* chunk_rows,
                               void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && chunk_rows && n_rows > 0, "spmv_plan: bad arguments");
   TFEM_REQUIRE(n_rows < (int64_t)INT32_MAX, "spmv_plan: n_rows must be < 2^31");
   const int64_t nc = tfem_spmv_num_chunks(nnz);
@@ -923,6 +873,7 @@ extern "C" int tfem_spmv(int64_t n_rows, int64_t nnz, const int64_t* indptr, con
                          const double* vals, const int32_t* chunk_rows, const double* x, double* y,
                          void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && cols && vals && chunk_rows && x && y, "spmv: null pointer");
   TFEM_REQUIRE(aligned16(cols) && aligned16(vals), "spmv: indices/values must be 16-byte aligned");
   Csr A{n_rows, nnz, tfem_spmv_num_chunks(nnz), indptr, cols, vals, chunk_rows};
@@ -932,6 +883,7 @@ extern "C" int tfem_spmv(int64_t n_rows, int64_t nnz, const int64_t* indptr, con
 extern "C" int tfem_csr_diag_positions(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
                                        int64_t* pos, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && cols && pos && n_rows > 0, "diag_positions: bad arguments");
   k_diag_positions<<<grid_for(n_rows, 256), 256, 0, st>>>(n_rows, indptr, cols, pos);
   TFEM_LAUNCH_CHECK();
@@ -941,6 +893,7 @@ extern "C" int tfem_csr_diag_positions(int64_t n_rows, const int64_t* indptr, co
 extern "C" int tfem_jacobi_setup(int64_t n_rows, const double* vals, const int64_t* pos, double* dinv,
                                  void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(vals && pos && dinv && n_rows > 0, "jacobi_setup: bad arguments");
   k_jacobi<<<grid_for(n_rows, 256), 256, 0, st>>>(n_rows, vals, pos, dinv);
   TFEM_LAUNCH_CHECK();
@@ -950,6 +903,7 @@ extern "C" int tfem_jacobi_setup(int64_t n_rows, const double* vals, const int64
 extern "C" int tfem_adjoint_matrix_grad(int64_t n_rows, const int64_t* indptr, const int32_t* cols,
                                         const double* lam, const double* x, double* g, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && cols && lam && x && g && n_rows > 0, "adjoint_matrix_grad: bad arguments");
   k_adjoint_grad<<<grid_for(n_rows * 32, 256), 256, 0, st>>>(n_rows, indptr, cols, lam, x, g);
   TFEM_LAUNCH_CHECK();
@@ -960,6 +914,7 @@ extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
                                   const int32_t* cols, const double* vals, int64_t* t_indptr,
                                   int32_t* t_cols, double* t_vals, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && cols && vals && t_indptr && t_cols && t_vals, "transpose: null pointer");
   TFEM_CUDA(cudaMemsetAsync(t_indptr, 0, (n_cols + 1) * sizeof(int64_t), st));
   if (nnz == 0) return TFEM_OK;
@@ -983,6 +938,7 @@ extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
 extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_t* slice_ptr,
                                    void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0, "sell_slice_ptr: bad arguments");
   const int64_t ns = (n_rows + 31) / 32;
   TFEM_CUDA(cudaMemsetAsync(slice_ptr, 0, sizeof(int64_t), st));
@@ -1001,6 +957,7 @@ extern "C" int tfem_sell_fill_rect(int64_t n_rows, int64_t n_cols, const int64_t
                                    const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
                                    double* sell_vals, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0 && n_cols > 0, "sell_fill: bad arguments");
   TFEM_REQUIRE((!sell_cols || cols) && (!sell_vals || vals), "sell_fill: output without input");
   const int64_t ns = (n_rows + 31) / 32;
@@ -1019,6 +976,7 @@ extern "C" int tfem_sell_fill(int64_t n_rows, const int64_t* indptr, const int32
 extern "C" int tfem_bsell_slice_ptr(int64_t n_rows, int dpn, const int64_t* slice_ptr,
                                     int64_t* bslice_ptr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(slice_ptr && bslice_ptr && n_rows > 0 && (dpn == 2 || dpn == 3), "bsell_slice_ptr: bad arguments");
   const int64_t ns = (n_rows + 31) / 32;
   const int nps = dpn == 3 ? 12 : 16;
@@ -1038,6 +996,7 @@ extern "C" int tfem_bsell_fill(int64_t n_rows, int dpn, int64_t n_nod, const int
                                const int32_t* adj, const int64_t* bslice_ptr, int32_t* bcols,
                                void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(node_ptr && adj && bslice_ptr && bcols && n_rows == n_nod * dpn && (dpn == 2 || dpn == 3),
                "bsell_fill: bad arguments");
   const int64_t ns = (n_rows + 31) / 32;
@@ -1049,6 +1008,7 @@ extern "C" int tfem_bsell_fill(int64_t n_rows, int dpn, int64_t n_nod, const int
 
 extern "C" int tfem_sell_spmv(const tfem_sell_t* a, const double* x, double* y, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   int rc = check_sell(a);
   if (rc != TFEM_OK) return rc;
   TFEM_REQUIRE(x && y, "sell_spmv: null pointer");
@@ -1249,6 +1209,7 @@ extern "C" int tfem_ebe_spmv(const tfem_ebe_t* a, const double* x, double* y, vo
 
 extern "C" int tfem_ebe_diag(const tfem_ebe_t* a, double* diag, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   int rc0 = check_ebe(a);
   if (rc0 != TFEM_OK) return rc0;
   TFEM_REQUIRE(diag, "ebe_diag: null pointer");
@@ -1270,6 +1231,7 @@ extern "C" int tfem_cg_stage(int stage, const tfem_sell_t* a, int64_t row_lo, in
                              const double* dinv, const double* b, double* x, double* work, double* red,
                              double rtol, double atol, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(a && a->n_rows > 0, "cg_stage: null matrix");
   const int64_t n_local = a->n_rows;
   TFEM_REQUIRE(work && red && n_owned > 0 && row_lo >= 0 && row_lo + n_owned <= n_local,
@@ -1327,6 +1289,7 @@ extern "C" int64_t tfem_krylov_work_offset(int64_t n_rows, int which) {
 // Copies {iterations, ||r||, ||b||, done flag} of the solve living in `work` to the host (synchronises).
 extern "C" int tfem_krylov_state(int64_t n_rows, const double* work, double* info_host, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(work && info_host, "krylov_state: null pointer");
   double sc_host[SC_COUNT];
   TFEM_CUDA(cudaMemcpyAsync(sc_host, work + 6 * pad32(n_rows), sizeof(sc_host), cudaMemcpyDeviceToHost, st));

@@ -260,6 +260,7 @@ extern "C" int tfem_pattern_phase1(int64_t n_nod, int64_t n_elem, int nn, int dp
                                    const int64_t* elements, int32_t* inc_ptr, int32_t* inc_list,
                                    int32_t* blk_cnt, int64_t* totals, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(n_nod > 0 && n_elem >= 0 && nn > 0 && dpn > 0, "pattern: bad sizes");
   TFEM_REQUIRE(elements && inc_ptr && inc_list && blk_cnt && totals, "pattern: null pointer");
   const int64_t n_slots = n_elem * nn;
@@ -315,6 +316,7 @@ extern "C" int tfem_pattern_phase2(int64_t n_nod, int64_t n_elem, int nn, int dp
                                    int32_t* adj, int64_t* indptr, int32_t* indices, int32_t* diag_map,
                                    int64_t* src_ptr, int32_t* src, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(elements && inc_ptr && inc_list && blk_cnt && node_ptr && adj && indptr && indices &&
                    diag_map && src_ptr && src, "pattern: null pointer");
   // exclusive scans over nodes: block offsets and scalar-entry offsets (n_nod+1 outputs each)
@@ -349,6 +351,7 @@ extern "C" int tfem_pattern_k_map(int64_t n_nod, int64_t n_elem, int nn, int dpn
                                   const int64_t* elements, const int64_t* node_ptr, const int32_t* adj,
                                   const int64_t* indptr, int32_t* k_map, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   (void)n_nod;
   TFEM_REQUIRE(elements && node_ptr && adj && indptr && k_map, "k_map: null pointer");
   const int64_t n_pairs = n_elem * nn * nn;
@@ -361,6 +364,7 @@ extern "C" int tfem_pattern_k_map(int64_t n_nod, int64_t n_elem, int nn, int dpn
 extern "C" int tfem_pattern_coo_rows(int64_t n_dofs, const int64_t* indptr, int64_t* rows,
                                      void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && rows && n_dofs > 0, "coo_rows: bad arguments");
   int64_t nnz = 0;
   TFEM_CUDA(cudaMemcpyAsync(&nnz, indptr + n_dofs, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

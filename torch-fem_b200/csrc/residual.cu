@@ -328,6 +328,7 @@ extern "C" int tfem_elem_force(int dim, int nn, int n_int, int dpn, const double
 extern "C" int tfem_ddot(int m, int64_t n_q, int64_t n_elem, const double* C, const double* E, int transpose,
                          double* out, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(C && E && out && n_q >= 0, "ddot: null pointer");
   TFEM_REQUIRE(m == 1 || m == 4 || m == 9, "ddot: m must be 1, 4 or 9 (d*d)");
   if (n_elem <= 0 || n_q == 0) return TFEM_OK;
@@ -348,6 +349,7 @@ extern "C" int tfem_ddot(int m, int64_t n_q, int64_t n_elem, const double* C, co
 extern "C" int tfem_ddot_outer(int m, int64_t n_q, int64_t n_elem, const double* G, const double* E, double* gC,
                                void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(G && E && gC && n_q >= 0, "ddot_outer: null pointer");
   TFEM_REQUIRE(m == 1 || m == 4 || m == 9, "ddot_outer: m must be 1, 4 or 9 (d*d)");
   if (n_elem <= 0) return TFEM_OK;

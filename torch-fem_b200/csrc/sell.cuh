@@ -42,6 +42,9 @@ struct Sell {
   const int32_t* cols;
   const double* vals;
   int64_t dot_lo = 0, dot_hi = INT64_MAX;  // rows that enter the fused x.y dot (owned rows of a rank)
+  // distributed multigrid (amg.cu, k_amg_spmv): only rows [dot_lo, dot_hi) are computed and WRITTEN (a peer may be
+  // storing into the halo entries of the output at the same time); slices outside [slice_lo, slice_hi) are skipped
+  int64_t slice_lo = 0, slice_hi = -1;     // -1: all slices
   // optional node-block column indices: one int per (node, block) instead of one per entry
   const int64_t* bslice_ptr = nullptr;
   const int32_t* bcols = nullptr;
@@ -218,13 +221,78 @@ inline int resident_ctas(K kernel, int threads) {
   return sms * (per_sm > 8 ? 8 : per_sm);
 }
 
+// grids are cached per (instantiation, device): one process may drive several devices
+template <typename K>
+int cached_resident_ctas(K kernel, int threads) {
+  static int g[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g[dev]) g[dev] = resident_ctas(kernel, threads);
+  return g[dev];
+}
+
+inline int vec_grid_cap() { return (num_sms() < kSMs ? num_sms() : kSMs) * 8; }
+
 inline int vec_grid(int64_t n) {
   const int64_t want = (n + kVecThreads * 4 - 1) / (kVecThreads * 4);
-  const int64_t cap = (int64_t)(num_sms() < kSMs ? num_sms() : kSMs) * 8;
+  const int64_t cap = vec_grid_cap();
   return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// y = A x, one warp per slice, persistent grid with the slices strided over it so that all SMs walk the same
+// band of the matrix (the gathered x window stays in L2). DPN = 0: scalar columns, 2/3: node-block columns.
+// DOT fuses x.y over the rows [dot_lo, dot_hi) (fixed-order reduction, last CTA writes *out_scalar).
+template <int DPN, bool DOT>
+__global__ void __launch_bounds__(kSellWarps * 32, 8)
+    k_sell_spmv(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc,
+                double* partials, unsigned int* ticket, double* out_scalar) {
+  __shared__ double s_red[kSellWarps];
+  if (DOT && sc[SC_DONE] != 0.0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double dot = 0.0;
+  const int64_t t_hi = A.slice_hi < 0 ? A.n_slices : A.slice_hi;
+  for (int64_t t = A.slice_lo + (int64_t)blockIdx.x * kSellWarps + warp; t < t_hi;
+       t += (int64_t)gridDim.x * kSellWarps) {
+    const int64_t row = t * 32 + lane;
+    // x[row] for the fused dot is requested BEFORE the row is streamed: asked for afterwards it costs every
+    // warp one exposed memory latency per slice (64 us of a 1.2 ms launch at config B)
+    double xr = 0.0;
+    if (DOT && row < A.n && row >= A.dot_lo && row < A.dot_hi) xr = __ldg(x + row);
+    const double acc = slice_row<DPN>(A, t, x, lane);
+    if (row < A.n) {
+      y[row] = acc;
+      if (DOT) dot = fma(acc, xr, dot);
+    }
+  }
+  if (DOT) {
+    const double b = block_sum<kSellWarps * 32>(dot, s_red);
+    double mine[1] = {b}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar = tot[0];
+  }
+}
+
+template <int DPN, bool DOT>
+int launch_sell_t(const Sell& A, const double* x, double* y, const double* sc, double* partials,
+                  unsigned int* ticket, double* out_scalar, cudaStream_t st) {
+  const int g = cached_resident_ctas(k_sell_spmv<DPN, DOT>, kSellWarps * 32);  // per instantiation and device
+  const int64_t n_sl = (A.slice_hi < 0 ? A.n_slices : A.slice_hi) - A.slice_lo;
+  const int64_t want = n_sl > 0 ? (n_sl + kSellWarps - 1) / kSellWarps : 1;
+  k_sell_spmv<DPN, DOT><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket,
+                                                                                out_scalar);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
+template <bool DOT>
+int launch_sell(const Sell& A, const double* x, double* y, const double* sc, double* partials,
+                unsigned int* ticket, double* out_scalar, cudaStream_t st) {
+  if (A.dpn == 3) return launch_sell_t<3, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
+  if (A.dpn == 2) return launch_sell_t<2, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
+  return launch_sell_t<0, DOT>(A, x, y, sc, partials, ticket, out_scalar, st);
+}
 
 // ---- Krylov work buffer: 6 vectors + device scalars + reduction partials + ticket
 struct Work {
