@@ -485,6 +485,13 @@ int tfem_amg_pcg_solve(const tfem_amg_level_t* levels_host, int n_levels, const 
                        const double* b_dev, const double* x0_dev, double rtol, double atol, int64_t maxiter,
                        double* x_dev, double* work_dev, double* info_host, void* stream);
 
+/* a9 — deterministic right-hand-side assembly, F[dpn*n + i] = sum over the slots (e, a) with elements[e,a] == n of
+ * f_e[e, a*dpn + i], summed in ascending slot order (bitwise reproducible; replaces base.py:428-445
+ * `F.index_add_(0, idx.ravel(), f.ravel())`, which uses floating-point atomics on CUDA). inc_ptr / inc_list: the
+ * incidence lists of tfem_pattern_phase1. f_e: double [n_elem, nn*dpn]; F: double [n_nod*dpn] out. */
+int tfem_assemble_rhs(int64_t n_nod, int dpn, const int32_t* inc_ptr_dev, const int32_t* inc_list_dev,
+                      const double* f_e_dev, double* F_dev, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Distributed AMG-PCG (SURVEY §8(f)-3 x §8(e)): the hierarchy of tfem_amg_* partitioned by rows over the ranks of a
  * tfem_comm. Aggregates are local to a rank, the prolongator smoothing and the Galerkin products are the global ones

@@ -129,6 +129,10 @@ def host_model(cls, nodes, elements, material, thickness=1.0):
             return torch.from_numpy(fn(nodes.detach().numpy(), elements.numpy(), bref.numpy(), w.numpy(),
                                        tangent.detach().numpy(), self.thickness.detach().numpy()))
 
+        def assemble_rhs(self, f):
+            F = torch.zeros(self.n_dofs, dtype=f.dtype)
+            return F.index_add_(0, self.idx.ravel().long(), f.ravel())     # sequential on the CPU: deterministic
+
         def assemble_matrix(self, k, con):
             val = O.assemble_values(k.detach().numpy(), self._k_map, self._glob_idx, self._diag_map,
                                     con.numpy(), self.n_dofs)

@@ -136,6 +136,26 @@ def test_assemble(T, tag):
     assert np.all(got[is_con.astype(bool)] == 0.0)
 
 
+@pytest.mark.parametrize("tag", ["hexa1", "tetra2", "quad2", "heat_hexa1", "hexa1_orphan"])
+def test_assemble_rhs_deterministic_gather(T, tag):
+    """a9 `assemble_rhs` (reference base.py:428-445) on the gather kernel: equals the oracle's index_add to round-off,
+    two runs are bitwise equal, the backward is the transposed gather."""
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    p = build_pattern(T, c, dpn)
+    nd = c["elements"].shape[1] * dpn
+    f = np.random.default_rng(3).standard_normal((len(c["elements"]), nd))
+    idx = O.dof_map(c["elements"], dpn)
+    ref = O.assemble_rhs(f, idx, dpn * c["nodes"].shape[0])
+    fd = dev(f).requires_grad_(True)
+    F = T.csr.assemble_rhs(p, fd)
+    assert np.abs(F.detach().cpu().numpy() - ref).max() <= 1e-14 * np.abs(ref).max()
+    assert torch.equal(F.detach(), T.csr.assemble_rhs(p, dev(f)))
+    g = dev(np.random.default_rng(4).standard_normal(ref.shape))
+    (F * g).sum().backward()
+    assert torch.equal(fd.grad, g[dev(idx.astype(np.int64))])
+
+
 @pytest.mark.parametrize("tag", MECH_CASES + HEAT_CASES)
 def test_residual_contractions(T, tag, tables):
     """K9/K10 (`tfem_elem_grad` / `tfem_elem_force`) against the reference formulas evaluated with torch on the

@@ -94,6 +94,7 @@ _SIGNATURES = {
                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tfem_ddot": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "tfem_ddot_outer": (c_int, [c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfem_assemble_rhs": (c_int, [c_int64, c_int] + [c_void_p] * 5),
     "tfem_assemble": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 9),
     "tfem_assemble_bc": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 11),
     "tfem_spmv_num_chunks": (c_int64, [c_int64]),

@@ -507,9 +507,10 @@ class FEM(ABC):
         return self.pattern.matrix(vals, symmetric=bool(getattr(self.material, "symmetric_tangent", True)))
 
     def assemble_rhs(self, f: Tensor) -> Tensor:
-        """Global vector from element vectors; differentiable (reference base.py:428-445)."""
-        F = torch.zeros(self.n_dofs, dtype=f.dtype, device=f.device)
-        return F.index_add_(0, self.idx.ravel(), f.ravel())
+        """Global vector from element vectors; differentiable (reference base.py:428-445). A deterministic gather
+        over the pattern's incidence lists (kernel `tfem_assemble_rhs`) instead of `index_add_`'s floating-point
+        atomics: two evaluations of a residual agree bit for bit, like on the reference's CPU path."""
+        return _csr.assemble_rhs(self.pattern, f)
 
     # ---- incremental Newton solve
     def solve(self, increments: Tensor | None = None, max_iter: int = 10, rtol: float = 1e-8,

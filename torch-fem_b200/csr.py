@@ -490,6 +490,35 @@ def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | N
     return vals
 
 
+class _AssembleRhs(torch.autograd.Function):
+    """F = sum of the element vectors at the global DOFs (kernel `tfem_assemble_rhs`: deterministic gather over the
+    pattern's incidence lists); backward = the transposed map, a plain gather g[idx]."""
+
+    @staticmethod
+    def forward(ctx, f: Tensor, pattern: "Pattern"):
+        ctx.pattern = pattern
+        ctx.shape = f.shape
+        fe = f.detach().to(torch.float64).contiguous()
+        F = torch.empty(pattern.n_dofs, dtype=torch.float64, device=fe.device)
+        L.check(L.lib.tfem_assemble_rhs(pattern.n_nod, pattern.dpn, L.ptr(pattern.inc_ptr), L.ptr(pattern.inc_list),
+                                        L.ptr(fe), L.ptr(F), L.stream()))
+        return F.to(f.dtype)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        p = ctx.pattern
+        return g.view(p.n_nod, p.dpn)[p.elements].reshape(ctx.shape), None
+
+
+def assemble_rhs(pattern: "Pattern", f: Tensor) -> Tensor:
+    """Global vector [n_dofs] from element vectors [n_elem, nn*dpn] (reference base.py:428-445), bitwise
+    reproducible and differentiable w.r.t. f (also twice: the backward is an indexing op)."""
+    L.require_cuda(f)
+    if f.numel() != pattern.n_elem * pattern.nn * pattern.dpn:
+        raise ValueError(f"f must hold {pattern.n_elem} x {pattern.nn * pattern.dpn} element values")
+    return _AssembleRhs.apply(f, pattern)
+
+
 class ElementOperator:
     """Matrix-free operator y = sum_e P_e^T k_e P_e x on stored element matrices (kernel K8) with the Dirichlet
     masking of `assemble` applied on the fly — the optional operator of the Krylov solve: no assembly, no SELL

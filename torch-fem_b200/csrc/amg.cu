@@ -1400,7 +1400,14 @@ static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
   const int64_t cap = (int64_t)num_sms() * per_sm;
   k_spgemm_num<D, G><<<(unsigned)(want < cap ? want : cap), W * G, smem, st>>>(nx, xptr, xcol, xvals, yptr, ycol,
                                                                                yvals, cptr, ccol, cvals, max_row, ht);
-  TFEM_LAUNCH_CHECK();
+  const cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    char msg[256];
+    snprintf(msg, sizeof(msg), "k_spgemm_num<%d,%d> launch: %s (nx %lld, max_row %d, W %d, smem %zu, grid %lld, per_sm %d)",
+             D, G, cudaGetErrorString(le), (long long)nx, max_row, W, smem, (long long)(want < cap ? want : cap), per_sm);
+    set_last_error("cuda", msg);
+    return TFEM_ERR_CUDA;
+  }
   return TFEM_OK;
 }
 

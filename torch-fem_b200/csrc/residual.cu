@@ -302,10 +302,38 @@ __global__ void __launch_bounds__(256)
   for (int k = 0; k < M; ++k) gC[(e * M + i) * M + k] = acc[k];
 }
 
+// a9 — deterministic `assemble_rhs` (src/torchfem/base.py:428-445: F.index_add_(0, idx.ravel(), f.ravel()), atomics on
+// CUDA): a gather over the node -> (element, local node) incidence lists of the pattern build. One thread per global
+// DOF sums its contributions in ascending slot order — the order the reference's CPU index_add_ meets them — so the
+// result is bitwise reproducible. Neighbouring threads read neighbouring doubles of the same element rows.
+__global__ void k_assemble_rhs(int64_t n_dofs, int dpn, const int32_t* __restrict__ inc_ptr,
+                               const int32_t* __restrict__ inc_list, const double* __restrict__ f,
+                               double* __restrict__ F) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_dofs) return;
+  const int64_t node = r / dpn;
+  const int i = (int)(r - node * dpn);
+  double s = 0.0;
+  for (int k = inc_ptr[node]; k < inc_ptr[node + 1]; ++k) s += f[(int64_t)inc_list[k] * dpn + i];
+  F[r] = s;
+}
+
 }  // namespace
 }  // namespace tfem
 
 using namespace tfem;
+
+extern "C" int tfem_assemble_rhs(int64_t n_nod, int dpn, const int32_t* inc_ptr, const int32_t* inc_list,
+                                 const double* f_e, double* F, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  TFEM_REQUIRE(inc_ptr && inc_list && f_e && F && dpn >= 1, "assemble_rhs: bad arguments");
+  if (n_nod <= 0) return TFEM_OK;
+  const int64_t n = n_nod * dpn;
+  k_assemble_rhs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, dpn, inc_ptr, inc_list, f_e, F);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
 
 extern "C" int tfem_elem_grad(int dim, int nn, int n_int, int dpn, const double* bref_host, const double* w_host,
                               const double* nodes, const int64_t* elements, int64_t n_elem, const double* u_e,
