@@ -659,6 +659,7 @@ def run_multi_gpu(args):
         ys = torch.empty_like(xs)
         spmv_ms = timed_max(lambda: A.matvec(xs, out=ys, fmt="sell"), 10)
     spmv_bytes = 12 * nnz_mine + 20 * n_owned      # §8(d) algorithmic bytes of the rows this rank multiplies
+    sell_padding = float(A._sell_struct.padded) / float(pattern.nnz) - 1.0 if A._sell_struct is not None else None
 
     # distributed AMG-PCG beside the Jacobi headline (like the N = 1 line)
     amg_info = None
@@ -692,6 +693,7 @@ def run_multi_gpu(args):
                        "nnz": int(nnz_owned.item()), "rtol": rtol,
                        "cg_iterations": iterations, "true_rel_residual": true_res,
                        "per_rank_local_dofs": int(A.n), "halo_bytes_per_exchange": plan.bytes_per_exchange(),
+                       "sell32_padding_overhead_rank0": sell_padding,
                        "collectives_per_iteration": ("fused into the kernels: halo = peer stores of the direction "
                                                      "update, 2 all-reduces = LL-protocol peer stores (tfem_dcg_solve)")
                        if fused else "NCCL: 1 halo exchange (P2P send/recv) + 2 all-reduces (1 and 2 doubles)",

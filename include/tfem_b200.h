@@ -195,6 +195,14 @@ int tfem_sell_fill_rect(int64_t n_rows, int64_t n_cols, const int64_t* indptr_de
                         const double* vals_dev, const int64_t* slice_ptr_dev, int32_t* sell_cols_dev,
                         double* sell_vals_dev, void* stream);
 
+/* The same with the long-row rule of tfem_sell_t: rows with more than long_cap entries are left EMPTY in the slices
+ * (pass TFEM_SELL_LONG_ROW; the uncapped functions above keep every row — the AMG operators use those). */
+int tfem_sell_slice_ptr_capped(int64_t n_rows, const int64_t* indptr_dev, int64_t long_cap, int64_t* slice_ptr_dev,
+                               void* stream);
+int tfem_sell_fill_capped(int64_t n_rows, int64_t n_cols, const int64_t* indptr_dev, const int32_t* cols_dev,
+                          const double* vals_dev, int64_t long_cap, const int64_t* slice_ptr_dev,
+                          int32_t* sell_cols_dev, double* sell_vals_dev, void* stream);
+
 /* Node-block column indices (optional, dpn = 2 or 3): FEM rows come in groups of dpn that share their column
  * blocks (column of entry k = dpn*adj[k/dpn] + k%dpn), so one int32 per (node, block) replaces one per entry
  * and the index stream drops from 4 to 4/dpn^2 bytes per nonzero (8.5 instead of 12 B/nnz for dpn = 3).
@@ -207,7 +215,15 @@ int tfem_bsell_fill(int64_t n_rows, int dpn, int64_t n_nod, const int64_t* node_
                     const int32_t* adj_dev, const int64_t* bslice_ptr_dev, int32_t* bcols_dev, void* stream);
 
 /* A SELL-32 matrix as the solver kernels take it (all device pointers). Either `cols` (scalar columns) or
- * `bcols` + `bslice_ptr` + `dpn` (node-block columns) must be given; if both are, block columns are used. */
+ * `bcols` + `bslice_ptr` + `dpn` (node-block columns) must be given; if both are, block columns are used.
+ *
+ * Long rows: a row with more than TFEM_SELL_LONG_ROW entries (the rows of a reference point coupled to a whole face,
+ * reference assembly.py:295-335: 11,169 entries against 81) would pad its whole slice to its own length and be walked
+ * by ONE lane. tfem_sell_slice_ptr / tfem_sell_fill therefore leave such rows EMPTY in the slices, and the SpMV
+ * computes them on a side path straight from the CSR arrays — one CTA per long row, products summed in a fixed
+ * order (deterministic). n_long > 0 requires long_rows (ascending row numbers) and the three CSR arrays. Supported
+ * by tfem_sell_spmv, tfem_krylov_solve and tfem_cg_stage; the AMG and the multi-GPU kernels reject such matrices. */
+#define TFEM_SELL_LONG_ROW 1024
 typedef struct tfem_sell {
   int64_t n_rows;
   const int64_t* slice_ptr;   /* [ceil(n/32)+1] */
@@ -216,6 +232,11 @@ typedef struct tfem_sell {
   const int64_t* bslice_ptr;  /* [ceil(n/32)+1] or NULL */
   const int32_t* bcols;       /* or NULL */
   int32_t dpn;                /* DOFs per node of the block structure (2 or 3), 0 if none */
+  int32_t n_long;             /* rows longer than TFEM_SELL_LONG_ROW (0: none) */
+  const int32_t* long_rows;   /* [n_long] */
+  const int64_t* csr_indptr;  /* the CSR arrays the matrix was converted from (read for the long rows only) */
+  const int32_t* csr_cols;
+  const double* csr_vals;
 } tfem_sell_t;
 
 int tfem_sell_spmv(const tfem_sell_t* A, const double* x_dev, double* y_dev, void* stream);

@@ -294,30 +294,44 @@ def test_larger_assembly_iterative_equals_monolithic(T):
     assert float((ua[0] - u_ref[lower]).abs().max()) <= 1e-6 * scale and float((ua[1] - u_ref[upper]).abs().max()) <= 1e-6 * scale
 
 
-@pytest.mark.skipif(os.environ.get("TFEM_TEST_BORDERED") != "1",
-                    reason="bordered Jacobi-PCG for long rows is opt-in and its GPU run is pending (DESIGN 3d); "
-                           "set TFEM_TEST_BORDERED=1 to run it")
-def test_bordered_solve_for_long_rows(T):
-    """A reference point driving a face of 441 nodes (six rows of 1,329 entries, 10,590 retained DOFs): with
-    `long_row_threshold` set, `sparse_solve` takes the bordered PCG and reproduces the regular Jacobi-PCG solution."""
+def test_reference_point_long_rows_take_the_side_path(T):
+    """A reference point driving a face of 441 nodes puts six rows of 1,329 entries into the reduced tangent (10,590
+    retained DOFs; reference assembly.py:295-335). Rows beyond TFEM_SELL_LONG_ROW stay out of the SELL-32 slices and are
+    computed by the side path of the SpMV (one CTA per row, fixed order): the product equals the CSR kernel's, CG /
+    MINRES reproduce the dense solution, two solves are bitwise equal, and the slices are not padded to 1,329."""
+    from torchfem_b200 import _lib as L
     from torchfem_b200.materials import IsotropicElasticity3D
     from torchfem_b200.mesh import cube_hexa
 
     nodes, elements = cube_hexa(21, 21, 9, 1.0, 1.0, 0.4)
     top = nodes[:, 2] == nodes[:, 2].max()
-    sols = []
-    for threshold in (None, 500):
+
+    def build():
         solid = T.Solid(nodes, elements, IsotropicElasticity3D(1000.0, 0.3))
         solid.constraints[nodes[:, 2] == 0.0] = True
         point = T.ReferencePoint([0.5, 0.5, 1.0])
         point.forces[0, 2], point.forces[0, 3], point.forces[0, 0] = -5.0, 2.0, 1.0
         asm = T.Assembly([solid, point])
-        asm.long_row_threshold = threshold
         asm.coupling(solid, top, point)
-        sols.append(asm.solve(method="cg", stol=1e-12))
-        split = getattr(asm._elimination._last[2], "border_split", None)
-        assert (split is None) == (threshold is None)
-        if split is not None:
-            assert split.k == 6
-    for a, b in zip(sols[0][0] + sols[0][1], sols[1][0] + sols[1][1]):
-        assert float((a - b).abs().max()) <= 1e-7 * max(float(a.abs().max()), 1e-300)
+        return asm
+
+    asm = build()
+    ref = asm.solve(method="spsolve")
+    K = asm._elimination._last[2]
+    lens = K.indptr[1:] - K.indptr[:-1]
+    assert int(lens.max()) > L.SELL_LONG_ROW and int((lens > L.SELL_LONG_ROW).sum()) == 6
+    st = K._sell_struct
+    K.sell()
+    assert st.long_rows is not None and st.long_rows.numel() == 6
+    assert st.padded < 1.2 * K.nnz                      # not padded to the longest row (that would be > 10x)
+    x = torch.randn(K.n, dtype=torch.float64, generator=torch.Generator(device="cuda").manual_seed(0))
+    y_sell, y_csr = K.matvec(x, fmt="sell"), K.matvec(x, fmt="csr")
+    assert float((y_sell - y_csr).abs().max()) <= 1e-12 * float(y_csr.abs().max())
+    assert torch.equal(y_sell, K.matvec(x, fmt="sell"))
+    for method in ("cg", "minres", None):
+        sol = build().solve(method=method, stol=1e-12)
+        for a, b in zip(ref[0] + ref[1], sol[0] + sol[1]):
+            assert float((a - b).abs().max()) <= 1e-6 * max(float(a.abs().max()), 1e-300)
+    again = build().solve(method="cg", stol=1e-12)
+    first = build().solve(method="cg", stol=1e-12)
+    assert all(torch.equal(a, b) for a, b in zip(first[0], again[0]))

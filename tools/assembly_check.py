@@ -31,8 +31,6 @@ def main():
     ap.add_argument("--stol", type=float, default=1e-8)
     ap.add_argument("--cases", nargs="+", default=["tie", "point"])
     ap.add_argument("--scalar", action="store_true", help="scalar (d = 1) operators instead of node blocks")
-    ap.add_argument("--long-rows", type=int, default=None,
-                    help="Assembly.long_row_threshold: rows longer than this go to the bordered PCG (opt-in)")
     a = ap.parse_args()
     torch.set_default_dtype(torch.float64)
     torch.set_default_device("cuda")
@@ -102,7 +100,6 @@ def main():
         point.forces[0, 2], point.forces[0, 0], point.forces[0, 4] = 1.0, 0.2, 0.05
         asm = T.Assembly([pa, pb, point])
         asm.node_blocks = not a.scalar
-        asm.long_row_threshold = a.long_rows
         asm.coupling(pb, face_b, pa, face_a)
         asm.coupling(pb, top_b, point)
         _, t1 = timed(lambda: asm.solve(method=method, stol=stol))
@@ -114,7 +111,7 @@ def main():
                                                   torch.nonzero(torch.cat([p.constraints.ravel() for p in asm.parts])
                                                                 [elim.retained]).ravel()))
         longest = int((K.indptr[1:] - K.indptr[:-1]).max())
-        print(json.dumps({"case": "tie+point", "block_size": elim.d, "long_row_threshold": a.long_rows, "n_dofs": asm.n_dofs, "n_retained": elim.n_retained,
+        print(json.dumps({"case": "tie+point", "block_size": elim.d, "n_dofs": asm.n_dofs, "n_retained": elim.n_retained,
                           "nnz_reduced": K.nnz, "longest_row": longest, "solve_ms_first": t1, "solve_ms_warm": t2,
                           "rigid_relation_max_err": float((u[1][top_b] - rigid).abs().max()),
                           "point_force": [round(v, 9) for v in f[2][0].tolist()],

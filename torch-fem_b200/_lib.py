@@ -27,11 +27,13 @@ TRACE_SLOTS = 16
 KIND_MECH, KIND_HEAT = 0, 1
 METHOD_CG, METHOD_MINRES = 0, 1
 SPMV_CHUNK = 512
+SELL_LONG_ROW = 1024
 
 class SellStruct(ctypes.Structure):
     """`tfem_sell_t` of include/tfem_b200.h."""
     _fields_ = [("n_rows", c_int64), ("slice_ptr", c_void_p), ("cols", c_void_p), ("vals", c_void_p),
-                ("bslice_ptr", c_void_p), ("bcols", c_void_p), ("dpn", ctypes.c_int32)]
+                ("bslice_ptr", c_void_p), ("bcols", c_void_p), ("dpn", ctypes.c_int32), ("n_long", ctypes.c_int32),
+                ("long_rows", c_void_p), ("csr_indptr", c_void_p), ("csr_cols", c_void_p), ("csr_vals", c_void_p)]
 
 
 _SELL_P = ctypes.POINTER(SellStruct)
@@ -114,6 +116,8 @@ _SIGNATURES = {
     "tfem_bsell_fill": (c_int, [c_int64, c_int, c_int64] + [c_void_p] * 5),
     "tfem_sell_slice_ptr": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_sell_fill": (c_int, [c_int64] + [c_void_p] * 7),
+    "tfem_sell_slice_ptr_capped": (c_int, [c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "tfem_sell_fill_capped": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64] + [c_void_p] * 4),
     "tfem_sell_fill_rect": (c_int, [c_int64, c_int64] + [c_void_p] * 7),
     "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_row_info": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),

@@ -34,7 +34,6 @@ from torch import Tensor
 from . import _lib as L
 from .amg import BlockOperator, spgemm
 from .base import FEM, Heat
-from .bordered import BorderSplit
 from .csr import CSRMatrix, sell_structure, spmv_plan
 from .sparse import describe_method, newton_solve
 
@@ -211,12 +210,8 @@ class _Elimination:
     AMG kernels can coarsen. Otherwise (`dofs=[...]` subsets, thermal parts, a 2-D point next to 2-DOF nodes) the
     operators are scalar CSR (d = 1)."""
 
-    MAX_BORDER = 64   # long rows the bordered solve keeps as dense columns
-
-    def __init__(self, asm: "Assembly", allow_blocks: bool = True, long_row_threshold: int | None = None):
+    def __init__(self, asm: "Assembly", allow_blocks: bool = True):
         dev = asm.device
-        self.long_row_threshold = long_row_threshold
-        self._border_split = None
         rows, cols, vals, retained = asm._triplets()
         n, n_ret = asm.n_dofs, int(retained.shape[0])
         self.retained = retained
@@ -309,11 +304,6 @@ class _Elimination:
         A, self._a_struct = spgemm(d, self._Ttb, KT, structure=self._a_struct)
         if self._template is None:
             self._template = self._matrix(A)
-            if self.long_row_threshold is not None:
-                lengths = self._template.indptr[1:] - self._template.indptr[:-1]
-                border = torch.nonzero(lengths > self.long_row_threshold).ravel()
-                if 0 < border.shape[0] <= self.MAX_BORDER:
-                    self._border_split = BorderSplit(self._template._indices(), self.n_retained, border)
         if self._mask_key != key:
             idx = self._template._indices()
             is_con = torch.zeros(self.n_retained, dtype=torch.bool, device=vals.device)
@@ -326,8 +316,6 @@ class _Elimination:
         values = A.vals.masked_fill(kill, 0.0)
         values[unit] = 1.0
         K = self._template._like(values)
-        if self._border_split is not None:
-            K.border_split = self._border_split   # read by sparse_solve (bordered.py)
         self._last = (list(blocks), key, K)
         return K
 
@@ -368,9 +356,6 @@ class Assembly:
         self._links: list[tuple[tuple[Part, Tensor], tuple[Part, Tensor]]] = []
         self._elimination: _Elimination | None = None
         self.node_blocks = True   # run the reduction on d x d node blocks where the couplings allow (see _Elimination)
-        # opt-in: rows of the reduced tangent longer than this (reference points driving whole faces) are solved around
-        # by the bordered Jacobi-PCG of bordered.py instead of being padded into the SELL-32 copy; None = off
-        self.long_row_threshold: int | None = None
 
     def __repr__(self) -> str:
         return f"<torch-fem assembly ({len(self.parts)} parts, {self.n_dofs} dofs)>"
@@ -505,7 +490,7 @@ class Assembly:
         track = any(p.requires_grad for p in params)
 
         if self._elimination is None:
-            self._elimination = _Elimination(self, self.node_blocks, self.long_row_threshold)
+            self._elimination = _Elimination(self, self.node_blocks)
         elim = self._elimination
         elim.forget()   # constraints and materials may have changed since the last solve; the patterns have not
         T, Tt, retained = elim.T, elim.Tt, elim.retained

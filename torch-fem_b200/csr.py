@@ -131,12 +131,28 @@ class SellStructure:
     indices (4 B/nnz) or node-block column indices (4/dpn^2 B/nnz, only for patterns built from a mesh
     with dpn in {2,3} and no unreferenced nodes). Built lazily, shared by every matrix on the pattern."""
 
-    def __init__(self, indptr: Tensor, indices: Tensor, n: int, block=None, n_cols: int | None = None):
+    def __init__(self, indptr: Tensor, indices: Tensor, n: int, block=None, n_cols: int | None = None,
+                 long_cap: int | None = None):
         self.indptr, self.indices, self.n = indptr, indices, int(n)
         self.n_cols = int(n) if n_cols is None else int(n_cols)   # rectangular operators (AMG P / R)
+        # long rows (reference-point couplings, reference assembly.py:295-335) stay out of the slices and are computed on
+        # the side path of the SpMV from the CSR arrays (`tfem_sell_t`); None: every row goes into its slice (AMG operators)
+        self.long_cap = None if long_cap is None else int(long_cap)
+        self.long_rows = None
+        if self.long_cap is not None:
+            lens = indptr[1:] - indptr[:-1]
+            rows = torch.nonzero(lens > self.long_cap).ravel()
+            if rows.numel():
+                self.long_rows = rows.to(torch.int32).contiguous()
+            else:
+                self.long_cap = None
         n_slices = (self.n + 31) // 32
         self.slice_ptr = _i64(n_slices + 1, indptr.device)
-        L.check(L.lib.tfem_sell_slice_ptr(self.n, L.ptr(indptr), L.ptr(self.slice_ptr), L.stream()))
+        if self.long_cap is None:
+            L.check(L.lib.tfem_sell_slice_ptr(self.n, L.ptr(indptr), L.ptr(self.slice_ptr), L.stream()))
+        else:
+            L.check(L.lib.tfem_sell_slice_ptr_capped(self.n, L.ptr(indptr), self.long_cap, L.ptr(self.slice_ptr),
+                                                     L.stream()))
         self.padded = int(self.slice_ptr[-1].item())
         self._cols = None
         self.block = block  # (dpn, n_nod, node_ptr, adj) or None
@@ -146,9 +162,14 @@ class SellStructure:
     def cols(self) -> Tensor:
         if self._cols is None:
             self._cols = _i32(max(self.padded, 4), self.indptr.device)
-            L.check(L.lib.tfem_sell_fill_rect(self.n, self.n_cols, L.ptr(self.indptr), L.ptr(self.indices), None,
-                                              L.ptr(self.slice_ptr), L.ptr(self._cols), None, L.stream()))
+            L.check(L.lib.tfem_sell_fill_capped(self.n, self.n_cols, L.ptr(self.indptr), L.ptr(self.indices), None,
+                                                self.fill_cap, L.ptr(self.slice_ptr), L.ptr(self._cols), None,
+                                                L.stream()))
         return self._cols
+
+    @property
+    def fill_cap(self) -> int:
+        return (1 << 62) if self.long_cap is None else self.long_cap
 
     @property
     def bcols(self):
@@ -170,13 +191,21 @@ class SellStructure:
 class SellMatrix:
     """A `tfem_sell_t` plus the tensors that keep its pointers alive."""
 
-    def __init__(self, st: SellStructure, vals: Tensor, use_block: bool = True):
+    def __init__(self, st: SellStructure, vals: Tensor, use_block: bool = True, csr_vals: Tensor | None = None):
         blk = st.bcols if use_block else None
         self.keep = [st.slice_ptr, vals]
         self.struct = L.SellStruct()
         self.struct.n_rows = st.n
         self.struct.slice_ptr = L.ptr(st.slice_ptr)
         self.struct.vals = L.ptr(vals)
+        self.struct.n_long = 0
+        if st.long_rows is not None:
+            if csr_vals is None:
+                raise ValueError("a SELL matrix with long rows needs the CSR values")
+            self.keep += [st.long_rows, st.indptr, st.indices, csr_vals]
+            self.struct.n_long = int(st.long_rows.numel())
+            self.struct.long_rows, self.struct.csr_indptr = L.ptr(st.long_rows), L.ptr(st.indptr)
+            self.struct.csr_cols, self.struct.csr_vals = L.ptr(st.indices), L.ptr(csr_vals)
         if blk is not None:
             bslice_ptr, bcols, dpn = blk
             self.keep += [bslice_ptr, bcols]
@@ -199,7 +228,8 @@ class SellMatrix:
 
 
 def sell_structure(indptr: Tensor, indices: Tensor, n: int, block=None) -> SellStructure:
-    return SellStructure(indptr, indices, n, block)
+    """SELL-32 structure of an assembled matrix (long rows on the side path)."""
+    return SellStructure(indptr, indices, n, block, long_cap=L.SELL_LONG_ROW)
 
 
 def spmv_plan(indptr: Tensor, n_rows: int, nnz: int) -> Tensor:
@@ -333,12 +363,12 @@ class CSRMatrix:
         st = self._sell_struct
         if self._sell_vals is None:
             sv = torch.empty(max(st.padded, 2), dtype=torch.float64, device=self.device)
-            L.check(L.lib.tfem_sell_fill(self.n, L.ptr(self.indptr), None, L.ptr(self.values_),
-                                         L.ptr(st.slice_ptr), None, L.ptr(sv), L.stream()))
+            L.check(L.lib.tfem_sell_fill_capped(self.n, self.n, L.ptr(self.indptr), None, L.ptr(self.values_), st.fill_cap,
+                                                L.ptr(st.slice_ptr), None, L.ptr(sv), L.stream()))
             self._sell_vals = sv
         key = bool(block and st.block is not None)
         if self._sell_mats.get(key) is None:
-            self._sell_mats[key] = SellMatrix(st, self._sell_vals, use_block=key)
+            self._sell_mats[key] = SellMatrix(st, self._sell_vals, use_block=key, csr_vals=self.values_)
         return self._sell_mats[key]
 
     def matvec(self, x: Tensor, out: Tensor | None = None, fmt: str = "auto") -> Tensor:

@@ -970,6 +970,7 @@ int make_oper(const tfem_amg_operator_t* o, Oper* out) {
   }
   int rc = check_sell(&o->sell);
   if (rc != TFEM_OK) return rc;
+  TFEM_REQUIRE(o->sell.n_long == 0, "amg: matrices with long rows (reference-point couplings) need method cg / minres");
   out->bcsr = false;
   out->sell = make_sell(&o->sell);
   out->n = o->sell.n_rows;
@@ -1387,11 +1388,13 @@ static int spgemm_num_launch(int64_t nx, const int64_t* xptr, const int32_t* xco
   }
   int W = 256 / G;
   if (G == 32) {
-    const int fit = (int)((48 * 1024) / (per_group ? per_group : 1));  // ~4 CTAs per SM
+    // ~4 CTAs per SM. 44 KB, not 48: the kernel's static shared memory counts against the 48 KB a launch may use
+    // without opting in (max_row = 78 gave 47,888 B dynamic + static > 48 KB -> "invalid argument" at launch)
+    const int fit = (int)((44 * 1024) / (per_group ? per_group : 1));
     W = fit < 1 ? 1 : (fit > 8 ? 8 : fit);
   }
   const size_t smem = W * per_group + 32;
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     TFEM_CUDA(cudaFuncSetAttribute(k_spgemm_num<D, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(208 * 1024)));
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spgemm_num<D, G>, W * G, smem) != cudaSuccess || per_sm < 1)

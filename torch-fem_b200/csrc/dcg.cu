@@ -391,6 +391,7 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
   TFEM_REQUIRE(!c->broken, "dcg_solve: communicator is out of step after a failed solve; create a new one");
   int rc0 = check_sell(a);
   if (rc0 != TFEM_OK) return rc0;
+  TFEM_REQUIRE(a->n_long == 0, "dcg_solve: matrices with long rows are not supported by the multi-GPU kernels");
   TFEM_REQUIRE(dinv && b && x && work && info, "dcg_solve: null pointer");
   const int64_t n_local = a->n_rows;
   const int64_t vec = c->heap_doubles / 2;

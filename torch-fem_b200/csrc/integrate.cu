@@ -66,8 +66,8 @@ constexpr int kCB = 8;  // column nodes per thread
 #endif
 #ifndef TFEM_K1_RPT
 #define TFEM_K1_RPT 1      // row nodes per thread (mechanics, even node counts). 2 halves the LDS operand traffic but
-                           // runs SLOWER on B200 (17.2 vs 15.2 ms at config B, 220 registers -> 8 warps per SM,
-                           // profiles/r2_e_k1_variants.txt): the kernel is bound by the latency of its phases, not by LDS
+                           // runs SLOWER on B200 (17.2-17.7 vs 15.1 ms at config B: 220 registers -> 8 warps per SM;
+                           // profiles/r2_e_k1_variants.txt, r2_f_k1_variants.txt)
 #endif
 
 template <int KIND, int NN>

@@ -89,12 +89,14 @@ inline int spmv_grid(int64_t n_chunks) {
 // ------------------------------------------------------------------------------------------ SELL-32
 // (layout and per-slice device code: sell.cuh)
 __global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __restrict__ indptr,
-                              int64_t* __restrict__ slice_elems) {
+                              int64_t* __restrict__ slice_elems, int64_t long_cap) {
   const int lane = threadIdx.x & 31;
   const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= n_slices) return;
   const int64_t r = t * 32 + lane;
-  int len = (r < n) ? (int)(indptr[r + 1] - indptr[r]) : 0;
+  int64_t len64 = (r < n) ? indptr[r + 1] - indptr[r] : 0;
+  if (len64 > long_cap) len64 = 0;   // long rows stay out of the slices (side path k_sell_long)
+  int len = (int)len64;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
   if (lane == 0) slice_elems[t] = (int64_t)((len + 1) & ~1) * 32;
@@ -104,7 +106,7 @@ __global__ void k_sell_widths(int64_t n, int64_t n_slices, const int64_t* __rest
 __global__ void k_sell_fill(int64_t n, int64_t n_cols, int64_t n_slices, const int64_t* __restrict__ indptr,
                             const int32_t* __restrict__ cols, const double* __restrict__ vals,
                             const int64_t* __restrict__ slice_ptr, int32_t* __restrict__ s_cols,
-                            double* __restrict__ s_vals) {
+                            double* __restrict__ s_vals, int64_t long_cap) {
   const int lane = threadIdx.x & 31;
   const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (t >= n_slices) return;
@@ -112,7 +114,9 @@ __global__ void k_sell_fill(int64_t n, int64_t n_cols, int64_t n_slices, const i
   const int total = (int)(slice_ptr[t + 1] - base);  // 32 * W
   const int64_t my_row = t * 32 + lane;
   const int64_t my_beg = (my_row < n) ? indptr[my_row] : 0;
-  const int my_len = (my_row < n) ? (int)(indptr[my_row + 1] - my_beg) : 0;
+  int64_t my_len64 = (my_row < n) ? indptr[my_row + 1] - my_beg : 0;
+  if (my_len64 > long_cap) my_len64 = 0;   // long rows stay out of the slices (side path k_sell_long)
+  const int my_len = (int)my_len64;
   for (int o = lane; o < total; o += 32) {
     const int s2 = o >> 6, rem = o & 63;
     const int rl = rem >> 1, k = s2 * 2 + (rem & 1);
@@ -152,7 +156,9 @@ __global__ void k_bsell_fill(int64_t n_slices, int64_t n_nod, int dpn, int nps,
     if (node >= n_nod) node = n_nod - 1;
     const int64_t nb = node_ptr[node];
     const int cnt = (int)(node_ptr[node + 1] - nb);
-    bcols[base + o] = cnt > 0 ? adj[nb + (kb < cnt ? kb : cnt - 1)] : (int32_t)node;
+    // an empty row (halo rows of a distributed operator) pads with block column 0: always inside the operand, also for
+    // rectangular operators (its own node index may lie beyond a shorter coarse vector); the values there are 0.0
+    bcols[base + o] = cnt > 0 ? adj[nb + (kb < cnt ? kb : cnt - 1)] : 0;
   }
 }
 
@@ -935,14 +941,18 @@ extern "C" int tfem_csr_transpose(int64_t n_rows, int64_t n_cols, int64_t nnz, c
   return TFEM_OK;
 }
 
-extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_t* slice_ptr,
-                                   void* stream_) {
+extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_t* slice_ptr, void* stream_) {
+  return tfem_sell_slice_ptr_capped(n_rows, indptr, INT64_MAX, slice_ptr, stream_);
+}
+
+extern "C" int tfem_sell_slice_ptr_capped(int64_t n_rows, const int64_t* indptr, int64_t long_cap,
+                                          int64_t* slice_ptr, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0, "sell_slice_ptr: bad arguments");
   const int64_t ns = (n_rows + 31) / 32;
   TFEM_CUDA(cudaMemsetAsync(slice_ptr, 0, sizeof(int64_t), st));
-  k_sell_widths<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, ns, indptr, slice_ptr + 1);
+  k_sell_widths<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, ns, indptr, slice_ptr + 1, long_cap);
   TFEM_LAUNCH_CHECK();
   size_t bytes = 0;
   TFEM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, bytes, slice_ptr + 1, slice_ptr + 1, (int)ns, st));
@@ -956,13 +966,19 @@ extern "C" int tfem_sell_slice_ptr(int64_t n_rows, const int64_t* indptr, int64_
 extern "C" int tfem_sell_fill_rect(int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* cols,
                                    const double* vals, const int64_t* slice_ptr, int32_t* sell_cols,
                                    double* sell_vals, void* stream_) {
+  return tfem_sell_fill_capped(n_rows, n_cols, indptr, cols, vals, INT64_MAX, slice_ptr, sell_cols, sell_vals, stream_);
+}
+
+extern "C" int tfem_sell_fill_capped(int64_t n_rows, int64_t n_cols, const int64_t* indptr, const int32_t* cols,
+                                     const double* vals, int64_t long_cap, const int64_t* slice_ptr,
+                                     int32_t* sell_cols, double* sell_vals, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
   TFEM_REQUIRE(indptr && slice_ptr && n_rows > 0 && n_cols > 0, "sell_fill: bad arguments");
   TFEM_REQUIRE((!sell_cols || cols) && (!sell_vals || vals), "sell_fill: output without input");
   const int64_t ns = (n_rows + 31) / 32;
   k_sell_fill<<<grid_for(ns * 32, 256), 256, 0, st>>>(n_rows, n_cols, ns, indptr, cols, vals, slice_ptr, sell_cols,
-                                                      sell_vals);
+                                                      sell_vals, long_cap);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }
@@ -1113,7 +1129,7 @@ static int krylov_solve_impl(int method, const Op& A, const double* dinv, const 
   // small systems on the assembled matrix: the whole loop in one cooperative kernel (see k_cg_coop / k_mr_coop)
   static const bool coop_off = getenv("TFEM_CG_COOP") && atoi(getenv("TFEM_CG_COOP")) == 0;
   bool coop_done = false;
-  if (!A.ebe && !coop_off && n <= kCoopMaxRows) {
+  if (!A.ebe && !coop_off && n <= kCoopMaxRows && A.sell.n_long == 0) {  // (the long-row side path is a second kernel)
     int rc = TFEM_ERR_INVALID;
     if (method == TFEM_METHOD_CG) {
       if (A.sell.dpn == 3) rc = cg_coop_batches<3>(A.sell, dinv, x, w, maxiter, sc_host, &launches, &spmvs, st);

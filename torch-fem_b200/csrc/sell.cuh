@@ -45,6 +45,12 @@ struct Sell {
   // distributed multigrid (amg.cu, k_amg_spmv): only rows [dot_lo, dot_hi) are computed and WRITTEN (a peer may be
   // storing into the halo entries of the output at the same time); slices outside [slice_lo, slice_hi) are skipped
   int64_t slice_lo = 0, slice_hi = -1;     // -1: all slices
+  // rows longer than TFEM_SELL_LONG_ROW are empty in the slices and computed from the CSR arrays (k_sell_long)
+  int n_long = 0;
+  const int32_t* long_rows = nullptr;
+  const int64_t* csr_indptr = nullptr;
+  const int32_t* csr_cols = nullptr;
+  const double* csr_vals = nullptr;
   // optional node-block column indices: one int per (node, block) instead of one per entry
   const int64_t* bslice_ptr = nullptr;
   const int32_t* bcols = nullptr;
@@ -61,6 +67,11 @@ inline Sell make_sell(const tfem_sell_t* a) {
   A.bslice_ptr = a->bslice_ptr;
   A.bcols = a->bcols;
   A.dpn = a->bcols ? a->dpn : 0;
+  A.n_long = a->n_long;
+  A.long_rows = a->long_rows;
+  A.csr_indptr = a->csr_indptr;
+  A.csr_cols = a->csr_cols;
+  A.csr_vals = a->csr_vals;
   return A;
 }
 
@@ -69,6 +80,8 @@ inline int check_sell(const tfem_sell_t* a) {
   TFEM_REQUIRE(a->cols || (a->bcols && a->bslice_ptr), "SELL matrix: neither scalar nor block columns given");
   TFEM_REQUIRE(aligned16(a->vals) && (!a->cols || aligned16(a->cols)), "SELL arrays must be 16-byte aligned");
   TFEM_REQUIRE(!a->bcols || a->dpn == 2 || a->dpn == 3, "block columns need 2 or 3 DOFs per node");
+  TFEM_REQUIRE(a->n_long >= 0 && (a->n_long == 0 || (a->long_rows && a->csr_indptr && a->csr_cols && a->csr_vals)),
+               "SELL matrix: long rows need the row list and the CSR arrays");
   return TFEM_OK;
 }
 
@@ -274,6 +287,32 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
   }
 }
 
+// The long rows (empty in the slices): one CTA per row straight from the CSR arrays. Every thread sums its strided
+// entries in order, the partial sums are combined in a fixed tree: deterministic. DOT: the row's term x_r y_r is added
+// to *out_scalar (which k_sell_spmv has written) by the CTA that finishes last, in row order.
+constexpr int kLongThreads = 256;
+template <bool DOT>
+__global__ void __launch_bounds__(kLongThreads)
+    k_sell_long(Sell A, const double* __restrict__ x, double* __restrict__ y, const double* sc, double* partials,
+                unsigned int* ticket, double* out_scalar) {
+  __shared__ double s_red[kLongThreads / 32];
+  if (DOT && sc[SC_DONE] != 0.0) return;
+  const int64_t r = A.long_rows[blockIdx.x];
+  const int64_t b = A.csr_indptr[r], e = A.csr_indptr[r + 1];
+  double acc = 0.0;
+  for (int64_t k = b + threadIdx.x; k < e; k += kLongThreads) acc = fma(A.csr_vals[k], __ldg(x + A.csr_cols[k]), acc);
+  const double row_sum = block_sum<kLongThreads>(acc, s_red);   // valid in thread 0
+  double term = 0.0;
+  if (threadIdx.x == 0) {
+    y[r] = row_sum;
+    if (DOT && r >= A.dot_lo && r < A.dot_hi) term = row_sum * x[r];
+  }
+  if (DOT) {
+    double mine[1] = {term}, tot[1];
+    if (publish_and_reduce<1>(mine, partials, ticket, tot) && threadIdx.x == 0) *out_scalar += tot[0];
+  }
+}
+
 template <int DPN, bool DOT>
 int launch_sell_t(const Sell& A, const double* x, double* y, const double* sc, double* partials,
                   unsigned int* ticket, double* out_scalar, cudaStream_t st) {
@@ -282,6 +321,7 @@ int launch_sell_t(const Sell& A, const double* x, double* y, const double* sc, d
   const int64_t want = n_sl > 0 ? (n_sl + kSellWarps - 1) / kSellWarps : 1;
   k_sell_spmv<DPN, DOT><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket,
                                                                                 out_scalar);
+  if (A.n_long > 0) k_sell_long<DOT><<<A.n_long, kLongThreads, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;
 }

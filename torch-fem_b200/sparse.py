@@ -23,7 +23,6 @@ from torch.autograd import Function
 
 from . import csr as _csr
 from .amg import AMGPreconditioner
-from .bordered import BorderedOperator, bordered_pcg
 from .csr import CSRMatrix, ElementOperator, JacobiPreconditioner
 
 # "amgx" names the reference's GPU AMG method (sparse.py:422-442); here it is served by the in-house AMG kernels.
@@ -108,17 +107,11 @@ def sparse_solve(A, b: Tensor, B: Tensor | None = None, stol: float = 1e-10, dev
 
     if method == "pardiso":
         raise RuntimeError("Pardiso backend is not available on GPU.")
-    split = getattr(Ac, "border_split", None)
-    if split is not None and n >= DIRECT_LIMIT and (auto_selected or method == "cg"):
-        # opt-in (Assembly.long_row_threshold): the few very long rows of a reference-point coupling stay out of the
-        # SELL-32 copy (bordered.py). A breakdown under the size policy falls through to the regular solvers below.
-        try:
-            x, _ = bordered_pcg(BorderedOperator(split, Ac.values_, CSRMatrix), rhs, rtol=stol,
-                                x0=None if x0 is None else x0.detach())
-            return x.to(device=out_device, dtype=b.dtype), None
-        except RuntimeError:
-            if not auto_selected:
-                raise
+    if (method == "amgx" and auto_selected and isinstance(Ac, CSRMatrix) and Ac._sell_struct is not None
+            and Ac._sell_struct.long_rows is not None):
+        # rows of a reference point coupled to a whole face (kept out of the SELL slices, csr.SellStructure): the AMG
+        # kernels do not take such matrices; the Krylov kernels compute the long rows on their side path
+        method = "minres"
     if method == "amgx":
         # reference sparse.py:422-442: hierarchy built on the first solve, coefficients refreshed when the solver
         # object comes back in as M
