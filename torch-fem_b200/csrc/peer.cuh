@@ -185,8 +185,24 @@ __device__ __forceinline__ bool halo_send_and_release(const Peers& P, const Halo
     double* dst = heap(P, H.send_peer[s]) + vec_off;
     const int32_t* si = H.send_src[s];
     const int32_t* di = H.send_dst[s];
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < H.send_count[s];
-         k += (int64_t)n_halo_ctas * blockDim.x) {
+    const int64_t stride = (int64_t)n_halo_ctas * blockDim.x, cnt = H.send_count[s];
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // four entries in flight per thread: the loop is a chain of dependent memory latencies otherwise
+    for (; k + 3 * stride < cnt; k += 4 * stride) {
+      int64_t i[4], d[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t ku = k + u * stride;
+        i[u] = si ? (int64_t)si[ku] : H.src0[s] + ku;
+        d[u] = di ? (int64_t)di[ku] : H.dst0[s] + ku;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = value(i[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dst[d[u]] = v[u];
+    }
+    for (; k < cnt; k += stride) {
       const int64_t i = si ? (int64_t)si[k] : H.src0[s] + k;
       const int64_t d = di ? (int64_t)di[k] : H.dst0[s] + k;
       dst[d] = value(i);
