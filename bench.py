@@ -664,8 +664,11 @@ def run_multi_gpu(args):
     # distributed AMG-PCG beside the Jacobi headline (like the N = 1 line)
     amg_info = None
     if not args.no_amg and multi_amg_available():
-        amg_info = bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, row_lo, n_owned, x, solve,
-                                         global_res, timed_max, n_dofs_global, build_ms)
+        try:
+            amg_info = bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, row_lo, n_owned, x,
+                                             solve, global_res, timed_max, n_dofs_global, build_ms)
+        except RuntimeError as exc:      # reported beside the headline, never instead of it
+            amg_info = {"error": str(exc)[:300]}
 
     probe = None
     if config_c or args.probe:

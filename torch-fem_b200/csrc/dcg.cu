@@ -425,10 +425,11 @@ extern "C" int tfem_dcg_solve(void* comm, const tfem_sell_t* a, int64_t row_lo, 
   // init kernel: the first CTAs also send p0's halo; direction kernel: `hd` DEDICATED halo CTAs out of the grid
   int hc = halo_ctas(H.send_total, kVecThreads);
   if (hc > vg) hc = vg;
-  // <= 16 entries per thread, four in flight: at 433 k entries (two neighbours at config B) 32 CTAs with 53 entries per
-  // thread took longer than the whole streaming loop (direction kernel 68 vs 54 us, profiles/r2_n8_*wait_trace*)
-  int hd = H.send_total > 0 ? (int)((H.send_total + 4095) / 4096) : 0;
-  if (hd > 112) hd = 112;
+  // <= 32 entries per thread, four in flight (peer.cuh): at 433 k entries (two neighbours at config B) 32 CTAs with 53
+  // entries per thread, one at a time, took longer than the whole streaming loop (direction kernel 68 vs 54 us,
+  // profiles/r2_n8_*wait_trace*)
+  int hd = H.send_total > 0 ? (int)((H.send_total + 8191) / 8192) : 0;
+  if (hd > 64) hd = 64;
   if (H.send_total > 0 && hd < 1) hd = 1;
   const int vgd = vg + (vg + hd <= vec_grid_cap() ? hd : 0);             // stay within one resident wave
   if (vgd == vg && hd >= vg) hd = vg > 1 ? vg - 1 : 0;
