@@ -47,7 +47,9 @@ def main():
     w = ET.iweights.to(torch.float64).cpu()
     C1 = IsotropicElasticity3D(1000.0, 0.3).C.to(torch.float64).cpu()
 
-    def system(nodes_h, elements_h):
+    patterns = {}
+
+    def system(nodes_h, elements_h, heterogeneous=False):
         nodes, elements = nodes_h.to(dev), elements_h.to(dev)
         con = torch.zeros(nodes_h.shape[0], 3, dtype=torch.bool)
         disp = torch.zeros(nodes_h.shape[0], 3)
@@ -56,8 +58,14 @@ def main():
         con[right, 0] = True
         disp[right, 0] = 0.1
         is_con, disp = con.ravel().to(torch.uint8).to(dev), disp.ravel().to(dev)
-        p = csr.Pattern(elements, nodes_h.shape[0], 3)
+        key = (nodes_h.shape[0], len(elements_h))
+        if key not in patterns:
+            patterns[key] = csr.Pattern(elements, nodes_h.shape[0], 3)
+        p = patterns[key]
         Cd = C1.expand(len(elements_h), 3, 3, 3, 3).contiguous().to(dev)
+        if heterogeneous:   # a second set of coefficients on the same pattern (stiffness varying with the element centre)
+            centre = nodes[elements].mean(dim=1)
+            Cd = Cd * (1.0 + 0.8 * torch.sin(7.0 * centre[:, 0] + 3.0 * centre[:, 1]) * torch.cos(5.0 * centre[:, 2]))[:, None, None, None, None]
         k = csr.integrate_k(L.KIND_MECH, bref, w, nodes, elements, Cd)
         rhs = torch.empty(p.n_dofs, device=dev)
         A = p.matrix(csr.assemble(p, k, is_con, ubc=disp, lift=rhs))
@@ -109,6 +117,19 @@ def main():
                 "launches": st["launches"]}
         out["cases"].append(case)
         ok = ok and case["rel_diff_vs_jacobi_pcg"] <= 1e-8 and case["true_rel_residual"] <= 10 * a.rtol and case["bitwise_reproducible"]
+        # resetup: new coefficients on the stored hierarchy (AmgX life-cycle, reference sparse.py:440-441) must give
+        # what a hierarchy built from scratch for them gives
+        _, A2, rhs2 = system(nodes_h, mesh.elements, heterogeneous=True)
+        M2 = csr.JacobiPreconditioner(A2)
+        x_j2, _ = cg.solve(A2, M2.dinv, rhs2, rtol=a.rtol, maxiter=50000)
+        H.resetup(A2)
+        x_r, st_r = H.solve(rhs2, rtol=a.rtol)
+        H2 = damg.DistributedAMG(A2, mesh.lo, mesh.n_owned, mesh.global_nodes, node_plan, gather_max=gather_max)
+        x_f, st_f = H2.solve(rhs2, rtol=a.rtol)
+        case["resetup"] = {"iterations": st_r["iterations"], "iterations_fresh_setup": st_f["iterations"],
+                           "rel_diff_vs_jacobi_pcg": rel_diff(x_r, x_j2), "equals_fresh_setup_bitwise": bool(torch.equal(x_r[own], x_f[own]))}
+        ok = ok and case["resetup"]["rel_diff_vs_jacobi_pcg"] <= 1e-8 and abs(st_r["iterations"] - st_f["iterations"]) <= 1
+        H2.close()
         H.close()
     # single-GPU hierarchy on the whole problem (rank 0)
     if rank == 0:

@@ -1552,19 +1552,18 @@ __global__ void k_allreduce(Peers P, int set, unsigned long long epoch, const do
   }
 }
 
-// halo exchange of a heap vector, step 1: store my entries into the neighbours' copies, release the channel flag
+// Halo exchange of a heap vector in ONE kernel: the CTAs store my boundary entries into the neighbours' copies (the last
+// one releases the channel flag there), then thread 0 of CTA 0 waits until every neighbour has delivered — so the next
+// kernel on the stream may read the halo. No deadlock: every rank's stores precede its wait and depend on nothing remote.
 __global__ void __launch_bounds__(kVecThreads)
-    k_halo_push(Peers P, Halo H, int64_t vec_off, int channel, unsigned long long epoch, unsigned int* halo_ticket,
-                const double* sc) {
+    k_halo_exchange(Peers P, Halo H, int64_t vec_off, int channel, unsigned long long epoch, unsigned int* halo_ticket,
+                    double* sc) {
   if (sc[P_DONE] == 4.0) return;
-  const double* v = heap(P, P.rank) + vec_off;
-  halo_send_and_release(P, H, vec_off, channel, epoch, (int)gridDim.x, halo_ticket, [&](int64_t i) { return v[i]; });
-}
-
-// step 2: the stream waits until every neighbour has delivered
-__global__ void k_halo_wait(Peers P, Halo H, int channel, unsigned long long epoch, double* sc) {
-  if (sc[P_DONE] == 4.0) return;
-  if (threadIdx.x == 0 && !halo_wait_thread(P, H, channel, epoch)) sc[P_DONE] = 4.0;
+  if (H.n_send > 0 && H.send_total > 0) {
+    const double* v = heap(P, P.rank) + vec_off;
+    halo_send_and_release(P, H, vec_off, channel, epoch, (int)gridDim.x, halo_ticket, [&](int64_t i) { return v[i]; });
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && H.n_recv > 0 && !halo_wait_thread(P, H, channel, epoch)) sc[P_DONE] = 4.0;
 }
 
 __global__ void __launch_bounds__(kVecThreads)
@@ -1605,14 +1604,10 @@ void restrict_rows(Oper& A, int64_t lo, int64_t hi) {  // scalar rows [lo, hi) a
 int halo_exchange(DCtx& X, const Halo& H, int64_t vec_off, int channel) {
   if (X.c->world == 1) return TFEM_OK;
   const unsigned long long ep = ++X.c->chan_epoch[channel];
-  if (H.n_send > 0 && H.send_total > 0) {
-    int g = halo_ctas(H.send_total, kVecThreads);
+  if ((H.n_send > 0 && H.send_total > 0) || H.n_recv > 0) {
+    int g = H.send_total > 0 ? halo_ctas(H.send_total, kVecThreads) : 1;
     if (g > 64) g = 64;
-    k_halo_push<<<g, kVecThreads, 0, X.st>>>(X.P, H, vec_off, channel, ep, X.halo_ticket, X.sc);
-    ++X.launches;
-  }
-  if (H.n_recv > 0) {
-    k_halo_wait<<<1, 32, 0, X.st>>>(X.P, H, channel, ep, X.sc);
+    k_halo_exchange<<<g, kVecThreads, 0, X.st>>>(X.P, H, vec_off, channel, ep, X.halo_ticket, X.sc);
     ++X.launches;
   }
   TFEM_LAUNCH_CHECK();

@@ -16,6 +16,10 @@ namespace tfem {
 namespace {
 
 constexpr int kWarps = 8;
+#ifndef TFEM_K2_INFLIGHT
+#define TFEM_K2_INFLIGHT 2
+#endif
+constexpr int kInFlight = TFEM_K2_INFLIGHT;  // contributions whose loads are issued before the first is added
 
 // NN = nodes per element as a compile-time constant (0: run-time value) so the slot decoding needs no
 // integer division. One lane per node BLOCK (neighbour p of the node): it decodes every contribution once and
@@ -61,10 +65,10 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int i = 0; i < DPN; ++i)
 #pragma unroll
       for (int j = 0; j < DPN; ++j) acc[i][j] = 0.0;
-    for (int64_t s = sb; s < se; s += 2) {
-      const double* kb[2];
+    for (int64_t s = sb; s < se; s += kInFlight) {
+      const double* kb[kInFlight];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < kInFlight; ++u) {
         const int cc = (s + u < se) ? src[s + u] : -1;  // e*nn*nn + a*nn + b
         if (cc < 0) {
           kb[u] = nullptr;
@@ -74,15 +78,15 @@ __global__ void __launch_bounds__(kWarps * 32)
           kb[u] = k + e * nd2 + (int64_t)(aq * DPN) * nd + bq * DPN;
         }
       }
-      double v[2][DPN][DPN];
+      double v[kInFlight][DPN][DPN];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < kInFlight; ++u)
 #pragma unroll
         for (int i = 0; i < DPN; ++i)
 #pragma unroll
           for (int j = 0; j < DPN; ++j) v[u][i][j] = kb[u] ? kb[u][i * nd + j] : 0.0;
 #pragma unroll
-      for (int u = 0; u < 2; ++u)  // + 0.0 for the missing one: exact
+      for (int u = 0; u < kInFlight; ++u)  // + 0.0 for the missing ones: exact; slot order kept
 #pragma unroll
         for (int i = 0; i < DPN; ++i)
 #pragma unroll

@@ -26,6 +26,7 @@ Everything the hierarchy needs from the mesh partition is the node-level halo pl
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -38,7 +39,8 @@ from .amg import AMGPreconditioner, BlockOperator, _empty, spgemm
 from .csr import CSRMatrix
 from .distributed import HaloPlan, PeerComm, _as_range
 
-GATHER_MAX_DOFS = 400_000     # a level with at most this many unknowns (global) is gathered and solved redundantly
+# a level with at most this many unknowns (global) is gathered and solved redundantly (TFEM_DAMG_GATHER_MAX: experiments)
+GATHER_MAX_DOFS = int(os.environ.get("TFEM_DAMG_GATHER_MAX", 400_000))
 MAX_DIST_LEVELS = 4
 
 
@@ -211,36 +213,68 @@ def _frame_rows(bptr_rows: Tensor, lo: int, n_total: int) -> Tensor:
 
 class DistributedAMG:
     """The distributed hierarchy plus its work vectors; `solve(b)` = AMG-preconditioned CG over all ranks
-    (`tfem_damg_pcg_solve`). Collective: every rank constructs it and calls `solve` together. `close()` frees the
-    communicator (explicitly, like the reference's AmgX handle, amgx.py:385-395)."""
+    (`tfem_damg_pcg_solve`). Collective: every rank constructs it and calls `resetup` / `solve` together. Life-cycle of
+    the reference's AmgX solver object (amgx.py:211-383): construction = setup, `resetup(A)` = new coefficients on the
+    stored aggregates / patterns / exchange plans (numeric phases and value exchanges only), `solve`, explicit `close()`
+    (amgx.py:385-395)."""
 
     def __init__(self, A: CSRMatrix, own_lo_node: int, n_owned_nodes: int, global_nodes: Tensor, node_plan: HaloPlan,
                  group=None, gather_max: int = GATHER_MAX_DOFS, max_coarse: int = _amg.MAX_COARSE_DOFS,
                  comm: PeerComm | None = None):
         if not isinstance(A, CSRMatrix) or A._sell_struct is None or A._sell_struct.block is None:
             raise TypeError("the distributed AMG needs an assembled CSRMatrix on a mesh pattern (node blocks)")
-        self.W = W = _World(group)
-        self.device = dev = A.device
+        self.W = _World(group)
+        self.device = A.device
         self.gather_max, self.max_coarse = int(gather_max), int(max_coarse)
         self.levels: list[_DLevel] = []
+        self._own = (int(own_lo_node), int(own_lo_node + n_owned_nodes))
+        self._plan0 = node_plan_from_halo_plan(node_plan, self.device, self.W)
+        self.comm = None
+        self._setup(A, symbolic=True)
+        self._allocate(comm)
+
+    def resetup(self, A: CSRMatrix) -> None:
+        """New coefficients on the same sparsity pattern and partition (Newton iterations, load cases, design updates):
+        aggregates, the patterns of P / R / A·P / A_c, the coarse numberings and every exchange plan are kept; row info,
+        spectral radii, P values, the two value exchanges per level, the numeric SpGEMMs and the tail are refreshed in
+        place (AmgX `resetup`, reference sparse.py:440-441)."""
+        if (A.indptr.data_ptr(), A.indices.data_ptr(), A.n) != self._pattern_key:
+            raise ValueError("resetup needs a matrix on the pattern the hierarchy was built for")
+        self._setup(A, symbolic=False)
+        # the new matrix brings its own values and SELL copy: level 0's operator descriptor is rebuilt, the coarser
+        # levels were refreshed in place
+        self._structs[0].lv.A, keep = self.levels[0].op.operator_struct()
+        self._keep.append(keep)
+        for i, lv in enumerate(self.levels):
+            self._structs[i].lv.omega = lv.omega
+        if self.W.on:
+            dist.barrier(group=self.W.group)
+
+    # ------------------------------------------------------------------------------------------ setup
+    def _setup(self, A: CSRMatrix, symbolic: bool) -> None:
+        W, dev, st = self.W, self.device, L.stream()
         self._A = A
-        st = L.stream()
+        self._pattern_key = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n)
         d, n_nod, node_ptr, adj = A._sell_struct.block
         op = BlockOperator(d, n_nod, n_nod, node_ptr, adj, A.values_, sell=A.sell())
-        lo, hi = int(own_lo_node), int(own_lo_node + n_owned_nodes)
-        plan = node_plan_from_halo_plan(node_plan, dev, W)
-        counts = W.all_gather_int(hi - lo, dev)
-        n_global = sum(counts)
-        self.level_sizes = [n_global * d]
-        self.d = d
-
+        lo, hi = self._own
+        plan = self._plan0
+        if symbolic:
+            self.d = d
+            self.level_sizes = [sum(W.all_gather_int(hi - lo, dev)) * d]
+        li = 0
         while True:
-            lv = _DLevel()
-            self.levels.append(lv)
-            li = len(self.levels) - 1
-            lv.op, lv.lo, lv.hi, lv.plan, lv.d, lv.n = op, lo, hi, plan, d, op.n_rows
-            nb = op.nbr
-            lv.dinv, lv.iso = _empty(lv.n, torch.float64, dev), _empty(lv.n, torch.uint8, dev)
+            if symbolic:
+                lv = _DLevel()
+                self.levels.append(lv)
+                lv.op, lv.lo, lv.hi, lv.plan, lv.d, lv.n = op, lo, hi, plan, d, op.n_rows
+                lv.dinv, lv.iso = _empty(lv.n, torch.float64, dev), _empty(lv.n, torch.uint8, dev)
+            else:
+                lv = self.levels[li]
+                if li == 0:
+                    lv.op = op
+                op, lo, hi, plan = lv.op, lv.lo, lv.hi, lv.plan
+            nb, n_own = op.nbr, hi - lo
             L.check(L.lib.tfem_amg_row_info(d, nb, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals), 1 if li > 0 else 0,
                                             L.ptr(lv.dinv), L.ptr(lv.iso), st))
             if li > 0:
@@ -258,179 +292,232 @@ class DistributedAMG:
             lv.rho = W.max_float(rho.value, dev) * _amg.RHO_SAFETY
             lv.omega = 4.0 / (3.0 * lv.rho)
 
-            # ---- aggregation on the owned subgraph
-            exclude = torch.ones(nb, dtype=torch.uint8, device=dev)
-            exclude[lo:hi] = 0
-            agg = _empty(nb, torch.int32, dev)
-            state, flag, index = _empty(nb, torch.int8, dev), _empty(nb, torch.uint8, dev), _empty(nb, torch.int32, dev)
-            n_agg, rounds = ctypes.c_int64(0), ctypes.c_int32(0)
-            for distance in (1, 2):
-                L.check(L.lib.tfem_amg_aggregate_masked(nb, L.ptr(op.bptr), L.ptr(op.bcol), distance, L.ptr(exclude),
-                                                        L.ptr(state), L.ptr(flag), L.ptr(index), L.ptr(agg),
-                                                        ctypes.byref(n_agg), ctypes.byref(rounds), st))
-                if (hi - lo) >= _amg.MIN_AGG_SIZE * n_agg.value:
-                    break
-            n_agg_r = int(n_agg.value)
-            aggs = W.all_gather_int(n_agg_r, dev)
-            offs = [0]
-            for a in aggs:
-                offs.append(offs[-1] + a)
-            n_agg_global = offs[-1]
-            if n_agg_global >= 2 ** 31 - 1:
-                raise RuntimeError("more than 2^31 aggregates")
-            c_off = offs[W.rank]
-            agg_g = torch.full((nb,), -1, dtype=torch.int64, device=dev)
-            agg_g[lo:hi] = agg[lo:hi].to(torch.int64) + c_off
-            plan.fill_halo(agg_g, W)                       # aggregate numbers of the halo nodes, from their owners
+            if symbolic:
+                self._aggregate(lv, op, plan, lo, hi)
             iso_nodes = lv.iso.view(nb, d).clone()
-            plan.fill_halo(iso_nodes, W)                   # and their isolated-DOF flags
+            plan.fill_halo(iso_nodes, W)                   # isolated-DOF flags of the halo nodes, from their owners
             iso_ext = iso_nodes.reshape(-1).contiguous()
-            # nodes of the local numbering that no owned row references (none in practice) keep agg -1 -> give them a
-            # valid dummy so that the kernels never index with -1
-            agg32 = torch.where(agg_g < 0, torch.zeros_like(agg_g), agg_g).to(torch.int32).contiguous()
 
             # ---- P rows of the owned nodes (global aggregate numbers as columns)
-            n_own = hi - lo
-            max_row = int((op.bptr[1:] - op.bptr[:-1]).max().item())
-            pptr = _empty(n_own + 1, torch.int64, dev)
-            L.check(L.lib.tfem_amg_prolongator_count_rows(d, lo, n_own, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(agg32),
-                                                          L.ptr(pptr), st))
-            npb = int(pptr[-1].item())
-            pcol = _empty(npb, torch.int32, dev)[:npb]
-            pval = _empty(d * d * npb, torch.float64, dev)[: d * d * npb]
+            if symbolic:
+                lv.max_row = int((op.bptr[1:] - op.bptr[:-1]).max().item())
+                lv.pptr = _empty(n_own + 1, torch.int64, dev)
+                L.check(L.lib.tfem_amg_prolongator_count_rows(d, lo, n_own, L.ptr(op.bptr), L.ptr(op.bcol),
+                                                              L.ptr(lv.agg32), L.ptr(lv.pptr), st))
+                npb = int(lv.pptr[-1].item())
+                lv.pcol = _empty(npb, torch.int32, dev)[:npb]
+                lv.pval = _empty(d * d * npb, torch.float64, dev)[: d * d * npb]
             L.check(L.lib.tfem_amg_prolongator_fill_rows(d, lo, n_own, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals),
-                                                         L.ptr(agg32), L.ptr(lv.dinv), L.ptr(iso_ext), lv.omega,
-                                                         L.ptr(pptr), L.ptr(pcol), L.ptr(pval), max_row, st))
-            # ---- P_ext: + the rows of the halo nodes from their owners; rows in local order = rank order
-            P_ext = self._extend_rows(plan, pptr, pcol.to(torch.int64), pval, d, lo, hi, nb, n_agg_global)
-            # ---- R = (P_ext[:, owned aggregates])^T
-            R_own = self._transpose_owned_columns(P_ext, c_off, n_agg_r)
+                                                         L.ptr(lv.agg32), L.ptr(lv.dinv), L.ptr(iso_ext), lv.omega,
+                                                         L.ptr(lv.pptr), L.ptr(lv.pcol), L.ptr(lv.pval), lv.max_row, st))
+            # ---- P_ext: + the rows of the halo nodes from their owners
+            if symbolic:
+                lv.P_ext, lv.p_exch = self._extend_rows(plan, lv.pptr, lv.pcol.to(torch.int64), lv.pval, d, lo, hi, nb,
+                                                        lv.n_agg_global)
+            else:
+                self._refresh_rows(plan, lv.p_exch, lv.pptr, lv.pval, d, lo, lv.P_ext)
+            # ---- R = rows of P_ext^T for the owned aggregates
+            if symbolic:
+                self._transpose_structure(lv)
+            R = lv.R_own
+            L.check(L.lib.tfem_amg_transpose_values(d, lv.n_c_compact, L.ptr(lv.Pc_bptr), L.ptr(lv.P_ext.vals),
+                                                    L.ptr(lv.t_ptr), L.ptr(lv.t_col), L.ptr(lv.t_src),
+                                                    L.ptr(lv.t_vals), st))
             # ---- W = A P_ext for the owned rows, + halo rows from the owners
             Aown = BlockOperator(d, n_own, nb, op.bptr[lo:hi + 1], op.bcol, op.vals)
-            Wown, _ = spgemm(d, Aown, P_ext)
-            W_ext = self._extend_rows(plan, Wown.bptr, Wown.bcol.to(torch.int64), Wown.vals, d, lo, hi, nb, n_agg_global)
+            if symbolic:
+                Wown, lv.w_structure = spgemm(d, Aown, lv.P_ext)
+                lv.W_ext, lv.w_exch = self._extend_rows(plan, Wown.bptr, Wown.bcol.to(torch.int64), Wown.vals, d, lo, hi,
+                                                        nb, lv.n_agg_global)
+                lv.w_ptr = Wown.bptr
+            else:
+                Wown, _ = spgemm(d, Aown, lv.P_ext, lv.w_structure)
+                self._refresh_rows(plan, lv.w_exch, lv.w_ptr, Wown.vals, d, lo, lv.W_ext)
             del Wown, Aown
             # ---- A_c rows of the owned aggregates, global columns
-            Ac, _ = spgemm(d, R_own, W_ext)
-            del W_ext
+            if symbolic:
+                Ac, lv.ac_structure = spgemm(d, R, lv.W_ext)
+                lv.gather = lv.n_agg_global * d <= self.gather_max or li + 1 >= MAX_DIST_LEVELS
+                self.level_sizes.append(lv.n_agg_global * d)
+                c_off, n_agg_r = lv.c_off, lv.n_agg_r
+                if lv.gather:
+                    # coarse index space = global numbering of the tail
+                    lv.c_lo, lv.c_hi, lv.n_c = c_off, c_off + n_agg_r, lv.n_agg_global
+                    lv.P = BlockOperator(d, nb, lv.n_agg_global, _frame_rows(lv.pptr, lo, nb), lv.pcol, lv.pval)
+                    lv.R = BlockOperator(d, lv.n_agg_global, nb, _frame_rows(R.bptr, c_off, lv.n_agg_global), R.bcol, R.vals)
+                    lv.Ac = Ac
+                    self._build_tail(lv, d)
+                    break
+                # ---- next level distributed: local numbering of the coarse nodes = sorted global ids that occur
+                uniq = torch.unique(Ac.bcol.to(torch.int64))
+                n_c = int(uniq.numel())
+                c_lo = int(torch.searchsorted(uniq, torch.tensor(c_off, device=dev)).item())
+                if not bool((uniq[c_lo:c_lo + n_agg_r] == torch.arange(c_off, c_off + n_agg_r, device=dev)).all()):
+                    raise RuntimeError("distributed AMG: an owned aggregate has no diagonal block")
+                lv.c_lo, lv.c_hi, lv.n_c = c_lo, c_lo + n_agg_r, n_c
+                to_local = lambda g: torch.searchsorted(uniq, g.to(torch.int64)).to(torch.int32)  # noqa: E731
+                lv.P = BlockOperator(d, nb, n_c, _frame_rows(lv.pptr, lo, nb), to_local(lv.pcol), lv.pval)
+                lv.R = BlockOperator(d, n_c, nb, _frame_rows(R.bptr, c_lo, n_c), R.bcol, R.vals)
+                lv.Ac = Ac
+                op = BlockOperator(d, n_c, n_c, _frame_rows(Ac.bptr, c_lo, n_c), to_local(Ac.bcol), Ac.vals)
+                plan = self._coarse_plan(uniq, lv, c_lo, n_agg_r, n_c)
+                lo, hi = c_lo, c_lo + n_agg_r
+            else:
+                spgemm(d, R, lv.W_ext, lv.ac_structure, out_vals=lv.Ac.vals)   # next level's operator, in place
+                if lv.gather:
+                    self._refresh_tail(lv, d)
+                    break
+            li += 1
+        if not symbolic:
+            for lv in self.levels:
+                lv.P.prepare(), lv.R.prepare()
 
-            gather = n_agg_global * d <= self.gather_max or li + 1 >= MAX_DIST_LEVELS
-            lv.n_agg_r, lv.c_off, lv.n_agg_global, lv.gather = n_agg_r, c_off, n_agg_global, gather
-            self.level_sizes.append(n_agg_global * d)
-            P_own_cols, P_own_ptr, P_own_vals = pcol, pptr, pval
-            if gather:
-                # coarse index space = global numbering of the tail
-                lv.c_lo, lv.c_hi, lv.n_c = c_off, c_off + n_agg_r, n_agg_global
-                lv.P = BlockOperator(d, nb, n_agg_global, _frame_rows(P_own_ptr, lo, nb), P_own_cols, P_own_vals)
-                lv.R = BlockOperator(d, n_agg_global, nb, _frame_rows(R_own.bptr, c_off, n_agg_global), R_own.bcol, R_own.vals)
-                self._build_tail(Ac, aggs, offs, d)
+    def _aggregate(self, lv, op, plan, lo, hi) -> None:
+        """Aggregation on the owned subgraph; global aggregate numbers for owned and halo nodes."""
+        W, dev, st = self.W, self.device, L.stream()
+        nb = op.nbr
+        exclude = torch.ones(nb, dtype=torch.uint8, device=dev)
+        exclude[lo:hi] = 0
+        agg = _empty(nb, torch.int32, dev)
+        state, flag, index = _empty(nb, torch.int8, dev), _empty(nb, torch.uint8, dev), _empty(nb, torch.int32, dev)
+        n_agg, rounds = ctypes.c_int64(0), ctypes.c_int32(0)
+        for distance in (1, 2):
+            L.check(L.lib.tfem_amg_aggregate_masked(nb, L.ptr(op.bptr), L.ptr(op.bcol), distance, L.ptr(exclude),
+                                                    L.ptr(state), L.ptr(flag), L.ptr(index), L.ptr(agg),
+                                                    ctypes.byref(n_agg), ctypes.byref(rounds), st))
+            if (hi - lo) >= _amg.MIN_AGG_SIZE * n_agg.value:
                 break
-            # ---- next level distributed: local numbering of the coarse nodes = sorted global ids that occur
-            uniq = torch.unique(Ac.bcol.to(torch.int64))
-            n_c = int(uniq.numel())
-            c_lo = int(torch.searchsorted(uniq, torch.tensor(c_off, device=dev)).item())
-            if not bool((uniq[c_lo:c_lo + n_agg_r] == torch.arange(c_off, c_off + n_agg_r, device=dev)).all()):
-                raise RuntimeError("distributed AMG: an owned aggregate has no diagonal block")
-            lv.c_lo, lv.c_hi, lv.n_c = c_lo, c_lo + n_agg_r, n_c
-            to_local = lambda g: torch.searchsorted(uniq, g.to(torch.int64)).to(torch.int32)  # noqa: E731
-            lv.P = BlockOperator(d, nb, n_c, _frame_rows(P_own_ptr, lo, nb), to_local(P_own_cols), P_own_vals)
-            lv.R = BlockOperator(d, n_c, nb, _frame_rows(R_own.bptr, c_lo, n_c), R_own.bcol, R_own.vals)
-            op = BlockOperator(d, n_c, n_c, _frame_rows(Ac.bptr, c_lo, n_c), to_local(Ac.bcol), Ac.vals)
-            # halo plan of the next level: which coarse nodes I need from whom / who needs mine
-            starts = torch.tensor(offs, device=dev)
-            halo_local = torch.cat([torch.arange(0, c_lo, device=dev), torch.arange(c_lo + n_agg_r, n_c, device=dev)])
-            halo_global = uniq[halo_local]
-            owner = torch.searchsorted(starts, halo_global, right=True) - 1
-            need = {int(s): halo_global[owner == s].cpu().numpy() for s in torch.unique(owner).tolist()}
-            gathered = W.all_gather_object(need)
-            send, recv = {}, {}
-            for s in range(W.size):
-                if s == W.rank:
-                    continue
-                theirs = gathered[s].get(W.rank) if gathered[s] else None
-                if theirs is not None and len(theirs):
-                    send[s] = torch.searchsorted(uniq, torch.as_tensor(theirs, device=dev))
-                if s in need and len(need[s]):
-                    recv[s] = torch.searchsorted(uniq, torch.as_tensor(need[s], device=dev))
-            plan = _NodePlan(send, recv, W)
-            lo, hi = c_lo, c_lo + n_agg_r
+        lv.n_agg_r = int(n_agg.value)
+        lv.aggs = W.all_gather_int(lv.n_agg_r, dev)
+        lv.offs = [0]
+        for a in lv.aggs:
+            lv.offs.append(lv.offs[-1] + a)
+        lv.n_agg_global = lv.offs[-1]
+        if lv.n_agg_global >= 2 ** 31 - 1:
+            raise RuntimeError("more than 2^31 aggregates")
+        lv.c_off = lv.offs[W.rank]
+        agg_g = torch.full((nb,), -1, dtype=torch.int64, device=dev)
+        agg_g[lo:hi] = agg[lo:hi].to(torch.int64) + lv.c_off
+        plan.fill_halo(agg_g, W)                       # aggregate numbers of the halo nodes, from their owners
+        # nodes of the local numbering that no owned row references keep -1: give them a valid number
+        lv.agg32 = torch.where(agg_g < 0, torch.zeros_like(agg_g), agg_g).to(torch.int32).contiguous()
 
-        self._allocate(comm)
+    def _coarse_plan(self, uniq, lv, c_lo, n_agg_r, n_c) -> _NodePlan:
+        """Halo plan of the next level: which coarse nodes I need from whom / who needs mine."""
+        W, dev = self.W, self.device
+        starts = torch.tensor(lv.offs, device=dev)
+        halo_local = torch.cat([torch.arange(0, c_lo, device=dev), torch.arange(c_lo + n_agg_r, n_c, device=dev)])
+        halo_global = uniq[halo_local]
+        owner = torch.searchsorted(starts, halo_global, right=True) - 1
+        need = {int(s): halo_global[owner == s].cpu().numpy() for s in torch.unique(owner).tolist()}
+        gathered = W.all_gather_object(need)
+        send, recv = {}, {}
+        for s in range(W.size):
+            if s == W.rank:
+                continue
+            theirs = gathered[s].get(W.rank) if gathered[s] else None
+            if theirs is not None and len(theirs):
+                send[s] = torch.searchsorted(uniq, torch.as_tensor(theirs, device=dev))
+            if s in need and len(need[s]):
+                recv[s] = torch.searchsorted(uniq, torch.as_tensor(need[s], device=dev))
+        return _NodePlan(send, recv, W)
 
     # ------------------------------------------------------------------------------------------ setup pieces
-    def _extend_rows(self, plan: _NodePlan, bptr_own, bcol_own_global, vals_own, d, lo, hi, nb, n_cols) -> BlockOperator:
+    def _extend_rows(self, plan: _NodePlan, bptr_own, bcol_own_global, vals_own, d, lo, hi, nb, n_cols):
         """Operator over all `nb` local rows: the owned rows as given + the rows of the halo nodes from their owners.
-        Local order = rank order (global ids are contiguous per rank), so the pieces are concatenated rank by rank."""
+        Local order = rank order (global ids are contiguous per rank), so the pieces are concatenated rank by rank.
+        Returns (operator, exchange record for the values-only refresh)."""
         W = self.W
         got = plan.exchange_rows(bptr_own, bcol_own_global, vals_own, d, lo, W)
         dev = vals_own.device
         lens_all = torch.zeros(nb, dtype=torch.int64, device=dev)
         lens_all[lo:hi] = bptr_own[1:] - bptr_own[:-1]
-        pieces = [(lo, bcol_own_global, vals_own)]
+        pieces = [(lo, None, bcol_own_global, vals_own)]
         for s, (lens, cols, vv) in got.items():
             nodes = plan.recv[s]
             rng = _as_range(nodes)
             if rng is None:
                 raise RuntimeError("distributed AMG: the halo nodes of a neighbour are not contiguous in the local numbering")
             lens_all[nodes] = lens
-            pieces.append((rng[0], cols, vv))
+            pieces.append((rng[0], s, cols, vv))
         pieces.sort(key=lambda p: p[0])
         bptr = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
         bptr[1:] = torch.cumsum(lens_all, 0)
-        bcol = torch.cat([p[1].to(torch.int64) for p in pieces]).to(torch.int32).contiguous()
-        vals = torch.cat([p[2] for p in pieces]).contiguous()
-        return BlockOperator(d, nb, n_cols, bptr, bcol, vals)
+        bcol = torch.cat([p[2].to(torch.int64) for p in pieces]).to(torch.int32).contiguous()
+        vals = torch.cat([p[3] for p in pieces]).contiguous()
+        # where each piece's values live in `vals` (for the values-only refresh), what to send (value index per peer)
+        at, place = 0, {}
+        for first_row, s, _, vv in pieces:
+            place[s] = (at, at + vv.numel())
+            at += vv.numel()
+        send_idx = {}
+        for s, nodes in plan.send.items():
+            rows = nodes - lo
+            rng = _as_range(rows)
+            if rng is not None:
+                send_idx[s] = (int(bptr_own[rng[0]]) * d * d, int(bptr_own[rng[1]]) * d * d)
+            else:
+                starts = bptr_own[rows]
+                send_idx[s] = _ragged(d * d * starts, d * d * (bptr_own[rows + 1] - starts))
+        return BlockOperator(d, nb, n_cols, bptr, bcol, vals), (place, send_idx)
 
-    def _transpose_owned_columns(self, P_ext: BlockOperator, c_off: int, n_agg_r: int) -> BlockOperator:
-        """(P_ext[:, c_off : c_off + n_agg_r])^T as a block operator [n_agg_r x nb] (K14 on the filtered blocks)."""
-        d, dev, st = P_ext.d, P_ext.vals.device, L.stream()
-        nb = P_ext.nbr
-        cnt = P_ext.bptr[1:] - P_ext.bptr[:-1]
-        row_of = torch.repeat_interleave(torch.arange(nb, device=dev), cnt)
-        keep = (P_ext.bcol >= c_off) & (P_ext.bcol < c_off + n_agg_r)
-        kidx = torch.nonzero(keep).ravel()
-        rows_k = row_of[kidx]
-        new_cnt = torch.bincount(rows_k, minlength=nb)
-        fptr = torch.zeros(nb + 1, dtype=torch.int64, device=dev)
-        fptr[1:] = torch.cumsum(new_cnt, 0)
-        fcol = (P_ext.bcol[kidx] - c_off).to(torch.int32).contiguous()
-        # values of the kept blocks in the layout of the filtered rows: (a, s', c) at d*d*fptr[I] + (a*m' + s')*d + c
-        s_old = kidx - P_ext.bptr[:-1][rows_k]
-        m_old = cnt[rows_k]
-        s_new = torch.arange(kidx.numel(), device=dev) - fptr[:-1][rows_k]
-        m_new = new_cnt[rows_k]
-        a = torch.arange(d, device=dev).view(1, d, 1)
-        c = torch.arange(d, device=dev).view(1, 1, d)
-        src = (d * d * P_ext.bptr[:-1][rows_k]).view(-1, 1, 1) + (a * m_old.view(-1, 1, 1) + s_old.view(-1, 1, 1)) * d + c
-        dst = (d * d * fptr[:-1][rows_k]).view(-1, 1, 1) + (a * m_new.view(-1, 1, 1) + s_new.view(-1, 1, 1)) * d + c
-        fvals = torch.empty(d * d * kidx.numel(), dtype=torch.float64, device=dev)
-        fvals[dst.reshape(-1)] = P_ext.vals[src.reshape(-1)]
-        del src, dst
-        npb = int(kidx.numel())
-        tptr = _empty(n_agg_r + 1, torch.int64, dev)
-        tcol, tsrc = _empty(npb, torch.int32, dev)[:npb], _empty(npb, torch.int32, dev)[:npb]
-        L.check(L.lib.tfem_amg_transpose_structure(nb, n_agg_r, L.ptr(fptr), L.ptr(fcol), npb, L.ptr(tptr), L.ptr(tcol),
-                                                   L.ptr(tsrc), st))
-        tvals = torch.empty_like(fvals)
-        L.check(L.lib.tfem_amg_transpose_values(d, n_agg_r, L.ptr(fptr), L.ptr(fvals), L.ptr(tptr), L.ptr(tcol),
-                                                L.ptr(tsrc), L.ptr(tvals), st))
-        return BlockOperator(d, n_agg_r, nb, tptr, tcol, tvals)
+    def _refresh_rows(self, plan: _NodePlan, record, bptr_own, vals_own, d, lo, ext: BlockOperator) -> None:
+        """Values-only version of `_extend_rows`: own values copied, halo rows' values received, all in place."""
+        place, send_idx = record
+        out = {}
+        for s, idx in send_idx.items():
+            out[s] = vals_own[idx[0]:idx[1]] if isinstance(idx, tuple) else vals_own[idx]
+        dev = vals_own.device
+        got = self.W.exchange(out, {s: (place[s][1] - place[s][0], torch.float64, dev) for s in plan.recv if s in place})
+        a, b = place[None]
+        ext.vals[a:b] = vals_own
+        for s, v in got.items():
+            a, b = place[s]
+            ext.vals[a:b] = v
 
-    def _build_tail(self, Ac: BlockOperator, aggs: list[int], offs: list[int], d: int) -> None:
+    def _transpose_structure(self, lv) -> None:
+        """Structure of R = rows of P_ext^T for the owned aggregates. The columns of P_ext are renumbered compactly
+        (owned aggregates first, the halo aggregates that occur after them) so that K14 transposes the whole operator
+        and the owned rows are simply the first n_agg_r rows of the result."""
+        P, dev, st = lv.P_ext, self.device, L.stream()
+        d, nb = P.d, P.nbr
+        col = P.bcol.to(torch.int64)
+        own = (col >= lv.c_off) & (col < lv.c_off + lv.n_agg_r)
+        halo_ids = torch.unique(col[~own])
+        compact = torch.where(own, col - lv.c_off, lv.n_agg_r + torch.searchsorted(halo_ids, col))
+        lv.n_c_compact = lv.n_agg_r + int(halo_ids.numel())
+        lv.Pc_bptr = P.bptr
+        pc_col = compact.to(torch.int32).contiguous()
+        npb = P.nblk
+        lv.t_ptr = _empty(lv.n_c_compact + 1, torch.int64, dev)
+        lv.t_col, lv.t_src = _empty(npb, torch.int32, dev)[:npb], _empty(npb, torch.int32, dev)[:npb]
+        L.check(L.lib.tfem_amg_transpose_structure(nb, lv.n_c_compact, L.ptr(P.bptr), L.ptr(pc_col), npb, L.ptr(lv.t_ptr),
+                                                   L.ptr(lv.t_col), L.ptr(lv.t_src), st))
+        lv.t_vals = torch.empty_like(P.vals)
+        n_r = int(lv.t_ptr[lv.n_agg_r].item())
+        lv.R_own = BlockOperator(d, lv.n_agg_r, nb, lv.t_ptr[:lv.n_agg_r + 1], lv.t_col[:n_r], lv.t_vals[:d * d * n_r])
+
+    def _build_tail(self, lv, d: int) -> None:
         """Gather the coarse operator (rows of the owned aggregates, global columns) to every rank and continue with the
         single-GPU hierarchy on it."""
         W, dev = self.W, self.device
+        Ac = lv.Ac
         lens = Ac.bptr[1:] - Ac.bptr[:-1]
-        nblk = W.all_gather_int(Ac.nblk, dev)
-        all_lens = W.broadcast_all(lens.contiguous(), aggs)
-        all_cols = W.broadcast_all(Ac.bcol.contiguous(), nblk)
-        all_vals = W.broadcast_all(Ac.vals.contiguous(), [n * d * d for n in nblk])
-        n = offs[-1]
+        lv.tail_nblk = W.all_gather_int(Ac.nblk, dev)
+        all_lens = W.broadcast_all(lens.contiguous(), lv.aggs)
+        all_cols = W.broadcast_all(Ac.bcol.contiguous(), lv.tail_nblk)
+        all_vals = W.broadcast_all(Ac.vals.contiguous(), [n * d * d for n in lv.tail_nblk])
+        n = lv.offs[-1]
         bptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         bptr[1:] = torch.cumsum(torch.cat(all_lens), 0)
-        op = BlockOperator(d, n, n, bptr, torch.cat(all_cols).contiguous(), torch.cat(all_vals).contiguous())
-        self.tail = AMGPreconditioner.from_operator(op, max_coarse=self.max_coarse)
-        self.level_sizes += [int(lv.n) for lv in self.tail.levels[1:]]
+        self.tail_op = BlockOperator(d, n, n, bptr, torch.cat(all_cols).contiguous(), torch.cat(all_vals).contiguous())
+        self.tail = AMGPreconditioner.from_operator(self.tail_op, max_coarse=self.max_coarse)
+        self.level_sizes += [int(t.n) for t in self.tail.levels[1:]]
+
+    def _refresh_tail(self, lv, d: int) -> None:
+        all_vals = self.W.broadcast_all(lv.Ac.vals.contiguous(), [n * d * d for n in lv.tail_nblk])
+        self.tail_op.vals.copy_(torch.cat(all_vals))
+        self.tail._setup(None, symbolic=False, op0=self.tail_op)
 
     def _allocate(self, comm: PeerComm | None) -> None:
         """Heap vectors (x, t of every distributed level, p, the gathered tail right-hand side) at equal offsets on all
