@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 METRIC = "DOFs solved/sec (assembly+PCG)"
 UNIT = "DOF/s"
 RTOL = 1e-8
-NCU_SPMV_DRAM_BYTES_CONFIG_B = 7233556000 + 85765120
+NCU_SPMV_DRAM_BYTES_CONFIG_B = 7233596000 + 85989632   # profiles/r2_x_cg_iteration_ncu.txt
 
 
 def measured_peaks():
@@ -459,9 +459,10 @@ def run_ours(args):
                      "peak_source": peak_src, "frac_of_spec_8000": achieved / 8000.0,
                      "algorithmic_bytes": int(spmv_bytes), "ms_per_launch": spmv_ms,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at config B from the committed
-                     # `ncu --set full` capture (profiles/r1_t_cg_iteration_ncu.txt); other sizes: not captured
+                     # `ncu --set full` capture (profiles/r2_x_cg_iteration_ncu.txt); other sizes: not captured
                      "traffic": NCU_SPMV_DRAM_BYTES_CONFIG_B if E == 150 else None,
-                     "traffic_source": "profiles/r1_t_cg_iteration_ncu.txt (k_sell_spmv<3,1>: 7.234 GB read + 0.086 GB written per launch)"},
+                     "traffic_source": "profiles/r2_x_cg_iteration_ncu.txt (k_sell_spmv<3,1>: 7.234 GB read + 0.086 GB written per launch, "
+                                       "1.116 ms under ncu; launch list of this command: profiles/r2_x_launches_bench_command.csv)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
@@ -799,7 +800,8 @@ def bench_distributed_amg(args, D, csr, pattern, A, rhs, M, mesh, plan, ranges, 
     out = {"call": "damg.DistributedAMG: rank-local aggregates, distributed Galerkin levels, V(1,1) + CG over peer memory",
            "setup_ms": setup_ms, "solve_ms": solve_ms, "iterations": st["iterations"],
            "ms_per_iteration": solve_ms / max(1, st["iterations"]), "true_rel_residual": res,
-           "levels": state["H"].level_sizes, "rel_diff_vs_jacobi_pcg_stol_1e-12": float((num[0] / num[1]).sqrt()),
+           "levels": state["H"].level_sizes, "setup_phases_ms_rank0": state["H"]._timing,
+           "rel_diff_vs_jacobi_pcg_stol_1e-12": float((num[0] / num[1]).sqrt()),
            "iterations_stol_1e-12": state["st"]["iterations"],
            "dofs_per_s_integrate_assemble_setup_solve": n_dofs_global / ((build_ms + setup_ms + solve_ms) * 1e-3)}
     state["H"].close()

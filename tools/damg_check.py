@@ -112,6 +112,7 @@ def main():
         x_a, st = H.solve(rhs, rtol=a.rtol)
         x_b, st2 = H.solve(rhs, rtol=a.rtol)
         case = {"gather_max": gather_max, "distributed_levels": len(H.levels), "levels": H.level_sizes,
+                "setup_phases_ms": H._timing,
                 "iterations": st["iterations"], "true_rel_residual": true_res(x_a),
                 "rel_diff_vs_jacobi_pcg": rel_diff(x_a, x_j), "bitwise_reproducible": bool(torch.equal(x_a[own], x_b[own])),
                 "launches": st["launches"]}

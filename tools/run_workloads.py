@@ -87,6 +87,13 @@ def topopt(T, N, method, stol):
             "bwd_s": t_bwd, "compliance": float(compliance), "grad_rho_norm": float(rho.grad.norm())}
 
 
+def neo_hooke_psi(F, params):
+    """Strain energy of benchmarks/hyperelasticity.py:24-30 — a module-level function there too."""
+    Cg = F.transpose(-1, -2) @ F
+    logJ = 0.5 * torch.logdet(Cg)
+    return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+
+
 def hyper(T, N, method, stol):
     from torchfem_b200.materials import Hyperelastic3D
     from torchfem_b200.mesh import cube_hexa
@@ -95,10 +102,7 @@ def hyper(T, N, method, stol):
     LBD = En * NU / ((1.0 + NU) * (1.0 - 2.0 * NU))
     MU = En / (2.0 * (1.0 + NU))
 
-    def psi(F, params):
-        Cg = F.transpose(-1, -2) @ F
-        logJ = 0.5 * torch.logdet(Cg)
-        return params[0] / 2 * (torch.trace(Cg) - 3.0) - params[0] * logJ + params[1] / 2 * logJ ** 2
+    psi = neo_hooke_psi
 
     lx = 4.0 / (N - 1)
     nodes, elements = cube_hexa(5, N, N, lx, 1.0, 1.0)

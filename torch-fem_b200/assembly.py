@@ -220,8 +220,15 @@ class _Elimination:
         self.Tt = _RectCSR.from_coo(cols, rows, vals, n_ret, n)
         self.T.transposed, self.Tt.transposed = self.Tt, self.T
         self.n = n
-        d = self.d = self._block_size(asm, retained) if allow_blocks else 1
+        self._asm, self._coo = asm, (rows, cols, vals)
+        self._build(self._block_size(asm, retained) if allow_blocks else 1)
 
+    def _build(self, d: int) -> None:
+        """Block-diagonal pattern of the part tangents and the operators T, T^T with d x d blocks (d = 1: scalar)."""
+        asm, dev = self._asm, self._asm.device
+        rows, cols, vals = self._coo
+        n, n_ret = self.n, self.n_retained
+        self.d = d
         ptr_parts, col_parts, self._segments = [], [], []
         nblk = 0
         for part, offset in zip(asm.parts, asm.offsets):
@@ -300,8 +307,17 @@ class _Elimination:
         vals = torch.cat([seg if seg is not None else K._values() for seg, K in zip(self._segments, blocks)])
         d = self.d
         Kop = BlockOperator(d, self.n // d, self.n // d, self.kptr, self.kcol, vals.contiguous())
-        KT, self._kt_struct = spgemm(d, Kop, self._Tb, structure=self._kt_struct)
-        A, self._a_struct = spgemm(d, self._Ttb, KT, structure=self._a_struct)
+        try:
+            KT, self._kt_struct = spgemm(d, Kop, self._Tb, structure=self._kt_struct)
+            A, self._a_struct = spgemm(d, self._Ttb, KT, structure=self._a_struct)
+        except L.TfemError as exc:
+            # a reference point coupled to thousands of nodes: its product row (3,723 blocks of 3 x 3 for a face of 3,721
+            # nodes) does not fit the SpGEMM's shared-memory accumulators with node blocks — scalar operators hold rows
+            # of up to ~12,000 entries
+            if exc.rc != L.ERR_CAPACITY or d == 1:
+                raise
+            self._build(1)
+            return self.reduced(blocks, con)
         if self._template is None:
             self._template = self._matrix(A)
         if self._mask_key != key:

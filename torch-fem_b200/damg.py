@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import time
 
 import numpy as np
 import torch
@@ -251,8 +252,21 @@ class DistributedAMG:
             dist.barrier(group=self.W.group)
 
     # ------------------------------------------------------------------------------------------ setup
+    def _tick(self, name: str) -> None:
+        """Per-phase wall times of the setup (TFEM_AMG_TIMING=1; synchronises; diagnostics only)."""
+        if self._timing is None:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        self._timing[name] = self._timing.get(name, 0.0) + (now - self._t_last) * 1e3
+        self._t_last = now
+
     def _setup(self, A: CSRMatrix, symbolic: bool) -> None:
         W, dev, st = self.W, self.device, L.stream()
+        self._timing = {} if os.environ.get("TFEM_AMG_TIMING") else None
+        if self._timing is not None:
+            torch.cuda.synchronize()
+            self._t_last = time.perf_counter()
         self._A = A
         self._pattern_key = (A.indptr.data_ptr(), A.indices.data_ptr(), A.n)
         d, n_nod, node_ptr, adj = A._sell_struct.block
@@ -291,9 +305,11 @@ class DistributedAMG:
             del work, okeep, dmask
             lv.rho = W.max_float(rho.value, dev) * _amg.RHO_SAFETY
             lv.omega = 4.0 / (3.0 * lv.rho)
+            self._tick("row_info+rho")
 
             if symbolic:
                 self._aggregate(lv, op, plan, lo, hi)
+                self._tick("aggregate")
             iso_nodes = lv.iso.view(nb, d).clone()
             plan.fill_halo(iso_nodes, W)                   # isolated-DOF flags of the halo nodes, from their owners
             iso_ext = iso_nodes.reshape(-1).contiguous()
@@ -310,12 +326,14 @@ class DistributedAMG:
             L.check(L.lib.tfem_amg_prolongator_fill_rows(d, lo, n_own, L.ptr(op.bptr), L.ptr(op.bcol), L.ptr(op.vals),
                                                          L.ptr(lv.agg32), L.ptr(lv.dinv), L.ptr(iso_ext), lv.omega,
                                                          L.ptr(lv.pptr), L.ptr(lv.pcol), L.ptr(lv.pval), lv.max_row, st))
+            self._tick("P rows")
             # ---- P_ext: + the rows of the halo nodes from their owners
             if symbolic:
                 lv.P_ext, lv.p_exch = self._extend_rows(plan, lv.pptr, lv.pcol.to(torch.int64), lv.pval, d, lo, hi, nb,
                                                         lv.n_agg_global)
             else:
                 self._refresh_rows(plan, lv.p_exch, lv.pptr, lv.pval, d, lo, lv.P_ext)
+            self._tick("P halo rows")
             # ---- R = rows of P_ext^T for the owned aggregates
             if symbolic:
                 self._transpose_structure(lv)
@@ -323,6 +341,7 @@ class DistributedAMG:
             L.check(L.lib.tfem_amg_transpose_values(d, lv.n_c_compact, L.ptr(lv.Pc_bptr), L.ptr(lv.P_ext.vals),
                                                     L.ptr(lv.t_ptr), L.ptr(lv.t_col), L.ptr(lv.t_src),
                                                     L.ptr(lv.t_vals), st))
+            self._tick("R")
             # ---- W = A P_ext for the owned rows, + halo rows from the owners
             Aown = BlockOperator(d, n_own, nb, op.bptr[lo:hi + 1], op.bcol, op.vals)
             if symbolic:
@@ -334,6 +353,7 @@ class DistributedAMG:
                 Wown, _ = spgemm(d, Aown, lv.P_ext, lv.w_structure)
                 self._refresh_rows(plan, lv.w_exch, lv.w_ptr, Wown.vals, d, lo, lv.W_ext)
             del Wown, Aown
+            self._tick("A*P + halo rows")
             # ---- A_c rows of the owned aggregates, global columns
             if symbolic:
                 Ac, lv.ac_structure = spgemm(d, R, lv.W_ext)
@@ -346,7 +366,9 @@ class DistributedAMG:
                     lv.P = BlockOperator(d, nb, lv.n_agg_global, _frame_rows(lv.pptr, lo, nb), lv.pcol, lv.pval)
                     lv.R = BlockOperator(d, lv.n_agg_global, nb, _frame_rows(R.bptr, c_off, lv.n_agg_global), R.bcol, R.vals)
                     lv.Ac = Ac
+                    self._tick("R*(AP)")
                     self._build_tail(lv, d)
+                    self._tick("tail")
                     break
                 # ---- next level distributed: local numbering of the coarse nodes = sorted global ids that occur
                 uniq = torch.unique(Ac.bcol.to(torch.int64))
@@ -362,10 +384,13 @@ class DistributedAMG:
                 op = BlockOperator(d, n_c, n_c, _frame_rows(Ac.bptr, c_lo, n_c), to_local(Ac.bcol), Ac.vals)
                 plan = self._coarse_plan(uniq, lv, c_lo, n_agg_r, n_c)
                 lo, hi = c_lo, c_lo + n_agg_r
+                self._tick("R*(AP) + coarse numbering")
             else:
                 spgemm(d, R, lv.W_ext, lv.ac_structure, out_vals=lv.Ac.vals)   # next level's operator, in place
+                self._tick("R*(AP)")
                 if lv.gather:
                     self._refresh_tail(lv, d)
+                    self._tick("tail")
                     break
             li += 1
         if not symbolic:
