@@ -1,13 +1,10 @@
 #!/bin/bash
-TAG=${1:-dbg}
+TAG=${1:-dbg}; N=${2:-2}
 mkdir -p gpurun_out
-timeout 300 python tools/run_workloads.py --method cg --cube 0 --topopt 0 > gpurun_out/${TAG}_hyper_cg_graph.jsonl 2> gpurun_out/${TAG}_hyper.err; cat gpurun_out/${TAG}_hyper_cg_graph.jsonl
-TFEM_MATERIAL_GRAPH=0 timeout 300 python tools/run_workloads.py --method cg --cube 0 --topopt 0 > gpurun_out/${TAG}_hyper_cg_nograph.jsonl 2>> gpurun_out/${TAG}_hyper.err; cat gpurun_out/${TAG}_hyper_cg_nograph.jsonl
-timeout 300 python tools/run_workloads.py --method amgx --cube 0 --topopt 0 > gpurun_out/${TAG}_hyper_amgx.jsonl 2>> gpurun_out/${TAG}_hyper.err; cat gpurun_out/${TAG}_hyper_amgx.jsonl
-TFEM_MATERIAL_GRAPH=0 timeout 300 python tools/run_workloads.py --method amgx --cube 0 --topopt 0 > gpurun_out/${TAG}_hyper_amgx_nograph.jsonl 2>> gpurun_out/${TAG}_hyper.err; cat gpurun_out/${TAG}_hyper_amgx_nograph.jsonl
-tail -3 gpurun_out/${TAG}_hyper.err
-timeout 300 python tools/assembly_check.py --nodes 61 --method cg --cases point > gpurun_out/${TAG}_assembly_point.jsonl 2> gpurun_out/${TAG}_assembly_point.err; cat gpurun_out/${TAG}_assembly_point.jsonl; tail -3 gpurun_out/${TAG}_assembly_point.err
-TFEM_AMG_TIMING=1 timeout 300 python tools/damg_check.py --edge 100 > gpurun_out/${TAG}_damg_w1_e100.log 2>&1; echo "damg world1 e100 rc=$?"
-tail -3 gpurun_out/${TAG}_damg_w1_e100.log | cut -c1-3000
-timeout 300 python -m pytest tests/test_gpu_assembly.py tests/test_gpu_models.py -x -q -m gpu 2>&1 | tail -3
-bash tools/gpu_k2.sh > gpurun_out/${TAG}_k2.log 2>&1; cat gpurun_out/${TAG}_k2.log
+RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 300 $RUN --master-port 29521 tools/damg_check.py --edge 16 > gpurun_out/${TAG}_damg.log 2>&1; echo "damg rc=$?"
+grep "^{" gpurun_out/${TAG}_damg.log | tail -1 | cut -c1-2500
+TFEM_AMG_TIMING=1 timeout 600 $RUN --master-port 29513 bench.py --gpus $N --steps 2 --warmup 2 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json
+grep "TfemError\|Error" gpurun_out/${TAG}_bench.err | tail -3
+timeout 300 python tools/prof_hyper.py > gpurun_out/${TAG}_hyper_profile.txt 2>&1; head -50 gpurun_out/${TAG}_hyper_profile.txt | cut -c1-200

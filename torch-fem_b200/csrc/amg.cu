@@ -689,18 +689,17 @@ __global__ void __launch_bounds__(kSellWarps * 32, MINB)
 template <int DPN, int MODE, bool DOT>
 int launch_amg_spmv_t(const Sell& A, const double* x, double* y, const double* b, const double* dinv, double omega,
                       double* partials, unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  static int g = 0;  // per instantiation
   // 8 CTAs per SM (32 registers; the epilogue-heavy variants spill ~80 bytes outside the streaming loop) beat 6 CTAs
   // with 40 registers: 5.92 -> 5.55 ms per AMG-PCG iteration at config B. TFEM_AMG_OCC6=1 selects the latter.
   static const bool occ6 = getenv("TFEM_AMG_OCC6") && atoi(getenv("TFEM_AMG_OCC6")) != 0;
   const int64_t n_sl = (A.slice_hi < 0 ? A.n_slices : A.slice_hi) - A.slice_lo;
   const int64_t want = n_sl > 0 ? (n_sl + kSellWarps - 1) / kSellWarps : 1;
   if (occ6) {
-    if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT, 6>, kSellWarps * 32);
+    const int g = cached_resident_ctas(k_amg_spmv<DPN, MODE, DOT, 6>, kSellWarps * 32);
     k_amg_spmv<DPN, MODE, DOT, 6><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
                                                                                          partials, ticket, out_scalar);
   } else {
-    if (!g) g = resident_ctas(k_amg_spmv<DPN, MODE, DOT>, kSellWarps * 32);
+    const int g = cached_resident_ctas(k_amg_spmv<DPN, MODE, DOT>, kSellWarps * 32);  // per instantiation and device
     k_amg_spmv<DPN, MODE, DOT><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, x, y, b, dinv, omega,
                                                                                       partials, ticket, out_scalar);
   }
@@ -1204,12 +1203,10 @@ static int prolongator_launch(int d, int64_t nb, const int64_t* bptr, const int3
   const int stage_cap = FILL ? (max_row < 8 ? 8 : (max_row > kStageMax ? kStageMax : max_row)) : 0;
   const size_t stage = FILL ? (size_t)4 * stage_cap * d * d * sizeof(double) : 0;
   if (FILL) {
-    static bool attr_set[4] = {false, false, false, false};
-    if (!attr_set[d]) {
+    {  // (set on every call: the attribute is per device and costs nothing)
       if (d == 3) TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<3, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       else if (d == 2) TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<2, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
       else TFEM_CUDA(cudaFuncSetAttribute(k_prolongator<1, FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      attr_set[d] = true;
     }
   }
   if (d == 3) k_prolongator<3, FILL><<<grid, 128, stage, st>>>(nb, bptr, bcol, vals, agg, dinv, iso, omega, pcount, pptr, pcol, pvals, err, stage_cap, row0);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "tfem_b200.h"
 
@@ -37,27 +38,32 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 constexpr int kSMs = 148;  // B200: 2 dies x 74 SMs
 
-inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = kSMs;
-  }
-  return sms;
+inline int num_sms() {  // cached per device (a process may drive several)
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kSMs;
+  dev &= 63;
+  if (sms[dev] == 0 &&
+      (cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms[dev] <= 0))
+    sms[dev] = kSMs;
+  return sms[dev];
 }
 
 // Stream-ordered scratch allocations come from the device's default memory pool. Its default release threshold is 0:
 // every stream synchronisation hands unused pool memory back to the driver and the next allocation maps it again
-// (measured: stalls of 10-300 ms inside setup calls that allocate a 4-byte flag). Keep the pool's memory instead.
+// (measured: stalls of 10-300 ms inside setup calls that allocate a 4-byte flag). Keep the pool's memory instead —
+// once per device. This changes a process-wide setting of the CUDA default pool (INTEGRATION.md says so);
+// TFEM_KEEP_POOL=0 leaves the pool alone.
 inline void keep_pool_memory() {
-  static bool done = false;
-  if (done) return;
-  done = true;
+  static bool done[64] = {};
   int dev = 0;
   cudaMemPool_t pool;
-  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (done[dev & 63]) return;
+  done[dev & 63] = true;
+  const char* off = getenv("TFEM_KEEP_POOL");
+  if (off && off[0] == '0') return;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
   uint64_t threshold = UINT64_MAX;
   cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
 }

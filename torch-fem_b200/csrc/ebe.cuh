@@ -102,8 +102,7 @@ __global__ void k_ebe_diag(Ebe A, double* __restrict__ diag) {
 template <int DPN, bool DOT>
 int launch_ebe_t(const Ebe& A, const double* x, double* y, const double* sc, double* partials,
                  unsigned int* ticket, double* out_scalar, cudaStream_t st) {
-  static int g = 0;
-  if (!g) g = resident_ctas(k_ebe_spmv<DPN, DOT>, kEbeWarps * 32);
+  const int g = cached_resident_ctas(k_ebe_spmv<DPN, DOT>, kEbeWarps * 32);  // per instantiation and device
   const int64_t want = (A.n_nod + kEbeWarps - 1) / kEbeWarps;
   k_ebe_spmv<DPN, DOT><<<(int)(want < g ? want : g), kEbeWarps * 32, 0, st>>>(A, x, y, sc, partials, ticket, out_scalar);
   TFEM_LAUNCH_CHECK();
