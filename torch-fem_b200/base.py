@@ -359,8 +359,15 @@ class FEM(ABC):
 
     def _integrate_k_raw(self, tangent: Tensor) -> Tensor:
         bref, w = self._tables()
-        return _csr.integrate_k(self.KIND, bref, w, self.nodes.detach(), self.elements,
-                                tangent.detach().to(torch.float64), self._k_scale)
+        # det J depends on the mesh only: once a kernel has seen this geometry with all Jacobians positive, K1's flag
+        # need not be read back again (a host synchronisation per Newton iteration otherwise)
+        ok = getattr(self, "_k1_validated", None)
+        check = not self._cache_valid(ok)
+        k = _csr.integrate_k(self.KIND, bref, w, self.nodes.detach(), self.elements,
+                             tangent.detach().to(torch.float64), self._k_scale, check=check)
+        if check and not self.nodes.requires_grad:
+            self._k1_validated = (self._cache_key(),)
+        return k
 
     def compute_B(self) -> Tensor:
         """Rigid-body modes (near null space for AMG back ends; unused by Jacobi but part of the

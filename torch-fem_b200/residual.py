@@ -33,11 +33,18 @@ class Geometry:
         self.n_elem = int(elements.shape[0])
         self.dpn = int(dpn)
         self.flag = torch.zeros(1, dtype=torch.int32, device=nodes.device)
+        self.validated = False
 
     def check(self):
+        """Raise the reference's error if a kernel met det J <= 0 (base.py:311-312). The Jacobians depend on the mesh
+        only, so one clean evaluation validates this geometry for good: later calls skip the device read-back (a host
+        synchronisation per residual evaluation otherwise)."""
+        if self.validated:
+            return
         if int(self.flag.item()) != 0:
             self.flag.zero_()
             raise ValueError("Negative Jacobian. Check element numbering.")
+        self.validated = True
 
 
 def _grad(g: Geometry, u_e: Tensor, weighted: bool) -> Tensor:
