@@ -107,7 +107,7 @@ def main():
     out = {"world": world, "edge": E, "hexa2": a.hexa2, "n_dofs_global": int(allsum(torch.tensor([n_owned], device=dev)).item()),
            "iters_jacobi": info_j["iterations"], "cases": []}
     ok = True
-    for gather_max in (damg.GATHER_MAX_DOFS, 600):
+    for gather_max in (400_000, 600):
         H = damg.DistributedAMG(A, mesh.lo, mesh.n_owned, mesh.global_nodes, node_plan, gather_max=gather_max)
         x_a, st = H.solve(rhs, rtol=a.rtol)
         x_b, st2 = H.solve(rhs, rtol=a.rtol)

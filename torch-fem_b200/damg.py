@@ -16,7 +16,7 @@ Algorithm (the single-GPU one, `oracle/amg_oracle.py`, with ONE change: aggregat
   triple product, no approximation at the interfaces (filtering the interface couplings out of the smoother instead
   costs +35 % iterations on 2 slabs and more on 8: tools/damg_proto.py);
 * a level whose global size is below `gather_max` unknowns is gathered to every rank and continued redundantly with the
-  single-GPU hierarchy (`amg.AMGPreconditioner.from_operator`): at 8 x 10 M DOFs that is level 2 (0.3 M unknowns);
+  single-GPU hierarchy (`amg.AMGPreconditioner.from_operator`): at 8 x 10 M DOFs that is level 3 (9 k unknowns);
 * the cycle and the CG run in ONE C call (`tfem_damg_pcg_solve`): halo entries are stored straight into the
   neighbours' vectors over NVLink, dot products are LL-protocol all-reduces (csrc/peer.cuh); NCCL is used by the SETUP
   only (row exchanges, sizes).
@@ -40,8 +40,10 @@ from .amg import AMGPreconditioner, BlockOperator, _empty, spgemm
 from .csr import CSRMatrix
 from .distributed import HaloPlan, PeerComm, _as_range
 
-# a level with at most this many unknowns (global) is gathered and solved redundantly (TFEM_DAMG_GATHER_MAX: experiments)
-GATHER_MAX_DOFS = int(os.environ.get("TFEM_DAMG_GATHER_MAX", 400_000))
+# a level with at most this many unknowns (global) is gathered and solved redundantly (TFEM_DAMG_GATHER_MAX: experiments).
+# Measured on 8 B200 at 81.8 M DOFs: 400 k (a 317 k-unknown tail solved redundantly) 6.98 ms per iteration, 100 k (that
+# level distributed too, tail 9 k) 5.98 ms (profiles/r2_f8_*).
+GATHER_MAX_DOFS = int(os.environ.get("TFEM_DAMG_GATHER_MAX", 100_000))
 MAX_DIST_LEVELS = 4
 
 
