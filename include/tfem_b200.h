@@ -160,6 +160,20 @@ int tfem_assemble_bc(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr_dev
                      const double* k_dev, const uint8_t* is_con_dev, const double* ubc_dev, double* vals_dev,
                      double* lift_dev, void* stream);
 
+/* The same, writing what the Krylov solve consumes in the same pass (the CSR -> SELL copy of tfem_sell_fill and
+ * tfem_jacobi_setup become part of the assembly: 13 GB less traffic per step at BASELINE configs[1]):
+ * slice_ptr_dev : int64 [ceil(n_dofs/32)+1], tfem_sell_slice_ptr of the same pattern (no long rows)
+ * sell_vals_dev : double [slice_ptr[last]] out or NULL — the values in SELL-32 order (`tfem_sell_t.vals`), padding
+ *                 entries and the rows past n_dofs of the last slice written as 0.0; bitwise equal to
+ *                 tfem_sell_fill(vals_dev)
+ * dinv_dev      : double [n_dofs] out or NULL — 1 / diagonal after the masking (== tfem_jacobi_setup)
+ * vals_dev      : CSR values out, or NULL when only the solver's copy is wanted (one of the two must be given) */
+int tfem_assemble_solve(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr_dev, const int32_t* adj_dev,
+                        const int64_t* indptr_dev, const int64_t* src_ptr_dev, const int32_t* src_dev,
+                        const double* k_dev, const uint8_t* is_con_dev, const double* ubc_dev, double* vals_dev,
+                        double* lift_dev, const int64_t* slice_ptr_dev, double* sell_vals_dev, double* dinv_dev,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * K5 — CSR SpMV y = A x (fp64 values, int32 columns, int64 row offsets).  Replaces cusparseSpMV inside
  * cupy_cg / cupy_minres (sparse.py:411,419). Algorithmic bytes: 12*nnz + 20*n_rows.

@@ -93,7 +93,9 @@ def _worker(rank, world, port, out):
 def test_node_plan_halo_fill_and_row_exchange_world2():
     world = 2
     port = _free_port()
-    with mp.Manager() as m:
+    # a spawned manager (see tests/test_distributed_cpu.py): forking this process once BLAS / OpenMP thread pools exist
+    # leaves later LAPACK calls of the same pytest process hanging
+    with mp.get_context("spawn").Manager() as m:
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert sorted(out.keys()) == [0, 1]

@@ -136,6 +136,49 @@ def test_assemble(T, tag):
     assert np.all(got[is_con.astype(bool)] == 0.0)
 
 
+@pytest.mark.parametrize("tag", MECH_CASES + HEAT_CASES)
+def test_assemble_writes_solver_order(T, tag):
+    """The assembly's SELL-32 values and 1/diagonal == the CSR -> SELL copy and the Jacobi setup of its CSR values,
+    bit for bit (padding and the rows past the last one written as 0), with and without the CSR output."""
+    c = load_case(f"case_{tag}.npz")
+    dpn = 1 if tag.startswith("heat") else c["nodes"].shape[1]
+    n_dofs = dpn * c["nodes"].shape[0]
+    p = build_pattern(T, c, dpn)
+    is_con = np.zeros(n_dofs, dtype=np.uint8)
+    is_con[c["con"]] = 1
+    k = dev(c["k"])
+    vals = T.csr.assemble(p, k, dev(is_con))
+    A = p.matrix(vals)
+    want_sell = A.sell()                      # tfem_sell_fill of the CSR values
+    want = A._sell_vals.cpu().numpy()
+    want_dinv = T.csr.JacobiPreconditioner(A).dinv.cpu().numpy()
+    st = p.sell_structure
+    for csr_too in (True, False):
+        sv = torch.full((max(st.padded, 2),), np.nan, dtype=torch.float64, device="cuda")
+        dinv = torch.full((n_dofs,), np.nan, dtype=torch.float64, device="cuda")
+        v, sv2, dinv2 = T.csr.assemble(p, k, dev(is_con), csr=csr_too, sell_out=sv, dinv_out=dinv)
+        assert sv2 is sv and dinv2 is dinv
+        assert (v is None) == (not csr_too)
+        if csr_too:
+            assert torch.equal(v, vals)
+        assert np.array_equal(sv.cpu().numpy()[: st.padded], want[: st.padded])
+        assert np.array_equal(dinv.cpu().numpy(), want_dinv)
+    # the solver-only matrix: same product, same Krylov solve, bit for bit
+    rng = np.random.default_rng(5)
+    _, sv, dinv = T.csr.assemble(p, k, dev(is_con), csr=False, sell_out=True, dinv_out=True)
+    S = p.matrix(None, sell_vals=sv)
+    xv = dev(rng.standard_normal(n_dofs))
+    assert torch.equal(S.matvec(xv), A.matvec(xv, fmt="sell"))
+    if tag == "hexa1":
+        b = dev(rng.standard_normal(n_dofs) * (1 - is_con))
+        x_ref, _, info_ref = T.csr.krylov_solve(A, b, rtol=1e-10)
+        x, _, info = T.csr.krylov_solve(S, b, rtol=1e-10, M=T.csr.JacobiPreconditioner(dinv=dinv))
+        assert info["iterations"] == info_ref["iterations"] and torch.equal(x, x_ref)
+    with pytest.raises(ValueError, match="assembled for the solver only"):
+        S.values_
+    del want_sell
+
+
 @pytest.mark.parametrize("tag", ["hexa1", "tetra2", "quad2", "heat_hexa1", "hexa1_orphan"])
 def test_assemble_rhs_deterministic_gather(T, tag):
     """a9 `assemble_rhs` (reference base.py:428-445) on the gather kernel: equals the oracle's index_add to round-off,

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "tfem_assemble_rhs": (c_int, [c_int64, c_int] + [c_void_p] * 5),
     "tfem_assemble": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 9),
     "tfem_assemble_bc": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 11),
+    "tfem_assemble_solve": (c_int, [c_int64, c_int, c_int] + [c_void_p] * 14),
     "tfem_spmv_num_chunks": (c_int64, [c_int64]),
     "tfem_spmv_plan": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "tfem_spmv": (c_int, [c_int64, c_int64] + [c_void_p] * 7),

@@ -80,6 +80,9 @@ def _det_inv(J: Tensor) -> tuple[Tensor, Tensor]:
     return det, inv
 
 
+_SOLVER_ORDER_MIN_DOFS = 10_000   # = sparse.DIRECT_LIMIT: below it `sparse_solve` factorises and no SELL copy is read
+
+
 class _IntegrateK(torch.autograd.Function):
     """k_e = sum_q w_q detJ_q s_e B_q^T C B_q (kernel K1) with the adjoint contraction for the tangent:
     dL/dC[e,i,J,k,L] = sum_q w detJ s sum_{p,r} B_q[J,p] B_q[L,r] dL/dk[e,(p,i),(r,k)]  (mechanics, base.py:1088),
@@ -509,9 +512,14 @@ class FEM(ABC):
         is_con = torch.zeros(self.n_dofs, dtype=torch.bool, device=self.device)
         is_con[con.to(self.device)] = True
         self.is_constrained = is_con
-        vals = _csr.assemble(self.pattern, k.detach().to(torch.float64),
-                             is_con.to(torch.uint8) if con.numel() else None)
-        return self.pattern.matrix(vals, symmetric=bool(getattr(self.material, "symmetric_tangent", True)))
+        symmetric = bool(getattr(self.material, "symmetric_tangent", True))
+        mask = is_con.to(torch.uint8) if con.numel() else None
+        if self.n_dofs >= _SOLVER_ORDER_MIN_DOFS and self.pattern.sell_structure.long_rows is None:
+            # systems the iterative solvers take: the same pass also writes the values in their SELL-32 order
+            vals, sell_vals, _ = _csr.assemble(self.pattern, k.detach().to(torch.float64), mask, sell_out=True)
+            return self.pattern.matrix(vals, symmetric=symmetric, sell_vals=sell_vals)
+        vals = _csr.assemble(self.pattern, k.detach().to(torch.float64), mask)
+        return self.pattern.matrix(vals, symmetric=symmetric)
 
     def assemble_rhs(self, f: Tensor) -> Tensor:
         """Global vector from element vectors; differentiable (reference base.py:428-445). A deterministic gather

@@ -119,11 +119,14 @@ class Pattern:
             self._sell = sell_structure(self.indptr, self.indices, self.n_dofs, block)
         return self._sell
 
-    def matrix(self, values: Tensor, symmetric: bool = True) -> "CSRMatrix":
-        """Wrap CSR values living on this pattern."""
-        return CSRMatrix(self.indptr, self.indices, values, self.n_dofs, chunk_rows=self.chunk_rows,
-                         diag_pos=self.diag_pos, symmetric=symmetric, sell_struct=self.sell_structure,
-                         coo_indices=self._glob_idx)
+    def matrix(self, values: Tensor | None, symmetric: bool = True, sell_vals: Tensor | None = None) -> "CSRMatrix":
+        """Wrap CSR values living on this pattern. `sell_vals`: the same values in the solver's SELL-32 order when the
+        assembly wrote them (`assemble(..., sell_out=)`); `values=None` is a matrix that exists for the solver only."""
+        A = CSRMatrix(self.indptr, self.indices, values, self.n_dofs, chunk_rows=self.chunk_rows,
+                      diag_pos=self.diag_pos, symmetric=symmetric, sell_struct=self.sell_structure,
+                      coo_indices=self._glob_idx)
+        A._sell_vals = sell_vals
+        return A
 
 
 class SellStructure:
@@ -249,12 +252,14 @@ class CSRMatrix:
 
     def __init__(self, indptr: Tensor, indices: Tensor, values: Tensor, n: int, *, chunk_rows=None,
                  diag_pos=None, symmetric=False, coo_indices=None, sell_struct=None):
-        L.require_cuda(indptr, indices, values)
-        if values.dtype != torch.float64:
-            raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
-        self.indptr, self.indices, self.values_ = indptr, indices, values
+        L.require_cuda(indptr, indices)
+        if values is not None:
+            L.require_cuda(values)
+            if values.dtype != torch.float64:
+                raise TypeError("torch-fem_b200 computes in float64 only (the reference runs in float64)")
+        self.indptr, self.indices, self._values_csr = indptr, indices, values
         self.n = int(n)
-        self.nnz = int(values.shape[0])
+        self.nnz = int(indices.shape[0])
         self.symmetric = symmetric
         self.chunk_rows = chunk_rows if chunk_rows is not None else spmv_plan(indptr, self.n, self.nnz)
         self._diag_pos = diag_pos
@@ -263,6 +268,17 @@ class CSRMatrix:
         self._sell_struct = sell_struct
         self._sell_vals = None
         self._sell_mats = {}
+
+    @property
+    def values_(self) -> Tensor:
+        if self._values_csr is None:
+            raise ValueError("this matrix was assembled for the solver only (SELL-32 values); "
+                             "assemble with csr=True for its CSR values")
+        return self._values_csr
+
+    @values_.setter
+    def values_(self, v):
+        self._values_csr = v
 
     # ---- torch-sparse look-alike surface used by the reference's callers
     @property
@@ -278,11 +294,11 @@ class CSRMatrix:
 
     @property
     def device(self):
-        return self.values_.device
+        return self.indptr.device
 
     @property
     def dtype(self):
-        return self.values_.dtype
+        return torch.float64
 
     @property
     def is_cuda(self):
@@ -368,7 +384,7 @@ class CSRMatrix:
             self._sell_vals = sv
         key = bool(block and st.block is not None)
         if self._sell_mats.get(key) is None:
-            self._sell_mats[key] = SellMatrix(st, self._sell_vals, use_block=key, csr_vals=self.values_)
+            self._sell_mats[key] = SellMatrix(st, self._sell_vals, use_block=key, csr_vals=self._values_csr)
         return self._sell_mats[key]
 
     def matvec(self, x: Tensor, out: Tensor | None = None, fmt: str = "auto") -> Tensor:
@@ -494,10 +510,16 @@ def integrate_k(kind: int, bref: Tensor, w: Tensor, nodes: Tensor, elements: Ten
 
 
 def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | None = None,
-             ubc: Tensor | None = None, lift: Tensor | None = None) -> Tensor:
+             ubc: Tensor | None = None, lift: Tensor | None = None, *, csr: bool = True,
+             sell_out: Tensor | bool | None = None, dinv_out: Tensor | bool | None = None):
     """CSR values from element matrices with kernel K2/K3 (deterministic; Dirichlet rows/cols fused).
     With `ubc` (prescribed values, [n_dofs]) and `lift` ([n_dofs] out) the kernel also returns the Dirichlet
-    lifting K[free, con] @ ubc[con] (the right-hand side of the first Newton step, base.py:708-741)."""
+    lifting K[free, con] @ ubc[con] (the right-hand side of the first Newton step, base.py:708-741).
+
+    `sell_out` / `dinv_out` (a tensor, or True to allocate): the same pass also writes the values in the solver's
+    SELL-32 order and 1/diagonal, so that neither the CSR -> SELL copy nor the Jacobi setup runs afterwards;
+    `csr=False` skips the CSR values. Returns the CSR values, or (vals | None, sell_vals | None, dinv | None) when one
+    of the solver outputs was asked for."""
     L.require_cuda(k)
     nd = pattern.nn * pattern.dpn
     if k.dtype != torch.float64:
@@ -507,17 +529,41 @@ def assemble(pattern: Pattern, k: Tensor, is_con: Tensor | None, out: Tensor | N
     k = k.contiguous()
     if is_con is not None:
         is_con = is_con.to(torch.uint8).contiguous() if is_con.dtype != torch.uint8 else is_con.contiguous()
-    vals = out if out is not None else torch.empty(pattern.nnz, dtype=torch.float64, device=k.device)
+    solver_outputs = (sell_out is not None and sell_out is not False) or (dinv_out is not None and dinv_out is not False)
+    if not csr and not solver_outputs:
+        raise ValueError("assemble: nothing to write (csr=False needs sell_out)")
+    vals = None
+    if csr:
+        vals = out if out is not None else torch.empty(pattern.nnz, dtype=torch.float64, device=k.device)
     if lift is not None:
         if is_con is None or ubc is None:
             raise ValueError("the Dirichlet lifting needs is_con and ubc")
         L.require_cuda(ubc, lift)
         ubc = ubc.to(torch.float64).contiguous()
-    L.check(L.lib.tfem_assemble_bc(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
-                                   L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
-                                   L.ptr(pattern.src), L.ptr(k), L.ptr(is_con),
-                                   L.ptr(ubc) if lift is not None else None, L.ptr(vals), L.ptr(lift), L.stream()))
-    return vals
+    if not solver_outputs:
+        L.check(L.lib.tfem_assemble_bc(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
+                                       L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
+                                       L.ptr(pattern.src), L.ptr(k), L.ptr(is_con),
+                                       L.ptr(ubc) if lift is not None else None, L.ptr(vals), L.ptr(lift), L.stream()))
+        return vals
+    st = pattern.sell_structure
+    sv = dinv = None
+    if sell_out is not None and sell_out is not False:
+        if st.long_rows is not None:
+            raise ValueError("assemble: patterns with long rows keep their values in CSR order (SELL side path)")
+        sv = sell_out if isinstance(sell_out, Tensor) else torch.empty(max(st.padded, 2), dtype=torch.float64,
+                                                                       device=k.device)
+        if sv.dtype != torch.float64 or sv.numel() < st.padded or not sv.is_contiguous():
+            raise ValueError(f"sell_out must be a contiguous float64 tensor of at least {st.padded} entries")
+    if dinv_out is not None and dinv_out is not False:
+        dinv = dinv_out if isinstance(dinv_out, Tensor) else torch.empty(pattern.n_dofs, dtype=torch.float64,
+                                                                         device=k.device)
+    L.check(L.lib.tfem_assemble_solve(pattern.n_nod, pattern.nn, pattern.dpn, L.ptr(pattern.node_ptr),
+                                      L.ptr(pattern.adj), L.ptr(pattern.indptr), L.ptr(pattern.src_ptr),
+                                      L.ptr(pattern.src), L.ptr(k), L.ptr(is_con),
+                                      L.ptr(ubc) if lift is not None else None, L.ptr(vals), L.ptr(lift),
+                                      L.ptr(st.slice_ptr), L.ptr(sv), L.ptr(dinv), L.stream()))
+    return vals, sv, dinv
 
 
 class _AssembleRhs(torch.autograd.Function):
@@ -600,7 +646,11 @@ class JacobiPreconditioner:
     """M = diag(A)^-1 (reference GPU path: `cupy_diags(1.0 / A_cp.diagonal())`, sparse.py:408-409).
     Returned by `sparse_solve` as `M` and accepted back, like the reference's preconditioner object."""
 
-    def __init__(self, A):
+    def __init__(self, A=None, dinv: Tensor | None = None):
+        if dinv is not None:   # written by the assembly (`assemble(..., dinv_out=)`)
+            self.dinv = dinv
+            self.shape = (dinv.shape[0], dinv.shape[0])
+            return
         if isinstance(A, ElementOperator):
             self.dinv = 1.0 / A.diagonal()
         else:

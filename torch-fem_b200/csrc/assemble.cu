@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(kWarps * 32)
                const int32_t* __restrict__ adj, const int64_t* __restrict__ indptr,
                const int64_t* __restrict__ src_ptr, const int32_t* __restrict__ src,
                const double* __restrict__ k, const uint8_t* __restrict__ is_con,
-               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift) {
+               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift,
+               const int64_t* __restrict__ slice_ptr, double* __restrict__ sell_vals, double* __restrict__ dinv) {
   const int nn = NN > 0 ? NN : nn_rt;
   const int lane = threadIdx.x & 31;
   const int64_t node = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
@@ -40,10 +41,40 @@ __global__ void __launch_bounds__(kWarps * 32)
   const int64_t nb = node_ptr[node];
   const int cnt = (int)(node_ptr[node + 1] - nb);
   const int64_t row0 = node * DPN;
+  // SELL-32 position of entry k of row r: slice_ptr[r / 32] + (k / 2) * 64 + (r % 32) * 2 + (k % 2)   (sell.cuh)
+  int64_t sbase[DPN];
+  int sw[DPN];
+  if (sell_vals) {
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) {
+      const int64_t r = row0 + i, s0 = slice_ptr[r >> 5];
+      sbase[i] = s0 + (r & 31) * 2;
+      sw[i] = (int)((slice_ptr[(r >> 5) + 1] - s0) >> 5);
+    }
+    if (node == n_nod - 1) {  // the rows past the end of the last slice
+      const int64_t n_rows = n_nod * DPN, r_end = (n_rows + 31) & ~(int64_t)31;
+      for (int64_t r = n_rows; r < r_end; ++r)
+        for (int k = lane; k < sw[DPN - 1]; k += 32) sell_vals[slice_ptr[r >> 5] + (k >> 1) * 64 + (r & 31) * 2 + (k & 1)] = 0.0;
+    }
+  }
+  auto sell_pad = [&](int len) {  // zero entries [len, width) of my rows
+#pragma unroll
+    for (int i = 0; i < DPN; ++i)
+      for (int k = len + lane; k < sw[i]; k += 32) sell_vals[sbase[i] + (k >> 1) * 64 + (k & 1)] = 0.0;
+  };
   if (cnt == 0) {  // unreferenced node: lone diagonal, value 0 unless constrained (base.py:419)
     if (lane < DPN) {
-      vals[indptr[row0 + lane]] = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
+      const double d = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
+      if (vals) vals[indptr[row0 + lane]] = d;
       if (lift) lift[row0 + lane] = 0.0;
+      if (dinv) dinv[row0 + lane] = 1.0 / d;
+    }
+    if (sell_vals) {
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < DPN; ++i) sell_vals[sbase[i]] = (is_con && is_con[row0 + i]) ? 1.0 : 0.0;
+      }
+      sell_pad(1);
     }
     return;
   }
@@ -55,7 +86,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 #pragma unroll
   for (int i = 0; i < DPN; ++i) {
     row_con[i] = is_con && is_con[row0 + i];
-    rp[i] = indptr[row0 + i];
+    rp[i] = vals ? indptr[row0 + i] : 0;
     lsum[i] = 0.0;
   }
   for (int p = lane; p < cnt; p += 32) {
@@ -104,10 +135,16 @@ __global__ void __launch_bounds__(kWarps * 32)
         // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
         if (lift && col_con && !row_con[i]) lsum[i] = fma(a, uc, lsum[i]);
         if (row_con[i] || col_con) a = (col == row0 + i) ? 1.0 : 0.0;
-        vals[rp[i] + (int64_t)p * DPN + j] = a;
+        if (vals) vals[rp[i] + (int64_t)p * DPN + j] = a;
+        if (sell_vals) {
+          const int kk = p * DPN + j;
+          sell_vals[sbase[i] + (kk >> 1) * 64 + (kk & 1)] = a;
+        }
+        if (dinv && col == row0 + i) dinv[row0 + i] = 1.0 / a;
       }
     }
   }
+  if (sell_vals) sell_pad(cnt * DPN);
   if (lift) {
 #pragma unroll
     for (int i = 0; i < DPN; ++i) {
@@ -120,11 +157,12 @@ __global__ void __launch_bounds__(kWarps * 32)
 template <int DPN>
 int launch_assemble(int64_t n_nod, int nn, const int64_t* node_ptr, const int32_t* adj, const int64_t* indptr,
                     const int64_t* src_ptr, const int32_t* src, const double* k, const uint8_t* is_con,
-                    const double* ubc, double* vals, double* lift, cudaStream_t st) {
+                    const double* ubc, double* vals, double* lift, const int64_t* slice_ptr, double* sell_vals,
+                    double* dinv, cudaStream_t st) {
   const unsigned grid = (unsigned)((n_nod + kWarps - 1) / kWarps);
 #define TFEM_ASM(NNC)                                                                                        \
   k_assemble<DPN, NNC><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, \
-                                                     ubc, vals, lift)
+                                                     ubc, vals, lift, slice_ptr, sell_vals, dinv)
   switch (nn) {
     case 3: TFEM_ASM(3); break;
     case 4: TFEM_ASM(4); break;
@@ -144,22 +182,40 @@ int launch_assemble(int64_t n_nod, int nn, const int64_t* node_ptr, const int32_
 
 using namespace tfem;
 
+extern "C" int tfem_assemble_solve(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
+                                   const int64_t* indptr, const int64_t* src_ptr, const int32_t* src,
+                                   const double* k, const uint8_t* is_con, const double* ubc, double* vals,
+                                   double* lift, const int64_t* slice_ptr, double* sell_vals, double* dinv,
+                                   void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  TFEM_REQUIRE(node_ptr && adj && indptr && src_ptr && src && k, "assemble: null pointer");
+  TFEM_REQUIRE(vals || sell_vals, "assemble: no output (CSR values, SELL values or both)");
+  TFEM_REQUIRE(!sell_vals || slice_ptr, "assemble: SELL values need the slice offsets of tfem_sell_slice_ptr");
+  TFEM_REQUIRE(n_nod > 0 && nn > 0, "assemble: bad sizes");
+  TFEM_REQUIRE(!lift || (is_con && ubc), "assemble: the Dirichlet lifting needs is_con and the prescribed values");
+  switch (dpn) {
+    case 1:
+      return launch_assemble<1>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, slice_ptr,
+                                sell_vals, dinv, st);
+    case 2:
+      return launch_assemble<2>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, slice_ptr,
+                                sell_vals, dinv, st);
+    case 3:
+      return launch_assemble<3>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, slice_ptr,
+                                sell_vals, dinv, st);
+  }
+  set_last_error("invalid argument", "assemble: dofs per node must be 1, 2 or 3");
+  return TFEM_ERR_INVALID;
+}
+
 extern "C" int tfem_assemble_bc(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
                                 const int64_t* indptr, const int64_t* src_ptr, const int32_t* src,
                                 const double* k, const uint8_t* is_con, const double* ubc, double* vals,
                                 double* lift, void* stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
-  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
-  TFEM_REQUIRE(node_ptr && adj && indptr && src_ptr && src && k && vals, "assemble: null pointer");
-  TFEM_REQUIRE(n_nod > 0 && nn > 0, "assemble: bad sizes");
-  TFEM_REQUIRE(!lift || (is_con && ubc), "assemble: the Dirichlet lifting needs is_con and the prescribed values");
-  switch (dpn) {
-    case 1: return launch_assemble<1>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
-    case 2: return launch_assemble<2>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
-    case 3: return launch_assemble<3>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, st);
-  }
-  set_last_error("invalid argument", "assemble: dofs per node must be 1, 2 or 3");
-  return TFEM_ERR_INVALID;
+  TFEM_REQUIRE(vals, "assemble: null pointer");
+  return tfem_assemble_solve(n_nod, nn, dpn, node_ptr, adj, indptr, src_ptr, src, k, is_con, ubc, vals, lift, nullptr,
+                             nullptr, nullptr, stream_);
 }
 
 extern "C" int tfem_assemble(int64_t n_nod, int nn, int dpn, const int64_t* node_ptr, const int32_t* adj,
