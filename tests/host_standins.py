@@ -62,6 +62,9 @@ class HostMatrix:
         r, c = self._indices()
         return torch.zeros(self.n, dtype=torch.float64).index_add_(0, r, self.values_ * x[c])
 
+    def matmat(self, X):
+        return torch.stack([self.matvec(X[:, j]) for j in range(X.shape[1])], dim=1)
+
     def dense(self):
         r, c = self._indices()
         out = np.zeros((self.n, self.n))

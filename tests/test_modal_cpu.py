@@ -17,6 +17,9 @@ class _ScipyOperator:
     def matvec(self, x, fmt=None):
         return torch.from_numpy(self.A @ x.numpy())
 
+    def matmat(self, X):
+        return torch.from_numpy(self.A @ X.numpy())
+
 
 def test_lobpcg_with_amg_preconditioner_matches_shift_invert_lanczos():
     from torchfem_b200.modal import lobpcg

@@ -36,6 +36,14 @@ def ev(fn, reps=5):
 
 k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
 vals = torch.empty(p.nnz, device=dev)
-print("integrate_k %.3f ms   assemble %.3f ms" % (
-    ev(lambda: csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)),
-    ev(lambda: csr.assemble(p, k, is_con, out=vals))))
+sv = torch.empty(p.sell_structure.padded, device=dev)
+dinv = torch.empty(p.n_dofs, device=dev)
+A = p.matrix(vals)
+print("integrate_k %.3f ms   assemble %.3f ms   assemble in solver order (SELL-32 + 1/diag, no CSR) %.3f ms   "
+      "both orders %.3f ms   CSR + 1/diag by the solver-order kernel %.3f ms   CSR -> SELL copy %.3f ms" % (
+          ev(lambda: csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)),
+          ev(lambda: csr.assemble(p, k, is_con, out=vals)),
+          ev(lambda: csr.assemble(p, k, is_con, csr=False, sell_out=sv, dinv_out=dinv)),
+          ev(lambda: csr.assemble(p, k, is_con, out=vals, sell_out=sv, dinv_out=dinv)),
+          ev(lambda: csr.assemble(p, k, is_con, out=vals, dinv_out=dinv)),
+          ev(lambda: (setattr(A, "_sell_vals", None), A._sell_mats.clear(), A.sell()))))

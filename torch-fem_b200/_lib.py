@@ -121,6 +121,7 @@ _SIGNATURES = {
     "tfem_sell_fill_capped": (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64] + [c_void_p] * 4),
     "tfem_sell_fill_rect": (c_int, [c_int64, c_int64] + [c_void_p] * 7),
     "tfem_sell_spmv": (c_int, [_SELL_P, c_void_p, c_void_p, c_void_p]),
+    "tfem_sell_spmm": (c_int, [_SELL_P, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "tfem_amg_row_info": (c_int, [c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_work_doubles": (c_int64, [c_int64]),
     "tfem_amg_rho": (c_int, [ctypes.POINTER(AmgOperatorStruct), c_void_p, c_int, c_void_p, ctypes.POINTER(c_double),

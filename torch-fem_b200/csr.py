@@ -405,6 +405,36 @@ class CSRMatrix:
                                     L.stream()))
         return y
 
+    def matmat(self, X: Tensor, out: Tensor | None = None) -> Tensor:
+        """Y = A X for a block of vectors X [n, m] (row-major) with the multi-vector SELL kernel: the matrix is read once
+        per 8 columns. Each column equals `matvec(X[:, j], fmt="sell")` bit for bit."""
+        L.require_cuda(X)
+        if X.dtype != torch.float64 or X.dim() != 2 or X.shape[0] != self.n:
+            raise ValueError("matmat expects a float64 block of shape [n, m]")
+        X = X.contiguous()
+        m = int(X.shape[1])
+        Y = out if out is not None else torch.empty_like(X)
+        if Y.shape != X.shape or not Y.is_contiguous() or Y.data_ptr() == X.data_ptr():
+            raise ValueError("matmat: `out` must be a separate contiguous block of X's shape")
+        S = self.sell()
+        if m == 0:
+            return Y
+        if S.struct.n_long > 0:   # long rows live on the single-vector side path
+            for j in range(m):
+                Y[:, j] = self.matvec(X[:, j].contiguous(), fmt="sell")
+            return Y
+        if m <= 8:
+            L.check(L.lib.tfem_sell_spmm(S.ref, m, L.ptr(X), m, L.ptr(Y), m, L.stream()))
+            return Y
+        # wider blocks: 8 columns at a time, packed (a gathered row of X must be one or two full sectors; with the
+        # leading dimension of a wide block the product is slower than single products)
+        for j0 in range(0, m, 8):
+            Xc = X[:, j0:j0 + 8].contiguous()
+            Yc = torch.empty_like(Xc)
+            L.check(L.lib.tfem_sell_spmm(S.ref, Xc.shape[1], L.ptr(Xc), Xc.shape[1], L.ptr(Yc), Xc.shape[1], L.stream()))
+            Y[:, j0:j0 + 8] = Yc
+        return Y
+
     def __matmul__(self, x: Tensor) -> Tensor:
         """A @ x, differentiable w.r.t. x (the reference's `self.M @ du` on a sparse COO tensor, base.py:1483)."""
         shape = x.shape

@@ -19,6 +19,9 @@ constexpr int kWarps = 8;
 #ifndef TFEM_K2_INFLIGHT
 #define TFEM_K2_INFLIGHT 2
 #endif
+#ifndef TFEM_K2_SOLVER_MINB
+#define TFEM_K2_SOLVER_MINB 4  // resident CTAs the solver-order instantiation must allow (64 registers)
+#endif
 constexpr int kInFlight = TFEM_K2_INFLIGHT;  // contributions whose loads are issued before the first is added
 
 // NN = nodes per element as a compile-time constant (0: run-time value) so the slot decoding needs no
@@ -32,8 +35,7 @@ __global__ void __launch_bounds__(kWarps * 32)
                const int32_t* __restrict__ adj, const int64_t* __restrict__ indptr,
                const int64_t* __restrict__ src_ptr, const int32_t* __restrict__ src,
                const double* __restrict__ k, const uint8_t* __restrict__ is_con,
-               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift,
-               const int64_t* __restrict__ slice_ptr, double* __restrict__ sell_vals, double* __restrict__ dinv) {
+               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift) {
   const int nn = NN > 0 ? NN : nn_rt;
   const int lane = threadIdx.x & 31;
   const int64_t node = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
@@ -41,40 +43,10 @@ __global__ void __launch_bounds__(kWarps * 32)
   const int64_t nb = node_ptr[node];
   const int cnt = (int)(node_ptr[node + 1] - nb);
   const int64_t row0 = node * DPN;
-  // SELL-32 position of entry k of row r: slice_ptr[r / 32] + (k / 2) * 64 + (r % 32) * 2 + (k % 2)   (sell.cuh)
-  int64_t sbase[DPN];
-  int sw[DPN];
-  if (sell_vals) {
-#pragma unroll
-    for (int i = 0; i < DPN; ++i) {
-      const int64_t r = row0 + i, s0 = slice_ptr[r >> 5];
-      sbase[i] = s0 + (r & 31) * 2;
-      sw[i] = (int)((slice_ptr[(r >> 5) + 1] - s0) >> 5);
-    }
-    if (node == n_nod - 1) {  // the rows past the end of the last slice
-      const int64_t n_rows = n_nod * DPN, r_end = (n_rows + 31) & ~(int64_t)31;
-      for (int64_t r = n_rows; r < r_end; ++r)
-        for (int k = lane; k < sw[DPN - 1]; k += 32) sell_vals[slice_ptr[r >> 5] + (k >> 1) * 64 + (r & 31) * 2 + (k & 1)] = 0.0;
-    }
-  }
-  auto sell_pad = [&](int len) {  // zero entries [len, width) of my rows
-#pragma unroll
-    for (int i = 0; i < DPN; ++i)
-      for (int k = len + lane; k < sw[i]; k += 32) sell_vals[sbase[i] + (k >> 1) * 64 + (k & 1)] = 0.0;
-  };
   if (cnt == 0) {  // unreferenced node: lone diagonal, value 0 unless constrained (base.py:419)
     if (lane < DPN) {
-      const double d = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
-      if (vals) vals[indptr[row0 + lane]] = d;
+      vals[indptr[row0 + lane]] = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
       if (lift) lift[row0 + lane] = 0.0;
-      if (dinv) dinv[row0 + lane] = 1.0 / d;
-    }
-    if (sell_vals) {
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < DPN; ++i) sell_vals[sbase[i]] = (is_con && is_con[row0 + i]) ? 1.0 : 0.0;
-      }
-      sell_pad(1);
     }
     return;
   }
@@ -86,7 +58,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 #pragma unroll
   for (int i = 0; i < DPN; ++i) {
     row_con[i] = is_con && is_con[row0 + i];
-    rp[i] = vals ? indptr[row0 + i] : 0;
+    rp[i] = indptr[row0 + i];
     lsum[i] = 0.0;
   }
   for (int p = lane; p < cnt; p += 32) {
@@ -135,16 +107,161 @@ __global__ void __launch_bounds__(kWarps * 32)
         // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
         if (lift && col_con && !row_con[i]) lsum[i] = fma(a, uc, lsum[i]);
         if (row_con[i] || col_con) a = (col == row0 + i) ? 1.0 : 0.0;
-        if (vals) vals[rp[i] + (int64_t)p * DPN + j] = a;
-        if (sell_vals) {
-          const int kk = p * DPN + j;
-          sell_vals[sbase[i] + (kk >> 1) * 64 + (kk & 1)] = a;
-        }
-        if (dinv && col == row0 + i) dinv[row0 + i] = 1.0 / a;
+        vals[rp[i] + (int64_t)p * DPN + j] = a;
       }
     }
   }
-  if (sell_vals) sell_pad(cnt * DPN);
+  if (lift) {
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) {
+      const double t = warp_sum(lsum[i]);
+      if (lane == 0) lift[row0 + i] = t;
+    }
+  }
+}
+
+// The same, also (or only) writing the values in the solver's SELL-32 order and 1/diagonal. A separate kernel: with the
+// extra outputs compiled into k_assemble the CSR-only path went from 6.5 to 9.3 ms at config B.
+template <int DPN, int NN>
+__global__ void __launch_bounds__(kWarps * 32, TFEM_K2_SOLVER_MINB)
+    k_assemble_solver(int64_t n_nod, int nn_rt, const int64_t* __restrict__ node_ptr,
+               const int32_t* __restrict__ adj, const int64_t* __restrict__ indptr,
+               const int64_t* __restrict__ src_ptr, const int32_t* __restrict__ src,
+               const double* __restrict__ k, const uint8_t* __restrict__ is_con,
+               const double* __restrict__ ubc, double* __restrict__ vals, double* __restrict__ lift,
+               const int64_t* __restrict__ slice_ptr, double* __restrict__ sell_vals, double* __restrict__ dinv) {
+  const int nn = NN > 0 ? NN : nn_rt;
+  const int lane = threadIdx.x & 31;
+  const int64_t node = blockIdx.x * (int64_t)kWarps + (threadIdx.x >> 5);
+  if (node >= n_nod) return;
+  const int64_t nb = node_ptr[node];
+  const int cnt = (int)(node_ptr[node + 1] - nb);
+  const int64_t row0 = node * DPN;
+  // SELL-32 position of entry k of row r: slice_ptr[r / 32] + (k / 2) * 64 + (r % 32) * 2 + (k % 2)   (sell.cuh)
+  auto sell_base = [&](int64_t r) { return slice_ptr[r >> 5] + (r & 31) * 2; };
+  auto sell_pad = [&](int len) {  // zero entries [len, width) of my rows
+#pragma unroll
+    for (int i = 0; i < DPN; ++i) {
+      const int64_t r = row0 + i, s0 = slice_ptr[r >> 5];
+      const int width = (int)((slice_ptr[(r >> 5) + 1] - s0) >> 5);
+      for (int k = len + lane; k < width; k += 32) sell_vals[s0 + (r & 31) * 2 + (k >> 1) * 64 + (k & 1)] = 0.0;
+    }
+  };
+  if (sell_vals && node == n_nod - 1) {  // the rows past the end of the last slice
+    const int64_t n_rows = n_nod * DPN, r_end = (n_rows + 31) & ~(int64_t)31;
+    for (int64_t r = n_rows; r < r_end; ++r) {
+      const int64_t s0 = slice_ptr[r >> 5];
+      const int width = (int)((slice_ptr[(r >> 5) + 1] - s0) >> 5);
+      for (int k = lane; k < width; k += 32) sell_vals[s0 + (r & 31) * 2 + (k >> 1) * 64 + (k & 1)] = 0.0;
+    }
+  }
+  if (cnt == 0) {  // unreferenced node: lone diagonal, value 0 unless constrained (base.py:419)
+    if (lane < DPN) {
+      const double d = (is_con && is_con[row0 + lane]) ? 1.0 : 0.0;
+      if (vals) vals[indptr[row0 + lane]] = d;
+      if (lift) lift[row0 + lane] = 0.0;
+      if (dinv) dinv[row0 + lane] = 1.0 / d;
+      if (sell_vals) sell_vals[sell_base(row0 + lane)] = d;
+    }
+    if (sell_vals) sell_pad(1);
+    return;
+  }
+  const int nd = nn * DPN;
+  const int64_t nd2 = (int64_t)nd * nd;
+  bool row_con[DPN];
+  int64_t rp[DPN];
+  double lsum[DPN];
+#pragma unroll
+  for (int i = 0; i < DPN; ++i) {
+    row_con[i] = is_con && is_con[row0 + i];
+    rp[i] = vals ? indptr[row0 + i] : 0;
+    lsum[i] = 0.0;
+  }
+  // The SELL-32 values leave through shared memory: a lane owns the 3 consecutive entries of a node block, but in the
+  // slice two consecutive entries of ONE row are adjacent (16 B) and the node's rows follow each other, so the warp
+  // regroups a round of 32 blocks into (entry pair, row) items and writes 48-byte runs instead of scattered 8-byte words
+  // (8.8 -> 7.x ms at config B; written straight from the block registers the kernel is slower than the CSR order plus
+  // the copy it is meant to replace).
+  __shared__ __align__(16) double s_stage[kWarps][DPN][32 * DPN];
+  __shared__ int64_t s_sbase[kWarps][DPN];
+  const int warp = threadIdx.x >> 5;
+  if (sell_vals && lane < DPN) s_sbase[warp][lane] = sell_base(row0 + lane);
+  for (int p0 = 0; p0 < cnt; p0 += 32) {
+    const int p = p0 + lane;
+    const bool mine = p < cnt;
+    double acc[DPN][DPN];
+#pragma unroll
+    for (int i = 0; i < DPN; ++i)
+#pragma unroll
+      for (int j = 0; j < DPN; ++j) acc[i][j] = 0.0;
+    if (mine) {
+      const int64_t sb = src_ptr[nb + p], se = src_ptr[nb + p + 1];
+      for (int64_t s = sb; s < se; s += kInFlight) {
+        const double* kb[kInFlight];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+          const int cc = (s + u < se) ? src[s + u] : -1;  // e*nn*nn + a*nn + b
+          if (cc < 0) {
+            kb[u] = nullptr;
+          } else {
+            const int ea = cc / nn, bq = cc - ea * nn;
+            const int e = ea / nn, aq = ea - e * nn;
+            kb[u] = k + e * nd2 + (int64_t)(aq * DPN) * nd + bq * DPN;
+          }
+        }
+        double v[kInFlight][DPN][DPN];
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)
+#pragma unroll
+          for (int i = 0; i < DPN; ++i)
+#pragma unroll
+            for (int j = 0; j < DPN; ++j) v[u][i][j] = kb[u] ? kb[u][i * nd + j] : 0.0;
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u)  // + 0.0 for the missing ones: exact; slot order kept
+#pragma unroll
+          for (int i = 0; i < DPN; ++i)
+#pragma unroll
+            for (int j = 0; j < DPN; ++j) acc[i][j] += v[u][i][j];
+      }
+      const int64_t col0 = (int64_t)adj[nb + p] * DPN;
+#pragma unroll
+      for (int j = 0; j < DPN; ++j) {
+        const int64_t col = col0 + j;
+        const bool col_con = is_con && is_con[col];
+        const double uc = (lift && col_con) ? ubc[col] : 0.0;
+#pragma unroll
+        for (int i = 0; i < DPN; ++i) {
+          double a = acc[i][j];
+          // Dirichlet lifting: what the prescribed values contribute to the free rows, K[row, con] u[con]
+          if (lift && col_con && !row_con[i]) lsum[i] = fma(a, uc, lsum[i]);
+          if (row_con[i] || col_con) a = (col == row0 + i) ? 1.0 : 0.0;
+          if (vals) vals[rp[i] + (int64_t)p * DPN + j] = a;
+          acc[i][j] = a;
+        }
+      }
+      if (dinv && col0 == row0) {  // the lane of the diagonal block: 1 / diagonal after the masking
+#pragma unroll
+        for (int i = 0; i < DPN; ++i) dinv[row0 + i] = 1.0 / acc[i][i];
+      }
+    }
+    if (sell_vals) {
+#pragma unroll
+      for (int i = 0; i < DPN; ++i)
+#pragma unroll
+        for (int j = 0; j < DPN; ++j) s_stage[warp][i][lane * DPN + j] = acc[i][j];  // 0.0 beyond the last block
+      __syncwarp();
+      const int ne = (cnt - p0 < 32 ? cnt - p0 : 32) * DPN;  // entries of this round, per row
+      const int n_items = ((ne + 1) >> 1) * DPN;             // (entry pair, row); an odd tail pairs with a 0.0
+      const int64_t pair0 = ((int64_t)p0 * DPN) >> 1;         // p0 * DPN is even (p0 = 0, 32, ...)
+      for (int item = lane; item < n_items; item += 32) {
+        const int sp = item / DPN, i = item - sp * DPN;
+        const double2 v2 = *reinterpret_cast<const double2*>(&s_stage[warp][i][2 * sp]);
+        *reinterpret_cast<double2*>(sell_vals + s_sbase[warp][i] + (pair0 + sp) * 64) = v2;
+      }
+      __syncwarp();
+    }
+  }
+  if (sell_vals) sell_pad((cnt * DPN + 1) & ~1);
   if (lift) {
 #pragma unroll
     for (int i = 0; i < DPN; ++i) {
@@ -160,9 +277,13 @@ int launch_assemble(int64_t n_nod, int nn, const int64_t* node_ptr, const int32_
                     const double* ubc, double* vals, double* lift, const int64_t* slice_ptr, double* sell_vals,
                     double* dinv, cudaStream_t st) {
   const unsigned grid = (unsigned)((n_nod + kWarps - 1) / kWarps);
-#define TFEM_ASM(NNC)                                                                                        \
-  k_assemble<DPN, NNC><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, \
-                                                     ubc, vals, lift, slice_ptr, sell_vals, dinv)
+#define TFEM_ASM(NNC)                                                                                             \
+  if (sell_vals || dinv)                                                                                          \
+    k_assemble_solver<DPN, NNC><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k,  \
+                                                              is_con, ubc, vals, lift, slice_ptr, sell_vals, dinv); \
+  else                                                                                                            \
+    k_assemble<DPN, NNC><<<grid, kWarps * 32, 0, st>>>(n_nod, nn, node_ptr, adj, indptr, src_ptr, src, k, is_con, \
+                                                       ubc, vals, lift)
   switch (nn) {
     case 3: TFEM_ASM(3); break;
     case 4: TFEM_ASM(4); break;

@@ -1032,6 +1032,21 @@ extern "C" int tfem_sell_spmv(const tfem_sell_t* a, const double* x, double* y, 
   return launch_sell<false>(A, x, y, nullptr, nullptr, nullptr, nullptr, st);
 }
 
+extern "C" int tfem_sell_spmm(const tfem_sell_t* a, int64_t m, const double* X, int64_t ldx, double* Y, int64_t ldy,
+                              void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  int rc = check_sell(a);
+  if (rc != TFEM_OK) return rc;
+  TFEM_REQUIRE(X && Y && X != Y, "sell_spmm: null or aliased blocks");
+  TFEM_REQUIRE(m >= 1 && ldx >= m && ldy >= m, "sell_spmm: bad block shape");
+  Sell A = make_sell(a);
+  TFEM_REQUIRE(A.n_long == 0, "sell_spmm: matrices with long rows take one product per vector (tfem_sell_spmv)");
+  if (A.dpn == 3) return launch_spmm_t<3>(A, m, X, ldx, Y, ldy, st);
+  if (A.dpn == 2) return launch_spmm_t<2>(A, m, X, ldx, Y, ldy, st);
+  return launch_spmm_t<0>(A, m, X, ldx, Y, ldy, st);
+}
+
 extern "C" int64_t tfem_krylov_work_doubles(int64_t n_rows) {
   return 6 * pad32(n_rows) + SC_COUNT + kMaxPartials + 32;
 }

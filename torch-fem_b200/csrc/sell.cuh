@@ -287,6 +287,82 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
   }
 }
 
+// Y[:, 0:nb] = A X[:, 0:nb] for row-major blocks of vectors (the eigensolver's K X / M X, reference sparse.py:798-1011 hands
+// blocks to LOBPCG): the matrix is streamed once per MB vectors instead of once per vector, and each gathered row of X
+// is nb contiguous doubles. Per row and column the entries are added in the order of k_sell_spmv: the result equals nb
+// single products bit for bit.
+template <int DPN, int MB>
+__global__ void __launch_bounds__(kSellWarps * 32)
+    k_sell_spmm(Sell A, const double* __restrict__ X, int64_t ldx, double* __restrict__ Y, int64_t ldy, int nb) {
+  constexpr int NPS = Nps<DPN == 0 ? 3 : DPN>::v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double2* v2 = reinterpret_cast<const double2*>(A.vals);
+  for (int64_t t = (int64_t)blockIdx.x * kSellWarps + warp; t < A.n_slices; t += (int64_t)gridDim.x * kSellWarps) {
+    const int64_t row = t * 32 + lane;
+    const int64_t b2 = (A.slice_ptr[t] >> 1) + lane;
+    const int w2 = (int)((A.slice_ptr[t + 1] - A.slice_ptr[t]) >> 6);  // 128-bit steps = entry pairs
+    const int32_t* bc = nullptr;
+    if constexpr (DPN != 0) bc = A.bcols + A.bslice_ptr[t] + (int)(row / DPN - (t * 32) / DPN);
+    double acc[MB];
+#pragma unroll
+    for (int j = 0; j < MB; ++j) acc[j] = 0.0;
+#pragma unroll 2
+    for (int s = 0; s < w2; ++s) {
+      const double2 v = ldg_stream_double2(v2 + b2 + (int64_t)s * 32);
+      int64_t c0, c1;
+      if constexpr (DPN == 0) {
+        const int2 c = __ldg(reinterpret_cast<const int2*>(A.cols) + b2 + (int64_t)s * 32);
+        c0 = c.x;
+        c1 = c.y;
+      } else {
+        const int k0 = 2 * s, k1 = 2 * s + 1;
+        c0 = (int64_t)DPN * __ldg(bc + (k0 / DPN) * NPS) + k0 % DPN;
+        c1 = (int64_t)DPN * __ldg(bc + (k1 / DPN) * NPS) + k1 % DPN;
+      }
+      const double* x0 = X + c0 * ldx;
+      const double* x1 = X + c1 * ldx;
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (j < nb) acc[j] = fma(v.x, __ldg(x0 + j), acc[j]);
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (j < nb) acc[j] = fma(v.y, __ldg(x1 + j), acc[j]);
+    }
+    if (row < A.n) {
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (j < nb) Y[row * ldy + j] = acc[j];
+    }
+  }
+}
+
+// vectors per pass over the matrix: 8 while more than 4 are left, else 4. The caller packs at most 8 columns per call
+// contiguously (ldx = m): with a wider leading dimension the gathered rows of X waste their sectors and the product
+// becomes slower than single products (measured at config B, tools/time_spmm.py).
+template <int DPN, int MB>
+void launch_spmm_pass(const Sell& A, const double* X, int64_t ldx, double* Y, int64_t ldy, int nb, cudaStream_t st) {
+  const int g = cached_resident_ctas(k_sell_spmm<DPN, MB>, kSellWarps * 32);
+  const int64_t want = A.n_slices > 0 ? (A.n_slices + kSellWarps - 1) / kSellWarps : 1;
+  k_sell_spmm<DPN, MB><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, X, ldx, Y, ldy, nb);
+}
+
+template <int DPN>
+int launch_spmm_t(const Sell& A, int64_t m, const double* X, int64_t ldx, double* Y, int64_t ldy, cudaStream_t st) {
+  for (int64_t j0 = 0; j0 < m;) {
+    const int64_t rem = m - j0;
+    if (rem > 4) {
+      const int nb = (int)(rem < 8 ? rem : 8);
+      launch_spmm_pass<DPN, 8>(A, X + j0, ldx, Y + j0, ldy, nb, st);
+      j0 += nb;
+    } else {
+      launch_spmm_pass<DPN, 4>(A, X + j0, ldx, Y + j0, ldy, (int)rem, st);
+      j0 += rem;
+    }
+  }
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
 // The long rows (empty in the slices): one CTA per row straight from the CSR arrays. Every thread sums its strided
 // entries in order, the partial sums are combined in a fixed tree: deterministic. DOT: the row's term x_r y_r is added
 // to *out_scalar (which k_sell_spmv has written) by the CTA that finishes last, in row order.
