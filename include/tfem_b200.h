@@ -257,8 +257,8 @@ int tfem_sell_spmv(const tfem_sell_t* A, const double* x_dev, double* y_dev, voi
 
 /* Y = A X for a block of m vectors stored row-major (X[row * ldx + j], Y[row * ldy + j], j < m; ldx, ldy >= m): what the
  * eigensolver applies to its block (reference sparse.py:798-1011 passes K, M and the preconditioner to LOBPCG as block
- * operators). The matrix is streamed once per 8 vectors (4 for the last <= 4); keep m <= 8 and ldx = m per call: wider
- * leading dimensions waste the sectors of the gathered rows. Column j of Y equals tfem_sell_spmv on column j bit for bit.
+ * operators). The matrix is streamed once per 4 vectors; keep m <= 4 and ldx = m per call (pack the columns): wider
+ * leading dimensions waste the sectors of the gathered rows and are slower than single products. Column j of Y equals tfem_sell_spmv on column j bit for bit.
  * Matrices with long rows (n_long > 0) are refused with TFEM_ERR_INVALID: use tfem_sell_spmv per vector. */
 int tfem_sell_spmm(const tfem_sell_t* A, int64_t m, const double* X_dev, int64_t ldx, double* Y_dev, int64_t ldy,
                    void* stream);

@@ -407,7 +407,7 @@ class CSRMatrix:
 
     def matmat(self, X: Tensor, out: Tensor | None = None) -> Tensor:
         """Y = A X for a block of vectors X [n, m] (row-major) with the multi-vector SELL kernel: the matrix is read once
-        per 8 columns. Each column equals `matvec(X[:, j], fmt="sell")` bit for bit."""
+        per 4 columns. Each column equals `matvec(X[:, j], fmt="sell")` bit for bit."""
         L.require_cuda(X)
         if X.dtype != torch.float64 or X.dim() != 2 or X.shape[0] != self.n:
             raise ValueError("matmat expects a float64 block of shape [n, m]")
@@ -423,16 +423,19 @@ class CSRMatrix:
             for j in range(m):
                 Y[:, j] = self.matvec(X[:, j].contiguous(), fmt="sell")
             return Y
-        if m <= 8:
+        if m == 1:     # the single-vector kernel is faster than a pass with one live column (1.15 vs 1.44 ms at config B)
+            Y[:, 0] = self.matvec(X[:, 0].contiguous(), fmt="sell")
+            return Y
+        if m <= 4:
             L.check(L.lib.tfem_sell_spmm(S.ref, m, L.ptr(X), m, L.ptr(Y), m, L.stream()))
             return Y
-        # wider blocks: 8 columns at a time, packed (a gathered row of X must be one or two full sectors; with the
-        # leading dimension of a wide block the product is slower than single products)
-        for j0 in range(0, m, 8):
-            Xc = X[:, j0:j0 + 8].contiguous()
+        # wider blocks: 4 columns per pass, packed — a gathered row of X must be one full sector; with the leading
+        # dimension of a wide block the product gets slower than single products (tools/time_spmm.py)
+        for j0 in range(0, m, 4):
+            Xc = X[:, j0:j0 + 4].contiguous()
             Yc = torch.empty_like(Xc)
             L.check(L.lib.tfem_sell_spmm(S.ref, Xc.shape[1], L.ptr(Xc), Xc.shape[1], L.ptr(Yc), Xc.shape[1], L.stream()))
-            Y[:, j0:j0 + 8] = Yc
+            Y[:, j0:j0 + 4] = Yc
         return Y
 
     def __matmul__(self, x: Tensor) -> Tensor:

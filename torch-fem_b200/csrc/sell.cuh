@@ -336,28 +336,19 @@ __global__ void __launch_bounds__(kSellWarps * 32)
   }
 }
 
-// vectors per pass over the matrix: 8 while more than 4 are left, else 4. The caller packs at most 8 columns per call
-// contiguously (ldx = m): with a wider leading dimension the gathered rows of X waste their sectors and the product
-// becomes slower than single products (measured at config B, tools/time_spmm.py).
-template <int DPN, int MB>
-void launch_spmm_pass(const Sell& A, const double* X, int64_t ldx, double* Y, int64_t ldy, int nb, cudaStream_t st) {
-  const int g = cached_resident_ctas(k_sell_spmm<DPN, MB>, kSellWarps * 32);
-  const int64_t want = A.n_slices > 0 ? (A.n_slices + kSellWarps - 1) / kSellWarps : 1;
-  k_sell_spmm<DPN, MB><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, X, ldx, Y, ldy, nb);
-}
+// 4 vectors per pass over the matrix, measured at config B (tools/time_spmm.py, profiles/r2_spmm.txt): 2.25 ms per pass
+// against 4 x 1.15 ms of single products. 8 per pass is slower per vector (5.6 ms: the gathers of 64-byte rows of X, not
+// the matrix stream, bound the kernel), and so is any leading dimension wider than the pass (the gathered rows waste their
+// sectors: m = 16 unpacked took 19.5 ms, more than 16 single products) — the caller packs 4 columns per call (ldx = 4).
+constexpr int kSpmmBlock = 4;
 
 template <int DPN>
 int launch_spmm_t(const Sell& A, int64_t m, const double* X, int64_t ldx, double* Y, int64_t ldy, cudaStream_t st) {
-  for (int64_t j0 = 0; j0 < m;) {
-    const int64_t rem = m - j0;
-    if (rem > 4) {
-      const int nb = (int)(rem < 8 ? rem : 8);
-      launch_spmm_pass<DPN, 8>(A, X + j0, ldx, Y + j0, ldy, nb, st);
-      j0 += nb;
-    } else {
-      launch_spmm_pass<DPN, 4>(A, X + j0, ldx, Y + j0, ldy, (int)rem, st);
-      j0 += rem;
-    }
+  const int g = cached_resident_ctas(k_sell_spmm<DPN, kSpmmBlock>, kSellWarps * 32);
+  const int64_t want = A.n_slices > 0 ? (A.n_slices + kSellWarps - 1) / kSellWarps : 1;
+  for (int64_t j0 = 0; j0 < m; j0 += kSpmmBlock) {
+    const int nb = (int)(m - j0 < kSpmmBlock ? m - j0 : kSpmmBlock);
+    k_sell_spmm<DPN, kSpmmBlock><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, X + j0, ldx, Y + j0, ldy, nb);
   }
   TFEM_LAUNCH_CHECK();
   return TFEM_OK;

@@ -41,7 +41,7 @@ def _as_csr(A) -> CSRMatrix:
 
 
 def _spmm(A: CSRMatrix, X: Tensor, mask: Tensor) -> Tensor:
-    """mask * (A @ X) with the multi-vector SELL product (X is [n, m] row-major: the matrix is read once per 8 columns,
+    """mask * (A @ X) with the multi-vector SELL product (X is [n, m] row-major: the matrix is read once per 4 columns,
     not once per column)."""
     return A.matmat(X) * mask[:, None]
 
