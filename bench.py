@@ -479,7 +479,7 @@ def run_ours(args):
                      # `ncu --set full` capture (profiles/r2_x_cg_iteration_ncu.txt); other sizes: not captured
                      "traffic": NCU_SPMV_DRAM_BYTES_CONFIG_B if E == 150 else None,
                      "traffic_source": "profiles/r2_x_cg_iteration_ncu.txt (k_sell_spmv<3,1>: 7.234 GB read + 0.086 GB written per launch, "
-                                       "1.116 ms under ncu; launch list of this command: profiles/r2_x_launches_bench_command.csv)"},
+                                       "1.116 ms under ncu; launch list of this command: profiles/r2_fin_launches_bench_command.csv)"},
         "cpu_baseline": cpu,
         "clocks": clocks,
     }
