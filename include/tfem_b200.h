@@ -521,6 +521,14 @@ int tfem_amg_rho(const tfem_amg_operator_t* A, const double* dinv_dev, int itera
 int tfem_amg_vcycle(const tfem_amg_level_t* levels_host, int n_levels, const double* coarse_inv_dev,
                     const double* r_dev, double* z_dev, void* stream);
 
+/* One V cycle on a block of nb <= 4 vectors stored row-major (r_block[row * nb + j]): the preconditioner step of the
+ * eigensolver (reference sparse.py:798-1011 hands the preconditioner to LOBPCG as a block operator). The residual and
+ * the post-smoothing sweep on the finest level read the matrix once for the block (tfem_sell_spmm with the cycle's
+ * epilogues); restriction, coarse levels and prolongation run per vector. Column j of z_block equals tfem_amg_vcycle on
+ * column j bit for bit. work_dev: 2 * n * nb doubles. */
+int tfem_amg_vcycle_block(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv_dev, int nb,
+                          const double* r_block_dev, double* z_block_dev, double* work_dev, void* stream);
+
 /* CG preconditioned with the V cycle; stopping rule, maxiter and info_host as tfem_krylov_solve (CG). The r.z and p.q
  * dot products are fused into the last smoother / the SpMV. The host polls the convergence flag every iteration (one
  * iteration is a whole cycle). work_dev: double [tfem_amg_work_doubles(n)]. */

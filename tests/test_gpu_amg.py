@@ -71,6 +71,29 @@ def test_hierarchy_matches_oracle_mechanics(T, tables, N, max_coarse, layout, mo
     assert np.array_equal(z, amg.apply(dev(r)).cpu().numpy())      # bitwise reproducible
 
 
+@pytest.mark.parametrize("layout", ["auto", "sell"])
+@pytest.mark.parametrize("N,max_coarse,m", [(7, 150, 3), (11, 300, 4), (11, 300, 9), (4, 10**6, 5)])
+def test_block_vcycle_equals_single_cycles(T, tables, N, max_coarse, m, layout, monkeypatch):
+    """`apply_block` (the eigensolver's preconditioner step: finest-level sweeps on 4 vectors per pass over the matrix) ==
+    one `apply` per column, bit for bit; 2- and 3-level hierarchies, block-CSR and SELL coarse operators, and the
+    single-level (dense) case."""
+    from torchfem_b200 import amg as amg_mod
+    from torchfem_b200.amg import AMGPreconditioner
+
+    if layout == "sell":
+        monkeypatch.setattr(amg_mod, "BCSR_MAX_ROWS", 0)
+        monkeypatch.setattr(amg_mod, "BCSR_MIN_AVG", 10**9)
+    nodes, elements, bref, w, C, con_mask, disp, p, k, A = _cube_system(T, N, tables)
+    A = p.matrix(A.values_)
+    amg = AMGPreconditioner(A, max_coarse=max_coarse)
+    assert (amg.n_levels == 1) == (max_coarse == 10**6)
+    R = dev(np.random.default_rng(m).standard_normal((p.n_dofs, m)))
+    Z = amg.apply_block(R)
+    assert Z.shape == R.shape
+    for j in range(m):
+        assert torch.equal(Z[:, j], amg.apply(R[:, j].contiguous()))
+
+
 def _spd_on_pattern(c, n, seed=3):
     """A symmetric, strictly diagonally dominant matrix (SPD) with random entries on the pattern of a fixture
     (the fixtures' own K are unconstrained / geometrically nonlinear tangents, not all positive definite)."""

@@ -144,6 +144,7 @@ _SIGNATURES = {
     "tfem_amg_spgemm_fill": (c_int, [c_int64] + [c_void_p] * 7),
     "tfem_amg_spgemm_numeric": (c_int, [c_int, c_int64] + [c_void_p] * 9 + [c_int, c_int, c_void_p]),
     "tfem_amg_vcycle": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tfem_amg_vcycle_block": (c_int, [_AMG_P, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfem_amg_pcg_solve": (c_int, [_AMG_P, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
     "tfem_adjoint_matrix_grad": (c_int, [c_int64] + [c_void_p] * 6),

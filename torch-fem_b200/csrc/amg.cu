@@ -1039,6 +1039,79 @@ int vcycle(const Level* L, int n_levels, const double* coarse_inv, const double*
   return TFEM_OK;
 }
 
+// ---- V cycle on a block of nb <= 4 vectors stored row-major [n, nb] (the eigensolver's preconditioner step): the two
+// products with the finest operator — more than half of a cycle — read the matrix once for the block
+// (k_sell_spmm<., 4, MODE>); restriction, the coarse levels and prolongation run per vector on the levels' work vectors.
+// Every expression and summation order is the one of vcycle(): each column equals the single-vector cycle bit for bit.
+__global__ void __launch_bounds__(kVecThreads)
+    k_jacobi_first_block(int64_t n, int nb, double omega, const double* __restrict__ dinv, const double* __restrict__ B,
+                         double* __restrict__ X) {
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n * nb; i += (int64_t)gridDim.x * kVecThreads)
+    X[i] = omega * dinv[i / nb] * B[i];
+}
+
+__global__ void __launch_bounds__(kVecThreads)
+    k_block_column(int64_t n, int nb, int j, double* __restrict__ block, double* __restrict__ vec, int to_block) {
+  for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+    if (to_block) block[i * nb + j] = vec[i];
+    else vec[i] = block[i * nb + j];
+  }
+}
+
+template <int DPN, int MODE>
+void launch_spmm_mode(const Sell& A, const double* X, double* Y, int nb, const double* B, const double* dinv, double omega,
+                      cudaStream_t st) {
+  const int g = cached_resident_ctas(k_sell_spmm<DPN, kSpmmBlock, MODE>, kSellWarps * 32);
+  const int64_t want = A.n_slices > 0 ? (A.n_slices + kSellWarps - 1) / kSellWarps : 1;
+  k_sell_spmm<DPN, kSpmmBlock, MODE><<<(int)(want < g ? want : g), kSellWarps * 32, 0, st>>>(A, X, nb, Y, nb, nb, B, dinv,
+                                                                                            omega);
+}
+
+template <int MODE>
+void spmm_mode(const Sell& A, const double* X, double* Y, int nb, const double* B, const double* dinv, double omega,
+               cudaStream_t st) {
+  if (A.dpn == 3) launch_spmm_mode<3, MODE>(A, X, Y, nb, B, dinv, omega, st);
+  else if (A.dpn == 2) launch_spmm_mode<2, MODE>(A, X, Y, nb, B, dinv, omega, st);
+  else launch_spmm_mode<0, MODE>(A, X, Y, nb, B, dinv, omega, st);
+}
+
+int vcycle_block(const Level* L, int n_levels, const double* coarse_inv, int nb, const double* Rb, double* Zb,
+                 double* work, cudaStream_t st) {
+  const Level& v = L[0];
+  int64_t launches = 0;
+  int rc;
+  const bool batched = n_levels >= 2 && !v.A.bcsr && v.A.sell.n_long == 0 && v.A.sell.slice_lo == 0 &&
+                       v.A.sell.slice_hi < 0;
+  if (!batched) {  // a single level (dense) or a block-CSR finest operator: cycle by cycle through the work vectors
+    for (int j = 0; j < nb; ++j) {
+      double* rj = work;
+      double* zj = work + v.n;
+      k_block_column<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, nb, j, const_cast<double*>(Rb), rj, 0);
+      if ((rc = vcycle(L, n_levels, coarse_inv, rj, zj, nullptr, nullptr, nullptr, &launches, st))) return rc;
+      k_block_column<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, nb, j, Zb, zj, 1);
+    }
+    TFEM_LAUNCH_CHECK();
+    return TFEM_OK;
+  }
+  double* X0 = work;                    // [n, nb]
+  double* T0 = work + v.n * (int64_t)nb;  // [n, nb]
+  k_jacobi_first_block<<<vec_grid(v.n * nb), kVecThreads, 0, st>>>(v.n, nb, v.omega, v.dinv, Rb, X0);
+  spmm_mode<M_RES>(v.A.sell, X0, T0, nb, Rb, nullptr, 0.0, st);
+  for (int j = 0; j < nb; ++j) {
+    k_block_column<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, nb, j, T0, v.t, 0);
+    if ((rc = apply_oper<M_AX>(v.R, v.t, L[1].b, nullptr, nullptr, 0.0, st))) return rc;
+    // levels 1.. as a cycle of their own: right-hand side L[1].b, result in L[1].t
+    if ((rc = vcycle(L + 1, n_levels - 1, coarse_inv, L[1].b, L[1].t, nullptr, nullptr, nullptr, &launches, st)))
+      return rc;
+    k_block_column<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, nb, j, X0, v.x, 0);
+    if ((rc = apply_oper<M_ADD>(v.P, L[1].t, v.x, nullptr, nullptr, 0.0, st))) return rc;
+    k_block_column<<<vec_grid(v.n), kVecThreads, 0, st>>>(v.n, nb, j, X0, v.x, 1);
+  }
+  spmm_mode<M_JAC>(v.A.sell, X0, Zb, nb, Rb, v.dinv, v.omega, st);
+  TFEM_LAUNCH_CHECK();
+  return TFEM_OK;
+}
+
 int scan_in_place(int64_t* ptr, int64_t n, cudaStream_t st) {  // ptr[0] = 0, ptr[1..n] counts -> inclusive sums
   TFEM_CUDA(cudaMemsetAsync(ptr, 0, sizeof(int64_t), st));
   size_t bytes = 0;
@@ -1444,6 +1517,20 @@ extern "C" int tfem_amg_vcycle(const tfem_amg_level_t* levels, int n_levels, con
   if (rc != TFEM_OK) return rc;
   int64_t launches = 0;
   return vcycle(L, n_levels, coarse_inv, r, z, nullptr, nullptr, nullptr, &launches, st);
+}
+
+extern "C" int tfem_amg_vcycle_block(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv, int nb,
+                                     const double* r_block, double* z_block, double* work, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  (void)cudaGetLastError();  // a stale non-sticky error of another library (NCCL pointer queries) is not ours
+  TFEM_REQUIRE(levels && n_levels >= 1 && n_levels <= TFEM_AMG_MAX_LEVELS && coarse_inv && r_block && z_block && work &&
+                   r_block != z_block,
+               "amg_vcycle_block: bad arguments");
+  TFEM_REQUIRE(nb >= 1 && nb <= kSpmmBlock, "amg_vcycle_block: 1 to 4 vectors per call");
+  Level L[TFEM_AMG_MAX_LEVELS];
+  int rc = make_levels(levels, n_levels, L);
+  if (rc != TFEM_OK) return rc;
+  return vcycle_block(L, n_levels, coarse_inv, nb, r_block, z_block, work, st);
 }
 
 extern "C" int tfem_amg_pcg_solve(const tfem_amg_level_t* levels, int n_levels, const double* coarse_inv,

@@ -291,9 +291,12 @@ __global__ void __launch_bounds__(kSellWarps * 32, 8)
 // blocks to LOBPCG): the matrix is streamed once per MB vectors instead of once per vector, and each gathered row of X
 // is nb contiguous doubles. Per row and column the entries are added in the order of k_sell_spmv: the result equals nb
 // single products bit for bit.
-template <int DPN, int MB>
+// MODE 0: Y = A X;  1: Y = B - A X;  2: Y = X + omega dinv (B - A X)  (the residual and the damped-Jacobi sweep of the V cycle
+// on a block of vectors, same expressions as k_amg_spmv). B and Y share the layout of X.
+template <int DPN, int MB, int MODE = 0>
 __global__ void __launch_bounds__(kSellWarps * 32)
-    k_sell_spmm(Sell A, const double* __restrict__ X, int64_t ldx, double* __restrict__ Y, int64_t ldy, int nb) {
+    k_sell_spmm(Sell A, const double* __restrict__ X, int64_t ldx, double* __restrict__ Y, int64_t ldy, int nb,
+                const double* __restrict__ B = nullptr, const double* __restrict__ dinv = nullptr, double omega = 0.0) {
   constexpr int NPS = Nps<DPN == 0 ? 3 : DPN>::v;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double2* v2 = reinterpret_cast<const double2*>(A.vals);
@@ -303,6 +306,17 @@ __global__ void __launch_bounds__(kSellWarps * 32)
     const int w2 = (int)((A.slice_ptr[t + 1] - A.slice_ptr[t]) >> 6);  // 128-bit steps = entry pairs
     const int32_t* bc = nullptr;
     if constexpr (DPN != 0) bc = A.bcols + A.bslice_ptr[t] + (int)(row / DPN - (t * 32) / DPN);
+    // the epilogue operands are requested before the row is streamed (one exposed latency per slice otherwise)
+    double br[MB], xr[MB], dr = 0.0;
+    if (MODE != 0 && row < A.n) {
+      if (MODE == 2) dr = omega * __ldg(dinv + row);
+#pragma unroll
+      for (int j = 0; j < MB; ++j)
+        if (j < nb) {
+          br[j] = __ldg(B + row * ldx + j);
+          if (MODE == 2) xr[j] = __ldg(X + row * ldx + j);
+        }
+    }
     double acc[MB];
 #pragma unroll
     for (int j = 0; j < MB; ++j) acc[j] = 0.0;
@@ -331,7 +345,12 @@ __global__ void __launch_bounds__(kSellWarps * 32)
     if (row < A.n) {
 #pragma unroll
       for (int j = 0; j < MB; ++j)
-        if (j < nb) Y[row * ldy + j] = acc[j];
+        if (j < nb) {
+          double out = acc[j];
+          if (MODE == 1) out = br[j] - acc[j];
+          if (MODE == 2) out = fma(dr, br[j] - acc[j], xr[j]);
+          Y[row * ldy + j] = out;
+        }
     }
   }
 }

@@ -8,7 +8,8 @@ scale anyway. Here:
 
   * small systems (free DOFs <= DENSE_LIMIT) — dense generalized `eigh` on the GPU, the same policy as
     `method="spsolve"` (a library call on a tiny problem);
-  * everything else — LOBPCG (Knyazev 2001) on a block of vectors, preconditioned with one AMG V cycle per vector
+  * everything else — LOBPCG (Knyazev 2001) on a block of vectors, preconditioned with one AMG V cycle per vector (4 vectors per pass over
+    the finest matrix)
     (kernels K11-K16, `amg.AMGPreconditioner`), products with K and M through the SELL-32 SpMV kernels. The basis
     [X, W, P] is kept M-orthonormal block by block (Cholesky), the small Rayleigh-Ritz problems are dense `eigh` calls.
 
@@ -146,10 +147,7 @@ def modal_eigsolve(K, M, n_modes: int, free_indices: Tensor, tol: float = LOBPCG
     amg = AMGPreconditioner(Kc)
 
     def precondition(R: Tensor) -> Tensor:
-        Z = torch.empty_like(R)
-        for j in range(R.shape[1]):
-            Z[:, j] = amg.apply(R[:, j].contiguous())
-        return Z
+        return amg.apply_block(R)
 
     lam, X, _ = lobpcg(Kc, Mc, mask, n_modes, precondition, tol=tol)
     return lam, X
