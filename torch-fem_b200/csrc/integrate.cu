@@ -16,6 +16,13 @@
 // weights come in as a __grid_constant__ kernel parameter, so the call is re-entrant across streams). The
 // finished element matrix is staged in shared memory and written with fully coalesced stores: HBM traffic is
 // the 8*(nn*dpn)^2 B/element output plus ~1 kB/element of inputs.
+//
+// Two kernels: k_integrate (above; tangents that differ per Gauss point: hyperelasticity, plasticity) and
+// k_integrate_elastic (one tensor per element: linear elasticity, heat, topology optimisation — the benchmark's case),
+// which sums over the Gauss points FIRST (a 3 x 3 geometric block per node pair) and contracts the tangent once:
+// 10.6 kFMA per Hexa1 element, geometry in registers, k written from registers in whole sectors, global loads one
+// element ahead. 15.1 -> 5.1 ms at BASELINE configs[1] (profiles/r2_k1_elastic.txt). TFEM_K1_ELASTIC=0 forces the
+// general kernel.
 #include <stdlib.h>
 
 #include "common.cuh"
