@@ -176,6 +176,24 @@ def test_assemble_writes_solver_order(T, tag):
     del want_sell
 
 
+def test_assemble_solver_order_argument_errors(T):
+    c = load_case("case_hexa1.npz")
+    p = build_pattern(T, c, 3)
+    k = dev(c["k"])
+    with pytest.raises(ValueError, match="nothing to write"):
+        T.csr.assemble(p, k, None, csr=False)
+    with pytest.raises(ValueError, match="sell_out must be a contiguous float64 tensor"):
+        T.csr.assemble(p, k, None, sell_out=torch.empty(8, dtype=torch.float64, device="cuda"))
+    with pytest.raises(ValueError, match="needs is_con and ubc"):
+        T.csr.assemble(p, k, None, lift=torch.empty(p.n_dofs, dtype=torch.float64, device="cuda"), sell_out=True)
+    # the C entry point itself refuses a call without any output
+    L = T._lib
+    rc = L.lib.tfem_assemble_solve(p.n_nod, p.nn, p.dpn, L.ptr(p.node_ptr), L.ptr(p.adj), L.ptr(p.indptr),
+                                   L.ptr(p.src_ptr), L.ptr(p.src), L.ptr(k), None, None, None, None, None, None, None,
+                                   L.stream())
+    assert rc == L.ERR_INVALID
+
+
 @pytest.mark.parametrize("tag", ["hexa1", "tetra2", "quad2", "heat_hexa1", "hexa1_orphan"])
 def test_assemble_rhs_deterministic_gather(T, tag):
     """a9 `assemble_rhs` (reference base.py:428-445) on the gather kernel: equals the oracle's index_add to round-off,
