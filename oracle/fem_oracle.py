@@ -162,6 +162,29 @@ def to_csr(val, glob_idx, n_dofs):
 # Jacobi-preconditioned Krylov solvers (reference call sites src/torchfem/sparse.py:406-421 GPU,
 # :493-512 CPU; algorithm = scipy.sparse.linalg.cg / minres, scipy/sparse/linalg/_isolve)
 # --------------------------------------------------------------------------------------------------
+def sell32_values(indptr: np.ndarray, vals: np.ndarray):
+    """The solver-internal SELL-32 layout of CSR values (no reference counterpart: the reference hands CSR to cusparse,
+    sparse.py:411; this restates `torch-fem_b200/csrc/sell.cuh` so that the layout written by the assembly kernel and by
+    the CSR -> SELL copy is pinned by something that is not one of them). Slice t = rows 32 t .. 32 t + 31, width W_t =
+    the longest row of the slice rounded up to even; entry k of the row with lane l sits at
+    slice_ptr[t] + (k // 2) * 64 + 2 l + (k % 2); everything else is 0.0. Returns (slice_ptr, values)."""
+    n = len(indptr) - 1
+    lens = np.diff(indptr)
+    n_slices = (n + 31) // 32
+    padded = np.zeros(n_slices * 32, dtype=np.int64)
+    padded[:n] = lens
+    width = padded.reshape(n_slices, 32).max(axis=1)
+    width = (width + 1) & ~1
+    slice_ptr = np.zeros(n_slices + 1, dtype=np.int64)
+    np.cumsum(width * 32, out=slice_ptr[1:])
+    out = np.zeros(int(slice_ptr[-1]), dtype=np.float64)
+    rows = np.repeat(np.arange(n), lens)
+    k = np.arange(len(vals)) - np.repeat(indptr[:-1], lens)
+    pos = slice_ptr[rows // 32] + (k // 2) * 64 + 2 * (rows % 32) + (k % 2)
+    out[pos] = vals
+    return slice_ptr, out
+
+
 def jacobi_cg(A, b, rtol=1e-10, atol=0.0, x0=None, maxiter=None, dinv=None):
     """scipy `cg` restated (scipy/sparse/linalg/_isolve/iterative.py `cg`): stop when
     ||r|| < max(atol, rtol*||b||), tested at the top of every iteration; maxiter = 10 n;

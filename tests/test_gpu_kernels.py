@@ -153,6 +153,12 @@ def test_assemble_writes_solver_order(T, tag):
     want = A._sell_vals.cpu().numpy()
     want_dinv = T.csr.JacobiPreconditioner(A).dinv.cpu().numpy()
     st = p.sell_structure
+    # both are pinned by the numpy restatement of the layout (oracle/fem_oracle.py::sell32_values)
+    sp_ref, sell_ref = O.sell32_values(p.indptr.cpu().numpy(), vals.cpu().numpy())
+    assert np.array_equal(st.slice_ptr.cpu().numpy(), sp_ref) and st.padded == len(sell_ref)
+    assert np.array_equal(want[: st.padded], sell_ref)
+    with np.errstate(divide="ignore"):     # an unreferenced, unconstrained node has a zero diagonal (base.py:419)
+        assert np.array_equal(want_dinv, 1.0 / vals.cpu().numpy()[c["diag_map"]])
     for csr_too in (True, False):
         sv = torch.full((max(st.padded, 2),), np.nan, dtype=torch.float64, device="cuda")
         dinv = torch.full((n_dofs,), np.nan, dtype=torch.float64, device="cuda")

@@ -137,3 +137,21 @@ def test_krylov_restatements_match_scipy():
         xo, info_o, its = O.jacobi_minres(A, b, rtol=rtol)
         assert info == 0 and info_o == 0 and its == cnt[0]
         assert np.abs(xs - xo).max() <= 1e-11 * np.abs(xs).max()
+
+
+def test_sell32_layout_restatement_small_case():
+    """Hand-checked case of the SELL-32 restatement: 34 rows (two slices), ragged lengths, an empty row."""
+    lens = np.array([3, 0, 5] + [1] * 29 + [2, 4])
+    indptr = np.concatenate([[0], np.cumsum(lens)])
+    vals = np.arange(1, indptr[-1] + 1, dtype=np.float64)
+    slice_ptr, sv = O.sell32_values(indptr, vals)
+    assert slice_ptr.tolist() == [0, 6 * 32, 6 * 32 + 4 * 32]          # widths 5 -> 6 and 4
+    assert sv[0] == 1.0 and sv[1] == 2.0 and sv[64] == 3.0 and sv[65] == 0.0      # row 0: entries 0, 1 | 2, pad
+    assert sv[2] == 0.0 and sv[3] == 0.0                                           # row 1 is empty
+    assert sv[4] == 4.0 and sv[5] == 5.0 and sv[68] == 6.0 and sv[69] == 7.0 and sv[132] == 8.0 and sv[133] == 0.0
+    base = slice_ptr[1]
+    r32 = vals[indptr[32]:indptr[33]]
+    assert sv[base] == r32[0] and sv[base + 1] == r32[1] and sv[base + 64] == 0.0
+    r33 = vals[indptr[33]:indptr[34]]
+    assert [sv[base + 2], sv[base + 3], sv[base + 66], sv[base + 67]] == r33.tolist()
+    assert np.count_nonzero(sv) == len(vals)
