@@ -185,6 +185,20 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def element_tables(etype):
+    """(bref [n_q, dim, nn], w [n_q]) of an element type of the product package, on the host in float64: what
+    `csr.integrate_k` takes (the timing tools under tools/ use this too; nothing on the `ours` arm comes from oracle/)."""
+    import torch
+
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)   # the Gauss points are created in the default dtype, like the reference's
+    try:
+        ip = etype.ipoints.to(torch.float64).cpu()
+        return etype.B(ip), etype.iweights.to(torch.float64).cpu()
+    finally:
+        torch.set_default_dtype(prev)
+
+
 def build_problem(T, torch, E, device):
     """Synthetic inputs exactly as the reference generators make them (mesh.py:8-46, cubes.py:9-24),
     built with torch on the host, then moved to the device."""
@@ -239,8 +253,7 @@ def run_ours(args):
     from torchfem_b200.materials import IsotropicElasticity3D
 
     # reference-element tables of the PRODUCT package (elements.py; pinned to the reference in tests/test_elements.py)
-    ip = Hexa1.ipoints.to(torch.float64).cpu()
-    bref, w = Hexa1.B(ip), Hexa1.iweights.to(torch.float64).cpu()
+    bref, w = element_tables(Hexa1)
 
     # per-element material parameters (heterogeneous materials are the general case, cf. benchmarks/topopt.py);
     # the [n_elem,3,3,3,3] tangent is built from them ON THE DEVICE, as the reference's vectorised material does

@@ -32,13 +32,14 @@ def main():
     import torchfem_b200 as T
     from torchfem_b200 import csr
     from torchfem_b200.amg import AMGPreconditioner
-    from oracle import fem_oracle as O
+    from torchfem_b200.elements import Hexa1
+    from torchfem_b200.materials import IsotropicElasticity3D
 
     dev = torch.device("cuda", 0)
     for E in a.edge:
         nodes, elements, con, disp = bench.build_problem(T, torch, E, dev)
-        bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
-        C = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous().to(dev)
+        bref, w = bench.element_tables(Hexa1)
+        C = IsotropicElasticity3D(torch.full((len(elements),), 1000.0, device=dev), torch.full((len(elements),), 0.3, device=dev)).C
         nodes, elements = nodes.to(dev), elements.to(dev)
         is_con = con.ravel().to(torch.uint8).to(dev)
         ubc = (disp.ravel() * con.ravel()).to(dev)

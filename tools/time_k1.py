@@ -10,13 +10,14 @@ import bench  # noqa: E402
 torch.set_default_dtype(torch.float64)
 import torchfem_b200 as T  # noqa: E402
 from torchfem_b200 import csr  # noqa: E402
-from oracle import fem_oracle as O  # noqa: E402
+from torchfem_b200.elements import Hexa1  # noqa: E402
+from torchfem_b200.materials import IsotropicElasticity3D  # noqa: E402
 
 dev = torch.device("cuda", 0)
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 150
 nodes, elements, con, disp = bench.build_problem(T, torch, E, dev)
-bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
-C = torch.as_tensor(O.isotropic_C3d(1000.0, 0.3, 1)).expand(len(elements), 3, 3, 3, 3).contiguous().to(dev)
+bref, w = bench.element_tables(Hexa1)
+C = IsotropicElasticity3D(torch.full((len(elements),), 1000.0, device=dev), torch.full((len(elements),), 0.3, device=dev)).C
 nodes, elements = nodes.to(dev), elements.to(dev)
 is_con = con.ravel().to(torch.uint8).to(dev)
 p = csr.Pattern(elements, nodes.shape[0], 3)

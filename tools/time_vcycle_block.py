@@ -20,12 +20,8 @@ nodes, elements, con, disp = bench.build_problem(T, torch, E, dev)
 nodes, elements = nodes.to(dev), elements.to(dev)
 is_con = con.ravel().to(torch.uint8).to(dev)
 p = csr.Pattern(elements, nodes.shape[0], 3)
-et = Hexa1()
-bref, w = bench.element_tables(et) if hasattr(bench, "element_tables") else (None, None)
+bref, w = bench.element_tables(Hexa1)
 C = IsotropicElasticity3D(torch.full((len(elements),), 1000.0, device=dev), torch.full((len(elements),), 0.3, device=dev)).C
-if bref is None:
-    from oracle import fem_oracle as O
-    bref, w = (torch.as_tensor(t) for t in O.hexa1_tables())
 k = csr.integrate_k(T._lib.KIND_MECH, bref, w, nodes, elements, C, check=False)
 A = p.matrix(csr.assemble(p, k, is_con))
 del k, C
